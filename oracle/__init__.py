@@ -1,0 +1,241 @@
+"""ctypes view of the CPU oracle (oracle/oracle.cpp).
+
+TEST INFRASTRUCTURE ONLY.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs may import this module; the product (easy-ml_b200/) never does.
+Parity pinned against the reference's golden vectors (tests/golden/); see oracle/oracle.h.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "liboracle.so")
+
+ORC_OK, ORC_ERR_PANIC, ORC_ERR_INCONSISTENT = 0, -1, -2
+
+
+class ReferencePanic(Exception):
+    """The reference would `panic!` here; str(e) is the reference's message."""
+
+
+class InconsistentDimensionLengthError(Exception):
+    """Einsum `Err(InconsistentDimensionLengthError { lengths, dimension })` (einsum.rs:321)."""
+
+    def __init__(self, dimension, lengths):
+        super().__init__(f"InconsistentDimensionLengthError(dimension={dimension!r}, lengths={lengths})")
+        self.dimension, self.lengths = dimension, lengths
+
+
+def build(force=False):
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(
+        os.path.getmtime(os.path.join(_HERE, f)) for f in ("oracle.cpp", "oracle.h")
+    ):
+        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build()
+        _lib = C.CDLL(_LIB_PATH)
+        _lib.orc_last_error.restype = C.c_char_p
+        _lib.orc_scalar_product_f32.restype = C.c_float
+        _lib.orc_scalar_product_f64.restype = C.c_double
+        _lib.orc_tape_new.restype = C.c_void_p
+        for f in ("orc_tape_len", "orc_tape_append_nullary", "orc_tape_append_nullary_repeating",
+                  "orc_tape_append_unary", "orc_tape_append_binary"):
+            getattr(_lib, f).restype = C.c_int64
+    return _lib
+
+
+def _sfx(dtype):
+    dtype = np.dtype(dtype)
+    if dtype == np.float32:
+        return "f32", C.c_float
+    if dtype == np.float64:
+        return "f64", C.c_double
+    raise TypeError(f"oracle handles f32/f64 only, got {dtype}")
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _names(names):
+    arr = (C.c_char_p * max(len(names), 1))(*[n.encode() for n in names])
+    return arr
+
+
+def _i64(v):
+    return (C.c_int64 * max(len(v), 1))(*v)
+
+
+def _check(rc):
+    if rc == ORC_ERR_PANIC:
+        raise ReferencePanic(lib().orc_last_error().decode())
+    if rc != ORC_OK:
+        raise RuntimeError(f"oracle rc={rc}")
+
+
+def scalar_product(l, r):
+    """A1 on two 1-D arrays (any stride)."""
+    s, _ = _sfx(l.dtype)
+    assert l.dtype == r.dtype and l.ndim == r.ndim == 1 and len(l) == len(r) and len(l) > 0
+    isz = l.dtype.itemsize
+    f = getattr(lib(), f"orc_scalar_product_{s}")
+    return f(_p(l), C.c_int64(l.strides[0] // isz), _p(r), C.c_int64(r.strides[0] // isz), C.c_int64(len(l)))
+
+
+def matrix_mul(a, b, rows=None, threads=1):
+    """A2: Matrix * Matrix.  rows=(r0, r1) computes only that slab of C (others left zero)."""
+    s, _ = _sfx(a.dtype)
+    a = np.ascontiguousarray(a)
+    b = np.ascontiguousarray(b)
+    c = np.zeros((a.shape[0], b.shape[1]), dtype=a.dtype)
+    r0, r1 = rows if rows is not None else (0, a.shape[0])
+    rc = getattr(lib(), f"orc_matrix_mul_{s}")(
+        _p(a), C.c_int64(a.shape[0]), C.c_int64(a.shape[1]), _p(b), C.c_int64(b.shape[0]), C.c_int64(b.shape[1]),
+        _p(c), C.c_int64(r0), C.c_int64(r1), C.c_int(threads))
+    _check(rc)
+    return c
+
+
+def tensor_mul(a, a_names, b, b_names):
+    """A3: rank-2 Tensor * Tensor.  Returns (c, out_names)."""
+    s, _ = _sfx(a.dtype)
+    a = np.ascontiguousarray(a)
+    b = np.ascontiguousarray(b)
+    c = np.zeros((a.shape[0], b.shape[1] if a.shape[1] == b.shape[0] else 0), dtype=a.dtype)
+    on = (C.c_char_p * 2)()
+    rc = getattr(lib(), f"orc_tensor_mul_{s}")(
+        _p(a), _names(a_names), _i64(a.shape), _p(b), _names(b_names), _i64(b.shape), _p(c), on)
+    _check(rc)
+    return c, [on[0].decode(), on[1].decode()]
+
+
+def einsum2(a, a_names, b, b_names, out_names):
+    """A4: Einsum::with_2(a, b).named(a_names, b_names).to(out_names).  Returns the output array."""
+    s, _ = _sfx(a.dtype)
+    a = np.ascontiguousarray(a)
+    b = np.ascontiguousarray(b)
+    f = getattr(lib(), f"orc_einsum2_{s}")
+    ol = (C.c_int64 * max(len(out_names), 1))()
+    ed = C.c_char_p()
+    el = (C.c_int64 * 2)(-1, -1)
+    args = (_p(a), C.c_int(a.ndim), _names(a_names), _i64(a.shape), _p(b), C.c_int(b.ndim), _names(b_names),
+            _i64(b.shape), C.c_int(len(out_names)), _names(out_names), ol)
+    rc = f(*args, None, C.byref(ed), el)
+    if rc == ORC_ERR_INCONSISTENT:
+        raise InconsistentDimensionLengthError(ed.value.decode(), [None if x < 0 else int(x) for x in el])
+    _check(rc)
+    out = np.zeros([ol[i] for i in range(len(out_names))], dtype=a.dtype)
+    rc = f(*args, _p(out), C.byref(ed), el)
+    _check(rc)
+    return out
+
+
+def vector_dot(a, a_name, b, b_name):
+    s, ct = _sfx(a.dtype)
+    out = ct()
+    rc = getattr(lib(), f"orc_vector_dot_{s}")(_p(np.ascontiguousarray(a)), a_name.encode(), C.c_int64(len(a)),
+                                             _p(np.ascontiguousarray(b)), b_name.encode(), C.c_int64(len(b)),
+                                             C.byref(out))
+    _check(rc)
+    return out.value
+
+
+class Tape:
+    """The literal scalar WengertList (src/differentiation.rs:327-352)."""
+
+    def __init__(self, dtype):
+        self.dtype = np.dtype(dtype)
+        self.sfx, _ = _sfx(dtype)
+        self._h = C.c_void_p(lib().orc_tape_new(self.dtype.itemsize))
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.orc_tape_free(self._h)
+            self._h = None
+
+    def __len__(self):
+        return lib().orc_tape_len(self._h)
+
+    def clear(self):
+        lib().orc_tape_clear(self._h)
+
+    def entry(self, i):
+        lp, rp, ld, rd = C.c_int64(), C.c_int64(), C.c_double(), C.c_double()
+        lib().orc_tape_get(self._h, C.c_int64(i), C.byref(lp), C.byref(rp), C.byref(ld), C.byref(rd))
+        return lp.value, rp.value, ld.value, rd.value
+
+    def derivatives(self, index):
+        """Record::try_derivatives: full derivative vector (length = tape length)."""
+        out = np.zeros(len(self), dtype=self.dtype)
+        lib().orc_tape_derivatives(self._h, C.c_int64(index), _p(out))
+        return out
+
+    # -- containers as (numbers, indexes) pairs --
+    def variables(self, x):
+        """RecordTensor::variables (container_record/mod.rs:149-164)."""
+        x = np.ascontiguousarray(x, dtype=self.dtype)
+        start = lib().orc_tape_append_nullary_repeating(self._h, C.c_int64(x.size))
+        return x.copy(), (start + np.arange(x.size, dtype=np.int64)).reshape(x.shape)
+
+    @staticmethod
+    def constants(x, dtype=None):
+        """RecordTensor::constants (mod.rs:115-128): index 0 everywhere, no history."""
+        x = np.ascontiguousarray(x, dtype=dtype)
+        return x.copy(), np.zeros(x.shape, dtype=np.int64)
+
+    def matmul(self, a, b, tracked=True):
+        """record_tensor_matrix_multiply / record_matrix_matrix_multiply."""
+        (an, ai), (bn, bi) = a, b
+        m, k = an.shape
+        n = bn.shape[1]
+        c = np.zeros((m, n), dtype=self.dtype)
+        ci = np.zeros((m, n), dtype=np.int64)
+        getattr(lib(), f"orc_record_matmul_{self.sfx}")(
+            self._h if tracked else None, _p(np.ascontiguousarray(an)), _p(np.ascontiguousarray(ai)),
+            _p(np.ascontiguousarray(bn)), _p(np.ascontiguousarray(bi)), C.c_int64(m), C.c_int64(k), C.c_int64(n),
+            _p(c), _p(ci))
+        return c, ci
+
+    def scalar_record_matmul(self, a, b, a_tracked=True, b_tracked=True):
+        (an, ai), (bn, bi) = a, b
+        m, k = an.shape
+        n = bn.shape[1]
+        c = np.zeros((m, n), dtype=self.dtype)
+        ci = np.zeros((m, n), dtype=np.int64)
+        getattr(lib(), f"orc_scalar_record_matmul_{self.sfx}")(
+            self._h, _p(np.ascontiguousarray(an)), _p(np.ascontiguousarray(ai)), C.c_int(a_tracked),
+            _p(np.ascontiguousarray(bn)), _p(np.ascontiguousarray(bi)), C.c_int(b_tracked), C.c_int64(m),
+            C.c_int64(k), C.c_int64(n), _p(c), _p(ci))
+        return c, ci
+
+    def unary(self, op, x, scalar=0.0, tracked=True):
+        xn, xi = x
+        y = np.zeros(xn.shape, dtype=self.dtype)
+        yi = np.zeros(xn.shape, dtype=np.int64)
+        ct = C.c_float if self.sfx == "f32" else C.c_double
+        getattr(lib(), f"orc_record_unary_{self.sfx}")(
+            self._h if tracked else None, C.c_int(op), ct(scalar), _p(np.ascontiguousarray(xn)),
+            _p(np.ascontiguousarray(xi)), C.c_int64(xn.size), _p(y), _p(yi))
+        return y, yi
+
+    def binary(self, op, x, y, mode=3):
+        xn, xi = x
+        yn, yi = y
+        z = np.zeros(xn.shape, dtype=self.dtype)
+        zi = np.zeros(xn.shape, dtype=np.int64)
+        getattr(lib(), f"orc_record_binary_{self.sfx}")(
+            self._h if mode else None, C.c_int(op), C.c_int(mode), _p(np.ascontiguousarray(xn)),
+            _p(np.ascontiguousarray(xi)), _p(np.ascontiguousarray(yn)), _p(np.ascontiguousarray(yi)),
+            C.c_int64(xn.size), _p(z), _p(zi))
+        return z, zi

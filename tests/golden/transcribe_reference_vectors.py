@@ -1,0 +1,151 @@
+#!/usr/bin/env python
+"""Writes tests/golden/reference_vectors.json.
+
+The reference (Skeletonxf/easy-ml) is Rust and cannot be built or imported in this image, so the golden
+vectors are the literal inputs/outputs of the reference's OWN tests for the hot path, transcribed here
+with the file:line they come from (paths relative to /root/reference).  Nothing is computed: every
+"expect" below is a literal that appears in the reference's test source (integer arithmetic written out
+in the source, e.g. `1 * 10 + 2 * 12 + 3 * 14`, is evaluated).  Run: python tests/golden/transcribe_reference_vectors.py
+"""
+import json
+import os
+
+
+def randomish(shape):  # tests/einsum.rs:9-11  Tensor::from_fn(shape, |[x, y]| (x + (10 * y)) as f32)
+    return [[float(x + 10 * y) for y in range(shape[1])] for x in range(shape[0])]
+
+
+V = {"matmul": [], "matmul_panic": [], "tensor_matmul": [], "tensor_matmul_panic": [], "einsum2": [],
+     "einsum2_equiv": [], "record_matmul": [], "xor_nn": {}}
+
+# ---- A2 Matrix * Matrix ------------------------------------------------------------------------
+V["matmul"].append({
+    "cite": "tests/matrices.rs:161-166",
+    "a": [[1, 2], [3, 4], [5, 6]], "b": [[1, 2, 3], [4, 5, 6]],
+    "expect": [[9, 12, 15], [19, 26, 33], [29, 40, 51]]})
+V["matmul"].append({
+    "cite": "tests/linear_algebra.rs:183-190 (f32: L * L^T == A exactly)",
+    "a": [[5.0, 0.0, 0.0], [3.0, 3.0, 0.0], [-1.0, 1.0, 3.0]],
+    "b": [[5.0, 3.0, -1.0], [0.0, 3.0, 1.0], [0.0, 0.0, 3.0]],
+    "expect": [[25.0, 15.0, -5.0], [15.0, 18.0, 0.0], [-5.0, 0.0, 11.0]]})
+V["matmul"].append({
+    "cite": "src/differentiation/container_record/mod.rs:2816-2865 (numbers of RecordMatrix product)",
+    "a": [[1.0, 2.0, 3.0], [4.0, 5.0, 6.0], [7.0, 8.0, 9.0], [0.0, 5.0, 2.0]],
+    "b": [[1.0, 4.0, 7.0, 0.0], [2.0, 5.0, 8.0, 5.0], [3.0, 6.0, 9.0, 2.0]],
+    "expect": [[14.0, 32.0, 50.0, 16.0], [32.0, 77.0, 122.0, 37.0], [50.0, 122.0, 194.0, 58.0],
+               [16.0, 37.0, 58.0, 29.0]]})
+V["matmul_panic"].append({
+    "cite": "tests/matrices.rs:168-173 (#[should_panic]); message src/matrices/operations.rs:176-183",
+    "a_shape": [3, 2], "b_shape": [3, 2],
+    "message": "Mismatched Matrices, left is 3x2, right is 3x2, * is only defined for MxN * NxL"})
+
+# ---- A3 Tensor<T,2> * Tensor<T,2> --------------------------------------------------------------
+V["tensor_matmul"].append({
+    "cite": "src/tensors/operations.rs:521-546",
+    "a": [[1, 2, 3], [4, 5, 6]], "a_names": ["r", "c"],
+    "b": [[10, 11], [12, 13], [14, 15]], "b_names": ["r", "c"],
+    "expect": [[1 * 10 + 2 * 12 + 3 * 14, 1 * 11 + 2 * 13 + 3 * 15],
+               [4 * 10 + 5 * 12 + 6 * 14, 4 * 11 + 5 * 13 + 6 * 15]],
+    "expect_names": ["r", "c"]})
+V["tensor_matmul"].append({
+    "cite": "src/tensors/operations.rs:1655-1708 (all 16 owned/ref/view combinations agree)",
+    "a": [[1, 2, 3], [4, 5, 6]], "a_names": ["r", "c"],
+    "b": [[1, 2], [3, 4], [5, 6]], "b_names": ["a", "b"],
+    "expect": [[1 * 1 + 2 * 3 + 3 * 5, 1 * 2 + 2 * 4 + 3 * 6], [4 * 1 + 5 * 3 + 6 * 5, 4 * 2 + 5 * 4 + 6 * 6]],
+    "expect_names": ["r", "b"]})
+V["tensor_matmul"].append({
+    "cite": "tests/linear_algebra.rs:192-201 (f32 tensor L * L^T == A exactly)",
+    "a": [[5.0, 0.0, 0.0], [3.0, 3.0, 0.0], [-1.0, 1.0, 3.0]], "a_names": ["r", "c"],
+    "b": [[5.0, 3.0, -1.0], [0.0, 3.0, 1.0], [0.0, 0.0, 3.0]], "b_names": ["r", "c"],
+    "expect": [[25.0, 15.0, -5.0], [15.0, 18.0, 0.0], [-5.0, 0.0, 11.0]], "expect_names": ["r", "c"]})
+V["tensor_matmul"].append({
+    "cite": "src/differentiation/container_record/mod.rs:2721-2775 (numbers of RecordTensor product)",
+    "a": [[1.0, 2.0, 3.0], [4.0, 5.0, 6.0], [7.0, 8.0, 9.0], [0.0, 5.0, 2.0]], "a_names": ["r", "c"],
+    "b": [[1.0, 4.0, 7.0, 0.0], [2.0, 5.0, 8.0, 5.0], [3.0, 6.0, 9.0, 2.0]], "b_names": ["r", "c"],
+    "expect": [[14.0, 32.0, 50.0, 16.0], [32.0, 77.0, 122.0, 37.0], [50.0, 122.0, 194.0, 58.0],
+               [16.0, 37.0, 58.0, 29.0]], "expect_names": ["r", "c"]})
+V["tensor_matmul_panic"].append({
+    "cite": "src/tensors/operations.rs:14-18,492-501 (rows x columns * columns x rows is forbidden)",
+    "a_names": ["rows", "columns"], "a_shape": [2, 3], "b_names": ["columns", "rows"], "b_shape": [3, 2],
+    "message_prefix": "Matrix multiplication of tensors with shapes left [(\"rows\", 2), (\"columns\", 3)] and right "
+                      "[(\"columns\", 3), (\"rows\", 2)] would create duplicate dimension names as the shape "
+                      "[(\"rows\", 2), (\"rows\", 2)]."})
+V["tensor_matmul_panic"].append({
+    "cite": "src/tensors/operations.rs:485-491",
+    "a_names": ["r", "c"], "a_shape": [2, 3], "b_names": ["a", "b"], "b_shape": [2, 3],
+    "message_prefix": "Mismatched tensors, left is [(\"r\", 2), (\"c\", 3)], right is [(\"a\", 2), (\"b\", 3)], "
+                      "* is only defined for MxN * NxL dimension lengths"})
+
+# ---- A4 Einsum2 --------------------------------------------------------------------------------
+V["einsum2"].append({
+    "cite": "tests/einsum.rs:165-187 (ij,jk->ijk)",
+    "a": randomish([2, 3]), "a_names": ["i", "j"], "b": randomish([3, 4]), "b_names": ["j", "k"],
+    "out_names": ["i", "j", "k"],
+    "expect": [[[0.0, 0.0, 0.0, 0.0], [10.0, 110.0, 210.0, 310.0], [40.0, 240.0, 440.0, 640.0]],
+               [[0.0, 10.0, 20.0, 30.0], [11.0, 121.0, 231.0, 341.0], [42.0, 252.0, 462.0, 672.0]]]})
+V["einsum2"].append({
+    "cite": "tests/einsum.rs:189-206 (ij,kl->il)",
+    "a": randomish([2, 3]), "a_names": ["i", "j"], "b": randomish([3, 4]), "b_names": ["k", "l"],
+    "out_names": ["i", "l"],
+    "expect": [[90.0, 990.0, 1890.0, 2790.0], [99.0, 1089.0, 2079.0, 3069.0]]})
+# equivalences the reference asserts between Einsum and `*` (both sides recomputed by the test)
+V["einsum2_equiv"].append({
+    "cite": "tests/einsum.rs:60-74 (ab,cb->ac == x * y^T, matrix-vector)",
+    "a": randomish([2, 3]), "a_names": ["a", "b"], "b": randomish([1, 3]), "b_names": ["c", "b"],
+    "out_names": ["a", "c"], "equiv": "a @ b.T"})
+V["einsum2_equiv"].append({
+    "cite": "tests/einsum.rs:76-88 (ab,cb->ac == x * y^T)",
+    "a": randomish([2, 3]), "a_names": ["a", "b"], "b": randomish([2, 3]), "b_names": ["c", "b"],
+    "out_names": ["a", "c"], "equiv": "a @ b.T"})
+V["einsum2_equiv"].append({
+    "cite": "src/tensors/einsum.rs:58-72 doctest (ab,bc->ac == w * x)",
+    "a": [[float(a * 2 + b) for b in range(2)] for a in range(4)], "a_names": ["a", "b"],
+    "b": [[float(b * 3 + c) for c in range(3)] for b in range(2)], "b_names": ["b", "c"],
+    "out_names": ["a", "c"], "equiv": "a @ b"})
+V["einsum2_equiv"].append({
+    "cite": "src/tensors/einsum.rs:74-79 doctest (ab,ac->bc == w^T * z)",
+    "a": [[float(a * 2 + b) for b in range(2)] for a in range(4)], "a_names": ["a", "b"],
+    "b": [[float(a * 2 + c) for c in range(3)] for a in range(4)], "b_names": ["a", "c"],
+    "out_names": ["b", "c"], "equiv": "a.T @ b"})
+V["einsum2_equiv"].append({
+    "cite": "tests/einsum.rs:133-163 (batch a b,batch b c->batch a c == per-batch *)",
+    "a": [[[float(i + 10 * j + 2 * k) for k in range(5)] for j in range(2)] for i in range(3)],
+    "a_names": ["batch", "a", "b"],
+    "b": [[[float(i + 10 * j + 2 * k) for k in range(3)] for j in range(5)] for i in range(3)],
+    "b_names": ["batch", "b", "c"],
+    "out_names": ["batch", "a", "c"], "equiv": "batched a @ b"})
+V["einsum2_equiv"].append({
+    "cite": "tests/einsum.rs:90-98 (a,a-> == scalar_product)",
+    "a": [0.0, 1.0, 2.0], "a_names": ["a"], "b": [0.0, 1.0, 2.0], "b_names": ["a"], "out_names": [],
+    "equiv": "dot"})
+V["einsum2_equiv"].append({
+    "cite": "tests/einsum.rs:100-119 (ab,ab-> and ab,ab->ab == elementwise)",
+    "a": randomish([2, 3]), "a_names": ["a", "b"], "b": randomish([2, 3]), "b_names": ["a", "b"],
+    "out_names": ["a", "b"], "equiv": "a * b"})
+V["einsum2_equiv"].append({
+    "cite": "tests/einsum.rs:121-131 (a,b->ab outer product)",
+    "a": [0.0, 1.0, 2.0], "a_names": ["a"], "b": [0.0, 10.0, 20.0, 30.0, 40.0], "b_names": ["b"],
+    "out_names": ["a", "b"], "equiv": "outer"})
+
+# ---- A6-A9 RecordTensor / RecordMatrix matmul --------------------------------------------------
+V["record_matmul"].append({
+    "cite": "src/differentiation/container_record/mod.rs:2718-2811 and :2813-2903",
+    "dtype": "f64",
+    "a": [[1.0, 2.0, 3.0], [4.0, 5.0, 6.0], [7.0, 8.0, 9.0], [0.0, 5.0, 2.0]],
+    "b": [[1.0, 4.0, 7.0, 0.0], [2.0, 5.0, 8.0, 5.0], [3.0, 6.0, 9.0, 2.0]],
+    "expect": [[14.0, 32.0, 50.0, 16.0], [32.0, 77.0, 122.0, 37.0], [50.0, 122.0, 194.0, 58.0],
+               [16.0, 37.0, 58.0, 29.0]],
+    "asserts": ["numbers equal the scalar Record path", "every dC[i,j]/dA and dC[i,j]/dB equal the scalar path",
+                "tape lengths equal"]})
+
+# ---- end-to-end tape semantics: XOR network ----------------------------------------------------
+V["xor_nn"] = {
+    "cite": "tests/differentiation_nn.rs:23-120 (f32, ReLU, lr 0.1, 300 epochs, asserts losses[299] < 0.02)",
+    "w1": [[0.1, -0.1, -0.1], [0.5, 0.4, -0.1], [0.3, 0.5, 0.2]], "w2": [[0.3], [0.1], [-0.4]],
+    "inputs": [[0.0, 0.0, 1.0], [0.0, 1.0, 1.0], [1.0, 0.0, 1.0], [1.0, 1.0, 1.0]],
+    "labels": [0.0, 1.0, 1.0, 0.0], "learning_rate": 0.1, "epochs": 300, "final_loss_below": 0.02}
+
+out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_vectors.json")
+with open(out, "w") as f:
+    json.dump(V, f, indent=1)
+print("wrote", out)
