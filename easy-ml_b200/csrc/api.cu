@@ -1,0 +1,395 @@
+// api.cu -- the C ABI of include/easyml_b200.h: argument checks, kernel dispatch, host staging.
+#include <cstring>
+
+#include "common.h"
+
+namespace eml {
+
+namespace {
+
+template <class T>
+struct Threshold;
+template <>
+struct Threshold<double> {
+    // DMMA tiles are 128x128: below this the SIMT kernel's 64x64 tiles fill the machine better
+    static bool tensor_core(int64_t M, int64_t N, int64_t K) {
+        return (M < N ? M : N) >= 32 && K >= 8 && M * N * K >= (int64_t(1) << 21);
+    }
+};
+template <>
+struct Threshold<float> {
+    static bool tensor_core(int64_t M, int64_t N, int64_t K) {
+        return (M < N ? M : N) >= 64 && K >= 32 && M * N * K >= (int64_t(1) << 24);
+    }
+};
+
+template <class T>
+int tensor_core_path(DeviceCtx* ctx, const T* A, const T* B, T* C, int64_t batch, int64_t M, int64_t N,
+                     int64_t K, Strides3 sA, Strides3 sB, Strides3 sC, bool accumulate, cudaStream_t stream,
+                     bool* handled);
+template <>
+int tensor_core_path<double>(DeviceCtx* ctx, const double* A, const double* B, double* C, int64_t batch,
+                             int64_t M, int64_t N, int64_t K, Strides3 sA, Strides3 sB, Strides3 sC,
+                             bool accumulate, cudaStream_t stream, bool* handled) {
+    return launch_gemm_dmma_f64(ctx, A, B, C, batch, M, N, K, sA, sB, sC, accumulate, stream, handled);
+}
+template <>
+int tensor_core_path<float>(DeviceCtx* ctx, const float* A, const float* B, float* C, int64_t batch, int64_t M,
+                            int64_t N, int64_t K, Strides3 sA, Strides3 sB, Strides3 sC, bool accumulate,
+                            cudaStream_t stream, bool* handled) {
+    return launch_gemm_tf32x3_f32(ctx, A, B, C, batch, M, N, K, sA, sB, sC, accumulate, stream, handled);
+}
+
+}  // namespace
+
+template <class T>
+int contract_dev(DeviceCtx* ctx, const T* A, const T* B, T* C, int64_t batch, int64_t M, int64_t N, int64_t K,
+                 Strides3 sA, Strides3 sB, Strides3 sC, bool accumulate, bool exact, cudaStream_t stream) {
+    if (batch < 0 || M < 0 || N < 0) EML_BAD_ARG("contract: negative extent (batch=%lld M=%lld N=%lld)",
+                                                 (long long)batch, (long long)M, (long long)N);
+    if (K < 1) EML_BAD_ARG("contract: K must be >= 1 (got %lld); Easy ML containers have no zero-length dimension",
+                           (long long)K);
+    if (batch == 0 || M == 0 || N == 0) return EML_OK;
+    if (!A || !B || !C) EML_BAD_ARG("contract: null operand");
+    if (!stream) stream = ctx->stream;
+    if (!exact && Threshold<T>::tensor_core(M, N, K)) {
+        // the tensor-core kernels want C's column index contiguous; a row-contiguous C is the transposed
+        // problem C^T = B^T A^T with the same kernels
+        if (sC.c != 1 && sC.r == 1) {
+            Strides3 tA{sB.b, sB.c, sB.r}, tB{sA.b, sA.c, sA.r}, tC{sC.b, sC.c, sC.r};
+            bool handled = false;
+            EML_TRY(tensor_core_path<T>(ctx, B, A, C, batch, N, M, K, tA, tB, tC, accumulate, stream, &handled));
+            if (handled) return EML_OK;
+        } else {
+            bool handled = false;
+            EML_TRY(tensor_core_path<T>(ctx, A, B, C, batch, M, N, K, sA, sB, sC, accumulate, stream, &handled));
+            if (handled) return EML_OK;
+        }
+    }
+    return launch_gemm_simt<T>(A, B, C, batch, M, N, K, sA, sB, sC, accumulate, exact, stream);
+}
+
+template int contract_dev<float>(DeviceCtx*, const float*, const float*, float*, int64_t, int64_t, int64_t,
+                                 int64_t, Strides3, Strides3, Strides3, bool, bool, cudaStream_t);
+template int contract_dev<double>(DeviceCtx*, const double*, const double*, double*, int64_t, int64_t, int64_t,
+                                  int64_t, Strides3, Strides3, Strides3, bool, bool, cudaStream_t);
+
+namespace {
+
+inline Strides3 s3(const int64_t s[3]) { return Strides3{s[0], s[1], s[2]}; }
+
+// number of elements a strided (batch, r, c) view spans from its base pointer
+inline int64_t span(int64_t nb, int64_t nr, int64_t nc, Strides3 s) {
+    if (nb == 0 || nr == 0 || nc == 0) return 0;
+    return 1 + (nb - 1) * s.b + (nr - 1) * s.r + (nc - 1) * s.c;
+}
+
+inline bool nonneg(Strides3 s) { return s.b >= 0 && s.r >= 0 && s.c >= 0; }
+
+// Host entry: stage operands, run, copy the result back.  Blocks until C is in the caller's buffer.
+template <class T>
+int contract_host(const T* A, const T* B, T* C, int64_t batch, int64_t M, int64_t N, int64_t K, Strides3 sA,
+                  Strides3 sB, Strides3 sC, bool exact) {
+    DeviceCtx* ctx = nullptr;
+    EML_TRY(get_ctx(&ctx));
+    if (batch < 0 || M < 0 || N < 0 || K < 1) EML_BAD_ARG("contract: bad extents");
+    if (batch == 0 || M == 0 || N == 0) return EML_OK;
+    if (!A || !B || !C) EML_BAD_ARG("contract: null operand");
+    if (!nonneg(sA) || !nonneg(sB) || !nonneg(sC)) EML_BAD_ARG("contract: negative strides are not supported");
+    int64_t na = span(batch, M, K, sA), nb = span(batch, K, N, sB), nc = span(batch, M, N, sC);
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    void *dA, *dB, *dC;
+    EML_TRY(stage_buffer(ctx, 0, sizeof(T) * na, &dA));
+    EML_TRY(stage_buffer(ctx, 1, sizeof(T) * nb, &dB));
+    EML_TRY(stage_buffer(ctx, 2, sizeof(T) * nc, &dC));
+    cudaStream_t st = ctx->stream;
+    EML_CUDA(cudaMemcpyAsync(dA, A, sizeof(T) * na, cudaMemcpyHostToDevice, st));
+    EML_CUDA(cudaMemcpyAsync(dB, B, sizeof(T) * nb, cudaMemcpyHostToDevice, st));
+    // a strided C view may interleave with elements this call must not touch: bring them along
+    bool dense_c = (nc == batch * M * N);
+    if (!dense_c) EML_CUDA(cudaMemcpyAsync(dC, C, sizeof(T) * nc, cudaMemcpyHostToDevice, st));
+    EML_TRY(contract_dev<T>(ctx, (const T*)dA, (const T*)dB, (T*)dC, batch, M, N, K, sA, sB, sC, false, exact, st));
+    EML_CUDA(cudaMemcpyAsync(C, dC, sizeof(T) * nc, cudaMemcpyDeviceToHost, st));
+    EML_CUDA(cudaStreamSynchronize(st));
+    return EML_OK;
+}
+
+template <class T>
+int gemm_host(const T* A, const T* B, T* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc,
+              bool exact) {
+    if (M < 0 || N < 0 || K < 1) EML_BAD_ARG("gemm: bad extents M=%lld N=%lld K=%lld", (long long)M, (long long)N,
+                                             (long long)K);
+    if (lda < K || ldb < N || ldc < N) EML_BAD_ARG("gemm: leading dimension smaller than the row length");
+    return contract_host<T>(A, B, C, 1, M, N, K, Strides3{0, lda, 1}, Strides3{0, ldb, 1}, Strides3{0, ldc, 1},
+                            exact);
+}
+
+template <class T>
+int gemm_dev(const T* A, const T* B, T* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc,
+             bool exact, void* stream) {
+    DeviceCtx* ctx = nullptr;
+    EML_TRY(get_ctx(&ctx));
+    if (lda < K || ldb < N || ldc < N) EML_BAD_ARG("gemm: leading dimension smaller than the row length");
+    return contract_dev<T>(ctx, A, B, C, 1, M, N, K, Strides3{0, lda, 1}, Strides3{0, ldb, 1}, Strides3{0, ldc, 1},
+                           false, exact, (cudaStream_t)stream);
+}
+
+template <class T>
+int einsum_host(const T* A, int64_t a_elems, const T* B, int64_t b_elems, T* out, int n_out, const int64_t* out_len,
+                const int64_t* ao, const int64_t* bo, int n_sum, const int64_t* sum_len, const int64_t* as,
+                const int64_t* bs) {
+    DeviceCtx* ctx = nullptr;
+    EML_TRY(get_ctx(&ctx));
+    if (a_elems < 1 || b_elems < 1 || !A || !B || !out) EML_BAD_ARG("einsum2: empty operand");
+    if (n_out < 0 || n_out > 6 || n_sum < 0 || n_sum > 12) EML_BAD_ARG("einsum2: rank out of range");
+    int64_t total = 1, amax = 0, bmax = 0;
+    for (int d = 0; d < n_out; d++) {
+        if (out_len[d] < 0 || ao[d] < 0 || bo[d] < 0) EML_BAD_ARG("einsum2: negative length/stride");
+        total *= out_len[d];
+        if (out_len[d]) amax += (out_len[d] - 1) * ao[d], bmax += (out_len[d] - 1) * bo[d];
+    }
+    for (int d = 0; d < n_sum; d++) {
+        if (sum_len[d] < 0 || as[d] < 0 || bs[d] < 0) EML_BAD_ARG("einsum2: negative length/stride");
+        if (sum_len[d]) amax += (sum_len[d] - 1) * as[d], bmax += (sum_len[d] - 1) * bs[d];
+    }
+    if (total == 0) return EML_OK;
+    if (amax >= a_elems || bmax >= b_elems) EML_BAD_ARG("einsum2: strides reach outside the operand buffers");
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    void *dA, *dB, *dC;
+    EML_TRY(stage_buffer(ctx, 0, sizeof(T) * a_elems, &dA));
+    EML_TRY(stage_buffer(ctx, 1, sizeof(T) * b_elems, &dB));
+    EML_TRY(stage_buffer(ctx, 2, sizeof(T) * total, &dC));
+    cudaStream_t st = ctx->stream;
+    EML_CUDA(cudaMemcpyAsync(dA, A, sizeof(T) * a_elems, cudaMemcpyHostToDevice, st));
+    EML_CUDA(cudaMemcpyAsync(dB, B, sizeof(T) * b_elems, cudaMemcpyHostToDevice, st));
+    EML_TRY(launch_einsum2<T>((const T*)dA, (const T*)dB, (T*)dC, n_out, out_len, ao, bo, n_sum, sum_len, as, bs, st));
+    EML_CUDA(cudaMemcpyAsync(out, dC, sizeof(T) * total, cudaMemcpyDeviceToHost, st));
+    EML_CUDA(cudaStreamSynchronize(st));
+    return EML_OK;
+}
+
+template <class T>
+int dot_host(const T* x, int64_t incx, const T* y, int64_t incy, int64_t n, T* out) {
+    DeviceCtx* ctx = nullptr;
+    EML_TRY(get_ctx(&ctx));
+    if (n < 1 || incx < 1 || incy < 1 || !x || !y || !out) EML_BAD_ARG("dot: n >= 1 and positive increments required");
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    void *dx, *dy, *dout;
+    int64_t nx = 1 + (n - 1) * incx, ny = 1 + (n - 1) * incy;
+    EML_TRY(stage_buffer(ctx, 0, sizeof(T) * nx, &dx));
+    EML_TRY(stage_buffer(ctx, 1, sizeof(T) * ny, &dy));
+    EML_TRY(stage_buffer(ctx, 2, sizeof(T), &dout));
+    cudaStream_t st = ctx->stream;
+    EML_CUDA(cudaMemcpyAsync(dx, x, sizeof(T) * nx, cudaMemcpyHostToDevice, st));
+    EML_CUDA(cudaMemcpyAsync(dy, y, sizeof(T) * ny, cudaMemcpyHostToDevice, st));
+    EML_TRY(launch_dot<T>((const T*)dx, incx, (const T*)dy, incy, n, (T*)dout, st));
+    EML_CUDA(cudaMemcpyAsync(out, dout, sizeof(T), cudaMemcpyDeviceToHost, st));
+    EML_CUDA(cudaStreamSynchronize(st));
+    return EML_OK;
+}
+
+template <class T>
+int matmul_bwd_dev(const T* dC, const T* A, const T* B, T* dA, T* dB, int64_t M, int64_t N, int64_t K,
+                   void* stream) {
+    DeviceCtx* ctx = nullptr;
+    EML_TRY(get_ctx(&ctx));
+    if (!dC || !A || !B) EML_BAD_ARG("matmul_bwd: null operand");
+    cudaStream_t st = (cudaStream_t)stream;
+    // dA[M x K] += dC[M x N] * B^T[N x K]   (B^T read in place: element (n,k) at B[k*N + n])
+    if (dA)
+        EML_TRY(contract_dev<T>(ctx, dC, B, dA, 1, M, K, N, Strides3{0, N, 1}, Strides3{0, 1, N}, Strides3{0, K, 1},
+                                true, false, st));
+    // dB[K x N] += A^T[K x M] * dC[M x N]   (A^T read in place: element (k,m) at A[m*K + k])
+    if (dB)
+        EML_TRY(contract_dev<T>(ctx, A, dC, dB, 1, K, N, M, Strides3{0, 1, K}, Strides3{0, N, 1}, Strides3{0, N, 1},
+                                true, false, st));
+    return EML_OK;
+}
+
+#define EML_STREAM_OR_CTX(st)                 \
+    DeviceCtx* ctx = nullptr;                 \
+    EML_TRY(get_ctx(&ctx));                   \
+    cudaStream_t st = (cudaStream_t)stream;   \
+    if (!st) st = ctx->stream;
+
+}  // namespace
+}  // namespace eml
+
+using namespace eml;
+
+extern "C" {
+
+int eml_init(int* n_devices) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        n = 0;
+    }
+    if (n_devices) *n_devices = n;
+    if (n == 0) {
+        set_error("no CUDA device present: the f32/f64 path has no CPU fallback");
+        return EML_ERR_NO_DEVICE;
+    }
+    return EML_OK;
+}
+void eml_shutdown(void) { shutdown_all(); }
+const char* eml_last_error(void) { return last_error(); }
+int eml_version(void) { return 100; }
+int64_t eml_kernel_launches(void) { return launches(); }
+const char* eml_last_kernel(void) { return last_kernel(); }
+
+int eml_gemm_f32(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda,
+                 int64_t ldb, int64_t ldc) {
+    return gemm_host<float>(A, B, C, M, N, K, lda, ldb, ldc, false);
+}
+int eml_gemm_f64(const double* A, const double* B, double* C, int64_t M, int64_t N, int64_t K, int64_t lda,
+                 int64_t ldb, int64_t ldc) {
+    return gemm_host<double>(A, B, C, M, N, K, lda, ldb, ldc, false);
+}
+int eml_gemm_exact_f32(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda,
+                       int64_t ldb, int64_t ldc) {
+    return gemm_host<float>(A, B, C, M, N, K, lda, ldb, ldc, true);
+}
+int eml_gemm_exact_f64(const double* A, const double* B, double* C, int64_t M, int64_t N, int64_t K,
+                       int64_t lda, int64_t ldb, int64_t ldc) {
+    return gemm_host<double>(A, B, C, M, N, K, lda, ldb, ldc, true);
+}
+int eml_contract_f32(const float* A, const float* B, float* C, int64_t batch, int64_t M, int64_t N, int64_t K,
+                     const int64_t sA[3], const int64_t sB[3], const int64_t sC[3]) {
+    if (!sA || !sB || !sC) EML_BAD_ARG("contract: null strides");
+    return contract_host<float>(A, B, C, batch, M, N, K, s3(sA), s3(sB), s3(sC), false);
+}
+int eml_contract_f64(const double* A, const double* B, double* C, int64_t batch, int64_t M, int64_t N,
+                     int64_t K, const int64_t sA[3], const int64_t sB[3], const int64_t sC[3]) {
+    if (!sA || !sB || !sC) EML_BAD_ARG("contract: null strides");
+    return contract_host<double>(A, B, C, batch, M, N, K, s3(sA), s3(sB), s3(sC), false);
+}
+int eml_einsum2_f32(const float* A, int64_t ae, const float* B, int64_t be, float* out, int n_out,
+                    const int64_t* out_len, const int64_t* ao, const int64_t* bo, int n_sum, const int64_t* sum_len,
+                    const int64_t* as, const int64_t* bs) {
+    return einsum_host<float>(A, ae, B, be, out, n_out, out_len, ao, bo, n_sum, sum_len, as, bs);
+}
+int eml_einsum2_f64(const double* A, int64_t ae, const double* B, int64_t be, double* out, int n_out,
+                    const int64_t* out_len, const int64_t* ao, const int64_t* bo, int n_sum, const int64_t* sum_len,
+                    const int64_t* as, const int64_t* bs) {
+    return einsum_host<double>(A, ae, B, be, out, n_out, out_len, ao, bo, n_sum, sum_len, as, bs);
+}
+int eml_dot_f32(const float* x, int64_t incx, const float* y, int64_t incy, int64_t n, float* out) {
+    return dot_host<float>(x, incx, y, incy, n, out);
+}
+int eml_dot_f64(const double* x, int64_t incx, const double* y, int64_t incy, int64_t n, double* out) {
+    return dot_host<double>(x, incx, y, incy, n, out);
+}
+
+int eml_alloc(void** dptr, size_t bytes) {
+    DeviceCtx* ctx = nullptr;
+    EML_TRY(get_ctx(&ctx));
+    if (!dptr) EML_BAD_ARG("alloc: null out pointer");
+    EML_CUDA(cudaMalloc(dptr, bytes ? bytes : 16));
+    return EML_OK;
+}
+int eml_free(void* dptr) {
+    if (dptr) EML_CUDA(cudaFree(dptr));
+    return EML_OK;
+}
+int eml_upload(void* dst, const void* src, size_t bytes) {
+    DeviceCtx* ctx = nullptr;
+    EML_TRY(get_ctx(&ctx));
+    EML_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    EML_CUDA(cudaStreamSynchronize(ctx->stream));
+    return EML_OK;
+}
+int eml_download(void* dst, const void* src, size_t bytes) {
+    DeviceCtx* ctx = nullptr;
+    EML_TRY(get_ctx(&ctx));
+    EML_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    EML_CUDA(cudaStreamSynchronize(ctx->stream));
+    return EML_OK;
+}
+int eml_sync(void) {
+    DeviceCtx* ctx = nullptr;
+    EML_TRY(get_ctx(&ctx));
+    EML_CUDA(cudaDeviceSynchronize());
+    return EML_OK;
+}
+
+int eml_contract_f32_dev(const float* A, const float* B, float* C, int64_t batch, int64_t M, int64_t N,
+                         int64_t K, const int64_t sA[3], const int64_t sB[3], const int64_t sC[3],
+                         int accumulate, void* stream) {
+    DeviceCtx* ctx = nullptr;
+    EML_TRY(get_ctx(&ctx));
+    if (!sA || !sB || !sC) EML_BAD_ARG("contract: null strides");
+    return contract_dev<float>(ctx, A, B, C, batch, M, N, K, s3(sA), s3(sB), s3(sC), accumulate != 0, false,
+                               (cudaStream_t)stream);
+}
+int eml_contract_f64_dev(const double* A, const double* B, double* C, int64_t batch, int64_t M, int64_t N,
+                         int64_t K, const int64_t sA[3], const int64_t sB[3], const int64_t sC[3],
+                         int accumulate, void* stream) {
+    DeviceCtx* ctx = nullptr;
+    EML_TRY(get_ctx(&ctx));
+    if (!sA || !sB || !sC) EML_BAD_ARG("contract: null strides");
+    return contract_dev<double>(ctx, A, B, C, batch, M, N, K, s3(sA), s3(sB), s3(sC), accumulate != 0, false,
+                                (cudaStream_t)stream);
+}
+int eml_gemm_f32_dev(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda,
+                     int64_t ldb, int64_t ldc, void* stream) {
+    return gemm_dev<float>(A, B, C, M, N, K, lda, ldb, ldc, false, stream);
+}
+int eml_gemm_f64_dev(const double* A, const double* B, double* C, int64_t M, int64_t N, int64_t K, int64_t lda,
+                     int64_t ldb, int64_t ldc, void* stream) {
+    return gemm_dev<double>(A, B, C, M, N, K, lda, ldb, ldc, false, stream);
+}
+int eml_gemm_exact_f32_dev(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K,
+                           int64_t lda, int64_t ldb, int64_t ldc, void* stream) {
+    return gemm_dev<float>(A, B, C, M, N, K, lda, ldb, ldc, true, stream);
+}
+int eml_gemm_exact_f64_dev(const double* A, const double* B, double* C, int64_t M, int64_t N, int64_t K,
+                           int64_t lda, int64_t ldb, int64_t ldc, void* stream) {
+    return gemm_dev<double>(A, B, C, M, N, K, lda, ldb, ldc, true, stream);
+}
+int eml_matmul_bwd_f32_dev(const float* dC, const float* A, const float* B, float* dA, float* dB, int64_t M,
+                           int64_t N, int64_t K, void* stream) {
+    return matmul_bwd_dev<float>(dC, A, B, dA, dB, M, N, K, stream);
+}
+int eml_matmul_bwd_f64_dev(const double* dC, const double* A, const double* B, double* dA, double* dB,
+                           int64_t M, int64_t N, int64_t K, void* stream) {
+    return matmul_bwd_dev<double>(dC, A, B, dA, dB, M, N, K, stream);
+}
+
+int eml_unary_f32_dev(int op, float c, const float* x, float* y, float* dydx, int64_t n, void* stream) {
+    EML_STREAM_OR_CTX(st);
+    return launch_unary<float>(op, c, x, y, dydx, n, st);
+}
+int eml_unary_f64_dev(int op, double c, const double* x, double* y, double* dydx, int64_t n, void* stream) {
+    EML_STREAM_OR_CTX(st);
+    return launch_unary<double>(op, c, x, y, dydx, n, st);
+}
+int eml_binary_f32_dev(int op, const float* x, const float* y, float* z, float* dzdx, float* dzdy, int64_t n,
+                       void* stream) {
+    EML_STREAM_OR_CTX(st);
+    return launch_binary<float>(op, x, y, z, dzdx, dzdy, n, st);
+}
+int eml_binary_f64_dev(int op, const double* x, const double* y, double* z, double* dzdx, double* dzdy,
+                       int64_t n, void* stream) {
+    EML_STREAM_OR_CTX(st);
+    return launch_binary<double>(op, x, y, z, dzdx, dzdy, n, st);
+}
+int eml_chain_f32_dev(const float* dout, const float* deriv, float* dparent, int64_t n, void* stream) {
+    EML_STREAM_OR_CTX(st);
+    return launch_chain<float>(dout, deriv, dparent, n, st);
+}
+int eml_chain_f64_dev(const double* dout, const double* deriv, double* dparent, int64_t n, void* stream) {
+    EML_STREAM_OR_CTX(st);
+    return launch_chain<double>(dout, deriv, dparent, n, st);
+}
+int eml_sgd_f32_dev(float* w, const float* d, float lr, int64_t n, void* stream) {
+    EML_STREAM_OR_CTX(st);
+    return launch_sgd<float>(w, d, lr, n, st);
+}
+int eml_sgd_f64_dev(double* w, const double* d, double lr, int64_t n, void* stream) {
+    EML_STREAM_OR_CTX(st);
+    return launch_sgd<double>(w, d, lr, n, st);
+}
+
+}  // extern "C"

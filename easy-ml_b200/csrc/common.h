@@ -1,0 +1,139 @@
+// common.h -- shared host-side plumbing of libeasyml_b200 (errors, per-device context, launch counting).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+#include <mutex>
+
+#include "easyml_b200.h"
+
+namespace eml {
+
+// ---- errors (thread-local message behind eml_last_error) ----
+void set_error(const char* fmt, ...) __attribute__((format(printf, 1, 2)));
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+const char* last_error();
+
+#define EML_CUDA(expr)                                                              \
+    do {                                                                            \
+        cudaError_t eml_e_ = (expr);                                                \
+        if (eml_e_ != cudaSuccess) return ::eml::cuda_fail(eml_e_, #expr, __FILE__, __LINE__); \
+    } while (0)
+
+#define EML_TRY(expr)                \
+    do {                             \
+        int eml_rc_ = (expr);        \
+        if (eml_rc_ != EML_OK) return eml_rc_; \
+    } while (0)
+
+#define EML_BAD_ARG(...)             \
+    do {                             \
+        ::eml::set_error(__VA_ARGS__); \
+        return EML_ERR_BAD_ARG;      \
+    } while (0)
+
+// every kernel launch of this library goes through here (bench.py reports the count)
+void count_launch(int n = 1);
+int64_t launches();
+void set_last_kernel(const char* name);
+const char* last_kernel();
+// call after a launch: picks up launch-configuration errors
+int check_launch(const char* what);
+
+// ---- per-device context ----
+struct DeviceCtx {
+    int device = -1;
+    int sm_count = 148;
+    size_t smem_optin = 0;
+    cudaStream_t stream = nullptr;  // library stream for host entry points / NULL-stream _dev calls
+    std::mutex mu;  // guards the staging buffers of the host entry points
+    // staging for host entry points (device side), grow-only, one slot per operand
+    void* stage[3] = {nullptr, nullptr, nullptr};
+    size_t stage_bytes[3] = {0, 0, 0};
+};
+
+// context of the calling thread's current device; EML_ERR_NO_DEVICE when there is no GPU
+int get_ctx(DeviceCtx** out);
+// Scratch (pack buffers, split-K partials, reduction partials) comes from CUDA's stream-ordered
+// allocator: allocation and release are ordered on the stream that uses the memory, so concurrent
+// callers on different streams never share a buffer.  The pool keeps freed blocks (release threshold
+// = max), so steady-state calls do not touch the OS allocator.
+struct TempBuf {
+    void* p = nullptr;
+    cudaStream_t s = nullptr;
+    TempBuf() = default;
+    TempBuf(const TempBuf&) = delete;
+    TempBuf& operator=(const TempBuf&) = delete;
+    ~TempBuf() {
+        if (p) cudaFreeAsync(p, s);
+    }
+    int alloc(size_t bytes, cudaStream_t stream);
+    template <class T>
+    T* as() const { return static_cast<T*>(p); }
+};
+int stage_buffer(DeviceCtx* ctx, int slot, size_t bytes, void** out);
+void shutdown_all();
+
+struct Strides3 {
+    int64_t b, r, c;  // batch, row, column strides in elements
+};
+
+// ---- kernels (one translation unit each) ----
+// general strided batched contraction C[b,m,n] (+)= sum_k A[b,m,k] B[b,k,n]; dispatches between the
+// tensor-core kernels and the SIMT kernel.  exact = reference operation order, bit-exact.
+template <class T>
+int contract_dev(DeviceCtx* ctx, const T* A, const T* B, T* C, int64_t batch, int64_t M, int64_t N, int64_t K,
+                 Strides3 sA, Strides3 sB, Strides3 sC, bool accumulate, bool exact, cudaStream_t stream);
+
+template <class T>
+int launch_gemm_simt(const T* A, const T* B, T* C, int64_t batch, int64_t M, int64_t N, int64_t K, Strides3 sA,
+                     Strides3 sB, Strides3 sC, bool accumulate, bool exact, cudaStream_t stream);
+
+// f64 tensor-core (DMMA) kernel.  Returns EML_OK and sets *handled=false when the layout is not one it
+// supports (caller falls through to another GPU kernel).
+int launch_gemm_dmma_f64(DeviceCtx* ctx, const double* A, const double* B, double* C, int64_t batch, int64_t M,
+                         int64_t N, int64_t K, Strides3 sA, Strides3 sB, Strides3 sC, bool accumulate,
+                         cudaStream_t stream, bool* handled);
+
+// f32 3xTF32 on tcgen05 + TMEM, operands staged by TMA (pack kernel splits into big/small parts).
+int launch_gemm_tf32x3_f32(DeviceCtx* ctx, const float* A, const float* B, float* C, int64_t batch, int64_t M,
+                           int64_t N, int64_t K, Strides3 sA, Strides3 sB, Strides3 sC, bool accumulate,
+                           cudaStream_t stream, bool* handled);
+
+template <class T>
+int launch_einsum2(const T* A, const T* B, T* out, int n_out, const int64_t* out_len, const int64_t* a_out_stride,
+                   const int64_t* b_out_stride, int n_sum, const int64_t* sum_len, const int64_t* a_sum_stride,
+                   const int64_t* b_sum_stride, cudaStream_t stream);
+
+template <class T>
+int launch_dot(const T* x, int64_t incx, const T* y, int64_t incy, int64_t n, T* out_dev, cudaStream_t stream);
+
+template <class T>
+int launch_unary(int op, T c, const T* x, T* y, T* dydx, int64_t n, cudaStream_t stream);
+template <class T>
+int launch_binary(int op, const T* x, const T* y, T* z, T* dzdx, T* dzdy, int64_t n, cudaStream_t stream);
+template <class T>
+int launch_chain(const T* dout, const T* deriv, T* dparent, int64_t n, cudaStream_t stream);
+template <class T>
+int launch_sgd(T* w, const T* d, T lr, int64_t n, cudaStream_t stream);
+// out[i] = value (fill), used by the tape (seeding, zeroing is cudaMemsetAsync)
+template <class T>
+int launch_fill(T* out, T value, int64_t n, cudaStream_t stream);
+// deterministic full reduction: out[0] (+)= sum_i x[i] (fixed tree); and the column / row sums used by the
+// constant-operand path of the matmul backward.
+template <class T>
+int launch_reduce_sum(DeviceCtx* ctx, const T* x, int64_t n, T* out, bool accumulate, cudaStream_t stream);
+template <class T>
+int launch_col_sums(const T* x, int64_t rows, int64_t cols, T* out, cudaStream_t stream);  // out[c] = sum_r x[r,c]
+template <class T>
+int launch_row_sums(const T* x, int64_t rows, int64_t cols, T* out, cudaStream_t stream);  // out[r] = sum_c x[r,c]
+// out[0] (+)= sum_i x[i]*y[i], fixed order
+template <class T>
+int launch_dot_accumulate(DeviceCtx* ctx, const T* x, const T* y, int64_t n, T* out, bool accumulate,
+                          cudaStream_t stream);
+// dst[i] = src[idx(i)] strided gather/scatter helpers for matmul-output derivative vectors
+template <class T>
+int launch_add_inplace(T* dst, const T* src, int64_t n, cudaStream_t stream);
+
+}  // namespace eml

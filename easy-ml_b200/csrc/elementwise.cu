@@ -1,0 +1,485 @@
+// elementwise.cu -- HBM-bound kernels around the GEMMs: container unary/binary ops with their tape
+// derivatives in one pass, the backward chain rule, SGD, deterministic reductions, generic einsum.
+//
+// Compiled with -fmad=false: +,-,*,/ stay separately rounded IEEE operations, so these kernels are
+// bit-exact with the reference's rules (src/differentiation/functions.rs) for the arithmetic ops;
+// exp/ln/sin/cos/pow differ from Rust's libm by the usual ulp or two (tolerance stated in the tests).
+#include <type_traits>
+
+#include "common.h"
+
+namespace eml {
+
+namespace {
+
+constexpr int EW_THREADS = 256;
+
+inline int ew_grid(int64_t n, int per_thread) {
+    int64_t blocks = (n + (int64_t)EW_THREADS * per_thread - 1) / ((int64_t)EW_THREADS * per_thread);
+    const int64_t cap = 148 * 16;  // 16 resident 256-thread CTAs per SM
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+// 16-byte vectors: float4 / double2
+template <class T>
+struct Vec;
+template <>
+struct Vec<float> {
+    using type = float4;
+    static constexpr int N = 4;
+};
+template <>
+struct Vec<double> {
+    using type = double2;
+    static constexpr int N = 2;
+};
+
+template <class T>
+__device__ __forceinline__ void vload(const T* p, T (&v)[Vec<T>::N]) {
+    typename Vec<T>::type t = *reinterpret_cast<const typename Vec<T>::type*>(p);
+    const T* e = reinterpret_cast<const T*>(&t);
+#pragma unroll
+    for (int i = 0; i < Vec<T>::N; i++) v[i] = e[i];
+}
+template <class T>
+__device__ __forceinline__ void vstore(T* p, const T (&v)[Vec<T>::N]) {
+    typename Vec<T>::type t;
+    T* e = reinterpret_cast<T*>(&t);
+#pragma unroll
+    for (int i = 0; i < Vec<T>::N; i++) e[i] = v[i];
+    *reinterpret_cast<typename Vec<T>::type*>(p) = t;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// ---- rules (reference src/differentiation/functions.rs) ----
+template <class T, int OP>
+__device__ __forceinline__ void unary_rule(T c, T x, T& y, T& d) {
+    if (OP == EML_OP_NEG) { y = -x; d = -T(1); }
+    else if (OP == EML_OP_SIN) { y = sin(x); d = cos(x); }
+    else if (OP == EML_OP_COS) { y = cos(x); d = -sin(x); }
+    else if (OP == EML_OP_EXP) { y = exp(x); d = y; }
+    else if (OP == EML_OP_LN) { y = log(x); d = T(1) / x; }
+    else if (OP == EML_OP_SQRT) { y = sqrt(x); d = T(1) / ((T(1) + T(1)) * y); }
+    else if (OP == EML_OP_ADD_C) { y = x + c; d = T(1); }
+    else if (OP == EML_OP_SUB_C) { y = x - c; d = T(1); }
+    else if (OP == EML_OP_MUL_C) { y = x * c; d = c; }
+    else if (OP == EML_OP_DIV_C) { y = x / c; d = T(1) / c; }
+    else if (OP == EML_OP_POW_C) { y = pow(x, c); d = c * pow(x, c - T(1)); }
+    else if (OP == EML_OP_C_SUB) { y = c - x; d = -T(1); }
+    else if (OP == EML_OP_C_DIV) { y = c / x; d = -c / (x * x); }
+    else if (OP == EML_OP_C_POW) { y = pow(c, x); d = y * log(c); }
+}
+
+template <class T, int OP>
+__device__ __forceinline__ void binary_rule(T x, T y, T& z, T& dx, T& dy) {
+    if (OP == EML_OP_ADD) { z = x + y; dx = T(1); dy = T(1); }
+    else if (OP == EML_OP_SUB) { z = x - y; dx = T(1); dy = -T(1); }
+    else if (OP == EML_OP_MUL) { z = x * y; dx = y; dy = x; }
+    else if (OP == EML_OP_DIV) { z = x / y; dx = T(1) / y; dy = -x / (y * y); }
+    else if (OP == EML_OP_POW) { z = pow(x, y); dx = y * pow(x, y - T(1)); dy = z * log(x); }
+}
+
+template <class T, int OP, bool VEC>
+__global__ void __launch_bounds__(EW_THREADS)
+unary_kernel(T c, const T* __restrict__ x, T* __restrict__ y, T* __restrict__ dydx, int64_t n) {
+    constexpr int V = VEC ? Vec<T>::N : 1;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x * V;
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * V; i < n; i += stride) {
+        if (VEC && i + V <= n) {
+            T xv[Vec<T>::N], yv[Vec<T>::N], dv[Vec<T>::N];
+            vload<T>(x + i, xv);
+#pragma unroll
+            for (int j = 0; j < Vec<T>::N; j++) unary_rule<T, OP>(c, xv[j], yv[j], dv[j]);
+            if (y) vstore<T>(y + i, yv);
+            if (dydx) vstore<T>(dydx + i, dv);
+        } else {
+            for (int j = 0; j < V && i + j < n; j++) {
+                T yy, dd;
+                unary_rule<T, OP>(c, x[i + j], yy, dd);
+                if (y) y[i + j] = yy;
+                if (dydx) dydx[i + j] = dd;
+            }
+        }
+    }
+}
+
+template <class T, int OP, bool VEC>
+__global__ void __launch_bounds__(EW_THREADS)
+binary_kernel(const T* __restrict__ x, const T* __restrict__ y, T* __restrict__ z, T* __restrict__ dzdx,
+              T* __restrict__ dzdy, int64_t n) {
+    constexpr int V = VEC ? Vec<T>::N : 1;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x * V;
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * V; i < n; i += stride) {
+        if (VEC && i + V <= n) {
+            T xv[Vec<T>::N], yv[Vec<T>::N], zv[Vec<T>::N], ax[Vec<T>::N], ay[Vec<T>::N];
+            vload<T>(x + i, xv);
+            vload<T>(y + i, yv);
+#pragma unroll
+            for (int j = 0; j < Vec<T>::N; j++) binary_rule<T, OP>(xv[j], yv[j], zv[j], ax[j], ay[j]);
+            if (z) vstore<T>(z + i, zv);
+            if (dzdx) vstore<T>(dzdx + i, ax);
+            if (dzdy) vstore<T>(dzdy + i, ay);
+        } else {
+            for (int j = 0; j < V && i + j < n; j++) {
+                T zz, a, b;
+                binary_rule<T, OP>(x[i + j], y[i + j], zz, a, b);
+                if (z) z[i + j] = zz;
+                if (dzdx) dzdx[i + j] = a;
+                if (dzdy) dzdy[i + j] = b;
+            }
+        }
+    }
+}
+
+// MODE 0: dparent += dout*deriv   1: w -= lr*d  (lr in c)   2: out = c   3: dst += src
+template <class T, int MODE, bool VEC>
+__global__ void __launch_bounds__(EW_THREADS)
+axpy_kernel(T c, const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, int64_t n) {
+    constexpr int V = VEC ? Vec<T>::N : 1;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x * V;
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * V; i < n; i += stride) {
+        if (VEC && i + V <= n) {
+            T av[Vec<T>::N], bv[Vec<T>::N], ov[Vec<T>::N];
+            if (MODE != 2) vload<T>(a + i, av);
+            if (MODE == 0) vload<T>(b + i, bv);
+            if (MODE != 2) vload<T>(out + i, ov);
+#pragma unroll
+            for (int j = 0; j < Vec<T>::N; j++) {
+                if (MODE == 0) ov[j] = ov[j] + av[j] * bv[j];
+                if (MODE == 1) ov[j] = ov[j] - av[j] * c;
+                if (MODE == 2) ov[j] = c;
+                if (MODE == 3) ov[j] = ov[j] + av[j];
+            }
+            vstore<T>(out + i, ov);
+        } else {
+            for (int j = 0; j < V && i + j < n; j++) {
+                int64_t q = i + j;
+                if (MODE == 0) out[q] = out[q] + a[q] * b[q];
+                if (MODE == 1) out[q] = out[q] - a[q] * c;
+                if (MODE == 2) out[q] = c;
+                if (MODE == 3) out[q] = out[q] + a[q];
+            }
+        }
+    }
+}
+
+// ---- deterministic reductions ----
+constexpr int RED_THREADS = 256;
+
+template <class T>
+__device__ __forceinline__ T block_reduce(T v, T* smem) {
+    // fixed tree: warp shuffles then the 8 warp sums added in order
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) smem[w] = v;
+    __syncthreads();
+    T total = T(0);
+    if (threadIdx.x == 0)
+        for (int i = 0; i < RED_THREADS / 32; i++) total += smem[i];
+    __syncthreads();
+    return total;  // valid in thread 0
+}
+
+// stage 1: block b sums elements [b*chunk, min(n,(b+1)*chunk)) of x[i*incx] * (y ? y[i*incy] : 1)
+template <class T>
+__global__ void __launch_bounds__(RED_THREADS)
+reduce_stage1(const T* __restrict__ x, int64_t incx, const T* __restrict__ y, int64_t incy, int64_t n,
+              int64_t chunk, T* __restrict__ partials) {
+    __shared__ T smem[RED_THREADS / 32];
+    int64_t lo = (int64_t)blockIdx.x * chunk, hi = lo + chunk < n ? lo + chunk : n;
+    T acc = T(0);
+    for (int64_t i = lo + threadIdx.x; i < hi; i += RED_THREADS) {
+        T v = x[i * incx];
+        if (y) v = v * y[i * incy];
+        acc += v;
+    }
+    T total = block_reduce<T>(acc, smem);
+    if (threadIdx.x == 0) partials[blockIdx.x] = total;
+}
+
+template <class T>
+__global__ void __launch_bounds__(RED_THREADS)
+reduce_stage2(const T* __restrict__ partials, int count, T* __restrict__ out, int accumulate) {
+    __shared__ T smem[RED_THREADS / 32];
+    T acc = T(0);
+    for (int i = threadIdx.x; i < count; i += RED_THREADS) acc += partials[i];
+    T total = block_reduce<T>(acc, smem);
+    if (threadIdx.x == 0) out[0] = accumulate ? out[0] + total : total;
+}
+
+template <class T>
+int reduce_impl(const T* x, int64_t incx, const T* y, int64_t incy, int64_t n, T* out, bool accumulate,
+                cudaStream_t stream) {
+    int blocks = (int)((n + 4095) / 4096);
+    if (blocks > 1024) blocks = 1024;
+    if (blocks < 1) blocks = 1;
+    int64_t chunk = (n + blocks - 1) / blocks;
+    TempBuf partials;
+    EML_TRY(partials.alloc(sizeof(T) * blocks, stream));
+    reduce_stage1<T><<<blocks, RED_THREADS, 0, stream>>>(x, incx, y, incy, n, chunk, partials.as<T>());
+    reduce_stage2<T><<<1, RED_THREADS, 0, stream>>>(partials.as<T>(), blocks, out, accumulate ? 1 : 0);
+    count_launch(2);
+    return check_launch("reduce");
+}
+
+// column sums: partial[chunk][c] = sum over the chunk's rows, then a fixed-order sum over chunks
+template <class T>
+__global__ void __launch_bounds__(256)
+col_sums_stage1(const T* __restrict__ x, int64_t rows, int64_t cols, int64_t rows_per_chunk, T* __restrict__ partial) {
+    __shared__ T smem[8][33];
+    int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    int64_t c = (int64_t)blockIdx.x * 32 + tx;
+    int64_t r0 = (int64_t)blockIdx.y * rows_per_chunk, r1 = r0 + rows_per_chunk < rows ? r0 + rows_per_chunk : rows;
+    T acc = T(0);
+    if (c < cols)
+        for (int64_t r = r0 + ty; r < r1; r += 8) acc += x[r * cols + c];
+    smem[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0 && c < cols) {
+        T t = T(0);
+        for (int i = 0; i < 8; i++) t += smem[i][tx];
+        partial[(int64_t)blockIdx.y * cols + c] = t;
+    }
+}
+template <class T>
+__global__ void col_sums_stage2(const T* __restrict__ partial, int chunks, int64_t cols, T* __restrict__ out) {
+    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    T t = T(0);
+    for (int i = 0; i < chunks; i++) t += partial[(int64_t)i * cols + c];
+    out[c] = t;
+}
+
+template <class T>
+__global__ void __launch_bounds__(256) row_sums_kernel(const T* __restrict__ x, int64_t rows, int64_t cols, T* __restrict__ out) {
+    int lane = threadIdx.x & 31;
+    int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= rows) return;
+    T acc = T(0);
+    for (int64_t c = lane; c < cols; c += 32) acc += x[r * cols + c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[r] = acc;
+}
+
+// ---- generic two-operand einsum (bit-exact with the reference's loop nest) ----
+constexpr int MAX_OUT = 6, MAX_SUM = 12;
+struct EinsumParams {
+    int n_out, n_sum;
+    int64_t total;
+    int64_t out_len[MAX_OUT], a_out[MAX_OUT], b_out[MAX_OUT];
+    int64_t sum_len[MAX_SUM], a_sum[MAX_SUM], b_sum[MAX_SUM];
+    int64_t sum_total;
+};
+
+template <class T>
+__global__ void __launch_bounds__(256) einsum2_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ out, EinsumParams p) {
+    for (int64_t flat = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; flat < p.total;
+         flat += (int64_t)gridDim.x * blockDim.x) {
+        int64_t rem = flat, a_off = 0, b_off = 0;
+        for (int d = p.n_out - 1; d >= 0; d--) {
+            int64_t i = rem % p.out_len[d];
+            rem /= p.out_len[d];
+            a_off += i * p.a_out[d];
+            b_off += i * p.b_out[d];
+        }
+        T sum = T(0);  // reference src/tensors/einsum.rs:932
+        if (p.n_sum == 0) {
+            sum = sum + A[a_off] * B[b_off];  // :945 (fmad off: separate roundings)
+        } else {
+            int64_t idx[MAX_SUM];
+            for (int d = 0; d < p.n_sum; d++) idx[d] = 0;
+            for (int64_t s = 0; s < p.sum_total; s++) {
+                sum = sum + A[a_off] * B[b_off];  // :968
+                // odometer, last dimension fastest (reference src/tensors/indexing.rs:905-925)
+                for (int d = p.n_sum - 1; d >= 0; d--) {
+                    a_off += p.a_sum[d];
+                    b_off += p.b_sum[d];
+                    if (++idx[d] < p.sum_len[d]) break;
+                    a_off -= p.a_sum[d] * p.sum_len[d];
+                    b_off -= p.b_sum[d] * p.sum_len[d];
+                    idx[d] = 0;
+                }
+            }
+        }
+        out[flat] = sum;
+    }
+}
+
+template <class T, int OP>
+int launch_unary_op(T c, const T* x, T* y, T* dydx, int64_t n, cudaStream_t stream) {
+    bool vec = aligned16(x) && (!y || aligned16(y)) && (!dydx || aligned16(dydx));
+    if (vec)
+        unary_kernel<T, OP, true><<<ew_grid(n, Vec<T>::N), EW_THREADS, 0, stream>>>(c, x, y, dydx, n);
+    else
+        unary_kernel<T, OP, false><<<ew_grid(n, 1), EW_THREADS, 0, stream>>>(c, x, y, dydx, n);
+    count_launch();
+    return check_launch("unary");
+}
+
+template <class T, int OP>
+int launch_binary_op(const T* x, const T* y, T* z, T* dzdx, T* dzdy, int64_t n, cudaStream_t stream) {
+    bool vec = aligned16(x) && aligned16(y) && (!z || aligned16(z)) && (!dzdx || aligned16(dzdx)) &&
+               (!dzdy || aligned16(dzdy));
+    if (vec)
+        binary_kernel<T, OP, true><<<ew_grid(n, Vec<T>::N), EW_THREADS, 0, stream>>>(x, y, z, dzdx, dzdy, n);
+    else
+        binary_kernel<T, OP, false><<<ew_grid(n, 1), EW_THREADS, 0, stream>>>(x, y, z, dzdx, dzdy, n);
+    count_launch();
+    return check_launch("binary");
+}
+
+template <class T, int MODE>
+int launch_axpy(T c, const T* a, const T* b, T* out, int64_t n, cudaStream_t stream) {
+    if (n <= 0) return EML_OK;
+    bool vec = aligned16(out) && (!a || aligned16(a)) && (!b || aligned16(b));
+    if (vec)
+        axpy_kernel<T, MODE, true><<<ew_grid(n, Vec<T>::N), EW_THREADS, 0, stream>>>(c, a, b, out, n);
+    else
+        axpy_kernel<T, MODE, false><<<ew_grid(n, 1), EW_THREADS, 0, stream>>>(c, a, b, out, n);
+    count_launch();
+    return check_launch("axpy");
+}
+
+}  // namespace
+
+template <class T>
+int launch_unary(int op, T c, const T* x, T* y, T* dydx, int64_t n, cudaStream_t stream) {
+    if (n <= 0) return EML_OK;
+    switch (op) {
+#define EML_U(OP) \
+    case OP:      \
+        return launch_unary_op<T, OP>(c, x, y, dydx, n, stream);
+        EML_U(EML_OP_NEG) EML_U(EML_OP_SIN) EML_U(EML_OP_COS) EML_U(EML_OP_EXP) EML_U(EML_OP_LN)
+        EML_U(EML_OP_SQRT) EML_U(EML_OP_ADD_C) EML_U(EML_OP_SUB_C) EML_U(EML_OP_MUL_C) EML_U(EML_OP_DIV_C)
+        EML_U(EML_OP_POW_C) EML_U(EML_OP_C_SUB) EML_U(EML_OP_C_DIV) EML_U(EML_OP_C_POW)
+#undef EML_U
+        default:
+            EML_BAD_ARG("unknown unary op %d", op);
+    }
+}
+
+template <class T>
+int launch_binary(int op, const T* x, const T* y, T* z, T* dzdx, T* dzdy, int64_t n, cudaStream_t stream) {
+    if (n <= 0) return EML_OK;
+    switch (op) {
+#define EML_B(OP) \
+    case OP:      \
+        return launch_binary_op<T, OP>(x, y, z, dzdx, dzdy, n, stream);
+        EML_B(EML_OP_ADD) EML_B(EML_OP_SUB) EML_B(EML_OP_MUL) EML_B(EML_OP_DIV) EML_B(EML_OP_POW)
+#undef EML_B
+        default:
+            EML_BAD_ARG("unknown binary op %d", op);
+    }
+}
+
+template <class T>
+int launch_chain(const T* dout, const T* deriv, T* dparent, int64_t n, cudaStream_t stream) {
+    return launch_axpy<T, 0>(T(0), dout, deriv, dparent, n, stream);
+}
+template <class T>
+int launch_sgd(T* w, const T* d, T lr, int64_t n, cudaStream_t stream) {
+    return launch_axpy<T, 1>(lr, d, nullptr, w, n, stream);
+}
+template <class T>
+int launch_fill(T* out, T value, int64_t n, cudaStream_t stream) {
+    return launch_axpy<T, 2>(value, nullptr, nullptr, out, n, stream);
+}
+template <class T>
+int launch_add_inplace(T* dst, const T* src, int64_t n, cudaStream_t stream) {
+    return launch_axpy<T, 3>(T(0), src, nullptr, dst, n, stream);
+}
+
+template <class T>
+int launch_dot(const T* x, int64_t incx, const T* y, int64_t incy, int64_t n, T* out_dev, cudaStream_t stream) {
+    return reduce_impl<T>(x, incx, y, incy, n, out_dev, false, stream);
+}
+template <class T>
+int launch_reduce_sum(DeviceCtx*, const T* x, int64_t n, T* out, bool accumulate, cudaStream_t stream) {
+    return reduce_impl<T>(x, 1, nullptr, 0, n, out, accumulate, stream);
+}
+template <class T>
+int launch_dot_accumulate(DeviceCtx*, const T* x, const T* y, int64_t n, T* out, bool accumulate,
+                          cudaStream_t stream) {
+    return reduce_impl<T>(x, 1, y, 1, n, out, accumulate, stream);
+}
+
+template <class T>
+int launch_col_sums(const T* x, int64_t rows, int64_t cols, T* out, cudaStream_t stream) {
+    int chunks = (int)((rows + 255) / 256);
+    if (chunks > 128) chunks = 128;
+    if (chunks < 1) chunks = 1;
+    int64_t rpc = (rows + chunks - 1) / chunks;
+    TempBuf partial;
+    EML_TRY(partial.alloc(sizeof(T) * chunks * cols, stream));
+    dim3 grid((unsigned)((cols + 31) / 32), (unsigned)chunks);
+    col_sums_stage1<T><<<grid, 256, 0, stream>>>(x, rows, cols, rpc, partial.as<T>());
+    col_sums_stage2<T><<<(unsigned)((cols + 127) / 128), 128, 0, stream>>>(partial.as<T>(), chunks, cols, out);
+    count_launch(2);
+    return check_launch("col_sums");
+}
+
+template <class T>
+int launch_row_sums(const T* x, int64_t rows, int64_t cols, T* out, cudaStream_t stream) {
+    row_sums_kernel<T><<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(x, rows, cols, out);
+    count_launch();
+    return check_launch("row_sums");
+}
+
+template <class T>
+int launch_einsum2(const T* A, const T* B, T* out, int n_out, const int64_t* out_len, const int64_t* a_out_stride,
+                   const int64_t* b_out_stride, int n_sum, const int64_t* sum_len, const int64_t* a_sum_stride,
+                   const int64_t* b_sum_stride, cudaStream_t stream) {
+    if (n_out < 0 || n_out > MAX_OUT || n_sum < 0 || n_sum > MAX_SUM)
+        EML_BAD_ARG("einsum2: n_out=%d (max %d) n_sum=%d (max %d)", n_out, MAX_OUT, n_sum, MAX_SUM);
+    EinsumParams p{};
+    p.n_out = n_out;
+    p.n_sum = n_sum;
+    p.total = 1;
+    for (int d = 0; d < n_out; d++) {
+        if (out_len[d] < 0) EML_BAD_ARG("einsum2: negative length");
+        p.out_len[d] = out_len[d];
+        p.a_out[d] = a_out_stride[d];
+        p.b_out[d] = b_out_stride[d];
+        p.total *= out_len[d];
+    }
+    p.sum_total = 1;
+    for (int d = 0; d < n_sum; d++) {
+        if (sum_len[d] < 0) EML_BAD_ARG("einsum2: negative length");
+        p.sum_len[d] = sum_len[d];
+        p.a_sum[d] = a_sum_stride[d];
+        p.b_sum[d] = b_sum_stride[d];
+        p.sum_total *= sum_len[d];
+    }
+    if (p.total == 0) return EML_OK;
+    int64_t blocks = (p.total + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    einsum2_kernel<T><<<(unsigned)blocks, 256, 0, stream>>>(A, B, out, p);
+    count_launch();
+    set_last_kernel("einsum_generic");
+    return check_launch("einsum2");
+}
+
+#define EML_INST(T)                                                                                              \
+    template int launch_unary<T>(int, T, const T*, T*, T*, int64_t, cudaStream_t);                               \
+    template int launch_binary<T>(int, const T*, const T*, T*, T*, T*, int64_t, cudaStream_t);                   \
+    template int launch_chain<T>(const T*, const T*, T*, int64_t, cudaStream_t);                                 \
+    template int launch_sgd<T>(T*, const T*, T, int64_t, cudaStream_t);                                          \
+    template int launch_fill<T>(T*, T, int64_t, cudaStream_t);                                                   \
+    template int launch_add_inplace<T>(T*, const T*, int64_t, cudaStream_t);                                     \
+    template int launch_dot<T>(const T*, int64_t, const T*, int64_t, int64_t, T*, cudaStream_t);                 \
+    template int launch_reduce_sum<T>(DeviceCtx*, const T*, int64_t, T*, bool, cudaStream_t);                    \
+    template int launch_dot_accumulate<T>(DeviceCtx*, const T*, const T*, int64_t, T*, bool, cudaStream_t);      \
+    template int launch_col_sums<T>(const T*, int64_t, int64_t, T*, cudaStream_t);                               \
+    template int launch_row_sums<T>(const T*, int64_t, int64_t, T*, cudaStream_t);                               \
+    template int launch_einsum2<T>(const T*, const T*, T*, int, const int64_t*, const int64_t*, const int64_t*,  \
+                                   int, const int64_t*, const int64_t*, const int64_t*, cudaStream_t);
+EML_INST(float)
+EML_INST(double)
+#undef EML_INST
+
+}  // namespace eml

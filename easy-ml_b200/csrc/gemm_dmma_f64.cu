@@ -1,0 +1,257 @@
+// gemm_dmma_f64.cu -- f64 GEMM on the FP64 tensor pipe (DMMA.8x8x4) for sm_100a.
+//
+// tcgen05 has no f64 kind, so FP64 tensor math on Blackwell is the warp-level
+// `mma.sync.aligned.m8n8k4.f64` (every larger PTX f64 shape lowers to DMMA.8x8x4 SASS on sm_100a --
+// checked with cuobjdump).  Accumulators live in registers (no TMEM for f64).
+//
+// Tiling: CTA 128x128x16, 8 warps as 2(M) x 4(N), warp tile 64x32 = 8x4 DMMA fragments, 64 f64
+// accumulators per thread.  4-stage cp.async ring in shared memory (160 KB), one CTA per SM.
+// Shared layouts are padded so every fragment load (LDS.64) is bank-conflict free:
+//   K-inner  tile[mn][k]  pitch 20 doubles  (operand whose k index is contiguous in memory)
+//   MN-inner tile[k][mn]  pitch 132 doubles (operand whose m / n index is contiguous in memory)
+// so row-major A (K-inner) x row-major B (MN-inner) and all transposed combinations run without a
+// pack pass -- the backward products dA = dC * B^T and dB = A^T * dC use the same kernel.
+//
+// Determinism: fixed tile -> CTA map, k tiles consumed in ascending order, no atomics, no split-K.
+//
+// Algorithmic work per launch: 2*M*N*K flop; (M*K + K*N + M*N) * 8 bytes.
+#include "common.h"
+
+namespace eml {
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 16, STAGES = 4, THREADS = 256;
+constexpr int KIN_PITCH = BK + 4;    // 20
+constexpr int MNIN_PITCH = BM + 4;   // 132 (BM == BN)
+constexpr int OPERAND_ELEMS = BM * KIN_PITCH > BK * MNIN_PITCH ? BM * KIN_PITCH : BK * MNIN_PITCH;  // 2560
+constexpr int STAGE_ELEMS = 2 * OPERAND_ELEMS;
+constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_ELEMS * sizeof(double);  // 163840
+
+__device__ __forceinline__ void cp_async_16(void* smem, const void* gmem, int src_bytes) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_8(void* smem, const void* gmem, int src_bytes) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// Copies one operand tile into shared memory.
+//   KIN:  tile[mn][k], global element (mn, k) at g[mn*ld_mn + k]          (k contiguous)
+//   !KIN: tile[k][mn], global element (mn, k) at g[k*ld_k + mn]           (mn contiguous)
+// `ld` is the stride of the non-contiguous index.  Out-of-range elements are zero-filled.
+template <bool KIN, int VEC>
+__device__ __forceinline__ void load_tile(double* smem, const double* __restrict__ g, int64_t ld, int64_t mn0,
+                                          int64_t mn_extent, int64_t k0, int64_t k_extent, int tid) {
+    if (KIN) {
+        constexpr int CH_PER_ROW = BK / VEC;  // chunks along k per mn row
+        constexpr int ITERS = BM * CH_PER_ROW / THREADS;
+#pragma unroll
+        for (int i = 0; i < ITERS; i++) {
+            int c = tid + i * THREADS;
+            int row = c / CH_PER_ROW, kc = (c % CH_PER_ROW) * VEC;
+            int64_t gm = mn0 + row, gk = k0 + kc;
+            int64_t left = k_extent - gk;
+            int valid = (gm < mn_extent && left > 0) ? (left >= VEC ? VEC : (int)left) : 0;
+            const double* src = valid ? g + gm * ld + gk : g;
+            double* dst = smem + row * KIN_PITCH + kc;
+            if (VEC == 2)
+                cp_async_16(dst, src, valid * 8);
+            else
+                cp_async_8(dst, src, valid * 8);
+        }
+    } else {
+        constexpr int CH_PER_ROW = BM / VEC;  // chunks along mn per k row
+        constexpr int ITERS = BK * CH_PER_ROW / THREADS;
+#pragma unroll
+        for (int i = 0; i < ITERS; i++) {
+            int c = tid + i * THREADS;
+            int k = c / CH_PER_ROW, mc = (c % CH_PER_ROW) * VEC;
+            int64_t gk = k0 + k, gm = mn0 + mc;
+            int64_t left = mn_extent - gm;
+            int valid = (gk < k_extent && left > 0) ? (left >= VEC ? VEC : (int)left) : 0;
+            const double* src = valid ? g + gk * ld + gm : g;
+            double* dst = smem + k * MNIN_PITCH + mc;
+            if (VEC == 2)
+                cp_async_16(dst, src, valid * 8);
+            else
+                cp_async_8(dst, src, valid * 8);
+        }
+    }
+}
+
+template <bool A_KIN, bool B_KIN, int VEC>
+__global__ void __launch_bounds__(THREADS, 1)
+dgemm_dmma_kernel(const double* __restrict__ A, const double* __restrict__ B, double* C, int64_t M,
+                  int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int64_t strideA, int64_t strideB,
+                  int64_t strideC, int tiles_m, int tiles_n, int accumulate) {
+    extern __shared__ __align__(16) double smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = (warp >> 2) * 64, wn = (warp & 3) * 32;
+
+    // tile raster: groups of 8 tile rows walked column by column keep a wave's A/B panels L2-resident
+    constexpr int GROUP = 8;
+    int tile = blockIdx.x;
+    int tiles_per_group = GROUP * tiles_n;
+    int group = tile / tiles_per_group;
+    int first_m = group * GROUP;
+    int group_rows = tiles_m - first_m < GROUP ? tiles_m - first_m : GROUP;
+    int in_group = tile % tiles_per_group;
+    int tm = first_m + in_group % group_rows;
+    int tn = in_group / group_rows;
+    const int64_t m0 = (int64_t)tm * BM, n0 = (int64_t)tn * BN;
+
+    const int64_t batch = blockIdx.y;
+    A += batch * strideA;
+    B += batch * strideB;
+    C += batch * strideC;
+
+    // accumulate: the accumulators START from C, so a K-split sequence of launches continues one
+    // k-ordered chain per element and produces the same bits as a single launch over the whole K
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            acc[i][j][0] = acc[i][j][1] = 0.0;
+            if (accumulate) {
+                int64_t row = m0 + wm + i * 8 + g, col = n0 + wn + j * 8 + 2 * t;
+                if (row < M && col < N) acc[i][j][0] = C[row * ldc + col];
+                if (row < M && col + 1 < N) acc[i][j][1] = C[row * ldc + col + 1];
+            }
+        }
+
+    const int ktiles = (int)((K + BK - 1) / BK);
+
+    auto issue = [&](int kt) {
+        if (kt < ktiles) {
+            double* sA = smem + (size_t)(kt % STAGES) * STAGE_ELEMS;
+            double* sB = sA + OPERAND_ELEMS;
+            load_tile<A_KIN, VEC>(sA, A, lda, m0, M, (int64_t)kt * BK, K, tid);
+            load_tile<B_KIN, VEC>(sB, B, ldb, n0, N, (int64_t)kt * BK, K, tid);
+        }
+        cp_async_commit();
+    };
+
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; s++) issue(s);
+
+    for (int kt = 0; kt < ktiles; kt++) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        issue(kt + STAGES - 1);  // refills the slot consumed in iteration kt-1
+
+        const double* sA = smem + (size_t)(kt % STAGES) * STAGE_ELEMS;
+        const double* sB = sA + OPERAND_ELEMS;
+#pragma unroll
+        for (int ks = 0; ks < BK / 4; ks++) {
+            double a[8], b[4];
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                a[i] = A_KIN ? sA[(wm + i * 8 + g) * KIN_PITCH + ks * 4 + t]
+                             : sA[(ks * 4 + t) * MNIN_PITCH + wm + i * 8 + g];
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                b[j] = B_KIN ? sB[(wn + j * 8 + g) * KIN_PITCH + ks * 4 + t]
+                             : sB[(ks * 4 + t) * MNIN_PITCH + wn + j * 8 + g];
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+    }
+    cp_async_wait<0>();
+
+    // epilogue: each thread owns 2 adjacent columns per fragment -> 16-byte stores when aligned
+    const bool vec_ok = ((ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        int64_t row = m0 + wm + i * 8 + g;
+        if (row >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            int64_t col = n0 + wn + j * 8 + 2 * t;
+            if (col >= N) continue;
+            double* p = C + row * ldc + col;
+            if (vec_ok && col + 1 < N) {
+                *reinterpret_cast<double2*>(p) = make_double2(acc[i][j][0], acc[i][j][1]);
+            } else {
+                p[0] = acc[i][j][0];
+                if (col + 1 < N) p[1] = acc[i][j][1];
+            }
+        }
+    }
+}
+
+template <bool A_KIN, bool B_KIN, int VEC>
+int launch_variant(const double* A, const double* B, double* C, int64_t batch, int64_t M, int64_t N, int64_t K,
+                   int64_t lda, int64_t ldb, int64_t ldc, int64_t stA, int64_t stB, int64_t stC, bool accumulate,
+                   cudaStream_t stream) {
+    auto kern = dgemm_dmma_kernel<A_KIN, B_KIN, VEC>;
+    static thread_local int configured_dev = -1;
+    int dev = 0;
+    EML_CUDA(cudaGetDevice(&dev));
+    if (configured_dev != dev) {
+        EML_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        configured_dev = dev;
+    }
+    int64_t tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
+    if (tiles_m * tiles_n > 0x7fffffffLL || batch > 65535) EML_BAD_ARG("dgemm_dmma: grid too large");
+    dim3 grid((unsigned)(tiles_m * tiles_n), (unsigned)batch);
+    kern<<<grid, THREADS, SMEM_BYTES, stream>>>(A, B, C, M, N, K, lda, ldb, ldc, stA, stB, stC, (int)tiles_m,
+                                                (int)tiles_n, accumulate ? 1 : 0);
+    count_launch();
+    set_last_kernel("dmma_f64");
+    return check_launch("dgemm_dmma");
+}
+
+inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+
+int launch_gemm_dmma_f64(DeviceCtx*, const double* A, const double* B, double* C, int64_t batch, int64_t M,
+                         int64_t N, int64_t K, Strides3 sA, Strides3 sB, Strides3 sC, bool accumulate,
+                         cudaStream_t stream, bool* handled) {
+    *handled = false;
+    if (batch == 0 || M == 0 || N == 0) {
+        *handled = true;
+        return EML_OK;
+    }
+    // needs unit stride on one index of each operand and on C's column index; batch fits gridDim.y
+    bool a_kin = sA.c == 1, a_min = sA.r == 1;
+    bool b_nin = sB.c == 1, b_kin = sB.r == 1;
+    if (!(a_kin || a_min) || !(b_nin || b_kin) || sC.c != 1 || batch > 65535) return EML_OK;
+    // degenerate extents make both strides "1"-compatible; prefer the natural row-major reading
+    bool A_KIN = a_kin;
+    bool B_KIN = !b_nin;
+    int64_t lda = A_KIN ? sA.r : sA.c;
+    int64_t ldb = B_KIN ? sB.c : sB.r;
+    int64_t ldc = sC.r;
+    bool vec = al16(A) && al16(B) && (lda % 2 == 0) && (ldb % 2 == 0) && (sA.b % 2 == 0) && (sB.b % 2 == 0);
+    *handled = true;
+#define EML_D(AK, BKK)                                                                                           \
+    return vec ? launch_variant<AK, BKK, 2>(A, B, C, batch, M, N, K, lda, ldb, ldc, sA.b, sB.b, sC.b, accumulate, \
+                                            stream)                                                              \
+               : launch_variant<AK, BKK, 1>(A, B, C, batch, M, N, K, lda, ldb, ldc, sA.b, sB.b, sC.b, accumulate, \
+                                            stream);
+    if (A_KIN && !B_KIN) { EML_D(true, false) }
+    if (A_KIN && B_KIN) { EML_D(true, true) }
+    if (!A_KIN && !B_KIN) { EML_D(false, false) }
+    EML_D(false, true)
+#undef EML_D
+}
+
+}  // namespace eml

@@ -1,0 +1,157 @@
+// gemm_simt.cu -- general strided batched GEMM on the FMA pipes.
+//
+// Role: the any-layout, any-shape kernel (ragged edges, odd strides, skinny outputs such as N = 10)
+// and the bit-exact mode.  The large contiguous cases go to the tensor-core kernels
+// (gemm_dmma_f64.cu, gemm_tf32x3.cu); this one is never the benchmark's dominant kernel.
+//
+// EXACT = the reference's operation order for one output element (scalar_product,
+// reference src/tensors/operations.rs:441-445): first product seeds the sum, then k ascending with a
+// separately rounded multiply and add -- no FMA.  k tiles are walked in ascending order, so the chain
+// per element is exactly the sequential one.
+#include "common.h"
+
+namespace eml {
+
+namespace {
+
+template <class T>
+__device__ __forceinline__ T mul_rn(T a, T b);
+template <>
+__device__ __forceinline__ float mul_rn<float>(float a, float b) { return __fmul_rn(a, b); }
+template <>
+__device__ __forceinline__ double mul_rn<double>(double a, double b) { return __dmul_rn(a, b); }
+template <class T>
+__device__ __forceinline__ T add_rn(T a, T b);
+template <>
+__device__ __forceinline__ float add_rn<float>(float a, float b) { return __fadd_rn(a, b); }
+template <>
+__device__ __forceinline__ double add_rn<double>(double a, double b) { return __dadd_rn(a, b); }
+
+constexpr int BM = 64, BN = 64, BK = 16, PAD = 4, THREADS = 256;
+
+template <class T, bool EXACT>
+__global__ void __launch_bounds__(THREADS)
+gemm_simt_kernel(const T* __restrict__ A, const T* __restrict__ B, T* C, int64_t batch, int64_t M,
+                 int64_t N, int64_t K, Strides3 sA, Strides3 sB, Strides3 sC, int accumulate, int64_t tiles_n) {
+    __shared__ T As[BK][BM + PAD];
+    __shared__ T Bs[BK][BN + PAD];
+    const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+    const int64_t tile = blockIdx.x;
+    const int64_t m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+    const bool a_kfast = (sA.c == 1), b_nfast = (sB.c == 1);
+
+    for (int64_t b = blockIdx.y; b < batch; b += gridDim.y) {
+        const T* Ab = A + b * sA.b;
+        const T* Bb = B + b * sB.b;
+        T* Cb = C + b * sC.b;
+        // accumulate: start the chain from C (a K-split sequence of launches == one launch, bit for bit)
+        T acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                int64_t gm = m0 + ty * 4 + i, gn = n0 + tx * 4 + j;
+                acc[i][j] = (accumulate && gm < M && gn < N) ? Cb[gm * sC.r + gn * sC.c] : T(0);
+            }
+
+        for (int64_t k0 = 0; k0 < K; k0 += BK) {
+#pragma unroll
+            for (int i = 0; i < (BM * BK) / THREADS; i++) {
+                int e = tid + i * THREADS;
+                int m = a_kfast ? e / BK : e % BM;
+                int k = a_kfast ? e % BK : e / BM;
+                int64_t gm = m0 + m, gk = k0 + k;
+                As[k][m] = (gm < M && gk < K) ? Ab[gm * sA.r + gk * sA.c] : T(0);
+            }
+#pragma unroll
+            for (int i = 0; i < (BN * BK) / THREADS; i++) {
+                int e = tid + i * THREADS;
+                int n = b_nfast ? e % BN : e / BK;
+                int k = b_nfast ? e / BN : e % BK;
+                int64_t gn = n0 + n, gk = k0 + k;
+                Bs[k][n] = (gn < N && gk < K) ? Bb[gk * sB.r + gn * sB.c] : T(0);
+            }
+            __syncthreads();
+            const int kmax = (K - k0) < BK ? int(K - k0) : BK;
+            if (kmax == BK) {
+#pragma unroll
+                for (int k = 0; k < BK; k++) {
+                    T a[4], bb[4];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) a[i] = As[k][ty * 4 + i];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) bb[j] = Bs[k][tx * 4 + j];
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            if (EXACT) {
+                                T p = mul_rn<T>(a[i], bb[j]);
+                                acc[i][j] = (k0 == 0 && k == 0) ? p : add_rn<T>(acc[i][j], p);
+                            } else {
+                                acc[i][j] = fma(a[i], bb[j], acc[i][j]);
+                            }
+                        }
+                }
+            } else {
+                for (int k = 0; k < kmax; k++) {
+                    T a[4], bb[4];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) a[i] = As[k][ty * 4 + i];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) bb[j] = Bs[k][tx * 4 + j];
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            if (EXACT) {
+                                T p = mul_rn<T>(a[i], bb[j]);
+                                acc[i][j] = (k0 == 0 && k == 0) ? p : add_rn<T>(acc[i][j], p);
+                            } else {
+                                acc[i][j] = fma(a[i], bb[j], acc[i][j]);
+                            }
+                        }
+                }
+            }
+            __syncthreads();
+        }
+
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            int64_t gm = m0 + ty * 4 + i;
+            if (gm >= M) continue;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                int64_t gn = n0 + tx * 4 + j;
+                if (gn >= N) continue;
+                Cb[gm * sC.r + gn * sC.c] = acc[i][j];
+            }
+        }
+    }
+}
+
+}  // namespace
+
+template <class T>
+int launch_gemm_simt(const T* A, const T* B, T* C, int64_t batch, int64_t M, int64_t N, int64_t K, Strides3 sA,
+                     Strides3 sB, Strides3 sC, bool accumulate, bool exact, cudaStream_t stream) {
+    if (batch == 0 || M == 0 || N == 0) return EML_OK;
+    int64_t tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
+    if (tiles_m * tiles_n > 0x7fffffffLL) EML_BAD_ARG("gemm_simt: too many tiles");
+    dim3 grid((unsigned)(tiles_m * tiles_n), (unsigned)(batch < 65535 ? batch : 65535));
+    if (exact)
+        gemm_simt_kernel<T, true><<<grid, THREADS, 0, stream>>>(A, B, C, batch, M, N, K, sA, sB, sC, 0, tiles_n);
+    else
+        gemm_simt_kernel<T, false>
+            <<<grid, THREADS, 0, stream>>>(A, B, C, batch, M, N, K, sA, sB, sC, accumulate ? 1 : 0, tiles_n);
+    count_launch();
+    set_last_kernel(exact ? "simt_exact" : "simt");
+    return check_launch("gemm_simt");
+}
+
+template int launch_gemm_simt<float>(const float*, const float*, float*, int64_t, int64_t, int64_t, int64_t,
+                                     Strides3, Strides3, Strides3, bool, bool, cudaStream_t);
+template int launch_gemm_simt<double>(const double*, const double*, double*, int64_t, int64_t, int64_t, int64_t,
+                                      Strides3, Strides3, Strides3, bool, bool, cudaStream_t);
+
+}  // namespace eml

@@ -1,0 +1,721 @@
+// tape.cu -- device-resident reverse-mode tape behind RecordTensor / RecordMatrix / WengertList.
+//
+// The reference tape is scalar-granular: a tracked M x K by K x N matmul appends M*N*(2K-1) `Operation`s
+// (record_scalar_product, reference src/differentiation/container_record/container_operations.rs:1263-1315);
+// at the benchmark's NN shape that is 158 GB.  Here a matmul, a container unary op and a container
+// binary op are ONE macro node each.  The node remembers which range of reference tape indexes it stands
+// for, so tape length, every element's Index and every derivative the reverse sweep
+// (Record::try_derivatives, reference src/differentiation.rs:623-648) would produce are reproduced,
+// without the entries ever existing.  Sweep of a matmul node = two GEMMs; of an elementwise node = one
+// fused multiply-accumulate pass.
+#include <algorithm>
+#include <memory>
+#include <vector>
+
+#include "common.h"
+
+namespace eml {
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    cudaStream_t s = nullptr;
+    ~DevBuf() {
+        if (p) cudaFreeAsync(p, s);
+    }
+};
+using Buf = std::shared_ptr<DevBuf>;
+
+int new_buf(size_t bytes, cudaStream_t s, Buf* out) {
+    auto b = std::make_shared<DevBuf>();
+    b->s = s;
+    b->bytes = bytes;
+    EML_CUDA(cudaMallocAsync(&b->p, bytes ? bytes : 16, s));
+    *out = b;
+    return EML_OK;
+}
+
+enum class Kind { VARIABLES, UNARY, BINARY, MATMUL };
+
+// A record container: numbers on the device + how its elements map to tape indexes.
+struct Value {
+    Buf numbers;
+    int64_t rows = 0, cols = 0;
+    bool tracked = false;  // history.is_some()
+    int node = -1;         // producing node in the CURRENT epoch; -1: every Index is 0 (constants)
+    uint64_t epoch = 0;    // tape epoch the node id belongs to
+    bool alive = false;
+    int64_t n() const { return rows * cols; }
+};
+
+struct Node {
+    Kind kind;
+    int64_t base = 0;   // first reference tape index this node stands for
+    int64_t count = 0;  // how many reference entries
+    int64_t n = 0;      // elements of the produced container
+    int64_t M = 0, N = 0, K = 0;
+    // parents: node ids (-1 = Index 0 everywhere) and whether that side takes part in the sweep
+    int p0 = -1, p1 = -1;
+    bool p0_tracked = false, p1_tracked = false;
+    Buf a, b;  // matmul: parent numbers A, B.  unary: a = dy/dx.  binary: a = dz/dx, b = dz/dy.
+    // index of element e of the produced container on the reference tape
+    int64_t index_of(int64_t e) const {
+        if (kind == Kind::MATMUL && K > 1) return base + e * (2 * K - 1) + 2 * K - 2;
+        return base + e;
+    }
+    // produced element whose derivative reference entry `index` carries (interior matmul entries carry
+    // the derivative of their output element: the adds propagate it unchanged to every entry of the chain)
+    int64_t element_of(int64_t index) const {
+        if (kind == Kind::MATMUL && K > 1) return (index - base) / (2 * K - 1);
+        return index - base;
+    }
+};
+
+}  // namespace
+
+}  // namespace eml
+
+using namespace eml;
+
+struct eml_derivs {
+    eml_tape* tape = nullptr;  // the tape must outlive its derivatives objects
+    int dtype = EML_F32;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int64_t len = 0;
+    uint64_t epoch = 0;
+    std::vector<Node> nodes;  // copies of the metadata (buffers shared)
+    std::vector<Buf> grads;   // per node, n elements
+};
+
+struct eml_tape {
+    int dtype = EML_F32;
+    int device = 0;
+    DeviceCtx* ctx = nullptr;
+    cudaStream_t stream = nullptr;
+    int64_t len = 0;
+    uint64_t epoch = 1;
+    std::vector<Node> nodes;
+    std::vector<Value> values;
+    std::vector<eml_val> free_slots;
+    std::mutex mu;
+};
+
+namespace eml {
+namespace {
+
+size_t esize(int dtype) { return dtype == EML_F32 ? 4 : 8; }
+
+int check_tape(eml_tape* t) {
+    if (!t) EML_BAD_ARG("null tape");
+    int dev = -1;
+    EML_CUDA(cudaGetDevice(&dev));
+    if (dev != t->device) EML_CUDA(cudaSetDevice(t->device));
+    return EML_OK;
+}
+
+int get_value(eml_tape* t, eml_val v, Value** out) {
+    if (v < 0 || v >= (eml_val)t->values.size() || !t->values[v].alive) EML_BAD_ARG("invalid container handle %lld", (long long)v);
+    *out = &t->values[v];
+    return EML_OK;
+}
+
+eml_val put_value(eml_tape* t, Value&& val) {
+    val.alive = true;
+    if (!t->free_slots.empty()) {
+        eml_val h = t->free_slots.back();
+        t->free_slots.pop_back();
+        t->values[h] = std::move(val);
+        return h;
+    }
+    t->values.push_back(std::move(val));
+    return (eml_val)t->values.size() - 1;
+}
+
+// node id usable in the current epoch, or -1.  A tracked container from before the last clear() that was
+// not reset is the reference's "stale Record": its indexes point at entries that no longer exist.
+int live_node(eml_tape* t, const Value& v, bool* stale) {
+    *stale = false;
+    if (v.node < 0) return -1;
+    if (v.epoch != t->epoch) {
+        *stale = true;
+        return -1;
+    }
+    return v.node;
+}
+
+template <class T>
+int new_container(eml_tape* t, const void* src, bool src_on_device, int64_t rows, int64_t cols, bool variables,
+                  eml_val* out) {
+    if (rows < 1 || cols < 1) EML_BAD_ARG("container shape %lldx%lld: Easy ML containers have at least one element",
+                                          (long long)rows, (long long)cols);
+    if (!src || !out) EML_BAD_ARG("null argument");
+    Value v;
+    v.rows = rows;
+    v.cols = cols;
+    EML_TRY(new_buf(sizeof(T) * rows * cols, t->stream, &v.numbers));
+    EML_CUDA(cudaMemcpyAsync(v.numbers->p, src, sizeof(T) * rows * cols,
+                             src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, t->stream));
+    if (!src_on_device) EML_CUDA(cudaStreamSynchronize(t->stream));  // the host buffer is the caller's
+    if (variables) {
+        Node nd;
+        nd.kind = Kind::VARIABLES;
+        nd.base = t->len;  // append_nullary_repeating: starting_index = operations.len()
+        nd.count = nd.n = rows * cols;
+        t->len += nd.count;
+        t->nodes.push_back(nd);
+        v.tracked = true;
+        v.node = (int)t->nodes.size() - 1;
+        v.epoch = t->epoch;
+    }
+    *out = put_value(t, std::move(v));
+    return EML_OK;
+}
+
+template <class T>
+int tape_matmul(eml_tape* t, eml_val ha, eml_val hb, eml_val* out) {
+    Value *a, *b;
+    EML_TRY(get_value(t, ha, &a));
+    EML_TRY(get_value(t, hb, &b));
+    if (a->cols != b->rows)
+        EML_BAD_ARG("Mismatched Matrices, left is %lldx%lld, right is %lldx%lld, * is only defined for MxN * NxL",
+                    (long long)a->rows, (long long)a->cols, (long long)b->rows, (long long)b->cols);
+    bool sa, sb;
+    int na = live_node(t, *a, &sa), nb = live_node(t, *b, &sb);
+    if (sa || sb) {
+        set_error("container was not reset after WengertList::clear(); its indexes are stale");
+        return EML_ERR_STATE;
+    }
+    const int64_t M = a->rows, K = a->cols, N = b->cols;
+    Value c;
+    c.rows = M;
+    c.cols = N;
+    EML_TRY(new_buf(sizeof(T) * M * N, t->stream, &c.numbers));
+    EML_TRY(contract_dev<T>(t->ctx, (const T*)a->numbers->p, (const T*)b->numbers->p, (T*)c.numbers->p, 1, M, N, K,
+                            Strides3{0, K, 1}, Strides3{0, N, 1}, Strides3{0, N, 1}, false, false, t->stream));
+    // history = lhs's else rhs's (reference container_operations.rs:1357-1361); with a history every
+    // product is recorded with BOTH operands as parents (:1291-1296), whatever their own history
+    c.tracked = a->tracked || b->tracked;
+    if (c.tracked) {
+        Node nd;
+        nd.kind = Kind::MATMUL;
+        nd.base = t->len;
+        nd.count = M * N * (2 * K - 1);
+        nd.n = M * N;
+        nd.M = M;
+        nd.N = N;
+        nd.K = K;
+        nd.p0 = na;
+        nd.p1 = nb;
+        nd.p0_tracked = nd.p1_tracked = true;
+        nd.a = a->numbers;
+        nd.b = b->numbers;
+        t->len += nd.count;
+        t->nodes.push_back(nd);
+        c.node = (int)t->nodes.size() - 1;
+        c.epoch = t->epoch;
+    }
+    *out = put_value(t, std::move(c));
+    return EML_OK;
+}
+
+template <class T>
+int tape_unary(eml_tape* t, int op, double cst, eml_val hx, eml_val* out) {
+    Value* x;
+    EML_TRY(get_value(t, hx, &x));
+    bool stale;
+    int nx = live_node(t, *x, &stale);
+    if (stale) {
+        set_error("container was not reset after WengertList::clear(); its indexes are stale");
+        return EML_ERR_STATE;
+    }
+    Value y;
+    y.rows = x->rows;
+    y.cols = x->cols;
+    const int64_t n = x->n();
+    EML_TRY(new_buf(sizeof(T) * n, t->stream, &y.numbers));
+    if (!x->tracked) {  // history None -> constants (reference container_record/mod.rs:852)
+        EML_TRY(launch_unary<T>(op, (T)cst, (const T*)x->numbers->p, (T*)y.numbers->p, (T*)nullptr, n, t->stream));
+    } else {
+        Node nd;
+        nd.kind = Kind::UNARY;
+        nd.base = t->len;
+        nd.count = nd.n = n;
+        nd.p0 = nx;
+        nd.p0_tracked = true;
+        EML_TRY(new_buf(sizeof(T) * n, t->stream, &nd.a));
+        EML_TRY(launch_unary<T>(op, (T)cst, (const T*)x->numbers->p, (T*)y.numbers->p, (T*)nd.a->p, n, t->stream));
+        t->len += n;
+        t->nodes.push_back(nd);
+        y.tracked = true;
+        y.node = (int)t->nodes.size() - 1;
+        y.epoch = t->epoch;
+    }
+    *out = put_value(t, std::move(y));
+    return EML_OK;
+}
+
+template <class T>
+int tape_binary(eml_tape* t, int op, eml_val hx, eml_val hy, eml_val* out) {
+    Value *x, *y;
+    EML_TRY(get_value(t, hx, &x));
+    EML_TRY(get_value(t, hy, &y));
+    if (x->rows != y->rows || x->cols != y->cols)
+        EML_BAD_ARG("Record containers must have the same shape for a binary operation: (left: %lldx%lld, right: %lldx%lld)",
+                    (long long)x->rows, (long long)x->cols, (long long)y->rows, (long long)y->cols);
+    bool sx, sy;
+    int nx = live_node(t, *x, &sx), ny = live_node(t, *y, &sy);
+    if (sx || sy) {
+        set_error("container was not reset after WengertList::clear(); its indexes are stale");
+        return EML_ERR_STATE;
+    }
+    Value z;
+    z.rows = x->rows;
+    z.cols = x->cols;
+    const int64_t n = x->n();
+    EML_TRY(new_buf(sizeof(T) * n, t->stream, &z.numbers));
+    const T* xp = (const T*)x->numbers->p;
+    const T* yp = (const T*)y->numbers->p;
+    if (!x->tracked && !y->tracked) {  // (None, None) reference mod.rs:984
+        EML_TRY(launch_binary<T>(op, xp, yp, (T*)z.numbers->p, (T*)nullptr, (T*)nullptr, n, t->stream));
+    } else {
+        Node nd;
+        nd.kind = Kind::BINARY;
+        nd.base = t->len;
+        nd.count = nd.n = n;
+        nd.p0 = nx;
+        nd.p1 = ny;
+        nd.p0_tracked = x->tracked;  // binary_x_history / binary_y_history / binary_both_history
+        nd.p1_tracked = y->tracked;
+        if (nd.p0_tracked) EML_TRY(new_buf(sizeof(T) * n, t->stream, &nd.a));
+        if (nd.p1_tracked) EML_TRY(new_buf(sizeof(T) * n, t->stream, &nd.b));
+        EML_TRY(launch_binary<T>(op, xp, yp, (T*)z.numbers->p, nd.a ? (T*)nd.a->p : nullptr,
+                                 nd.b ? (T*)nd.b->p : nullptr, n, t->stream));
+        t->len += n;
+        t->nodes.push_back(nd);
+        z.tracked = true;
+        z.node = (int)t->nodes.size() - 1;
+        z.epoch = t->epoch;
+    }
+    *out = put_value(t, std::move(z));
+    return EML_OK;
+}
+
+// The reverse sweep over macro nodes.
+template <class T>
+int tape_sweep(eml_tape* t, eml_val hv, int64_t row, int64_t col, eml_derivs** out) {
+    Value* v;
+    EML_TRY(get_value(t, hv, &v));
+    if (!v->tracked) {
+        set_error("Record has no WengertList to find derivatives from");
+        return EML_ERR_STATE;
+    }
+    if (row < 0 || row >= v->rows || col < 0 || col >= v->cols) EML_BAD_ARG("element (%lld,%lld) out of range", (long long)row, (long long)col);
+    bool stale;
+    int nv = live_node(t, *v, &stale);
+    if (stale) {
+        set_error("container was not reset after WengertList::clear(); its indexes are stale");
+        return EML_ERR_STATE;
+    }
+    if (t->nodes.empty()) {
+        set_error("the WengertList is empty: index out of bounds in the reference");
+        return EML_ERR_STATE;
+    }
+    cudaStream_t st = t->stream;
+    auto d = std::make_unique<eml_derivs>();
+    d->tape = t;
+    d->dtype = t->dtype;
+    d->device = t->device;
+    d->stream = st;
+    d->len = t->len;
+    d->epoch = t->epoch;
+    d->nodes = t->nodes;
+    d->grads.resize(t->nodes.size());
+    for (size_t i = 0; i < t->nodes.size(); i++) {
+        EML_TRY(new_buf(sizeof(T) * t->nodes[i].n, st, &d->grads[i]));
+        EML_CUDA(cudaMemsetAsync(d->grads[i]->p, 0, sizeof(T) * t->nodes[i].n, st));  // vec![0; len] :627
+    }
+    // contributions to reference index 0 from parents that carry Index 0 (constants)
+    TempBuf slot0;
+    EML_TRY(slot0.alloc(sizeof(T), st));
+    EML_CUDA(cudaMemsetAsync(slot0.p, 0, sizeof(T), st));
+    bool slot0_used = false;
+    // derivatives[self.index] = 1  (:630)
+    if (nv >= 0) {
+        EML_TRY(launch_fill<T>((T*)d->grads[nv]->p + (row * v->cols + col), T(1), 1, st));
+    } else {
+        EML_TRY(launch_fill<T>(slot0.as<T>(), T(1), 1, st));
+        slot0_used = true;
+    }
+
+    for (int i = (int)t->nodes.size() - 1; i >= 0; i--) {
+        const Node& nd = t->nodes[i];
+        const T* g = (const T*)d->grads[i]->p;
+        if (nd.kind == Kind::VARIABLES) continue;
+        if (nd.kind == Kind::UNARY) {
+            if (nd.p0 >= 0)
+                EML_TRY(launch_chain<T>(g, (const T*)nd.a->p, (T*)d->grads[nd.p0]->p, nd.n, st));
+            else {
+                EML_TRY(launch_dot_accumulate<T>(t->ctx, g, (const T*)nd.a->p, nd.n, slot0.as<T>(), true, st));
+                slot0_used = true;
+            }
+        } else if (nd.kind == Kind::BINARY) {
+            if (nd.p0_tracked) {
+                if (nd.p0 >= 0)
+                    EML_TRY(launch_chain<T>(g, (const T*)nd.a->p, (T*)d->grads[nd.p0]->p, nd.n, st));
+                else {
+                    EML_TRY(launch_dot_accumulate<T>(t->ctx, g, (const T*)nd.a->p, nd.n, slot0.as<T>(), true, st));
+                    slot0_used = true;
+                }
+            }
+            if (nd.p1_tracked) {
+                if (nd.p1 >= 0)
+                    EML_TRY(launch_chain<T>(g, (const T*)nd.b->p, (T*)d->grads[nd.p1]->p, nd.n, st));
+                else {
+                    EML_TRY(launch_dot_accumulate<T>(t->ctx, g, (const T*)nd.b->p, nd.n, slot0.as<T>(), true, st));
+                    slot0_used = true;
+                }
+            }
+        } else {  // MATMUL: dA += G * B^T, dB += A^T * G
+            const int64_t M = nd.M, N = nd.N, K = nd.K;
+            const T* A = (const T*)nd.a->p;
+            const T* B = (const T*)nd.b->p;
+            if (nd.p0 >= 0) {
+                EML_TRY(contract_dev<T>(t->ctx, g, B, (T*)d->grads[nd.p0]->p, 1, M, K, N, Strides3{0, N, 1},
+                                        Strides3{0, 1, N}, Strides3{0, K, 1}, true, false, st));
+            } else {
+                // every element of A carries Index 0: derivatives[0] += sum_ik (G B^T)[i,k]
+                //   = sum_j colsum(G)[j] * colsum(B)[j]
+                TempBuf cg, cb;
+                EML_TRY(cg.alloc(sizeof(T) * N, st));
+                EML_TRY(cb.alloc(sizeof(T) * N, st));
+                EML_TRY(launch_col_sums<T>(g, M, N, cg.as<T>(), st));
+                EML_TRY(launch_col_sums<T>(B, K, N, cb.as<T>(), st));
+                EML_TRY(launch_dot_accumulate<T>(t->ctx, cg.as<T>(), cb.as<T>(), N, slot0.as<T>(), true, st));
+                slot0_used = true;
+            }
+            if (nd.p1 >= 0) {
+                EML_TRY(contract_dev<T>(t->ctx, A, g, (T*)d->grads[nd.p1]->p, 1, K, N, M, Strides3{0, 1, K},
+                                        Strides3{0, N, 1}, Strides3{0, N, 1}, true, false, st));
+            } else {
+                // derivatives[0] += sum_kj (A^T G)[k,j] = sum_i rowsum(A)[i] * rowsum(G)[i]
+                TempBuf ra, rg;
+                EML_TRY(ra.alloc(sizeof(T) * M, st));
+                EML_TRY(rg.alloc(sizeof(T) * M, st));
+                EML_TRY(launch_row_sums<T>(A, M, K, ra.as<T>(), st));
+                EML_TRY(launch_row_sums<T>(g, M, N, rg.as<T>(), st));
+                EML_TRY(launch_dot_accumulate<T>(t->ctx, ra.as<T>(), rg.as<T>(), M, slot0.as<T>(), true, st));
+                slot0_used = true;
+            }
+        }
+    }
+    if (slot0_used) {
+        // reference index 0 is element 0 of the first node
+        EML_TRY(launch_add_inplace<T>((T*)d->grads[0]->p, slot0.as<T>(), 1, st));
+    }
+    *out = d.release();
+    return EML_OK;
+}
+
+int find_node(const eml_derivs* d, int64_t index) {
+    if (index < 0 || index >= d->len) return -1;
+    int lo = 0, hi = (int)d->nodes.size() - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) / 2;
+        if (d->nodes[mid].base <= index)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    return lo;
+}
+
+}  // namespace
+}  // namespace eml
+
+#define TAPE_DISPATCH(t, expr_f32, expr_f64) ((t)->dtype == EML_F32 ? (expr_f32) : (expr_f64))
+
+extern "C" {
+
+int eml_tape_create(int dtype, eml_tape** out) {
+    if (!out || (dtype != EML_F32 && dtype != EML_F64)) EML_BAD_ARG("tape_create: dtype must be EML_F32 or EML_F64");
+    DeviceCtx* ctx = nullptr;
+    EML_TRY(get_ctx(&ctx));
+    auto* t = new eml_tape();
+    t->dtype = dtype;
+    t->device = ctx->device;
+    t->ctx = ctx;
+    t->stream = ctx->stream;
+    *out = t;
+    return EML_OK;
+}
+
+int eml_tape_destroy(eml_tape* t) {
+    if (!t) return EML_OK;
+    check_tape(t);
+    cudaStreamSynchronize(t->stream);
+    delete t;
+    return EML_OK;
+}
+
+int eml_tape_len(eml_tape* t, int64_t* len) {
+    if (!t || !len) EML_BAD_ARG("null argument");
+    *len = t->len;
+    return EML_OK;
+}
+
+int eml_tape_clear(eml_tape* t) {
+    EML_TRY(check_tape(t));
+    std::lock_guard<std::mutex> lock(t->mu);
+    t->nodes.clear();
+    t->len = 0;
+    t->epoch++;
+    return EML_OK;
+}
+
+int eml_tape_variables(eml_tape* t, const void* host, int64_t rows, int64_t cols, eml_val* out) {
+    EML_TRY(check_tape(t));
+    std::lock_guard<std::mutex> lock(t->mu);
+    return TAPE_DISPATCH(t, new_container<float>(t, host, false, rows, cols, true, out),
+                         new_container<double>(t, host, false, rows, cols, true, out));
+}
+int eml_tape_constants(eml_tape* t, const void* host, int64_t rows, int64_t cols, eml_val* out) {
+    EML_TRY(check_tape(t));
+    std::lock_guard<std::mutex> lock(t->mu);
+    return TAPE_DISPATCH(t, new_container<float>(t, host, false, rows, cols, false, out),
+                         new_container<double>(t, host, false, rows, cols, false, out));
+}
+int eml_tape_variables_dev(eml_tape* t, const void* dev, int64_t rows, int64_t cols, eml_val* out) {
+    EML_TRY(check_tape(t));
+    std::lock_guard<std::mutex> lock(t->mu);
+    return TAPE_DISPATCH(t, new_container<float>(t, dev, true, rows, cols, true, out),
+                         new_container<double>(t, dev, true, rows, cols, true, out));
+}
+int eml_tape_constants_dev(eml_tape* t, const void* dev, int64_t rows, int64_t cols, eml_val* out) {
+    EML_TRY(check_tape(t));
+    std::lock_guard<std::mutex> lock(t->mu);
+    return TAPE_DISPATCH(t, new_container<float>(t, dev, true, rows, cols, false, out),
+                         new_container<double>(t, dev, true, rows, cols, false, out));
+}
+
+int eml_tape_reset(eml_tape* t, eml_val h) {
+    EML_TRY(check_tape(t));
+    std::lock_guard<std::mutex> lock(t->mu);
+    Value* v;
+    EML_TRY(get_value(t, h, &v));
+    if (!v->tracked) return EML_OK;  // history None => noop (reference mod.rs:351)
+    Node nd;
+    nd.kind = Kind::VARIABLES;
+    nd.base = t->len;
+    nd.count = nd.n = v->n();
+    t->len += nd.count;
+    t->nodes.push_back(nd);
+    v->node = (int)t->nodes.size() - 1;
+    v->epoch = t->epoch;
+    return EML_OK;
+}
+
+int eml_val_release(eml_tape* t, eml_val h) {
+    EML_TRY(check_tape(t));
+    std::lock_guard<std::mutex> lock(t->mu);
+    Value* v;
+    EML_TRY(get_value(t, h, &v));
+    *v = Value();
+    t->free_slots.push_back(h);
+    return EML_OK;
+}
+
+int eml_val_shape(eml_tape* t, eml_val h, int64_t* rows, int64_t* cols, int* tracked) {
+    if (!t) EML_BAD_ARG("null tape");
+    std::lock_guard<std::mutex> lock(t->mu);
+    Value* v;
+    EML_TRY(get_value(t, h, &v));
+    if (rows) *rows = v->rows;
+    if (cols) *cols = v->cols;
+    if (tracked) *tracked = v->tracked ? 1 : 0;
+    return EML_OK;
+}
+
+int eml_val_numbers(eml_tape* t, eml_val h, void* host_out) {
+    EML_TRY(check_tape(t));
+    std::lock_guard<std::mutex> lock(t->mu);
+    Value* v;
+    EML_TRY(get_value(t, h, &v));
+    EML_CUDA(cudaMemcpyAsync(host_out, v->numbers->p, esize(t->dtype) * v->n(), cudaMemcpyDeviceToHost, t->stream));
+    EML_CUDA(cudaStreamSynchronize(t->stream));
+    return EML_OK;
+}
+
+int eml_val_indexes(eml_tape* t, eml_val h, int64_t* host_out) {
+    if (!t || !host_out) EML_BAD_ARG("null argument");
+    std::lock_guard<std::mutex> lock(t->mu);
+    Value* v;
+    EML_TRY(get_value(t, h, &v));
+    bool stale;
+    int n = live_node(t, *v, &stale);
+    if (stale) {
+        set_error("container was not reset after WengertList::clear(); its indexes are stale");
+        return EML_ERR_STATE;
+    }
+    for (int64_t e = 0; e < v->n(); e++) host_out[e] = n < 0 ? 0 : t->nodes[n].index_of(e);
+    return EML_OK;
+}
+
+int eml_val_device_ptr(eml_tape* t, eml_val h, void** dev) {
+    if (!t || !dev) EML_BAD_ARG("null argument");
+    std::lock_guard<std::mutex> lock(t->mu);
+    Value* v;
+    EML_TRY(get_value(t, h, &v));
+    *dev = v->numbers->p;
+    return EML_OK;
+}
+
+int eml_tape_matmul(eml_tape* t, eml_val a, eml_val b, eml_val* c) {
+    EML_TRY(check_tape(t));
+    if (!c) EML_BAD_ARG("null argument");
+    std::lock_guard<std::mutex> lock(t->mu);
+    return TAPE_DISPATCH(t, tape_matmul<float>(t, a, b, c), tape_matmul<double>(t, a, b, c));
+}
+int eml_tape_unary(eml_tape* t, int op, double cst, eml_val x, eml_val* y) {
+    EML_TRY(check_tape(t));
+    if (!y) EML_BAD_ARG("null argument");
+    std::lock_guard<std::mutex> lock(t->mu);
+    return TAPE_DISPATCH(t, tape_unary<float>(t, op, cst, x, y), tape_unary<double>(t, op, cst, x, y));
+}
+int eml_tape_binary(eml_tape* t, int op, eml_val x, eml_val y, eml_val* z) {
+    EML_TRY(check_tape(t));
+    if (!z) EML_BAD_ARG("null argument");
+    std::lock_guard<std::mutex> lock(t->mu);
+    return TAPE_DISPATCH(t, tape_binary<float>(t, op, x, y, z), tape_binary<double>(t, op, x, y, z));
+}
+
+int eml_tape_derivatives(eml_tape* t, eml_val v, int64_t row, int64_t col, eml_derivs** out) {
+    EML_TRY(check_tape(t));
+    if (!out) EML_BAD_ARG("null argument");
+    std::lock_guard<std::mutex> lock(t->mu);
+    return TAPE_DISPATCH(t, tape_sweep<float>(t, v, row, col, out), tape_sweep<double>(t, v, row, col, out));
+}
+
+int eml_derivs_free(eml_derivs* d) {
+    if (!d) return EML_OK;
+    cudaSetDevice(d->device);
+    delete d;
+    return EML_OK;
+}
+
+int eml_derivs_len(eml_derivs* d, int64_t* len) {
+    if (!d || !len) EML_BAD_ARG("null argument");
+    *len = d->len;
+    return EML_OK;
+}
+
+int eml_derivs_at(eml_derivs* d, int64_t index, double* out) {
+    if (!d || !out) EML_BAD_ARG("null argument");
+    int n = find_node(d, index);
+    if (n < 0) EML_BAD_ARG("index out of bounds: the len is %lld but the index is %lld", (long long)d->len, (long long)index);
+    int64_t e = d->nodes[n].element_of(index);
+    EML_CUDA(cudaSetDevice(d->device));
+    if (d->dtype == EML_F32) {
+        float f;
+        EML_CUDA(cudaMemcpyAsync(&f, (const float*)d->grads[n]->p + e, 4, cudaMemcpyDeviceToHost, d->stream));
+        EML_CUDA(cudaStreamSynchronize(d->stream));
+        *out = f;
+    } else {
+        EML_CUDA(cudaMemcpyAsync(out, (const double*)d->grads[n]->p + e, 8, cudaMemcpyDeviceToHost, d->stream));
+        EML_CUDA(cudaStreamSynchronize(d->stream));
+    }
+    return EML_OK;
+}
+
+static int derivs_at_val(eml_derivs* d, eml_val h, void* dst, bool dst_on_device) {
+    if (!d || !dst) EML_BAD_ARG("null argument");
+    eml_tape* t = d->tape;
+    EML_TRY(check_tape(t));
+    std::lock_guard<std::mutex> lock(t->mu);
+    Value* v;
+    EML_TRY(get_value(t, h, &v));
+    size_t es = esize(d->dtype);
+    int n = v->node;
+    if (n >= 0 && (v->epoch != d->epoch || n >= (int)d->nodes.size())) {
+        set_error("container does not belong to the computation these derivatives were taken from");
+        return EML_ERR_STATE;
+    }
+    cudaMemcpyKind kind = dst_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    if (n >= 0) {
+        EML_CUDA(cudaMemcpyAsync(dst, d->grads[n]->p, es * v->n(), kind, d->stream));
+    } else {
+        // every Index is 0: each element reads derivatives[0]
+        for (int64_t e = 0; e < v->n(); e++)
+            EML_CUDA(cudaMemcpyAsync((char*)dst + es * e, d->grads[0]->p, es, kind, d->stream));
+    }
+    if (!dst_on_device) EML_CUDA(cudaStreamSynchronize(d->stream));
+    return EML_OK;
+}
+
+int eml_derivs_at_val(eml_derivs* d, eml_val v, void* host_out) { return derivs_at_val(d, v, host_out, false); }
+int eml_derivs_at_val_dev(eml_derivs* d, eml_val v, void* dev_out) { return derivs_at_val(d, v, dev_out, true); }
+
+int eml_derivs_to_host(eml_derivs* d, void* host_out) {
+    if (!d || !host_out) EML_BAD_ARG("null argument");
+    if (d->len > (int64_t(1) << 28))
+        EML_BAD_ARG("derivs_to_host: the reference tape would have %lld entries; materialising it is refused", (long long)d->len);
+    EML_CUDA(cudaSetDevice(d->device));
+    size_t es = esize(d->dtype);
+    std::vector<char> tmp;
+    for (size_t i = 0; i < d->nodes.size(); i++) {
+        const Node& nd = d->nodes[i];
+        tmp.resize(es * nd.n);
+        EML_CUDA(cudaMemcpyAsync(tmp.data(), d->grads[i]->p, es * nd.n, cudaMemcpyDeviceToHost, d->stream));
+        EML_CUDA(cudaStreamSynchronize(d->stream));
+        char* dst = (char*)host_out + es * nd.base;
+        if (nd.kind == Kind::MATMUL && nd.K > 1) {
+            int64_t seg = 2 * nd.K - 1;
+            for (int64_t e = 0; e < nd.n; e++)
+                for (int64_t s = 0; s < seg; s++) memcpy(dst + es * (e * seg + s), tmp.data() + es * e, es);
+        } else {
+            memcpy(dst, tmp.data(), es * nd.n);
+        }
+    }
+    return EML_OK;
+}
+
+int eml_tape_sgd_update(eml_tape* t, eml_val hw, eml_derivs* d, double lr) {
+    EML_TRY(check_tape(t));
+    if (!d) EML_BAD_ARG("null argument");
+    std::lock_guard<std::mutex> lock(t->mu);
+    Value* w;
+    EML_TRY(get_value(t, hw, &w));
+    if (!w->tracked || w->node < 0 || w->epoch != t->epoch || d->epoch != t->epoch || w->node >= (int)d->nodes.size()) {
+        set_error("sgd_update: container is not a tracked variable of the computation these derivatives belong to");
+        return EML_ERR_STATE;
+    }
+    const int64_t n = w->n();
+    size_t es = esize(t->dtype);
+    // x - (derivatives[&x] * lr): a new container (the nodes that captured the old numbers keep them)
+    Buf fresh;
+    EML_TRY(new_buf(es * n, t->stream, &fresh));
+    EML_CUDA(cudaMemcpyAsync(fresh->p, w->numbers->p, es * n, cudaMemcpyDeviceToDevice, t->stream));
+    Node nd;
+    nd.kind = Kind::UNARY;  // Record - T => append_unary(x.index, 1)
+    nd.base = t->len;
+    nd.count = nd.n = n;
+    nd.p0 = w->node;
+    nd.p0_tracked = true;
+    EML_TRY(new_buf(es * n, t->stream, &nd.a));
+    if (t->dtype == EML_F32) {
+        EML_TRY(launch_sgd<float>((float*)fresh->p, (const float*)d->grads[w->node]->p, (float)lr, n, t->stream));
+        EML_TRY(launch_fill<float>((float*)nd.a->p, 1.0f, n, t->stream));
+    } else {
+        EML_TRY(launch_sgd<double>((double*)fresh->p, (const double*)d->grads[w->node]->p, lr, n, t->stream));
+        EML_TRY(launch_fill<double>((double*)nd.a->p, 1.0, n, t->stream));
+    }
+    t->len += n;
+    t->nodes.push_back(nd);
+    w->numbers = fresh;
+    w->node = (int)t->nodes.size() - 1;
+    return EML_OK;
+}
+
+}  // extern "C"

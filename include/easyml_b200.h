@@ -1,0 +1,261 @@
+/*
+ * easyml_b200.h -- C ABI of the B200-native dense-contraction path for Easy ML (f32 / f64).
+ *
+ * This is the drop-in boundary.  The reference (Skeletonxf/easy-ml) has no FFI:
+ * its "interface" for this path is five private Rust functions behind `std::ops::Mul` / `Einsum` /
+ * `RecordTensor`.  Behind a `cuda` Cargo feature each of them validates exactly as today and then calls
+ * one entry point below (the binding a maintainer would add is shown in INTEGRATION.md).  Every entry
+ * point cites the reference code it replaces (paths relative to the reference repo root).
+ *
+ * Conventions
+ *  - plain pointers and sizes, no C++/torch types; all extents and strides are int64_t ELEMENTS.
+ *  - every function returns int: 0 = EML_OK, negative = EML_ERR_*; nothing throws or aborts across the
+ *    boundary.  eml_last_error() returns a thread-local, library-owned message valid until the next call
+ *    on that thread.
+ *  - no CPU fallback: with no CUDA device every compute entry point returns EML_ERR_NO_DEVICE.
+ *  - deterministic: fixed tile->CTA map, fixed k order, no atomics, fixed-order split-K; results are
+ *    bit-identical run to run on the same GPU model.
+ *  - host entry points (no suffix) take HOST pointers, stage through pinned memory and block until the
+ *    result is in the caller's buffer.  `_dev` entry points take DEVICE pointers plus a cudaStream_t
+ *    (as void*; NULL = the library's stream for the current device) and are asynchronous.
+ *  - the device used is the calling thread's current CUDA device (cudaSetDevice / torch.cuda.set_device);
+ *    state is cached per device; entry points are re-entrant across threads.
+ */
+#ifndef EASYML_B200_H
+#define EASYML_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EML_OK 0
+#define EML_ERR_NO_DEVICE (-1)
+#define EML_ERR_BAD_ARG (-2)
+#define EML_ERR_OOM (-3)
+#define EML_ERR_CUDA (-4)
+#define EML_ERR_NCCL (-5)
+#define EML_ERR_STATE (-6)
+
+#define EML_F32 0
+#define EML_F64 1
+
+/* Elementwise container ops (A10).  Values and derivative rules are those of
+ * src/differentiation/functions.rs; the unary list is the set of `RecordTensor::unary` callers in
+ * src/differentiation/container_record/container_operations.rs:1644-1804 and
+ * container_operations/swapped.rs:25-45 (c = the scalar operand). */
+#define EML_OP_NEG 0    /* -x            d = -1                 functions.rs:143-161 */
+#define EML_OP_SIN 1    /* sin x         d = cos x              :163-181 */
+#define EML_OP_COS 2    /* cos x         d = -sin x             :183-201 */
+#define EML_OP_EXP 3    /* e^x           d = e^x                :203-221 */
+#define EML_OP_LN 4     /* ln x          d = 1/x                :223-241 */
+#define EML_OP_SQRT 5   /* sqrt x        d = 1/((1+1) sqrt x)   :243-261 */
+#define EML_OP_ADD_C 6  /* x + c         d = 1                  :18-41  (d/dx) */
+#define EML_OP_SUB_C 7  /* x - c         d = 1                  :43-66  (d/dx) */
+#define EML_OP_MUL_C 8  /* x * c         d = c                  :68-91  (d/dx) */
+#define EML_OP_DIV_C 9  /* x / c         d = 1/c                :93-116 (d/dx) */
+#define EML_OP_POW_C 10 /* x ^ c         d = c x^(c-1)          :118-141 (d/dx) */
+#define EML_OP_C_SUB 11 /* c - x         d = -1                 sub_swapped (d/dy) */
+#define EML_OP_C_DIV 12 /* c / x         d = -c/(x x)           div_swapped (d/dy) */
+#define EML_OP_C_POW 13 /* c ^ x         d = c^x ln c           pow swapped (d/dy) */
+#define EML_OP_ADD 32   /* x + y         dx = 1     dy = 1 */
+#define EML_OP_SUB 33   /* x - y         dx = 1     dy = -1 */
+#define EML_OP_MUL 34   /* x * y         dx = y     dy = x        (elementwise_multiply, mod.rs:1224) */
+#define EML_OP_DIV 35   /* x / y         dx = 1/y   dy = -x/(y y) (elementwise_divide,   mod.rs:1247) */
+#define EML_OP_POW 36   /* x ^ y         dx = y x^(y-1)  dy = x^y ln x */
+
+/* ---------------------------------------------------------------------------------------------
+ * Library lifetime and errors
+ * ------------------------------------------------------------------------------------------- */
+/* Counts CUDA devices.  Returns EML_ERR_NO_DEVICE (and *n_devices = 0) when there is none: the f32/f64
+ * path has no CPU fallback, the Rust shim turns this into a panic. */
+int eml_init(int* n_devices);
+void eml_shutdown(void);
+const char* eml_last_error(void);
+int eml_version(void);
+/* How many kernels this library has launched so far in this process (all threads, all devices). */
+int64_t eml_kernel_launches(void);
+/* Name of the kernel family the last GEMM/contract call on this thread dispatched to
+ * ("dmma_f64", "tf32x3_tcgen05", "simt", "einsum_generic", ...).  Library-owned string. */
+const char* eml_last_kernel(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Tier 1 -- host-pointer drop-ins
+ * ------------------------------------------------------------------------------------------- */
+/* C[MxN] = A[MxK] * B[KxN], row-major with leading dimensions (elements).
+ * Replaces matrix_view_multiplication, src/matrices/operations.rs:165-196 (the 16 Matrix/MatrixView Mul
+ * impls), and tensor_view_matrix_product, src/tensors/operations.rs:474-519 (the 16 rank-2
+ * Tensor/TensorView Mul impls); per element it replaces scalar_product, src/tensors/operations.rs:429-446.
+ * Shape/name validation (operations.rs:176-183, :485-501) stays in the caller. */
+int eml_gemm_f32(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda,
+                 int64_t ldb, int64_t ldc);
+int eml_gemm_f64(const double* A, const double* B, double* C, int64_t M, int64_t N, int64_t K, int64_t lda,
+                 int64_t ldb, int64_t ldc);
+
+/* Strided-batched contraction  C[b,m,n] = sum_k A[b,m,k] * B[b,k,n].
+ * sA = element strides of A for (batch, m, k); sB for (batch, k, n); sC for (batch, m, n).
+ * Replaces Einsum2::to, src/tensors/einsum.rs:908-980, for every name pattern that classifies into
+ * batch / M / N / K roles (each role may be a product of several named dimensions only when they are
+ * jointly contiguous); the classification itself (output_shape_for :563, summation_dimensions :579)
+ * stays in the caller.  Buffers are host pointers spanning the strided extents. */
+int eml_contract_f32(const float* A, const float* B, float* C, int64_t batch, int64_t M, int64_t N, int64_t K,
+                     const int64_t sA[3], const int64_t sB[3], const int64_t sC[3]);
+int eml_contract_f64(const double* A, const double* B, double* C, int64_t batch, int64_t M, int64_t N,
+                     int64_t K, const int64_t sA[3], const int64_t sB[3], const int64_t sC[3]);
+
+/* General two-operand Einstein summation for the patterns that are NOT (batched) GEMMs
+ * (e.g. ij,jk->ijk ; ij,kl->il ; ab,ab-> ; a,b->ab):
+ *   out[o] = sum over s of A[o . a_out_stride + s . a_sum_stride] * B[o . b_out_stride + s . b_sum_stride]
+ * out is contiguous row-major over out_len[0..n_out); a stride of 0 means "this operand does not carry
+ * that dimension".  The sum is seeded with zero and runs in the reference's order (summation dimensions in
+ * order of first appearance, last fastest; src/tensors/einsum.rs:932-972, src/tensors/indexing.rs:876-933)
+ * with separately rounded multiply and add, so this entry point is BIT-EXACT with the reference.
+ * n_out <= 6, n_sum <= 12 (two rank-6 inputs).  Host pointers; a_elems / b_elems = buffer lengths. */
+int eml_einsum2_f32(const float* A, int64_t a_elems, const float* B, int64_t b_elems, float* out, int n_out,
+                    const int64_t* out_len, const int64_t* a_out_stride, const int64_t* b_out_stride, int n_sum,
+                    const int64_t* sum_len, const int64_t* a_sum_stride, const int64_t* b_sum_stride);
+int eml_einsum2_f64(const double* A, int64_t a_elems, const double* B, int64_t b_elems, double* out, int n_out,
+                    const int64_t* out_len, const int64_t* a_out_stride, const int64_t* b_out_stride, int n_sum,
+                    const int64_t* sum_len, const int64_t* a_sum_stride, const int64_t* b_sum_stride);
+
+/* Dot product of two strided vectors (n >= 1).  Replaces Tensor<T,1>::scalar_product,
+ * src/tensors/mod.rs:1773 -> src/tensors/operations.rs:1773-1808. */
+int eml_dot_f32(const float* x, int64_t incx, const float* y, int64_t incy, int64_t n, float* out);
+int eml_dot_f64(const double* x, int64_t incx, const double* y, int64_t incy, int64_t n, double* out);
+
+/* Bit-exact GEMM: same contract as eml_gemm_*, but every C[i,j] is the reference's exact operation
+ * sequence (first product, then k-ascending separately rounded multiply and add -- scalar_product,
+ * src/tensors/operations.rs:441-445).  Slow (no tensor cores, no FMA); exists so parity can be shown
+ * bit-for-bit against the oracle at sizes the fast kernels are only checked within tolerance. */
+int eml_gemm_exact_f32(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda,
+                       int64_t ldb, int64_t ldc);
+int eml_gemm_exact_f64(const double* A, const double* B, double* C, int64_t M, int64_t N, int64_t K,
+                       int64_t lda, int64_t ldb, int64_t ldc);
+
+/* ---------------------------------------------------------------------------------------------
+ * Tier 2 -- device-resident variants (benchmarks, keeping an NN step on the GPU)
+ * ------------------------------------------------------------------------------------------- */
+int eml_alloc(void** dptr, size_t bytes);
+int eml_free(void* dptr);
+int eml_upload(void* dst_dev, const void* src_host, size_t bytes);   /* blocking */
+int eml_download(void* dst_host, const void* src_dev, size_t bytes); /* blocking */
+int eml_sync(void);                                                  /* current device */
+
+/* accumulate != 0:  C += A*B (the fused "accumulate into the derivative" epilogue of the backward). */
+int eml_contract_f32_dev(const float* A, const float* B, float* C, int64_t batch, int64_t M, int64_t N,
+                         int64_t K, const int64_t sA[3], const int64_t sB[3], const int64_t sC[3],
+                         int accumulate, void* stream);
+int eml_contract_f64_dev(const double* A, const double* B, double* C, int64_t batch, int64_t M, int64_t N,
+                         int64_t K, const int64_t sA[3], const int64_t sB[3], const int64_t sC[3],
+                         int accumulate, void* stream);
+int eml_gemm_f32_dev(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda,
+                     int64_t ldb, int64_t ldc, void* stream);
+int eml_gemm_f64_dev(const double* A, const double* B, double* C, int64_t M, int64_t N, int64_t K, int64_t lda,
+                     int64_t ldb, int64_t ldc, void* stream);
+int eml_gemm_exact_f32_dev(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K,
+                           int64_t lda, int64_t ldb, int64_t ldc, void* stream);
+int eml_gemm_exact_f64_dev(const double* A, const double* B, double* C, int64_t M, int64_t N, int64_t K,
+                           int64_t lda, int64_t ldb, int64_t ldc, void* stream);
+
+/* Backward of C = A*B for reverse-mode autodiff:  dA += dC * B^T  and/or  dB += A^T * dC  (either
+ * output may be NULL).  This is what the reverse sweep Record::try_derivatives,
+ * src/differentiation.rs:623-648, computes over the M*N*(2K-1) tape entries that
+ * record_scalar_product, container_operations.rs:1263-1315, appends for one matmul.  Row-major, dense. */
+int eml_matmul_bwd_f32_dev(const float* dC, const float* A, const float* B, float* dA, float* dB, int64_t M,
+                           int64_t N, int64_t K, void* stream);
+int eml_matmul_bwd_f64_dev(const double* dC, const double* A, const double* B, double* dA, double* dB,
+                           int64_t M, int64_t N, int64_t K, void* stream);
+
+/* Elementwise forward:  y[i] = f(x[i], c) and dydx[i] = f'(x[i], c)  (dydx may be NULL) -- the value and
+ * the tape derivative of RecordTensor::unary, container_record/mod.rs:642-668, in one pass. */
+int eml_unary_f32_dev(int op, float c, const float* x, float* y, float* dydx, int64_t n, void* stream);
+int eml_unary_f64_dev(int op, double c, const double* x, double* y, double* dydx, int64_t n, void* stream);
+/* z = f(x,y), dzdx, dzdy (either may be NULL): RecordTensor::binary, mod.rs:672-768. */
+int eml_binary_f32_dev(int op, const float* x, const float* y, float* z, float* dzdx, float* dzdy, int64_t n,
+                       void* stream);
+int eml_binary_f64_dev(int op, const double* x, const double* y, double* z, double* dzdx, double* dzdy,
+                       int64_t n, void* stream);
+/* Backward chain rule of one elementwise tape segment:  dparent[i] += dout[i] * deriv[i]
+ * (src/differentiation.rs:641-644 restricted to the segment). */
+int eml_chain_f32_dev(const float* dout, const float* deriv, float* dparent, int64_t n, void* stream);
+int eml_chain_f64_dev(const double* dout, const double* deriv, double* dparent, int64_t n, void* stream);
+/* w[i] -= lr * d[i]: the weight update `w.map_mut(|x| x - derivatives[&x] * lr)`,
+ * src/neural_networks.rs:418-420, as one kernel. */
+int eml_sgd_f32_dev(float* w, const float* d, float lr, int64_t n, void* stream);
+int eml_sgd_f64_dev(double* w, const double* d, double lr, int64_t n, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Tier 3 -- device-resident reverse-mode tape (RecordTensor / RecordMatrix / WengertList)
+ *
+ * One eml_tape per WengertList<T> (src/differentiation.rs:327-331).  Containers are rank-2 (rows x cols,
+ * row-major); rank and dimension names are caller-side metadata.  The tape never materialises the scalar
+ * entries: a matmul is ONE macro node, yet every observable of the reference is reproduced --
+ *   - tape length (== WengertList.operations.len(), grows by M*N*(2K-1) per tracked matmul),
+ *   - every element's Index (variables: start+i, src/differentiation.rs:708-727; matmul outputs:
+ *     base + (i*N+j)*(2K-1) + 2K-2, K==1: base + i*N+j; unary/binary outputs: base+i),
+ *   - derivative values of the reverse sweep (src/differentiation.rs:623-648), including the
+ *     reference's constant-operand behaviour: a constant container carries Index 0
+ *     (container_record/mod.rs:120-126) and record_scalar_product records it as a parent
+ *     (container_operations.rs:1291-1296), so its derivative sum lands in derivatives[0].
+ * ------------------------------------------------------------------------------------------- */
+typedef struct eml_tape eml_tape;
+typedef struct eml_derivs eml_derivs;
+typedef int64_t eml_val; /* handle of a record container living on the tape's device */
+
+int eml_tape_create(int dtype, eml_tape** out); /* WengertList::new */
+int eml_tape_destroy(eml_tape* t);
+int eml_tape_len(eml_tape* t, int64_t* len);    /* operations.len() */
+/* WengertList::clear, src/differentiation.rs:674.  Values created before the clear stay usable as
+ * numbers; tracked ones must be eml_tape_reset before further tracked use (as in the reference). */
+int eml_tape_clear(eml_tape* t);
+/* RecordTensor::variables / RecordMatrix::variables, container_record/mod.rs:149-164,:426: appends
+ * rows*cols nullary entries, Index = start + i in row-major order.  host_numbers: rows*cols elements. */
+int eml_tape_variables(eml_tape* t, const void* host_numbers, int64_t rows, int64_t cols, eml_val* out);
+/* RecordTensor::constants, mod.rs:115-128: no history, every Index = 0. */
+int eml_tape_constants(eml_tape* t, const void* host_numbers, int64_t rows, int64_t cols, eml_val* out);
+/* same, adopting a device buffer the caller already filled (copied; async on the tape's stream) */
+int eml_tape_constants_dev(eml_tape* t, const void* dev_numbers, int64_t rows, int64_t cols, eml_val* out);
+int eml_tape_variables_dev(eml_tape* t, const void* dev_numbers, int64_t rows, int64_t cols, eml_val* out);
+/* RecordTensor::reset, mod.rs:349-365: re-append rows*cols nullary entries and renumber start + i. */
+int eml_tape_reset(eml_tape* t, eml_val v);
+int eml_val_release(eml_tape* t, eml_val v); /* drop a container (its node stays while referenced) */
+int eml_val_shape(eml_tape* t, eml_val v, int64_t* rows, int64_t* cols, int* tracked);
+int eml_val_numbers(eml_tape* t, eml_val v, void* host_out);     /* rows*cols numbers, row-major */
+int eml_val_indexes(eml_tape* t, eml_val v, int64_t* host_out);  /* rows*cols tape indexes */
+int eml_val_device_ptr(eml_tape* t, eml_val v, void** dev_numbers); /* borrowed; valid until release */
+
+/* record_tensor_matrix_multiply / record_matrix_matrix_multiply,
+ * container_operations.rs:1318-1381,:1494-1531 (+ the 8 Mul impls): c = a * b. */
+int eml_tape_matmul(eml_tape* t, eml_val a, eml_val b, eml_val* c);
+/* RecordTensor::unary and its operator front-ends (Neg, Sin, Cos, Exp, Ln, Sqrt, container (op) scalar,
+ * sub_swapped, div_swapped): container_record/mod.rs:845-861, container_operations.rs:1644-1804. */
+int eml_tape_unary(eml_tape* t, int op, double c, eml_val x, eml_val* y);
+/* RecordTensor::binary (elementwise +, -, elementwise_multiply, elementwise_divide), mod.rs:962-1043:
+ * history selection (None,None)/(Some,None)/(None,Some)/(Some,Some) as in the reference. */
+int eml_tape_binary(eml_tape* t, int op, eml_val x, eml_val y, eml_val* z);
+
+/* Record::derivatives of element (row, col) of v, src/differentiation.rs:606-648 /
+ * RecordTensor::derivatives_for, mod.rs:1201.  Returns EML_ERR_STATE if v has no history
+ * ("Record has no WengertList to find derivatives from"). */
+int eml_tape_derivatives(eml_tape* t, eml_val v, int64_t row, int64_t col, eml_derivs** out);
+int eml_derivs_free(eml_derivs* d);
+int eml_derivs_len(eml_derivs* d, int64_t* len); /* == tape length at the time of the sweep */
+/* Derivatives::at / Index<&Record>, src/differentiation.rs:387-403: d[index] as a double. */
+int eml_derivs_at(eml_derivs* d, int64_t index, double* out);
+/* Derivatives::at_tensor / at_matrix, mod.rs:1292,:1328: rows*cols values for container v. */
+int eml_derivs_at_val(eml_derivs* d, eml_val v, void* host_out);
+int eml_derivs_at_val_dev(eml_derivs* d, eml_val v, void* dev_out);
+/* Vec::from(Derivatives), src/differentiation.rs:405-414: the whole vector (tape-length elements).
+ * Entries interior to a matmul macro node are materialised on demand (they equal dC[i,j]). */
+int eml_derivs_to_host(eml_derivs* d, void* host_out);
+/* `w.map_mut(|x| x - derivatives[&x] * lr)`, src/neural_networks.rs:418-420, fused on the device:
+ * numbers updated in place and, like the reference, one unary entry per element is appended (the
+ * container's indexes move to the new entries until the next clear + reset). */
+int eml_tape_sgd_update(eml_tape* t, eml_val w, eml_derivs* d, double lr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EASYML_B200_H */

@@ -1,0 +1,101 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol the header
+declares, fails loudly without a device, and the host mirror validates like the reference BEFORE the FFI."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import easy_ml_b200 as eml
+from easy_ml_b200 import _ffi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "easyml_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(eml_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    syms = header_symbols()
+    assert len(syms) > 60
+    for s in syms:
+        assert hasattr(_ffi.lib, s), f"{s} declared in include/easyml_b200.h but not exported"
+    # and the ctypes table binds exactly the declared set
+    assert sorted(_ffi.SIGNATURES) == syms
+
+
+def test_no_torch_types_in_the_abi():
+    text = open(os.path.join(ROOT, "include", "easyml_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)  # declarations only
+    assert "torch" not in text.lower() and "at::" not in text and "#include <cuda" not in text
+
+
+def has_gpu():
+    import ctypes
+
+    n = ctypes.c_int()
+    return _ffi.lib.eml_init(ctypes.byref(n)) == 0
+
+
+@pytest.mark.skipif(has_gpu(), reason="checks the no-device behaviour")
+def test_no_device_is_a_hard_error():
+    with pytest.raises(eml.NoDeviceError):
+        eml.device_count()
+    with pytest.raises(eml.NoDeviceError):
+        eml.Matrix([[1.0, 2.0]]) * eml.Matrix([[1.0], [2.0]])
+    with pytest.raises(eml.NoDeviceError):
+        eml.Tensor([("a", 3)], [1.0, 2.0, 3.0]).scalar_product(eml.Tensor([("a", 3)], [1.0, 2.0, 3.0]))
+    with pytest.raises(eml.NoDeviceError):
+        eml.WengertList(np.float32)
+    x = eml.Tensor([("a", 2), ("b", 2)], [1.0, 2.0, 3.0, 4.0], dtype=np.float32)
+    with pytest.raises(eml.NoDeviceError):
+        eml.Einsum.with_2(x, x).named(["a", "b"], ["b", "c"]).to(["a", "c"])
+    assert "no CPU fallback" in _ffi.last_error()
+
+
+def test_host_validation_matches_reference_panics(golden):
+    for g in golden["matmul_panic"]:
+        with pytest.raises(eml.Panic) as e:
+            eml.Matrix(np.zeros(g["a_shape"])) * eml.Matrix(np.zeros(g["b_shape"]))
+        assert str(e.value) == g["message"]
+    for g in golden["tensor_matmul_panic"]:
+        a = eml.Tensor(list(zip(g["a_names"], g["a_shape"])), np.zeros(g["a_shape"]))
+        b = eml.Tensor(list(zip(g["b_names"], g["b_shape"])), np.zeros(g["b_shape"]))
+        with pytest.raises(eml.Panic) as e:
+            a * b
+        assert str(e.value).startswith(g["message_prefix"])
+
+
+def test_host_validation_agrees_with_oracle_messages(orc):
+    # the oracle restates the reference's panic text; the host mirror must produce the same strings
+    cases = [((2, 3), ["r", "c"], (2, 3), ["a", "b"]), ((2, 3), ["rows", "columns"], (3, 2), ["columns", "rows"])]
+    for ashape, an, bshape, bn in cases:
+        with pytest.raises(orc.ReferencePanic) as want:
+            orc.tensor_mul(np.zeros(ashape), an, np.zeros(bshape), bn)
+        with pytest.raises(eml.Panic) as got:
+            eml.Tensor(list(zip(an, ashape)), np.zeros(ashape)) * eml.Tensor(list(zip(bn, bshape)), np.zeros(bshape))
+        assert str(got.value) == str(want.value)
+    with pytest.raises(orc.ReferencePanic) as want:
+        orc.vector_dot(np.zeros(3), "a", np.zeros(4), "a")
+    with pytest.raises(eml.Panic) as got:
+        eml.Tensor([("a", 3)], np.zeros(3)).scalar_product(eml.Tensor([("a", 4)], np.zeros(4)))
+    assert str(got.value) == str(want.value)
+
+
+def test_einsum_errors_match_oracle(orc):
+    a = eml.Tensor([("a", 2), ("b", 3)], np.zeros((2, 3), np.float32))
+    b = eml.Tensor([("b", 4), ("c", 5)], np.zeros((4, 5), np.float32))
+    for out in (["a", "c"], ["a", "z"]):
+        with pytest.raises(orc.InconsistentDimensionLengthError) as want:
+            orc.einsum2(a.data, a.names(), b.data, b.names(), out)
+        with pytest.raises(eml.InconsistentDimensionLengthError) as got:
+            eml.Einsum.with_2(a, b).to(out)
+        assert (got.value.dimension, got.value.lengths) == (want.value.dimension, want.value.lengths)
+
+
+def test_non_float_types_are_not_this_paths_business():
+    with pytest.raises(TypeError):
+        eml.host._sfx(np.int32)

@@ -1,0 +1,376 @@
+"""Parity of the CUDA path against the CPU oracle, through the C ABI (run with -m gpu on a B200).
+
+Bars (BASELINE.json north_star): shapes / names / tape indexes bit-exact; numbers within
+|gpu - ref| <= tol * sum_k |a_k b_k| with tol = 1e-12 (f64) / 1e-5 (f32); small-integer inputs and the
+`exact` / generic-einsum kernels must match the oracle bit for bit.
+"""
+import ctypes as C
+import hashlib
+
+import numpy as np
+import pytest
+
+import easy_ml_b200 as eml
+from easy_ml_b200 import _ffi
+from easy_ml_b200._ffi import check, lib
+
+pytestmark = pytest.mark.gpu
+
+TOL = {np.dtype(np.float32): 1e-5, np.dtype(np.float64): 1e-12}
+DTYPES = [np.float32, np.float64]
+
+
+def rng(seed):
+    return np.random.default_rng(0x5EED0000 + seed)
+
+
+def uniform(r, shape, dtype):
+    return r.uniform(-1.0, 1.0, size=shape).astype(dtype)
+
+
+def ints(r, shape, dtype):
+    return r.integers(-8, 9, size=shape).astype(dtype)
+
+
+def assert_within(got, a, b, ref, dtype, what=""):
+    """|got - ref| <= tol * (|a| @ |b|) elementwise (the K-scaled bound of the north star)."""
+    scale = np.abs(a).astype(np.float64) @ np.abs(b).astype(np.float64)
+    err = np.abs(got.astype(np.float64) - ref.astype(np.float64))
+    bound = TOL[np.dtype(dtype)] * scale + np.finfo(dtype).tiny
+    worst = np.max(err / bound)
+    assert worst <= 1.0, f"{what}: error {worst:.3g}x the allowed bound"
+
+
+def ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def gemm(a, b, exact=False):
+    sfx = "f32" if a.dtype == np.float32 else "f64"
+    c = np.empty((a.shape[0], b.shape[1]), a.dtype)
+    f = getattr(lib, f"eml_gemm_exact_{sfx}" if exact else f"eml_gemm_{sfx}")
+    check(f(ptr(a), ptr(b), ptr(c), a.shape[0], b.shape[1], a.shape[1], a.shape[1], b.shape[1], b.shape[1]))
+    return c
+
+
+# ------------------------------------------------------------------ reference goldens on the GPU
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_reference_goldens_exact(golden, dtype):
+    for g in golden["matmul"]:
+        got = eml.Matrix(g["a"], dtype) * eml.Matrix(g["b"], dtype)
+        assert got == eml.Matrix(g["expect"], dtype), g["cite"]
+    for g in golden["tensor_matmul"]:
+        a = eml.Tensor(list(zip(g["a_names"], np.shape(g["a"]))), g["a"], dtype)
+        b = eml.Tensor(list(zip(g["b_names"], np.shape(g["b"]))), g["b"], dtype)
+        want = eml.Tensor(list(zip(g["expect_names"], np.shape(g["expect"]))), g["expect"], dtype)
+        assert a * b == want, g["cite"]
+    for g in golden["einsum2"]:
+        a = eml.Tensor(list(zip(g["a_names"], np.shape(g["a"]))), g["a"], dtype)
+        b = eml.Tensor(list(zip(g["b_names"], np.shape(g["b"]))), g["b"], dtype)
+        got = eml.Einsum.with_2(a, b).to(g["out_names"])
+        assert got.names() == g["out_names"]
+        assert np.array_equal(got.data, np.array(g["expect"], dtype)), g["cite"]
+        assert eml.last_kernel() == "einsum_generic"
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_reference_einsum_equivalences(golden, orc, dtype):
+    for g in golden["einsum2_equiv"]:
+        a = eml.Tensor(list(zip(g["a_names"], np.shape(g["a"]))), g["a"], dtype)
+        b = eml.Tensor(list(zip(g["b_names"], np.shape(g["b"]))), g["b"], dtype)
+        got = eml.Einsum.with_2(a, b).to(g["out_names"])
+        want = orc.einsum2(a.data, g["a_names"], b.data, g["b_names"], g["out_names"])
+        assert np.array_equal(got.data, want), g["cite"]  # small integers: exact in any order
+
+
+# ------------------------------------------------------------------ GEMM vs oracle
+SHAPES = [(1, 1, 1), (3, 2, 3), (17, 33, 5), (64, 64, 64), (100, 70, 130), (256, 256, 256), (129, 257, 131),
+          (512, 10, 784), (10, 512, 300), (300, 200, 1)]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("m,n,k", SHAPES)
+def test_gemm_matches_oracle(orc, dtype, m, n, k):
+    r = rng(m * 7 + n * 3 + k)
+    a, b = uniform(r, (m, k), dtype), uniform(r, (k, n), dtype)
+    ref = orc.matrix_mul(a, b, threads=4)
+    assert_within(gemm(a, b), a, b, ref, dtype, f"gemm {m}x{n}x{k}")
+    # exact mode: the reference's operation order, bit for bit
+    assert np.array_equal(gemm(a, b, exact=True), ref)
+    # small integers: exact regardless of summation order
+    ai, bi = ints(r, (m, k), dtype), ints(r, (k, n), dtype)
+    assert np.array_equal(gemm(ai, bi), orc.matrix_mul(ai, bi, threads=4))
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_gemm_c1_config_256(orc, dtype):
+    """BASELINE config 1: 256x256 (the reference's own CPU-runnable case)."""
+    r = rng(1)
+    a, b = uniform(r, (256, 256), dtype), uniform(r, (256, 256), dtype)
+    got = (eml.Matrix(a) * eml.Matrix(b)).data
+    assert_within(got, a, b, orc.matrix_mul(a, b, threads=4), dtype, "C1")
+    t = eml.Tensor([("r", 256), ("c", 256)], a) * eml.Tensor([("x", 256), ("y", 256)], b)
+    assert t.names() == ["r", "y"] and np.array_equal(t.data, got)  # Matrix and Tensor entry points share the kernel
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_gemm_tensor_core_kernels_sampled_rows(orc, dtype):
+    """Sizes that dispatch to the tensor-core kernels; the oracle checks a sample of rows."""
+    r = rng(2)
+    m, n, k = 1024, 768, 1536
+    a, b = uniform(r, (m, k), dtype), uniform(r, (k, n), dtype)
+    got = gemm(a, b)
+    assert eml.last_kernel() in ("dmma_f64", "tf32x3_tcgen05", "simt")
+    rows = [0, 1, 127, 128, 511, 640, 1023]
+    for i in rows:
+        ref = orc.matrix_mul(a[i:i + 1], b)
+        assert_within(got[i:i + 1], a[i:i + 1], b, ref, dtype, f"row {i}")
+    ai, bi = ints(r, (m, k), dtype), ints(r, (k, n), dtype)
+    gi = gemm(ai, bi)
+    assert np.array_equal(gi, (ai.astype(np.float64) @ bi.astype(np.float64)).astype(dtype))
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_gemm_leading_dimensions(orc, dtype):
+    r = rng(3)
+    big_a, big_b = uniform(r, (150, 200), dtype), uniform(r, (200, 180), dtype)
+    a, b = big_a[10:140, 16:176], big_b[16:176, 4:164]  # views with lda/ldb > row length
+    sfx = "f32" if dtype == np.float32 else "f64"
+    c = np.full((130, 170), 7.0, dtype)
+    check(getattr(lib, f"eml_gemm_{sfx}")(ptr(big_a[10:, 16:]), ptr(big_b[16:, 4:]), ptr(c), 130, 160, 160, 200, 180, 170))
+    ref = orc.matrix_mul(np.ascontiguousarray(a), np.ascontiguousarray(b))
+    assert_within(c[:, :160], a, b, ref, dtype, "ld")
+    assert np.all(c[:, 160:] == 7.0)  # elements outside the C view are untouched
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_run_to_run_determinism(dtype):
+    r = rng(4)
+    a, b = uniform(r, (640, 512), dtype), uniform(r, (512, 384), dtype)
+    digests = {hashlib.sha256(gemm(a, b).tobytes()).hexdigest() for _ in range(4)}
+    assert len(digests) == 1
+
+
+def test_bad_arguments_are_errors_not_crashes():
+    a = np.zeros((2, 2), np.float64)
+    with pytest.raises(eml.BadArgError):
+        check(lib.eml_gemm_f64(ptr(a), ptr(a), ptr(a), 2, 2, 0, 2, 2, 2))
+    with pytest.raises(eml.BadArgError):
+        check(lib.eml_gemm_f64(ptr(a), ptr(a), ptr(a), 2, 2, 2, 1, 2, 2))
+    with pytest.raises(eml.BadArgError):
+        check(lib.eml_gemm_f64(None, ptr(a), ptr(a), 2, 2, 2, 2, 2, 2))
+
+
+# ------------------------------------------------------------------ named contraction
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_batched_contraction_vs_oracle(orc, dtype):
+    r = rng(5)
+    bt, m, k, n = 3, 20, 37, 12
+    x = eml.Tensor([("batch", bt), ("row", m), ("k", k)], uniform(r, (bt, m, k), dtype))
+    y = eml.Tensor([("batch", bt), ("k", k), ("col", n)], uniform(r, (bt, k, n), dtype))
+    got = eml.Einsum.with_2(x, y).to(["batch", "row", "col"])
+    assert eml.last_kernel() != "einsum_generic"
+    ref = orc.einsum2(x.data, x.names(), y.data, y.names(), ["batch", "row", "col"])
+    assert got.shape() == [("batch", bt), ("row", m), ("col", n)]
+    for i in range(bt):
+        assert_within(got.data[i], x.data[i], y.data[i], ref[i], dtype, f"batch {i}")
+    # permuted dimension orders need no host transpose: same numbers
+    xp = eml.Tensor([("row", m), ("batch", bt), ("k", k)], np.ascontiguousarray(x.data.transpose(1, 0, 2)))
+    yp = eml.Tensor([("col", n), ("k", k), ("batch", bt)], np.ascontiguousarray(y.data.transpose(2, 1, 0)))
+    for out in (["batch", "row", "col"], ["batch", "col", "row"], ["row", "batch", "col"], ["col", "row", "batch"]):
+        g2 = eml.Einsum.with_2(xp, yp).to(out)
+        ref2 = orc.einsum2(xp.data, xp.names(), yp.data, yp.names(), out)
+        assert g2.names() == out
+        back = np.transpose(g2.data, [out.index(d) for d in ("batch", "row", "col")])
+        refb = np.transpose(ref2, [out.index(d) for d in ("batch", "row", "col")])
+        for i in range(bt):
+            assert_within(back[i], x.data[i], y.data[i], refb[i], dtype, f"{out} batch {i}")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_generic_einsum_is_bit_exact(orc, dtype):
+    r = rng(6)
+    a = uniform(r, (5, 7, 3), dtype)
+    b = uniform(r, (3, 4, 7), dtype)
+    cases = [(["i", "j", "k"], ["k", "l", "j"], ["i", "l"]),          # two summation dims
+             (["i", "j", "k"], ["k", "l", "j"], ["i", "j", "l"]),     # batch-like j
+             (["i", "j", "k"], ["k", "l", "j"], []),                  # full reduction
+             (["i", "j", "k"], ["x", "l", "y"], ["i", "l"]),          # unrelated dims summed on each side
+             (["i", "j", "k"], ["k", "l", "j"], ["l", "k", "j", "i"])]  # no summation
+    for an, bn, out in cases:
+        x, y = eml.Tensor(list(zip(an, a.shape)), a), eml.Tensor(list(zip(bn, b.shape)), b)
+        check(0)
+        sfx = "f32" if dtype == np.float32 else "f64"
+        got = eml.Einsum.with_2(x, y).to(out)
+        want = orc.einsum2(a, an, b, bn, out)
+        if eml.last_kernel() == "einsum_generic":
+            assert np.array_equal(got.data, want), (an, bn, out)
+        else:
+            assert np.allclose(got.data, want, rtol=1e-4 if sfx == "f32" else 1e-11)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_vector_dot(orc, dtype):
+    r = rng(7)
+    for n in (1, 3, 1000, 100003):
+        a, b = uniform(r, n, dtype), uniform(r, n, dtype)
+        got = eml.Tensor([("a", n)], a).scalar_product(eml.Tensor([("a", n)], b))
+        ref = orc.vector_dot(a, "a", b, "a")
+        assert abs(float(got) - float(ref)) <= TOL[np.dtype(dtype)] * float(np.abs(a).astype(np.float64) @ np.abs(b)) + 1e-300
+
+
+# ------------------------------------------------------------------ autodiff
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_record_matmul_reference_fixture(orc, golden, dtype):
+    """container_record/mod.rs:2718-2903: numbers, every derivative, and tape length."""
+    g = golden["record_matmul"][0]
+    a, b = np.array(g["a"], dtype), np.array(g["b"], dtype)
+    for kind in ("tensor", "matrix"):
+        hist = eml.WengertList(dtype)
+        if kind == "tensor":
+            ra = eml.RecordTensor.variables(hist, eml.Tensor([("r", 4), ("c", 3)], a))
+            rb = eml.RecordTensor.variables(hist, eml.Tensor([("r", 3), ("c", 4)], b))
+        else:
+            ra = eml.RecordMatrix.variables(hist, eml.Matrix(a))
+            rb = eml.RecordMatrix.variables(hist, eml.Matrix(b))
+        rc = ra * rb
+        tape = orc.Tape(dtype)
+        oa, ob = tape.variables(a), tape.variables(b)
+        oc, oci = tape.matmul(oa, ob)
+        assert np.array_equal(rc.numbers().data, np.array(g["expect"], dtype))
+        assert len(hist) == len(tape)
+        assert np.array_equal(ra.indexes(), oa[1]) and np.array_equal(rb.indexes(), ob[1])
+        assert np.array_equal(rc.indexes(), oci)
+        for i in range(4):
+            for j in range(4):
+                d = rc.derivatives_for([i, j]) if kind == "tensor" else rc.derivatives_for(i, j)
+                od = tape.derivatives(oci[i, j])
+                da = d.at_tensor(ra).data if kind == "tensor" else d.at_matrix(ra).data
+                db = d.at_tensor(rb).data if kind == "tensor" else d.at_matrix(rb).data
+                assert np.array_equal(da, od[oa[1]]) and np.array_equal(db, od[ob[1]])
+                assert len(d) == len(tape)
+                if i == 1 and j == 2:
+                    assert np.array_equal(d.to_vec(), od)  # Vec::from(Derivatives), interior entries included
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_record_chain_vs_scalar_tape(orc, dtype):
+    """Two-layer network with container ops only: tape length, indexes, loss and gradients vs the oracle's
+    literal scalar tape (including the reference's constants-carry-Index-0 behaviour)."""
+    r = rng(8)
+    n, din, dh, dout = 6, 5, 4, 3
+    x = r.uniform(0, 1, (n, din)).astype(dtype)
+    w1 = r.uniform(-0.5, 0.5, (din, dh)).astype(dtype)
+    w2 = r.uniform(-0.5, 0.5, (dh, dout)).astype(dtype)
+    tgt = r.uniform(0, 1, (n, dout)).astype(dtype)
+    ones_l, ones_r = np.ones((1, n), dtype), np.ones((dout, 1), dtype)
+
+    hist = eml.WengertList(dtype)
+    T = lambda names, a: eml.Tensor(list(zip(names, a.shape)), a)
+    W1 = eml.RecordTensor.variables(hist, T(["i", "h"], w1))
+    W2 = eml.RecordTensor.variables(hist, T(["h", "o"], w2))
+    X = eml.RecordTensor.constants(T(["n", "i"], x), hist)
+    Y = eml.RecordTensor.constants(T(["n", "o"], tgt), hist)
+    L = eml.RecordTensor.constants(T(["u", "n"], ones_l), hist)
+    R = eml.RecordTensor.constants(T(["o", "v"], ones_r), hist)
+
+    def sigmoid(z):
+        return ((-z).exp() + 1.0).div_swapped(1.0)
+
+    h = sigmoid(X * W1)
+    out = sigmoid(h * W2)
+    diff = out - Y
+    sq = diff.elementwise_multiply(diff)
+    loss = ((L * sq) * R) / float(n)
+
+    tape = orc.Tape(dtype)
+    ow1, ow2 = tape.variables(w1), tape.variables(w2)
+    ox, oy = orc.Tape.constants(x, dtype), orc.Tape.constants(tgt, dtype)
+    ol, orr = orc.Tape.constants(ones_l, dtype), orc.Tape.constants(ones_r, dtype)
+
+    def osig(z):
+        return tape.unary(12, tape.unary(6, tape.unary(3, tape.unary(0, z)), 1.0), 1.0)
+
+    oh = osig(tape.matmul(ox, ow1))
+    oout = osig(tape.matmul(oh, ow2))
+    odiff = tape.binary(33, oout, oy, mode=1)
+    osq = tape.binary(34, odiff, odiff, mode=3)
+    oloss = tape.unary(9, tape.matmul(tape.matmul(ol, osq), orr), float(n))
+
+    assert len(hist) == len(tape)
+    assert np.array_equal(loss.indexes(), oloss[1]) and np.array_equal(out.indexes(), oout[1])
+    rtol = 2e-5 if dtype == np.float32 else 1e-12
+    assert np.allclose(loss.numbers().data, oloss[0], rtol=rtol)
+    d = loss.derivatives_for([0, 0])
+    od = tape.derivatives(oloss[1][0, 0])
+    atol = (2e-6 if dtype == np.float32 else 1e-13) * max(1.0, float(np.abs(od).max()))
+    for rec, (_, oidx) in ((W1, ow1), (W2, ow2)):
+        assert np.allclose(d.at_tensor(rec).data, od[oidx], rtol=50 * rtol, atol=atol)
+    # the constant operand X carries Index 0 == W1[0,0]: its derivative sum lands there, as in the reference
+    assert abs(float(d.at_index(0)) - float(od[0])) <= 50 * rtol * abs(float(od[0])) + atol
+    plain = np.zeros_like(w1)  # what W1[0,0]'s gradient would be WITHOUT the quirk differs from od[0]
+    assert od[0] != plain[0, 0]
+
+    # SGD update + clear + reset renumbers the variables exactly like the reference
+    before = W1.numbers().data.copy()
+    eml.sgd_update(W1, d, 0.1)
+    assert len(hist) == len(tape) + w1.size
+    assert np.allclose(W1.numbers().data, before - d.at_index(0) * 0 - 0.1 * od[ow1[1]], rtol=50 * rtol, atol=atol)
+    hist.clear()
+    W1.reset()
+    W2.reset()
+    assert len(hist) == w1.size + w2.size
+    assert np.array_equal(W1.indexes().ravel(), np.arange(w1.size))
+    assert np.array_equal(W2.indexes().ravel(), w1.size + np.arange(w2.size))
+
+
+def test_stale_and_untracked_containers():
+    hist = eml.WengertList(np.float64)
+    w = eml.RecordMatrix.variables(hist, eml.Matrix([[1.0, 2.0], [3.0, 4.0]]))
+    c = eml.RecordMatrix.constants(eml.Matrix([[1.0, 0.0], [0.0, 1.0]]), hist)
+    cc = c * c
+    assert len(hist) == 4 and cc.history() is None and cc.derivatives_for(0, 0) is None
+    assert np.array_equal(cc.indexes(), np.zeros((2, 2), np.int64))
+    hist.clear()
+    with pytest.raises(eml.StateError):
+        w * c  # not reset after clear: the reference would index out of bounds
+    w.reset()
+    y = w * c
+    assert len(hist) == 4 + 4 * 3
+    with pytest.raises(eml.Panic):
+        w * eml.RecordMatrix.constants(eml.Matrix([[1.0, 2.0, 3.0]]), hist)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_container_elementwise_rules(orc, dtype):
+    r = rng(9)
+    x = r.uniform(0.5, 2.0, (7, 9)).astype(dtype)
+    y = r.uniform(0.5, 2.0, (7, 9)).astype(dtype)
+    hist = eml.WengertList(dtype)
+    X = eml.RecordMatrix.variables(hist, eml.Matrix(x))
+    Y = eml.RecordMatrix.variables(hist, eml.Matrix(y))
+    tape = orc.Tape(dtype)
+    ox, oy = tape.variables(x), tape.variables(y)
+    exact_ops = [("NEG", 0.0), ("ADD_C", 1.5), ("SUB_C", 0.25), ("MUL_C", 3.0), ("DIV_C", 3.0), ("C_SUB", 2.0),
+                 ("C_DIV", 2.0), ("SQRT", 0.0)]
+    approx_ops = [("EXP", 0.0), ("LN", 0.0), ("SIN", 0.0), ("COS", 0.0), ("POW_C", 2.5)]
+    for name, c in exact_ops + approx_ops:
+        z = X._unary(name, c)
+        oz, ozi = tape.unary(eml.OPS[name], ox, c)
+        assert np.array_equal(z.indexes(), ozi)
+        d = z.derivatives_for(3, 4).at_matrix(X).data
+        od = tape.derivatives(ozi[3, 4])[ox[1]]
+        if (name, c) in exact_ops:
+            assert np.array_equal(z.numbers().data, oz), name
+            assert np.array_equal(d, od), name
+        else:
+            assert np.allclose(z.numbers().data, oz, rtol=1e-6 if dtype == np.float32 else 1e-14), name
+            assert np.allclose(d, od, rtol=1e-5 if dtype == np.float32 else 1e-13), name
+    for name in ("ADD", "SUB", "MUL", "DIV"):
+        z = X._binary(name, Y)
+        oz, ozi = tape.binary(eml.OPS[name], ox, oy)
+        assert np.array_equal(z.numbers().data, oz) and np.array_equal(z.indexes(), ozi)
+        dd = z.derivatives_for(6, 8)
+        od = tape.derivatives(ozi[6, 8])
+        assert np.array_equal(dd.at_matrix(X).data, od[ox[1]]) and np.array_equal(dd.at_matrix(Y).data, od[oy[1]])
+    assert len(hist) == len(tape)
