@@ -51,7 +51,6 @@ int contract_dev(DeviceCtx* ctx, const T* A, const T* B, T* C, int64_t batch, in
                            (long long)K);
     if (batch == 0 || M == 0 || N == 0) return EML_OK;
     if (!A || !B || !C) EML_BAD_ARG("contract: null operand");
-    if (!stream) stream = ctx->stream;
     if (!exact && Threshold<T>::tensor_core(M, N, K)) {
         // the tensor-core kernels want C's column index contiguous; a row-contiguous C is the transposed
         // problem C^T = B^T A^T with the same kernels
@@ -209,8 +208,7 @@ int matmul_bwd_dev(const T* dC, const T* A, const T* B, T* dA, T* dB, int64_t M,
 #define EML_STREAM_OR_CTX(st)                 \
     DeviceCtx* ctx = nullptr;                 \
     EML_TRY(get_ctx(&ctx));                   \
-    cudaStream_t st = (cudaStream_t)stream;   \
-    if (!st) st = ctx->stream;
+    cudaStream_t st = (cudaStream_t)stream;
 
 }  // namespace
 }  // namespace eml

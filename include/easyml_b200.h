@@ -17,7 +17,7 @@
  *    bit-identical run to run on the same GPU model.
  *  - host entry points (no suffix) take HOST pointers, stage through pinned memory and block until the
  *    result is in the caller's buffer.  `_dev` entry points take DEVICE pointers plus a cudaStream_t
- *    (as void*; NULL = the library's stream for the current device) and are asynchronous.
+ *    (as void*; NULL = CUDA's default stream, exactly as in the CUDA runtime) and are asynchronous.
  *  - the device used is the calling thread's current CUDA device (cudaSetDevice / torch.cuda.set_device);
  *    state is cached per device; entry points are re-entrant across threads.
  */
