@@ -15,7 +15,11 @@
 // Determinism: fixed tile -> CTA map, k tiles consumed in ascending order, no atomics, no split-K.
 //
 // Algorithmic work per launch: 2*M*N*K flop; (M*K + K*N + M*N) * 8 bytes.
+#include <cstdlib>
+#include <string>
+
 #include "common.h"
+#include "sm100.cuh"
 
 namespace eml {
 
@@ -220,6 +224,210 @@ int launch_variant(const double* A, const double* B, double* C, int64_t batch, i
 
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// =================================================================================================
+// TMA-staged, warp-specialised variant (the fast path).
+//
+// One producer lane issues cp.async.bulk.tensor (TMA) loads into a 3-stage ring; eight consumer warps
+// wait on the stage's `full` mbarrier, run the DMMA fragments and arrive on its `empty` mbarrier.  No
+// CTA-wide barrier in the main loop: the consumer warps never wait for each other.
+//
+// Shared-memory tiles are laid out by the TMA box itself so that fragment loads stay conflict free
+// without padding (TMA writes dense boxes): the tensor map views each operand with a 4-element
+// (32-byte) innermost dimension, so the 4 (k or mn) x 4 (mn or k) elements a half-warp reads are 16
+// consecutive doubles:
+//   K-inner  operand: dims (4, MN, K/4, batch),  box (4, 128, BK/4, 1) -> smem [k/4][mn][k%4]
+//   MN-inner operand: dims (4, K, MN/4, batch),  box (4, BK, 32, 1)    -> smem [mn/4][k][mn%4]
+// Out-of-range box rows are zero-filled by TMA (ragged M/N/K tails need no special code).
+// =================================================================================================
+namespace tma {
+
+// 8 consumer warps (two warpgroups) + one producer warpgroup (one lane of it works).  The register file is
+// re-split with setmaxnreg: a 384-thread CTA compiles to <= 168 registers per thread, the consumers need
+// 128 for the accumulators alone, so the producer warpgroup hands its share over (40 vs 232).
+constexpr int TBK = 32, TSTAGES = 3, CONSUMER_WARPS = 8, TTHREADS = (CONSUMER_WARPS + 4) * 32;
+constexpr int PRODUCER_REGS = 40, CONSUMER_REGS = 232;  // 4*32*40 + 8*32*232 = 64512 <= 65536
+constexpr int T_OPERAND_ELEMS = BM * TBK;                      // 4096 doubles = 32 KB
+constexpr int T_STAGE_ELEMS = 2 * T_OPERAND_ELEMS;             // 64 KB
+constexpr uint32_t T_STAGE_BYTES = T_STAGE_ELEMS * sizeof(double);
+constexpr size_t T_SMEM_BYTES = (size_t)TSTAGES * T_STAGE_BYTES + 128 /*align*/ + 64 /*barriers*/;
+
+template <bool A_KIN, bool B_KIN>
+__global__ void __launch_bounds__(TTHREADS, 1)
+dgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, double* C,
+                 int64_t M, int64_t N, int64_t K, int64_t ldc, int64_t strideC, int tiles_m, int tiles_n,
+                 int accumulate) {
+    using namespace sm100;
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    // offset (not a cast through an integer) so the compiler keeps the shared address space: LDS, not LD
+    uint8_t* base = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+    double* tiles = reinterpret_cast<double*>(base);
+    uint64_t* full = reinterpret_cast<uint64_t*>(base + (size_t)TSTAGES * T_STAGE_BYTES);
+    uint64_t* empty = full + TSTAGES;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    constexpr int GROUP = 8;
+    int tile = blockIdx.x;
+    int tiles_per_group = GROUP * tiles_n;
+    int group = tile / tiles_per_group;
+    int first_m = group * GROUP;
+    int group_rows = tiles_m - first_m < GROUP ? tiles_m - first_m : GROUP;
+    int in_group = tile % tiles_per_group;
+    const int tm = first_m + in_group % group_rows;
+    const int tn = in_group / group_rows;
+    const int batch = blockIdx.y;
+    const int ktiles = (int)((K + TBK - 1) / TBK);
+
+    if (tid == 0) {
+        prefetch_tensormap(&mapA);
+        prefetch_tensormap(&mapB);
+        for (int s = 0; s < TSTAGES; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], CONSUMER_WARPS);
+        }
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    if (warp >= CONSUMER_WARPS) {
+        // ---------------- producer warpgroup ----------------
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PRODUCER_REGS));
+        if (warp == CONSUMER_WARPS && lane == 0) {
+            for (int kt = 0; kt < ktiles; kt++) {
+                const int s = kt % TSTAGES;
+                if (kt >= TSTAGES) mbar_wait(&empty[s], ((kt / TSTAGES) - 1) & 1);
+                double* sA = tiles + (size_t)s * T_STAGE_ELEMS;
+                double* sB = sA + T_OPERAND_ELEMS;
+                mbar_expect_tx(&full[s], T_STAGE_BYTES);
+                if (A_KIN)
+                    tma_load_4d(sA, &mapA, &full[s], 0, tm * BM, kt * (TBK / 4), batch);
+                else
+                    tma_load_4d(sA, &mapA, &full[s], 0, kt * TBK, tm * (BM / 4), batch);
+                if (B_KIN)
+                    tma_load_4d(sB, &mapB, &full[s], 0, tn * BN, kt * (TBK / 4), batch);
+                else
+                    tma_load_4d(sB, &mapB, &full[s], 0, kt * TBK, tn * (BN / 4), batch);
+            }
+        }
+        return;
+    }
+
+    // ---------------- consumers ----------------
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CONSUMER_REGS));
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = (warp >> 2) * 64, wn = (warp & 3) * 32;
+    const int64_t m0 = (int64_t)tm * BM, n0 = (int64_t)tn * BN;
+    C += (int64_t)batch * strideC;
+
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            acc[i][j][0] = acc[i][j][1] = 0.0;
+            if (accumulate) {  // continue the k-ordered chain from C (see the cp.async kernel)
+                int64_t row = m0 + wm + i * 8 + g, col = n0 + wn + j * 8 + 2 * t;
+                if (row < M && col < N) acc[i][j][0] = C[row * ldc + col];
+                if (row < M && col + 1 < N) acc[i][j][1] = C[row * ldc + col + 1];
+            }
+        }
+
+    // per-thread fragment offset inside an operand tile (fragment 0, ks = 0); fragment i is 8 rows further
+    // on, which is a compile-time stride in both layouts, so every LDS uses base + immediate
+    const int ra = wm + g, cb = wn + g;
+    const int a_off = A_KIN ? ra * 4 + t : (ra >> 2) * (TBK * 4) + t * 4 + (ra & 3);
+    const int b_off = B_KIN ? cb * 4 + t : (cb >> 2) * (TBK * 4) + t * 4 + (cb & 3);
+    constexpr int A_FR = A_KIN ? 32 : 2 * TBK * 4;  // +8 rows
+    constexpr int B_FR = B_KIN ? 32 : 2 * TBK * 4;
+    constexpr int A_KS = A_KIN ? BM * 4 : 16;  // offset of the next group of 4 k inside the tile
+    constexpr int B_KS = B_KIN ? BN * 4 : 16;
+
+    for (int kt = 0; kt < ktiles; kt++) {
+        const int s = kt % TSTAGES;
+        mbar_wait(&full[s], (kt / TSTAGES) & 1);
+        const double* sA = tiles + (size_t)s * T_STAGE_ELEMS;
+        const double* sB = sA + T_OPERAND_ELEMS;
+#pragma unroll
+        for (int ks = 0; ks < TBK / 4; ks++) {
+            double a[8], b[4];
+#pragma unroll
+            for (int i = 0; i < 8; i++) a[i] = sA[a_off + i * A_FR + ks * A_KS];
+#pragma unroll
+            for (int j = 0; j < 4; j++) b[j] = sB[b_off + j * B_FR + ks * B_KS];
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+    }
+
+    const bool vec_ok = ((ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        int64_t row = m0 + wm + i * 8 + g;
+        if (row >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            int64_t col = n0 + wn + j * 8 + 2 * t;
+            if (col >= N) continue;
+            double* p = C + row * ldc + col;
+            if (vec_ok && col + 1 < N) {
+                *reinterpret_cast<double2*>(p) = make_double2(acc[i][j][0], acc[i][j][1]);
+            } else {
+                p[0] = acc[i][j][0];
+                if (col + 1 < N) p[1] = acc[i][j][1];
+            }
+        }
+    }
+}
+
+// Tensor map of one operand.  KIN: element (mn, k) at base[mn*ld + k]; else at base[k*ld + mn].
+int operand_map(CUtensorMap* map, const double* base, bool kin, int64_t mn, int64_t k, int64_t ld, int64_t batch,
+                int64_t batch_stride) {
+    uint64_t dims[4], strides[3];
+    uint32_t box[4];
+    uint64_t bs = (uint64_t)(batch > 1 ? batch_stride : 2) * 8;
+    if (kin) {
+        dims[0] = 4; dims[1] = (uint64_t)mn; dims[2] = (uint64_t)(k / 4); dims[3] = (uint64_t)batch;
+        box[0] = 4; box[1] = BM; box[2] = TBK / 4; box[3] = 1;
+    } else {
+        dims[0] = 4; dims[1] = (uint64_t)k; dims[2] = (uint64_t)(mn / 4); dims[3] = (uint64_t)batch;
+        box[0] = 4; box[1] = TBK; box[2] = BM / 4; box[3] = 1;
+    }
+    strides[0] = (uint64_t)ld * 8;
+    strides[1] = 32;
+    strides[2] = bs;
+    return sm100::make_tensor_map(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, base, dims, strides, box,
+                                  CU_TENSOR_MAP_SWIZZLE_NONE);
+}
+
+template <bool A_KIN, bool B_KIN>
+int launch(const double* A, const double* B, double* C, int64_t batch, int64_t M, int64_t N, int64_t K, int64_t lda,
+           int64_t ldb, int64_t ldc, int64_t stA, int64_t stB, int64_t stC, bool accumulate, cudaStream_t stream) {
+    CUtensorMap mapA, mapB;
+    EML_TRY(operand_map(&mapA, A, A_KIN, M, K, lda, batch, stA));
+    EML_TRY(operand_map(&mapB, B, B_KIN, N, K, ldb, batch, stB));
+    auto kern = dgemm_tma_kernel<A_KIN, B_KIN>;
+    static thread_local int configured_dev = -1;
+    int dev = 0;
+    EML_CUDA(cudaGetDevice(&dev));
+    if (configured_dev != dev) {
+        EML_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T_SMEM_BYTES));
+        configured_dev = dev;
+    }
+    int64_t tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
+    dim3 grid((unsigned)(tiles_m * tiles_n), (unsigned)batch);
+    kern<<<grid, TTHREADS, T_SMEM_BYTES, stream>>>(mapA, mapB, C, M, N, K, ldc, stC, (int)tiles_m, (int)tiles_n,
+                                                   accumulate ? 1 : 0);
+    count_launch();
+    set_last_kernel("dmma_f64_tma");
+    return check_launch("dgemm_tma");
+}
+
+}  // namespace tma
+
 }  // namespace
 
 int launch_gemm_dmma_f64(DeviceCtx*, const double* A, const double* B, double* C, int64_t batch, int64_t M,
@@ -242,7 +450,21 @@ int launch_gemm_dmma_f64(DeviceCtx*, const double* A, const double* B, double* C
     int64_t ldc = sC.r;
     bool vec = al16(A) && al16(B) && (lda % 2 == 0) && (ldb % 2 == 0) && (sA.b % 2 == 0) && (sB.b % 2 == 0);
     *handled = true;
-#define EML_D(AK, BKK)                                                                                           \
+    // TMA path: 16-byte aligned rows and the 4-element inner box dimension must tile the contiguous index
+    // EML_DGEMM_KERNEL=cpasync selects the cp.async kernel (A/B comparisons in tests and bench); read per call
+    const char* forced = getenv("EML_DGEMM_KERNEL");
+    const bool force_cpasync = forced && std::string(forced) == "cpasync";
+    bool tma_ok = vec && !force_cpasync && al16(C) && ((A_KIN ? K : M) % 4 == 0) && ((B_KIN ? K : N) % 4 == 0);
+    if (tma_ok) {
+        if (A_KIN && !B_KIN)
+            return tma::launch<true, false>(A, B, C, batch, M, N, K, lda, ldb, ldc, sA.b, sB.b, sC.b, accumulate, stream);
+        if (A_KIN && B_KIN)
+            return tma::launch<true, true>(A, B, C, batch, M, N, K, lda, ldb, ldc, sA.b, sB.b, sC.b, accumulate, stream);
+        if (!A_KIN && !B_KIN)
+            return tma::launch<false, false>(A, B, C, batch, M, N, K, lda, ldb, ldc, sA.b, sB.b, sC.b, accumulate, stream);
+        return tma::launch<false, true>(A, B, C, batch, M, N, K, lda, ldb, ldc, sA.b, sB.b, sC.b, accumulate, stream);
+    }
+#define EML_D(AK, BKK)                                                                                          \
     return vec ? launch_variant<AK, BKK, 2>(A, B, C, batch, M, N, K, lda, ldb, ldc, sA.b, sB.b, sC.b, accumulate, \
                                             stream)                                                              \
                : launch_variant<AK, BKK, 1>(A, B, C, batch, M, N, K, lda, ldb, ldc, sA.b, sB.b, sC.b, accumulate, \
