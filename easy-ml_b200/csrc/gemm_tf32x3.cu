@@ -1,9 +1,366 @@
-// gemm_tf32x3.cu -- placeholder until the tcgen05 kernel lands: reports "not handled" so f32 uses SIMT.
+// gemm_tf32x3.cu -- f32 GEMM at f32-level accuracy on the 5th-generation tensor cores (tcgen05) for sm_100a.
+//
+// "3xTF32": every f32 operand x is split into big = tf32(x) and small = tf32(x - big); the product is
+//      A*B ~= Asmall*Bbig + Abig*Bsmall + Abig*Bbig        (the dropped small*small term is ~2^-22 relative)
+// with f32 accumulation in tensor memory (TMEM).  Products of two TF32 numbers are exact in f32, so the
+// result carries f32-level error (checked against the oracle within 1e-5 * sum_k |a_k b_k|).
+//
+// Pipeline of one call
+//   1. split_pack_kernel (HBM-bound): reads an operand once through ANY (batch, mn, k) strides -- so
+//      row-major A, row-major B and the transposed reads of the backward products need no separate
+//      transpose -- and writes big/small planes in the canonical K-major layout [batch][MN_pad][K_pad],
+//      zero padded to whole tiles (ragged edges vanish from the GEMM main loop).
+//   2. tf32x3_kernel, one 128 x BN output tile per CTA (BN = 256 or 128), warp-specialised:
+//        warp 0      TMA producer: cp.async.bulk.tensor 128B-swizzled boxes of Abig, Asmall, Bbig, Bsmall
+//                    into a ring of shared-memory stages (mbarrier full/empty)
+//        warp 1      allocates TMEM; one elected lane issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8):
+//                    12 MMAs per 32-wide k block (3 products x 4 k steps), k blocks ascending,
+//                    tcgen05.commit releases the stage / signals the epilogue
+//        warps 2..5  epilogue: tcgen05.ld 32 lanes x 32 columns -> registers -> 128-byte row stores
+//                    (optionally C += ...), bounds-checked against the unpadded M, N
+//      Optional deterministic split-K (grid.z): each split writes its partial tile to a workspace and
+//      splitk_reduce_kernel adds the partials in ascending split order (fixed order, no atomics).
+//
+// Determinism: fixed tile -> CTA map, fixed k order inside a CTA, fixed split order in the reduction.
+// Algorithmic work per launch: 2*M*N*K flop (the 3x tensor work is an implementation cost, not counted);
+// bytes (M*K + K*N + M*N) * 4.
+#include <cstdlib>
+#include <string>
+
 #include "common.h"
+#include "sm100.cuh"
+
 namespace eml {
-int launch_gemm_tf32x3_f32(DeviceCtx*, const float*, const float*, float*, int64_t, int64_t, int64_t, int64_t,
-                           Strides3, Strides3, Strides3, bool, cudaStream_t, bool* handled) {
-    *handled = false;
+
+namespace {
+
+using namespace sm100;
+
+constexpr int BM = 128, BK = 32;  // BK f32 = 128 bytes = one SWIZZLE_128B row
+constexpr int GEMM_THREADS = 192; // 6 warps: producer, mma, 4 epilogue
+
+template <int BN>
+struct Cfg {
+    static constexpr int A_TILE_BYTES = BM * BK * 4;          // 16 KB
+    static constexpr int B_TILE_BYTES = BN * BK * 4;          // 32 KB (BN=256) / 16 KB (BN=128)
+    static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
+    static constexpr int STAGES = (BN == 256) ? 2 : 3;        // 192 KB either way
+    static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 128 /*barriers*/;
+    static constexpr uint32_t TMEM_COLS = BN;                 // f32 accumulator: one column per n
+};
+
+// ------------------------------------------------------------------------------------------------
+// split + pack: src element (b, mn, k) at src[b*sb + mn*smn + k*sk]  ->  big/small[b][mn][k], padded.
+// 32 x 32 tiles through shared memory so both the read (along whichever source index is contiguous)
+// and the write (along k) are coalesced.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+__global__ void __launch_bounds__(256)
+split_pack_kernel(const float* __restrict__ src, float* __restrict__ big, float* __restrict__ small, int64_t MN,
+                  int64_t K, int64_t MNp, int64_t Kp, int64_t sb, int64_t smn, int64_t sk, int k_fast) {
+    __shared__ float tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    const int64_t k0 = (int64_t)blockIdx.x * 32, mn0 = (int64_t)blockIdx.y * 32, b = blockIdx.z;
+    const float* s = src + b * sb;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        int row = ty + r * 8;
+        // k_fast: tx walks k (source contiguous along k); else tx walks mn
+        int64_t mn = mn0 + (k_fast ? row : tx), k = k0 + (k_fast ? tx : row);
+        float v = (mn < MN && k < K) ? s[mn * smn + k * sk] : 0.0f;
+        if (k_fast)
+            tile[row][tx] = v;  // [mn][k]
+        else
+            tile[tx][row] = v;  // [mn][k]
+    }
+    __syncthreads();
+    const int64_t plane = MNp * Kp;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        int row = ty + r * 8;
+        int64_t mn = mn0 + row, k = k0 + tx;  // Kp, MNp are multiples of 32: always in range
+        float v = tile[row][tx];
+        float hi = to_tf32(v);
+        float lo = to_tf32(v - hi);
+        int64_t o = b * plane + mn * Kp + k;
+        big[o] = hi;
+        small[o] = lo;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the GEMM
+// ------------------------------------------------------------------------------------------------
+struct Maps {
+    CUtensorMap a_big, a_small, b_big, b_small;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+tf32x3_kernel(const __grid_constant__ Maps maps, float* __restrict__ C, int64_t M, int64_t N, int64_t ldc,
+              int64_t strideC, int kblocks_total, int kblocks_per_split, int accumulate, float* __restrict__ ws,
+              int64_t ws_split_stride) {
+    using cfg = Cfg<BN>;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* full = reinterpret_cast<uint64_t*>(base + (size_t)cfg::STAGES * cfg::STAGE_BYTES);
+    uint64_t* empty = full + cfg::STAGES;
+    uint64_t* acc_ready = empty + cfg::STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_ready + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // tile raster: groups of 16 tile rows walked column by column, so one wave of 148 CTAs touches a
+    // near-square set of A and B panels (DRAM traffic per wave ~ its perimeter)
+    constexpr int GROUP = 16;
+    const int tiles_m = (int)((M + BM - 1) / BM), tiles_n = (int)((N + BN - 1) / BN);
+    const int tiles_per_group = GROUP * tiles_n;
+    const int first_m = ((int)blockIdx.x / tiles_per_group) * GROUP;
+    const int group_rows = tiles_m - first_m < GROUP ? tiles_m - first_m : GROUP;
+    const int in_group = (int)blockIdx.x % tiles_per_group;
+    const int tm = first_m + in_group % group_rows;
+    const int tn = in_group / group_rows;
+    const int batch = blockIdx.y, split = blockIdx.z;
+    const int kb0 = split * kblocks_per_split;
+    const int kb1 = min(kblocks_total, kb0 + kblocks_per_split);
+    const int nkb = kb1 - kb0;  // >= 1 by construction of the grid
+
+    if (threadIdx.x == 0) {
+        prefetch_tensormap(&maps.a_big);
+        prefetch_tensormap(&maps.a_small);
+        prefetch_tensormap(&maps.b_big);
+        prefetch_tensormap(&maps.b_small);
+        for (int s = 0; s < cfg::STAGES; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(acc_ready, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_acc = *tmem_slot;
+
+    if (warp == 0) {
+        // ---------------- TMA producer ----------------
+        if (lane == 0) {
+            for (int i = 0; i < nkb; i++) {
+                const int s = i % cfg::STAGES;
+                if (i >= cfg::STAGES) mbar_wait(&empty[s], ((i / cfg::STAGES) - 1) & 1);
+                uint8_t* st = base + (size_t)s * cfg::STAGE_BYTES;
+                mbar_expect_tx(&full[s], cfg::STAGE_BYTES);
+                const int kc = (kb0 + i) * BK;
+                tma_load_3d(st, &maps.a_big, &full[s], kc, tm * BM, batch);
+                tma_load_3d(st + cfg::A_TILE_BYTES, &maps.a_small, &full[s], kc, tm * BM, batch);
+                tma_load_3d(st + 2 * cfg::A_TILE_BYTES, &maps.b_big, &full[s], kc, tn * BN, batch);
+                tma_load_3d(st + 2 * cfg::A_TILE_BYTES + cfg::B_TILE_BYTES, &maps.b_small, &full[s], kc, tn * BN, batch);
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------- MMA issuer ----------------
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_tf32(BM, BN);
+            for (int i = 0; i < nkb; i++) {
+                const int s = i % cfg::STAGES;
+                mbar_wait(&full[s], (i / cfg::STAGES) & 1);
+                tc_fence_after();
+                const uint32_t st = smem_u32(base + (size_t)s * cfg::STAGE_BYTES);
+                const uint64_t a_big = umma_desc_k_sw128(st);
+                const uint64_t a_small = umma_desc_k_sw128(st + cfg::A_TILE_BYTES);
+                const uint64_t b_big = umma_desc_k_sw128(st + 2 * cfg::A_TILE_BYTES);
+                const uint64_t b_small = umma_desc_k_sw128(st + 2 * cfg::A_TILE_BYTES + cfg::B_TILE_BYTES);
+                // small terms first, then the dominant one; 8 tf32 = 32 bytes per k step (>>4 = 2)
+#pragma unroll
+                for (int k = 0; k < BK / 8; k++) umma_tf32(tmem_acc, a_small + 2 * k, b_big + 2 * k, idesc, (i | k) != 0);
+#pragma unroll
+                for (int k = 0; k < BK / 8; k++) umma_tf32(tmem_acc, a_big + 2 * k, b_small + 2 * k, idesc, 1);
+#pragma unroll
+                for (int k = 0; k < BK / 8; k++) umma_tf32(tmem_acc, a_big + 2 * k, b_big + 2 * k, idesc, 1);
+                umma_commit(&empty[s]);  // the stage is free once these MMAs have read it
+            }
+            umma_commit(acc_ready);
+        }
+    } else {
+        // ---------------- epilogue: TMEM -> registers -> global ----------------
+        const int q = warp & 3;  // TMEM lane quarter this warp may read
+        mbar_wait(acc_ready, 0);
+        tc_fence_after();
+        const int64_t row = (int64_t)tm * BM + q * 32 + lane;
+        const int64_t n0 = (int64_t)tn * BN;
+        float* out;
+        int64_t ld;
+        if (ws) {  // split-K partial: dense [split][batch][M][N]
+            out = ws + (int64_t)split * ws_split_stride + (int64_t)batch * M * N;
+            ld = N;
+        } else {
+            out = C + (int64_t)batch * strideC;
+            ld = ldc;
+        }
+        const bool add = accumulate && !ws;
+        const bool vec_ok = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; c++) {
+            uint32_t v[32];
+            const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32);
+            tmem_ld_32x32b_x32(taddr, v);
+            tmem_ld_wait();
+            const int64_t col0 = n0 + c * 32;
+            if (row < M && col0 < N) {
+                float* p = out + row * ld + col0;
+                if (vec_ok && col0 + 32 <= N) {
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                               __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                        if (add) {
+                            float4 old = *reinterpret_cast<const float4*>(p + 4 * j);
+                            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                        }
+                        *reinterpret_cast<float4*>(p + 4 * j) = o;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; j++)
+                        if (col0 + j < N) p[j] = add ? p[j] + __uint_as_float(v[j]) : __uint_as_float(v[j]);
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_acc, cfg::TMEM_COLS);
+}
+
+// C[b][m][n] (+)= sum over splits, ascending: the fixed-order reduction that keeps split-K deterministic
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ ws, int splits, int64_t split_stride, float* __restrict__ C,
+                     int64_t M, int64_t N, int64_t ldc, int64_t strideC, int64_t batch, int accumulate) {
+    const int64_t total = batch * M * N;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t b = i / (M * N), r = (i / N) % M, c = i % N;
+        float* p = C + b * strideC + r * ldc + c;
+        float acc = accumulate ? *p : 0.0f;
+        for (int s = 0; s < splits; s++) acc += ws[(int64_t)s * split_stride + i];
+        *p = acc;
+    }
+}
+
+int plane_map(CUtensorMap* map, const float* base, int64_t MNp, int64_t Kp, int64_t batch, int box_rows) {
+    uint64_t dims[3] = {(uint64_t)Kp, (uint64_t)MNp, (uint64_t)batch};
+    uint64_t strides[2] = {(uint64_t)Kp * 4, (uint64_t)MNp * (uint64_t)Kp * 4};
+    uint32_t box[3] = {(uint32_t)BK, (uint32_t)box_rows, 1};
+    return make_tensor_map(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box,
+                           CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+template <int BN>
+int launch_tile(const Maps& maps, float* C, int64_t batch, int64_t M, int64_t N, int64_t ldc, int64_t strideC,
+                int kblocks, int splits, bool accumulate, float* ws, cudaStream_t stream) {
+    auto kern = tf32x3_kernel<BN>;
+    static thread_local int configured_dev = -1;
+    int dev = 0;
+    EML_CUDA(cudaGetDevice(&dev));
+    if (configured_dev != dev) {
+        EML_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<BN>::SMEM_BYTES));
+        configured_dev = dev;
+    }
+    int64_t tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+    int per_split = (kblocks + splits - 1) / splits;
+    int used_splits = (kblocks + per_split - 1) / per_split;  // every split owns >= 1 k block
+    dim3 grid((unsigned)tiles, (unsigned)batch, (unsigned)used_splits);
+    kern<<<grid, GEMM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(maps, C, M, N, ldc, strideC, kblocks, per_split,
+                                                              accumulate ? 1 : 0, ws, batch * M * N);
+    count_launch();
+    EML_TRY(check_launch("tf32x3_tcgen05"));
+    if (ws) {
+        int64_t total = batch * M * N;
+        int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+        splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(ws, used_splits, batch * M * N, C, M, N, ldc, strideC, batch,
+                                                         accumulate ? 1 : 0);
+        count_launch();
+        EML_TRY(check_launch("tf32x3 split-K reduce"));
+    }
     return EML_OK;
 }
+
+}  // namespace
+
+int launch_gemm_tf32x3_f32(DeviceCtx* ctx, const float* A, const float* B, float* C, int64_t batch, int64_t M,
+                           int64_t N, int64_t K, Strides3 sA, Strides3 sB, Strides3 sC, bool accumulate,
+                           cudaStream_t stream, bool* handled) {
+    *handled = false;
+    if (batch == 0 || M == 0 || N == 0) {
+        *handled = true;
+        return EML_OK;
+    }
+    if (sC.c != 1 || batch > 65535) return EML_OK;  // C rows must be contiguous (the caller transposes otherwise)
+    const char* forced = getenv("EML_SGEMM_KERNEL");
+    if (forced && std::string(forced) == "simt") return EML_OK;
+    *handled = true;
+
+    const int sms = ctx ? ctx->sm_count : 148;
+    const int64_t Kp = round_up(K, BK);
+    const int kblocks = (int)(Kp / BK);
+    const int64_t tiles_m = (M + BM - 1) / BM;
+    // tile width: 256 when that still fills the machine, else 128
+    const int64_t tiles256 = tiles_m * ((N + 255) / 256) * batch;
+    const int BN = (N > 128 && tiles256 * 10 >= (int64_t)sms * 8) ? 256 : 128;
+    const int64_t tiles = tiles_m * ((N + BN - 1) / BN) * batch;
+    // deterministic split-K when the output has too few tiles for 148 SMs (e.g. dW = X^T dH, K = batch size)
+    int splits = 1;
+    if (tiles * 2 <= sms && kblocks >= 8) {
+        splits = (int)((sms + tiles - 1) / tiles);
+        if (splits > kblocks / 4) splits = kblocks / 4;
+        if (splits < 1) splits = 1;
+    }
+    const int64_t Mp = round_up(M, BM), Np = round_up(N, BN);
+
+    TempBuf packed, wsbuf;
+    const int64_t a_plane = batch * Mp * Kp, b_plane = batch * Np * Kp;
+    EML_TRY(packed.alloc(sizeof(float) * 2 * (size_t)(a_plane + b_plane), stream));
+    float* a_big = packed.as<float>();
+    float* a_small = a_big + a_plane;
+    float* b_big = a_small + a_plane;
+    float* b_small = b_big + b_plane;
+    float* ws = nullptr;
+    if (splits > 1) {
+        EML_TRY(wsbuf.alloc(sizeof(float) * (size_t)splits * (size_t)(batch * M * N), stream));
+        ws = wsbuf.as<float>();
+    }
+
+    {
+        dim3 grid((unsigned)(Kp / 32), (unsigned)(Mp / 32), (unsigned)batch);
+        if (grid.y > 65535) EML_BAD_ARG("tf32x3: M too large for the pack grid");
+        split_pack_kernel<<<grid, 256, 0, stream>>>(A, a_big, a_small, M, K, Mp, Kp, sA.b, sA.r, sA.c, sA.c == 1);
+        count_launch();
+        EML_TRY(check_launch("tf32x3 pack A"));
+    }
+    {
+        // B element (k, n) at B[k*sB.r + n*sB.c]: its "mn" index is n
+        dim3 grid((unsigned)(Kp / 32), (unsigned)(Np / 32), (unsigned)batch);
+        if (grid.y > 65535) EML_BAD_ARG("tf32x3: N too large for the pack grid");
+        split_pack_kernel<<<grid, 256, 0, stream>>>(B, b_big, b_small, N, K, Np, Kp, sB.b, sB.c, sB.r, sB.r == 1);
+        count_launch();
+        EML_TRY(check_launch("tf32x3 pack B"));
+    }
+
+    Maps maps;
+    EML_TRY(plane_map(&maps.a_big, a_big, Mp, Kp, batch, BM));
+    EML_TRY(plane_map(&maps.a_small, a_small, Mp, Kp, batch, BM));
+    EML_TRY(plane_map(&maps.b_big, b_big, Np, Kp, batch, BN));
+    EML_TRY(plane_map(&maps.b_small, b_small, Np, Kp, batch, BN));
+    set_last_kernel("tf32x3_tcgen05");
+    if (BN == 256) return launch_tile<256>(maps, C, batch, M, N, sC.r, sC.b, kblocks, splits, accumulate, ws, stream);
+    return launch_tile<128>(maps, C, batch, M, N, sC.r, sC.b, kblocks, splits, accumulate, ws, stream);
+}
+
 }  // namespace eml

@@ -168,6 +168,59 @@ def test_dgemm_tma_all_layouts_ragged(orc, monkeypatch, a_kin, b_kin, batch, m, 
     assert np.array_equal(got, other)
 
 
+@pytest.mark.parametrize("a_kin", [True, False])
+@pytest.mark.parametrize("b_kin", [True, False])
+@pytest.mark.parametrize("batch,m,n,k", [(1, 256, 256, 256), (1, 384, 260, 196), (3, 300, 264, 224), (1, 1000, 520, 1028)])
+def test_sgemm_tf32x3_all_layouts_ragged(orc, a_kin, b_kin, batch, m, n, k):
+    """The tcgen05 3xTF32 kernel: every operand orientation through the split/pack pass, ragged M/N/K
+    (zero padded by the pack), batched, split-K on the small grids.  f32-level accuracy: within
+    1e-5 * sum|a_k b_k| of the oracle's sequential sum."""
+    r = rng(80 + m + n + k)
+    a = uniform(r, (batch, m, k), np.float32)
+    b = uniform(r, (batch, k, n), np.float32)
+    a_buf = np.ascontiguousarray(a if a_kin else a.transpose(0, 2, 1))
+    b_buf = np.ascontiguousarray(b.transpose(0, 2, 1) if b_kin else b)
+    sa = (m * k, k, 1) if a_kin else (m * k, 1, m)
+    sb = (k * n, 1, k) if b_kin else (k * n, n, 1)
+    got = contract_strided(a_buf, b_buf, batch, m, n, k, sa, sb, np.float32)
+    assert eml.last_kernel() == "tf32x3_tcgen05"
+    for bi in range(batch):
+        for i in sorted({0, 1, m // 2, m - 1}):
+            ref = orc.matrix_mul(np.ascontiguousarray(a[bi, i:i + 1]), np.ascontiguousarray(b[bi]))
+            assert_within(got[bi, i:i + 1], a[bi, i:i + 1], b[bi], ref, np.float32, f"batch {bi} row {i}")
+        exact = a[bi].astype(np.float64) @ b[bi].astype(np.float64)
+        assert_within(got[bi], a[bi], b[bi], exact, np.float32, f"batch {bi} vs f64")
+    # small integers are exact TF32 numbers with a zero small part: any summation order gives the same bits
+    ai, bi_ = ints(r, (batch, m, k), np.float32), ints(r, (batch, k, n), np.float32)
+    gi = contract_strided(ai, bi_, batch, m, n, k, (m * k, k, 1), (k * n, n, 1), np.float32)
+    assert np.array_equal(gi, np.matmul(ai.astype(np.float64), bi_.astype(np.float64)).astype(np.float32))
+
+
+def test_sgemm_tf32x3_wide_tile_accumulate_device():
+    """128x256 tiles (enough tiles to fill the machine) and the C += A*B epilogue, device-resident."""
+    import torch
+
+    m, n, k = 2048, 2304, 328
+    g = torch.Generator(device="cuda").manual_seed(7)
+    a = torch.rand((m, k), generator=g, device="cuda") * 2 - 1
+    b = torch.rand((k, n), generator=g, device="cuda") * 2 - 1
+    c0 = torch.rand((m, n), generator=g, device="cuda")
+    c = c0.clone()
+    s3 = lambda *s: (C.c_int64 * 3)(*s)
+    vp = lambda t: C.c_void_p(t.data_ptr())
+    sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    check(lib.eml_contract_f32_dev(vp(a), vp(b), vp(c), 1, m, n, k, s3(0, k, 1), s3(0, n, 1), s3(0, n, 1), 1, sp))
+    torch.cuda.synchronize()
+    assert eml.last_kernel() == "tf32x3_tcgen05"
+    want = c0.double() + a.double() @ b.double()
+    bound = 1e-5 * (a.abs().double() @ b.abs().double()) + 1e-6 * c0.abs().double()
+    assert bool(((c.double() - want).abs() <= bound).all())
+    c2 = torch.empty_like(c)
+    check(lib.eml_contract_f32_dev(vp(a), vp(b), vp(c2), 1, m, n, k, s3(0, k, 1), s3(0, n, 1), s3(0, n, 1), 0, sp))
+    torch.cuda.synchronize()
+    assert bool(((c2.double() - a.double() @ b.double()).abs() <= 1e-5 * (a.abs().double() @ b.abs().double())).all())
+
+
 @pytest.mark.parametrize("dtype", DTYPES)
 def test_gemm_leading_dimensions(orc, dtype):
     r = rng(3)
