@@ -451,43 +451,39 @@ def nn_steps(torch, eml, np, batch=8192, steps=5, warmup=3):
 
 
 def sharded(args, torch, dist, eml, lib, check, dev, stream, sp, rank, world, timed, barrier, max_over_ranks):
+    """BASELINE config 5: f64 n x n, A and C row-sharded over `world` GPUs, B broadcast in K panels from rank 0
+    under the compute, C slabs all-gathered (easy-ml_b200/sharded.py holds the plan and the step)."""
+    from easy_ml_b200.sharded import ShardedGemm, ShardPlan
+
     n = args.size or 32768
-    rows = n // world
-    assert rows * world == n
+    plan = ShardPlan(m=n, n=n, k=n, world=world, rank=rank, panels=8)
+    h = plan.slab_rows
+    first, last = plan.my_rows
     f64 = torch.float64
     gen = torch.Generator(device=dev)
     gen.manual_seed(0x5EED0005 + rank)
-    A = torch.rand((rows, n), generator=gen, device=dev, dtype=f64) * 2 - 1   # this rank's row slab of A
+    A = torch.rand((h, n), generator=gen, device=dev, dtype=f64) * 2 - 1   # this rank's row slab of A
     B = torch.empty((n, n), device=dev, dtype=f64)
     B_src = None
     if rank == 0:
         gen.manual_seed(0x5EED0006)
         B_src = torch.rand((n, n), generator=gen, device=dev, dtype=f64) * 2 - 1
-    Cfull = torch.empty((n, n), device=dev, dtype=f64)
-    Cslab = Cfull[rank * rows:(rank + 1) * rows]
-    panels = 8
-    pk = n // panels
+    Cfull = torch.empty((world * h, n), device=dev, dtype=f64)
     s3 = lambda a, b, c: (C.c_int64 * 3)(a, b, c)
 
     def vp(t):
         return C.c_void_p(t.data_ptr())
 
+    def slab_gemm(a, b, c, accumulate):
+        # c (+)= a * b on views of row-major buffers: strides come from the views, no copies
+        check(lib.eml_contract_f64_dev(vp(a), vp(b), vp(c), 1, a.shape[0], b.shape[1], a.shape[1],
+                                       s3(0, a.stride(0), 1), s3(0, b.stride(0), 1), s3(0, c.stride(0), 1),
+                                       1 if accumulate else 0, sp))
+
+    op = ShardedGemm(plan, dist, slab_gemm, b_owner=0)
+
     def step():
-        # broadcast B from rank 0 in K panels; panel p+1 travels while panel p is multiplied.
-        works = []
-        for p in range(panels):
-            blk = B[p * pk:(p + 1) * pk]
-            if rank == 0:
-                blk.copy_(B_src[p * pk:(p + 1) * pk], non_blocking=True)
-            works.append(dist.broadcast(blk, src=0, async_op=True))
-        for p in range(panels):
-            works[p].wait()
-            # Cslab (+)= A[:, panel] * B[panel, :]; accumulate continues the same k-ordered chain, so the bits
-            # equal a single-launch product
-            Ap = A[:, p * pk:(p + 1) * pk]
-            check(lib.eml_contract_f64_dev(vp(Ap), vp(B[p * pk:(p + 1) * pk]), vp(Cslab), 1, rows, n, pk,
-                                           s3(0, n, 1), s3(0, n, 1), s3(0, n, 1), 1 if p else 0, sp))
-        dist.all_gather_into_tensor(Cfull, Cslab)  # in place: the slab already sits at its offset in Cfull
+        op.step(A, B, Cfull, B_src)
 
     flop = 2.0 * n * n * n
     ms, launches, clocks = timed(step, args.steps, args.warmup)
@@ -495,13 +491,18 @@ def sharded(args, torch, dist, eml, lib, check, dev, stream, sp, rank, world, ti
     # kernel-only time of this rank's slab (no communication) for the roofline line
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    Cslab = Cfull[rank * h:rank * h + (last - first)]
     e0.record(stream)
-    check(lib.eml_contract_f64_dev(vp(A), vp(B), vp(Cslab), 1, rows, n, n, s3(0, n, 1), s3(0, n, 1), s3(0, n, 1), 0, sp))
+    slab_gemm(A[:last - first], B, Cslab, False)
     e1.record(stream)
     torch.cuda.synchronize()
     kms = max_over_ranks(e0.elapsed_time(e1))
-    achieved = flop / world / (kms * 1e-3) / 1e12
-    comm_bytes = (world - 1) / world * n * n * 8
+    achieved = 2.0 * (last - first) * n * n / (kms * 1e-3) / 1e12
+    # the panelled, overlapped step must equal the single-launch product bit for bit (same k-ordered chain)
+    single = Cslab.clone()
+    step()
+    torch.cuda.synchronize()
+    same_bits = bool(torch.equal(single, Cfull[rank * h:rank * h + (last - first)]))
     return {
         "metric": "f64 matmul throughput", "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -512,7 +513,9 @@ def sharded(args, torch, dist, eml, lib, check, dev, stream, sp, rank, world, ti
         "roofline": {"bound": "tensor", "kernel": eml.last_kernel(), "achieved": achieved, "peak": NOMINAL_FP64_TFLOPS,
                      "unit": "TFLOP/s", "frac": achieved / NOMINAL_FP64_TFLOPS, "traffic": None,
                      "peak_source": "nominal B200 FP64 per GPU", "kernel_ms": kms,
-                     "nvlink_bytes_per_gpu_per_step": {"broadcast_in": n * n * 8 if rank else 0, "allgather_in": comm_bytes}},
+                     "algorithmic_flop_per_launch": 2.0 * (last - first) * n * n,
+                     "nvlink_bytes_in_per_gpu_per_step": plan.comm_bytes(8)},
+        "parity": {"panelled_step_equals_single_launch_bits": same_bits},
         "cpu_baseline": None,
     }
 

@@ -58,6 +58,8 @@ SIGNATURES = {
     "eml_upload": (cint, [vp, vp, C.c_size_t]),
     "eml_download": (cint, [vp, vp, C.c_size_t]),
     "eml_sync": (cint, []),
+    "eml_host_alloc": (cint, [C.POINTER(vp), C.c_size_t]),
+    "eml_host_free": (cint, [vp]),
     "eml_tape_create": (cint, [cint, C.POINTER(vp)]),
     "eml_tape_destroy": (cint, [vp]),
     "eml_tape_len": (cint, [vp, pi64]),

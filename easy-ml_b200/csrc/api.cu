@@ -42,9 +42,57 @@ int tensor_core_path<float>(DeviceCtx* ctx, const float* A, const float* B, floa
 
 }  // namespace
 
+namespace {
+// set around launches whose bits must not depend on how the caller partitioned the rows (the pipelined
+// host GEMM equals a single device launch bit for bit)
+thread_local bool t_no_split_k = false;
+struct NoSplitK {
+    bool prev;
+    NoSplitK() : prev(t_no_split_k) { t_no_split_k = true; }
+    ~NoSplitK() { t_no_split_k = prev; }
+};
+
+template <class T>
+struct SplitK;
+// f64: the DMMA kernels have no split of their own.  f32: gemm_tf32x3.cu splits inside its own launch, so
+// only the SIMT-bound (skinny) shapes are split here.
+template <>
+struct SplitK<double> {
+    static bool wanted(int64_t, int64_t, int64_t) { return true; }
+};
+template <>
+struct SplitK<float> {
+    static bool wanted(int64_t M, int64_t N, int64_t K) { return !Threshold<float>::tensor_core(M, N, K); }
+};
+}  // namespace
+
 template <class T>
 int contract_dev(DeviceCtx* ctx, const T* A, const T* B, T* C, int64_t batch, int64_t M, int64_t N, int64_t K,
                  Strides3 sA, Strides3 sB, Strides3 sC, bool accumulate, bool exact, cudaStream_t stream) {
+    // Deterministic split-K for outputs with too few tiles for 148 SMs and a long K (the loss reduction
+    // L[1 x batch] * d[batch x 10], dW2 = H^T[512 x batch] * dY[batch x 10], ...): K is cut into S equal
+    // chunks which run as S "batches" of one launch into a workspace [S][M][N]; a fixed-order reduction
+    // adds them.  S depends on the shape only, so results stay bit-identical run to run.
+    if (!exact && !t_no_split_k && batch == 1 && M > 0 && N > 0 && K >= 512 && A && B && C &&
+        SplitK<T>::wanted(M, N, K)) {
+        const bool tc = Threshold<T>::tensor_core(M, N, K);
+        const int64_t tile = tc ? 128 : 64, min_chunk = tc ? 256 : 64;
+        const int64_t tiles = ((M + tile - 1) / tile) * ((N + tile - 1) / tile);
+        const int64_t sms = ctx ? ctx->sm_count : 148;
+        if (tiles * 2 <= sms) {
+            int64_t S = (sms + tiles - 1) / tiles;
+            if (S > K / min_chunk) S = K / min_chunk;
+            while (S > 1 && (K % S != 0 || (K / S) % 4 != 0)) S--;  // equal, 32-byte aligned chunks
+            if (S > 1) {
+                const int64_t Kc = K / S;
+                TempBuf ws;
+                EML_TRY(ws.alloc(sizeof(T) * (size_t)(S * M * N), stream));
+                EML_TRY(contract_dev<T>(ctx, A, B, ws.as<T>(), S, M, N, Kc, Strides3{Kc * sA.c, sA.r, sA.c},
+                                        Strides3{Kc * sB.r, sB.r, sB.c}, Strides3{M * N, N, 1}, false, false, stream));
+                return launch_splitk_reduce<T>(ws.as<T>(), (int)S, C, 1, M, N, sC, accumulate, stream);
+            }
+        }
+    }
     if (batch < 0 || M < 0 || N < 0) EML_BAD_ARG("contract: negative extent (batch=%lld M=%lld N=%lld)",
                                                  (long long)batch, (long long)M, (long long)N);
     if (K < 1) EML_BAD_ARG("contract: K must be >= 1 (got %lld); Easy ML containers have no zero-length dimension",
@@ -85,6 +133,76 @@ inline int64_t span(int64_t nb, int64_t nr, int64_t nc, Strides3 s) {
 
 inline bool nonneg(Strides3 s) { return s.b >= 0 && s.r >= 0 && s.c >= 0; }
 
+// Large row-major GEMM from host buffers: PCIe traffic is hidden under the compute instead of bracketing it.
+//   phase 1 (while B is still arriving): B travels in K panels; the first M1 rows of C accumulate panel by
+//            panel, C[0:M1] (+)= A[0:M1, kq] * B[kq, :]   (the kernels' `accumulate` continues the k-ordered
+//            chain, so this equals one launch over the whole K);
+//   phase 2 (B resident): the remaining rows in row panels -- A panel p+1 uploads and C panel p-1 downloads
+//            while panel p is multiplied.
+// Three streams (H2D, compute, D2H) ordered by events.  Host buffers should be pinned (eml_host_alloc, or
+// cudaHostRegister by the caller) for the copies to be truly asynchronous; pageable memory still works.
+template <class T>
+int gemm_host_pipelined(DeviceCtx* ctx, const T* A, const T* B, T* C, int64_t M, int64_t N, int64_t K, int64_t lda,
+                        int64_t ldb, int64_t ldc) {
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    void *vA, *vB, *vC;
+    EML_TRY(stage_buffer(ctx, 0, sizeof(T) * (size_t)(M * K), &vA));
+    EML_TRY(stage_buffer(ctx, 1, sizeof(T) * (size_t)(K * N), &vB));
+    EML_TRY(stage_buffer(ctx, 2, sizeof(T) * (size_t)(M * N), &vC));
+    T *dA = (T*)vA, *dB = (T*)vB, *dC = (T*)vC;  // dense on the device: ld = K, N, N
+    cudaStream_t in = ctx->copy_in, cs = ctx->stream, out = ctx->copy_out;
+    int ev = 0;
+    auto next_event = [&]() { return ctx->events[ev++ % 64]; };
+    const size_t es = sizeof(T);
+    auto round_to = [](int64_t x, int64_t m) { return (x + m - 1) / m * m; };
+
+    constexpr int Q = 8;                                      // K panels of phase 1
+    const int64_t kq = round_to((K + Q - 1) / Q, 32);
+    int64_t M1 = round_to(M * 2 / 5, 128);                    // ~ compute(M1 rows) == upload(B + A[0:M1])
+    if (M1 > M) M1 = M;
+    const int64_t panels2 = (M - M1 + 1023) / 1024;           // row panels of phase 2, evenly sized
+    const int64_t R = panels2 ? round_to((M - M1 + panels2 - 1) / panels2, 128) : 1024;
+    NoSplitK no_split;  // same bits as one device launch over the whole problem
+
+    // the previous call's work on these streams is complete (every call ends with a synchronize)
+    for (int64_t k0 = 0, q = 0; k0 < K; k0 += kq, q++) {
+        const int64_t k1 = k0 + kq < K ? k0 + kq : K;
+        EML_CUDA(cudaMemcpy2DAsync(dB + k0 * N, N * es, B + k0 * ldb, ldb * es, N * es, k1 - k0,
+                                   cudaMemcpyHostToDevice, in));
+        EML_CUDA(cudaMemcpy2DAsync(dA + k0, K * es, A + k0, lda * es, (k1 - k0) * es, M1, cudaMemcpyHostToDevice, in));
+        cudaEvent_t e = next_event();
+        EML_CUDA(cudaEventRecord(e, in));
+        EML_CUDA(cudaStreamWaitEvent(cs, e, 0));
+        EML_TRY(contract_dev<T>(ctx, dA + k0, dB + k0 * N, dC, 1, M1, N, k1 - k0, Strides3{0, K, 1}, Strides3{0, N, 1},
+                                Strides3{0, N, 1}, q > 0, false, cs));
+    }
+    {
+        cudaEvent_t e = next_event();
+        EML_CUDA(cudaEventRecord(e, cs));
+        EML_CUDA(cudaStreamWaitEvent(out, e, 0));
+        EML_CUDA(cudaMemcpy2DAsync(C, ldc * es, dC, N * es, N * es, M1, cudaMemcpyDeviceToHost, out));
+    }
+    for (int64_t r0 = M1; r0 < M; r0 += R) {
+        const int64_t r1 = r0 + R < M ? r0 + R : M;
+        EML_CUDA(cudaMemcpy2DAsync(dA + r0 * K, K * es, A + r0 * lda, lda * es, K * es, r1 - r0, cudaMemcpyHostToDevice,
+                                   in));
+        cudaEvent_t e = next_event();
+        EML_CUDA(cudaEventRecord(e, in));
+        EML_CUDA(cudaStreamWaitEvent(cs, e, 0));
+        EML_TRY(contract_dev<T>(ctx, dA + r0 * K, dB, dC + r0 * N, 1, r1 - r0, N, K, Strides3{0, K, 1},
+                                Strides3{0, N, 1}, Strides3{0, N, 1}, false, false, cs));
+        cudaEvent_t d = next_event();
+        EML_CUDA(cudaEventRecord(d, cs));
+        EML_CUDA(cudaStreamWaitEvent(out, d, 0));
+        EML_CUDA(cudaMemcpy2DAsync(C + r0 * ldc, ldc * es, dC + r0 * N, N * es, N * es, r1 - r0, cudaMemcpyDeviceToHost,
+                                   out));
+    }
+    EML_CUDA(cudaStreamSynchronize(out));
+    EML_CUDA(cudaStreamSynchronize(cs));
+    EML_CUDA(cudaStreamSynchronize(in));
+    return EML_OK;
+}
+
 // Host entry: stage operands, run, copy the result back.  Blocks until C is in the caller's buffer.
 template <class T>
 int contract_host(const T* A, const T* B, T* C, int64_t batch, int64_t M, int64_t N, int64_t K, Strides3 sA,
@@ -119,6 +237,13 @@ int gemm_host(const T* A, const T* B, T* C, int64_t M, int64_t N, int64_t K, int
     if (M < 0 || N < 0 || K < 1) EML_BAD_ARG("gemm: bad extents M=%lld N=%lld K=%lld", (long long)M, (long long)N,
                                              (long long)K);
     if (lda < K || ldb < N || ldc < N) EML_BAD_ARG("gemm: leading dimension smaller than the row length");
+    // events available: 8 (phase 1) + 1 + 2 per row panel of phase 2  ->  M <= ~ 27 * 1024 rows after M1
+    if (!exact && A && B && C && M >= 2048 && M <= 40960 && N >= 512 && K >= 512 &&
+        (M * K + K * N + M * N) >= (int64_t(1) << 24)) {
+        DeviceCtx* ctx = nullptr;
+        EML_TRY(get_ctx(&ctx));
+        return gemm_host_pipelined<T>(ctx, A, B, C, M, N, K, lda, ldb, ldc);
+    }
     return contract_host<T>(A, B, C, 1, M, N, K, Strides3{0, lda, 1}, Strides3{0, ldb, 1}, Strides3{0, ldc, 1},
                             exact);
 }
@@ -303,6 +428,17 @@ int eml_download(void* dst, const void* src, size_t bytes) {
     EML_TRY(get_ctx(&ctx));
     EML_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     EML_CUDA(cudaStreamSynchronize(ctx->stream));
+    return EML_OK;
+}
+int eml_host_alloc(void** hptr, size_t bytes) {
+    DeviceCtx* ctx = nullptr;
+    EML_TRY(get_ctx(&ctx));
+    if (!hptr) EML_BAD_ARG("host_alloc: null out pointer");
+    EML_CUDA(cudaHostAlloc(hptr, bytes ? bytes : 16, cudaHostAllocDefault));
+    return EML_OK;
+}
+int eml_host_free(void* hptr) {
+    if (hptr) EML_CUDA(cudaFreeHost(hptr));
     return EML_OK;
 }
 int eml_sync(void) {

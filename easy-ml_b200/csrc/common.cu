@@ -76,6 +76,9 @@ int get_ctx(DeviceCtx** out) {
         ctx->sm_count = prop.multiProcessorCount;
         ctx->smem_optin = prop.sharedMemPerBlockOptin;
         EML_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        EML_CUDA(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
+        EML_CUDA(cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+        for (auto& ev : ctx->events) EML_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         cudaMemPool_t pool;
         EML_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
         uint64_t keep = UINT64_MAX;
@@ -116,6 +119,10 @@ void shutdown_all() {
         for (int i = 0; i < 3; i++)
             if (c->stage[i]) cudaFree(c->stage[i]);
         if (c->stream) cudaStreamDestroy(c->stream);
+        if (c->copy_in) cudaStreamDestroy(c->copy_in);
+        if (c->copy_out) cudaStreamDestroy(c->copy_out);
+        for (auto ev : c->events)
+            if (ev) cudaEventDestroy(ev);
     }
     g_ctx.clear();
 }

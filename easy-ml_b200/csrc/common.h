@@ -47,6 +47,8 @@ struct DeviceCtx {
     int sm_count = 148;
     size_t smem_optin = 0;
     cudaStream_t stream = nullptr;  // library stream for host entry points / NULL-stream _dev calls
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;  // H2D / D2H streams of the pipelined host GEMM
+    cudaEvent_t events[64] = {};    // reusable (timing disabled) events of the pipelined host GEMM
     std::mutex mu;  // guards the staging buffers of the host entry points
     // staging for host entry points (device side), grow-only, one slot per operand
     void* stage[3] = {nullptr, nullptr, nullptr};
@@ -100,6 +102,12 @@ int launch_gemm_dmma_f64(DeviceCtx* ctx, const double* A, const double* B, doubl
 int launch_gemm_tf32x3_f32(DeviceCtx* ctx, const float* A, const float* B, float* C, int64_t batch, int64_t M,
                            int64_t N, int64_t K, Strides3 sA, Strides3 sB, Strides3 sC, bool accumulate,
                            cudaStream_t stream, bool* handled);
+
+// C[b][m][n] (+)= sum over splits (ascending) of ws[s][b][m][n]: the fixed-order reduction behind every
+// split-K path (deterministic: no atomics).  ws is dense; C is strided.
+template <class T>
+int launch_splitk_reduce(const T* ws, int splits, T* C, int64_t batch, int64_t M, int64_t N, Strides3 sC,
+                         bool accumulate, cudaStream_t stream);
 
 template <class T>
 int launch_einsum2(const T* A, const T* B, T* out, int n_out, const int64_t* out_len, const int64_t* a_out_stride,

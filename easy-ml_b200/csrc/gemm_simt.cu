@@ -149,6 +149,38 @@ int launch_gemm_simt(const T* A, const T* B, T* C, int64_t batch, int64_t M, int
     return check_launch("gemm_simt");
 }
 
+namespace {
+template <class T>
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const T* __restrict__ ws, int splits, int64_t split_stride, T* __restrict__ C, int64_t M,
+                     int64_t N, Strides3 sC, int64_t batch, int accumulate) {
+    const int64_t total = batch * M * N;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t b = i / (M * N), r = (i / N) % M, c = i % N;
+        T* p = C + b * sC.b + r * sC.r + c * sC.c;
+        T acc = accumulate ? *p : T(0);
+        for (int s = 0; s < splits; s++) acc += ws[(int64_t)s * split_stride + i];
+        *p = acc;
+    }
+}
+}  // namespace
+
+template <class T>
+int launch_splitk_reduce(const T* ws, int splits, T* C, int64_t batch, int64_t M, int64_t N, Strides3 sC,
+                         bool accumulate, cudaStream_t stream) {
+    int64_t total = batch * M * N;
+    if (total == 0) return EML_OK;
+    int64_t want = (total + 255) / 256;
+    int blocks = (int)(want < 148 * 8 ? want : 148 * 8);
+    splitk_reduce_kernel<T><<<blocks, 256, 0, stream>>>(ws, splits, total, C, M, N, sC, batch, accumulate ? 1 : 0);
+    count_launch();
+    return check_launch("split-K reduce");
+}
+template int launch_splitk_reduce<float>(const float*, int, float*, int64_t, int64_t, int64_t, Strides3, bool,
+                                         cudaStream_t);
+template int launch_splitk_reduce<double>(const double*, int, double*, int64_t, int64_t, int64_t, Strides3, bool,
+                                          cudaStream_t);
+
 template int launch_gemm_simt<float>(const float*, const float*, float*, int64_t, int64_t, int64_t, int64_t,
                                      Strides3, Strides3, Strides3, bool, bool, cudaStream_t);
 template int launch_gemm_simt<double>(const double*, const double*, double*, int64_t, int64_t, int64_t, int64_t,

@@ -19,7 +19,7 @@
 //        warps 2..5  epilogue: tcgen05.ld 32 lanes x 32 columns -> registers -> 128-byte row stores
 //                    (optionally C += ...), bounds-checked against the unpadded M, N
 //      Optional deterministic split-K (grid.z): each split writes its partial tile to a workspace and
-//      splitk_reduce_kernel adds the partials in ascending split order (fixed order, no atomics).
+//      launch_splitk_reduce adds the partials in ascending split order (fixed order, no atomics).
 //
 // Determinism: fixed tile -> CTA map, fixed k order inside a CTA, fixed split order in the reduction.
 // Algorithmic work per launch: 2*M*N*K flop (the 3x tensor work is an implementation cost, not counted);
@@ -238,20 +238,6 @@ tf32x3_kernel(const __grid_constant__ Maps maps, float* __restrict__ C, int64_t 
     if (warp == 1) tmem_dealloc(tmem_acc, cfg::TMEM_COLS);
 }
 
-// C[b][m][n] (+)= sum over splits, ascending: the fixed-order reduction that keeps split-K deterministic
-__global__ void __launch_bounds__(256)
-splitk_reduce_kernel(const float* __restrict__ ws, int splits, int64_t split_stride, float* __restrict__ C,
-                     int64_t M, int64_t N, int64_t ldc, int64_t strideC, int64_t batch, int accumulate) {
-    const int64_t total = batch * M * N;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        int64_t b = i / (M * N), r = (i / N) % M, c = i % N;
-        float* p = C + b * strideC + r * ldc + c;
-        float acc = accumulate ? *p : 0.0f;
-        for (int s = 0; s < splits; s++) acc += ws[(int64_t)s * split_stride + i];
-        *p = acc;
-    }
-}
-
 int plane_map(CUtensorMap* map, const float* base, int64_t MNp, int64_t Kp, int64_t batch, int box_rows) {
     uint64_t dims[3] = {(uint64_t)Kp, (uint64_t)MNp, (uint64_t)batch};
     uint64_t strides[2] = {(uint64_t)Kp * 4, (uint64_t)MNp * (uint64_t)Kp * 4};
@@ -281,14 +267,7 @@ int launch_tile(const Maps& maps, float* C, int64_t batch, int64_t M, int64_t N,
                                                               accumulate ? 1 : 0, ws, batch * M * N);
     count_launch();
     EML_TRY(check_launch("tf32x3_tcgen05"));
-    if (ws) {
-        int64_t total = batch * M * N;
-        int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
-        splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(ws, used_splits, batch * M * N, C, M, N, ldc, strideC, batch,
-                                                         accumulate ? 1 : 0);
-        count_launch();
-        EML_TRY(check_launch("tf32x3 split-K reduce"));
-    }
+    if (ws) EML_TRY(launch_splitk_reduce<float>(ws, used_splits, C, batch, M, N, Strides3{strideC, ldc, 1}, accumulate, stream));
     return EML_OK;
 }
 

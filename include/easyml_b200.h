@@ -142,6 +142,11 @@ int eml_free(void* dptr);
 int eml_upload(void* dst_dev, const void* src_host, size_t bytes);   /* blocking */
 int eml_download(void* dst_host, const void* src_dev, size_t bytes); /* blocking */
 int eml_sync(void);                                                  /* current device */
+/* Page-locked host memory.  The host entry points accept any host pointer; with pinned buffers the large
+ * GEMMs overlap their PCIe copies with the compute (three streams), which pageable memory cannot do.  A Rust
+ * shim would back `Matrix<f32|f64>` storage created under the `cuda` feature with these. */
+int eml_host_alloc(void** hptr, size_t bytes);
+int eml_host_free(void* hptr);
 
 /* accumulate != 0:  C += A*B (the fused "accumulate into the derivative" epilogue of the backward). */
 int eml_contract_f32_dev(const float* A, const float* B, float* C, int64_t batch, int64_t M, int64_t N,

@@ -222,6 +222,49 @@ def test_sgemm_tf32x3_wide_tile_accumulate_device():
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("m,n,k", [(1, 10, 8192), (512, 10, 8192), (8, 8, 4096), (200, 136, 2048), (10, 512, 1000)])
+def test_split_k_skinny_outputs(orc, dtype, m, n, k):
+    """Few output tiles + long K (the NN's loss reduction and dW2 = H^T dY): deterministic split-K through
+    the batch dimension and a fixed-order reduction.  Within tolerance of the oracle, bit-identical run to run."""
+    r = rng(300 + m + n + k)
+    a, b = uniform(r, (m, k), dtype), uniform(r, (k, n), dtype)
+    got = gemm(a, b)
+    assert_within(got, a, b, orc.matrix_mul(a, b, threads=4), dtype, f"split-K {m}x{n}x{k}")
+    assert np.array_equal(got, gemm(a, b))
+    ai, bi = ints(r, (m, k), dtype), ints(r, (k, n), dtype)
+    assert np.array_equal(gemm(ai, bi), orc.matrix_mul(ai, bi, threads=4))
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_host_gemm_pipelined_copies(orc, dtype):
+    """Large host-pointer GEMM: the three-stream pipelined path (B in K panels under an accumulating first
+    row block, then row panels), with leading dimensions larger than the rows.  f64 must equal the
+    device-resident single launch bit for bit (same k-ordered chain per element)."""
+    import torch
+
+    r = rng(500)
+    m, n, k = 4224, 2048, 2080
+    big_a, big_b = uniform(r, (m, k + 16), dtype), uniform(r, (k, n + 8), dtype)
+    a, b = big_a[:, :k], big_b[:, :n]
+    sfx = "f32" if dtype == np.float32 else "f64"
+    c = np.full((m, n + 24), 3.0, dtype)
+    check(getattr(lib, f"eml_gemm_{sfx}")(ptr(big_a), ptr(big_b), ptr(c), m, n, k, k + 16, n + 8, n + 24))
+    assert np.all(c[:, n:] == 3.0)  # elements outside the C view are untouched
+    for i in (0, 1, 1663, 1664, 1800, 2751, 2752, m - 1):
+        ref = orc.matrix_mul(np.ascontiguousarray(a[i:i + 1]), np.ascontiguousarray(b))
+        assert_within(c[i:i + 1, :n], a[i:i + 1], b, ref, dtype, f"row {i}")
+    exact = a.astype(np.float64) @ b.astype(np.float64)
+    assert_within(c[:, :n], a, b, exact, dtype, "whole product vs f64")
+    if dtype == np.float64:
+        ta, tb = torch.from_numpy(np.ascontiguousarray(a)).cuda(), torch.from_numpy(np.ascontiguousarray(b)).cuda()
+        tc = torch.empty((m, n), dtype=torch.float64, device="cuda")
+        vp = lambda t: C.c_void_p(t.data_ptr())
+        check(lib.eml_gemm_f64_dev(vp(ta), vp(tb), vp(tc), m, n, k, k, n, n, None))
+        torch.cuda.synchronize()
+        assert np.array_equal(tc.cpu().numpy(), c[:, :n])
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 def test_gemm_leading_dimensions(orc, dtype):
     r = rng(3)
     big_a, big_b = uniform(r, (150, 200), dtype), uniform(r, (200, 180), dtype)

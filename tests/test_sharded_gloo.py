@@ -1,0 +1,87 @@
+"""Host logic of the row-sharded GEMM (easy-ml_b200/sharded.py) on CPU: world_size 2 and 3 over gloo.
+
+The slab product is a stand-in (torch CPU matmul with an accumulate flag); what is tested here is the
+partition, the panelled broadcast of B, the in-place all-gather and the ragged cases (M not divisible by
+the world size, more ranks than rows) -- the parts that are identical on NCCL.
+"""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from easy_ml_b200.sharded import ShardedGemm, ShardPlan, k_panels, row_range, rows_per_rank
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, m, n, k, panels, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(1234)
+        a_full = torch.randint(-8, 9, (m, k), generator=g).double()
+        b_full = torch.randint(-8, 9, (k, n), generator=g).double()
+        plan = ShardPlan(m=m, n=n, k=k, world=world, rank=rank, panels=panels)
+        h = plan.slab_rows
+        first, last = plan.my_rows
+        a_slab = torch.zeros((h, k), dtype=torch.float64)
+        a_slab[:last - first] = a_full[first:last]
+        b = torch.zeros((k, n), dtype=torch.float64)  # only the owner has the data before the step
+        b_src = b_full.clone() if rank == 0 else None
+        c_full = torch.full((world * h, n), -1.0, dtype=torch.float64)
+        calls = []
+
+        def slab_gemm(a, bb, c, accumulate):
+            calls.append((tuple(a.shape), tuple(bb.shape), accumulate))
+            if accumulate:
+                c += a @ bb
+            else:
+                c.copy_(a @ bb)
+
+        c = ShardedGemm(plan, dist, slab_gemm, b_owner=0).step(a_slab, b, c_full, b_src)
+        ok = torch.equal(c, a_full @ b_full) and torch.equal(b, b_full)
+        # first panel overwrites, later ones accumulate; one call per panel on ranks that own rows
+        expect_calls = len(k_panels(k, panels)) if last > first else 0
+        ok = ok and len(calls) == expect_calls and all(acc == (i > 0) for i, (_, _, acc) in enumerate(calls))
+        out[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,m,n,k,panels", [(2, 64, 48, 40, 4), (2, 33, 20, 17, 3), (3, 10, 7, 9, 8), (3, 2, 5, 6, 2)])
+def test_sharded_gemm_over_gloo(world, m, n, k, panels):
+    port = _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_worker, args=(world, port, m, n, k, panels, out), nprocs=world, join=True)
+        assert all(out.get(r) for r in range(world)), dict(out)
+
+
+def test_partition_covers_rows_once():
+    for m in (1, 2, 7, 64, 1000, 32768):
+        for world in (1, 2, 3, 4, 8):
+            h = rows_per_rank(m, world)
+            ranges = [row_range(m, world, r) for r in range(world)]
+            assert ranges[0][0] == 0 and max(e for _, e in ranges) == m
+            assert all(0 <= e - s <= h for s, e in ranges)
+            covered = sum(e - s for s, e in ranges)
+            assert covered == m
+            for (s0, e0), (s1, e1) in zip(ranges, ranges[1:]):
+                assert e0 == s1 or (s1 == m and e1 == m)
+
+
+def test_k_panels_cover_k_once():
+    for k in (1, 5, 17, 4096):
+        for p in (1, 2, 8, 100):
+            ps = k_panels(k, p)
+            assert ps[0][0] == 0 and ps[-1][1] == k
+            assert all(a[1] == b[0] for a, b in zip(ps, ps[1:]))
+            assert all(b > a for a, b in ps)
