@@ -40,6 +40,13 @@ def parse():
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--size", type=int, default=0, help="override the matrix size (development only)")
     p.add_argument("--no-extra", action="store_true", help="skip the secondary workloads (f32, contraction, NN)")
+    p.add_argument("--nccl-channels", type=int, default=8,
+                   help="N>1: cap NCCL's channels (= SMs its kernels take from the GEMM); 0 leaves NCCL's default")
+    p.add_argument("--bcast", default="ce", choices=["ce", "nccl"],
+                   help="N>1: B panels pulled from rank 0 by the copy engines over NVLink (ce) or ncclBroadcast")
+    p.add_argument("--diag", action="store_true", help="N>1: also time broadcast / all-gather / compute alone")
+    p.add_argument("--gather", default="fused", choices=["fused", "nccl"],
+                   help="N>1: C slabs delivered by the GEMM epilogue's peer stores (fused) or by ncclAllGather")
     return p.parse_args()
 
 
@@ -166,19 +173,36 @@ def run_reference(args):
         "e2e": {"value": tflops, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference is Rust (no toolchain here): oracle/ C++ restatement of Matrix::mul, -O2 -ffp-contract=off",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
-def workload_config(n, gpus):
+def workload_config(n, gpus, gather="fused into the GEMM epilogue: peer stores over NVLink"):
     if gpus == 1:
         return {"workload": f"f64 Matrix x Matrix {n}x{n} (BASELINE config 2)", "M": n, "N": n, "K": n,
                 "l2": "operands (3 x %.0f MB) exceed the 126 MB L2" % (n * n * 8 / 1e6), "parallelism": "1 GPU"}
-    return {"workload": f"f64 {n}x{n} row-sharded over {gpus} GPUs, NCCL broadcast of B + all-gather of C (BASELINE config 5)",
-            "M": n, "N": n, "K": n, "l2": "operands exceed the 126 MB L2", "parallelism": f"row-shard x{gpus}"}
+    return {"workload": f"f64 {n}x{n} row-sharded over {gpus} GPUs, NCCL broadcast of B in K panels + all-gather of C "
+                        f"({gather}) (BASELINE config 5)",
+            "M": n, "N": n, "K": n, "l2": "operands exceed the 126 MB L2", "parallelism": f"row-shard x{gpus}",
+            "gather": gather}
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else a library prints (NCCL's version banner...)
+    was diverted to stderr by main()."""
+    out = os.fdopen(os.dup(_REAL_STDOUT), "w") if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    global _REAL_STDOUT
     args = parse()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
         return
@@ -198,6 +222,8 @@ def main():
         import torch.distributed as dist_mod
 
         dist = dist_mod
+        if args.nccl_channels > 0:  # the broadcast only has to outrun the compute that consumes it
+            os.environ.setdefault("NCCL_MAX_NCHANNELS", str(args.nccl_channels))
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     peak, peak_kind = peaks()
@@ -335,7 +361,7 @@ def main():
         out = sharded(args, torch, dist, eml, lib, check, dev, stream, sp, rank, world, timed, barrier, max_over_ranks)
 
     if rank == 0:
-        print(json.dumps(out), flush=True)
+        emit(out)
     if dist:
         dist.barrier()
         dist.destroy_process_group()
@@ -456,31 +482,93 @@ def sharded(args, torch, dist, eml, lib, check, dev, stream, sp, rank, world, ti
     from easy_ml_b200.sharded import ShardedGemm, ShardPlan
 
     n = args.size or 32768
-    plan = ShardPlan(m=n, n=n, k=n, world=world, rank=rank, panels=8)
+    plan = ShardPlan(m=n, n=n, k=n, world=world, rank=rank, panels=6)
     h = plan.slab_rows
     first, last = plan.my_rows
     f64 = torch.float64
     gen = torch.Generator(device=dev)
     gen.manual_seed(0x5EED0005 + rank)
     A = torch.rand((h, n), generator=gen, device=dev, dtype=f64) * 2 - 1   # this rank's row slab of A
-    B = torch.empty((n, n), device=dev, dtype=f64)
-    B_src = None
-    if rank == 0:
-        gen.manual_seed(0x5EED0006)
-        B_src = torch.rand((n, n), generator=gen, device=dev, dtype=f64) * 2 - 1
-    Cfull = torch.empty((world * h, n), device=dev, dtype=f64)
     s3 = lambda a, b, c: (C.c_int64 * 3)(a, b, c)
 
     def vp(t):
         return C.c_void_p(t.data_ptr())
 
-    def slab_gemm(a, b, c, accumulate):
-        # c (+)= a * b on views of row-major buffers: strides come from the views, no copies
-        check(lib.eml_contract_f64_dev(vp(a), vp(b), vp(c), 1, a.shape[0], b.shape[1], a.shape[1],
-                                       s3(0, a.stride(0), 1), s3(0, b.stride(0), 1), s3(0, c.stride(0), 1),
-                                       1 if accumulate else 0, sp))
+    class RawCuda:  # zero-copy torch view of a buffer from eml_alloc (cudaMalloc: exportable over CUDA IPC)
+        def __init__(self, ptr, shape):
+            self.__cuda_array_interface__ = {"shape": shape, "typestr": "<f8", "data": (ptr, False), "version": 2}
 
-    op = ShardedGemm(plan, dist, slab_gemm, b_owner=0)
+    def shared_buffer(shape):
+        """eml_alloc'd tensor + the base pointers of every rank's copy (None for this rank), over CUDA IPC."""
+        raw = C.c_void_p()
+        check(lib.eml_alloc(C.byref(raw), shape[0] * shape[1] * 8))
+        t = torch.as_tensor(RawCuda(raw.value, shape), device=dev)
+        handle = C.create_string_buffer(64)
+        check(lib.eml_ipc_export(raw, handle))
+        handles = [None] * world
+        dist.all_gather_object(handles, handle.raw)
+        bases = []
+        for r in range(world):
+            if r == rank:
+                bases.append(None)
+                continue
+            base = C.c_void_p()
+            check(lib.eml_ipc_open(C.create_string_buffer(handles[r], 64), C.byref(base)))
+            bases.append(base.value)
+        return t, bases
+
+    fused = args.gather == "fused"
+    remote = None
+    if fused:
+        Cfull, c_bases = shared_buffer((world * h, n))
+        peers = [b + rank * h * n * 8 for b in c_bases if b is not None]  # my rows inside each peer's copy of C
+        remote = (C.c_void_p * len(peers))(*peers)
+    else:
+        Cfull = torch.empty((world * h, n), device=dev, dtype=f64)
+    flag = torch.zeros(1, device=dev)
+
+    # B lives on rank 0 (generated in place); the other ranks' B is the destination of the broadcast
+    pull_b = None
+    if args.bcast == "ce":
+        B, b_bases = shared_buffer((n, n))
+        side = torch.cuda.Stream(device=dev)
+
+        class Arrival:
+            def __init__(self, ev):
+                self.ev = ev
+
+            def wait(self):
+                stream.wait_event(self.ev)
+
+        def pull_b(k0, k1):
+            # copy-engine pull of rows [k0, k1) of rank 0's B over NVLink, on a side stream
+            side.wait_stream(stream)  # WAR: the previous step's GEMMs have finished reading these rows
+            check(lib.eml_copy_async(C.c_void_p(B.data_ptr() + k0 * n * 8), C.c_void_p(b_bases[0] + k0 * n * 8),
+                                     (k1 - k0) * n * 8, C.c_void_p(side.cuda_stream)))
+            ev = torch.cuda.Event()
+            ev.record(side)
+            return Arrival(ev)
+    else:
+        B = torch.empty((n, n), device=dev, dtype=f64)
+    B_src = None
+    if rank == 0:
+        gen.manual_seed(0x5EED0006)
+        B.copy_(torch.rand((n, n), generator=gen, device=dev, dtype=f64) * 2 - 1)
+        B_src = B
+    torch.cuda.synchronize()
+    dist.barrier()
+
+    def slab_gemm(a, b, c, accumulate, scatter=False):
+        # c (+)= a * b on views of row-major buffers: strides come from the views, no copies
+        if scatter:
+            check(lib.eml_gemm_f64_scatter_dev(vp(a), vp(b), vp(c), a.shape[0], b.shape[1], a.shape[1], a.stride(0),
+                                               b.stride(0), c.stride(0), 1 if accumulate else 0, remote, len(remote), sp))
+        else:
+            check(lib.eml_contract_f64_dev(vp(a), vp(b), vp(c), 1, a.shape[0], b.shape[1], a.shape[1],
+                                           s3(0, a.stride(0), 1), s3(0, b.stride(0), 1), s3(0, c.stride(0), 1),
+                                           1 if accumulate else 0, sp))
+
+    op = ShardedGemm(plan, dist, slab_gemm, b_owner=0, gather=args.gather, flag=flag, pull_b=pull_b)
 
     def step():
         op.step(A, B, Cfull, B_src)
@@ -503,10 +591,49 @@ def sharded(args, torch, dist, eml, lib, check, dev, stream, sp, rank, world, ti
     step()
     torch.cuda.synchronize()
     same_bits = bool(torch.equal(single, Cfull[rank * h:rank * h + (last - first)]))
+    diag = None
+    if args.diag:
+        def ev_time(fn, reps=2):
+            fn()
+            barrier()
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for _ in range(reps):
+                fn()
+            b_.record(stream)
+            barrier()
+            return max_over_ranks(a.elapsed_time(b_) / reps)
+
+        from easy_ml_b200.sharded import k_panels
+
+        def bcast_only():
+            ws = [dist.broadcast(B[k0:k1], src=0, async_op=True) for k0, k1 in k_panels(n, plan.panels)]
+            for w in ws:
+                w.wait()
+
+        tmp = torch.empty((world * h, n), device=dev, dtype=f64)
+        diag = {"broadcast_B_ms": ev_time(bcast_only),
+                "nccl_allgather_C_ms": ev_time(lambda: dist.all_gather_into_tensor(tmp, tmp[rank * h:(rank + 1) * h])),
+                "barrier_allreduce_ms": ev_time(lambda: dist.all_reduce(flag)),
+                "slab_gemm_single_launch_ms": kms}
+        del tmp
+    gather_check = None
+    if fused:
+        # correctness baseline: the same step with ncclAllGather delivering the slabs must give the same C
+        Cref = torch.empty((world * h, n), device=dev, dtype=f64)
+        ShardedGemm(plan, dist, slab_gemm, b_owner=0, gather="nccl", flag=flag).step(A, B, Cref, B_src)  # ncclBroadcast too
+        torch.cuda.synchronize()
+        ok = torch.tensor([1.0 if torch.equal(Cref, Cfull) else 0.0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        gather_check = bool(ok.item() == 1.0)
+        del Cref
     return {
         "metric": "f64 matmul throughput", "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic", "config": workload_config(n, world), "clocks": clocks,
+        "dtype": "f64", "data": "synthetic",
+        "config": workload_config(n, world, "fused into the GEMM epilogue: peer stores over NVLink" if fused
+                                  else "ncclAllGather"),
+        "clocks": clocks,
         "gpu_launches": int(launches),
         "e2e": {"value": value, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                 "note": "sharded run keeps operands in HBM; host-pointer e2e is reported by the 1-GPU run"},
@@ -515,7 +642,9 @@ def sharded(args, torch, dist, eml, lib, check, dev, stream, sp, rank, world, ti
                      "peak_source": "nominal B200 FP64 per GPU", "kernel_ms": kms,
                      "algorithmic_flop_per_launch": 2.0 * (last - first) * n * n,
                      "nvlink_bytes_in_per_gpu_per_step": plan.comm_bytes(8)},
-        "parity": {"panelled_step_equals_single_launch_bits": same_bits},
+        "parity": {"panelled_step_equals_single_launch_bits": same_bits,
+                   "fused_allgather_equals_nccl_allgather": gather_check},
+        "diag": diag,
         "cpu_baseline": None,
     }
 

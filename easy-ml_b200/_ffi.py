@@ -58,6 +58,11 @@ SIGNATURES = {
     "eml_upload": (cint, [vp, vp, C.c_size_t]),
     "eml_download": (cint, [vp, vp, C.c_size_t]),
     "eml_sync": (cint, []),
+    "eml_gemm_f64_scatter_dev": (cint, [vp, vp, vp, i64, i64, i64, i64, i64, i64, cint, C.POINTER(vp), cint, vp]),
+    "eml_ipc_export": (cint, [vp, vp]),
+    "eml_ipc_open": (cint, [vp, C.POINTER(vp)]),
+    "eml_ipc_close": (cint, [vp]),
+    "eml_copy_async": (cint, [vp, vp, C.c_size_t, vp]),
     "eml_host_alloc": (cint, [C.POINTER(vp), C.c_size_t]),
     "eml_host_free": (cint, [vp]),
     "eml_tape_create": (cint, [cint, C.POINTER(vp)]),

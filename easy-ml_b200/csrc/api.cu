@@ -430,6 +430,53 @@ int eml_download(void* dst, const void* src, size_t bytes) {
     EML_CUDA(cudaStreamSynchronize(ctx->stream));
     return EML_OK;
 }
+int eml_gemm_f64_scatter_dev(const double* A, const double* B, double* C, int64_t M, int64_t N, int64_t K,
+                             int64_t lda, int64_t ldb, int64_t ldc, int accumulate, double* const* c_remote,
+                             int n_remote, void* stream) {
+    DeviceCtx* ctx = nullptr;
+    EML_TRY(get_ctx(&ctx));
+    if (n_remote < 0 || n_remote > 7 || (n_remote && !c_remote)) EML_BAD_ARG("scatter: 0..7 remote destinations");
+    if (lda < K || ldb < N || ldc < N) EML_BAD_ARG("gemm: leading dimension smaller than the row length");
+    cudaStream_t st = (cudaStream_t)stream;
+    NoSplitK no_split;  // the rows must carry the same bits as an unsharded launch
+    set_remote_c(c_remote, n_remote);
+    int rc = contract_dev<double>(ctx, A, B, C, 1, M, N, K, Strides3{0, lda, 1}, Strides3{0, ldb, 1},
+                                  Strides3{0, ldc, 1}, accumulate != 0, false, st);
+    bool pending = remote_c_pending();
+    clear_remote_c();
+    EML_TRY(rc);
+    if (pending)  // a kernel without the fused epilogue ran (unaligned / tiny shape): copy the rows instead
+        for (int r = 0; r < n_remote; r++)
+            EML_CUDA(cudaMemcpy2DAsync(c_remote[r], ldc * sizeof(double), C, ldc * sizeof(double), N * sizeof(double),
+                                       M, cudaMemcpyDefault, st));
+    return EML_OK;
+}
+int eml_ipc_export(void* dptr, void* handle64) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    if (!dptr || !handle64) EML_BAD_ARG("ipc_export: null argument");
+    cudaIpcMemHandle_t h;
+    EML_CUDA(cudaIpcGetMemHandle(&h, dptr));
+    memcpy(handle64, &h, 64);
+    return EML_OK;
+}
+int eml_ipc_open(const void* handle64, void** dptr) {
+    if (!dptr || !handle64) EML_BAD_ARG("ipc_open: null argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    EML_CUDA(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return EML_OK;
+}
+int eml_ipc_close(void* dptr) {
+    if (dptr) EML_CUDA(cudaIpcCloseMemHandle(dptr));
+    return EML_OK;
+}
+int eml_copy_async(void* dst, const void* src, size_t bytes, void* stream) {
+    DeviceCtx* ctx = nullptr;
+    EML_TRY(get_ctx(&ctx));
+    if (!dst || !src) EML_BAD_ARG("copy_async: null pointer");
+    EML_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+    return EML_OK;
+}
 int eml_host_alloc(void** hptr, size_t bytes) {
     DeviceCtx* ctx = nullptr;
     EML_TRY(get_ctx(&ctx));

@@ -98,6 +98,13 @@ int launch_gemm_dmma_f64(DeviceCtx* ctx, const double* A, const double* B, doubl
                          int64_t N, int64_t K, Strides3 sA, Strides3 sB, Strides3 sC, bool accumulate,
                          cudaStream_t stream, bool* handled);
 
+// Fused all-gather: register up to 7 peer-mapped copies of C for the NEXT f64 GEMM launch on this thread; the
+// TMA DMMA kernel stores every finished tile to them too.  remote_c_pending() stays true when the dispatch
+// took a kernel without that epilogue (the caller then copies the rows itself).
+void set_remote_c(double* const* ptrs, int n);
+bool remote_c_pending();
+void clear_remote_c();
+
 // f32 3xTF32 on tcgen05 + TMEM, operands staged by TMA (pack kernel splits into big/small parts).
 int launch_gemm_tf32x3_f32(DeviceCtx* ctx, const float* A, const float* B, float* C, int64_t batch, int64_t M,
                            int64_t N, int64_t K, Strides3 sA, Strides3 sB, Strides3 sC, bool accumulate,

@@ -241,6 +241,15 @@ inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) =
 // =================================================================================================
 namespace tma {
 
+// Extra destinations of the epilogue: the same C tile is also stored, at the same offsets, into up to 7
+// peer GPUs' buffers (peer-mapped pointers, st.global over NVLink) -- the all-gather of a row-sharded GEMM
+// fused into the kernel that produces the rows.
+struct Remote {
+    double* p[7];
+    int n;
+};
+thread_local Remote t_remote = {{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}, 0};
+
 // 8 consumer warps (two warpgroups) + one producer warpgroup (one lane of it works).  The register file is
 // re-split with setmaxnreg: a 384-thread CTA compiles to <= 168 registers per thread, the consumers need
 // 128 for the accumulators alone, so the producer warpgroup hands its share over (40 vs 232).
@@ -255,7 +264,7 @@ template <bool A_KIN, bool B_KIN>
 __global__ void __launch_bounds__(TTHREADS, 1)
 dgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, double* C,
                  int64_t M, int64_t N, int64_t K, int64_t ldc, int64_t strideC, int tiles_m, int tiles_n,
-                 int accumulate) {
+                 int accumulate, const Remote remote) {
     using namespace sm100;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     // offset (not a cast through an integer) so the compiler keeps the shared address space: LDS, not LD
@@ -381,6 +390,28 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             }
         }
     }
+    // fused all-gather: the finished tile goes to every peer's copy of C as well (same layout, same ldc)
+    for (int r = 0; r < remote.n; r++) {
+        double* R = remote.p[r] + (int64_t)batch * strideC;
+        const bool rvec = ((ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(R) & 15) == 0);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            int64_t row = m0 + wm + i * 8 + g;
+            if (row >= M) continue;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                int64_t col = n0 + wn + j * 8 + 2 * t;
+                if (col >= N) continue;
+                double* p = R + row * ldc + col;
+                if (rvec && col + 1 < N) {
+                    *reinterpret_cast<double2*>(p) = make_double2(acc[i][j][0], acc[i][j][1]);
+                } else {
+                    p[0] = acc[i][j][0];
+                    if (col + 1 < N) p[1] = acc[i][j][1];
+                }
+            }
+        }
+    }
 }
 
 // Tensor map of one operand.  KIN: element (mn, k) at base[mn*ld + k]; else at base[k*ld + mn].
@@ -419,16 +450,25 @@ int launch(const double* A, const double* B, double* C, int64_t batch, int64_t M
     }
     int64_t tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
     dim3 grid((unsigned)(tiles_m * tiles_n), (unsigned)batch);
+    const Remote remote = t_remote;
+    t_remote.n = 0;  // consumed: the caller checks remote_c_pending() to see whether a kernel took them
     kern<<<grid, TTHREADS, T_SMEM_BYTES, stream>>>(mapA, mapB, C, M, N, K, ldc, stC, (int)tiles_m, (int)tiles_n,
-                                                   accumulate ? 1 : 0);
+                                                   accumulate ? 1 : 0, remote);
     count_launch();
-    set_last_kernel("dmma_f64_tma");
+    set_last_kernel(remote.n ? "dmma_f64_tma+peer_allgather" : "dmma_f64_tma");
     return check_launch("dgemm_tma");
 }
 
 }  // namespace tma
 
 }  // namespace
+
+void set_remote_c(double* const* ptrs, int n) {
+    tma::t_remote.n = n;
+    for (int i = 0; i < n && i < 7; i++) tma::t_remote.p[i] = ptrs[i];
+}
+bool remote_c_pending() { return tma::t_remote.n != 0; }
+void clear_remote_c() { tma::t_remote.n = 0; }
 
 int launch_gemm_dmma_f64(DeviceCtx*, const double* A, const double* B, double* C, int64_t batch, int64_t M,
                          int64_t N, int64_t K, Strides3 sA, Strides3 sB, Strides3 sC, bool accumulate,

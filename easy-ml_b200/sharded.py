@@ -6,7 +6,10 @@ contiguous row blocks, B is replicated:
 
     rank r owns rows [row_range(M, world, r))            no cross-rank reduction -> same bits as one GPU
     B travels from its owner in K panels (broadcast)     panel p+1 is in flight while panel p is multiplied
-    C slabs are delivered with one all-gather             in place: every slab already sits at its offset
+    C slabs are delivered either by one NCCL all-gather (in place: every slab already sits at its offset;
+    the correctness baseline) or -- gather="fused" -- by the GEMM kernel itself: the launch of the last K
+    panel stores every finished tile into all peers' copies of C over NVLink (peer-mapped pointers), so no
+    separate collective runs; a stream-ordered 1-element all-reduce is the only synchronisation
 
 One process per GPU; `torch.distributed` (NCCL on GPUs, gloo on CPU for the host-logic tests) is the
 plumbing.  The slab product itself is injected (`slab_gemm`): on the GPU it is the library's
@@ -30,10 +33,25 @@ def row_range(m, world, rank):
 
 
 def k_panels(k, panels):
-    """[first, last) k ranges of the broadcast panels (the last one takes the remainder)."""
+    """[first, last) k ranges of the broadcast panels.
+
+    Geometric schedule: the first two panels are k / 2^(panels-1) deep and every later one doubles, so the only
+    exposed communication is the arrival of a thin first panel, while most of the work runs in a few deep
+    launches (each launch re-reads C once and pays one prologue/epilogue per tile).  Boundaries are multiples
+    of 32 (the kernels' k tile) whenever k allows it."""
     panels = max(1, min(panels, k))
-    step = (k + panels - 1) // panels
-    return [(p * step, min(k, (p + 1) * step)) for p in range(panels) if p * step < k]
+    if panels == 1:
+        return [(0, k)]
+    unit = max(1, k >> (panels - 1))
+    if k >= 64:
+        unit = max(32, unit // 32 * 32)
+    edges, depth = [0], unit
+    while edges[-1] + depth < k and len(edges) < panels:
+        edges.append(edges[-1] + depth)
+        if len(edges) > 2:
+            depth *= 2
+    edges.append(k)
+    return [(a, b) for a, b in zip(edges, edges[1:]) if b > a]
 
 
 @dataclass
@@ -66,11 +84,19 @@ class ShardedGemm:
     a_slab : [slab_rows, K]  this rank's rows of A (rows past M are ignored)
     b      : [K, N]          replicated destination of the broadcast (b_src on the owner holds the data)
     c_full : [world * slab_rows, N]  every rank ends up with all of C in c_full[:M]
-    slab_gemm(a_view, b_view, c_view, accumulate) computes c_view (+)= a_view @ b_view on the device.
+    slab_gemm(a_view, b_view, c_view, accumulate, scatter) computes c_view (+)= a_view @ b_view on the device;
+    scatter=True (only ever on the last K panel, only with gather="fused") asks it to also deliver the
+    finished rows to every peer.
     """
 
-    def __init__(self, plan, dist, slab_gemm, b_owner=0):
+    def __init__(self, plan, dist, slab_gemm, b_owner=0, gather="nccl", flag=None, pull_b=None):
+        assert gather in ("nccl", "fused")
         self.plan, self.dist, self.slab_gemm, self.b_owner = plan, dist, slab_gemm, b_owner
+        self.gather, self.flag = gather, flag  # flag: 1-element tensor on this rank's device (fused barrier)
+        # pull_b(k0, k1) -> object with .wait(): fetches rows [k0, k1) of B from the owner into this rank's b
+        # without NCCL (copy engines over NVLink on a side stream: no SMs are taken from the GEMM).
+        # None = dist.broadcast.
+        self.pull_b = pull_b
 
     def step(self, a_slab, b, c_full, b_src=None):
         p, dist = self.plan, self.dist
@@ -84,12 +110,21 @@ class ShardedGemm:
             blk = b[k0:k1]
             if p.rank == self.b_owner and b_src is not None and b_src.data_ptr() != b.data_ptr():
                 blk.copy_(b_src[k0:k1], non_blocking=True)
-            works.append(dist.broadcast(blk, src=self.b_owner, async_op=True) if p.world > 1 else None)
+            if p.world == 1:
+                works.append(None)
+            elif self.pull_b is not None:
+                works.append(self.pull_b(k0, k1) if p.rank != self.b_owner else None)
+            else:
+                works.append(dist.broadcast(blk, src=self.b_owner, async_op=True))
         for i, (k0, k1) in enumerate(panels):
             if works[i] is not None:
                 works[i].wait()
             if rows > 0:
-                self.slab_gemm(a_slab[:rows, k0:k1], b[k0:k1], c_slab[:rows], i > 0)
+                scatter = self.gather == "fused" and p.world > 1 and i == len(panels) - 1
+                self.slab_gemm(a_slab[:rows, k0:k1], b[k0:k1], c_slab[:rows], i > 0, scatter)
         if p.world > 1:
-            dist.all_gather_into_tensor(c_full, c_slab)  # in place: the slab is a view into c_full
+            if self.gather == "fused":
+                dist.all_reduce(self.flag)  # stream-ordered barrier: every peer's stores have been issued and drained
+            else:
+                dist.all_gather_into_tensor(c_full, c_slab)  # in place: the slab is a view into c_full
         return c_full[:p.m]

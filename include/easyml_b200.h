@@ -164,6 +164,24 @@ int eml_gemm_exact_f32_dev(const float* A, const float* B, float* C, int64_t M, 
 int eml_gemm_exact_f64_dev(const double* A, const double* B, double* C, int64_t M, int64_t N, int64_t K,
                            int64_t lda, int64_t ldb, int64_t ldc, void* stream);
 
+/* Row-sharded GEMM with the all-gather fused into the epilogue (BASELINE config 5).
+ * C (+)= A*B exactly as eml_gemm_f64_dev, and every finished tile is ALSO stored -- same offsets, same ldc --
+ * into n_remote other buffers, normally the same rows of C in the peer GPUs' memory (pointers obtained with
+ * eml_ipc_open; stores travel over NVLink from inside the GEMM kernel, no separate collective).  The caller
+ * orders the peers afterwards (any stream-ordered barrier, e.g. a 1-element NCCL all-reduce).
+ * Replaces, for one row block, matrix_view_multiplication src/matrices/operations.rs:165-196. */
+int eml_gemm_f64_scatter_dev(const double* A, const double* B, double* C, int64_t M, int64_t N, int64_t K,
+                             int64_t lda, int64_t ldb, int64_t ldc, int accumulate, double* const* c_remote,
+                             int n_remote, void* stream);
+/* CUDA IPC plumbing for the peer-mapped buffers (one process per GPU): export a buffer obtained from
+ * eml_alloc as a 64-byte handle, open a peer's handle in this process (peer access is enabled on demand). */
+int eml_ipc_export(void* dptr, void* handle64);
+int eml_ipc_open(const void* handle64, void** dptr);
+int eml_ipc_close(void* dptr);
+/* Asynchronous copy between any two device-visible buffers (local, or a peer's opened with eml_ipc_open:
+ * such copies run on the copy engines over NVLink and take no SM from a concurrent GEMM). */
+int eml_copy_async(void* dst, const void* src, size_t bytes, void* stream);
+
 /* Backward of C = A*B for reverse-mode autodiff:  dA += dC * B^T  and/or  dB += A^T * dC  (either
  * output may be NULL).  This is what the reverse sweep Record::try_derivatives,
  * src/differentiation.rs:623-648, computes over the M*N*(2K-1) tape entries that

@@ -21,7 +21,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, m, n, k, panels, out):
+def _worker(rank, world, port, m, n, k, panels, out, gather="nccl"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -39,14 +39,33 @@ def _worker(rank, world, port, m, n, k, panels, out):
         c_full = torch.full((world * h, n), -1.0, dtype=torch.float64)
         calls = []
 
-        def slab_gemm(a, bb, c, accumulate):
+        scatters = []
+
+        def slab_gemm(a, bb, c, accumulate, scatter):
             calls.append((tuple(a.shape), tuple(bb.shape), accumulate))
+            scatters.append(scatter)
             if accumulate:
                 c += a @ bb
             else:
                 c.copy_(a @ bb)
 
-        c = ShardedGemm(plan, dist, slab_gemm, b_owner=0).step(a_slab, b, c_full, b_src)
+        flag = torch.zeros(1)
+        op = ShardedGemm(plan, dist, slab_gemm, b_owner=0, gather=gather, flag=flag)
+        c = op.step(a_slab, b, c_full, b_src)
+        if gather == "fused":
+            # on the GPU the last launch stores the rows into the peers; emulate those stores here, after
+            # checking that exactly the last panel was asked to scatter and that no collective moved C
+            assert scatters == [False] * (len(scatters) - 1) + [True] * (1 if scatters else 0)
+            mine = c_full[rank * h:(rank + 1) * h].clone()
+            pieces = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(pieces, mine)
+            for r, piece in enumerate(pieces):
+                if r != rank:
+                    assert torch.all(c_full[r * h:(r + 1) * h] == -1.0)  # untouched by the step itself
+                    c_full[r * h:(r + 1) * h] = piece
+            c = c_full[:m]
+        else:
+            assert not any(scatters)
         ok = torch.equal(c, a_full @ b_full) and torch.equal(b, b_full)
         # first panel overwrites, later ones accumulate; one call per panel on ranks that own rows
         expect_calls = len(k_panels(k, panels)) if last > first else 0
@@ -63,6 +82,15 @@ def test_sharded_gemm_over_gloo(world, m, n, k, panels):
         out = mgr.dict()
         mp.spawn(_worker, args=(world, port, m, n, k, panels, out), nprocs=world, join=True)
         assert all(out.get(r) for r in range(world)), dict(out)
+
+
+def test_sharded_gemm_fused_gather_protocol_over_gloo():
+    """gather="fused": only the last K panel is asked to scatter, no collective moves C, one barrier."""
+    port = _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_worker, args=(2, port, 24, 16, 20, 4, out, "fused"), nprocs=2, join=True)
+        assert all(out.get(r) for r in range(2)), dict(out)
 
 
 def test_partition_covers_rows_once():
