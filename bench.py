@@ -30,6 +30,10 @@ if ROOT not in sys.path:
 NOMINAL_FP64_TFLOPS = 37.0   # HGX B200 datasheet, per GPU (FP64 vector == FP64 tensor)
 NOMINAL_FP32_TFLOPS = 75.0   # FFMA
 NOMINAL_TF32_TFLOPS = 1100.0
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE dgemm_tma_kernel launch at 8192^3, from the round-1
+# `ncu --set full` capture (profiles/r1_prof_dgemm_tma_r1_raw.csv): 6.771 GB + 0.530 GB.  4.5x the algorithmic
+# 1.61 GB (panel re-reads that miss L2) at 3 % DRAM utilisation: the kernel is DMMA-pipe bound (97.6 % active).
+NCU_DRAM_TRAFFIC_DGEMM_8192 = {"bytes": 7.300e9, "source": "profiles/r1_prof_dgemm_tma_r1_raw.csv"}
 
 
 def parse():
@@ -346,8 +350,12 @@ def main():
             "e2e": {"value": flop / (e2e_ms * 1e-3) / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": 2 * n * n * 8,
                     "d2h_bytes_per_step": n * n * 8, "ms_per_step": e2e_ms, "matches_device_result": e2e_ok},
             "roofline": {"bound": "tensor", "kernel": kernel_name, "achieved": achieved, "peak": NOMINAL_FP64_TFLOPS,
-                         "unit": "TFLOP/s", "frac": achieved / NOMINAL_FP64_TFLOPS, "traffic": None,
-                         "peak_source": "nominal B200 FP64 (MEASURED_PEAKS.json holds no FP64 figure; it is %s)" % peak_kind,
+                         "unit": "TFLOP/s", "frac": achieved / NOMINAL_FP64_TFLOPS,
+                         "traffic": NCU_DRAM_TRAFFIC_DGEMM_8192["bytes"] if n == 8192 else None,
+                         "traffic_source": NCU_DRAM_TRAFFIC_DGEMM_8192["source"] if n == 8192 else None,
+                         "peak_source": "nominal B200 FP64 37 TF = 128 flop/clk/SM x 148 SM x 1.965 GHz (ncu: "
+                                        "sm__ops_path_tensor_src_fp64 peak_sustained 128/clk/SM); MEASURED_PEAKS.json "
+                                        "(%s) holds HBM and bf16 figures only" % peak_kind,
                          "cublas_dgemm_tflops_same_run": cublas_tf, "frac_of_cublas": achieved / cublas_tf,
                          "kernel_ms": kernel_ms, "algorithmic_flop_per_launch": flop,
                          "algorithmic_bytes_per_launch": 3 * n * n * 8},
