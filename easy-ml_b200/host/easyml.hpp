@@ -1,0 +1,522 @@
+// easyml.hpp -- C++ mirror of Easy ML's operator API for the f32/f64 dense-contraction path, over the C ABI
+// of include/easyml_b200.h.  Header-only, C++17.
+//
+// The reference is a Rust crate (no Rust toolchain in this image), so this is the compiled-language host side
+// of the drop-in boundary: same names, same argument meaning, same validation and the same messages as the
+// reference -- a Rust `panic!` becomes `easyml::Panic`, `Err(InconsistentDimensionLengthError)` becomes the
+// exception of that name.  Every check runs BEFORE the FFI call, exactly where the Rust shim keeps them
+// (INTEGRATION.md section 4).  There is no CPU fallback: without a B200 every product throws
+// `easyml::BackendError` carrying the library's message.
+//
+// Citations are file:line of the reference (Skeletonxf/easy-ml), relative to its repository root.
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <optional>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <type_traits>
+#include <utility>
+#include <vector>
+
+#include "easyml_b200.h"
+
+namespace easyml {
+
+struct Panic : std::runtime_error {  // the reference would panic!() with this text
+    using std::runtime_error::runtime_error;
+};
+struct BackendError : std::runtime_error {  // non-zero code from the C ABI (no device, CUDA error ...)
+    int code;
+    BackendError(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+using Dimension = std::string;  // `&'static str` in the reference, src/tensors/mod.rs:57
+using Shape = std::vector<std::pair<Dimension, int64_t>>;
+
+// Err(InconsistentDimensionLengthError { lengths, dimension }), src/tensors/einsum.rs:321
+struct InconsistentDimensionLengthError : std::runtime_error {
+    Dimension dimension;
+    std::vector<std::optional<int64_t>> lengths;
+    InconsistentDimensionLengthError(Dimension d, std::vector<std::optional<int64_t>> l)
+        : std::runtime_error("InconsistentDimensionLengthError: dimension " + d), dimension(std::move(d)),
+          lengths(std::move(l)) {}
+};
+
+namespace detail {
+inline void check(int code) {
+    if (code != EML_OK) throw BackendError(code, eml_last_error());
+}
+template <class T>
+constexpr bool is_f32 = std::is_same<T, float>::value;
+template <class T>
+constexpr void require_float() {
+    static_assert(std::is_same<T, float>::value || std::is_same<T, double>::value,
+                  "the B200 path serves f32 and f64; other numeric types stay on the reference's generic path");
+}
+// Debug formatting of [(Dimension, usize); D], e.g. [("r", 2), ("c", 3)]
+inline std::string shape_debug(const Shape& s) {
+    std::ostringstream o;
+    o << "[";
+    for (size_t i = 0; i < s.size(); i++) o << (i ? ", " : "") << "(\"" << s[i].first << "\", " << s[i].second << ")";
+    o << "]";
+    return o.str();
+}
+}  // namespace detail
+
+// ------------------------------------------------------------------------------------------------ Matrix
+// easy_ml::matrices::Matrix<T>: flat row-major storage, src/matrices/mod.rs:67-71
+template <class T>
+class Matrix {
+  public:
+    Matrix(int64_t rows, int64_t cols, std::vector<T> row_major)  // from_flat_row_major, mod.rs:213
+        : rows_(rows), cols_(cols), data_(std::move(row_major)) {
+        detail::require_float<T>();
+        if (rows < 1 || cols < 1 || (int64_t)data_.size() != rows * cols)
+            throw Panic("Inconsistent size, attempted to construct a " + std::to_string(rows) + "x" +
+                        std::to_string(cols) + " matrix but provided with " + std::to_string(data_.size()) +
+                        " elements.");
+    }
+    int64_t rows() const { return rows_; }
+    int64_t columns() const { return cols_; }
+    const T& get(int64_t r, int64_t c) const { return data_[r * cols_ + c]; }
+    const std::vector<T>& data() const { return data_; }
+    bool operator==(const Matrix& o) const { return rows_ == o.rows_ && cols_ == o.cols_ && data_ == o.data_; }
+
+    // <&Matrix<T> as Mul<&Matrix<T>>>::mul -> matrix_view_multiplication, src/matrices/operations.rs:165-196
+    Matrix operator*(const Matrix& right) const {
+        if (cols_ != right.rows_) {  // assert, :176-183
+            std::ostringstream m;
+            m << "Mismatched Matrices, left is " << rows_ << "x" << cols_ << ", right is " << right.rows_ << "x"
+              << right.cols_ << ", * is only defined for MxN * NxL";
+            throw Panic(m.str());
+        }
+        std::vector<T> c((size_t)(rows_ * right.cols_));
+        if constexpr (detail::is_f32<T>)
+            detail::check(eml_gemm_f32(data_.data(), right.data_.data(), c.data(), rows_, right.cols_, cols_, cols_,
+                                       right.cols_, right.cols_));
+        else
+            detail::check(eml_gemm_f64(data_.data(), right.data_.data(), c.data(), rows_, right.cols_, cols_, cols_,
+                                       right.cols_, right.cols_));
+        return Matrix(rows_, right.cols_, std::move(c));
+    }
+
+  private:
+    int64_t rows_, cols_;
+    std::vector<T> data_;
+};
+
+// ------------------------------------------------------------------------------------------------ Tensor
+// easy_ml::tensors::Tensor<T, D>: row-major Vec<T> + [(Dimension, usize); D], src/tensors/mod.rs:244-250.
+// The rank is a runtime property here (C++ has no need of the const generic); rank-specific operations check it.
+template <class T>
+class Tensor {
+  public:
+    Tensor(Shape shape, std::vector<T> data) : shape_(std::move(shape)), data_(std::move(data)) {
+        detail::require_float<T>();
+        int64_t n = 1;
+        for (auto& d : shape_) {
+            if (d.second < 1) throw Panic("Invalid shape: " + detail::shape_debug(shape_));  // mod.rs:96-123
+            n *= d.second;
+        }
+        for (size_t i = 0; i < shape_.size(); i++)
+            for (size_t j = i + 1; j < shape_.size(); j++)
+                if (shape_[i].first == shape_[j].first)
+                    throw Panic("Dimension names must all be unique: " + detail::shape_debug(shape_));
+        if ((int64_t)data_.size() != n)
+            throw Panic("Length of data does not match size of the shape: " + detail::shape_debug(shape_));
+    }
+    const Shape& shape() const { return shape_; }
+    const std::vector<T>& data() const { return data_; }
+    size_t rank() const { return shape_.size(); }
+    std::vector<Dimension> names() const {
+        std::vector<Dimension> n;
+        for (auto& d : shape_) n.push_back(d.first);
+        return n;
+    }
+    std::vector<int64_t> strides() const {  // compute_strides, mod.rs:563
+        std::vector<int64_t> s(shape_.size(), 1);
+        for (int i = (int)shape_.size() - 2; i >= 0; i--) s[i] = s[i + 1] * shape_[i + 1].second;
+        return s;
+    }
+    bool operator==(const Tensor& o) const { return shape_ == o.shape_ && data_ == o.data_; }
+
+    // Mul for rank 2 -> tensor_view_matrix_product, src/tensors/operations.rs:474-519
+    Tensor operator*(const Tensor& right) const {
+        if (rank() != 2 || right.rank() != 2) throw std::invalid_argument("* is defined for rank 2 tensors");
+        if (shape_[1].second != right.shape_[0].second)  // :485-491
+            throw Panic("Mismatched tensors, left is " + detail::shape_debug(shape_) + ", right is " +
+                        detail::shape_debug(right.shape_) +
+                        ", * is only defined for MxN * NxL dimension lengths");
+        Shape out{shape_[0], right.shape_[1]};
+        if (shape_[0].first == right.shape_[1].first)  // :492-501
+            throw Panic("Matrix multiplication of tensors with shapes left " + detail::shape_debug(shape_) +
+                        " and right " + detail::shape_debug(right.shape_) +
+                        " would create duplicate dimension names as the shape " + detail::shape_debug(out) +
+                        ". Rename one or both of the dimension names in the input to prevent this. * is defined as "
+                        "MxN * NxL = MxL");
+        const int64_t m = shape_[0].second, k = shape_[1].second, n = right.shape_[1].second;
+        std::vector<T> c((size_t)(m * n));
+        if constexpr (detail::is_f32<T>)
+            detail::check(eml_gemm_f32(data_.data(), right.data_.data(), c.data(), m, n, k, k, n, n));
+        else
+            detail::check(eml_gemm_f64(data_.data(), right.data_.data(), c.data(), m, n, k, k, n, n));
+        return Tensor(out, std::move(c));
+    }
+
+    // Tensor<T, 1>::scalar_product, src/tensors/mod.rs:1773 -> operations.rs:1773-1808
+    T scalar_product(const Tensor& right) const {
+        if (rank() != 1 || right.rank() != 1) throw std::invalid_argument("scalar_product is defined for rank 1");
+        if (shape_ != right.shape_)
+            throw Panic("Dimensions of left and right tensors are not the same: (left: " + detail::shape_debug(shape_) +
+                        ", right: " + detail::shape_debug(right.shape_) + ")");
+        T out{};
+        if constexpr (detail::is_f32<T>)
+            detail::check(eml_dot_f32(data_.data(), 1, right.data_.data(), 1, (int64_t)data_.size(), &out));
+        else
+            detail::check(eml_dot_f64(data_.data(), 1, right.data_.data(), 1, (int64_t)data_.size(), &out));
+        return out;
+    }
+
+  private:
+    Shape shape_;
+    std::vector<T> data_;
+};
+
+// ------------------------------------------------------------------------------------------------ Einsum
+// Einsum::with_2(&x, &y).to([...]) -- Einsum2::to, src/tensors/einsum.rs:908-980
+template <class T>
+class Einsum2 {
+  public:
+    Einsum2(const Tensor<T>& x, const Tensor<T>& y) : x_(x), y_(y) {}
+
+    Tensor<T> to(const std::vector<Dimension>& output) const {
+        const Shape &xs = x_.shape(), &ys = y_.shape();
+        auto find = [](const Shape& s, const Dimension& d) -> std::optional<int64_t> {
+            for (auto& e : s)
+                if (e.first == d) return e.second;
+            return std::nullopt;
+        };
+        // output_shape_for :563-572 with length_of :508-538
+        Shape out_shape;
+        for (auto& d : output) {
+            std::vector<std::optional<int64_t>> lengths{find(xs, d), find(ys, d)};
+            std::optional<int64_t> known;
+            bool ok = true;
+            for (auto& l : lengths)
+                if (l) {
+                    if (known && *known != *l) ok = false;
+                    known = l;
+                }
+            if (!known || !ok) throw InconsistentDimensionLengthError(d, lengths);
+            out_shape.emplace_back(d, *known);
+        }
+        for (size_t i = 0; i < output.size(); i++)
+            for (size_t j = i + 1; j < output.size(); j++)
+                if (output[i] == output[j])
+                    throw Panic("Dimension names must all be unique: " + detail::shape_debug(out_shape));
+        auto in_out = [&](const Dimension& d) { return std::find(output.begin(), output.end(), d) != output.end(); };
+        // summation_dimensions :579-622: input names not in the output, in order of first appearance
+        Shape summation;
+        for (const Shape* s : {&xs, &ys})
+            for (auto& e : *s) {
+                if (in_out(e.first)) continue;
+                auto seen = find(summation, e.first);
+                if (!seen)
+                    summation.push_back(e);
+                else if (*seen != e.second)
+                    throw InconsistentDimensionLengthError(e.first, {find(xs, e.first), find(ys, e.first)});
+            }
+        std::map<Dimension, int64_t> len, sx, sy, so;
+        for (auto& e : out_shape) len[e.first] = e.second;
+        for (auto& e : summation) len[e.first] = e.second;
+        {
+            auto st = x_.strides();
+            for (size_t i = 0; i < xs.size(); i++) sx[xs[i].first] = st[i];
+            st = y_.strides();
+            for (size_t i = 0; i < ys.size(); i++) sy[ys[i].first] = st[i];
+            int64_t acc = 1;
+            for (int i = (int)out_shape.size() - 1; i >= 0; i--) {
+                so[out_shape[i].first] = acc;
+                acc *= out_shape[i].second;
+            }
+        }
+        auto stride = [](const std::map<Dimension, int64_t>& m, const Dimension& d) {
+            auto it = m.find(d);
+            return it == m.end() ? int64_t(0) : it->second;
+        };
+        int64_t total = 1;
+        for (auto& e : out_shape) total *= e.second;
+        std::vector<T> out((size_t)total);
+
+        // classify every name by where it appears: batch / M / N / K
+        std::vector<Dimension> batch, md, nd, kd;
+        bool lone_sum = false;
+        for (auto& d : output) {
+            bool ix = sx.count(d), iy = sy.count(d);
+            (ix && iy ? batch : ix ? md : nd).push_back(d);
+        }
+        for (auto& e : summation) {
+            if (sx.count(e.first) && sy.count(e.first))
+                kd.push_back(e.first);
+            else
+                lone_sum = true;
+        }
+        struct Role {
+            bool ok = true;
+            int64_t length = 1;
+            std::vector<int64_t> strides;
+        };
+        // several names playing one role merge only when they nest contiguously, in order, in every tensor
+        auto merge = [&](std::vector<Dimension> dims, std::vector<const std::map<Dimension, int64_t>*> maps) {
+            Role r;
+            r.strides.assign(maps.size(), 0);
+            if (dims.empty()) return r;
+            std::vector<Dimension> kept;
+            for (auto& d : dims)
+                if (len[d] > 1) kept.push_back(d);
+            if (kept.empty()) kept.push_back(dims[0]);
+            for (auto& d : kept) r.length *= len[d];
+            for (size_t t = 0; t < maps.size(); t++) {
+                for (size_t i = 0; i + 1 < kept.size(); i++)
+                    if (stride(*maps[t], kept[i]) != stride(*maps[t], kept[i + 1]) * len[kept[i + 1]]) r.ok = false;
+                r.strides[t] = stride(*maps[t], kept.back());
+            }
+            return r;
+        };
+        bool gemm = !kd.empty() && !lone_sum;
+        Role b, m, n, k;
+        if (gemm) {
+            b = merge(batch, {&sx, &sy, &so});
+            m = merge(md, {&sx, &so});
+            n = merge(nd, {&sy, &so});
+            k = merge(kd, {&sx, &sy});
+            gemm = b.ok && m.ok && n.ok && k.ok;
+        }
+        if (gemm) {
+            const int64_t sA[3] = {b.strides[0], m.strides[0], k.strides[0]};
+            const int64_t sB[3] = {b.strides[1], k.strides[1], n.strides[0]};
+            const int64_t sC[3] = {b.strides[2], m.strides[1], n.strides[1]};
+            if constexpr (detail::is_f32<T>)
+                detail::check(eml_contract_f32(x_.data().data(), y_.data().data(), out.data(), b.length, m.length,
+                                               n.length, k.length, sA, sB, sC));
+            else
+                detail::check(eml_contract_f64(x_.data().data(), y_.data().data(), out.data(), b.length, m.length,
+                                               n.length, k.length, sA, sB, sC));
+        } else {
+            // not a (batched) GEMM: the strided loop nest in the reference's order, bit-exact
+            std::vector<int64_t> ol, ao, bo, sl, as, bs;
+            for (auto& e : out_shape) {
+                ol.push_back(e.second);
+                ao.push_back(stride(sx, e.first));
+                bo.push_back(stride(sy, e.first));
+            }
+            for (auto& e : summation) {
+                sl.push_back(e.second);
+                as.push_back(stride(sx, e.first));
+                bs.push_back(stride(sy, e.first));
+            }
+            if constexpr (detail::is_f32<T>)
+                detail::check(eml_einsum2_f32(x_.data().data(), (int64_t)x_.data().size(), y_.data().data(),
+                                              (int64_t)y_.data().size(), out.data(), (int)ol.size(), ol.data(),
+                                              ao.data(), bo.data(), (int)sl.size(), sl.data(), as.data(), bs.data()));
+            else
+                detail::check(eml_einsum2_f64(x_.data().data(), (int64_t)x_.data().size(), y_.data().data(),
+                                              (int64_t)y_.data().size(), out.data(), (int)ol.size(), ol.data(),
+                                              ao.data(), bo.data(), (int)sl.size(), sl.data(), as.data(), bs.data()));
+        }
+        return Tensor<T>(out_shape, std::move(out));
+    }
+
+  private:
+    const Tensor<T>& x_;
+    const Tensor<T>& y_;
+};
+struct Einsum {
+    template <class T>
+    static Einsum2<T> with_2(const Tensor<T>& x, const Tensor<T>& y) { return Einsum2<T>(x, y); }  // einsum.rs:113-127
+};
+
+// ------------------------------------------------------------------------------------------------ autodiff
+// WengertList<T>, src/differentiation.rs:327-331 -- here a handle to the device tape (one macro node per
+// container operation; tape length and every Index equal the reference's scalar tape, see csrc/tape.cu).
+template <class T>
+class WengertList {
+  public:
+    WengertList() {
+        detail::require_float<T>();
+        detail::check(eml_tape_create(detail::is_f32<T> ? EML_F32 : EML_F64, &t_));
+    }
+    ~WengertList() {
+        if (t_) eml_tape_destroy(t_);
+    }
+    WengertList(const WengertList&) = delete;
+    WengertList& operator=(const WengertList&) = delete;
+    int64_t len() const {  // operations.len()
+        int64_t n = 0;
+        detail::check(eml_tape_len(t_, &n));
+        return n;
+    }
+    void clear() { detail::check(eml_tape_clear(t_)); }  // differentiation.rs:674
+    eml_tape* raw() const { return t_; }
+
+  private:
+    eml_tape* t_ = nullptr;
+};
+
+template <class T>
+class RecordTensor;
+
+// Derivatives<T>, src/differentiation.rs:365-367
+template <class T>
+class Derivatives {
+  public:
+    explicit Derivatives(eml_derivs* d) : d_(d, [](eml_derivs* p) { eml_derivs_free(p); }) {}
+    T at(int64_t index) const {  // Index<&Record>, differentiation.rs:387-403
+        double v = 0;
+        detail::check(eml_derivs_at(d_.get(), index, &v));
+        return (T)v;
+    }
+    Tensor<T> at_tensor(const RecordTensor<T>& input) const;  // container_record/mod.rs:1292
+    int64_t len() const {
+        int64_t n = 0;
+        detail::check(eml_derivs_len(d_.get(), &n));
+        return n;
+    }
+    eml_derivs* raw() const { return d_.get(); }
+
+  private:
+    std::shared_ptr<eml_derivs> d_;
+};
+
+// RecordTensor<'a, T, S, 2> / RecordMatrix, container_record/mod.rs:66-89 (rank 2: the matmul path)
+template <class T>
+class RecordTensor {
+  public:
+    // RecordTensor::variables, mod.rs:149-164
+    static RecordTensor variables(const WengertList<T>& history, const Tensor<T>& x) {
+        require_rank2(x);
+        eml_val v;
+        detail::check(eml_tape_variables(history.raw(), x.data().data(), x.shape()[0].second, x.shape()[1].second, &v));
+        return RecordTensor(&history, v, x.shape(), true);
+    }
+    // RecordTensor::constants, mod.rs:115-128 (no history; `owner` only says which device tape holds the numbers)
+    static RecordTensor constants(const Tensor<T>& x, const WengertList<T>& owner) {
+        require_rank2(x);
+        eml_val v;
+        detail::check(eml_tape_constants(owner.raw(), x.data().data(), x.shape()[0].second, x.shape()[1].second, &v));
+        return RecordTensor(&owner, v, x.shape(), false);
+    }
+    RecordTensor(RecordTensor&& o) noexcept : list_(o.list_), v_(o.v_), shape_(std::move(o.shape_)), tracked_(o.tracked_) {
+        o.v_ = -1;
+    }
+    RecordTensor(const RecordTensor&) = delete;
+    ~RecordTensor() {
+        if (v_ >= 0) eml_val_release(list_->raw(), v_);
+    }
+    const Shape& shape() const { return shape_; }
+    bool has_history() const { return tracked_; }
+    eml_val raw() const { return v_; }
+    const WengertList<T>* list() const { return list_; }
+    void reset() { detail::check(eml_tape_reset(list_->raw(), v_)); }  // mod.rs:349-365
+
+    Tensor<T> numbers() const {
+        std::vector<T> out((size_t)(shape_[0].second * shape_[1].second));
+        detail::check(eml_val_numbers(list_->raw(), v_, out.data()));
+        return Tensor<T>(shape_, std::move(out));
+    }
+    std::vector<int64_t> indexes() const {  // the Index half of the (T, Index) view, mod.rs:2511
+        std::vector<int64_t> out((size_t)(shape_[0].second * shape_[1].second));
+        detail::check(eml_val_indexes(list_->raw(), v_, out.data()));
+        return out;
+    }
+
+    // &RecordTensor * &RecordTensor -> record_tensor_matrix_multiply, container_operations.rs:1318-1381
+    RecordTensor operator*(const RecordTensor& right) const {
+        if (tracked_ && right.tracked_ && list_ != right.list_)  // assert same list, :1331
+            throw Panic("Record containers must be using the same WengertList");
+        if (shape_[1].second != right.shape_[0].second)  // :1339-1345
+            throw Panic("Mismatched tensors, left is " + detail::shape_debug(shape_) + ", right is " +
+                        detail::shape_debug(right.shape_) +
+                        ", * is only defined for MxN * NxL dimension lengths");
+        Shape out{shape_[0], right.shape_[1]};
+        if (shape_[0].first == right.shape_[1].first)  // :1346-1355
+            throw Panic("Matrix multiplication of tensors with shapes left " + detail::shape_debug(shape_) +
+                        " and right " + detail::shape_debug(right.shape_) +
+                        " would create duplicate dimension names as the shape " + detail::shape_debug(out) +
+                        ". Rename one or both of the dimension names in the input to prevent this. * is defined as "
+                        "MxN * NxL = MxL");
+        eml_val c;
+        detail::check(eml_tape_matmul(list_->raw(), v_, right.v_, &c));
+        return RecordTensor(list_, c, out, tracked_ || right.tracked_);
+    }
+    // unary container operators, container_operations.rs:1644-1804 and swapped.rs:25-45
+    RecordTensor operator-() const { return unary(EML_OP_NEG, 0); }
+    RecordTensor exp() const { return unary(EML_OP_EXP, 0); }
+    RecordTensor ln() const { return unary(EML_OP_LN, 0); }
+    RecordTensor sin() const { return unary(EML_OP_SIN, 0); }
+    RecordTensor cos() const { return unary(EML_OP_COS, 0); }
+    RecordTensor sqrt() const { return unary(EML_OP_SQRT, 0); }
+    RecordTensor pow(T c) const { return unary(EML_OP_POW_C, c); }
+    RecordTensor operator+(T c) const { return unary(EML_OP_ADD_C, c); }
+    RecordTensor operator-(T c) const { return unary(EML_OP_SUB_C, c); }
+    RecordTensor operator*(T c) const { return unary(EML_OP_MUL_C, c); }
+    RecordTensor operator/(T c) const { return unary(EML_OP_DIV_C, c); }
+    RecordTensor sub_swapped(T c) const { return unary(EML_OP_C_SUB, c); }
+    RecordTensor div_swapped(T c) const { return unary(EML_OP_C_DIV, c); }
+    // binary container operators, container_record/mod.rs:962-1043, :1224, :1247
+    RecordTensor operator+(const RecordTensor& o) const { return binary(EML_OP_ADD, o); }
+    RecordTensor operator-(const RecordTensor& o) const { return binary(EML_OP_SUB, o); }
+    RecordTensor elementwise_multiply(const RecordTensor& o) const { return binary(EML_OP_MUL, o); }
+    RecordTensor elementwise_divide(const RecordTensor& o) const { return binary(EML_OP_DIV, o); }
+
+    // derivatives_for, mod.rs:1201-1213 -> Record::try_derivatives, differentiation.rs:623-648
+    Derivatives<T> derivatives_for(int64_t row, int64_t col) const {
+        if (!tracked_) throw Panic("Record has no WengertList to find derivatives from");
+        eml_derivs* d = nullptr;
+        detail::check(eml_tape_derivatives(list_->raw(), v_, row, col, &d));
+        return Derivatives<T>(d);
+    }
+
+  private:
+    RecordTensor(const WengertList<T>* l, eml_val v, Shape s, bool tracked)
+        : list_(l), v_(v), shape_(std::move(s)), tracked_(tracked) {}
+    static void require_rank2(const Tensor<T>& x) {
+        if (x.rank() != 2) throw std::invalid_argument("the device tape holds rank 2 containers");
+    }
+    RecordTensor unary(int op, double c) const {
+        eml_val y;
+        detail::check(eml_tape_unary(list_->raw(), op, c, v_, &y));
+        return RecordTensor(list_, y, shape_, tracked_);
+    }
+    RecordTensor binary(int op, const RecordTensor& o) const {
+        if (shape_ != o.shape_)  // mod.rs:973-980
+            throw Panic("Record containers must have the same shape for a binary operation: (left: " +
+                        detail::shape_debug(shape_) + ", right: " + detail::shape_debug(o.shape_) + ")");
+        eml_val z;
+        detail::check(eml_tape_binary(list_->raw(), op, v_, o.v_, &z));
+        return RecordTensor(list_, z, shape_, tracked_ || o.tracked_);
+    }
+    const WengertList<T>* list_;
+    eml_val v_;
+    Shape shape_;
+    bool tracked_;
+    friend class Derivatives<T>;
+};
+
+template <class T>
+Tensor<T> Derivatives<T>::at_tensor(const RecordTensor<T>& input) const {
+    std::vector<T> out((size_t)(input.shape()[0].second * input.shape()[1].second));
+    detail::check(eml_derivs_at_val(d_.get(), input.raw(), out.data()));
+    return Tensor<T>(input.shape(), std::move(out));
+}
+
+// `w.map_mut(|x| x - derivatives[&x] * lr)`, src/neural_networks.rs:418-420, fused on the device
+template <class T>
+void sgd_update(RecordTensor<T>& w, const Derivatives<T>& d, T lr) {
+    detail::check(eml_tape_sgd_update(w.list()->raw(), w.raw(), d.raw(), (double)lr));
+}
+
+}  // namespace easyml

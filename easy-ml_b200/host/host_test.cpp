@@ -1,0 +1,177 @@
+// host_test.cpp -- the reference's own known-answer tests for the hot path, replayed through the C++ mirror
+// (easyml.hpp) and the C ABI.  Exit code 0 = all passed.  Without a GPU it checks that the product path fails
+// loudly (BackendError: no CUDA device), i.e. that there is no CPU fallback, and exits 3.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+
+#include "easyml.hpp"
+
+using namespace easyml;
+
+static int failures = 0;
+#define EXPECT(cond)                                                            \
+    do {                                                                        \
+        if (!(cond)) {                                                          \
+            std::fprintf(stderr, "FAIL %s:%d  %s\n", __FILE__, __LINE__, #cond); \
+            failures++;                                                         \
+        }                                                                       \
+    } while (0)
+
+template <class F>
+static std::string panic_text(F&& f) {
+    try {
+        f();
+    } catch (const Panic& p) {
+        return p.what();
+    }
+    return "<no panic>";
+}
+
+template <class T>
+static void matrix_goldens() {
+    // tests/matrices.rs:161-166
+    Matrix<T> a(3, 2, {1, 2, 3, 4, 5, 6}), b(2, 3, {1, 2, 3, 4, 5, 6});
+    EXPECT((a * b) == Matrix<T>(3, 3, {9, 12, 15, 19, 26, 33, 29, 40, 51}));
+    // tests/matrices.rs:168-173 (#[should_panic]); message src/matrices/operations.rs:176-183
+    EXPECT(panic_text([&] { (void)(a * a); }) ==
+           "Mismatched Matrices, left is 3x2, right is 3x2, * is only defined for MxN * NxL");
+    // tests/linear_algebra.rs:183-190: L * L^T == A exactly
+    Matrix<T> l(3, 3, {5, 0, 0, 3, 3, 0, -1, 1, 3}), lt(3, 3, {5, 3, -1, 0, 3, 1, 0, 0, 3});
+    EXPECT((l * lt) == Matrix<T>(3, 3, {25, 15, -5, 15, 18, 0, -5, 0, 11}));
+}
+
+template <class T>
+static void tensor_goldens() {
+    // src/tensors/operations.rs:521-546
+    Tensor<T> a({{"r", 2}, {"c", 3}}, {1, 2, 3, 4, 5, 6}), b({{"r", 3}, {"c", 2}}, {10, 11, 12, 13, 14, 15});
+    EXPECT((a * b) == Tensor<T>({{"r", 2}, {"c", 2}}, {76, 82, 184, 199}));
+    // :1655-1708: output takes the left's first and the right's second dimension name
+    Tensor<T> c({{"a", 3}, {"b", 2}}, {1, 2, 3, 4, 5, 6});
+    EXPECT((a * c) == Tensor<T>({{"r", 2}, {"b", 2}}, {22, 28, 49, 64}));
+    // :485-491 and :14-18,492-501
+    Tensor<T> bad({{"a", 2}, {"b", 3}}, {1, 2, 3, 4, 5, 6});
+    EXPECT(panic_text([&] { (void)(a * bad); }) ==
+           "Mismatched tensors, left is [(\"r\", 2), (\"c\", 3)], right is [(\"a\", 2), (\"b\", 3)], * is only defined "
+           "for MxN * NxL dimension lengths");
+    Tensor<T> rc({{"rows", 2}, {"columns", 3}}, {1, 2, 3, 4, 5, 6}), cr({{"columns", 3}, {"rows", 2}}, {1, 2, 3, 4, 5, 6});
+    EXPECT(panic_text([&] { (void)(rc * cr); }).rfind("Matrix multiplication of tensors with shapes left "
+                                                       "[(\"rows\", 2), (\"columns\", 3)] and right [(\"columns\", 3), "
+                                                       "(\"rows\", 2)] would create duplicate dimension names", 0) == 0);
+    // Tensor<T,1>::scalar_product
+    Tensor<T> u({{"x", 3}}, {1, 2, 3}), v({{"x", 3}}, {4, 5, 6});
+    EXPECT(u.scalar_product(v) == T(32));
+}
+
+template <class T>
+static void einsum_goldens() {
+    // tests/einsum.rs:165-187 (ij,jk->ijk) and :189-206 (ij,kl->il): not GEMMs, bit-exact generic kernel
+    Tensor<T> x({{"i", 2}, {"j", 3}}, {0, 10, 20, 1, 11, 21});
+    Tensor<T> y({{"j", 3}, {"k", 4}}, {0, 10, 20, 30, 1, 11, 21, 31, 2, 12, 22, 32});
+    auto ijk = Einsum::with_2(x, y).to({"i", "j", "k"});
+    EXPECT(ijk.shape() == (Shape{{"i", 2}, {"j", 3}, {"k", 4}}));
+    EXPECT(ijk.data()[4] == T(10) && ijk.data()[5] == T(110) && ijk.data()[11] == T(640));
+    Tensor<T> y2({{"k", 3}, {"l", 4}}, y.data());
+    EXPECT(Einsum::with_2(x, y2).to({"i", "l"}) == Tensor<T>({{"i", 2}, {"l", 4}}, {90, 990, 1890, 2790, 99, 1089, 2079, 3069}));
+    // src/tensors/einsum.rs:58-72 doctest: ab,bc->ac == w * x
+    Tensor<T> w({{"a", 4}, {"b", 2}}, {0, 1, 2, 3, 4, 5, 6, 7}), z({{"b", 2}, {"c", 3}}, {0, 1, 2, 3, 4, 5});
+    EXPECT(Einsum::with_2(w, z).to({"a", "c"}) == (w * z));
+    // tests/einsum.rs:76-88: ab,cb->ac == x * y^T
+    Tensor<T> p({{"a", 2}, {"b", 3}}, {0, 10, 20, 1, 11, 21}), q({{"c", 2}, {"b", 3}}, {0, 10, 20, 1, 11, 21});
+    Tensor<T> qt({{"b", 3}, {"c", 2}}, {0, 1, 10, 11, 20, 21});
+    EXPECT(Einsum::with_2(p, q).to({"a", "c"}) == (p * qt));
+    // tests/einsum.rs:133-163: batched matmul == per-batch *
+    std::vector<T> xb(3 * 2 * 5), yb(3 * 5 * 3);
+    for (size_t i = 0; i < xb.size(); i++) xb[i] = T((int)(i % 7) - 3);
+    for (size_t i = 0; i < yb.size(); i++) yb[i] = T((int)(i % 5) - 2);
+    Tensor<T> X({{"batch", 3}, {"a", 2}, {"b", 5}}, xb), Y({{"batch", 3}, {"b", 5}, {"c", 3}}, yb);
+    auto Z = Einsum::with_2(X, Y).to({"batch", "a", "c"});
+    for (int bt = 0; bt < 3; bt++) {
+        Tensor<T> xs({{"a", 2}, {"b", 5}}, std::vector<T>(xb.begin() + bt * 10, xb.begin() + bt * 10 + 10));
+        Tensor<T> ys({{"b", 5}, {"c", 3}}, std::vector<T>(yb.begin() + bt * 15, yb.begin() + bt * 15 + 15));
+        auto zs = xs * ys;
+        EXPECT(std::equal(zs.data().begin(), zs.data().end(), Z.data().begin() + bt * 6));
+    }
+    // Err(InconsistentDimensionLengthError)
+    bool threw = false;
+    try {
+        (void)Einsum::with_2(x, y).to({"i", "nope"});
+    } catch (const InconsistentDimensionLengthError& e) {
+        threw = e.dimension == "nope" && !e.lengths[0] && !e.lengths[1];
+    }
+    EXPECT(threw);
+}
+
+template <class T>
+static void record_goldens() {
+    // src/differentiation/container_record/mod.rs:2718-2811: 4x3 * 3x4, numbers, every derivative, tape length
+    WengertList<T> list;
+    std::vector<T> av{1, 2, 3, 4, 5, 6, 7, 8, 9, 0, 5, 2}, bv{1, 4, 7, 0, 2, 5, 8, 5, 3, 6, 9, 2};
+    auto A = RecordTensor<T>::variables(list, Tensor<T>({{"r", 4}, {"c", 3}}, av));
+    auto B = RecordTensor<T>::variables(list, Tensor<T>({{"x", 3}, {"y", 4}}, bv));
+    EXPECT(list.len() == 24);
+    EXPECT(A.indexes().front() == 0 && A.indexes().back() == 11 && B.indexes().front() == 12);
+    auto Cm = A * B;
+    EXPECT(Cm.shape() == (Shape{{"r", 4}, {"y", 4}}));
+    EXPECT(Cm.numbers().data() == (std::vector<T>{14, 32, 50, 16, 32, 77, 122, 37, 50, 122, 194, 58, 16, 37, 58, 29}));
+    // tape length of the scalar path: 16 outputs x (3 multiplies + 2 adds)   (mod.rs:2805-2810)
+    EXPECT(list.len() == 24 + 16 * 5);
+    // Index of C[i,j] = base + (i*N+j)*(2K-1) + 2K-2   (the last add of its chain)
+    auto ci = Cm.indexes();
+    EXPECT(ci[0] == 24 + 4 && ci[5] == 24 + 5 * 5 + 4 && ci[15] == 24 + 15 * 5 + 4);
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++) {
+            auto d = Cm.derivatives_for(i, j);
+            auto dA = d.at_tensor(A), dB = d.at_tensor(B);
+            for (int r = 0; r < 4; r++)
+                for (int k = 0; k < 3; k++) EXPECT(dA.data()[r * 3 + k] == (r == i ? bv[k * 4 + j] : T(0)));
+            for (int k = 0; k < 3; k++)
+                for (int c = 0; c < 4; c++) EXPECT(dB.data()[k * 4 + c] == (c == j ? av[i * 3 + k] : T(0)));
+            EXPECT(d.at(ci[i * 4 + j]) == T(1) && d.len() == list.len());
+        }
+    // container ops around the matmul (functions.rs rules): d/dx of sum-free chain y = exp(-x) at one element
+    auto E = (-A).exp();
+    auto de = E.derivatives_for(1, 2).at_tensor(A);
+    EXPECT(std::fabs(de.data()[5] + std::exp(-T(6))) < T(1e-6) && de.data()[4] == T(0));
+    EXPECT(panic_text([&] { (void)(A + B); }).rfind("Record containers must have the same shape", 0) == 0);
+    // constants carry no history
+    auto K = RecordTensor<T>::constants(Tensor<T>({{"x", 3}, {"y", 4}}, bv), list);
+    EXPECT(!K.has_history());
+    EXPECT(panic_text([&] { (void)K.derivatives_for(0, 0); }) == "Record has no WengertList to find derivatives from");
+    list.clear();
+    EXPECT(list.len() == 0);
+    A.reset();
+    EXPECT(list.len() == 12 && A.indexes().front() == 0);
+}
+
+int main() {
+    int n = 0;
+    if (eml_init(&n) != EML_OK) {
+        // no device: the product path must refuse to run (no CPU fallback), with the library's message
+        bool loud = false;
+        try {
+            Matrix<double> a(1, 1, {1.0});
+            (void)(a * a);
+        } catch (const BackendError& e) {
+            loud = e.code == EML_ERR_NO_DEVICE;
+            std::printf("no CUDA device: product path failed loudly as required: %s\n", e.what());
+        }
+        return loud ? 3 : 1;
+    }
+    matrix_goldens<float>();
+    matrix_goldens<double>();
+    tensor_goldens<float>();
+    tensor_goldens<double>();
+    einsum_goldens<float>();
+    einsum_goldens<double>();
+    record_goldens<float>();
+    record_goldens<double>();
+    if (failures) {
+        std::fprintf(stderr, "%d check(s) failed\n", failures);
+        return 1;
+    }
+    std::printf("host_test: all reference known-answer tests passed through the C++ mirror (%lld kernel launches)\n",
+                (long long)eml_kernel_launches());
+    return 0;
+}
