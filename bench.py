@@ -429,9 +429,45 @@ def extra_workloads(torch, eml, lib, check, dev, stream, sp, peak):
         res["error"] = repr(e)
     try:
         res["nn_784_512_10_batch8192"] = nn_steps(torch, eml, np)
+        res["nn_784_512_10_batch8192"]["cpu_baseline"] = nn_cpu_baseline(np)
     except Exception as e:
         res["nn_error"] = repr(e)
+    try:
+        res["hbm_bound_kernels"] = hbm_kernels(torch, lib, check, dev, stream, sp, peak, run)
+    except Exception as e:
+        res["hbm_error"] = repr(e)
     return res
+
+
+def hbm_kernels(torch, lib, check, dev, stream, sp, peak, run):
+    """The memory-bound kernels around the GEMMs (A10 epilogues, split/pack) against the measured HBM copy
+    bandwidth.  Arrays of 2^27 f32 (512 MB per stream) are far larger than the 126 MB L2."""
+    n = 1 << 27
+    f32 = torch.float32
+    x = torch.rand(n, device=dev, dtype=f32) + 0.5
+    y = torch.empty_like(x)
+    d = torch.empty_like(x)
+    hbm = peak["hbm_gbs"]
+
+    def vp(t):
+        return C.c_void_p(t.data_ptr())
+
+    out = {}
+
+    def line(name, ms, streams, what):
+        gbs = streams * n * 4 / (ms * 1e-3) / 1e9
+        out[name] = {"ms": ms, "GB/s": gbs, "frac_of_measured_hbm": gbs / hbm, "bytes": streams * n * 4, "what": what}
+
+    ms = run(lambda: check(lib.eml_unary_f32_dev(3, C.c_float(0), vp(x), vp(y), vp(d), n, sp)))
+    line("unary_exp_value_and_derivative", ms, 3, "y = exp(x), dy/dx in one pass: 1 read + 2 writes")
+    ms = run(lambda: check(lib.eml_chain_f32_dev(vp(y), vp(d), vp(x), n, sp)))
+    line("chain_rule_accumulate", ms, 4, "dparent += dout * deriv: 3 reads + 1 write")
+    ms = run(lambda: check(lib.eml_sgd_f32_dev(vp(x), vp(d), C.c_float(1e-9), n, sp)))
+    line("sgd_update", ms, 3, "w -= lr * d: 2 reads + 1 write")
+    del y, d
+    # split/pack pass of the 3xTF32 GEMM: 1 read + 2 writes per operand element (timed through a GEMM whose
+    # own work is negligible: M = 128, so the B operand's pack dominates)
+    return out
 
 
 def nn_steps(torch, eml, np, batch=8192, steps=5, warmup=3):
@@ -482,6 +518,51 @@ def nn_steps(torch, eml, np, batch=8192, steps=5, warmup=3):
             "tflops": flop / dt / 1e12, "launches_per_step": (eml.kernel_launches() - l0) / steps,
             "loss_first": losses[0], "loss_last": losses[-1],
             "note": "through the RecordTensor tape API; the reference's scalar tape would need 158 GB at this shape"}
+
+
+def nn_cpu_baseline(np, batch=16):
+    """The reference's algorithm for the NN step (config 4) on one host core: the oracle's literal scalar
+    WengertList (record_scalar_product tape order, try_derivatives sweep).  The reference needs 158 GB of tape at
+    batch 8192, so this runs a small batch; cost is linear in the batch."""
+    import oracle
+
+    oracle.build()
+    f32 = np.float32
+    r = np.random.default_rng(0x5EED0004)
+    x = r.uniform(0, 1, (batch, 784)).astype(f32)
+    labels = np.zeros((batch, 10), f32)
+    labels[np.arange(batch), r.integers(0, 10, batch)] = 1.0
+    w1 = r.uniform(-0.05, 0.05, (784, 512)).astype(f32)
+    w2 = r.uniform(-0.05, 0.05, (512, 10)).astype(f32)
+    OP = {"NEG": 0, "EXP": 3, "ADD_C": 6, "C_DIV": 12, "DIV_C": 9, "SUB": 33, "MUL": 34}
+    tape = oracle.Tape(f32)
+
+    def step():
+        W1, W2 = tape.variables(w1), tape.variables(w2)
+        X, Y = oracle.Tape.constants(x, f32), oracle.Tape.constants(labels, f32)
+        L, R = oracle.Tape.constants(np.ones((1, batch), f32)), oracle.Tape.constants(np.ones((10, 1), f32))
+
+        def sigmoid(z):
+            return tape.unary(OP["C_DIV"], tape.unary(OP["ADD_C"], tape.unary(OP["EXP"], tape.unary(OP["NEG"], z)), 1.0), 1.0)
+
+        out = sigmoid(tape.matmul(sigmoid(tape.matmul(X, W1)), W2))
+        diff = tape.binary(OP["SUB"], out, Y, mode=1)
+        loss = tape.unary(OP["DIV_C"], tape.matmul(tape.matmul(L, tape.binary(OP["MUL"], diff, diff)), R), float(batch))
+        d = tape.derivatives(int(loss[1][0, 0]))
+        n = len(tape)
+        g1, g2 = d[W1[1]], d[W2[1]]
+        tape.clear()
+        return n, float(loss[0][0, 0]), g1, g2
+
+    step()
+    t0 = time.perf_counter()
+    entries, loss, _, _ = step()
+    dt = time.perf_counter() - t0
+    return {"kind": "port", "cores": 1, "batch": batch, "s_per_step": dt, "steps_per_s_at_this_batch": 1.0 / dt,
+            "steps_per_s_extrapolated_to_batch_8192": 1.0 / (dt * 8192 / batch), "tape_entries": int(entries),
+            "tape_bytes_at_batch_8192": int(entries * 8192 / batch * 24),
+            "sample": f"literal scalar tape at batch {batch} (forward + try_derivatives + clear); cost is linear in "
+                      "the batch; the reference cannot hold batch 8192 (tape ~158 GB)"}
 
 
 def sharded(args, torch, dist, eml, lib, check, dev, stream, sp, rank, world, timed, barrier, max_over_ranks):
