@@ -238,6 +238,240 @@ tf32x3_kernel(const __grid_constant__ Maps maps, float* __restrict__ C, int64_t 
     if (warp == 1) tmem_dealloc(tmem_acc, cfg::TMEM_COLS);
 }
 
+
+// =================================================================================================
+// CTA-pair, persistent variant (the fast path for M > 128 and N > 128).
+//
+// The single-CTA kernel above is shared-memory-bandwidth bound: each 128x256x8 MMA reads 12 KB of operands
+// from shared memory in 128 cycles (96 B/clk) while TMA writes the next stage (62 B/clk) -- more than the
+// 128 B/clk an SM has, which caps the tensor pipe near 80 % (ncu: 79 %).  Here two CTAs of a cluster form a
+// pair (tcgen05 cta_group::2) and compute a 256 x 256 tile together: each CTA stages only ITS 128 rows of A
+// and ITS 128-column half of B (64 KB per k block instead of 96 KB), the pair's tensor cores read both halves
+// of B across the pair, so per SM the MMA reads 8 KB per 128 cycles and the ring holds 3 stages.
+//
+// Persistent: one cluster per SM pair walks a static list of work items (tile x split), the f32 accumulator
+// is double buffered in TMEM (2 x 256 columns), so the epilogue of item i overlaps the MMAs of item i+1.
+//   warp 0 (both CTAs)   TMA producer: own halves into own shared memory, completion on the LEADER's barrier
+//   warp 1 (leader CTA)  MMA issuer: tcgen05.mma.cta_group::2 (M=256, N=256, K=8), commits multicast to both CTAs
+//   warp 1 (both)        TMEM allocation / release (cta_group::2)
+//   warps 2..5 (both)    epilogue: tcgen05.ld -> registers -> global; release the accumulator stage to the leader
+// =================================================================================================
+namespace pair {
+
+constexpr int PM = 256, PN = 256;           // tile of one CTA pair
+constexpr int HALF = 128;                   // rows of A / columns of B staged by one CTA
+constexpr int TILE_BYTES = HALF * BK * 4;   // 16 KB
+constexpr int STAGE_BYTES = 4 * TILE_BYTES; // A big, A small, B big, B small: 64 KB
+constexpr int STAGES = 3;
+constexpr int ACC_STAGES = 2;
+constexpr uint32_t TMEM_COLS = 512;         // 2 accumulator stages x 256 columns
+constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int EPI_WARPS = 4;
+
+struct Work {
+    int tm, tn, batch, split;
+};
+
+__device__ __forceinline__ Work decode(int w, int tiles_m, int tiles_n, int splits) {
+    Work k;
+    k.split = w % splits;
+    int t = w / splits;
+    const int tiles = tiles_m * tiles_n;
+    k.batch = t / tiles;
+    t %= tiles;
+    // groups of 8 pair rows (2048 rows of C) walked column by column
+    constexpr int GROUP = 8;
+    const int per_group = GROUP * tiles_n;
+    const int first_m = (t / per_group) * GROUP;
+    const int rows = tiles_m - first_m < GROUP ? tiles_m - first_m : GROUP;
+    const int in_group = t % per_group;
+    k.tm = first_m + in_group % rows;
+    k.tn = in_group / rows;
+    return k;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+tf32x3_pair_kernel(const __grid_constant__ Maps maps, float* __restrict__ C, int64_t M, int64_t N, int64_t ldc,
+                   int64_t strideC, int kblocks_total, int kblocks_per_split, int splits, int tiles_m, int tiles_n,
+                   int work_items, int accumulate, float* __restrict__ ws, int64_t ws_split_stride) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* full = reinterpret_cast<uint64_t*>(base + (size_t)STAGES * STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* acc_full = empty + STAGES;
+    uint64_t* acc_empty = acc_full + ACC_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + ACC_STAGES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();  // 0 = leader
+    const int cluster = blockIdx.x >> 1, clusters = gridDim.x >> 1;
+
+    if (threadIdx.x == 0) {
+        prefetch_tensormap(&maps.a_big);
+        prefetch_tensormap(&maps.a_small);
+        prefetch_tensormap(&maps.b_big);
+        prefetch_tensormap(&maps.b_small);
+        for (int s = 0; s < STAGES; s++) {
+            mbar_init(&full[s], 1);   // leader's copy is the one in use: its producer arrives, both CTAs' bytes land
+            mbar_init(&empty[s], 1);  // one multicast commit per use
+        }
+        for (int a = 0; a < ACC_STAGES; a++) {
+            mbar_init(&acc_full[a], 1);               // one multicast commit per work item
+            mbar_init(&acc_empty[a], 2 * EPI_WARPS);  // leader's copy: every epilogue warp of both CTAs
+        }
+        fence_barrier_init();
+    }
+    __syncwarp();
+    if (warp == 1) tmem_alloc_pair(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    cluster_sync_all();  // barriers of BOTH CTAs are initialised before any remote arrive / multicast commit
+    tc_fence_after();
+    const uint32_t tmem_acc = *tmem_slot;
+
+    if (warp == 0) {
+        // ---------------- TMA producer (both CTAs) ----------------
+        if (lane == 0) {
+            int n = 0;
+            for (int w = cluster; w < work_items; w += clusters) {
+                const Work wk = decode(w, tiles_m, tiles_n, splits);
+                const int kb0 = wk.split * kblocks_per_split;
+                const int kb1 = min(kblocks_total, kb0 + kblocks_per_split);
+                const int row_a = wk.tm * PM + (int)rank * HALF, row_b = wk.tn * PN + (int)rank * HALF;
+                for (int kb = kb0; kb < kb1; kb++, n++) {
+                    const int s = n % STAGES;
+                    if (n >= STAGES) mbar_wait(&empty[s], ((n / STAGES) - 1) & 1);
+                    uint8_t* st = base + (size_t)s * STAGE_BYTES;
+                    if (rank == 0) mbar_expect_tx(&full[s], 2 * STAGE_BYTES);
+                    const int kc = kb * BK;
+                    tma_load_3d_pair(st, &maps.a_big, &full[s], kc, row_a, wk.batch);
+                    tma_load_3d_pair(st + TILE_BYTES, &maps.a_small, &full[s], kc, row_a, wk.batch);
+                    tma_load_3d_pair(st + 2 * TILE_BYTES, &maps.b_big, &full[s], kc, row_b, wk.batch);
+                    tma_load_3d_pair(st + 3 * TILE_BYTES, &maps.b_small, &full[s], kc, row_b, wk.batch);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------- MMA issuer (leader CTA only) ----------------
+        if (rank == 0 && lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_tf32(PM, PN);
+            int n = 0, it = 0;
+            for (int w = cluster; w < work_items; w += clusters, it++) {
+                const Work wk = decode(w, tiles_m, tiles_n, splits);
+                const int kb0 = wk.split * kblocks_per_split;
+                const int kb1 = min(kblocks_total, kb0 + kblocks_per_split);
+                const int as = it & 1;
+                if (it >= ACC_STAGES) mbar_wait(&acc_empty[as], ((it >> 1) - 1) & 1);  // epilogue drained this stage
+                tc_fence_after();
+                const uint32_t d = tmem_acc + (uint32_t)as * PN;
+                for (int kb = kb0; kb < kb1; kb++, n++) {
+                    const int s = n % STAGES;
+                    mbar_wait(&full[s], (n / STAGES) & 1);
+                    tc_fence_after();
+                    const uint32_t st = smem_u32(base + (size_t)s * STAGE_BYTES);
+                    const uint64_t a_big = umma_desc_k_sw128(st), a_small = umma_desc_k_sw128(st + TILE_BYTES);
+                    const uint64_t b_big = umma_desc_k_sw128(st + 2 * TILE_BYTES);
+                    const uint64_t b_small = umma_desc_k_sw128(st + 3 * TILE_BYTES);
+                    const uint32_t first = kb != kb0;
+#pragma unroll
+                    for (int k = 0; k < BK / 8; k++) umma_tf32_pair(d, a_small + 2 * k, b_big + 2 * k, idesc, first | (uint32_t)k);
+#pragma unroll
+                    for (int k = 0; k < BK / 8; k++) umma_tf32_pair(d, a_big + 2 * k, b_small + 2 * k, idesc, 1);
+#pragma unroll
+                    for (int k = 0; k < BK / 8; k++) umma_tf32_pair(d, a_big + 2 * k, b_big + 2 * k, idesc, 1);
+                    umma_commit_pair(&empty[s], 0b11);  // frees the stage in both CTAs
+                }
+                umma_commit_pair(&acc_full[as], 0b11);  // the accumulator is complete: wake both epilogues
+            }
+        }
+    } else {
+        // ---------------- epilogue (both CTAs) ----------------
+        const int q = warp & 3;
+        int it = 0;
+        for (int w = cluster; w < work_items; w += clusters, it++) {
+            const Work wk = decode(w, tiles_m, tiles_n, splits);
+            const int as = it & 1;
+            mbar_wait(&acc_full[as], (it >> 1) & 1);
+            tc_fence_after();
+            const int64_t row = (int64_t)wk.tm * PM + (int64_t)rank * HALF + q * 32 + lane;
+            const int64_t n0 = (int64_t)wk.tn * PN;
+            float* out;
+            int64_t ld;
+            if (ws) {
+                out = ws + (int64_t)wk.split * ws_split_stride + (int64_t)wk.batch * M * N;
+                ld = N;
+            } else {
+                out = C + (int64_t)wk.batch * strideC;
+                ld = ldc;
+            }
+            const bool add = accumulate && !ws;
+            const bool vec_ok = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+#pragma unroll 1
+            for (int c = 0; c < PN / 32; c++) {
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * PN + c * 32), v);
+                tmem_ld_wait();
+                if (c == PN / 32 - 1) {  // everything is in registers: hand the accumulator stage back
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(&acc_empty[as], 0);
+                }
+                const int64_t col0 = n0 + c * 32;
+                if (row < M && col0 < N) {
+                    float* p = out + row * ld + col0;
+                    if (vec_ok && col0 + 32 <= N) {
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                   __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                            if (add) {
+                                float4 old = *reinterpret_cast<const float4*>(p + 4 * j);
+                                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                            }
+                            *reinterpret_cast<float4*>(p + 4 * j) = o;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; j++)
+                            if (col0 + j < N) p[j] = add ? p[j] + __uint_as_float(v[j]) : __uint_as_float(v[j]);
+                    }
+                }
+            }
+        }
+    }
+
+    __syncwarp();  // the elected lanes rejoin their warps: the cluster barrier below is warp-aligned
+    tc_fence_before();
+    cluster_sync_all();  // no CTA frees TMEM or exits while its peer may still address it
+    if (warp == 1) tmem_dealloc_pair(tmem_acc, TMEM_COLS);
+}
+
+int launch(const Maps& maps, float* C, int64_t batch, int64_t M, int64_t N, int64_t ldc, int64_t strideC, int kblocks,
+           int splits, int sms, bool accumulate, float* ws, cudaStream_t stream) {
+    static thread_local int configured_dev = -1;
+    int dev = 0;
+    EML_CUDA(cudaGetDevice(&dev));
+    if (configured_dev != dev) {
+        EML_CUDA(cudaFuncSetAttribute(tf32x3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        configured_dev = dev;
+    }
+    const int tiles_m = (int)((M + PM - 1) / PM), tiles_n = (int)((N + PN - 1) / PN);
+    const int per_split = (kblocks + splits - 1) / splits;
+    const int used_splits = (kblocks + per_split - 1) / per_split;
+    const int64_t items = (int64_t)batch * tiles_m * tiles_n * used_splits;
+    if (items > 0x7fffffffLL) EML_BAD_ARG("tf32x3: too many work items");
+    int clusters = sms / 2;
+    if (items < clusters) clusters = (int)items;
+    tf32x3_pair_kernel<<<2 * clusters, GEMM_THREADS, SMEM_BYTES, stream>>>(
+        maps, C, M, N, ldc, strideC, kblocks, per_split, used_splits, tiles_m, tiles_n, (int)items, accumulate ? 1 : 0, ws,
+        batch * M * N);
+    count_launch();
+    EML_TRY(check_launch("tf32x3_tcgen05 (CTA pair)"));
+    if (ws) EML_TRY(launch_splitk_reduce<float>(ws, used_splits, C, batch, M, N, Strides3{strideC, ldc, 1}, accumulate, stream));
+    return EML_OK;
+}
+
+}  // namespace pair
+
 int plane_map(CUtensorMap* map, const float* base, int64_t MNp, int64_t Kp, int64_t batch, int box_rows) {
     uint64_t dims[3] = {(uint64_t)Kp, (uint64_t)MNp, (uint64_t)batch};
     uint64_t strides[2] = {(uint64_t)Kp * 4, (uint64_t)MNp * (uint64_t)Kp * 4};
@@ -290,18 +524,35 @@ int launch_gemm_tf32x3_f32(DeviceCtx* ctx, const float* A, const float* B, float
     const int64_t Kp = round_up(K, BK);
     const int kblocks = (int)(Kp / BK);
     const int64_t tiles_m = (M + BM - 1) / BM;
-    // tile width: 256 when that still fills the machine, else 128
-    const int64_t tiles256 = tiles_m * ((N + 255) / 256) * batch;
-    const int BN = (N > 128 && tiles256 * 10 >= (int64_t)sms * 8) ? 256 : 128;
-    const int64_t tiles = tiles_m * ((N + BN - 1) / BN) * batch;
-    // deterministic split-K when the output has too few tiles for 148 SMs (e.g. dW = X^T dH, K = batch size)
-    int splits = 1;
-    if (tiles * 2 <= sms && kblocks >= 8) {
-        splits = (int)((sms + tiles - 1) / tiles);
-        if (splits > kblocks / 4) splits = kblocks / 4;
-        if (splits < 1) splits = 1;
+    // CTA-pair persistent kernel for outputs wider and taller than one 128-row tile
+    const bool use_pair = M > 128 && N > 128 && !(forced && std::string(forced) == "1cta");
+    int BN, splits = 1;
+    int64_t Mp, Np;
+    if (use_pair) {
+        BN = pair::PN;
+        Mp = round_up(M, pair::PM);
+        Np = round_up(N, pair::PN);
+        const int64_t tiles = (Mp / pair::PM) * (Np / pair::PN) * batch;
+        const int clusters = sms / 2;
+        if (tiles * 2 <= clusters && kblocks >= 8) {  // too few tiles for 74 SM pairs: deterministic split-K
+            splits = (int)(clusters / tiles);
+            if (splits > kblocks / 4) splits = kblocks / 4;
+            if (splits < 1) splits = 1;
+        }
+    } else {
+        // tile width: 256 when that still fills the machine, else 128
+        const int64_t tiles256 = tiles_m * ((N + 255) / 256) * batch;
+        BN = (N > 128 && tiles256 * 10 >= (int64_t)sms * 8) ? 256 : 128;
+        const int64_t tiles = tiles_m * ((N + BN - 1) / BN) * batch;
+        // deterministic split-K when the output has too few tiles for 148 SMs (e.g. dW = X^T dH, K = batch size)
+        if (tiles * 2 <= sms && kblocks >= 8) {
+            splits = (int)((sms + tiles - 1) / tiles);
+            if (splits > kblocks / 4) splits = kblocks / 4;
+            if (splits < 1) splits = 1;
+        }
+        Mp = round_up(M, BM);
+        Np = round_up(N, BN);
     }
-    const int64_t Mp = round_up(M, BM), Np = round_up(N, BN);
 
     TempBuf packed, wsbuf;
     const int64_t a_plane = batch * Mp * Kp, b_plane = batch * Np * Kp;
@@ -333,11 +584,14 @@ int launch_gemm_tf32x3_f32(DeviceCtx* ctx, const float* A, const float* B, float
     }
 
     Maps maps;
+    const int b_box = use_pair ? pair::HALF : BN;  // rows of B one TMA box brings in
     EML_TRY(plane_map(&maps.a_big, a_big, Mp, Kp, batch, BM));
     EML_TRY(plane_map(&maps.a_small, a_small, Mp, Kp, batch, BM));
-    EML_TRY(plane_map(&maps.b_big, b_big, Np, Kp, batch, BN));
-    EML_TRY(plane_map(&maps.b_small, b_small, Np, Kp, batch, BN));
+    EML_TRY(plane_map(&maps.b_big, b_big, Np, Kp, batch, b_box));
+    EML_TRY(plane_map(&maps.b_small, b_small, Np, Kp, batch, b_box));
     set_last_kernel("tf32x3_tcgen05");
+    if (use_pair)
+        return pair::launch(maps, C, batch, M, N, sC.r, sC.b, kblocks, splits, sms, accumulate, ws, stream);
     if (BN == 256) return launch_tile<256>(maps, C, batch, M, N, sC.r, sC.b, kblocks, splits, accumulate, ws, stream);
     return launch_tile<128>(maps, C, batch, M, N, sC.r, sC.b, kblocks, splits, accumulate, ws, stream);
 }

@@ -171,10 +171,16 @@ def test_dgemm_tma_all_layouts_ragged(orc, monkeypatch, a_kin, b_kin, batch, m, 
 @pytest.mark.parametrize("a_kin", [True, False])
 @pytest.mark.parametrize("b_kin", [True, False])
 @pytest.mark.parametrize("batch,m,n,k", [(1, 256, 256, 256), (1, 384, 260, 196), (3, 300, 264, 224), (1, 1000, 520, 1028)])
-def test_sgemm_tf32x3_all_layouts_ragged(orc, a_kin, b_kin, batch, m, n, k):
+@pytest.mark.parametrize("variant", ["pair", "1cta"])
+def test_sgemm_tf32x3_all_layouts_ragged(orc, monkeypatch, variant, a_kin, b_kin, batch, m, n, k):
     """The tcgen05 3xTF32 kernel: every operand orientation through the split/pack pass, ragged M/N/K
     (zero padded by the pack), batched, split-K on the small grids.  f32-level accuracy: within
-    1e-5 * sum|a_k b_k| of the oracle's sequential sum."""
+    1e-5 * sum|a_k b_k| of the oracle's sequential sum.  Both kernels: the persistent CTA-pair kernel
+    (cta_group::2, double-buffered TMEM) and the single-CTA kernel it supersedes for M, N > 128."""
+    if variant == "1cta":
+        monkeypatch.setenv("EML_SGEMM_KERNEL", "1cta")
+    else:
+        monkeypatch.delenv("EML_SGEMM_KERNEL", raising=False)
     r = rng(80 + m + n + k)
     a = uniform(r, (batch, m, k), np.float32)
     b = uniform(r, (batch, k, n), np.float32)
