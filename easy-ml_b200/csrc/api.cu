@@ -113,6 +113,8 @@ int contract_dev(DeviceCtx* ctx, const T* A, const T* B, T* C, int64_t batch, in
             if (handled) return EML_OK;
         }
     }
+    if (!exact && N <= 16 && sA.c == 1 && M >= 256 && K >= 64)
+        return launch_gemm_skinny<T>(A, B, C, batch, M, N, K, sA, sB, sC, accumulate, stream);
     return launch_gemm_simt<T>(A, B, C, batch, M, N, K, sA, sB, sC, accumulate, exact, stream);
 }
 

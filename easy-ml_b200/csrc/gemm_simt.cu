@@ -149,6 +149,88 @@ int launch_gemm_simt(const T* A, const T* B, T* C, int64_t batch, int64_t M, int
     return check_launch("gemm_simt");
 }
 
+// ------------------------------------------------------------------------------------------------
+// Skinny-N GEMM: C[M x N] (+)= A[M x K] * B[K x N] with N <= 16 and A contiguous along k (the NN's
+// H[8192 x 512] * W2[512 x 10]).  HBM-bound on A: every warp streams whole rows of A with coalesced loads,
+// B sits in shared memory (k chunks, [n][k] so lanes hit distinct banks), each lane keeps N partial sums
+// over its k's and a fixed shuffle tree combines the 32 lanes -- deterministic, no atomics.
+// ------------------------------------------------------------------------------------------------
+namespace {
+constexpr int SK_NMAX = 16, SK_ROWS = 4, SK_WARPS = 16, SK_THREADS = SK_WARPS * 32;
+
+template <class T>
+__global__ void __launch_bounds__(SK_THREADS)
+gemm_skinny_kernel(const T* __restrict__ A, const T* __restrict__ B, T* C, int64_t batch, int64_t M, int N, int64_t K,
+                   Strides3 sA, Strides3 sB, Strides3 sC, int accumulate) {
+    constexpr int KC = 2048 / sizeof(T);  // k chunk: 512 (f32) / 256 (f64) -> 32 KB of shared memory
+    __shared__ T sBk[SK_NMAX][KC];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t row_blocks = (M + SK_WARPS * SK_ROWS - 1) / (SK_WARPS * SK_ROWS);
+    for (int64_t blk = blockIdx.x; blk < row_blocks * batch; blk += gridDim.x) {
+        const int64_t b = blk / row_blocks;
+        const int64_t m0 = (blk % row_blocks) * (SK_WARPS * SK_ROWS) + warp * SK_ROWS;
+        const T* Ab = A + b * sA.b;
+        const T* Bb = B + b * sB.b;
+        T acc[SK_ROWS][SK_NMAX];
+#pragma unroll
+        for (int r = 0; r < SK_ROWS; r++)
+#pragma unroll
+            for (int n = 0; n < SK_NMAX; n++) acc[r][n] = T(0);
+        for (int64_t k0 = 0; k0 < K; k0 += KC) {
+            const int kc = (int)((K - k0) < KC ? (K - k0) : KC);
+            __syncthreads();  // the previous chunk has been consumed
+            for (int e = threadIdx.x; e < N * kc; e += SK_THREADS) {
+                int n = e % N, k = e / N;  // consecutive threads walk n then k: B rows are read contiguously
+                sBk[n][k] = Bb[(k0 + k) * sB.r + n * sB.c];
+            }
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < SK_ROWS; r++) {
+                const int64_t m = m0 + r;
+                if (m >= M) continue;
+                const T* a = Ab + m * sA.r + k0;
+                for (int k = lane; k < kc; k += 32) {
+                    const T av = a[k];
+#pragma unroll
+                    for (int n = 0; n < SK_NMAX; n++)
+                        if (n < N) acc[r][n] = fma(av, sBk[n][k], acc[r][n]);
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < SK_ROWS; r++) {
+            const int64_t m = m0 + r;
+#pragma unroll
+            for (int n = 0; n < SK_NMAX; n++) {
+                T v = acc[r][n];
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+                if (lane == 0 && n < N && m < M) {
+                    T* p = C + b * sC.b + m * sC.r + n * sC.c;
+                    *p = accumulate ? *p + v : v;
+                }
+            }
+        }
+    }
+}
+}  // namespace
+
+template <class T>
+int launch_gemm_skinny(const T* A, const T* B, T* C, int64_t batch, int64_t M, int64_t N, int64_t K, Strides3 sA,
+                       Strides3 sB, Strides3 sC, bool accumulate, cudaStream_t stream) {
+    int64_t blocks = ((M + SK_WARPS * SK_ROWS - 1) / (SK_WARPS * SK_ROWS)) * batch;
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    gemm_skinny_kernel<T><<<(unsigned)blocks, SK_THREADS, 0, stream>>>(A, B, C, batch, M, (int)N, K, sA, sB, sC,
+                                                                       accumulate ? 1 : 0);
+    count_launch();
+    set_last_kernel("skinny_n");
+    return check_launch("gemm_skinny");
+}
+template int launch_gemm_skinny<float>(const float*, const float*, float*, int64_t, int64_t, int64_t, int64_t, Strides3,
+                                       Strides3, Strides3, bool, cudaStream_t);
+template int launch_gemm_skinny<double>(const double*, const double*, double*, int64_t, int64_t, int64_t, int64_t,
+                                        Strides3, Strides3, Strides3, bool, cudaStream_t);
+
 namespace {
 template <class T>
 __global__ void __launch_bounds__(256)

@@ -93,6 +93,91 @@ split_pack_kernel(const float* __restrict__ src, float* __restrict__ big, float*
     }
 }
 
+
+// Vectorised split + pack: 64 (mn) x 64 (k) tiles, 128-bit global loads along the source's contiguous index
+// and 128-bit stores along k.  Requires 16-byte aligned rows in the source (the dispatcher checks and falls
+// back to split_pack_kernel otherwise).  K_FAST: the source is contiguous along k (no transpose needed, no
+// shared memory); otherwise along mn (transpose through shared memory).
+__device__ __forceinline__ float4 load4_guarded(const float* p, int64_t first, int64_t extent) {
+    // 4 consecutive elements starting at index `first` of a contiguous run of `extent` (zero past the end)
+    if (first + 3 < extent) return *reinterpret_cast<const float4*>(p);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (first < extent) v.x = p[0];
+    if (first + 1 < extent) v.y = p[1];
+    if (first + 2 < extent) v.z = p[2];
+    return v;
+}
+__device__ __forceinline__ void store_split4(float* big, float* small, float4 v) {
+    float4 hi = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+    float4 lo = make_float4(to_tf32(v.x - hi.x), to_tf32(v.y - hi.y), to_tf32(v.z - hi.z), to_tf32(v.w - hi.w));
+    *reinterpret_cast<float4*>(big) = hi;
+    *reinterpret_cast<float4*>(small) = lo;
+}
+
+template <bool K_FAST>
+__global__ void __launch_bounds__(256)
+split_pack_vec_kernel(const float* __restrict__ src, float* __restrict__ big, float* __restrict__ small, int64_t MN,
+                      int64_t K, int64_t MNp, int64_t Kp, int64_t sb, int64_t s_slow) {
+    const int tid = threadIdx.x;
+    const int64_t k0 = (int64_t)blockIdx.x * 64, mn0 = (int64_t)blockIdx.y * 64, b = blockIdx.z;
+    const float* s = src + b * sb;
+    float* ob = big + b * MNp * Kp;
+    float* os = small + b * MNp * Kp;
+    const int c4 = (tid & 15) * 4, r = tid >> 4;  // 16 float4 columns x 16 rows per pass
+    if (K_FAST) {
+        // element (mn, k) at s[mn * s_slow + k]
+#pragma unroll
+        for (int pass = 0; pass < 4; pass++) {
+            const int64_t mn = mn0 + r + 16 * pass, k = k0 + c4;
+            if (mn >= MNp || k >= Kp) continue;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (mn < MN) v = load4_guarded(s + mn * s_slow + k, k, K);
+            store_split4(ob + mn * Kp + k, os + mn * Kp + k, v);
+        }
+    } else {
+        // element (mn, k) at s[k * s_slow + mn]: read rows of k, write rows of mn
+        __shared__ float tile[64][65];
+#pragma unroll
+        for (int pass = 0; pass < 4; pass++) {
+            const int kk = r + 16 * pass;
+            const int64_t k = k0 + kk, mn = mn0 + c4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k < K) v = load4_guarded(s + k * s_slow + mn, mn, MN);
+            tile[kk][c4] = v.x;
+            tile[kk][c4 + 1] = v.y;
+            tile[kk][c4 + 2] = v.z;
+            tile[kk][c4 + 3] = v.w;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int pass = 0; pass < 4; pass++) {
+            const int m = r + 16 * pass;
+            const int64_t mn = mn0 + m, k = k0 + c4;
+            if (mn >= MNp || k >= Kp) continue;
+            float4 v = make_float4(tile[c4][m], tile[c4 + 1][m], tile[c4 + 2][m], tile[c4 + 3][m]);
+            store_split4(ob + mn * Kp + k, os + mn * Kp + k, v);
+        }
+    }
+}
+
+// one operand: vector kernel when the source allows 128-bit loads, the scalar tile kernel otherwise
+int launch_split_pack(const float* src, float* big, float* small, int64_t batch, int64_t MN, int64_t K, int64_t MNp,
+                      int64_t Kp, int64_t sb, int64_t smn, int64_t sk, cudaStream_t stream) {
+    if (MNp / 32 > 65535 || batch > 65535) EML_BAD_ARG("tf32x3: operand too large for the pack grid");
+    const bool al = (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (sb & 3) == 0;
+    dim3 vgrid((unsigned)((Kp + 63) / 64), (unsigned)((MNp + 63) / 64), (unsigned)batch);
+    if (al && sk == 1 && (smn & 3) == 0) {
+        split_pack_vec_kernel<true><<<vgrid, 256, 0, stream>>>(src, big, small, MN, K, MNp, Kp, sb, smn);
+    } else if (al && smn == 1 && (sk & 3) == 0) {
+        split_pack_vec_kernel<false><<<vgrid, 256, 0, stream>>>(src, big, small, MN, K, MNp, Kp, sb, sk);
+    } else {
+        dim3 grid((unsigned)(Kp / 32), (unsigned)(MNp / 32), (unsigned)batch);
+        split_pack_kernel<<<grid, 256, 0, stream>>>(src, big, small, MN, K, MNp, Kp, sb, smn, sk, sk == 1);
+    }
+    count_launch();
+    return check_launch("tf32x3 split/pack");
+}
+
 // ------------------------------------------------------------------------------------------------
 // the GEMM
 // ------------------------------------------------------------------------------------------------
@@ -567,21 +652,9 @@ int launch_gemm_tf32x3_f32(DeviceCtx* ctx, const float* A, const float* B, float
         ws = wsbuf.as<float>();
     }
 
-    {
-        dim3 grid((unsigned)(Kp / 32), (unsigned)(Mp / 32), (unsigned)batch);
-        if (grid.y > 65535) EML_BAD_ARG("tf32x3: M too large for the pack grid");
-        split_pack_kernel<<<grid, 256, 0, stream>>>(A, a_big, a_small, M, K, Mp, Kp, sA.b, sA.r, sA.c, sA.c == 1);
-        count_launch();
-        EML_TRY(check_launch("tf32x3 pack A"));
-    }
-    {
-        // B element (k, n) at B[k*sB.r + n*sB.c]: its "mn" index is n
-        dim3 grid((unsigned)(Kp / 32), (unsigned)(Np / 32), (unsigned)batch);
-        if (grid.y > 65535) EML_BAD_ARG("tf32x3: N too large for the pack grid");
-        split_pack_kernel<<<grid, 256, 0, stream>>>(B, b_big, b_small, N, K, Np, Kp, sB.b, sB.c, sB.r, sB.r == 1);
-        count_launch();
-        EML_TRY(check_launch("tf32x3 pack B"));
-    }
+    EML_TRY(launch_split_pack(A, a_big, a_small, batch, M, K, Mp, Kp, sA.b, sA.r, sA.c, stream));
+    // B element (k, n) at B[k*sB.r + n*sB.c]: its "mn" index is n
+    EML_TRY(launch_split_pack(B, b_big, b_small, batch, N, K, Np, Kp, sB.b, sB.c, sB.r, stream));
 
     Maps maps;
     const int b_box = use_pair ? pair::HALF : BN;  // rows of B one TMA box brings in

@@ -271,6 +271,20 @@ def test_host_gemm_pipelined_copies(orc, dtype):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("m,n,k", [(8192, 10, 512), (300, 1, 64), (1000, 16, 777), (257, 7, 1500)])
+def test_skinny_n_streaming_kernel(orc, dtype, m, n, k):
+    """N <= 16 with A contiguous along k (the NN's H * W2): the HBM-bound streaming kernel."""
+    r = rng(700 + m + n + k)
+    a, b = uniform(r, (m, k), dtype), uniform(r, (k, n), dtype)
+    got = gemm(a, b)
+    assert eml.last_kernel() == "skinny_n"
+    assert_within(got, a, b, orc.matrix_mul(a, b, threads=4), dtype, f"skinny {m}x{n}x{k}")
+    assert np.array_equal(got, gemm(a, b))
+    ai, bi = ints(r, (m, k), dtype), ints(r, (k, n), dtype)
+    assert np.array_equal(gemm(ai, bi), orc.matrix_mul(ai, bi, threads=4))
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 def test_gemm_leading_dimensions(orc, dtype):
     r = rng(3)
     big_a, big_b = uniform(r, (150, 200), dtype), uniform(r, (200, 180), dtype)
