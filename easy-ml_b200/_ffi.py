@@ -63,6 +63,7 @@ SIGNATURES = {
     "eml_ipc_open": (cint, [vp, C.POINTER(vp)]),
     "eml_ipc_close": (cint, [vp]),
     "eml_copy_async": (cint, [vp, vp, C.c_size_t, vp]),
+    "eml_measure_fp64_tensor_peak": (cint, [C.POINTER(C.c_double)]),
     "eml_host_alloc": (cint, [C.POINTER(vp), C.c_size_t]),
     "eml_host_free": (cint, [vp]),
     "eml_tape_create": (cint, [cint, C.POINTER(vp)]),

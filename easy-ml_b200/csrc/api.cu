@@ -479,6 +479,12 @@ int eml_copy_async(void* dst, const void* src, size_t bytes, void* stream) {
     EML_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
     return EML_OK;
 }
+int eml_measure_fp64_tensor_peak(double* tflops) {
+    DeviceCtx* ctx = nullptr;
+    EML_TRY(get_ctx(&ctx));
+    if (!tflops) EML_BAD_ARG("null out pointer");
+    return measure_dmma_peak(ctx, tflops);
+}
 int eml_host_alloc(void** hptr, size_t bytes) {
     DeviceCtx* ctx = nullptr;
     EML_TRY(get_ctx(&ctx));

@@ -103,6 +103,9 @@ int launch_gemm_dmma_f64(DeviceCtx* ctx, const double* A, const double* B, doubl
                          int64_t N, int64_t K, Strides3 sA, Strides3 sB, Strides3 sC, bool accumulate,
                          cudaStream_t stream, bool* handled);
 
+// measured FP64 tensor-pipe (DMMA) peak of the current device, TFLOP/s (register-resident chains)
+int measure_dmma_peak(DeviceCtx* ctx, double* tflops);
+
 // Fused all-gather: register up to 7 peer-mapped copies of C for the NEXT f64 GEMM launch on this thread; the
 // TMA DMMA kernel stores every finished tile to them too.  remote_c_pending() stays true when the dispatch
 // took a kernel without that epilogue (the caller then copies the rows itself).

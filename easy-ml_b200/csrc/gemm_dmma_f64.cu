@@ -463,6 +463,50 @@ int launch(const double* A, const double* B, double* C, int64_t batch, int64_t M
 
 }  // namespace
 
+// ------------------------------------------------------------------------------------------------
+// FP64 tensor-pipe peak of THIS GPU at its current clocks: register-resident DMMA chains, no memory traffic.
+// bench.py uses it as the measured roofline denominator of the f64 GEMM (MEASURED_PEAKS.json has no FP64 row).
+// ------------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256, 1) dmma_peak_kernel(double* out, int iters) {
+    double acc[32][2];
+#pragma unroll
+    for (int i = 0; i < 32; i++) acc[i][0] = acc[i][1] = 0.0;
+    double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 32; i++) dmma884(acc[i][0], acc[i][1], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 32; i++) s += acc[i][0] + acc[i][1];
+    if (s == 12345.678) out[0] = s;  // keeps the chains alive without a store in the common case
+}
+}  // namespace
+
+int measure_dmma_peak(DeviceCtx* ctx, double* tflops) {
+    const int sms = ctx ? ctx->sm_count : 148, iters = 20000;
+    double* d = nullptr;
+    EML_CUDA(cudaMalloc(&d, 8));
+    cudaEvent_t e0, e1;
+    EML_CUDA(cudaEventCreate(&e0));
+    EML_CUDA(cudaEventCreate(&e1));
+    dmma_peak_kernel<<<sms, 256>>>(d, iters / 10);  // warm-up
+    EML_CUDA(cudaEventRecord(e0));
+    dmma_peak_kernel<<<sms, 256>>>(d, iters);
+    EML_CUDA(cudaEventRecord(e1));
+    EML_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    EML_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    count_launch(2);
+    // per warp and iteration: 32 DMMA.8x8x4 of 8*8*4 multiply-adds
+    *tflops = 2.0 * 256.0 * 32.0 * 8.0 * (double)iters * sms / (ms * 1e-3) / 1e12;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    return check_launch("dmma_peak");
+}
+
 void set_remote_c(double* const* ptrs, int n) {
     tma::t_remote.n = n;
     for (int i = 0; i < n && i < 7; i++) tma::t_remote.p[i] = ptrs[i];

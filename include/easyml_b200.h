@@ -145,6 +145,9 @@ int eml_sync(void);                                                  /* current 
 /* Page-locked host memory.  The host entry points accept any host pointer; with pinned buffers the large
  * GEMMs overlap their PCIe copies with the compute (three streams), which pageable memory cannot do.  A Rust
  * shim would back `Matrix<f32|f64>` storage created under the `cuda` feature with these. */
+/* Measured FP64 tensor-pipe (DMMA) peak of the current device at its current clocks, in TFLOP/s: a
+ * register-resident DMMA loop with no memory traffic (~0.1 s).  The roofline denominator of the f64 GEMM. */
+int eml_measure_fp64_tensor_peak(double* tflops);
 int eml_host_alloc(void** hptr, size_t bytes);
 int eml_host_free(void* hptr);
 

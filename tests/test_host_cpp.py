@@ -15,7 +15,7 @@ HOST = os.path.join(ROOT, "easy-ml_b200", "host")
 
 def _build():
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "easy-ml_b200", "csrc"), "-s", "-j", "8"])
-    subprocess.check_call(["make", "-C", HOST, "-s"])
+    subprocess.check_call(["make", "-C", HOST, "-s", "all"])
     return os.path.join(HOST, "host_test")
 
 
