@@ -443,6 +443,22 @@ def extra_workloads(torch, eml, lib, check, dev, stream, sp, peak):
     except Exception as e:
         res["nn_error"] = repr(e)
     try:
+        # next row: covariance of 2048 column features over 65536 samples, f32 and f64, device-resident
+        cov = {}
+        for name, dt, fn in (("f32", torch.float32, lib.eml_covariance_f32_dev), ("f64", torch.float64, lib.eml_covariance_f64_dev)):
+            S, F = 65536, 2048
+            X = torch.rand((S, F), generator=gen, device=dev, dtype=dt)
+            out = torch.empty((F, F), device=dev, dtype=dt)
+            ms = run(lambda: check(fn(vp(X), S, F, 1, vp(out), sp)))
+            want = torch.cov(X[:, :64].double().T, correction=0)
+            err = float((out[:64, :64].double() - want).abs().max())
+            cov[name] = {"samples": S, "features": F, "ms": ms, "tflops": 2.0 * S * F * F / (ms * 1e-3) / 1e12,
+                         "max_abs_err_vs_torch_f64_on_64_features": err}
+            del X, out
+        res["covariance_65536x2048"] = cov
+    except Exception as e:
+        res["covariance_error"] = repr(e)
+    try:
         res["hbm_bound_kernels"] = hbm_kernels(torch, lib, check, dev, stream, sp, peak, run)
     except Exception as e:
         res["hbm_error"] = repr(e)

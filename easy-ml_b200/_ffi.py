@@ -63,6 +63,10 @@ SIGNATURES = {
     "eml_ipc_open": (cint, [vp, C.POINTER(vp)]),
     "eml_ipc_close": (cint, [vp]),
     "eml_copy_async": (cint, [vp, vp, C.c_size_t, vp]),
+    "eml_covariance_f32": (cint, [vp, i64, i64, i64, cint, vp]),
+    "eml_covariance_f64": (cint, [vp, i64, i64, i64, cint, vp]),
+    "eml_covariance_f32_dev": (cint, [vp, i64, i64, cint, vp, vp]),
+    "eml_covariance_f64_dev": (cint, [vp, i64, i64, cint, vp, vp]),
     "eml_measure_fp64_tensor_peak": (cint, [C.POINTER(C.c_double)]),
     "eml_host_alloc": (cint, [C.POINTER(vp), C.c_size_t]),
     "eml_host_free": (cint, [vp]),

@@ -332,6 +332,51 @@ int matmul_bwd_dev(const T* dC, const T* A, const T* B, T* dA, T* dB, int64_t M,
     return EML_OK;
 }
 
+// covariance on the device: sums -> centre -> GEMM (Xc^T Xc or Xc Xc^T via strides) -> / S
+template <class T>
+int covariance_dev(DeviceCtx* ctx, const T* X, int64_t rows, int64_t cols, int axis, T* out, cudaStream_t st) {
+    if (!X || !out) EML_BAD_ARG("covariance: null operand");
+    if (rows < 1 || cols < 1) EML_BAD_ARG("covariance: empty matrix");
+    if (axis != 0 && axis != 1) EML_BAD_ARG("covariance: feature_axis must be 0 (rows) or 1 (columns)");
+    const int64_t F = axis == 1 ? cols : rows, S = axis == 1 ? rows : cols;
+    TempBuf sums, xc;
+    EML_TRY(sums.alloc(sizeof(T) * (size_t)F, st));
+    EML_TRY(xc.alloc(sizeof(T) * (size_t)(rows * cols), st));
+    if (axis == 1)
+        EML_TRY(launch_col_sums<T>(X, rows, cols, sums.as<T>(), st));
+    else
+        EML_TRY(launch_row_sums<T>(X, rows, cols, sums.as<T>(), st));
+    EML_TRY(launch_center<T>(X, sums.as<T>(), S, rows, cols, axis, xc.as<T>(), st));
+    const T* c = xc.as<T>();
+    if (axis == 1)  // A(i, s) = Xc[s*F + i], B(s, j) = Xc[s*F + j]
+        EML_TRY(contract_dev<T>(ctx, c, c, out, 1, F, F, S, Strides3{0, 1, F}, Strides3{0, F, 1}, Strides3{0, F, 1}, false,
+                                false, st));
+    else  // A(i, s) = Xc[i*S + s], B(s, j) = Xc[j*S + s]
+        EML_TRY(contract_dev<T>(ctx, c, c, out, 1, F, F, S, Strides3{0, S, 1}, Strides3{0, 1, S}, Strides3{0, F, 1}, false,
+                                false, st));
+    return launch_unary<T>(EML_OP_DIV_C, (T)S, out, out, (T*)nullptr, F * F, st);
+}
+
+template <class T>
+int covariance_host(const T* X, int64_t rows, int64_t cols, int64_t ldx, int axis, T* out) {
+    DeviceCtx* ctx = nullptr;
+    EML_TRY(get_ctx(&ctx));
+    if (!X || !out) EML_BAD_ARG("covariance: null operand");
+    if (rows < 1 || cols < 1 || ldx < cols) EML_BAD_ARG("covariance: bad shape %lldx%lld (ld %lld)", (long long)rows,
+                                                        (long long)cols, (long long)ldx);
+    const int64_t F = axis == 1 ? cols : rows;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    void *dX, *dOut;
+    EML_TRY(stage_buffer(ctx, 0, sizeof(T) * (size_t)(rows * cols), &dX));
+    EML_TRY(stage_buffer(ctx, 2, sizeof(T) * (size_t)(F * F), &dOut));
+    cudaStream_t st = ctx->stream;
+    EML_CUDA(cudaMemcpy2DAsync(dX, cols * sizeof(T), X, ldx * sizeof(T), cols * sizeof(T), rows, cudaMemcpyHostToDevice, st));
+    EML_TRY(covariance_dev<T>(ctx, (const T*)dX, rows, cols, axis, (T*)dOut, st));
+    EML_CUDA(cudaMemcpyAsync(out, dOut, sizeof(T) * (size_t)(F * F), cudaMemcpyDeviceToHost, st));
+    EML_CUDA(cudaStreamSynchronize(st));
+    return EML_OK;
+}
+
 #define EML_STREAM_OR_CTX(st)                 \
     DeviceCtx* ctx = nullptr;                 \
     EML_TRY(get_ctx(&ctx));                   \
@@ -478,6 +523,22 @@ int eml_copy_async(void* dst, const void* src, size_t bytes, void* stream) {
     if (!dst || !src) EML_BAD_ARG("copy_async: null pointer");
     EML_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
     return EML_OK;
+}
+int eml_covariance_f32(const float* X, int64_t rows, int64_t cols, int64_t ldx, int feature_axis, float* out) {
+    return covariance_host<float>(X, rows, cols, ldx, feature_axis, out);
+}
+int eml_covariance_f64(const double* X, int64_t rows, int64_t cols, int64_t ldx, int feature_axis, double* out) {
+    return covariance_host<double>(X, rows, cols, ldx, feature_axis, out);
+}
+int eml_covariance_f32_dev(const float* X, int64_t rows, int64_t cols, int feature_axis, float* out, void* stream) {
+    DeviceCtx* ctx = nullptr;
+    EML_TRY(get_ctx(&ctx));
+    return covariance_dev<float>(ctx, X, rows, cols, feature_axis, out, (cudaStream_t)stream);
+}
+int eml_covariance_f64_dev(const double* X, int64_t rows, int64_t cols, int feature_axis, double* out, void* stream) {
+    DeviceCtx* ctx = nullptr;
+    EML_TRY(get_ctx(&ctx));
+    return covariance_dev<double>(ctx, X, rows, cols, feature_axis, out, (cudaStream_t)stream);
 }
 int eml_measure_fp64_tensor_peak(double* tflops) {
     DeviceCtx* ctx = nullptr;

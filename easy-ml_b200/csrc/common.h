@@ -151,6 +151,10 @@ template <class T>
 int launch_col_sums(const T* x, int64_t rows, int64_t cols, T* out, cudaStream_t stream);  // out[c] = sum_r x[r,c]
 template <class T>
 int launch_row_sums(const T* x, int64_t rows, int64_t cols, T* out, cudaStream_t stream);  // out[r] = sum_c x[r,c]
+// out = x - sums[feature] / samples (covariance centring); axis 1: columns are features, 0: rows
+template <class T>
+int launch_center(const T* x, const T* sums, int64_t samples, int64_t rows, int64_t cols, int axis, T* out,
+                  cudaStream_t stream);
 // out[0] (+)= sum_i x[i]*y[i], fixed order
 template <class T>
 int launch_dot_accumulate(DeviceCtx* ctx, const T* x, const T* y, int64_t n, T* out, bool accumulate,

@@ -430,6 +430,32 @@ int launch_row_sums(const T* x, int64_t rows, int64_t cols, T* out, cudaStream_t
     return check_launch("row_sums");
 }
 
+// out[r, c] = x[r, c] - sums[f] / samples, f = c (axis 1: columns are features) or r (axis 0): the centring
+// pass of the covariance (x - mean with mean = sum / S, the reference's own two roundings)
+namespace {
+template <class T>
+__global__ void __launch_bounds__(256)
+center_kernel(const T* __restrict__ x, const T* __restrict__ sums, T samples, int64_t rows, int64_t cols, int axis,
+              T* __restrict__ out) {
+    const int64_t n = rows * cols;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t f = axis == 1 ? i % cols : i / cols;
+        out[i] = x[i] - sums[f] / samples;
+    }
+}
+}  // namespace
+
+template <class T>
+int launch_center(const T* x, const T* sums, int64_t samples, int64_t rows, int64_t cols, int axis, T* out,
+                  cudaStream_t stream) {
+    int64_t want = (rows * cols + 255) / 256;
+    int blocks = (int)(want < 148 * 16 ? want : 148 * 16);
+    if (blocks < 1) blocks = 1;
+    center_kernel<T><<<blocks, 256, 0, stream>>>(x, sums, (T)samples, rows, cols, axis, out);
+    count_launch();
+    return check_launch("center");
+}
+
 template <class T>
 int launch_einsum2(const T* A, const T* B, T* out, int n_out, const int64_t* out_len, const int64_t* a_out_stride,
                    const int64_t* b_out_stride, int n_sum, const int64_t* sum_len, const int64_t* a_sum_stride,
@@ -476,6 +502,7 @@ int launch_einsum2(const T* A, const T* B, T* out, int n_out, const int64_t* out
     template int launch_dot_accumulate<T>(DeviceCtx*, const T*, const T*, int64_t, T*, bool, cudaStream_t);      \
     template int launch_col_sums<T>(const T*, int64_t, int64_t, T*, cudaStream_t);                               \
     template int launch_row_sums<T>(const T*, int64_t, int64_t, T*, cudaStream_t);                               \
+    template int launch_center<T>(const T*, const T*, int64_t, int64_t, int64_t, int, T*, cudaStream_t);         \
     template int launch_einsum2<T>(const T*, const T*, T*, int, const int64_t*, const int64_t*, const int64_t*,  \
                                    int, const int64_t*, const int64_t*, const int64_t*, cudaStream_t);
 EML_INST(float)

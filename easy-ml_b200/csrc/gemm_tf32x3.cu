@@ -351,7 +351,18 @@ constexpr int STAGES = 3;
 constexpr int ACC_STAGES = 2;
 constexpr uint32_t TMEM_COLS = 512;         // 2 accumulator stages x 256 columns
 constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-constexpr int EPI_WARPS = 4;
+constexpr int EPI_WARPS = 8;                 // warp = (TMEM lane quarter, column half)
+constexpr int THREADS = (4 + EPI_WARPS) * 32;  // warpgroup 0: producer, MMA issuer, 2 idle; warpgroups 1-2: epilogue
+// 384 threads compile to <= 168 registers; the epilogue keeps 128 sums + 32 loaded values per thread, so the
+// register file is re-split with setmaxnreg: 4*32*40 + 8*32*232 = 64512 <= 65536
+constexpr int CONTROL_REGS = 40, EPILOGUE_REGS = 232;
+// The tensor core adds into its f32 accumulator with truncation (round toward zero): over a long chain of
+// same-sign products the bias grows with the number of MMAs (measured: 5e-4 relative at K = 65536).  So an
+// accumulator is only trusted for FLUSH_KB k blocks (512 k = 192 MMAs, bias < 3e-6 of sum|a b|); then the MMA
+// warp moves to the other TMEM stage and the epilogue warps add the drained partial into a running f32 sum
+// held in REGISTERS (128 columns of one row per thread) with IEEE round-to-nearest adds, under the next
+// chunk's MMAs; C is written once per tile.
+constexpr int FLUSH_KB = 16;
 
 struct Work {
     int tm, tn, batch, split;
@@ -375,7 +386,7 @@ __device__ __forceinline__ Work decode(int w, int tiles_m, int tiles_n, int spli
     return k;
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 tf32x3_pair_kernel(const __grid_constant__ Maps maps, float* __restrict__ C, int64_t M, int64_t N, int64_t ldc,
                    int64_t strideC, int kblocks_total, int kblocks_per_split, int splits, int tiles_m, int tiles_n,
                    int work_items, int accumulate, float* __restrict__ ws, int64_t ws_split_stride) {
@@ -413,6 +424,7 @@ tf32x3_pair_kernel(const __grid_constant__ Maps maps, float* __restrict__ C, int
     tc_fence_after();
     const uint32_t tmem_acc = *tmem_slot;
 
+    if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CONTROL_REGS));
     if (warp == 0) {
         // ---------------- TMA producer (both CTAs) ----------------
         if (lane == 0) {
@@ -439,46 +451,74 @@ tf32x3_pair_kernel(const __grid_constant__ Maps maps, float* __restrict__ C, int
         // ---------------- MMA issuer (leader CTA only) ----------------
         if (rank == 0 && lane == 0) {
             constexpr uint32_t idesc = umma_idesc_tf32(PM, PN);
-            int n = 0, it = 0;
-            for (int w = cluster; w < work_items; w += clusters, it++) {
+            int n = 0, it = 0;  // it counts accumulator uses (one per k chunk)
+            for (int w = cluster; w < work_items; w += clusters) {
                 const Work wk = decode(w, tiles_m, tiles_n, splits);
                 const int kb0 = wk.split * kblocks_per_split;
                 const int kb1 = min(kblocks_total, kb0 + kblocks_per_split);
-                const int as = it & 1;
-                if (it >= ACC_STAGES) mbar_wait(&acc_empty[as], ((it >> 1) - 1) & 1);  // epilogue drained this stage
-                tc_fence_after();
-                const uint32_t d = tmem_acc + (uint32_t)as * PN;
-                for (int kb = kb0; kb < kb1; kb++, n++) {
-                    const int s = n % STAGES;
-                    mbar_wait(&full[s], (n / STAGES) & 1);
+                for (int c0 = kb0; c0 < kb1; c0 += FLUSH_KB, it++) {
+                    const int c1 = min(kb1, c0 + FLUSH_KB);
+                    const int as = it & 1;
+                    if (it >= ACC_STAGES) mbar_wait(&acc_empty[as], ((it >> 1) - 1) & 1);  // epilogue drained this stage
                     tc_fence_after();
-                    const uint32_t st = smem_u32(base + (size_t)s * STAGE_BYTES);
-                    const uint64_t a_big = umma_desc_k_sw128(st), a_small = umma_desc_k_sw128(st + TILE_BYTES);
-                    const uint64_t b_big = umma_desc_k_sw128(st + 2 * TILE_BYTES);
-                    const uint64_t b_small = umma_desc_k_sw128(st + 3 * TILE_BYTES);
-                    const uint32_t first = kb != kb0;
+                    const uint32_t d = tmem_acc + (uint32_t)as * PN;
+                    for (int kb = c0; kb < c1; kb++, n++) {
+                        const int s = n % STAGES;
+                        mbar_wait(&full[s], (n / STAGES) & 1);
+                        tc_fence_after();
+                        const uint32_t st = smem_u32(base + (size_t)s * STAGE_BYTES);
+                        const uint64_t a_big = umma_desc_k_sw128(st), a_small = umma_desc_k_sw128(st + TILE_BYTES);
+                        const uint64_t b_big = umma_desc_k_sw128(st + 2 * TILE_BYTES);
+                        const uint64_t b_small = umma_desc_k_sw128(st + 3 * TILE_BYTES);
+                        const uint32_t first = kb != c0;
 #pragma unroll
-                    for (int k = 0; k < BK / 8; k++) umma_tf32_pair(d, a_small + 2 * k, b_big + 2 * k, idesc, first | (uint32_t)k);
+                        for (int k = 0; k < BK / 8; k++)
+                            umma_tf32_pair(d, a_small + 2 * k, b_big + 2 * k, idesc, first | (uint32_t)k);
 #pragma unroll
-                    for (int k = 0; k < BK / 8; k++) umma_tf32_pair(d, a_big + 2 * k, b_small + 2 * k, idesc, 1);
+                        for (int k = 0; k < BK / 8; k++) umma_tf32_pair(d, a_big + 2 * k, b_small + 2 * k, idesc, 1);
 #pragma unroll
-                    for (int k = 0; k < BK / 8; k++) umma_tf32_pair(d, a_big + 2 * k, b_big + 2 * k, idesc, 1);
-                    umma_commit_pair(&empty[s], 0b11);  // frees the stage in both CTAs
+                        for (int k = 0; k < BK / 8; k++) umma_tf32_pair(d, a_big + 2 * k, b_big + 2 * k, idesc, 1);
+                        umma_commit_pair(&empty[s], 0b11);  // frees the stage in both CTAs
+                    }
+                    umma_commit_pair(&acc_full[as], 0b11);  // this chunk's partial is complete: wake both epilogues
                 }
-                umma_commit_pair(&acc_full[as], 0b11);  // the accumulator is complete: wake both epilogues
             }
         }
-    } else {
+    } else if (warp >= 4) {
         // ---------------- epilogue (both CTAs) ----------------
-        const int q = warp & 3;
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(EPILOGUE_REGS));
+        const int q = warp & 3, half = (warp - 4) >> 2;  // TMEM lane quarter, 128-column half
         int it = 0;
-        for (int w = cluster; w < work_items; w += clusters, it++) {
+        for (int w = cluster; w < work_items; w += clusters) {
             const Work wk = decode(w, tiles_m, tiles_n, splits);
-            const int as = it & 1;
-            mbar_wait(&acc_full[as], (it >> 1) & 1);
-            tc_fence_after();
+            const int kb0 = wk.split * kblocks_per_split;
+            const int kb1 = min(kblocks_total, kb0 + kblocks_per_split);
+            float sum[128];  // this thread's row, 128 columns: the IEEE-rounded running sum over k chunks
+            for (int c0 = kb0; c0 < kb1; c0 += FLUSH_KB, it++) {
+                const int as = it & 1;
+                mbar_wait(&acc_full[as], (it >> 1) & 1);
+                tc_fence_after();
+                const uint32_t t0 = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * PN + half * 128);
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(t0 + (uint32_t)(c * 32), v);
+                    tmem_ld_wait();
+                    if (c0 == kb0) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) sum[c * 32 + j] = __uint_as_float(v[j]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) sum[c * 32 + j] += __uint_as_float(v[j]);
+                    }
+                }
+                tc_fence_before();  // the chunk is in registers: hand the accumulator stage back to the leader
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(&acc_empty[as], 0);
+            }
+            // one store of the tile
             const int64_t row = (int64_t)wk.tm * PM + (int64_t)rank * HALF + q * 32 + lane;
-            const int64_t n0 = (int64_t)wk.tn * PN;
+            const int64_t n0 = (int64_t)wk.tn * PN + half * 128;
             float* out;
             int64_t ld;
             if (ws) {
@@ -490,24 +530,17 @@ tf32x3_pair_kernel(const __grid_constant__ Maps maps, float* __restrict__ C, int
             }
             const bool add = accumulate && !ws;
             const bool vec_ok = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
-#pragma unroll 1
-            for (int c = 0; c < PN / 32; c++) {
-                uint32_t v[32];
-                tmem_ld_32x32b_x32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * PN + c * 32), v);
-                tmem_ld_wait();
-                if (c == PN / 32 - 1) {  // everything is in registers: hand the accumulator stage back
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_cluster(&acc_empty[as], 0);
-                }
-                const int64_t col0 = n0 + c * 32;
-                if (row < M && col0 < N) {
+            if (row < M) {
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    const int64_t col0 = n0 + c * 32;
+                    if (col0 >= N) continue;
                     float* p = out + row * ld + col0;
                     if (vec_ok && col0 + 32 <= N) {
 #pragma unroll
                         for (int j = 0; j < 8; j++) {
-                            float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                                   __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                            float4 o = make_float4(sum[c * 32 + 4 * j], sum[c * 32 + 4 * j + 1], sum[c * 32 + 4 * j + 2],
+                                                   sum[c * 32 + 4 * j + 3]);
                             if (add) {
                                 float4 old = *reinterpret_cast<const float4*>(p + 4 * j);
                                 o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
@@ -517,7 +550,7 @@ tf32x3_pair_kernel(const __grid_constant__ Maps maps, float* __restrict__ C, int
                     } else {
 #pragma unroll
                         for (int j = 0; j < 32; j++)
-                            if (col0 + j < N) p[j] = add ? p[j] + __uint_as_float(v[j]) : __uint_as_float(v[j]);
+                            if (col0 + j < N) p[j] = add ? p[j] + sum[c * 32 + j] : sum[c * 32 + j];
                     }
                 }
             }
@@ -546,7 +579,7 @@ int launch(const Maps& maps, float* C, int64_t batch, int64_t M, int64_t N, int6
     if (items > 0x7fffffffLL) EML_BAD_ARG("tf32x3: too many work items");
     int clusters = sms / 2;
     if (items < clusters) clusters = (int)items;
-    tf32x3_pair_kernel<<<2 * clusters, GEMM_THREADS, SMEM_BYTES, stream>>>(
+    tf32x3_pair_kernel<<<2 * clusters, THREADS, SMEM_BYTES, stream>>>(
         maps, C, M, N, ldc, strideC, kblocks, per_split, used_splits, tiles_m, tiles_n, (int)items, accumulate ? 1 : 0, ws,
         batch * M * N);
     count_launch();
@@ -635,6 +668,9 @@ int launch_gemm_tf32x3_f32(DeviceCtx* ctx, const float* A, const float* B, float
             if (splits > kblocks / 4) splits = kblocks / 4;
             if (splits < 1) splits = 1;
         }
+        // bound the truncating TMEM accumulation chain (see pair::FLUSH_KB): at most 16 k blocks per split
+        const int min_splits = (kblocks + pair::FLUSH_KB - 1) / pair::FLUSH_KB;
+        if (splits < min_splits) splits = min_splits;
         Mp = round_up(M, BM);
         Np = round_up(N, BN);
     }

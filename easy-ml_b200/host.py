@@ -119,6 +119,21 @@ class Matrix:
                         f"{other.rows()}x{other.columns()}, * is only defined for MxN * NxL")
         return Matrix(_gemm(self.data, other.data))
 
+    def _covariance(self, axis):
+        a = np.ascontiguousarray(self.data)
+        f = a.shape[1] if axis == 1 else a.shape[0]
+        out = np.empty((f, f), dtype=a.dtype)
+        check(getattr(lib, f"eml_covariance_{_sfx(a.dtype)}")(_ptr(a), a.shape[0], a.shape[1], a.shape[1], axis, _ptr(out)))
+        return Matrix(out)
+
+    def covariance_column_features(self):
+        """linear_algebra::covariance_column_features, src/linear_algebra.rs:615-639 (Matrix method mod.rs:1874)."""
+        return self._covariance(1)
+
+    def covariance_row_features(self):
+        """linear_algebra::covariance_row_features, src/linear_algebra.rs:676-700."""
+        return self._covariance(0)
+
     def __repr__(self):
         return f"Matrix({self.data.tolist()})"
 
@@ -193,6 +208,21 @@ class Tensor:
                         f"{_shape_debug([ls[0], rs[1]])}. Rename one or both of the dimension names in the input "
                         "to prevent this. * is defined as MxN * NxL = MxL")
         return Tensor([ls[0], rs[1]], _gemm(self.data, other.data))
+
+    def covariance(self, feature_dimension):
+        """linear_algebra::covariance, src/linear_algebra.rs:778-832 (rank 2; output dimensions "i", "j")."""
+        if len(self._shape) != 2:
+            raise TypeError("covariance is defined for rank 2 tensors")
+        names = self.names()
+        if feature_dimension not in names:  # :797-802
+            raise Panic(f'Feature dimension "{feature_dimension}" is not present in the input tensor\'s shape: '
+                        f"{_shape_debug(self._shape)}")
+        axis = names.index(feature_dimension)
+        a = np.ascontiguousarray(self.data)
+        f = a.shape[axis]
+        out = np.empty((f, f), dtype=a.dtype)
+        check(getattr(lib, f"eml_covariance_{_sfx(a.dtype)}")(_ptr(a), a.shape[0], a.shape[1], a.shape[1], axis, _ptr(out)))
+        return Tensor([("i", f), ("j", f)], out)
 
     def scalar_product(self, other):
         # Tensor<T,1>::scalar_product, src/tensors/mod.rs:1773 -> operations.rs:1773-1808

@@ -103,7 +103,20 @@ class Matrix {
         return Matrix(rows_, right.cols_, std::move(c));
     }
 
+    // linear_algebra::covariance_column_features / covariance_row_features, src/linear_algebra.rs:615-639, :676-700
+    Matrix covariance_column_features() const { return covariance(1); }
+    Matrix covariance_row_features() const { return covariance(0); }
+
   private:
+    Matrix covariance(int axis) const {
+        const int64_t f = axis == 1 ? cols_ : rows_;
+        std::vector<T> out((size_t)(f * f));
+        if constexpr (detail::is_f32<T>)
+            detail::check(eml_covariance_f32(data_.data(), rows_, cols_, cols_, axis, out.data()));
+        else
+            detail::check(eml_covariance_f64(data_.data(), rows_, cols_, cols_, axis, out.data()));
+        return Matrix(f, f, std::move(out));
+    }
     int64_t rows_, cols_;
     std::vector<T> data_;
 };

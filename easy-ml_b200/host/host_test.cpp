@@ -37,6 +37,9 @@ static void matrix_goldens() {
     // tests/matrices.rs:168-173 (#[should_panic]); message src/matrices/operations.rs:176-183
     EXPECT(panic_text([&] { (void)(a * a); }) ==
            "Mismatched Matrices, left is 3x2, right is 3x2, * is only defined for MxN * NxL");
+    // tests/linear_algebra.rs:157-170: covariance of column features (exact: the data is +-1)
+    Matrix<T> feat(4, 3, {1, 1, -1, -1, -1, 1, -1, -1, 1, 1, 1, -1});
+    EXPECT(feat.covariance_column_features() == Matrix<T>(3, 3, {1, 1, -1, 1, 1, -1, -1, -1, 1}));
     // tests/linear_algebra.rs:183-190: L * L^T == A exactly
     Matrix<T> l(3, 3, {5, 0, 0, 3, 3, 0, -1, 1, 3}), lt(3, 3, {5, 3, -1, 0, 3, 1, 0, 0, 3});
     EXPECT((l * lt) == Matrix<T>(3, 3, {25, 15, -5, 15, 18, 0, -5, 0, 11}));

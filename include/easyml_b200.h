@@ -125,6 +125,19 @@ int eml_einsum2_f64(const double* A, int64_t a_elems, const double* B, int64_t b
 int eml_dot_f32(const float* x, int64_t incx, const float* y, int64_t incy, int64_t n, float* out);
 int eml_dot_f64(const double* x, int64_t incx, const double* y, int64_t incy, int64_t n, double* out);
 
+/* Covariance of features (the first "next" row: a SYRK-shaped caller of the GEMM):
+ *   cov[i][j] = (1/S) sum_s (x[s,i] - mean_i)(x[s,j] - mean_j),  mean_i = (sum_s x[s,i]) / S,  no Bessel correction.
+ * Replaces covariance_column_features (src/linear_algebra.rs:615-639; feature_axis = 1, S = rows),
+ * covariance_row_features (:676-700; feature_axis = 0, S = cols) and covariance (:778-832; the caller resolves the
+ * feature dimension name to an axis and keeps the reference's panic for an unknown name).  The reference
+ * recomputes both means for every (i, j) -- O(F^2 S) extra; here: column/row sums, one centring pass, one GEMM
+ * (X_c^T X_c or X_c X_c^T through strides), one scaling pass.  X: rows x cols row-major, ld = ldx; out: F x F. */
+int eml_covariance_f32(const float* X, int64_t rows, int64_t cols, int64_t ldx, int feature_axis, float* out);
+int eml_covariance_f64(const double* X, int64_t rows, int64_t cols, int64_t ldx, int feature_axis, double* out);
+/* device-resident: X dense (ld = cols) */
+int eml_covariance_f32_dev(const float* X, int64_t rows, int64_t cols, int feature_axis, float* out, void* stream);
+int eml_covariance_f64_dev(const double* X, int64_t rows, int64_t cols, int feature_axis, double* out, void* stream);
+
 /* Bit-exact GEMM: same contract as eml_gemm_*, but every C[i,j] is the reference's exact operation
  * sequence (first product, then k-ascending separately rounded multiply and add -- scalar_product,
  * src/tensors/operations.rs:441-445).  Slow (no tensor cores, no FMA); exists so parity can be shown

@@ -151,6 +151,17 @@ def vector_dot(a, a_name, b, b_name):
     return out.value
 
 
+def covariance(x, feature_axis):
+    """covariance_column_features (feature_axis=1) / covariance_row_features (0), linear_algebra.rs:615-700."""
+    x = np.ascontiguousarray(x)
+    sfx, _ = _sfx(x.dtype)
+    f = x.shape[1] if feature_axis == 1 else x.shape[0]
+    out = np.zeros((f, f), dtype=x.dtype)
+    getattr(lib(), f"orc_covariance_{sfx}")(_p(x), C.c_int64(x.shape[0]), C.c_int64(x.shape[1]), C.c_int(feature_axis),
+                                            _p(out))
+    return out
+
+
 class Tape:
     """The literal scalar WengertList (src/differentiation.rs:327-352)."""
 

@@ -485,6 +485,28 @@ void derivatives(const orc_tape* t, const std::vector<T>& ld, const std::vector<
 
 }  // namespace
 
+// covariance_*_features, src/linear_algebra.rs:615-639 / :676-700 / :778-832.  The reference recomputes both
+// feature means inside the closure of every (i, j); the values are the same each time, so they are computed
+// once here -- the operation sequence per number is unchanged.
+template <class T>
+static void covariance(const T* x, int64_t rows, int64_t cols, int axis, T* out) {
+    const int64_t F = axis == 1 ? cols : rows, S = axis == 1 ? rows : cols;
+    auto at = [&](int64_t s, int64_t f) { return axis == 1 ? x[s * cols + f] : x[f * cols + s]; };
+    const T samples = (T)S;  // T::from_usize
+    std::vector<T> mean((size_t)F);
+    for (int64_t f = 0; f < F; f++) {
+        T sum = T(0);
+        for (int64_t s = 0; s < S; s++) sum = sum + at(s, f);  // .sum::<T>()
+        mean[f] = sum / samples;
+    }
+    for (int64_t i = 0; i < F; i++)
+        for (int64_t j = 0; j < F; j++) {
+            T sum = T(0);
+            for (int64_t s = 0; s < S; s++) sum = sum + (at(s, i) - mean[i]) * (at(s, j) - mean[j]);
+            out[i * F + j] = sum / samples;
+        }
+}
+
 extern "C" {
 
 const char* orc_last_error(void) { return g_error.c_str(); }
@@ -532,6 +554,13 @@ int orc_vector_dot_f32(const float* a, const char* an, int64_t al, const float* 
 int orc_vector_dot_f64(const double* a, const char* an, int64_t al, const double* b, const char* bn, int64_t bl,
                        double* out) {
     return vector_dot<double>(a, an, al, b, bn, bl, out);
+}
+
+void orc_covariance_f32(const float* x, int64_t rows, int64_t cols, int axis, float* out) {
+    covariance<float>(x, rows, cols, axis, out);
+}
+void orc_covariance_f64(const double* x, int64_t rows, int64_t cols, int axis, double* out) {
+    covariance<double>(x, rows, cols, axis, out);
 }
 
 orc_tape* orc_tape_new(int elem_size) {

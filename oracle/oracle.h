@@ -65,6 +65,13 @@ int orc_vector_dot_f32(const float* a, const char* a_name, int64_t a_len, const 
 int orc_vector_dot_f64(const double* a, const char* a_name, int64_t a_len, const double* b,
                        const char* b_name, int64_t b_len, double* out);
 
+/* Next row: covariance_column_features / covariance_row_features / covariance,
+ * src/linear_algebra.rs:615-639, :676-700, :778-832.  x is rows x cols row-major; feature_axis 1 = columns are
+ * features (samples = rows), 0 = rows are features.  out is F x F.  Literal restatement: sequential sums from
+ * zero, mean = sum / S, sum of (x - mean_i)(y - mean_j) / S, no Bessel correction. */
+void orc_covariance_f32(const float* x, int64_t rows, int64_t cols, int feature_axis, float* out);
+void orc_covariance_f64(const double* x, int64_t rows, int64_t cols, int feature_axis, double* out);
+
 /* A9: WengertList, src/differentiation.rs:327-352, 674, 696-768, 811-878 -- the literal scalar tape */
 typedef struct orc_tape orc_tape; /* element type fixed at creation: 4 = f32, 8 = f64 */
 orc_tape* orc_tape_new(int elem_size);

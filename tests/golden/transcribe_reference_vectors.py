@@ -145,6 +145,17 @@ V["xor_nn"] = {
     "inputs": [[0.0, 0.0, 1.0], [0.0, 1.0, 1.0], [1.0, 0.0, 1.0], [1.0, 1.0, 1.0]],
     "labels": [0.0, 1.0, 1.0, 0.0], "learning_rate": 0.1, "epochs": 300, "final_loss_below": 0.02}
 
+# ---- next row: covariance ---------------------------------------------------------
+V["covariance"] = [
+    {"cite": "tests/linear_algebra.rs:157-170 (covariance_column_features::<f32>, assert_eq!: exact)",
+     "x": [[1, 1, -1], [-1, -1, 1], [-1, -1, 1], [1, 1, -1]], "feature_axis": 1,
+     "expect": [[1, 1, -1], [1, 1, -1], [-1, -1, 1]], "exact": True},
+    {"cite": "src/linear_algebra.rs:739-763 doctest (tensor.covariance(\"features\"), output printed to 3 decimals)",
+     "x": [[1.0, 0.0, 0.5], [1.2, -1.0, 0.4], [1.8, -1.2, 0.7], [0.9, 0.1, 0.3], [0.7, 0.5, 0.6]], "feature_axis": 1,
+     "names": ["samples", "features"], "feature_dimension": "features",
+     "expect": [[0.142, -0.226, 0.026], [-0.226, 0.438, -0.022], [0.026, -0.022, 0.020]], "exact": False,
+     "decimals": 3}]
+
 out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_vectors.json")
 with open(out, "w") as f:
     json.dump(V, f, indent=1)

@@ -202,6 +202,22 @@ def test_sgemm_tf32x3_all_layouts_ragged(orc, monkeypatch, variant, a_kin, b_kin
     assert np.array_equal(gi, np.matmul(ai.astype(np.float64), bi_.astype(np.float64)).astype(np.float32))
 
 
+@pytest.mark.parametrize("m,n,k", [(256, 384, 16384), (128, 256, 8192), (300, 100, 4096)])
+def test_sgemm_same_sign_long_k(m, n, k):
+    """Worst case for an accumulator that rounds toward zero: all products positive, long K.  The tensor core's
+    f32 accumulation truncates, so the kernels bound every TMEM accumulation chain to 512 k and combine the
+    partials with IEEE adds; the result must stay within 1e-5 * sum|a_k b_k| (here: of the value itself)."""
+    r = rng(1200 + m + n + k)
+    a = r.uniform(0.0, 1.0, (m, k)).astype(np.float32)
+    b = r.uniform(0.0, 1.0, (k, n)).astype(np.float32)
+    got = gemm(a, b)
+    assert eml.last_kernel() == "tf32x3_tcgen05"
+    exact = a.astype(np.float64) @ b.astype(np.float64)
+    assert_within(got, a, b, exact, np.float32, f"same-sign {m}x{n}x{k}")
+    # the tight version: f32-level relative error on every element (the sequential f32 reference itself is ~1e-5 off)
+    assert np.max(np.abs(got.astype(np.float64) - exact) / exact) < 5e-6
+
+
 def test_sgemm_tf32x3_wide_tile_accumulate_device():
     """128x256 tiles (enough tiles to fill the machine) and the C += A*B epilogue, device-resident."""
     import torch
@@ -528,3 +544,36 @@ def test_container_elementwise_rules(orc, dtype):
         od = tape.derivatives(ozi[6, 8])
         assert np.array_equal(dd.at_matrix(X).data, od[ox[1]]) and np.array_equal(dd.at_matrix(Y).data, od[oy[1]])
     assert len(hist) == len(tape)
+
+
+# ------------------------------------------------------------------ next row: covariance
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_covariance_reference_goldens_and_oracle(orc, golden, dtype):
+    for g in golden["covariance"]:
+        x = np.array(g["x"], dtype)
+        got = eml.Matrix(x).covariance_column_features().data if g["feature_axis"] == 1 else \
+            eml.Matrix(x).covariance_row_features().data
+        if g["exact"]:
+            assert np.array_equal(got, np.array(g["expect"], dtype)), g["cite"]
+        else:
+            assert np.array_equal(np.round(got.astype(np.float64), g["decimals"]), np.array(g["expect"])), g["cite"]
+        if "names" in g:
+            t = eml.Tensor(list(zip(g["names"], x.shape)), x)
+            c = t.covariance(g["feature_dimension"])
+            assert c.names() == ["i", "j"] and np.array_equal(c.data, got)
+            with pytest.raises(eml.Panic, match="is not present in the input tensor's shape"):
+                t.covariance("nope")
+    r = rng(900)
+    tol = TOL[np.dtype(dtype)]
+    for rows, cols in ((300, 40), (2048, 256), (70, 513)):
+        x = uniform(r, (rows, cols), dtype)
+        for axis in (1, 0):
+            got = (eml.Matrix(x).covariance_column_features() if axis == 1 else eml.Matrix(x).covariance_row_features()).data
+            ref = orc.covariance(x, axis).astype(np.float64)
+            x64 = x.astype(np.float64)
+            xc = x64 - x64.mean(axis=0 if axis == 1 else 1, keepdims=True)
+            s = rows if axis == 1 else cols
+            scale = (np.abs(xc).T @ np.abs(xc) if axis == 1 else np.abs(xc) @ np.abs(xc).T) / s
+            # 4x: both sides round the means and the centred values independently
+            assert np.all(np.abs(got.astype(np.float64) - ref) <= 4 * tol * scale + 1e-30), (rows, cols, axis)
+            assert np.array_equal(got, got.T) or np.allclose(got, got.T, rtol=0, atol=float(4 * tol * scale.max()))

@@ -209,3 +209,17 @@ def test_xor_network_replay(orc, golden):
         losses.append(float(loss.number))
     assert losses[-1] < g["final_loss_below"], losses[-1]
     assert losses[0] > losses[-1]
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_covariance_goldens(orc, golden, dtype):
+    """Next row (SURVEY 8f-2): covariance_column_features / covariance_row_features / Tensor::covariance."""
+    for g in golden["covariance"]:
+        x = np.array(g["x"], dtype)
+        got = orc.covariance(x, g["feature_axis"])
+        if g["exact"]:
+            assert np.array_equal(got, np.array(g["expect"], dtype)), g["cite"]
+        else:
+            assert np.array_equal(np.round(got.astype(np.float64), g["decimals"]), np.array(g["expect"])), g["cite"]
+        # row-features form of the same data
+        assert np.array_equal(orc.covariance(np.ascontiguousarray(x.T), 1 - g["feature_axis"]), got)
