@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <map>
+#include <vector>
 #include <memory>
 #include <string>
 
@@ -89,10 +90,83 @@ int get_ctx(DeviceCtx** out) {
     return EML_OK;
 }
 
-int TempBuf::alloc(size_t bytes, cudaStream_t stream) {
-    s = stream;
-    EML_CUDA(cudaMallocAsync(&p, bytes ? bytes : 16, stream));
+namespace {
+struct CacheKey {
+    int device;
+    cudaStream_t stream;
+    size_t bytes;
+    bool operator<(const CacheKey& o) const {
+        if (device != o.device) return device < o.device;
+        if (stream != o.stream) return stream < o.stream;
+        return bytes < o.bytes;
+    }
+};
+std::mutex g_cache_mu;
+std::map<CacheKey, std::vector<void*>> g_cache;
+size_t g_cached_bytes = 0;
+constexpr size_t CACHE_LIMIT = size_t(24) << 30;  // beyond this, blocks go straight back to CUDA
+
+inline size_t size_class(size_t bytes) { return bytes < 512 ? 512 : (bytes + 511) & ~size_t(511); }
+}  // namespace
+
+int stream_alloc(void** p, size_t bytes, cudaStream_t stream) {
+    const size_t sz = size_class(bytes);
+    int dev = 0;
+    EML_CUDA(cudaGetDevice(&dev));
+    {
+        std::lock_guard<std::mutex> lock(g_cache_mu);
+        auto it = g_cache.find(CacheKey{dev, stream, sz});
+        if (it != g_cache.end() && !it->second.empty()) {
+            *p = it->second.back();
+            it->second.pop_back();
+            g_cached_bytes -= sz;
+            return EML_OK;
+        }
+    }
+    cudaError_t e = cudaMallocAsync(p, sz, stream);
+    if (e == cudaErrorMemoryAllocation) {  // give the cache back and retry once
+        cudaGetLastError();
+        stream_cache_release_all();
+        e = cudaMallocAsync(p, sz, stream);
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMallocAsync", __FILE__, __LINE__);
     return EML_OK;
+}
+
+void stream_free(void* p, size_t bytes, cudaStream_t stream) {
+    if (!p) return;
+    const size_t sz = size_class(bytes);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    {
+        std::lock_guard<std::mutex> lock(g_cache_mu);
+        if (g_cached_bytes + sz <= CACHE_LIMIT) {
+            g_cache[CacheKey{dev, stream, sz}].push_back(p);
+            g_cached_bytes += sz;
+            return;
+        }
+    }
+    cudaFreeAsync(p, stream);
+}
+
+void stream_cache_release_all() {
+    std::lock_guard<std::mutex> lock(g_cache_mu);
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (auto& kv : g_cache) {
+        cudaSetDevice(kv.first.device);
+        for (void* q : kv.second) cudaFreeAsync(q, kv.first.stream);
+        kv.second.clear();
+    }
+    g_cache.clear();
+    g_cached_bytes = 0;
+    cudaSetDevice(cur);
+}
+
+int TempBuf::alloc(size_t n, cudaStream_t stream) {
+    s = stream;
+    bytes = n;
+    return stream_alloc(&p, n, stream);
 }
 
 int stage_buffer(DeviceCtx* ctx, int slot, size_t bytes, void** out) {
@@ -111,6 +185,7 @@ int stage_buffer(DeviceCtx* ctx, int slot, size_t bytes, void** out) {
 }
 
 void shutdown_all() {
+    stream_cache_release_all();
     std::lock_guard<std::mutex> lock(g_ctx_mu);
     for (auto& kv : g_ctx) {
         DeviceCtx* c = kv.second.get();

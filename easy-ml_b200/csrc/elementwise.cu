@@ -134,7 +134,7 @@ binary_kernel(const T* __restrict__ x, const T* __restrict__ y, T* __restrict__ 
     }
 }
 
-// MODE 0: dparent += dout*deriv   1: w -= lr*d  (lr in c)   2: out = c   3: dst += src
+// MODE 0: dparent += dout*deriv   1: w -= lr*d  (lr in c)   2: out = c   3: dst += src   4: out = b - lr*a
 template <class T, int MODE, bool VEC>
 __global__ void __launch_bounds__(EW_THREADS)
 axpy_kernel(T c, const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, int64_t n) {
@@ -144,14 +144,15 @@ axpy_kernel(T c, const T* __restrict__ a, const T* __restrict__ b, T* __restrict
         if (VEC && i + V <= n) {
             T av[Vec<T>::N], bv[Vec<T>::N], ov[Vec<T>::N];
             if (MODE != 2) vload<T>(a + i, av);
-            if (MODE == 0) vload<T>(b + i, bv);
-            if (MODE != 2) vload<T>(out + i, ov);
+            if (MODE == 0 || MODE == 4) vload<T>(b + i, bv);
+            if (MODE != 2 && MODE != 4) vload<T>(out + i, ov);
 #pragma unroll
             for (int j = 0; j < Vec<T>::N; j++) {
                 if (MODE == 0) ov[j] = ov[j] + av[j] * bv[j];
                 if (MODE == 1) ov[j] = ov[j] - av[j] * c;
                 if (MODE == 2) ov[j] = c;
                 if (MODE == 3) ov[j] = ov[j] + av[j];
+                if (MODE == 4) ov[j] = bv[j] - av[j] * c;
             }
             vstore<T>(out + i, ov);
         } else {
@@ -161,6 +162,7 @@ axpy_kernel(T c, const T* __restrict__ a, const T* __restrict__ b, T* __restrict
                 if (MODE == 1) out[q] = out[q] - a[q] * c;
                 if (MODE == 2) out[q] = c;
                 if (MODE == 3) out[q] = out[q] + a[q];
+                if (MODE == 4) out[q] = b[q] - a[q] * c;
             }
         }
     }
@@ -386,6 +388,10 @@ int launch_sgd(T* w, const T* d, T lr, int64_t n, cudaStream_t stream) {
     return launch_axpy<T, 1>(lr, d, nullptr, w, n, stream);
 }
 template <class T>
+int launch_sgd_out(T* out, const T* w, const T* d, T lr, int64_t n, cudaStream_t stream) {
+    return launch_axpy<T, 4>(lr, d, w, out, n, stream);
+}
+template <class T>
 int launch_fill(T* out, T value, int64_t n, cudaStream_t stream) {
     return launch_axpy<T, 2>(value, nullptr, nullptr, out, n, stream);
 }
@@ -495,6 +501,7 @@ int launch_einsum2(const T* A, const T* B, T* out, int n_out, const int64_t* out
     template int launch_binary<T>(int, const T*, const T*, T*, T*, T*, int64_t, cudaStream_t);                   \
     template int launch_chain<T>(const T*, const T*, T*, int64_t, cudaStream_t);                                 \
     template int launch_sgd<T>(T*, const T*, T, int64_t, cudaStream_t);                                          \
+    template int launch_sgd_out<T>(T*, const T*, const T*, T, int64_t, cudaStream_t);                            \
     template int launch_fill<T>(T*, T, int64_t, cudaStream_t);                                                   \
     template int launch_add_inplace<T>(T*, const T*, int64_t, cudaStream_t);                                     \
     template int launch_dot<T>(const T*, int64_t, const T*, int64_t, int64_t, T*, cudaStream_t);                 \

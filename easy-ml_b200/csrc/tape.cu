@@ -22,17 +22,27 @@ struct DevBuf {
     void* p = nullptr;
     size_t bytes = 0;
     cudaStream_t s = nullptr;
+    std::shared_ptr<DevBuf> parent;  // set for a view into another buffer (the view owns nothing)
     ~DevBuf() {
-        if (p) cudaFreeAsync(p, s);
+        if (p && !parent) stream_free(p, bytes, s);
     }
 };
 using Buf = std::shared_ptr<DevBuf>;
+
+Buf view_of(const Buf& arena, size_t offset, size_t bytes) {
+    auto b = std::make_shared<DevBuf>();
+    b->p = static_cast<char*>(arena->p) + offset;
+    b->bytes = bytes;
+    b->s = arena->s;
+    b->parent = arena;
+    return b;
+}
 
 int new_buf(size_t bytes, cudaStream_t s, Buf* out) {
     auto b = std::make_shared<DevBuf>();
     b->s = s;
     b->bytes = bytes;
-    EML_CUDA(cudaMallocAsync(&b->p, bytes ? bytes : 16, s));
+    EML_TRY(stream_alloc(&b->p, bytes, s));
     *out = b;
     return EML_OK;
 }
@@ -332,21 +342,26 @@ int tape_sweep(eml_tape* t, eml_val hv, int64_t row, int64_t col, eml_derivs** o
     d->len = t->len;
     d->epoch = t->epoch;
     d->nodes = t->nodes;
+    // vec![0; len] (:627): one arena for every node's derivatives (+ the Index-0 slot), one memset
     d->grads.resize(t->nodes.size());
+    std::vector<size_t> offs(t->nodes.size() + 1);
+    size_t total = 256;  // [0, 256): slot0
     for (size_t i = 0; i < t->nodes.size(); i++) {
-        EML_TRY(new_buf(sizeof(T) * t->nodes[i].n, st, &d->grads[i]));
-        EML_CUDA(cudaMemsetAsync(d->grads[i]->p, 0, sizeof(T) * t->nodes[i].n, st));  // vec![0; len] :627
+        offs[i] = total;
+        total += (sizeof(T) * (size_t)t->nodes[i].n + 255) & ~size_t(255);
     }
+    Buf arena;
+    EML_TRY(new_buf(total, st, &arena));
+    EML_CUDA(cudaMemsetAsync(arena->p, 0, total, st));
+    for (size_t i = 0; i < t->nodes.size(); i++) d->grads[i] = view_of(arena, offs[i], sizeof(T) * (size_t)t->nodes[i].n);
     // contributions to reference index 0 from parents that carry Index 0 (constants)
-    TempBuf slot0;
-    EML_TRY(slot0.alloc(sizeof(T), st));
-    EML_CUDA(cudaMemsetAsync(slot0.p, 0, sizeof(T), st));
+    T* const slot0_ptr = static_cast<T*>(arena->p);
     bool slot0_used = false;
     // derivatives[self.index] = 1  (:630)
     if (nv >= 0) {
         EML_TRY(launch_fill<T>((T*)d->grads[nv]->p + (row * v->cols + col), T(1), 1, st));
     } else {
-        EML_TRY(launch_fill<T>(slot0.as<T>(), T(1), 1, st));
+        EML_TRY(launch_fill<T>(slot0_ptr, T(1), 1, st));
         slot0_used = true;
     }
 
@@ -355,10 +370,17 @@ int tape_sweep(eml_tape* t, eml_val hv, int64_t row, int64_t col, eml_derivs** o
         const T* g = (const T*)d->grads[i]->p;
         if (nd.kind == Kind::VARIABLES) continue;
         if (nd.kind == Kind::UNARY) {
-            if (nd.p0 >= 0)
+            if (!nd.a) {  // derivative is exactly 1 for every element (x - constant): dparent += dout
+                if (nd.p0 >= 0)
+                    EML_TRY(launch_add_inplace<T>((T*)d->grads[nd.p0]->p, g, nd.n, st));
+                else {
+                    EML_TRY(launch_reduce_sum<T>(t->ctx, g, nd.n, slot0_ptr, true, st));
+                    slot0_used = true;
+                }
+            } else if (nd.p0 >= 0)
                 EML_TRY(launch_chain<T>(g, (const T*)nd.a->p, (T*)d->grads[nd.p0]->p, nd.n, st));
             else {
-                EML_TRY(launch_dot_accumulate<T>(t->ctx, g, (const T*)nd.a->p, nd.n, slot0.as<T>(), true, st));
+                EML_TRY(launch_dot_accumulate<T>(t->ctx, g, (const T*)nd.a->p, nd.n, slot0_ptr, true, st));
                 slot0_used = true;
             }
         } else if (nd.kind == Kind::BINARY) {
@@ -366,7 +388,7 @@ int tape_sweep(eml_tape* t, eml_val hv, int64_t row, int64_t col, eml_derivs** o
                 if (nd.p0 >= 0)
                     EML_TRY(launch_chain<T>(g, (const T*)nd.a->p, (T*)d->grads[nd.p0]->p, nd.n, st));
                 else {
-                    EML_TRY(launch_dot_accumulate<T>(t->ctx, g, (const T*)nd.a->p, nd.n, slot0.as<T>(), true, st));
+                    EML_TRY(launch_dot_accumulate<T>(t->ctx, g, (const T*)nd.a->p, nd.n, slot0_ptr, true, st));
                     slot0_used = true;
                 }
             }
@@ -374,7 +396,7 @@ int tape_sweep(eml_tape* t, eml_val hv, int64_t row, int64_t col, eml_derivs** o
                 if (nd.p1 >= 0)
                     EML_TRY(launch_chain<T>(g, (const T*)nd.b->p, (T*)d->grads[nd.p1]->p, nd.n, st));
                 else {
-                    EML_TRY(launch_dot_accumulate<T>(t->ctx, g, (const T*)nd.b->p, nd.n, slot0.as<T>(), true, st));
+                    EML_TRY(launch_dot_accumulate<T>(t->ctx, g, (const T*)nd.b->p, nd.n, slot0_ptr, true, st));
                     slot0_used = true;
                 }
             }
@@ -393,7 +415,7 @@ int tape_sweep(eml_tape* t, eml_val hv, int64_t row, int64_t col, eml_derivs** o
                 EML_TRY(cb.alloc(sizeof(T) * N, st));
                 EML_TRY(launch_col_sums<T>(g, M, N, cg.as<T>(), st));
                 EML_TRY(launch_col_sums<T>(B, K, N, cb.as<T>(), st));
-                EML_TRY(launch_dot_accumulate<T>(t->ctx, cg.as<T>(), cb.as<T>(), N, slot0.as<T>(), true, st));
+                EML_TRY(launch_dot_accumulate<T>(t->ctx, cg.as<T>(), cb.as<T>(), N, slot0_ptr, true, st));
                 slot0_used = true;
             }
             if (nd.p1 >= 0) {
@@ -406,14 +428,14 @@ int tape_sweep(eml_tape* t, eml_val hv, int64_t row, int64_t col, eml_derivs** o
                 EML_TRY(rg.alloc(sizeof(T) * M, st));
                 EML_TRY(launch_row_sums<T>(A, M, K, ra.as<T>(), st));
                 EML_TRY(launch_row_sums<T>(g, M, N, rg.as<T>(), st));
-                EML_TRY(launch_dot_accumulate<T>(t->ctx, ra.as<T>(), rg.as<T>(), M, slot0.as<T>(), true, st));
+                EML_TRY(launch_dot_accumulate<T>(t->ctx, ra.as<T>(), rg.as<T>(), M, slot0_ptr, true, st));
                 slot0_used = true;
             }
         }
     }
     if (slot0_used) {
         // reference index 0 is element 0 of the first node
-        EML_TRY(launch_add_inplace<T>((T*)d->grads[0]->p, slot0.as<T>(), 1, st));
+        EML_TRY(launch_add_inplace<T>((T*)d->grads[0]->p, slot0_ptr, 1, st));
     }
     *out = d.release();
     return EML_OK;
@@ -696,21 +718,18 @@ int eml_tape_sgd_update(eml_tape* t, eml_val hw, eml_derivs* d, double lr) {
     // x - (derivatives[&x] * lr): a new container (the nodes that captured the old numbers keep them)
     Buf fresh;
     EML_TRY(new_buf(es * n, t->stream, &fresh));
-    EML_CUDA(cudaMemcpyAsync(fresh->p, w->numbers->p, es * n, cudaMemcpyDeviceToDevice, t->stream));
     Node nd;
-    nd.kind = Kind::UNARY;  // Record - T => append_unary(x.index, 1)
+    nd.kind = Kind::UNARY;  // Record - T => append_unary(x.index, 1): nd.a stays null = derivative 1 everywhere
     nd.base = t->len;
     nd.count = nd.n = n;
     nd.p0 = w->node;
     nd.p0_tracked = true;
-    EML_TRY(new_buf(es * n, t->stream, &nd.a));
-    if (t->dtype == EML_F32) {
-        EML_TRY(launch_sgd<float>((float*)fresh->p, (const float*)d->grads[w->node]->p, (float)lr, n, t->stream));
-        EML_TRY(launch_fill<float>((float*)nd.a->p, 1.0f, n, t->stream));
-    } else {
-        EML_TRY(launch_sgd<double>((double*)fresh->p, (const double*)d->grads[w->node]->p, lr, n, t->stream));
-        EML_TRY(launch_fill<double>((double*)nd.a->p, 1.0, n, t->stream));
-    }
+    if (t->dtype == EML_F32)
+        EML_TRY(launch_sgd_out<float>((float*)fresh->p, (const float*)w->numbers->p,
+                                      (const float*)d->grads[w->node]->p, (float)lr, n, t->stream));
+    else
+        EML_TRY(launch_sgd_out<double>((double*)fresh->p, (const double*)w->numbers->p,
+                                       (const double*)d->grads[w->node]->p, lr, n, t->stream));
     t->len += n;
     t->nodes.push_back(nd);
     w->numbers = fresh;
