@@ -107,6 +107,17 @@ def matrix_mul(a, b, rows=None, threads=1):
     return c
 
 
+def matrix_mul_block(a, b, rows, cols, threads=1):
+    """C[rows[0]:rows[1], cols[0]:cols[1]] of A * B (a bounded sample for CPU-baseline timing)."""
+    s, _ = _sfx(a.dtype)
+    assert a.flags.c_contiguous and b.flags.c_contiguous and a.shape[1] == b.shape[0]
+    c = np.zeros((rows[1] - rows[0], cols[1] - cols[0]), dtype=a.dtype)
+    getattr(lib(), f"orc_matrix_mul_block_{s}")(
+        _p(a), C.c_int64(a.shape[1]), _p(b), C.c_int64(b.shape[1]), _p(c), C.c_int64(rows[0]), C.c_int64(rows[1]),
+        C.c_int64(cols[0]), C.c_int64(cols[1]), C.c_int(threads))
+    return c
+
+
 def tensor_mul(a, a_names, b, b_names):
     """A3: rank-2 Tensor * Tensor.  Returns (c, out_names)."""
     s, _ = _sfx(a.dtype)

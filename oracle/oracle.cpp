@@ -56,6 +56,32 @@ void matrix_mul_rows(const T* a, int64_t a_cols, const T* b, int64_t b_cols, T* 
             c[i * b_cols + j] = scalar_product<T>(a + i * a_cols, 1, b + j, b_cols, a_cols);
 }
 
+// A bounded SAMPLE of the same product for CPU-baseline timing: elements C[row0:row1, col0:col1] only, computed
+// exactly as above (B is still the full-width row-major matrix, so the column walk keeps its stride).  Every
+// element of C costs the same 2K flop; threads split the (row, column-chunk) work, results stay bit-identical.
+template <class T>
+void matrix_mul_block(const T* a, int64_t a_cols, const T* b, int64_t b_cols, T* c, int64_t row0, int64_t row1,
+                      int64_t col0, int64_t col1, int threads) {
+    const int64_t rows = row1 - row0, cols = col1 - col0;
+    auto work = [=](int t) {
+        // thread t takes every threads-th (row, 64-column chunk)
+        const int64_t chunks = (cols + 63) / 64;
+        for (int64_t w = t; w < rows * chunks; w += threads) {
+            const int64_t i = row0 + w / chunks, j0 = col0 + (w % chunks) * 64;
+            const int64_t j1 = j0 + 64 < col1 ? j0 + 64 : col1;
+            for (int64_t j = j0; j < j1; j++)
+                c[(i - row0) * cols + (j - col0)] = scalar_product<T>(a + i * a_cols, 1, b + j, b_cols, a_cols);
+        }
+    };
+    if (threads <= 1) {
+        work(0);
+        return;
+    }
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; t++) pool.emplace_back(work, t);
+    for (auto& th : pool) th.join();
+}
+
 template <class T>
 int matrix_mul(const T* a, int64_t a_rows, int64_t a_cols, const T* b, int64_t b_rows, int64_t b_cols, T* c,
                int64_t row0, int64_t row1, int threads) {
@@ -521,6 +547,14 @@ double orc_scalar_product_f64(const double* l, int64_t ls, const double* r, int6
 int orc_matrix_mul_f32(const float* a, int64_t ar, int64_t ac, const float* b, int64_t br, int64_t bc, float* c,
                        int64_t row0, int64_t row1, int threads) {
     return matrix_mul<float>(a, ar, ac, b, br, bc, c, row0, row1, threads);
+}
+void orc_matrix_mul_block_f32(const float* a, int64_t ac, const float* b, int64_t bc, float* c, int64_t row0,
+                              int64_t row1, int64_t col0, int64_t col1, int threads) {
+    matrix_mul_block<float>(a, ac, b, bc, c, row0, row1, col0, col1, threads);
+}
+void orc_matrix_mul_block_f64(const double* a, int64_t ac, const double* b, int64_t bc, double* c, int64_t row0,
+                              int64_t row1, int64_t col0, int64_t col1, int threads) {
+    matrix_mul_block<double>(a, ac, b, bc, c, row0, row1, col0, col1, threads);
 }
 int orc_matrix_mul_f64(const double* a, int64_t ar, int64_t ac, const double* b, int64_t br, int64_t bc,
                        double* c, int64_t row0, int64_t row1, int threads) {

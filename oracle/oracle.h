@@ -40,6 +40,13 @@ int orc_matrix_mul_f32(const float* a, int64_t a_rows, int64_t a_cols, const flo
 int orc_matrix_mul_f64(const double* a, int64_t a_rows, int64_t a_cols, const double* b, int64_t b_rows,
                        int64_t b_cols, double* c, int64_t row0, int64_t row1, int threads);
 
+/* Bounded sample of A2 for CPU-baseline timing: c (dense (row1-row0) x (col1-col0)) = C[row0:row1, col0:col1],
+ * every element by the same scalar_product walk (B keeps its full row-major width b_cols). */
+void orc_matrix_mul_block_f32(const float* a, int64_t a_cols, const float* b, int64_t b_cols, float* c, int64_t row0,
+                              int64_t row1, int64_t col0, int64_t col1, int threads);
+void orc_matrix_mul_block_f64(const double* a, int64_t a_cols, const double* b, int64_t b_cols, double* c,
+                              int64_t row0, int64_t row1, int64_t col0, int64_t col1, int threads);
+
 /* A3: tensor_view_matrix_product, src/tensors/operations.rs:474-519.  Names are C strings.
  * out_names[2] receives pointers to the (borrowed) output dimension names. */
 int orc_tensor_mul_f32(const float* a, const char* const* a_names, const int64_t* a_len, const float* b,
