@@ -179,14 +179,15 @@ def run_reference(args):
     emit(line)
 
 
-def workload_config(n, gpus, gather="fused into the GEMM epilogue: peer stores over NVLink"):
+def workload_config(n, gpus, gather="fused into the GEMM epilogue: peer stores over NVLink",
+                    bcast="copy-engine pull over NVLink"):
     if gpus == 1:
         return {"workload": f"f64 Matrix x Matrix {n}x{n} (BASELINE config 2)", "M": n, "N": n, "K": n,
                 "l2": "operands (3 x %.0f MB) exceed the 126 MB L2" % (n * n * 8 / 1e6), "parallelism": "1 GPU"}
-    return {"workload": f"f64 {n}x{n} row-sharded over {gpus} GPUs, NCCL broadcast of B in K panels + all-gather of C "
-                        f"({gather}) (BASELINE config 5)",
+    return {"workload": f"f64 {n}x{n} row-sharded over {gpus} GPUs, B broadcast from rank 0 in K panels ({bcast}) + "
+                        f"all-gather of C ({gather}) (BASELINE config 5)",
             "M": n, "N": n, "K": n, "l2": "operands exceed the 126 MB L2", "parallelism": f"row-shard x{gpus}",
-            "gather": gather}
+            "gather": gather, "broadcast": bcast}
 
 
 _REAL_STDOUT = None
@@ -750,7 +751,8 @@ def sharded(args, torch, dist, eml, lib, check, dev, stream, sp, rank, world, ti
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": workload_config(n, world, "fused into the GEMM epilogue: peer stores over NVLink" if fused
-                                  else "ncclAllGather"),
+                                  else "ncclAllGather",
+                                  "copy-engine pull over NVLink" if args.bcast == "ce" else "ncclBroadcast"),
         "clocks": clocks,
         "gpu_launches": int(launches),
         "e2e": {"value": value, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
