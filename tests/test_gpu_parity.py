@@ -577,3 +577,32 @@ def test_covariance_reference_goldens_and_oracle(orc, golden, dtype):
             # 4x: both sides round the means and the centred values independently
             assert np.all(np.abs(got.astype(np.float64) - ref) <= 4 * tol * scale + 1e-30), (rows, cols, axis)
             assert np.array_equal(got, got.T) or np.allclose(got, got.T, rtol=0, atol=float(4 * tol * scale.max()))
+
+
+# ------------------------------------------------------------------ re-entrancy (Matrix / Tensor are Send + Sync)
+def test_concurrent_host_calls_from_threads(orc):
+    """The reference's Matrix<T> / Tensor<T, D> are Send + Sync (src/matrices/mod.rs:2030-2040), so the library can be
+    entered from several host threads at once: results must be the single-threaded ones, bit for bit."""
+    import threading
+
+    r = rng(1500)
+    jobs = []
+    for i, dtype in enumerate([np.float32, np.float64, np.float32, np.float64]):
+        a, b = uniform(r, (300 + 64 * i, 200), dtype), uniform(r, (200, 260), dtype)
+        jobs.append((a, b, gemm(a, b)))
+    errors = []
+
+    def worker(a, b, want):
+        try:
+            for _ in range(8):
+                if not np.array_equal(gemm(a, b), want):
+                    errors.append("mismatch")
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=j) for j in jobs]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
