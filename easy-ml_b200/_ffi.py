@@ -63,6 +63,8 @@ SIGNATURES = {
     "eml_ipc_open": (cint, [vp, C.POINTER(vp)]),
     "eml_ipc_close": (cint, [vp]),
     "eml_copy_async": (cint, [vp, vp, C.c_size_t, vp]),
+    "eml_einsum_n_f32": (cint, [cint, C.POINTER(vp), pi64, vp, cint, pi64, pi64, cint, pi64, pi64]),
+    "eml_einsum_n_f64": (cint, [cint, C.POINTER(vp), pi64, vp, cint, pi64, pi64, cint, pi64, pi64]),
     "eml_covariance_f32": (cint, [vp, i64, i64, i64, cint, vp]),
     "eml_covariance_f64": (cint, [vp, i64, i64, i64, cint, vp]),
     "eml_covariance_f32_dev": (cint, [vp, i64, i64, cint, vp, vp]),

@@ -295,6 +295,48 @@ int einsum_host(const T* A, int64_t a_elems, const T* B, int64_t b_elems, T* out
 }
 
 template <class T>
+int einsum_n_host(int n_ops, const T* const* x, const int64_t* elems, T* out, int n_out, const int64_t* out_len,
+                  const int64_t* out_strides, int n_sum, const int64_t* sum_len, const int64_t* sum_strides) {
+    DeviceCtx* ctx = nullptr;
+    EML_TRY(get_ctx(&ctx));
+    if (n_ops < 1 || n_ops > 6 || !x || !elems || !out) EML_BAD_ARG("einsum: 1..6 operands, non-null arguments");
+    if (n_out < 0 || n_out > 6 || n_sum < 0 || n_sum > 36) EML_BAD_ARG("einsum: rank out of range");
+    int64_t total = 1;
+    for (int d = 0; d < n_out; d++) {
+        if (out_len[d] < 0) EML_BAD_ARG("einsum: negative length");
+        total *= out_len[d];
+    }
+    for (int i = 0; i < n_ops; i++) {  // every reachable index stays inside its operand
+        if (!x[i] || elems[i] < 1) EML_BAD_ARG("einsum: empty operand %d", i);
+        int64_t reach = 0;
+        for (int d = 0; d < n_out; d++) {
+            if (out_strides[i * n_out + d] < 0) EML_BAD_ARG("einsum: negative stride");
+            if (out_len[d]) reach += (out_len[d] - 1) * out_strides[i * n_out + d];
+        }
+        for (int d = 0; d < n_sum; d++) {
+            if (sum_len[d] < 0 || sum_strides[i * n_sum + d] < 0) EML_BAD_ARG("einsum: negative length/stride");
+            if (sum_len[d]) reach += (sum_len[d] - 1) * sum_strides[i * n_sum + d];
+        }
+        if (total && reach >= elems[i]) EML_BAD_ARG("einsum: strides reach outside operand %d", i);
+    }
+    if (total == 0) return EML_OK;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    cudaStream_t st = ctx->stream;
+    TempBuf dx[6], dout;
+    const T* dptr[6];
+    for (int i = 0; i < n_ops; i++) {
+        EML_TRY(dx[i].alloc(sizeof(T) * (size_t)elems[i], st));
+        EML_CUDA(cudaMemcpyAsync(dx[i].p, x[i], sizeof(T) * (size_t)elems[i], cudaMemcpyHostToDevice, st));
+        dptr[i] = dx[i].template as<T>();
+    }
+    EML_TRY(dout.alloc(sizeof(T) * (size_t)total, st));
+    EML_TRY(launch_einsum_n<T>(n_ops, dptr, dout.template as<T>(), n_out, out_len, out_strides, n_sum, sum_len, sum_strides, st));
+    EML_CUDA(cudaMemcpyAsync(out, dout.p, sizeof(T) * (size_t)total, cudaMemcpyDeviceToHost, st));
+    EML_CUDA(cudaStreamSynchronize(st));
+    return EML_OK;
+}
+
+template <class T>
 int dot_host(const T* x, int64_t incx, const T* y, int64_t incy, int64_t n, T* out) {
     DeviceCtx* ctx = nullptr;
     EML_TRY(get_ctx(&ctx));
@@ -523,6 +565,16 @@ int eml_copy_async(void* dst, const void* src, size_t bytes, void* stream) {
     if (!dst || !src) EML_BAD_ARG("copy_async: null pointer");
     EML_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
     return EML_OK;
+}
+int eml_einsum_n_f32(int n_ops, const float* const* x, const int64_t* elems, float* out, int n_out,
+                     const int64_t* out_len, const int64_t* out_strides, int n_sum, const int64_t* sum_len,
+                     const int64_t* sum_strides) {
+    return einsum_n_host<float>(n_ops, x, elems, out, n_out, out_len, out_strides, n_sum, sum_len, sum_strides);
+}
+int eml_einsum_n_f64(int n_ops, const double* const* x, const int64_t* elems, double* out, int n_out,
+                     const int64_t* out_len, const int64_t* out_strides, int n_sum, const int64_t* sum_len,
+                     const int64_t* sum_strides) {
+    return einsum_n_host<double>(n_ops, x, elems, out, n_out, out_len, out_strides, n_sum, sum_len, sum_strides);
 }
 int eml_covariance_f32(const float* X, int64_t rows, int64_t cols, int64_t ldx, int feature_axis, float* out) {
     return covariance_host<float>(X, rows, cols, ldx, feature_axis, out);

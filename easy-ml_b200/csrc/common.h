@@ -135,6 +135,11 @@ int launch_einsum2(const T* A, const T* B, T* out, int n_out, const int64_t* out
                    const int64_t* b_out_stride, int n_sum, const int64_t* sum_len, const int64_t* a_sum_stride,
                    const int64_t* b_sum_stride, cudaStream_t stream);
 
+// N-operand generic einsum (1..6 operands); out_strides is [n_ops][n_out], sum_strides [n_ops][n_sum]
+template <class T>
+int launch_einsum_n(int n_ops, const T* const* x, T* out, int n_out, const int64_t* out_len, const int64_t* out_strides,
+                    int n_sum, const int64_t* sum_len, const int64_t* sum_strides, cudaStream_t stream);
+
 template <class T>
 int launch_dot(const T* x, int64_t incx, const T* y, int64_t incy, int64_t n, T* out_dev, cudaStream_t stream);
 

@@ -312,6 +312,66 @@ __global__ void __launch_bounds__(256) einsum2_kernel(const T* __restrict__ A, c
     }
 }
 
+// ---- generic N-operand einsum, N = 1..6 (Einsum1 / Einsum3..6, reference src/tensors/einsum.rs:829-883,
+// :1019-1666): out[o] = sum_s ((x1 * x2) * x3) ... in the reference's order -- zero-seeded sum, summation
+// dimensions in order of first appearance with the last fastest, left-associated product, every operation
+// separately rounded (this file is compiled -fmad=false): bit-exact with the reference.
+constexpr int MAX_OPS = 6, MAX_SUM_N = 36;  // six rank-6 operands can carry 36 distinct summed names
+struct EinsumNParams {
+    int n_ops, n_out, n_sum;
+    int64_t total, sum_total;
+    const void* x[MAX_OPS];
+    int64_t out_len[MAX_OUT], sum_len[MAX_SUM_N];
+    int64_t out_stride[MAX_OPS][MAX_OUT];
+    int64_t sum_stride[MAX_OPS][MAX_SUM_N];
+};
+
+template <class T>
+__global__ void __launch_bounds__(256) einsum_n_kernel(T* __restrict__ out, const __grid_constant__ EinsumNParams p) {
+    for (int64_t flat = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; flat < p.total;
+         flat += (int64_t)gridDim.x * blockDim.x) {
+        int64_t off[MAX_OPS];
+#pragma unroll
+        for (int i = 0; i < MAX_OPS; i++) off[i] = 0;
+        int64_t rem = flat;
+        for (int d = p.n_out - 1; d >= 0; d--) {
+            int64_t ix = rem % p.out_len[d];
+            rem /= p.out_len[d];
+#pragma unroll
+            for (int i = 0; i < MAX_OPS; i++)
+                if (i < p.n_ops) off[i] += ix * p.out_stride[i][d];
+        }
+        auto product = [&]() {
+            T v = static_cast<const T*>(p.x[0])[off[0]];
+#pragma unroll
+            for (int i = 1; i < MAX_OPS; i++)
+                if (i < p.n_ops) v = v * static_cast<const T*>(p.x[i])[off[i]];  // ((p1 * p2) * p3) ...
+            return v;
+        };
+        T sum = T(0);
+        if (p.n_sum == 0) {
+            sum = sum + product();
+        } else {
+            int idx[MAX_SUM_N];
+            for (int d = 0; d < p.n_sum; d++) idx[d] = 0;
+            for (int64_t s = 0; s < p.sum_total; s++) {
+                sum = sum + product();
+                for (int d = p.n_sum - 1; d >= 0; d--) {  // odometer, last dimension fastest
+#pragma unroll
+                    for (int i = 0; i < MAX_OPS; i++)
+                        if (i < p.n_ops) off[i] += p.sum_stride[i][d];
+                    if (++idx[d] < p.sum_len[d]) break;
+#pragma unroll
+                    for (int i = 0; i < MAX_OPS; i++)
+                        if (i < p.n_ops) off[i] -= p.sum_stride[i][d] * p.sum_len[d];
+                    idx[d] = 0;
+                }
+            }
+        }
+        out[flat] = sum;
+    }
+}
+
 template <class T, int OP>
 int launch_unary_op(T c, const T* x, T* y, T* dydx, int64_t n, cudaStream_t stream) {
     bool vec = aligned16(x) && (!y || aligned16(y)) && (!dydx || aligned16(dydx));
@@ -496,7 +556,42 @@ int launch_einsum2(const T* A, const T* B, T* out, int n_out, const int64_t* out
     return check_launch("einsum2");
 }
 
+template <class T>
+int launch_einsum_n(int n_ops, const T* const* x, T* out, int n_out, const int64_t* out_len, const int64_t* out_strides,
+                    int n_sum, const int64_t* sum_len, const int64_t* sum_strides, cudaStream_t stream) {
+    if (n_ops < 1 || n_ops > MAX_OPS) EML_BAD_ARG("einsum: 1..%d operands (got %d)", MAX_OPS, n_ops);
+    if (n_out < 0 || n_out > MAX_OUT || n_sum < 0 || n_sum > MAX_SUM_N)
+        EML_BAD_ARG("einsum: n_out=%d (max %d) n_sum=%d (max %d)", n_out, MAX_OUT, n_sum, MAX_SUM_N);
+    EinsumNParams p{};
+    p.n_ops = n_ops;
+    p.n_out = n_out;
+    p.n_sum = n_sum;
+    p.total = p.sum_total = 1;
+    for (int i = 0; i < n_ops; i++) p.x[i] = x[i];
+    for (int d = 0; d < n_out; d++) {
+        if (out_len[d] < 0) EML_BAD_ARG("einsum: negative length");
+        p.out_len[d] = out_len[d];
+        p.total *= out_len[d];
+        for (int i = 0; i < n_ops; i++) p.out_stride[i][d] = out_strides[i * n_out + d];
+    }
+    for (int d = 0; d < n_sum; d++) {
+        if (sum_len[d] < 0) EML_BAD_ARG("einsum: negative length");
+        p.sum_len[d] = sum_len[d];
+        p.sum_total *= sum_len[d];
+        for (int i = 0; i < n_ops; i++) p.sum_stride[i][d] = sum_strides[i * n_sum + d];
+    }
+    if (p.total == 0) return EML_OK;
+    int64_t blocks = (p.total + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    einsum_n_kernel<T><<<(unsigned)blocks, 256, 0, stream>>>(out, p);
+    count_launch();
+    set_last_kernel("einsum_generic");
+    return check_launch("einsum_n");
+}
+
 #define EML_INST(T)                                                                                              \
+    template int launch_einsum_n<T>(int, const T* const*, T*, int, const int64_t*, const int64_t*, int,          \
+                                    const int64_t*, const int64_t*, cudaStream_t);                               \
     template int launch_unary<T>(int, T, const T*, T*, T*, int64_t, cudaStream_t);                               \
     template int launch_binary<T>(int, const T*, const T*, T*, T*, T*, int64_t, cudaStream_t);                   \
     template int launch_chain<T>(const T*, const T*, T*, int64_t, cudaStream_t);                                 \

@@ -353,12 +353,70 @@ class _Einsum2:
         return Tensor(out_shape, out)
 
 
+class _EinsumN:
+    """Einsum1 / Einsum3..6 (src/tensors/einsum.rs:829-883, :1019-1666): the strided loop nest on the device, in
+    the reference's order (bit-exact).  Two operands go through _Einsum2, which recognises (batched) GEMMs."""
+
+    def __init__(self, tensors):
+        self.tensors = list(tensors)
+
+    def named(self, *names):
+        if len(names) != len(self.tensors):
+            raise TypeError("one list of names per tensor")
+        return _EinsumN([t.rename(n) for t, n in zip(self.tensors, names)])
+
+    def to(self, output):
+        ts = self.tensors
+        dtype = ts[0].data.dtype
+        if any(t.data.dtype != dtype for t in ts):
+            raise TypeError("all tensors must have the same element type")
+        output = list(output)
+        inputs = [t._shape for t in ts]
+        out_shape = [(d, _length_of(d, inputs)) for d in output]  # output_shape_for :563-572
+        if len(set(output)) != len(output):
+            raise Panic(f"Dimension names must all be unique: {_shape_debug(out_shape)}")
+        summation = _summation_dimensions(inputs, output)  # :579-622
+        out = np.empty([l for _, l in out_shape], dtype=dtype)
+        arrays = [np.ascontiguousarray(t.data) for t in ts]
+        strides = [{n: a.strides[i] // a.itemsize for i, (n, _) in enumerate(t._shape)} for t, a in zip(ts, arrays)]
+        n = len(ts)
+        n_out, n_sum = len(out_shape), len(summation)
+        os_ = [st.get(d, 0) for st in strides for d, _ in out_shape]
+        ss_ = [st.get(d, 0) for st in strides for d, _ in summation]
+        xs = (C.c_void_p * n)(*[a.ctypes.data for a in arrays])
+        elems = _ffi.arrn([a.size for a in arrays])
+        check(getattr(lib, f"eml_einsum_n_{_sfx(dtype)}")(
+            n, xs, elems, _ptr(out), n_out, _ffi.arrn([l for _, l in out_shape]), _ffi.arrn(os_), n_sum,
+            _ffi.arrn([l for _, l in summation]), _ffi.arrn(ss_)))
+        return Tensor(out_shape, out)
+
+
 class Einsum:
-    """easy_ml::tensors::einsum::Einsum (two-operand form, src/tensors/einsum.rs:113-127)."""
+    """easy_ml::tensors::einsum::Einsum (src/tensors/einsum.rs:98-313): with_1 .. with_6."""
+
+    @staticmethod
+    def with_1(x):
+        return _EinsumN([x])
 
     @staticmethod
     def with_2(x, y):
         return _Einsum2(x, y)
+
+    @staticmethod
+    def with_3(a, b, c):
+        return _EinsumN([a, b, c])
+
+    @staticmethod
+    def with_4(a, b, c, d):
+        return _EinsumN([a, b, c, d])
+
+    @staticmethod
+    def with_5(a, b, c, d, e):
+        return _EinsumN([a, b, c, d, e])
+
+    @staticmethod
+    def with_6(a, b, c, d, e, f):
+        return _EinsumN([a, b, c, d, e, f])
 
 
 # ------------------------------------------------------------------------------------------------

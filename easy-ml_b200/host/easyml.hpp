@@ -347,9 +347,105 @@ class Einsum2 {
     const Tensor<T>& x_;
     const Tensor<T>& y_;
 };
-struct Einsum {
+// Einsum1 / Einsum3..6 (src/tensors/einsum.rs:829-883, :1019-1666): the strided loop nest on the device in the
+// reference's order (zero-seeded sum, left-associated product) -- bit-exact.
+template <class T>
+class EinsumN {
+  public:
+    explicit EinsumN(std::vector<const Tensor<T>*> xs) : xs_(std::move(xs)) {}
+    Tensor<T> to(const std::vector<Dimension>& output) const {
+        auto find = [](const Shape& s, const Dimension& d) -> std::optional<int64_t> {
+            for (auto& e : s)
+                if (e.first == d) return e.second;
+            return std::nullopt;
+        };
+        auto lengths_of = [&](const Dimension& d) {
+            std::vector<std::optional<int64_t>> l;
+            for (auto* x : xs_) l.push_back(find(x->shape(), d));
+            return l;
+        };
+        Shape out_shape, summation;
+        for (auto& d : output) {  // output_shape_for :563-572
+            auto lengths = lengths_of(d);
+            std::optional<int64_t> known;
+            bool ok = true;
+            for (auto& l : lengths)
+                if (l) {
+                    if (known && *known != *l) ok = false;
+                    if (!known) known = l;
+                }
+            if (!known || !ok) throw InconsistentDimensionLengthError(d, lengths);
+            out_shape.emplace_back(d, *known);
+        }
+        for (size_t i = 0; i < output.size(); i++)
+            for (size_t j = i + 1; j < output.size(); j++)
+                if (output[i] == output[j])
+                    throw Panic("Dimension names must all be unique: " + detail::shape_debug(out_shape));
+        for (auto* x : xs_)  // summation_dimensions :579-622
+            for (auto& e : x->shape()) {
+                if (std::find(output.begin(), output.end(), e.first) != output.end()) continue;
+                auto seen = find(summation, e.first);
+                if (!seen)
+                    summation.push_back(e);
+                else if (*seen != e.second)
+                    throw InconsistentDimensionLengthError(e.first, lengths_of(e.first));
+            }
+        const int n = (int)xs_.size(), n_out = (int)out_shape.size(), n_sum = (int)summation.size();
+        std::vector<int64_t> ol, sl, os((size_t)n * n_out, 0), ss((size_t)n * n_sum, 0), elems;
+        std::vector<const T*> ptrs;
+        int64_t total = 1;
+        for (auto& e : out_shape) {
+            ol.push_back(e.second);
+            total *= e.second;
+        }
+        for (auto& e : summation) sl.push_back(e.second);
+        for (int i = 0; i < n; i++) {
+            auto st = xs_[i]->strides();
+            const Shape& sh = xs_[i]->shape();
+            for (size_t k = 0; k < sh.size(); k++) {
+                for (int d = 0; d < n_out; d++)
+                    if (out_shape[d].first == sh[k].first) os[(size_t)i * n_out + d] = st[k];
+                for (int d = 0; d < n_sum; d++)
+                    if (summation[d].first == sh[k].first) ss[(size_t)i * n_sum + d] = st[k];
+            }
+            ptrs.push_back(xs_[i]->data().data());
+            elems.push_back((int64_t)xs_[i]->data().size());
+        }
+        std::vector<T> out((size_t)total);
+        if constexpr (detail::is_f32<T>)
+            detail::check(eml_einsum_n_f32(n, ptrs.data(), elems.data(), out.data(), n_out, ol.data(), os.data(), n_sum,
+                                           sl.data(), ss.data()));
+        else
+            detail::check(eml_einsum_n_f64(n, ptrs.data(), elems.data(), out.data(), n_out, ol.data(), os.data(), n_sum,
+                                           sl.data(), ss.data()));
+        return Tensor<T>(out_shape, std::move(out));
+    }
+
+  private:
+    std::vector<const Tensor<T>*> xs_;
+};
+
+struct Einsum {  // src/tensors/einsum.rs:98-313
     template <class T>
-    static Einsum2<T> with_2(const Tensor<T>& x, const Tensor<T>& y) { return Einsum2<T>(x, y); }  // einsum.rs:113-127
+    static EinsumN<T> with_1(const Tensor<T>& x) { return EinsumN<T>({&x}); }
+    template <class T>
+    static Einsum2<T> with_2(const Tensor<T>& x, const Tensor<T>& y) { return Einsum2<T>(x, y); }
+    template <class T>
+    static EinsumN<T> with_3(const Tensor<T>& a, const Tensor<T>& b, const Tensor<T>& c) { return EinsumN<T>({&a, &b, &c}); }
+    template <class T>
+    static EinsumN<T> with_4(const Tensor<T>& a, const Tensor<T>& b, const Tensor<T>& c, const Tensor<T>& d) {
+        return EinsumN<T>({&a, &b, &c, &d});
+    }
+    template <class T>
+    static EinsumN<T> with_5(const Tensor<T>& a, const Tensor<T>& b, const Tensor<T>& c, const Tensor<T>& d,
+                             const Tensor<T>& e) {
+        return EinsumN<T>({&a, &b, &c, &d, &e});
+    }
+    template <class T>
+    static EinsumN<T> with_6(const Tensor<T>& a, const Tensor<T>& b, const Tensor<T>& c, const Tensor<T>& d,
+                             const Tensor<T>& e, const Tensor<T>& f) {
+        return EinsumN<T>({&a, &b, &c, &d, &e, &f});
+    }
 };
 
 // ------------------------------------------------------------------------------------------------ autodiff

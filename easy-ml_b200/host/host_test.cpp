@@ -96,6 +96,11 @@ static void einsum_goldens() {
         auto zs = xs * ys;
         EXPECT(std::equal(zs.data().begin(), zs.data().end(), Z.data().begin() + bt * 6));
     }
+    // tests/einsum.rs:208-226: three operands ab,cb,bd->ac; :13-27 one operand ab->ba
+    Tensor<T> m23({{"a", 2}, {"b", 3}}, {0, 10, 20, 1, 11, 21}), n23({{"c", 2}, {"b", 3}}, {0, 10, 20, 1, 11, 21});
+    Tensor<T> m34({{"b", 3}, {"d", 4}}, {0, 10, 20, 30, 1, 11, 21, 31, 2, 12, 22, 32});
+    EXPECT(Einsum::with_3(m23, n23, m34).to({"a", "c"}) == Tensor<T>({{"a", 2}, {"c", 2}}, {33600, 35600, 35600, 37792}));
+    EXPECT(Einsum::with_1(m23).to({"b", "a"}) == Tensor<T>({{"b", 3}, {"a", 2}}, {0, 1, 10, 11, 20, 21}));
     // Err(InconsistentDimensionLengthError)
     bool threw = false;
     try {

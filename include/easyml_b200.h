@@ -120,6 +120,20 @@ int eml_einsum2_f64(const double* A, int64_t a_elems, const double* B, int64_t b
                     const int64_t* out_len, const int64_t* a_out_stride, const int64_t* b_out_stride, int n_sum,
                     const int64_t* sum_len, const int64_t* a_sum_stride, const int64_t* b_sum_stride);
 
+/* N-operand Einstein summation, N = 1..6: Einsum1::to and Einsum3..6::to,
+ * src/tensors/einsum.rs:829-883 and :1019-1666 (transposes, sums and traces of one tensor; chains of three to six):
+ *   out[o] = sum over s of ((x1 * x2) * x3) ...   each operand read at  o . out_strides[i] + s . sum_strides[i]
+ * out is contiguous row-major over out_len[0..n_out); out_strides is [n_ops][n_out] and sum_strides [n_ops][n_sum]
+ * (row-major; stride 0 = the operand does not carry that dimension).  Zero-seeded sum, summation dimensions in
+ * the order given (the reference's: first appearance, last fastest), left-associated product, separately
+ * rounded multiplies and adds: BIT-EXACT with the reference.  Host pointers; elems[i] = length of x[i]. */
+int eml_einsum_n_f32(int n_ops, const float* const* x, const int64_t* elems, float* out, int n_out,
+                     const int64_t* out_len, const int64_t* out_strides, int n_sum, const int64_t* sum_len,
+                     const int64_t* sum_strides);
+int eml_einsum_n_f64(int n_ops, const double* const* x, const int64_t* elems, double* out, int n_out,
+                     const int64_t* out_len, const int64_t* out_strides, int n_sum, const int64_t* sum_len,
+                     const int64_t* sum_strides);
+
 /* Dot product of two strided vectors (n >= 1).  Replaces Tensor<T,1>::scalar_product,
  * src/tensors/mod.rs:1773 -> src/tensors/operations.rs:1773-1808. */
 int eml_dot_f32(const float* x, int64_t incx, const float* y, int64_t incy, int64_t n, float* out);

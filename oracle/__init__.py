@@ -152,6 +152,32 @@ def einsum2(a, a_names, b, b_names, out_names):
     return out
 
 
+def einsum_n(arrays, names, out_names):
+    """Einsum::with_N(...).named(...).to(out_names) for N = 1..6 (src/tensors/einsum.rs:829-883, :1019-1666)."""
+    n = len(arrays)
+    s, _ = _sfx(arrays[0].dtype)
+    arrays = [np.ascontiguousarray(a) for a in arrays]
+    xs = (C.c_void_p * n)(*[a.ctypes.data for a in arrays])
+    ranks = (C.c_int * n)(*[a.ndim for a in arrays])
+    name_arrays = [_names(nm) for nm in names]
+    len_arrays = [_i64(a.shape) for a in arrays]
+    names_pp = (C.c_void_p * n)(*[C.cast(na, C.c_void_p).value for na in name_arrays])
+    lens_pp = (C.c_void_p * n)(*[C.cast(la, C.c_void_p).value for la in len_arrays])
+    f = getattr(lib(), f"orc_einsum_n_{s}")
+    ol = (C.c_int64 * max(len(out_names), 1))()
+    ed = C.c_char_p()
+    el = (C.c_int64 * n)(*([-1] * n))
+    on = _names(out_names)
+    rc = f(C.c_int(n), xs, ranks, names_pp, lens_pp, C.c_int(len(out_names)), on, ol, None, C.byref(ed), el)
+    if rc == ORC_ERR_INCONSISTENT:
+        raise InconsistentDimensionLengthError(ed.value.decode(), [None if v < 0 else int(v) for v in el])
+    _check(rc)
+    out = np.zeros([ol[i] for i in range(len(out_names))], dtype=arrays[0].dtype)
+    rc = f(C.c_int(n), xs, ranks, names_pp, lens_pp, C.c_int(len(out_names)), on, ol, _p(out), C.byref(ed), el)
+    _check(rc)
+    return out
+
+
 def vector_dot(a, a_name, b, b_name):
     s, ct = _sfx(a.dtype)
     out = ct()

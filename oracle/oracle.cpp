@@ -307,6 +307,71 @@ int einsum2(const T* a, int da, const char* const* an, const int64_t* al, const 
     return ORC_OK;
 }
 
+// Einsum1::to / Einsum3..6::to, src/tensors/einsum.rs:829-883 and :1019-1666: the same loop nest over n_ops
+// inputs; the term is the left-associated product ((p1 * p2) * p3) ..., each multiply separately rounded.
+template <class T>
+int einsum_n(int n_ops, const T* const* x, const int* ranks, const char* const* const* names,
+             const int64_t* const* lens, int dout, const char* const* on, int64_t* out_len, T* out,
+             const char** err_dim, int64_t* err_len) {
+    std::vector<std::vector<Dim>> in(n_ops);
+    for (int i = 0; i < n_ops; i++)
+        for (int d = 0; d < ranks[i]; d++) in[i].push_back({names[i][d], lens[i][d]});
+    std::vector<const char*> onames(on, on + dout);
+    std::vector<Dim> oshape;
+    for (int o = 0; o < dout; o++) {
+        int64_t len = 0;
+        int rc = length_of(on[o], in, &len, err_len);
+        if (rc != ORC_OK) {
+            if (err_dim) *err_dim = on[o];
+            return rc;
+        }
+        oshape.push_back({on[o], len});
+        if (out_len) out_len[o] = len;
+    }
+    std::vector<Dim> sum;
+    const char* ed = nullptr;
+    int rc = summation_dimensions(in, onames, &sum, &ed, err_len);
+    if (rc != ORC_OK) {
+        if (err_dim) *err_dim = ed;
+        return rc;
+    }
+    if (!out) return ORC_OK;
+    int64_t total = 1;
+    for (auto& d : oshape) total *= d.len;
+    if (total == 0) return ORC_OK;
+    bool sum_valid = true;
+    for (auto& sd : sum)
+        if (sd.len == 0) sum_valid = false;
+    std::vector<std::vector<int64_t>> strides;
+    for (int i = 0; i < n_ops; i++) strides.push_back(row_major_strides(in[i]));
+    std::vector<int64_t> oidx(dout, 0);
+    int64_t flat = 0;
+    auto term = [&](const std::vector<int64_t>& sidx) {
+        T p = x[0][input_offset(in[0], strides[0], oshape, oidx, sum, sidx)];
+        for (int i = 1; i < n_ops; i++) {
+            T q = x[i][input_offset(in[i], strides[i], oshape, oidx, sum, sidx)];
+            p = p * q;
+        }
+        return p;
+    };
+    do {
+        T acc = T(0);
+        if (sum.empty()) {
+            std::vector<int64_t> none;
+            T p = term(none);
+            acc = acc + p;
+        } else if (sum_valid) {
+            std::vector<int64_t> sidx(sum.size(), 0);
+            do {
+                T p = term(sidx);
+                acc = acc + p;
+            } while (advance(sidx, sum));
+        }
+        out[flat++] = acc;
+    } while (dout > 0 && advance(oidx, oshape));
+    return ORC_OK;
+}
+
 // ---- A5 -----------------------------------------------------------------------------------
 template <class T>
 int vector_dot(const T* a, const char* an, int64_t al, const T* b, const char* bn, int64_t bl, T* out) {
@@ -570,6 +635,16 @@ int orc_tensor_mul_f64(const double* a, const char* const* an, const int64_t* al
     return tensor_mul<double>(a, an, al, b, bn, bl, c, on);
 }
 
+int orc_einsum_n_f32(int n_ops, const float* const* x, const int* ranks, const char* const* const* names,
+                     const int64_t* const* lens, int dout, const char* const* on, int64_t* out_len, float* out,
+                     const char** err_dim, int64_t* err_len) {
+    return einsum_n<float>(n_ops, x, ranks, names, lens, dout, on, out_len, out, err_dim, err_len);
+}
+int orc_einsum_n_f64(int n_ops, const double* const* x, const int* ranks, const char* const* const* names,
+                     const int64_t* const* lens, int dout, const char* const* on, int64_t* out_len, double* out,
+                     const char** err_dim, int64_t* err_len) {
+    return einsum_n<double>(n_ops, x, ranks, names, lens, dout, on, out_len, out, err_dim, err_len);
+}
 int orc_einsum2_f32(const float* a, int da, const char* const* an, const int64_t* al, const float* b, int db,
                     const char* const* bn, const int64_t* bl, int dout, const char* const* on, int64_t* ol,
                     float* out, const char** ed, int64_t* el) {

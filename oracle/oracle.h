@@ -66,6 +66,15 @@ int orc_einsum2_f64(const double* a, int da, const char* const* a_names, const i
                     const char* const* out_names, int64_t* out_len, double* out, const char** err_dim,
                     int64_t* err_len);
 
+/* Next row: Einsum1::to and Einsum3..6::to, src/tensors/einsum.rs:829-883, :1019-1666.
+ * n_ops contiguous row-major inputs; err_len has n_ops entries. */
+int orc_einsum_n_f32(int n_ops, const float* const* x, const int* ranks, const char* const* const* names,
+                     const int64_t* const* lens, int dout, const char* const* out_names, int64_t* out_len, float* out,
+                     const char** err_dim, int64_t* err_len);
+int orc_einsum_n_f64(int n_ops, const double* const* x, const int* ranks, const char* const* const* names,
+                     const int64_t* const* lens, int dout, const char* const* out_names, int64_t* out_len, double* out,
+                     const char** err_dim, int64_t* err_len);
+
 /* A5: Tensor<T,1>::scalar_product, src/tensors/mod.rs:1773 -> operations.rs:1773-1808 */
 int orc_vector_dot_f32(const float* a, const char* a_name, int64_t a_len, const float* b, const char* b_name,
                        int64_t b_len, float* out);

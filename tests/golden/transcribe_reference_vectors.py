@@ -156,6 +156,52 @@ V["covariance"] = [
      "expect": [[0.142, -0.226, 0.026], [-0.226, 0.438, -0.022], [0.026, -0.022, 0.020]], "exact": False,
      "decimals": 3}]
 
+# ---- next row: one-operand and 3..6-operand einsum --------------------------------
+def from_fn(shape, f):  # Tensor::from_fn over a row-major index walk
+    import itertools
+    import functools
+    flat = [float(f(*ix)) for ix in itertools.product(*[range(n) for n in shape])]
+    def nest(vals, dims):
+        if len(dims) == 1:
+            return vals
+        step = functools.reduce(lambda a, b: a * b, dims[1:], 1)
+        return [nest(vals[i * step:(i + 1) * step], dims[1:]) for i in range(dims[0])]
+    return nest(flat, list(shape))
+
+
+W_ = from_fn((4, 2), lambda w, x: w * 2 + x)            # tests/einsum.rs:232, 254, 283, 312
+X_ = from_fn((2, 3), lambda x, y: x * 3 + y)
+Y_ = from_fn((2, 3, 2), lambda x, y, z: x * 6 + y * 2 + z)
+Z_ = from_fn((4, 2), lambda w, z: w * 2 + z)
+NEGX_ = from_fn((2, 3), lambda x, y: -(x * 3 + y))
+V["einsum_n"] = [
+    {"cite": "tests/einsum.rs:13-27 (transpose ab->ba == index_by([b, a]))", "operands": [randomish((3, 2))],
+     "names": [["a", "b"]], "out_names": ["b", "a"], "equiv": "x0.T"},
+    {"cite": "tests/einsum.rs:29-37 (summation ab-> == iter().sum())", "operands": [randomish((2, 3))],
+     "names": [["a", "b"]], "out_names": [], "equiv": "sequential_sum(x0)"},
+    {"cite": "tests/einsum.rs:39-47 (column_sum ab->b)", "operands": [randomish((3, 2))], "names": [["a", "b"]],
+     "out_names": ["b"], "equiv": "x0.sum(axis=0)"},
+    {"cite": "tests/einsum.rs:49-57 (row_sum ab->a)", "operands": [randomish((3, 2))], "names": [["a", "b"]],
+     "out_names": ["a"], "equiv": "x0.sum(axis=1)"},
+    {"cite": "tests/einsum.rs:208-226 (ab,cb,bd->ac)", "operands": [randomish((2, 3)), randomish((2, 3)), randomish((3, 4))],
+     "names": [["a", "b"], ["c", "b"], ["b", "d"]], "out_names": ["a", "c"],
+     "expect": [[33600.0, 35600.0], [35600.0, 37792.0]]},
+    {"cite": "tests/einsum.rs:228-247 (wx,xy,xyz,wz->xz)", "operands": [W_, X_, Y_, Z_],
+     "names": [["w", "x"], ["x", "y"], ["x", "y", "z"], ["w", "z"]], "out_names": ["x", "z"],
+     "expect": [[560.0, 884.0], [6800.0, 9408.0]]},
+    {"cite": "tests/einsum.rs:249-275 (wx,xy,xyz,wz,zyx->xz with .named)", "operands": [W_, X_, Y_, Z_, Y_],
+     "names": [["w", "x"], ["x", "y"], ["x", "y", "z"], ["w", "z"], ["z", "y", "x"]], "out_names": ["x", "z"],
+     "expect": [[2016.0, 8432.0], [24752.0, 90384.0]]},
+    {"cite": "tests/einsum.rs:277-304 (wx,xy,xyz,wz,xyz,xy->xyz)", "operands": [W_, X_, Y_, Z_, Y_, NEGX_],
+     "names": [["w", "x"], ["x", "y"], ["x", "y", "z"], ["w", "z"], ["x", "y", "z"], ["x", "y"]],
+     "out_names": ["x", "y", "z"],
+     "expect": [[[0.0, 0.0], [-224.0, -612.0], [-3584.0, -6800.0]],
+                [[-22032.0, -37044.0], [-69632.0, -108864.0], [-170000.0, -254100.0]]]},
+    {"cite": "tests/einsum.rs:306-319 (wx,xy,xyz,wz,xyz,xy->)", "operands": [W_, X_, Y_, Z_, Y_, NEGX_],
+     "names": [["w", "x"], ["x", "y"], ["x", "y", "z"], ["w", "z"], ["x", "y", "z"], ["x", "y"]], "out_names": [],
+     "expect": -672892.0},
+]
+
 out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_vectors.json")
 with open(out, "w") as f:
     json.dump(V, f, indent=1)

@@ -606,3 +606,33 @@ def test_concurrent_host_calls_from_threads(orc):
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+# ------------------------------------------------------------------ next row: 1 and 3..6 operand einsum
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_einsum_n_reference_goldens_and_oracle(orc, golden, dtype):
+    from test_oracle_golden import _einsum_n_expected
+
+    withs = {1: eml.Einsum.with_1, 3: eml.Einsum.with_3, 4: eml.Einsum.with_4, 5: eml.Einsum.with_5, 6: eml.Einsum.with_6}
+    for g in golden["einsum_n"]:
+        ops, want = _einsum_n_expected(g, dtype)
+        tensors = [eml.Tensor(list(zip(nm, o.shape)), o) for nm, o in zip(g["names"], ops)]
+        got = withs[len(ops)](*tensors).to(g["out_names"])
+        assert got.names() == g["out_names"] and np.array_equal(got.data, want), g["cite"]
+        assert eml.last_kernel() == "einsum_generic"
+    # random data, every arity: bit-exact with the oracle's restatement of the reference loop nest
+    r = rng(1700)
+    a, b, c = uniform(r, (5, 7), dtype), uniform(r, (7, 4, 3), dtype), uniform(r, (3, 5), dtype)
+    d, e, f = uniform(r, (4, 6), dtype), uniform(r, (6,), dtype), uniform(r, (5, 6), dtype)
+    cases = [([a], [["i", "j"]], ["j", "i"]), ([b], [["j", "k", "l"]], ["l"]),
+             ([a, b, c], [["i", "j"], ["j", "k", "l"], ["l", "i"]], ["i", "k"]),
+             ([a, b, c, d], [["i", "j"], ["j", "k", "l"], ["l", "i"], ["k", "m"]], ["m"]),
+             ([a, b, c, d, e], [["i", "j"], ["j", "k", "l"], ["l", "i"], ["k", "m"], ["m"]], []),
+             ([a, b, c, d, e, f], [["i", "j"], ["j", "k", "l"], ["l", "i"], ["k", "m"], ["m"], ["i", "m"]], ["k", "i"])]
+    for ops, names, out in cases:
+        tensors = [eml.Tensor(list(zip(nm, o.shape)), o) for nm, o in zip(names, ops)]
+        got = withs[len(ops)](*tensors).to(out)
+        assert np.array_equal(got.data, orc.einsum_n(ops, names, out)), (names, out)
+    with pytest.raises(eml.InconsistentDimensionLengthError):
+        eml.Einsum.with_3(eml.Tensor([("a", 2), ("b", 3)], a[:2, :3]), eml.Tensor([("b", 4), ("c", 2)], a[:4, :2]),
+                          eml.Tensor([("c", 2), ("d", 2)], a[:2, :2])).to(["a", "d"])

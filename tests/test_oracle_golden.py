@@ -223,3 +223,28 @@ def test_covariance_goldens(orc, golden, dtype):
             assert np.array_equal(np.round(got.astype(np.float64), g["decimals"]), np.array(g["expect"])), g["cite"]
         # row-features form of the same data
         assert np.array_equal(orc.covariance(np.ascontiguousarray(x.T), 1 - g["feature_axis"]), got)
+
+
+def _einsum_n_expected(g, dtype):
+    ops = [np.array(o, dtype) for o in g["operands"]]
+    if "expect" in g:
+        return ops, np.array(g["expect"], dtype)
+    x0 = ops[0]
+    if g["equiv"] == "sequential_sum(x0)":
+        acc = dtype(0)
+        for v in x0.reshape(-1):
+            acc = dtype(acc + v)
+        return ops, np.array(acc, dtype)
+    return ops, np.ascontiguousarray(eval(g["equiv"], {"x0": x0})).astype(dtype)  # small integers: exact
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_einsum_n_goldens(orc, golden, dtype):
+    """Next row: Einsum1 and Einsum3..6 against the literal expectations of tests/einsum.rs."""
+    for g in golden["einsum_n"]:
+        ops, want = _einsum_n_expected(g, dtype)
+        got = orc.einsum_n(ops, g["names"], g["out_names"])
+        assert got.shape == want.shape and np.array_equal(got, want), g["cite"]
+    with pytest.raises(orc.InconsistentDimensionLengthError):
+        orc.einsum_n([np.zeros((2, 3), dtype), np.zeros((4, 2), dtype), np.zeros((2, 2), dtype)],
+                     [["a", "b"], ["b", "c"], ["c", "d"]], ["a", "d"])
