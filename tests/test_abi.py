@@ -99,3 +99,30 @@ def test_einsum_errors_match_oracle(orc):
 def test_non_float_types_are_not_this_paths_business():
     with pytest.raises(TypeError):
         eml.host._sfx(np.int32)
+
+
+def test_rust_ffi_bindings_are_generated_from_the_header():
+    """easy-ml_b200/rust/src/cuda/ffi.rs (the `cuda` feature's raw bindings) is generated from include/easyml_b200.h:
+    the committed file must be up to date and declare every symbol the header does."""
+    import importlib.util
+    import re
+
+    gen_path = os.path.join(ROOT, "easy-ml_b200", "rust", "gen_ffi.py")
+    spec = importlib.util.spec_from_file_location("gen_ffi", gen_path)
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    committed = open(gen.OUT).read()
+    header = open(os.path.join(ROOT, "include", "easyml_b200.h")).read()
+    protos = list(gen.prototypes(header))
+    assert len(protos) >= 70
+    for _, name, _ in protos:
+        assert re.search(rf"pub fn {name}\(", committed), f"{name} missing from ffi.rs"
+    out = gen.OUT
+    try:
+        gen.OUT = out + ".check"
+        gen.main()
+        assert open(gen.OUT).read() == committed, "ffi.rs is stale: run python easy-ml_b200/rust/gen_ffi.py"
+    finally:
+        if os.path.exists(out + ".check"):
+            os.remove(out + ".check")
+        gen.OUT = out
