@@ -69,6 +69,9 @@ struct SplitK<float> {
 template <class T>
 int contract_dev(DeviceCtx* ctx, const T* A, const T* B, T* C, int64_t batch, int64_t M, int64_t N, int64_t K,
                  Strides3 sA, Strides3 sB, Strides3 sC, bool accumulate, bool exact, cudaStream_t stream) {
+    // pack-cache hints belong to THIS call only: take them now, hand them to the f32 tensor-core kernel below
+    uint64_t id_a = 0, id_b = 0;
+    take_pack_identity(&id_a, &id_b);
     // Deterministic split-K for outputs with too few tiles for 148 SMs and a long K (the loss reduction
     // L[1 x batch] * d[batch x 10], dW2 = H^T[512 x batch] * dY[batch x 10], ...): K is cut into S equal
     // chunks which run as S "batches" of one launch into a workspace [S][M][N]; a fixed-order reduction
@@ -102,16 +105,19 @@ int contract_dev(DeviceCtx* ctx, const T* A, const T* B, T* C, int64_t batch, in
     if (!exact && Threshold<T>::tensor_core(M, N, K)) {
         // the tensor-core kernels want C's column index contiguous; a row-contiguous C is the transposed
         // problem C^T = B^T A^T with the same kernels
+        bool handled = false;
+        int rc;
         if (sC.c != 1 && sC.r == 1) {
+            set_pack_identity(id_b, id_a);  // the operands swap roles in the transposed problem
             Strides3 tA{sB.b, sB.c, sB.r}, tB{sA.b, sA.c, sA.r}, tC{sC.b, sC.c, sC.r};
-            bool handled = false;
-            EML_TRY(tensor_core_path<T>(ctx, B, A, C, batch, N, M, K, tA, tB, tC, accumulate, stream, &handled));
-            if (handled) return EML_OK;
+            rc = tensor_core_path<T>(ctx, B, A, C, batch, N, M, K, tA, tB, tC, accumulate, stream, &handled);
         } else {
-            bool handled = false;
-            EML_TRY(tensor_core_path<T>(ctx, A, B, C, batch, M, N, K, sA, sB, sC, accumulate, stream, &handled));
-            if (handled) return EML_OK;
+            set_pack_identity(id_a, id_b);
+            rc = tensor_core_path<T>(ctx, A, B, C, batch, M, N, K, sA, sB, sC, accumulate, stream, &handled);
         }
+        take_pack_identity(&id_a, &id_b);  // whatever the kernel did not consume must not leak into a later call
+        EML_TRY(rc);
+        if (handled) return EML_OK;
     }
     if (!exact && N <= 16 && sA.c == 1 && M >= 256 && K >= 64)
         return launch_gemm_skinny<T>(A, B, C, batch, M, N, K, sA, sB, sC, accumulate, stream);

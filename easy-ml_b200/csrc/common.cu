@@ -185,6 +185,7 @@ int stage_buffer(DeviceCtx* ctx, int slot, size_t bytes, void** out) {
 }
 
 void shutdown_all() {
+    pack_cache_release_all();
     stream_cache_release_all();
     std::lock_guard<std::mutex> lock(g_ctx_mu);
     for (auto& kv : g_ctx) {

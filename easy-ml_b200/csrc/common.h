@@ -119,6 +119,17 @@ void set_remote_c(double* const* ptrs, int n);
 bool remote_c_pending();
 void clear_remote_c();
 
+// Split/pack cache of the f32 tensor-core GEMM.  An operand whose contents never change (a constant record
+// container: the NN's inputs) is identified by a non-zero id; its packed TF32 planes are then kept and reused by
+// later calls with the same id, shape and strides (the NN step packs X twice per step otherwise).  The ids are
+// thread-local hints consumed by the NEXT contract_dev call on this thread; pack_cache_drop forgets an id when its
+// buffer dies.
+uint64_t new_buffer_identity();
+void set_pack_identity(uint64_t a_id, uint64_t b_id);
+void take_pack_identity(uint64_t* a_id, uint64_t* b_id);  // reads and clears
+void pack_cache_drop(uint64_t id);
+void pack_cache_release_all();
+
 // f32 3xTF32 on tcgen05 + TMEM, operands staged by TMA (pack kernel splits into big/small parts).
 int launch_gemm_tf32x3_f32(DeviceCtx* ctx, const float* A, const float* B, float* C, int64_t batch, int64_t M,
                            int64_t N, int64_t K, Strides3 sA, Strides3 sB, Strides3 sC, bool accumulate,

@@ -6,6 +6,10 @@
 // exp/ln/sin/cos/pow differ from Rust's libm by the usual ulp or two (tolerance stated in the tests).
 #include <type_traits>
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "common.h"
 
 namespace eml {
@@ -186,12 +190,19 @@ __device__ __forceinline__ T block_reduce(T v, T* smem) {
     return total;  // valid in thread 0
 }
 
-// stage 1: block b sums elements [b*chunk, min(n,(b+1)*chunk)) of x[i*incx] * (y ? y[i*incy] : 1)
+// Single-pass deterministic reductions.  Every block writes its partial, takes a ticket from a per-stream counter
+// (atomicInc wraps to zero on the last ticket, so the counter resets itself), and the block that drew the last
+// ticket adds the partials in index order.  The atomic only elects that block; the sum order is fixed, so the
+// result is bit-identical run to run.  One launch instead of two.
+constexpr int MAX_TICKETS = 4096;
+
+// block b sums elements [b*chunk, min(n,(b+1)*chunk)) of x[i*incx] * (y ? y[i*incy] : 1); last block: out (+)= total
 template <class T>
 __global__ void __launch_bounds__(RED_THREADS)
-reduce_stage1(const T* __restrict__ x, int64_t incx, const T* __restrict__ y, int64_t incy, int64_t n,
-              int64_t chunk, T* __restrict__ partials) {
+reduce_kernel(const T* __restrict__ x, int64_t incx, const T* __restrict__ y, int64_t incy, int64_t n, int64_t chunk,
+              T* partials, unsigned* ticket, T* out, int accumulate) {
     __shared__ T smem[RED_THREADS / 32];
+    __shared__ bool last;
     int64_t lo = (int64_t)blockIdx.x * chunk, hi = lo + chunk < n ? lo + chunk : n;
     T acc = T(0);
     for (int64_t i = lo + threadIdx.x; i < hi; i += RED_THREADS) {
@@ -200,17 +211,38 @@ reduce_stage1(const T* __restrict__ x, int64_t incx, const T* __restrict__ y, in
         acc += v;
     }
     T total = block_reduce<T>(acc, smem);
-    if (threadIdx.x == 0) partials[blockIdx.x] = total;
+    if (threadIdx.x == 0) {
+        partials[blockIdx.x] = total;
+        __threadfence();
+        last = atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    acc = T(0);
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += RED_THREADS) acc += __ldcg(partials + i);
+    total = block_reduce<T>(acc, smem);
+    if (threadIdx.x == 0) out[0] = accumulate ? out[0] + total : total;
 }
 
-template <class T>
-__global__ void __launch_bounds__(RED_THREADS)
-reduce_stage2(const T* __restrict__ partials, int count, T* __restrict__ out, int accumulate) {
-    __shared__ T smem[RED_THREADS / 32];
-    T acc = T(0);
-    for (int i = threadIdx.x; i < count; i += RED_THREADS) acc += partials[i];
-    T total = block_reduce<T>(acc, smem);
-    if (threadIdx.x == 0) out[0] = accumulate ? out[0] + total : total;
+// zero-initialised, self-resetting ticket counters, one array per (device, stream): reductions on one stream are
+// ordered, so they can share it
+int ticket_counters(cudaStream_t stream, unsigned** out) {
+    static std::mutex mu;
+    static std::map<std::pair<int, cudaStream_t>, unsigned*> table;
+    int dev = 0;
+    EML_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    auto key = std::make_pair(dev, stream);
+    auto it = table.find(key);
+    if (it == table.end()) {
+        unsigned* p = nullptr;
+        EML_CUDA(cudaMalloc(&p, sizeof(unsigned) * MAX_TICKETS));
+        EML_CUDA(cudaMemset(p, 0, sizeof(unsigned) * MAX_TICKETS));
+        it = table.emplace(key, p).first;
+    }
+    *out = it->second;
+    return EML_OK;
 }
 
 template <class T>
@@ -222,17 +254,22 @@ int reduce_impl(const T* x, int64_t incx, const T* y, int64_t incy, int64_t n, T
     int64_t chunk = (n + blocks - 1) / blocks;
     TempBuf partials;
     EML_TRY(partials.alloc(sizeof(T) * blocks, stream));
-    reduce_stage1<T><<<blocks, RED_THREADS, 0, stream>>>(x, incx, y, incy, n, chunk, partials.as<T>());
-    reduce_stage2<T><<<1, RED_THREADS, 0, stream>>>(partials.as<T>(), blocks, out, accumulate ? 1 : 0);
-    count_launch(2);
+    unsigned* ticket = nullptr;
+    EML_TRY(ticket_counters(stream, &ticket));
+    reduce_kernel<T><<<blocks, RED_THREADS, 0, stream>>>(x, incx, y, incy, n, chunk, partials.as<T>(), ticket, out,
+                                                         accumulate ? 1 : 0);
+    count_launch();
     return check_launch("reduce");
 }
 
-// column sums: partial[chunk][c] = sum over the chunk's rows, then a fixed-order sum over chunks
+// column sums: partial[chunk][c] = sum over the chunk's rows; the last chunk-block of a column block adds the
+// chunks in index order
 template <class T>
 __global__ void __launch_bounds__(256)
-col_sums_stage1(const T* __restrict__ x, int64_t rows, int64_t cols, int64_t rows_per_chunk, T* __restrict__ partial) {
+col_sums_kernel(const T* __restrict__ x, int64_t rows, int64_t cols, int64_t rows_per_chunk, T* partial,
+                unsigned* tickets, T* __restrict__ out) {
     __shared__ T smem[8][33];
+    __shared__ bool last;
     int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     int64_t c = (int64_t)blockIdx.x * 32 + tx;
     int64_t r0 = (int64_t)blockIdx.y * rows_per_chunk, r1 = r0 + rows_per_chunk < rows ? r0 + rows_per_chunk : rows;
@@ -246,14 +283,17 @@ col_sums_stage1(const T* __restrict__ x, int64_t rows, int64_t cols, int64_t row
         for (int i = 0; i < 8; i++) t += smem[i][tx];
         partial[(int64_t)blockIdx.y * cols + c] = t;
     }
-}
-template <class T>
-__global__ void col_sums_stage2(const T* __restrict__ partial, int chunks, int64_t cols, T* __restrict__ out) {
-    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= cols) return;
-    T t = T(0);
-    for (int i = 0; i < chunks; i++) t += partial[(int64_t)i * cols + c];
-    out[c] = t;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicInc(tickets + blockIdx.x, gridDim.y - 1) == gridDim.y - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    if (ty == 0 && c < cols) {
+        T t = T(0);
+        for (int i = 0; i < (int)gridDim.y; i++) t += __ldcg(partial + (int64_t)i * cols + c);
+        out[c] = t;
+    }
 }
 
 template <class T>
@@ -483,9 +523,11 @@ int launch_col_sums(const T* x, int64_t rows, int64_t cols, T* out, cudaStream_t
     TempBuf partial;
     EML_TRY(partial.alloc(sizeof(T) * chunks * cols, stream));
     dim3 grid((unsigned)((cols + 31) / 32), (unsigned)chunks);
-    col_sums_stage1<T><<<grid, 256, 0, stream>>>(x, rows, cols, rpc, partial.as<T>());
-    col_sums_stage2<T><<<(unsigned)((cols + 127) / 128), 128, 0, stream>>>(partial.as<T>(), chunks, cols, out);
-    count_launch(2);
+    if (grid.x > (unsigned)MAX_TICKETS) EML_BAD_ARG("col_sums: more than %d column blocks", MAX_TICKETS);
+    unsigned* tickets = nullptr;
+    EML_TRY(ticket_counters(stream, &tickets));
+    col_sums_kernel<T><<<grid, 256, 0, stream>>>(x, rows, cols, rpc, partial.as<T>(), tickets, out);
+    count_launch();
     return check_launch("col_sums");
 }
 

@@ -24,8 +24,13 @@
 // Determinism: fixed tile -> CTA map, fixed k order inside a CTA, fixed split order in the reduction.
 // Algorithmic work per launch: 2*M*N*K flop (the 3x tensor work is an implementation cost, not counted);
 // bytes (M*K + K*N + M*N) * 4.
+#include <atomic>
 #include <cstdlib>
+#include <deque>
+#include <map>
+#include <mutex>
 #include <string>
+#include <tuple>
 
 #include "common.h"
 #include "sm100.cuh"
@@ -625,6 +630,113 @@ int launch_tile(const Maps& maps, float* C, int64_t batch, int64_t M, int64_t N,
 
 }  // namespace
 
+// ------------------------------------------------------------------------------------------------
+// split/pack cache for immutable operands (see common.h)
+// ------------------------------------------------------------------------------------------------
+namespace {
+thread_local uint64_t t_pack_id[2] = {0, 0};
+std::atomic<uint64_t> g_next_identity{1};
+
+struct PackKey {
+    uint64_t id;
+    int device;
+    cudaStream_t stream;
+    int64_t mn, k, mnp, kp, batch, sb, smn, sk;
+    bool operator<(const PackKey& o) const {
+        return std::tie(id, device, stream, mn, k, mnp, kp, batch, sb, smn, sk) <
+               std::tie(o.id, o.device, o.stream, o.mn, o.k, o.mnp, o.kp, o.batch, o.sb, o.smn, o.sk);
+    }
+};
+struct PackEntry {
+    float* planes;  // big plane followed by the small plane
+    size_t bytes;
+};
+std::mutex g_pack_mu;
+std::map<PackKey, PackEntry> g_pack;
+std::deque<PackKey> g_pack_order;  // insertion order, for eviction
+size_t g_pack_bytes = 0;
+constexpr size_t PACK_CACHE_LIMIT = size_t(4) << 30;
+
+void pack_evict_locked(const PackKey& key) {
+    auto it = g_pack.find(key);
+    if (it == g_pack.end()) return;
+    stream_free(it->second.planes, it->second.bytes, key.stream);
+    g_pack_bytes -= it->second.bytes;
+    g_pack.erase(it);
+}
+
+// big / small planes of one operand: from the cache when `id` is set (packing on a miss), else into `scratch`
+int packed_operand(uint64_t id, const float* src, int64_t batch, int64_t MN, int64_t K, int64_t MNp, int64_t Kp,
+                   int64_t sb, int64_t smn, int64_t sk, TempBuf& scratch, cudaStream_t stream, float** big,
+                   float** small) {
+    const size_t plane = (size_t)(batch * MNp * Kp);
+    const size_t bytes = sizeof(float) * 2 * plane;
+    if (id == 0) {
+        EML_TRY(scratch.alloc(bytes, stream));
+        *big = scratch.as<float>();
+        *small = *big + plane;
+        return launch_split_pack(src, *big, *small, batch, MN, K, MNp, Kp, sb, smn, sk, stream);
+    }
+    int dev = 0;
+    EML_CUDA(cudaGetDevice(&dev));
+    PackKey key{id, dev, stream, MN, K, MNp, Kp, batch, sb, smn, sk};
+    {
+        std::lock_guard<std::mutex> lock(g_pack_mu);
+        auto it = g_pack.find(key);
+        if (it != g_pack.end()) {
+            *big = it->second.planes;
+            *small = *big + plane;
+            return EML_OK;
+        }
+    }
+    void* p = nullptr;
+    EML_TRY(stream_alloc(&p, bytes, stream));
+    *big = static_cast<float*>(p);
+    *small = *big + plane;
+    EML_TRY(launch_split_pack(src, *big, *small, batch, MN, K, MNp, Kp, sb, smn, sk, stream));
+    std::lock_guard<std::mutex> lock(g_pack_mu);
+    while (g_pack_bytes + bytes > PACK_CACHE_LIMIT && !g_pack_order.empty()) {
+        pack_evict_locked(g_pack_order.front());
+        g_pack_order.pop_front();
+    }
+    g_pack[key] = PackEntry{*big, bytes};
+    g_pack_order.push_back(key);
+    g_pack_bytes += bytes;
+    return EML_OK;
+}
+}  // namespace
+
+uint64_t new_buffer_identity() { return g_next_identity.fetch_add(1); }
+void set_pack_identity(uint64_t a_id, uint64_t b_id) {
+    t_pack_id[0] = a_id;
+    t_pack_id[1] = b_id;
+}
+void take_pack_identity(uint64_t* a_id, uint64_t* b_id) {
+    *a_id = t_pack_id[0];
+    *b_id = t_pack_id[1];
+    t_pack_id[0] = t_pack_id[1] = 0;
+}
+void pack_cache_drop(uint64_t id) {
+    if (!id) return;
+    std::lock_guard<std::mutex> lock(g_pack_mu);
+    for (auto it = g_pack.begin(); it != g_pack.end();) {
+        if (it->first.id == id) {
+            stream_free(it->second.planes, it->second.bytes, it->first.stream);
+            g_pack_bytes -= it->second.bytes;
+            it = g_pack.erase(it);
+        } else {
+            ++it;
+        }
+    }
+}
+void pack_cache_release_all() {
+    std::lock_guard<std::mutex> lock(g_pack_mu);
+    for (auto& kv : g_pack) stream_free(kv.second.planes, kv.second.bytes, kv.first.stream);
+    g_pack.clear();
+    g_pack_order.clear();
+    g_pack_bytes = 0;
+}
+
 int launch_gemm_tf32x3_f32(DeviceCtx* ctx, const float* A, const float* B, float* C, int64_t batch, int64_t M,
                            int64_t N, int64_t K, Strides3 sA, Strides3 sB, Strides3 sC, bool accumulate,
                            cudaStream_t stream, bool* handled) {
@@ -675,22 +787,18 @@ int launch_gemm_tf32x3_f32(DeviceCtx* ctx, const float* A, const float* B, float
         Np = round_up(N, BN);
     }
 
-    TempBuf packed, wsbuf;
-    const int64_t a_plane = batch * Mp * Kp, b_plane = batch * Np * Kp;
-    EML_TRY(packed.alloc(sizeof(float) * 2 * (size_t)(a_plane + b_plane), stream));
-    float* a_big = packed.as<float>();
-    float* a_small = a_big + a_plane;
-    float* b_big = a_small + a_plane;
-    float* b_small = b_big + b_plane;
+    uint64_t a_id = 0, b_id = 0;
+    take_pack_identity(&a_id, &b_id);
+    TempBuf a_scratch, b_scratch, wsbuf;
+    float *a_big, *a_small, *b_big, *b_small;
+    EML_TRY(packed_operand(a_id, A, batch, M, K, Mp, Kp, sA.b, sA.r, sA.c, a_scratch, stream, &a_big, &a_small));
+    // B element (k, n) at B[k*sB.r + n*sB.c]: its "mn" index is n
+    EML_TRY(packed_operand(b_id, B, batch, N, K, Np, Kp, sB.b, sB.c, sB.r, b_scratch, stream, &b_big, &b_small));
     float* ws = nullptr;
     if (splits > 1) {
         EML_TRY(wsbuf.alloc(sizeof(float) * (size_t)splits * (size_t)(batch * M * N), stream));
         ws = wsbuf.as<float>();
     }
-
-    EML_TRY(launch_split_pack(A, a_big, a_small, batch, M, K, Mp, Kp, sA.b, sA.r, sA.c, stream));
-    // B element (k, n) at B[k*sB.r + n*sB.c]: its "mn" index is n
-    EML_TRY(launch_split_pack(B, b_big, b_small, batch, N, K, Np, Kp, sB.b, sB.c, sB.r, stream));
 
     Maps maps;
     const int b_box = use_pair ? pair::HALF : BN;  // rows of B one TMA box brings in

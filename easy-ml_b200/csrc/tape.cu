@@ -23,7 +23,9 @@ struct DevBuf {
     size_t bytes = 0;
     cudaStream_t s = nullptr;
     std::shared_ptr<DevBuf> parent;  // set for a view into another buffer (the view owns nothing)
+    uint64_t identity = 0;           // non-zero: immutable constant whose packed TF32 planes may be cached
     ~DevBuf() {
+        if (identity) pack_cache_drop(identity);
         if (p && !parent) stream_free(p, bytes, s);
     }
 };
@@ -169,6 +171,9 @@ int new_container(eml_tape* t, const void* src, bool src_on_device, int64_t rows
     EML_CUDA(cudaMemcpyAsync(v.numbers->p, src, sizeof(T) * rows * cols,
                              src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, t->stream));
     if (!src_on_device) EML_CUDA(cudaStreamSynchronize(t->stream));  // the host buffer is the caller's
+    // numbers of a container are never modified in place (operators and the SGD update produce fresh containers);
+    // constants typically live across many steps, so their split/packed planes are worth keeping
+    if (!variables) v.numbers->identity = new_buffer_identity();
     if (variables) {
         Node nd;
         nd.kind = Kind::VARIABLES;
@@ -203,6 +208,7 @@ int tape_matmul(eml_tape* t, eml_val ha, eml_val hb, eml_val* out) {
     c.rows = M;
     c.cols = N;
     EML_TRY(new_buf(sizeof(T) * M * N, t->stream, &c.numbers));
+    set_pack_identity(a->numbers->identity, b->numbers->identity);
     EML_TRY(contract_dev<T>(t->ctx, (const T*)a->numbers->p, (const T*)b->numbers->p, (T*)c.numbers->p, 1, M, N, K,
                             Strides3{0, K, 1}, Strides3{0, N, 1}, Strides3{0, N, 1}, false, false, t->stream));
     // history = lhs's else rhs's (reference container_operations.rs:1357-1361); with a history every
@@ -405,6 +411,7 @@ int tape_sweep(eml_tape* t, eml_val hv, int64_t row, int64_t col, eml_derivs** o
             const T* A = (const T*)nd.a->p;
             const T* B = (const T*)nd.b->p;
             if (nd.p0 >= 0) {
+                set_pack_identity(0, nd.b->identity);
                 EML_TRY(contract_dev<T>(t->ctx, g, B, (T*)d->grads[nd.p0]->p, 1, M, K, N, Strides3{0, N, 1},
                                         Strides3{0, 1, N}, Strides3{0, K, 1}, true, false, st));
             } else {
@@ -419,6 +426,7 @@ int tape_sweep(eml_tape* t, eml_val hv, int64_t row, int64_t col, eml_derivs** o
                 slot0_used = true;
             }
             if (nd.p1 >= 0) {
+                set_pack_identity(nd.a->identity, 0);
                 EML_TRY(contract_dev<T>(t->ctx, A, g, (T*)d->grads[nd.p1]->p, 1, K, N, M, Strides3{0, 1, K},
                                         Strides3{0, N, 1}, Strides3{0, N, 1}, true, false, st));
             } else {

@@ -636,3 +636,30 @@ def test_einsum_n_reference_goldens_and_oracle(orc, golden, dtype):
     with pytest.raises(eml.InconsistentDimensionLengthError):
         eml.Einsum.with_3(eml.Tensor([("a", 2), ("b", 3)], a[:2, :3]), eml.Tensor([("b", 4), ("c", 2)], a[:4, :2]),
                           eml.Tensor([("c", 2), ("d", 2)], a[:2, :2])).to(["a", "d"])
+
+
+def test_pack_cache_of_constants_follows_identity_not_address():
+    """Constant containers keep their split/packed TF32 planes across matmuls (the NN packs its inputs once, not
+    twice per step).  The cache is keyed by a buffer identity: a new constant that lands on a recycled address must
+    not see the previous one's planes, and repeated products must give the same bits."""
+    r = rng(2100)
+    hist = eml.WengertList(np.float32)
+    w = eml.RecordTensor.variables(hist, eml.Tensor([("k", 128), ("n", 160)], uniform(r, (128, 160), np.float32)))
+    results = []
+    for trial in range(3):
+        x = uniform(r, (1024, 128), np.float32)
+        X = eml.RecordTensor.constants(eml.Tensor([("m", 1024), ("k", 128)], x), hist)
+        first = (X * w).numbers().data
+        assert eml.last_kernel() == "tf32x3_tcgen05"
+        again = (X * w).numbers().data  # second product: planes of X come from the cache
+        assert np.array_equal(first, again)
+        want = x.astype(np.float64) @ w.numbers().data.astype(np.float64)
+        bound = 1e-5 * (np.abs(x).astype(np.float64) @ np.abs(w.numbers().data).astype(np.float64))
+        assert np.all(np.abs(first.astype(np.float64) - want) <= bound), trial
+        # backward through the cached operand as well: dW = X^T G
+        d = (X * w).derivatives_for([3, 5]).at_tensor(w).data
+        # (w[0, 0] is tape index 0, where the reference's constant-operand quirk parks the constant's would-be gradient)
+        assert np.allclose(d[:, 5], x[3], rtol=0, atol=1e-6) and np.count_nonzero(d[1:, :5]) == 0
+        results.append(first)
+        del X  # its buffer returns to the stream cache; the next constant reuses the address
+    assert not np.array_equal(results[0], results[1])
