@@ -524,8 +524,8 @@ def nn_steps(torch, eml, np, batch=8192, steps=5, warmup=3):
         diff = out - Y
         loss = ((L * diff.elementwise_multiply(diff)) * R) / float(batch)
         d = loss.derivatives_for([0, 0])
-        eml.sgd_update(W1, d, 0.5)
-        eml.sgd_update(W2, d, 0.5)
+        eml.sgd_update(W1, d, 0.05)
+        eml.sgd_update(W2, d, 0.05)
         losses.append(float(loss.numbers().data[0, 0]))  # D2H of the loss: the step's result
         hist.clear()
         W1.reset()

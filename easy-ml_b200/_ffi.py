@@ -84,6 +84,9 @@ SIGNATURES = {
     "eml_val_release": (cint, [vp, i64]),
     "eml_val_shape": (cint, [vp, i64, pi64, pi64, C.POINTER(cint)]),
     "eml_val_numbers": (cint, [vp, i64, vp]),
+    "eml_val_numbers_async": (cint, [vp, i64, vp, C.POINTER(vp)]),
+    "eml_arrival_wait": (cint, [vp]),
+    "eml_tape_sync": (cint, [vp]),
     "eml_val_indexes": (cint, [vp, i64, vp]),
     "eml_val_device_ptr": (cint, [vp, i64, C.POINTER(vp)]),
     "eml_tape_matmul": (cint, [vp, i64, i64, pi64]),

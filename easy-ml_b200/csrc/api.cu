@@ -72,6 +72,9 @@ int contract_dev(DeviceCtx* ctx, const T* A, const T* B, T* C, int64_t batch, in
     // pack-cache hints belong to THIS call only: take them now, hand them to the f32 tensor-core kernel below
     uint64_t id_a = 0, id_b = 0;
     take_pack_identity(&id_a, &id_b);
+    // tall-skinny A^T * B (N <= 16, A contiguous along m, long K): its own chunked kernel
+    if (!exact && batch == 1 && N >= 1 && N <= 16 && sA.r == 1 && sA.c != 1 && K >= 256 && M >= 32 && A && B && C)
+        return launch_gemm_skinny_tn<T>(ctx, A, B, C, M, N, K, sA, sB, sC, accumulate, stream);
     // Deterministic split-K for outputs with too few tiles for 148 SMs and a long K (the loss reduction
     // L[1 x batch] * d[batch x 10], dW2 = H^T[512 x batch] * dY[batch x 10], ...): K is cut into S equal
     // chunks which run as S "batches" of one launch into a workspace [S][M][N]; a fixed-order reduction

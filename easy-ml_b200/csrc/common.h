@@ -103,6 +103,11 @@ template <class T>
 int launch_gemm_skinny(const T* A, const T* B, T* C, int64_t batch, int64_t M, int64_t N, int64_t K, Strides3 sA,
                        Strides3 sB, Strides3 sC, bool accumulate, cudaStream_t stream);
 
+// N <= 16, A contiguous along m (A^T stored row-major), long K: per-k-chunk partials + fixed-order reduction
+template <class T>
+int launch_gemm_skinny_tn(DeviceCtx* ctx, const T* A, const T* B, T* C, int64_t M, int64_t N, int64_t K, Strides3 sA,
+                          Strides3 sB, Strides3 sC, bool accumulate, cudaStream_t stream);
+
 // f64 tensor-core (DMMA) kernel.  Returns EML_OK and sets *handled=false when the layout is not one it
 // supports (caller falls through to another GPU kernel).
 int launch_gemm_dmma_f64(DeviceCtx* ctx, const double* A, const double* B, double* C, int64_t batch, int64_t M,

@@ -156,7 +156,7 @@ int launch_gemm_simt(const T* A, const T* B, T* C, int64_t batch, int64_t M, int
 // over its k's and a fixed shuffle tree combines the 32 lanes -- deterministic, no atomics.
 // ------------------------------------------------------------------------------------------------
 namespace {
-constexpr int SK_NMAX = 16, SK_ROWS = 4, SK_WARPS = 16, SK_THREADS = SK_WARPS * 32;
+constexpr int SK_NMAX = 16, SK_ROWS = 8, SK_WARPS = 8, SK_THREADS = SK_WARPS * 32;
 
 template <class T>
 __global__ void __launch_bounds__(SK_THREADS)
@@ -184,17 +184,19 @@ gemm_skinny_kernel(const T* __restrict__ A, const T* __restrict__ B, T* C, int64
                 sBk[n][k] = Bb[(k0 + k) * sB.r + n * sB.c];
             }
             __syncthreads();
+            // the SK_ROWS rows of this warp advance together, so SK_ROWS independent loads are in flight per lane
+            // (a single row at a time is latency-bound: one dependent 128-byte load per 32 k)
+            for (int k = lane; k < kc; k += 32) {
+                T av[SK_ROWS];
 #pragma unroll
-            for (int r = 0; r < SK_ROWS; r++) {
-                const int64_t m = m0 + r;
-                if (m >= M) continue;
-                const T* a = Ab + m * sA.r + k0;
-                for (int k = lane; k < kc; k += 32) {
-                    const T av = a[k];
+                for (int r = 0; r < SK_ROWS; r++) av[r] = (m0 + r < M) ? Ab[(m0 + r) * sA.r + k0 + k] : T(0);
 #pragma unroll
-                    for (int n = 0; n < SK_NMAX; n++)
-                        if (n < N) acc[r][n] = fma(av, sBk[n][k], acc[r][n]);
-                }
+                for (int n = 0; n < SK_NMAX; n++)
+                    if (n < N) {
+                        const T bv = sBk[n][k];
+#pragma unroll
+                        for (int r = 0; r < SK_ROWS; r++) acc[r][n] = fma(av[r], bv, acc[r][n]);
+                    }
             }
         }
 #pragma unroll
@@ -214,6 +216,87 @@ gemm_skinny_kernel(const T* __restrict__ A, const T* __restrict__ B, T* C, int64
     }
 }
 }  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// Skinny-N GEMM with A contiguous along m (the NN's dW2 = H^T[512 x batch] * dY[batch x 10]): each thread owns one
+// output row m and N accumulators, a CTA walks one k chunk with coalesced loads of A[k][m..] (B's chunk sits in
+// shared memory), and the per-chunk partials are added in chunk order by the split-K reduction: deterministic.
+// ------------------------------------------------------------------------------------------------
+namespace {
+constexpr int TN_THREADS = 256, TN_KC = 64;  // k rows of B staged per pass
+
+template <class T>
+__global__ void __launch_bounds__(TN_THREADS)
+gemm_skinny_tn_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ ws, int64_t M, int N, int64_t K,
+                      Strides3 sA, Strides3 sB, int64_t k_per_chunk) {
+    __shared__ T sB_[TN_KC][SK_NMAX];
+    const int64_t m = (int64_t)blockIdx.x * TN_THREADS + threadIdx.x;
+    const int64_t kc0 = (int64_t)blockIdx.y * k_per_chunk, kc1 = kc0 + k_per_chunk < K ? kc0 + k_per_chunk : K;
+    T acc[SK_NMAX];
+#pragma unroll
+    for (int n = 0; n < SK_NMAX; n++) acc[n] = T(0);
+    for (int64_t k0 = kc0; k0 < kc1; k0 += TN_KC) {
+        const int kc = (int)(kc1 - k0 < TN_KC ? kc1 - k0 : TN_KC);
+        __syncthreads();
+        for (int e = threadIdx.x; e < kc * N; e += TN_THREADS) {
+            int k = e / N, n = e % N;
+            sB_[k][n] = B[(k0 + k) * sB.r + n * sB.c];
+        }
+        __syncthreads();
+        if (m < M) {
+            const T* a = A + m * sA.r + k0 * sA.c;
+            int k = 0;
+            for (; k + 4 <= kc; k += 4) {  // four independent loads in flight
+                T a0 = a[(k + 0) * sA.c], a1 = a[(k + 1) * sA.c], a2 = a[(k + 2) * sA.c], a3 = a[(k + 3) * sA.c];
+#pragma unroll
+                for (int n = 0; n < SK_NMAX; n++)
+                    if (n < N) {
+                        acc[n] = fma(a0, sB_[k][n], acc[n]);
+                        acc[n] = fma(a1, sB_[k + 1][n], acc[n]);
+                        acc[n] = fma(a2, sB_[k + 2][n], acc[n]);
+                        acc[n] = fma(a3, sB_[k + 3][n], acc[n]);
+                    }
+            }
+            for (; k < kc; k++) {
+                T a0 = a[k * sA.c];
+#pragma unroll
+                for (int n = 0; n < SK_NMAX; n++)
+                    if (n < N) acc[n] = fma(a0, sB_[k][n], acc[n]);
+            }
+        }
+    }
+    if (m < M) {
+        T* out = ws + ((int64_t)blockIdx.y * M + m) * N;
+#pragma unroll
+        for (int n = 0; n < SK_NMAX; n++)
+            if (n < N) out[n] = acc[n];
+    }
+}
+}  // namespace
+
+template <class T>
+int launch_gemm_skinny_tn(DeviceCtx* ctx, const T* A, const T* B, T* C, int64_t M, int64_t N, int64_t K, Strides3 sA,
+                          Strides3 sB, Strides3 sC, bool accumulate, cudaStream_t stream) {
+    const int64_t m_blocks = (M + TN_THREADS - 1) / TN_THREADS;
+    const int64_t sms = ctx ? ctx->sm_count : 148;
+    int64_t chunks = (2 * sms + m_blocks - 1) / m_blocks;  // ~2 CTAs per SM
+    if (chunks > (K + TN_KC - 1) / TN_KC) chunks = (K + TN_KC - 1) / TN_KC;
+    if (chunks < 1) chunks = 1;
+    const int64_t k_per_chunk = ((K + chunks - 1) / chunks + TN_KC - 1) / TN_KC * TN_KC;
+    chunks = (K + k_per_chunk - 1) / k_per_chunk;
+    TempBuf ws;
+    EML_TRY(ws.alloc(sizeof(T) * (size_t)(chunks * M * N), stream));
+    dim3 grid((unsigned)m_blocks, (unsigned)chunks);
+    gemm_skinny_tn_kernel<T><<<grid, TN_THREADS, 0, stream>>>(A, B, ws.as<T>(), M, (int)N, K, sA, sB, k_per_chunk);
+    count_launch();
+    set_last_kernel("skinny_tn");
+    EML_TRY(check_launch("gemm_skinny_tn"));
+    return launch_splitk_reduce<T>(ws.as<T>(), (int)chunks, C, 1, M, N, sC, accumulate, stream);
+}
+template int launch_gemm_skinny_tn<float>(DeviceCtx*, const float*, const float*, float*, int64_t, int64_t, int64_t,
+                                          Strides3, Strides3, Strides3, bool, cudaStream_t);
+template int launch_gemm_skinny_tn<double>(DeviceCtx*, const double*, const double*, double*, int64_t, int64_t, int64_t,
+                                           Strides3, Strides3, Strides3, bool, cudaStream_t);
 
 template <class T>
 int launch_gemm_skinny(const T* A, const T* B, T* C, int64_t batch, int64_t M, int64_t N, int64_t K, Strides3 sA,
@@ -247,11 +330,40 @@ splitk_reduce_kernel(const T* __restrict__ ws, int splits, int64_t split_stride,
 }
 }  // namespace
 
+namespace {
+// few outputs, many splits (the loss reduction: 10 outputs x 128 splits): one warp per output element, lanes take
+// every 32nd split and a fixed shuffle tree combines them -- still a fixed order
+template <class T>
+__global__ void __launch_bounds__(256)
+splitk_reduce_warp_kernel(const T* __restrict__ ws, int splits, int64_t split_stride, T* __restrict__ C, int64_t M,
+                          int64_t N, Strides3 sC, int64_t batch, int accumulate) {
+    const int lane = threadIdx.x & 31;
+    const int64_t total = batch * M * N;
+    for (int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); i < total; i += (int64_t)gridDim.x * 8) {
+        T acc = T(0);
+        for (int s = lane; s < splits; s += 32) acc += ws[(int64_t)s * split_stride + i];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        if (lane == 0) {
+            int64_t b = i / (M * N), r = (i / N) % M, c = i % N;
+            T* p = C + b * sC.b + r * sC.r + c * sC.c;
+            *p = accumulate ? *p + acc : acc;
+        }
+    }
+}
+}  // namespace
+
 template <class T>
 int launch_splitk_reduce(const T* ws, int splits, T* C, int64_t batch, int64_t M, int64_t N, Strides3 sC,
                          bool accumulate, cudaStream_t stream) {
     int64_t total = batch * M * N;
     if (total == 0) return EML_OK;
+    if (total <= 8192 && splits >= 16) {
+        int blocks = (int)((total + 7) / 8);
+        splitk_reduce_warp_kernel<T><<<blocks, 256, 0, stream>>>(ws, splits, total, C, M, N, sC, batch, accumulate ? 1 : 0);
+        count_launch();
+        return check_launch("split-K reduce (warp per element)");
+    }
     int64_t want = (total + 255) / 256;
     int blocks = (int)(want < 148 * 8 ? want : 148 * 8);
     splitk_reduce_kernel<T><<<blocks, 256, 0, stream>>>(ws, splits, total, C, M, N, sC, batch, accumulate ? 1 : 0);

@@ -578,6 +578,37 @@ int eml_val_numbers(eml_tape* t, eml_val h, void* host_out) {
     return EML_OK;
 }
 
+int eml_val_numbers_async(eml_tape* t, eml_val h, void* pinned_host_out, void** arrival) {
+    EML_TRY(check_tape(t));
+    if (!pinned_host_out) EML_BAD_ARG("null argument");
+    std::lock_guard<std::mutex> lock(t->mu);
+    Value* v;
+    EML_TRY(get_value(t, h, &v));
+    EML_CUDA(cudaMemcpyAsync(pinned_host_out, v->numbers->p, esize(t->dtype) * v->n(), cudaMemcpyDeviceToHost, t->stream));
+    if (arrival) {
+        cudaEvent_t ev;
+        EML_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        EML_CUDA(cudaEventRecord(ev, t->stream));
+        *arrival = ev;
+    }
+    return EML_OK;
+}
+
+int eml_arrival_wait(void* arrival) {
+    if (!arrival) EML_BAD_ARG("null arrival");
+    cudaEvent_t ev = (cudaEvent_t)arrival;
+    cudaError_t e = cudaEventSynchronize(ev);
+    cudaEventDestroy(ev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaEventSynchronize", __FILE__, __LINE__);
+    return EML_OK;
+}
+
+int eml_tape_sync(eml_tape* t) {
+    EML_TRY(check_tape(t));
+    EML_CUDA(cudaStreamSynchronize(t->stream));
+    return EML_OK;
+}
+
 int eml_val_indexes(eml_tape* t, eml_val h, int64_t* host_out) {
     if (!t || !host_out) EML_BAD_ARG("null argument");
     std::lock_guard<std::mutex> lock(t->mu);

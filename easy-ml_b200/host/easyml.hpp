@@ -536,6 +536,12 @@ class RecordTensor {
         detail::check(eml_val_numbers(list_->raw(), v_, out.data()));
         return Tensor<T>(shape_, std::move(out));
     }
+    // asynchronous read-back into page-locked memory; wait on the returned arrival (eml_arrival_wait) before reading
+    void* numbers_async(T* pinned_out) const {
+        void* arrival = nullptr;
+        detail::check(eml_val_numbers_async(list_->raw(), v_, pinned_out, &arrival));
+        return arrival;
+    }
     std::vector<int64_t> indexes() const {  // the Index half of the (T, Index) view, mod.rs:2511
         std::vector<int64_t> out((size_t)(shape_[0].second * shape_[1].second));
         detail::check(eml_val_indexes(list_->raw(), v_, out.data()));

@@ -277,6 +277,14 @@ int eml_val_release(eml_tape* t, eml_val v); /* drop a container (its node stays
 int eml_val_shape(eml_tape* t, eml_val v, int64_t* rows, int64_t* cols, int* tracked);
 int eml_val_numbers(eml_tape* t, eml_val v, void* host_out);     /* rows*cols numbers, row-major */
 int eml_val_indexes(eml_tape* t, eml_val v, int64_t* host_out);  /* rows*cols tape indexes */
+/* Asynchronous read-back: enqueues the copy of v's numbers into host_out (page-locked memory from eml_host_alloc)
+ * on the tape's stream and returns; the data is there after eml_arrival_wait(*arrival) (or eml_tape_sync; arrival
+ * may be NULL).  A training loop reads the loss of step i once step i+1 is enqueued, so the host never stalls
+ * the device. */
+int eml_val_numbers_async(eml_tape* t, eml_val v, void* pinned_host_out, void** arrival);
+/* Blocks until the copy that produced `arrival` has landed, then releases the handle. */
+int eml_arrival_wait(void* arrival);
+int eml_tape_sync(eml_tape* t);
 int eml_val_device_ptr(eml_tape* t, eml_val v, void** dev_numbers); /* borrowed; valid until release */
 
 /* record_tensor_matrix_multiply / record_matrix_matrix_multiply,

@@ -301,6 +301,20 @@ def test_skinny_n_streaming_kernel(orc, dtype, m, n, k):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("m,n,k", [(512, 10, 8192), (40, 1, 300), (700, 16, 1000), (33, 7, 4097)])
+def test_skinny_tn_chunked_kernel(orc, dtype, m, n, k):
+    """N <= 16 with A stored transposed (contiguous along m) and a long K -- the NN's dW2 = H^T dY."""
+    r = rng(2300 + m + n + k)
+    a, b = uniform(r, (m, k), dtype), uniform(r, (k, n), dtype)
+    a_t = np.ascontiguousarray(a.T)  # [k][m]: element (m, k) at a_t[k*m_total + m]
+    got = contract_strided(a_t, b, 1, m, n, k, (m * k, 1, m), (k * n, n, 1), dtype)[0]
+    assert eml.last_kernel() == "skinny_tn"
+    assert_within(got, a, b, orc.matrix_mul(a, b, threads=4), dtype, f"skinny_tn {m}x{n}x{k}")
+    again = contract_strided(a_t, b, 1, m, n, k, (m * k, 1, m), (k * n, n, 1), dtype)[0]
+    assert np.array_equal(got, again)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 def test_gemm_leading_dimensions(orc, dtype):
     r = rng(3)
     big_a, big_b = uniform(r, (150, 200), dtype), uniform(r, (200, 180), dtype)
