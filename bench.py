@@ -439,7 +439,7 @@ def extra_workloads(torch, eml, lib, check, dev, stream, sp, peak):
         res["nn_784_512_10_batch8192"]["cpu_baseline"] = nn_cpu_baseline(np)
         exe = os.path.join(ROOT, "easy-ml_b200", "host", "nn_bench")
         if os.path.exists(exe):  # the same step driven by the compiled C++ mirror (no interpreter in the loop)
-            r = subprocess.run([exe, "8192", "20"], capture_output=True, text=True, timeout=300)
+            r = subprocess.run([exe, "8192", "100"], capture_output=True, text=True, timeout=300)
             res["nn_784_512_10_batch8192"]["cpp_host"] = json.loads(r.stdout) if r.returncode == 0 else r.stderr[-300:]
     except Exception as e:
         res["nn_error"] = repr(e)
@@ -497,7 +497,7 @@ def hbm_kernels(torch, lib, check, dev, stream, sp, peak, run):
     return out
 
 
-def nn_steps(torch, eml, np, batch=8192, steps=5, warmup=3):
+def nn_steps(torch, eml, np, batch=8192, steps=50, warmup=3):
     """BASELINE config 4: feedforward 784-512-10, RecordTensor reverse-mode, batch 8192, f32.
     One step = forward + derivatives() + SGD update + clear/reset; inputs constants, weights tracked."""
     r = np.random.default_rng(0x5EED0004)
@@ -517,33 +517,62 @@ def nn_steps(torch, eml, np, batch=8192, steps=5, warmup=3):
     def sigmoid(z):
         return ((-z).exp() + 1.0).div_swapped(1.0)
 
+    slots = [eml.PinnedBuffer((1,), f32), eml.PinnedBuffer((1,), f32)]
     losses = []
 
-    def step():
+    def body(slot):
         out = sigmoid(sigmoid(X * W1) * W2)
         diff = out - Y
         loss = ((L * diff.elementwise_multiply(diff)) * R) / float(batch)
         d = loss.derivatives_for([0, 0])
         eml.sgd_update(W1, d, 0.05)
         eml.sgd_update(W2, d, 0.05)
-        losses.append(float(loss.numbers().data[0, 0]))  # D2H of the loss: the step's result
+        arrival = loss.numbers_async(slots[slot])  # D2H of the loss (the step's result) into page-locked memory
         hist.clear()
         W1.reset()
         W2.reset()
+        return arrival
 
-    for _ in range(warmup):
-        step()
+    pending = []
+
+    def collect():  # the loss of the PREVIOUS step: every step is read back, the host just never stalls the device
+        if pending:
+            arrival, slot = pending.pop()
+            eml.wait_arrival(arrival)
+            losses.append(float(slots[slot].array[0]))
+
+    def run(launch, n):
+        for i in range(n):
+            slot = i & 1
+            arrival = launch(slot)
+            collect()
+            pending.append((arrival, slot))
+        collect()
+
+    run(body, warmup)
     torch.cuda.synchronize()
     l0 = eml.kernel_launches()
     t0 = time.perf_counter()
-    for _ in range(steps):
-        step()
+    run(body, steps)
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / steps
+    launches = (eml.kernel_launches() - l0) / steps
+    eager_last = losses[-1]
+    # the same step recorded once (CUDA graph; one instance per read-back slot) and replayed
+    graphs = [hist.record(lambda: body(0)), hist.record(lambda: body(1))]
+    run(lambda slot: graphs[slot].launch(), 2)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    run(lambda slot: graphs[slot].launch(), steps)
+    torch.cuda.synchronize()
+    dtg = (time.perf_counter() - t0) / steps
     flop = 2.0 * batch * (784 * 512 + 512 * 10) * 2 + 2.0 * batch * 512 * 10  # fwd + dW1,dW2 + dH
     return {"steps_per_s": 1.0 / dt, "ms_per_step": dt * 1e3, "gflop_per_step": flop / 1e9,
-            "tflops": flop / dt / 1e12, "launches_per_step": (eml.kernel_launches() - l0) / steps,
-            "loss_first": losses[0], "loss_last": losses[-1],
+            "tflops": flop / dt / 1e12, "launches_per_step": launches,
+            "loss_first": losses[0], "loss_last": eager_last,
+            "loss_readback": "every step, asynchronous into page-locked memory, read one step later",
+            "recorded_step_cuda_graph": {"steps_per_s": 1.0 / dtg, "ms_per_step": dtg * 1e3, "launches_per_step": 1,
+                                         "loss_last": losses[-1], "tflops": flop / dtg / 1e12},
             "note": "through the RecordTensor tape API; the reference's scalar tape would need 158 GB at this shape"}
 
 

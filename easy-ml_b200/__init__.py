@@ -7,8 +7,8 @@ host.py (Python mirror of the reference operator API), host/ (C++ mirror), rust/
 """
 from . import _ffi  # raises ImportError when the CUDA library is not built: there is no fallback
 from ._ffi import EmlError, NoDeviceError, BadArgError, StateError, OPS, lib
-from .host import (Derivatives, Einsum, InconsistentDimensionLengthError, Matrix, Panic, RecordMatrix, RecordTensor,
-                   Tensor, WengertList, sgd_update)
+from .host import (Derivatives, Einsum, InconsistentDimensionLengthError, Matrix, Panic, PinnedBuffer, RecordMatrix,
+                   RecordTensor, RecordedStep, Tensor, WengertList, sgd_update, wait_arrival)
 
 
 def device_count():

@@ -87,6 +87,10 @@ SIGNATURES = {
     "eml_val_numbers_async": (cint, [vp, i64, vp, C.POINTER(vp)]),
     "eml_arrival_wait": (cint, [vp]),
     "eml_tape_sync": (cint, [vp]),
+    "eml_tape_capture_begin": (cint, [vp]),
+    "eml_tape_capture_end": (cint, [vp, C.POINTER(vp)]),
+    "eml_graph_launch": (cint, [vp, C.POINTER(vp)]),
+    "eml_graph_destroy": (cint, [vp]),
     "eml_val_indexes": (cint, [vp, i64, vp]),
     "eml_val_device_ptr": (cint, [vp, i64, C.POINTER(vp)]),
     "eml_tape_matmul": (cint, [vp, i64, i64, pi64]),

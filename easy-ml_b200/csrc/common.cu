@@ -109,6 +109,11 @@ constexpr size_t CACHE_LIMIT = size_t(24) << 30;  // beyond this, blocks go stra
 inline size_t size_class(size_t bytes) { return bytes < 512 ? 512 : (bytes + 511) & ~size_t(511); }
 }  // namespace
 
+namespace {
+thread_local bool t_forbid_new_blocks = false;
+}
+void stream_alloc_forbid_new(bool forbid) { t_forbid_new_blocks = forbid; }
+
 int stream_alloc(void** p, size_t bytes, cudaStream_t stream) {
     const size_t sz = size_class(bytes);
     int dev = 0;
@@ -122,6 +127,11 @@ int stream_alloc(void** p, size_t bytes, cudaStream_t stream) {
             g_cached_bytes -= sz;
             return EML_OK;
         }
+    }
+    if (t_forbid_new_blocks) {
+        set_error("a buffer of %zu bytes is not in the stream cache while a step is being captured: run the step "
+                  "eagerly once (same shapes) before eml_tape_capture_begin", sz);
+        return EML_ERR_STATE;
     }
     cudaError_t e = cudaMallocAsync(p, sz, stream);
     if (e == cudaErrorMemoryAllocation) {  // give the cache back and retry once

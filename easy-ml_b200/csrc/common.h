@@ -63,6 +63,9 @@ int get_ctx(DeviceCtx** out);
 // size) free lists: a training step repeats the same sizes, so steady state makes no allocator call at all
 // (an NN step went from ~120 cudaMallocAsync/cudaFreeAsync calls to none).
 int stream_alloc(void** p, size_t bytes, cudaStream_t stream);
+// While a step is being captured into a CUDA graph every block must come from the cache (a fresh cudaMallocAsync
+// would become graph-owned memory that the cache may not recycle): a miss is then an error.
+void stream_alloc_forbid_new(bool forbid);
 void stream_free(void* p, size_t bytes, cudaStream_t stream);
 void stream_cache_release_all();  // returns every cached block to CUDA (eml_shutdown)
 

@@ -102,7 +102,16 @@ struct eml_derivs {
     std::vector<Buf> grads;   // per node, n elements
 };
 
+struct eml_graph {
+    eml_tape* tape = nullptr;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+};
+
 struct eml_tape {
+    bool capturing = false;       // between eml_tape_capture_begin and _end
+    int64_t capture_len = 0;      // tape state at capture_begin: a recorded step must come back to it
+    size_t capture_nodes = 0;
     int dtype = EML_F32;
     int device = 0;
     DeviceCtx* ctx = nullptr;
@@ -119,6 +128,15 @@ namespace eml {
 namespace {
 
 size_t esize(int dtype) { return dtype == EML_F32 ? 4 : 8; }
+
+int not_while_capturing(eml_tape* t, const char* what) {
+    if (t->capturing) {
+        set_error("%s blocks on the device and cannot be part of a recorded step (between eml_tape_capture_begin and "
+                  "_end); use eml_val_numbers_async", what);
+        return EML_ERR_STATE;
+    }
+    return EML_OK;
+}
 
 int check_tape(eml_tape* t) {
     if (!t) EML_BAD_ARG("null tape");
@@ -164,6 +182,7 @@ int new_container(eml_tape* t, const void* src, bool src_on_device, int64_t rows
     if (rows < 1 || cols < 1) EML_BAD_ARG("container shape %lldx%lld: Easy ML containers have at least one element",
                                           (long long)rows, (long long)cols);
     if (!src || !out) EML_BAD_ARG("null argument");
+    if (!src_on_device) EML_TRY(not_while_capturing(t, "creating a container from host memory"));
     Value v;
     v.rows = rows;
     v.cols = cols;
@@ -573,6 +592,7 @@ int eml_val_numbers(eml_tape* t, eml_val h, void* host_out) {
     std::lock_guard<std::mutex> lock(t->mu);
     Value* v;
     EML_TRY(get_value(t, h, &v));
+    EML_TRY(not_while_capturing(t, "eml_val_numbers"));
     EML_CUDA(cudaMemcpyAsync(host_out, v->numbers->p, esize(t->dtype) * v->n(), cudaMemcpyDeviceToHost, t->stream));
     EML_CUDA(cudaStreamSynchronize(t->stream));
     return EML_OK;
@@ -585,7 +605,9 @@ int eml_val_numbers_async(eml_tape* t, eml_val h, void* pinned_host_out, void** 
     Value* v;
     EML_TRY(get_value(t, h, &v));
     EML_CUDA(cudaMemcpyAsync(pinned_host_out, v->numbers->p, esize(t->dtype) * v->n(), cudaMemcpyDeviceToHost, t->stream));
-    if (arrival) {
+    if (arrival && t->capturing) {
+        *arrival = nullptr;  // inside a recorded step the arrival comes from eml_graph_launch
+    } else if (arrival) {
         cudaEvent_t ev;
         EML_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         EML_CUDA(cudaEventRecord(ev, t->stream));
@@ -605,7 +627,80 @@ int eml_arrival_wait(void* arrival) {
 
 int eml_tape_sync(eml_tape* t) {
     EML_TRY(check_tape(t));
+    EML_TRY(not_while_capturing(t, "eml_tape_sync"));
     EML_CUDA(cudaStreamSynchronize(t->stream));
+    return EML_OK;
+}
+
+int eml_tape_capture_begin(eml_tape* t) {
+    EML_TRY(check_tape(t));
+    std::lock_guard<std::mutex> lock(t->mu);
+    if (t->capturing) {
+        set_error("a step is already being captured on this tape");
+        return EML_ERR_STATE;
+    }
+    EML_CUDA(cudaStreamBeginCapture(t->stream, cudaStreamCaptureModeThreadLocal));
+    t->capturing = true;
+    t->capture_len = t->len;
+    t->capture_nodes = t->nodes.size();
+    stream_alloc_forbid_new(true);
+    return EML_OK;
+}
+
+int eml_tape_capture_end(eml_tape* t, eml_graph** out) {
+    EML_TRY(check_tape(t));
+    if (!out) EML_BAD_ARG("null argument");
+    std::lock_guard<std::mutex> lock(t->mu);
+    if (!t->capturing) {
+        set_error("no capture in progress on this tape");
+        return EML_ERR_STATE;
+    }
+    t->capturing = false;
+    stream_alloc_forbid_new(false);
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamEndCapture(t->stream, &graph);
+    if (e != cudaSuccess || !graph) {
+        cudaGetLastError();
+        set_error("the step could not be captured: %s", cudaGetErrorString(e));
+        return EML_ERR_CUDA;
+    }
+    if (t->len != t->capture_len || t->nodes.size() != t->capture_nodes) {
+        cudaGraphDestroy(graph);
+        set_error("a recorded step must end in the tape state it started in (length %lld -> %lld): clear() the list and "
+                  "reset() the variables before eml_tape_capture_end", (long long)t->capture_len, (long long)t->len);
+        return EML_ERR_STATE;
+    }
+    auto g = std::make_unique<eml_graph>();
+    g->tape = t;
+    g->graph = graph;
+    e = cudaGraphInstantiate(&g->exec, graph, 0);
+    if (e != cudaSuccess) {
+        cudaGraphDestroy(graph);
+        return cuda_fail(e, "cudaGraphInstantiate", __FILE__, __LINE__);
+    }
+    *out = g.release();
+    return EML_OK;
+}
+
+int eml_graph_launch(eml_graph* g, void** arrival) {
+    if (!g || !g->exec) EML_BAD_ARG("null graph");
+    EML_TRY(check_tape(g->tape));
+    EML_CUDA(cudaGraphLaunch(g->exec, g->tape->stream));
+    count_launch();
+    if (arrival) {
+        cudaEvent_t ev;
+        EML_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        EML_CUDA(cudaEventRecord(ev, g->tape->stream));
+        *arrival = ev;
+    }
+    return EML_OK;
+}
+
+int eml_graph_destroy(eml_graph* g) {
+    if (!g) return EML_OK;
+    if (g->exec) cudaGraphExecDestroy(g->exec);
+    if (g->graph) cudaGraphDestroy(g->graph);
+    delete g;
     return EML_OK;
 }
 
@@ -672,7 +767,16 @@ int eml_derivs_len(eml_derivs* d, int64_t* len) {
     return EML_OK;
 }
 
+static int derivs_not_while_capturing(eml_derivs* d) {
+    if (d && d->tape && d->tape->capturing) {
+        set_error("reading derivatives on the host blocks on the device and cannot be part of a recorded step");
+        return EML_ERR_STATE;
+    }
+    return EML_OK;
+}
+
 int eml_derivs_at(eml_derivs* d, int64_t index, double* out) {
+    EML_TRY(derivs_not_while_capturing(d));
     if (!d || !out) EML_BAD_ARG("null argument");
     int n = find_node(d, index);
     if (n < 0) EML_BAD_ARG("index out of bounds: the len is %lld but the index is %lld", (long long)d->len, (long long)index);
@@ -715,11 +819,15 @@ static int derivs_at_val(eml_derivs* d, eml_val h, void* dst, bool dst_on_device
     return EML_OK;
 }
 
-int eml_derivs_at_val(eml_derivs* d, eml_val v, void* host_out) { return derivs_at_val(d, v, host_out, false); }
+int eml_derivs_at_val(eml_derivs* d, eml_val v, void* host_out) {
+    EML_TRY(derivs_not_while_capturing(d));
+    return derivs_at_val(d, v, host_out, false);
+}
 int eml_derivs_at_val_dev(eml_derivs* d, eml_val v, void* dev_out) { return derivs_at_val(d, v, dev_out, true); }
 
 int eml_derivs_to_host(eml_derivs* d, void* host_out) {
     if (!d || !host_out) EML_BAD_ARG("null argument");
+    EML_TRY(derivs_not_while_capturing(d));
     if (d->len > (int64_t(1) << 28))
         EML_BAD_ARG("derivs_to_host: the reference tape would have %lld entries; materialising it is refused", (long long)d->len);
     EML_CUDA(cudaSetDevice(d->device));
@@ -754,6 +862,23 @@ int eml_tape_sgd_update(eml_tape* t, eml_val hw, eml_derivs* d, double lr) {
     }
     const int64_t n = w->n();
     size_t es = esize(t->dtype);
+    if (t->capturing) {
+        // recorded step: the update happens in place, so a replay finds the weights where the last one left them
+        Node nd;
+        nd.kind = Kind::UNARY;
+        nd.base = t->len;
+        nd.count = nd.n = n;
+        nd.p0 = w->node;
+        nd.p0_tracked = true;
+        if (t->dtype == EML_F32)
+            EML_TRY(launch_sgd<float>((float*)w->numbers->p, (const float*)d->grads[w->node]->p, (float)lr, n, t->stream));
+        else
+            EML_TRY(launch_sgd<double>((double*)w->numbers->p, (const double*)d->grads[w->node]->p, lr, n, t->stream));
+        t->len += n;
+        t->nodes.push_back(nd);
+        w->node = (int)t->nodes.size() - 1;
+        return EML_OK;
+    }
     // x - (derivatives[&x] * lr): a new container (the nodes that captured the old numbers keep them)
     Buf fresh;
     EML_TRY(new_buf(es * n, t->stream, &fresh));

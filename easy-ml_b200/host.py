@@ -443,6 +443,65 @@ class WengertList:
     def clear(self):
         check(lib.eml_tape_clear(self._h))
 
+    def sync(self):
+        check(lib.eml_tape_sync(self._h))
+
+    def record(self, step):
+        """Records the device work `step()` issues and returns it as a replayable CUDA graph (RecordedStep).
+        No counterpart in the reference.  The step must have run eagerly once before (so every buffer size is in the
+        cache), may not block on the device (use numbers_async), must release the containers it creates and must
+        leave the tape as it found it (clear() + reset()); sgd_update works in place while recording."""
+        check(lib.eml_tape_capture_begin(self._h))
+        g = C.c_void_p()
+        try:
+            step()
+        except BaseException:
+            lib.eml_tape_capture_end(self._h, C.byref(g))
+            if g:
+                lib.eml_graph_destroy(g)
+            raise
+        check(lib.eml_tape_capture_end(self._h, C.byref(g)))
+        return RecordedStep(g)
+
+
+class RecordedStep:
+    def __init__(self, handle):
+        self._g = handle
+
+    def __del__(self):
+        if getattr(self, "_g", None):
+            lib.eml_graph_destroy(self._g)
+            self._g = None
+
+    def launch(self):
+        """Enqueues one replay; returns an arrival to pass to wait_arrival before reading what the step copied out."""
+        a = C.c_void_p()
+        check(lib.eml_graph_launch(self._g, C.byref(a)))
+        return a
+
+
+def wait_arrival(arrival):
+    if arrival:
+        check(lib.eml_arrival_wait(arrival))
+
+
+class PinnedBuffer:
+    """Page-locked host memory (eml_host_alloc) viewed as a numpy array: the target of asynchronous read-backs."""
+
+    def __init__(self, shape, dtype=np.float32):
+        self.dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) if np.ndim(shape) else int(shape)
+        self._p = C.c_void_p()
+        check(lib.eml_host_alloc(C.byref(self._p), max(n, 1) * self.dtype.itemsize))
+        ctype = C.c_float if self.dtype == np.float32 else C.c_double
+        self.array = np.ctypeslib.as_array(C.cast(self._p, C.POINTER(ctype)), shape=(max(n, 1),))[:n].reshape(shape)
+
+    def __del__(self):
+        if getattr(self, "_p", None):
+            self.array = None
+            lib.eml_host_free(self._p)
+            self._p = None
+
 
 def _same_list(a, b):
     if a is not None and b is not None and a is not b:
@@ -489,6 +548,13 @@ class _RecordContainer:
         out = np.empty(r * c, dtype=self._owner.dtype)
         check(lib.eml_val_numbers(self._owner._h, self._v, _ptr(out)))
         return out.reshape(self._lens())
+
+    def numbers_async(self, pinned):
+        """Enqueues the copy of the numbers into a PinnedBuffer; returns an arrival (None inside a recorded step,
+        where the arrival comes from RecordedStep.launch)."""
+        a = C.c_void_p()
+        check(lib.eml_val_numbers_async(self._owner._h, self._v, pinned._p, C.byref(a)))
+        return a if a else None
 
     def indexes(self):
         r, c = self._rc()

@@ -449,6 +449,28 @@ struct Einsum {  // src/tensors/einsum.rs:98-313
 };
 
 // ------------------------------------------------------------------------------------------------ autodiff
+// A step recorded once (WengertList::record) and replayed as one CUDA graph launch.  No counterpart in the
+// reference; see the restrictions at eml_tape_capture_begin in easyml_b200.h.
+class RecordedStep {
+  public:
+    explicit RecordedStep(eml_graph* g) : g_(g) {}
+    RecordedStep(RecordedStep&& o) noexcept : g_(o.g_) { o.g_ = nullptr; }
+    RecordedStep(const RecordedStep&) = delete;
+    ~RecordedStep() {
+        if (g_) eml_graph_destroy(g_);
+    }
+    // enqueues one replay; wait on the returned arrival (eml_arrival_wait) before reading what the step copied out
+    void* launch() const {
+        void* arrival = nullptr;
+        detail::check(eml_graph_launch(g_, &arrival));
+        return arrival;
+    }
+
+  private:
+    eml_graph* g_;
+};
+
+
 // WengertList<T>, src/differentiation.rs:327-331 -- here a handle to the device tape (one macro node per
 // container operation; tape length and every Index equal the reference's scalar tape, see csrc/tape.cu).
 template <class T>
@@ -469,6 +491,23 @@ class WengertList {
         return n;
     }
     void clear() { detail::check(eml_tape_clear(t_)); }  // differentiation.rs:674
+    // records the device work `step` issues (it must have run eagerly once before, and must leave the tape as it
+    // found it: clear() + reset()) and returns it as a replayable graph
+    template <class F>
+    RecordedStep record(F&& step) {
+        detail::check(eml_tape_capture_begin(t_));
+        try {
+            step();
+        } catch (...) {
+            eml_graph* dead = nullptr;
+            eml_tape_capture_end(t_, &dead);
+            if (dead) eml_graph_destroy(dead);
+            throw;
+        }
+        eml_graph* g = nullptr;
+        detail::check(eml_tape_capture_end(t_, &g));
+        return RecordedStep(g);
+    }
     eml_tape* raw() const { return t_; }
 
   private:

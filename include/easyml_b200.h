@@ -316,6 +316,25 @@ int eml_derivs_to_host(eml_derivs* d, void* host_out);
  * container's indexes move to the new entries until the next clear + reset). */
 int eml_tape_sgd_update(eml_tape* t, eml_val w, eml_derivs* d, double lr);
 
+/* ---------------------------------------------------------------------------------------------
+ * Recorded steps (CUDA graphs).  A training step issues ~50 small dependent launches; recorded once, the same
+ * device work is replayed as ONE graph launch.  No counterpart in the reference (it has no device); the tape
+ * semantics are unchanged, the restrictions below only apply between begin and end:
+ *   - run the identical step eagerly at least once first (every buffer size must already be in the cache);
+ *   - no blocking host<->device call (eml_val_numbers, eml_tape_variables/constants, eml_derivs_at*, ...): they
+ *     return EML_ERR_STATE; read results with eml_val_numbers_async into page-locked memory;
+ *   - eml_tape_sgd_update updates the weights IN PLACE (eagerly it produces a fresh container, so nodes recorded
+ *     earlier keep the old numbers; a recorded step must leave every persistent container where it found it);
+ *   - release every container created inside, and end in the tape state the step started in (the usual
+ *     clear() + reset() of the variables), so that a replay needs no host bookkeeping.
+ * eml_graph_launch enqueues one replay on the tape's stream; *arrival (optional) completes when it has finished.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct eml_graph eml_graph;
+int eml_tape_capture_begin(eml_tape* t);
+int eml_tape_capture_end(eml_tape* t, eml_graph** out);
+int eml_graph_launch(eml_graph* g, void** arrival);
+int eml_graph_destroy(eml_graph* g);
+
 #ifdef __cplusplus
 }
 #endif

@@ -677,3 +677,78 @@ def test_pack_cache_of_constants_follows_identity_not_address():
         results.append(first)
         del X  # its buffer returns to the stream cache; the next constant reuses the address
     assert not np.array_equal(results[0], results[1])
+
+
+# ------------------------------------------------------------------ recorded steps (CUDA graphs)
+def _small_net(dtype, seed=2500):
+    r = rng(seed)
+    batch = 256
+    x = uniform(r, (batch, 48), dtype)
+    y = uniform(r, (batch, 6), dtype)
+    w1, w2 = 0.1 * uniform(r, (48, 32), dtype), 0.1 * uniform(r, (32, 6), dtype)
+    T = lambda names, a: eml.Tensor(list(zip(names, a.shape)), a)
+    hist = eml.WengertList(dtype)
+    net = dict(hist=hist, W1=eml.RecordTensor.variables(hist, T(["i", "h"], w1)),
+               W2=eml.RecordTensor.variables(hist, T(["h", "o"], w2)), X=eml.RecordTensor.constants(T(["n", "i"], x), hist),
+               Y=eml.RecordTensor.constants(T(["n", "o"], y), hist),
+               L=eml.RecordTensor.constants(T(["u", "n"], np.ones((1, batch), dtype)), hist),
+               R=eml.RecordTensor.constants(T(["o", "v"], np.ones((6, 1), dtype)), hist), batch=batch,
+               slot=eml.PinnedBuffer((1,), dtype))
+
+    def step():
+        sig = lambda z: ((-z).exp() + 1.0).div_swapped(1.0)
+        out = sig(sig(net["X"] * net["W1"]) * net["W2"])
+        diff = out - net["Y"]
+        loss = ((net["L"] * diff.elementwise_multiply(diff)) * net["R"]) / float(batch)
+        d = loss.derivatives_for([0, 0])
+        eml.sgd_update(net["W1"], d, 0.1)
+        eml.sgd_update(net["W2"], d, 0.1)
+        arrival = loss.numbers_async(net["slot"])
+        hist.clear()
+        net["W1"].reset()
+        net["W2"].reset()
+        return arrival
+
+    net["step"] = step
+    return net
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_recorded_step_replays_the_eager_step_bit_for_bit(dtype):
+    """WengertList.record: the step captured as a CUDA graph and replayed N times must leave the same weights and
+    losses as N eager steps (same kernels, same order; the SGD update is in place while recording)."""
+    steps = 6
+    eager = _small_net(dtype)
+    losses_e = []
+    for _ in range(1 + steps):
+        eml.wait_arrival(eager["step"]())
+        losses_e.append(float(eager["slot"].array[0]))
+    rec = _small_net(dtype)
+    eml.wait_arrival(rec["step"]())  # one eager step first: fills the buffer cache with every size the step needs
+    losses_g = [float(rec["slot"].array[0])]
+    graph = rec["hist"].record(rec["step"])
+    assert len(rec["hist"]) == 48 * 32 + 32 * 6  # the tape is back where the step started
+    for _ in range(steps):
+        eml.wait_arrival(graph.launch())
+        losses_g.append(float(rec["slot"].array[0]))
+    assert losses_g == losses_e and losses_e[-1] < losses_e[0]
+    for name in ("W1", "W2"):
+        assert np.array_equal(rec[name].numbers().data, eager[name].numbers().data), name
+
+
+def test_recorded_step_restrictions_are_errors():
+    net = _small_net(np.float32, seed=2600)
+    hist = net["hist"]
+    # blocking call inside a recording
+    eml.wait_arrival(net["step"]())
+    with pytest.raises(eml.StateError, match="blocks on the device"):
+        hist.record(lambda: net["W1"].numbers())
+    # a step that does not return the tape to its starting state
+    with pytest.raises(eml.StateError, match="must end in the tape state it started in"):
+        hist.record(lambda: (net["X"] * net["W1"]))
+    hist.clear()
+    net["W1"].reset()
+    net["W2"].reset()
+    # the library still works eagerly afterwards
+    eml.wait_arrival(net["step"]())
+    assert np.isfinite(net["slot"].array[0])
