@@ -156,61 +156,73 @@ int launch_gemm_simt(const T* A, const T* B, T* C, int64_t batch, int64_t M, int
 // over its k's and a fixed shuffle tree combines the 32 lanes -- deterministic, no atomics.
 // ------------------------------------------------------------------------------------------------
 namespace {
-constexpr int SK_NMAX = 16, SK_ROWS = 8, SK_WARPS = 8, SK_THREADS = SK_WARPS * 32;
+constexpr int SK_NMAX = 16, SK_WARPS = 8, SK_THREADS = SK_WARPS * 32;
 
 template <class T>
 __global__ void __launch_bounds__(SK_THREADS)
 gemm_skinny_kernel(const T* __restrict__ A, const T* __restrict__ B, T* C, int64_t batch, int64_t M, int N, int64_t K,
                    Strides3 sA, Strides3 sB, Strides3 sC, int accumulate) {
     constexpr int KC = 2048 / sizeof(T);  // k chunk: 512 (f32) / 256 (f64) -> 32 KB of shared memory
+    constexpr int PER_LANE = KC / 32;     // loads one lane keeps in flight per chunk
     __shared__ T sBk[SK_NMAX][KC];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t row_blocks = (M + SK_WARPS * SK_ROWS - 1) / (SK_WARPS * SK_ROWS);
+    const int64_t row_blocks = (M + SK_WARPS - 1) / SK_WARPS;
+    // K fits one chunk and there is one B (the NN's H * W2): B is staged once per CTA, not once per row group
+    const bool stage_once = K <= KC && batch == 1;
+    auto stage = [&](const T* Bb, int64_t k0, int kc) {
+        // one k per thread and pass: its N loads are independent (all in flight together) and the stores are
+        // conflict free (consecutive threads, consecutive k)
+        for (int k = threadIdx.x; k < kc; k += SK_THREADS) {
+            T v[SK_NMAX];
+#pragma unroll
+            for (int n = 0; n < SK_NMAX; n++) v[n] = n < N ? Bb[(k0 + k) * sB.r + n * sB.c] : T(0);
+#pragma unroll
+            for (int n = 0; n < SK_NMAX; n++)
+                if (n < N) sBk[n][k] = v[n];
+        }
+    };
+    if (stage_once) {
+        stage(B, 0, (int)K);
+        __syncthreads();
+    }
     for (int64_t blk = blockIdx.x; blk < row_blocks * batch; blk += gridDim.x) {
         const int64_t b = blk / row_blocks;
-        const int64_t m0 = (blk % row_blocks) * (SK_WARPS * SK_ROWS) + warp * SK_ROWS;
+        const int64_t m = (blk % row_blocks) * SK_WARPS + warp;  // one row per warp
         const T* Ab = A + b * sA.b;
         const T* Bb = B + b * sB.b;
-        T acc[SK_ROWS][SK_NMAX];
+        T acc[SK_NMAX];
 #pragma unroll
-        for (int r = 0; r < SK_ROWS; r++)
-#pragma unroll
-            for (int n = 0; n < SK_NMAX; n++) acc[r][n] = T(0);
+        for (int n = 0; n < SK_NMAX; n++) acc[n] = T(0);
         for (int64_t k0 = 0; k0 < K; k0 += KC) {
             const int kc = (int)((K - k0) < KC ? (K - k0) : KC);
-            __syncthreads();  // the previous chunk has been consumed
-            for (int e = threadIdx.x; e < N * kc; e += SK_THREADS) {
-                int n = e % N, k = e / N;  // consecutive threads walk n then k: B rows are read contiguously
-                sBk[n][k] = Bb[(k0 + k) * sB.r + n * sB.c];
+            if (!stage_once) {
+                __syncthreads();  // the previous chunk has been consumed
+                stage(Bb, k0, kc);
+                __syncthreads();
             }
-            __syncthreads();
-            // the SK_ROWS rows of this warp advance together, so SK_ROWS independent loads are in flight per lane
-            // (a single row at a time is latency-bound: one dependent 128-byte load per 32 k)
-            for (int k = lane; k < kc; k += 32) {
-                T av[SK_ROWS];
+            if (m < M) {
+                // all of the lane's loads of this chunk are issued before the first use: PER_LANE coalesced 128-byte
+                // warp loads in flight per warp (one dependent load per 32 k is latency-bound)
+                T av[PER_LANE];
+                const T* a = Ab + m * sA.r + k0;
 #pragma unroll
-                for (int r = 0; r < SK_ROWS; r++) av[r] = (m0 + r < M) ? Ab[(m0 + r) * sA.r + k0 + k] : T(0);
+                for (int j = 0; j < PER_LANE; j++) av[j] = (lane + 32 * j < kc) ? a[lane + 32 * j] : T(0);
 #pragma unroll
                 for (int n = 0; n < SK_NMAX; n++)
                     if (n < N) {
-                        const T bv = sBk[n][k];
 #pragma unroll
-                        for (int r = 0; r < SK_ROWS; r++) acc[r][n] = fma(av[r], bv, acc[r][n]);
+                        for (int j = 0; j < PER_LANE; j++) acc[n] = fma(av[j], sBk[n][lane + 32 * j], acc[n]);
                     }
             }
         }
 #pragma unroll
-        for (int r = 0; r < SK_ROWS; r++) {
-            const int64_t m = m0 + r;
+        for (int n = 0; n < SK_NMAX; n++) {
+            T v = acc[n];
 #pragma unroll
-            for (int n = 0; n < SK_NMAX; n++) {
-                T v = acc[r][n];
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-                if (lane == 0 && n < N && m < M) {
-                    T* p = C + b * sC.b + m * sC.r + n * sC.c;
-                    *p = accumulate ? *p + v : v;
-                }
+            for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+            if (lane == 0 && n < N && m < M) {
+                T* p = C + b * sC.b + m * sC.r + n * sC.c;
+                *p = accumulate ? *p + v : v;
             }
         }
     }
@@ -246,15 +258,15 @@ gemm_skinny_tn_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __res
         if (m < M) {
             const T* a = A + m * sA.r + k0 * sA.c;
             int k = 0;
-            for (; k + 4 <= kc; k += 4) {  // four independent loads in flight
-                T a0 = a[(k + 0) * sA.c], a1 = a[(k + 1) * sA.c], a2 = a[(k + 2) * sA.c], a3 = a[(k + 3) * sA.c];
+            for (; k + 16 <= kc; k += 16) {  // sixteen independent (coalesced across the CTA) loads in flight
+                T av[16];
+#pragma unroll
+                for (int j = 0; j < 16; j++) av[j] = a[(k + j) * sA.c];
 #pragma unroll
                 for (int n = 0; n < SK_NMAX; n++)
                     if (n < N) {
-                        acc[n] = fma(a0, sB_[k][n], acc[n]);
-                        acc[n] = fma(a1, sB_[k + 1][n], acc[n]);
-                        acc[n] = fma(a2, sB_[k + 2][n], acc[n]);
-                        acc[n] = fma(a3, sB_[k + 3][n], acc[n]);
+#pragma unroll
+                        for (int j = 0; j < 16; j++) acc[n] = fma(av[j], sB_[k + j][n], acc[n]);
                     }
             }
             for (; k < kc; k++) {
@@ -301,8 +313,8 @@ template int launch_gemm_skinny_tn<double>(DeviceCtx*, const double*, const doub
 template <class T>
 int launch_gemm_skinny(const T* A, const T* B, T* C, int64_t batch, int64_t M, int64_t N, int64_t K, Strides3 sA,
                        Strides3 sB, Strides3 sC, bool accumulate, cudaStream_t stream) {
-    int64_t blocks = ((M + SK_WARPS * SK_ROWS - 1) / (SK_WARPS * SK_ROWS)) * batch;
-    if (blocks > 148 * 4) blocks = 148 * 4;
+    int64_t blocks = ((M + SK_WARPS - 1) / SK_WARPS) * batch;
+    if (blocks > 148 * 6) blocks = 148 * 6;
     gemm_skinny_kernel<T><<<(unsigned)blocks, SK_THREADS, 0, stream>>>(A, B, C, batch, M, (int)N, K, sA, sB, sC,
                                                                        accumulate ? 1 : 0);
     count_launch();
