@@ -752,3 +752,36 @@ def test_recorded_step_restrictions_are_errors():
     # the library still works eagerly afterwards
     eml.wait_arrival(net["step"]())
     assert np.isfinite(net["slot"].array[0])
+
+
+# ------------------------------------------------------------------ fused all-gather epilogue on one GPU
+@pytest.mark.parametrize("m,n,k,aligned", [(640, 512, 384, True), (300, 260, 132, True), (130, 70, 33, False)])
+def test_gemm_scatter_epilogue_writes_every_destination(m, n, k, aligned):
+    """eml_gemm_f64_scatter_dev stores every finished tile into the extra destinations too (on a multi-GPU box these
+    are the peers' copies of C; here they are buffers of the same GPU).  Covers the TMA kernel's fused epilogue and
+    the copy fallback for shapes that dispatch to a kernel without it, with and without `accumulate`."""
+    import torch
+
+    g = torch.Generator(device="cuda").manual_seed(31)
+    a = torch.rand((m, k), generator=g, device="cuda", dtype=torch.float64) * 2 - 1
+    b = torch.rand((k, n), generator=g, device="cuda", dtype=torch.float64) * 2 - 1
+    vp = lambda t: C.c_void_p(t.data_ptr())
+    for accumulate in (0, 1):
+        c = torch.rand((m, n), generator=g, device="cuda", dtype=torch.float64)
+        c0 = c.clone()
+        extra = [torch.full((m, n), -3.0, device="cuda", dtype=torch.float64) for _ in range(3)]
+        remote = (C.c_void_p * 3)(*[t.data_ptr() for t in extra])
+        check(lib.eml_gemm_f64_scatter_dev(vp(a), vp(b), vp(c), m, n, k, k, n, n, accumulate, remote, 3, None))
+        torch.cuda.synchronize()
+        kernel = eml.last_kernel()
+        assert (kernel == "dmma_f64_tma+peer_allgather") == aligned, kernel
+        want = a @ b + (c0 if accumulate else 0)
+        bound = 1e-12 * (a.abs() @ b.abs()) + 1e-15
+        assert bool(((c - want).abs() <= bound).all())
+        for t in extra:
+            assert torch.equal(t, c)
+    # eml_copy_async: the transport of the B panels (device to device here)
+    dst = torch.empty_like(a)
+    check(lib.eml_copy_async(vp(dst), vp(a), a.numel() * 8, None))
+    torch.cuda.synchronize()
+    assert torch.equal(dst, a)
