@@ -1,4 +1,5 @@
 // api.cu -- the C ABI of include/easyml_b200.h: argument checks, kernel dispatch, host staging.
+#include <cstdlib>
 #include <cstring>
 
 #include "common.h"
@@ -169,10 +170,28 @@ int gemm_host_pipelined(DeviceCtx* ctx, const T* A, const T* B, T* C, int64_t M,
 
     constexpr int Q = 8;                                      // K panels of phase 1
     const int64_t kq = round_to((K + Q - 1) / Q, 32);
-    int64_t M1 = round_to(M * 2 / 5, 128);                    // ~ compute(M1 rows) == upload(B + A[0:M1])
+    // Every launch covers whole waves of 148 CTAs as nearly as possible: a slab of r tile rows has r * tiles_n tiles,
+    // and a 128 x 128 x K tile is ~1 ms of work at K = 8192, so a nearly empty last wave per launch is expensive.
+    const int64_t tile = sizeof(T) == 8 ? 128 : 256, tiles_n = (N + tile - 1) / tile;
+    const int64_t quantum = sizeof(T) == 8 ? ctx->sm_count : ctx->sm_count / 2;  // CTAs (f64) / CTA pairs (f32) per wave
+    auto whole_waves = [&](int64_t target_rows, int64_t max_rows) {
+        int64_t best = round_to(target_rows, tile);
+        double best_eff = 0;
+        for (int64_t r = target_rows / tile - 4; r <= target_rows / tile + 4; r++) {
+            if (r < 1 || r * tile > max_rows) continue;
+            const int64_t tiles = r * tiles_n;
+            const double eff = (double)tiles / (double)(((tiles + quantum - 1) / quantum) * quantum);
+            if (eff > best_eff + 1e-9) best_eff = eff, best = r * tile;
+        }
+        return best < max_rows ? best : max_rows;
+    };
+    // ~ compute(M1 rows) == upload(B + A[0:M1]) at PCIe 5 / FP64 rates (EML_HOST_M1_PCT overrides)
+    int64_t pct = 55;
+    if (const char* e = getenv("EML_HOST_M1_PCT")) pct = atoi(e) > 0 && atoi(e) <= 100 ? atoi(e) : pct;
+    int64_t M1 = whole_waves(M * pct / 100, M);
     if (M1 > M) M1 = M;
-    const int64_t panels2 = (M - M1 + 1023) / 1024;           // row panels of phase 2, evenly sized
-    const int64_t R = panels2 ? round_to((M - M1 + panels2 - 1) / panels2, 128) : 1024;
+    int64_t R = whole_waves(1152, M - M1 > 0 ? M - M1 : 1);  // row panel of phase 2 (the last one takes the rest)
+    if (R < tile) R = tile;
     NoSplitK no_split;  // same bits as one device launch over the whole problem
 
     // the previous call's work on these streams is complete (every call ends with a synchronize)
