@@ -64,6 +64,19 @@ __device__ __forceinline__ float to_tf32(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
+// x = big + small with both TF32-representable.  Non-finite and near-overflow values must not manufacture NaNs the
+// reference would not produce: rounding FLT_MAX-sized values up to infinity is replaced by truncation, and an
+// infinite x has a zero small part (inf - inf would be NaN).
+__device__ __forceinline__ void split_tf32(float x, float& big, float& small) {
+    if ((__float_as_uint(x) & 0x7f800000u) == 0x7f000000u) {
+        // top binade (|x| >= 2^127): round both parts toward zero so that big + small never reaches 2^128
+        big = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+        small = __uint_as_float(__float_as_uint(x - big) & 0xffffe000u);
+        return;
+    }
+    big = to_tf32(x);
+    small = isfinite(x) ? to_tf32(x - big) : (isnan(x) ? x : 0.0f);
+}
 
 __global__ void __launch_bounds__(256)
 split_pack_kernel(const float* __restrict__ src, float* __restrict__ big, float* __restrict__ small, int64_t MN,
@@ -90,8 +103,8 @@ split_pack_kernel(const float* __restrict__ src, float* __restrict__ big, float*
         int row = ty + r * 8;
         int64_t mn = mn0 + row, k = k0 + tx;  // Kp, MNp are multiples of 32: always in range
         float v = tile[row][tx];
-        float hi = to_tf32(v);
-        float lo = to_tf32(v - hi);
+        float hi, lo;
+        split_tf32(v, hi, lo);
         int64_t o = b * plane + mn * Kp + k;
         big[o] = hi;
         small[o] = lo;
@@ -113,8 +126,11 @@ __device__ __forceinline__ float4 load4_guarded(const float* p, int64_t first, i
     return v;
 }
 __device__ __forceinline__ void store_split4(float* big, float* small, float4 v) {
-    float4 hi = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
-    float4 lo = make_float4(to_tf32(v.x - hi.x), to_tf32(v.y - hi.y), to_tf32(v.z - hi.z), to_tf32(v.w - hi.w));
+    float4 hi, lo;
+    split_tf32(v.x, hi.x, lo.x);
+    split_tf32(v.y, hi.y, lo.y);
+    split_tf32(v.z, hi.z, lo.z);
+    split_tf32(v.w, hi.w, lo.w);
     *reinterpret_cast<float4*>(big) = hi;
     *reinterpret_cast<float4*>(small) = lo;
 }

@@ -785,3 +785,28 @@ def test_gemm_scatter_epilogue_writes_every_destination(m, n, k, aligned):
     check(lib.eml_copy_async(vp(dst), vp(a), a.numel() * 8, None))
     torch.cuda.synchronize()
     assert torch.equal(dst, a)
+
+
+def test_sgemm_non_finite_and_huge_values():
+    """inf, nan and near-FLT_MAX entries through the 3xTF32 path.  Near-overflow values must stay finite (the split
+    truncates instead of rounding FLT_MAX up to infinity).  Documented deviation: an infinite entry comes out
+    non-finite but possibly as NaN where the reference gives +-inf, because the OTHER operand's zero small part
+    meets it (0 * inf) in the cross terms of the split; nan propagates as nan."""
+    m = n = k = 256
+    a = np.zeros((m, k), np.float32)
+    b = np.zeros((k, n), np.float32)
+    a[np.arange(m), np.arange(m)] = 1.0            # identity: C = B, entry by entry
+    b[:] = rng(2700).uniform(-1, 1, (k, n)).astype(np.float32)
+    b[0, 0], b[1, 1], b[2, 2], b[3, 3] = np.inf, -np.inf, np.nan, np.finfo(np.float32).max
+    b[4, 4] = -np.finfo(np.float32).max
+    with np.errstate(all="ignore"):
+        got = gemm(a, b)
+    assert eml.last_kernel() == "tf32x3_tcgen05"
+    assert not np.isfinite(got[0, 0]) and not np.isfinite(got[1, 1]) and np.isnan(got[2, 2])
+    assert np.isfinite(got[3, 3]) and got[3, 3] >= np.float32(3.4e38) and got[4, 4] <= np.float32(-3.4e38)
+    finite = np.isfinite(b)
+    # every other entry of the rows / columns without special values is the usual f32-accurate copy of B
+    clean = np.ones_like(b, dtype=bool)
+    clean[:5, :] = False
+    clean[:, :5] = False
+    assert np.allclose(got[clean], b[clean], rtol=1e-6, atol=0) and finite.sum() > 0
