@@ -4,6 +4,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <vector>
 #include <memory>
@@ -41,6 +42,18 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 int64_t launches() { return g_launches.load(std::memory_order_relaxed); }
 void set_last_kernel(const char* name) { t_kernel = name; }
 const char* last_kernel() { return t_kernel; }
+
+namespace {
+thread_local bool t_pdl_suppressed = false;
+}
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("EML_PDL");
+        return !(e && e[0] == '0');
+    }();
+    return on && !t_pdl_suppressed;
+}
+void pdl_suppress(bool suppress) { t_pdl_suppressed = suppress; }
 
 int check_launch(const char* what) {
     cudaError_t e = cudaGetLastError();

@@ -33,6 +33,37 @@ const char* last_error();
         return EML_ERR_BAD_ARG;      \
     } while (0)
 
+// Programmatic dependent launch (PDL).  Most of an autodiff step is a chain of short dependent kernels on one stream;
+// launched normally, each pays the full launch latency after its predecessor has drained.  Every kernel of this
+// library starts with pdl_prologue(): it lets the NEXT kernel of the stream be scheduled right away
+// (griddepcontrol.launch_dependents) and then waits until the PREVIOUS kernel has completed and flushed its memory
+// (griddepcontrol.wait) before touching any global data -- so kernels still execute in order, only their launch and
+// prologue overlap the predecessor.  launch_k() sets the matching launch attribute; EML_PDL=0 disables it, and it
+// is off while a step is being captured into a graph.  Launched without the attribute the prologue is a no-op.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_prologue() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+#endif
+bool pdl_enabled();
+void pdl_suppress(bool suppress);  // thread-local (graph capture)
+
+template <class... P, class... A>
+inline cudaError_t launch_k(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, A&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);
+}
+
 // every kernel launch of this library goes through here (bench.py reports the count)
 void count_launch(int n = 1);
 int64_t launches();

@@ -89,6 +89,7 @@ __device__ __forceinline__ void binary_rule(T x, T y, T& z, T& dx, T& dy) {
 template <class T, int OP, bool VEC>
 __global__ void __launch_bounds__(EW_THREADS)
 unary_kernel(T c, const T* __restrict__ x, T* __restrict__ y, T* __restrict__ dydx, int64_t n) {
+    pdl_prologue();
     constexpr int V = VEC ? Vec<T>::N : 1;
     int64_t stride = (int64_t)gridDim.x * blockDim.x * V;
     for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * V; i < n; i += stride) {
@@ -114,6 +115,7 @@ template <class T, int OP, bool VEC>
 __global__ void __launch_bounds__(EW_THREADS)
 binary_kernel(const T* __restrict__ x, const T* __restrict__ y, T* __restrict__ z, T* __restrict__ dzdx,
               T* __restrict__ dzdy, int64_t n) {
+    pdl_prologue();
     constexpr int V = VEC ? Vec<T>::N : 1;
     int64_t stride = (int64_t)gridDim.x * blockDim.x * V;
     for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * V; i < n; i += stride) {
@@ -142,6 +144,7 @@ binary_kernel(const T* __restrict__ x, const T* __restrict__ y, T* __restrict__ 
 template <class T, int MODE, bool VEC>
 __global__ void __launch_bounds__(EW_THREADS)
 axpy_kernel(T c, const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, int64_t n) {
+    pdl_prologue();
     constexpr int V = VEC ? Vec<T>::N : 1;
     int64_t stride = (int64_t)gridDim.x * blockDim.x * V;
     for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * V; i < n; i += stride) {
@@ -201,6 +204,7 @@ template <class T>
 __global__ void __launch_bounds__(RED_THREADS)
 reduce_kernel(const T* __restrict__ x, int64_t incx, const T* __restrict__ y, int64_t incy, int64_t n, int64_t chunk,
               T* partials, unsigned* ticket, T* out, int accumulate) {
+    pdl_prologue();
     __shared__ T smem[RED_THREADS / 32];
     __shared__ bool last;
     int64_t lo = (int64_t)blockIdx.x * chunk, hi = lo + chunk < n ? lo + chunk : n;
@@ -256,7 +260,7 @@ int reduce_impl(const T* x, int64_t incx, const T* y, int64_t incy, int64_t n, T
     EML_TRY(partials.alloc(sizeof(T) * blocks, stream));
     unsigned* ticket = nullptr;
     EML_TRY(ticket_counters(stream, &ticket));
-    reduce_kernel<T><<<blocks, RED_THREADS, 0, stream>>>(x, incx, y, incy, n, chunk, partials.as<T>(), ticket, out,
+    launch_k(reduce_kernel<T>, dim3(blocks), dim3(RED_THREADS), 0, stream, x, incx, y, incy, n, chunk, partials.as<T>(), ticket, out,
                                                          accumulate ? 1 : 0);
     count_launch();
     return check_launch("reduce");
@@ -268,6 +272,7 @@ template <class T>
 __global__ void __launch_bounds__(256)
 col_sums_kernel(const T* __restrict__ x, int64_t rows, int64_t cols, int64_t rows_per_chunk, T* partial,
                 unsigned* tickets, T* __restrict__ out) {
+    pdl_prologue();
     __shared__ T smem[8][33];
     __shared__ bool last;
     int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -298,6 +303,7 @@ col_sums_kernel(const T* __restrict__ x, int64_t rows, int64_t cols, int64_t row
 
 template <class T>
 __global__ void __launch_bounds__(256) row_sums_kernel(const T* __restrict__ x, int64_t rows, int64_t cols, T* __restrict__ out) {
+    pdl_prologue();
     int lane = threadIdx.x & 31;
     int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (r >= rows) return;
@@ -320,6 +326,7 @@ struct EinsumParams {
 
 template <class T>
 __global__ void __launch_bounds__(256) einsum2_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ out, EinsumParams p) {
+    pdl_prologue();
     for (int64_t flat = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; flat < p.total;
          flat += (int64_t)gridDim.x * blockDim.x) {
         int64_t rem = flat, a_off = 0, b_off = 0;
@@ -368,6 +375,7 @@ struct EinsumNParams {
 
 template <class T>
 __global__ void __launch_bounds__(256) einsum_n_kernel(T* __restrict__ out, const __grid_constant__ EinsumNParams p) {
+    pdl_prologue();
     for (int64_t flat = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; flat < p.total;
          flat += (int64_t)gridDim.x * blockDim.x) {
         int64_t off[MAX_OPS];
@@ -416,9 +424,9 @@ template <class T, int OP>
 int launch_unary_op(T c, const T* x, T* y, T* dydx, int64_t n, cudaStream_t stream) {
     bool vec = aligned16(x) && (!y || aligned16(y)) && (!dydx || aligned16(dydx));
     if (vec)
-        unary_kernel<T, OP, true><<<ew_grid(n, Vec<T>::N), EW_THREADS, 0, stream>>>(c, x, y, dydx, n);
+        launch_k(unary_kernel<T, OP, true>, dim3(ew_grid(n, Vec<T>::N)), dim3(EW_THREADS), 0, stream, c, x, y, dydx, n);
     else
-        unary_kernel<T, OP, false><<<ew_grid(n, 1), EW_THREADS, 0, stream>>>(c, x, y, dydx, n);
+        launch_k(unary_kernel<T, OP, false>, dim3(ew_grid(n, 1)), dim3(EW_THREADS), 0, stream, c, x, y, dydx, n);
     count_launch();
     return check_launch("unary");
 }
@@ -428,9 +436,9 @@ int launch_binary_op(const T* x, const T* y, T* z, T* dzdx, T* dzdy, int64_t n, 
     bool vec = aligned16(x) && aligned16(y) && (!z || aligned16(z)) && (!dzdx || aligned16(dzdx)) &&
                (!dzdy || aligned16(dzdy));
     if (vec)
-        binary_kernel<T, OP, true><<<ew_grid(n, Vec<T>::N), EW_THREADS, 0, stream>>>(x, y, z, dzdx, dzdy, n);
+        launch_k(binary_kernel<T, OP, true>, dim3(ew_grid(n, Vec<T>::N)), dim3(EW_THREADS), 0, stream, x, y, z, dzdx, dzdy, n);
     else
-        binary_kernel<T, OP, false><<<ew_grid(n, 1), EW_THREADS, 0, stream>>>(x, y, z, dzdx, dzdy, n);
+        launch_k(binary_kernel<T, OP, false>, dim3(ew_grid(n, 1)), dim3(EW_THREADS), 0, stream, x, y, z, dzdx, dzdy, n);
     count_launch();
     return check_launch("binary");
 }
@@ -440,9 +448,9 @@ int launch_axpy(T c, const T* a, const T* b, T* out, int64_t n, cudaStream_t str
     if (n <= 0) return EML_OK;
     bool vec = aligned16(out) && (!a || aligned16(a)) && (!b || aligned16(b));
     if (vec)
-        axpy_kernel<T, MODE, true><<<ew_grid(n, Vec<T>::N), EW_THREADS, 0, stream>>>(c, a, b, out, n);
+        launch_k(axpy_kernel<T, MODE, true>, dim3(ew_grid(n, Vec<T>::N)), dim3(EW_THREADS), 0, stream, c, a, b, out, n);
     else
-        axpy_kernel<T, MODE, false><<<ew_grid(n, 1), EW_THREADS, 0, stream>>>(c, a, b, out, n);
+        launch_k(axpy_kernel<T, MODE, false>, dim3(ew_grid(n, 1)), dim3(EW_THREADS), 0, stream, c, a, b, out, n);
     count_launch();
     return check_launch("axpy");
 }
@@ -526,14 +534,14 @@ int launch_col_sums(const T* x, int64_t rows, int64_t cols, T* out, cudaStream_t
     if (grid.x > (unsigned)MAX_TICKETS) EML_BAD_ARG("col_sums: more than %d column blocks", MAX_TICKETS);
     unsigned* tickets = nullptr;
     EML_TRY(ticket_counters(stream, &tickets));
-    col_sums_kernel<T><<<grid, 256, 0, stream>>>(x, rows, cols, rpc, partial.as<T>(), tickets, out);
+    launch_k(col_sums_kernel<T>, dim3(grid), dim3(256), 0, stream, x, rows, cols, rpc, partial.as<T>(), tickets, out);
     count_launch();
     return check_launch("col_sums");
 }
 
 template <class T>
 int launch_row_sums(const T* x, int64_t rows, int64_t cols, T* out, cudaStream_t stream) {
-    row_sums_kernel<T><<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(x, rows, cols, out);
+    launch_k(row_sums_kernel<T>, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, stream, x, rows, cols, out);
     count_launch();
     return check_launch("row_sums");
 }
@@ -545,6 +553,7 @@ template <class T>
 __global__ void __launch_bounds__(256)
 center_kernel(const T* __restrict__ x, const T* __restrict__ sums, T samples, int64_t rows, int64_t cols, int axis,
               T* __restrict__ out) {
+    pdl_prologue();
     const int64_t n = rows * cols;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t f = axis == 1 ? i % cols : i / cols;
@@ -559,7 +568,7 @@ int launch_center(const T* x, const T* sums, int64_t samples, int64_t rows, int6
     int64_t want = (rows * cols + 255) / 256;
     int blocks = (int)(want < 148 * 16 ? want : 148 * 16);
     if (blocks < 1) blocks = 1;
-    center_kernel<T><<<blocks, 256, 0, stream>>>(x, sums, (T)samples, rows, cols, axis, out);
+    launch_k(center_kernel<T>, dim3(blocks), dim3(256), 0, stream, x, sums, (T)samples, rows, cols, axis, out);
     count_launch();
     return check_launch("center");
 }
@@ -592,7 +601,7 @@ int launch_einsum2(const T* A, const T* B, T* out, int n_out, const int64_t* out
     if (p.total == 0) return EML_OK;
     int64_t blocks = (p.total + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    einsum2_kernel<T><<<(unsigned)blocks, 256, 0, stream>>>(A, B, out, p);
+    launch_k(einsum2_kernel<T>, dim3((unsigned)blocks), dim3(256), 0, stream, A, B, out, p);
     count_launch();
     set_last_kernel("einsum_generic");
     return check_launch("einsum2");
@@ -625,7 +634,7 @@ int launch_einsum_n(int n_ops, const T* const* x, T* out, int n_out, const int64
     if (p.total == 0) return EML_OK;
     int64_t blocks = (p.total + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    einsum_n_kernel<T><<<(unsigned)blocks, 256, 0, stream>>>(out, p);
+    launch_k(einsum_n_kernel<T>, dim3((unsigned)blocks), dim3(256), 0, stream, out, p);
     count_launch();
     set_last_kernel("einsum_generic");
     return check_launch("einsum_n");

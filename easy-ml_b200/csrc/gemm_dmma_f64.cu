@@ -101,6 +101,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 dgemm_dmma_kernel(const double* __restrict__ A, const double* __restrict__ B, double* C, int64_t M,
                   int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int64_t strideA, int64_t strideB,
                   int64_t strideC, int tiles_m, int tiles_n, int accumulate) {
+    pdl_prologue();
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
@@ -215,7 +216,7 @@ int launch_variant(const double* A, const double* B, double* C, int64_t batch, i
     int64_t tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
     if (tiles_m * tiles_n > 0x7fffffffLL || batch > 65535) EML_BAD_ARG("dgemm_dmma: grid too large");
     dim3 grid((unsigned)(tiles_m * tiles_n), (unsigned)batch);
-    kern<<<grid, THREADS, SMEM_BYTES, stream>>>(A, B, C, M, N, K, lda, ldb, ldc, stA, stB, stC, (int)tiles_m,
+    launch_k(kern, dim3(grid), dim3(THREADS), SMEM_BYTES, stream, A, B, C, M, N, K, lda, ldb, ldc, stA, stB, stC, (int)tiles_m,
                                                 (int)tiles_n, accumulate ? 1 : 0);
     count_launch();
     set_last_kernel("dmma_f64");
@@ -265,6 +266,7 @@ __global__ void __launch_bounds__(TTHREADS, 1)
 dgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, double* C,
                  int64_t M, int64_t N, int64_t K, int64_t ldc, int64_t strideC, int tiles_m, int tiles_n,
                  int accumulate, const Remote remote) {
+    pdl_prologue();
     using namespace sm100;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     // offset (not a cast through an integer) so the compiler keeps the shared address space: LDS, not LD
@@ -452,7 +454,7 @@ int launch(const double* A, const double* B, double* C, int64_t batch, int64_t M
     dim3 grid((unsigned)(tiles_m * tiles_n), (unsigned)batch);
     const Remote remote = t_remote;
     t_remote.n = 0;  // consumed: the caller checks remote_c_pending() to see whether a kernel took them
-    kern<<<grid, TTHREADS, T_SMEM_BYTES, stream>>>(mapA, mapB, C, M, N, K, ldc, stC, (int)tiles_m, (int)tiles_n,
+    launch_k(kern, dim3(grid), dim3(TTHREADS), T_SMEM_BYTES, stream, mapA, mapB, C, M, N, K, ldc, stC, (int)tiles_m, (int)tiles_n,
                                                    accumulate ? 1 : 0, remote);
     count_launch();
     set_last_kernel(remote.n ? "dmma_f64_tma+peer_allgather" : "dmma_f64_tma");
@@ -469,6 +471,7 @@ int launch(const double* A, const double* B, double* C, int64_t batch, int64_t M
 // ------------------------------------------------------------------------------------------------
 namespace {
 __global__ void __launch_bounds__(256, 1) dmma_peak_kernel(double* out, int iters) {
+    pdl_prologue();
     double acc[32][2];
 #pragma unroll
     for (int i = 0; i < 32; i++) acc[i][0] = acc[i][1] = 0.0;
@@ -491,9 +494,9 @@ int measure_dmma_peak(DeviceCtx* ctx, double* tflops) {
     cudaEvent_t e0, e1;
     EML_CUDA(cudaEventCreate(&e0));
     EML_CUDA(cudaEventCreate(&e1));
-    dmma_peak_kernel<<<sms, 256>>>(d, iters / 10);  // warm-up
+    launch_k(dmma_peak_kernel, dim3(sms), dim3(256), 0, nullptr, d, iters / 10);  // warm-up
     EML_CUDA(cudaEventRecord(e0));
-    dmma_peak_kernel<<<sms, 256>>>(d, iters);
+    launch_k(dmma_peak_kernel, dim3(sms), dim3(256), 0, nullptr, d, iters);
     EML_CUDA(cudaEventRecord(e1));
     EML_CUDA(cudaEventSynchronize(e1));
     float ms = 0;

@@ -33,6 +33,7 @@ template <class T, bool EXACT>
 __global__ void __launch_bounds__(THREADS)
 gemm_simt_kernel(const T* __restrict__ A, const T* __restrict__ B, T* C, int64_t batch, int64_t M,
                  int64_t N, int64_t K, Strides3 sA, Strides3 sB, Strides3 sC, int accumulate, int64_t tiles_n) {
+    pdl_prologue();
     __shared__ T As[BK][BM + PAD];
     __shared__ T Bs[BK][BN + PAD];
     const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
@@ -140,10 +141,9 @@ int launch_gemm_simt(const T* A, const T* B, T* C, int64_t batch, int64_t M, int
     if (tiles_m * tiles_n > 0x7fffffffLL) EML_BAD_ARG("gemm_simt: too many tiles");
     dim3 grid((unsigned)(tiles_m * tiles_n), (unsigned)(batch < 65535 ? batch : 65535));
     if (exact)
-        gemm_simt_kernel<T, true><<<grid, THREADS, 0, stream>>>(A, B, C, batch, M, N, K, sA, sB, sC, 0, tiles_n);
+        launch_k(gemm_simt_kernel<T, true>, dim3(grid), dim3(THREADS), 0, stream, A, B, C, batch, M, N, K, sA, sB, sC, 0, tiles_n);
     else
-        gemm_simt_kernel<T, false>
-            <<<grid, THREADS, 0, stream>>>(A, B, C, batch, M, N, K, sA, sB, sC, accumulate ? 1 : 0, tiles_n);
+        launch_k(gemm_simt_kernel<T, false>, dim3(grid), dim3(THREADS), 0, stream, A, B, C, batch, M, N, K, sA, sB, sC, accumulate ? 1 : 0, tiles_n);
     count_launch();
     set_last_kernel(exact ? "simt_exact" : "simt");
     return check_launch("gemm_simt");
@@ -162,6 +162,7 @@ template <class T>
 __global__ void __launch_bounds__(SK_THREADS)
 gemm_skinny_kernel(const T* __restrict__ A, const T* __restrict__ B, T* C, int64_t batch, int64_t M, int N, int64_t K,
                    Strides3 sA, Strides3 sB, Strides3 sC, int accumulate) {
+    pdl_prologue();
     constexpr int KC = 2048 / sizeof(T);  // k chunk: 512 (f32) / 256 (f64) -> 32 KB of shared memory
     constexpr int PER_LANE = KC / 32;     // loads one lane keeps in flight per chunk
     __shared__ T sBk[SK_NMAX][KC];
@@ -172,10 +173,12 @@ gemm_skinny_kernel(const T* __restrict__ A, const T* __restrict__ B, T* C, int64
     auto stage = [&](const T* Bb, int64_t k0, int kc) {
         // one k per thread and pass: its N loads are independent (all in flight together) and the stores are
         // conflict free (consecutive threads, consecutive k)
-        for (int k = threadIdx.x; k < kc; k += SK_THREADS) {
+        // (the tail [kc, KC) is zero filled: the compute loop multiplies it by zero-padded A values, and stale
+        //  shared memory could hold NaN / Inf patterns)
+        for (int k = threadIdx.x; k < KC; k += SK_THREADS) {
             T v[SK_NMAX];
 #pragma unroll
-            for (int n = 0; n < SK_NMAX; n++) v[n] = n < N ? Bb[(k0 + k) * sB.r + n * sB.c] : T(0);
+            for (int n = 0; n < SK_NMAX; n++) v[n] = (n < N && k < kc) ? Bb[(k0 + k) * sB.r + n * sB.c] : T(0);
 #pragma unroll
             for (int n = 0; n < SK_NMAX; n++)
                 if (n < N) sBk[n][k] = v[n];
@@ -241,6 +244,7 @@ template <class T>
 __global__ void __launch_bounds__(TN_THREADS)
 gemm_skinny_tn_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ ws, int64_t M, int N, int64_t K,
                       Strides3 sA, Strides3 sB, int64_t k_per_chunk) {
+    pdl_prologue();
     __shared__ T sB_[TN_KC][SK_NMAX];
     const int64_t m = (int64_t)blockIdx.x * TN_THREADS + threadIdx.x;
     const int64_t kc0 = (int64_t)blockIdx.y * k_per_chunk, kc1 = kc0 + k_per_chunk < K ? kc0 + k_per_chunk : K;
@@ -299,7 +303,7 @@ int launch_gemm_skinny_tn(DeviceCtx* ctx, const T* A, const T* B, T* C, int64_t 
     TempBuf ws;
     EML_TRY(ws.alloc(sizeof(T) * (size_t)(chunks * M * N), stream));
     dim3 grid((unsigned)m_blocks, (unsigned)chunks);
-    gemm_skinny_tn_kernel<T><<<grid, TN_THREADS, 0, stream>>>(A, B, ws.as<T>(), M, (int)N, K, sA, sB, k_per_chunk);
+    launch_k(gemm_skinny_tn_kernel<T>, dim3(grid), dim3(TN_THREADS), 0, stream, A, B, ws.as<T>(), M, (int)N, K, sA, sB, k_per_chunk);
     count_launch();
     set_last_kernel("skinny_tn");
     EML_TRY(check_launch("gemm_skinny_tn"));
@@ -315,7 +319,7 @@ int launch_gemm_skinny(const T* A, const T* B, T* C, int64_t batch, int64_t M, i
                        Strides3 sB, Strides3 sC, bool accumulate, cudaStream_t stream) {
     int64_t blocks = ((M + SK_WARPS - 1) / SK_WARPS) * batch;
     if (blocks > 148 * 6) blocks = 148 * 6;
-    gemm_skinny_kernel<T><<<(unsigned)blocks, SK_THREADS, 0, stream>>>(A, B, C, batch, M, (int)N, K, sA, sB, sC,
+    launch_k(gemm_skinny_kernel<T>, dim3((unsigned)blocks), dim3(SK_THREADS), 0, stream, A, B, C, batch, M, (int)N, K, sA, sB, sC,
                                                                        accumulate ? 1 : 0);
     count_launch();
     set_last_kernel("skinny_n");
@@ -331,6 +335,7 @@ template <class T>
 __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const T* __restrict__ ws, int splits, int64_t split_stride, T* __restrict__ C, int64_t M,
                      int64_t N, Strides3 sC, int64_t batch, int accumulate) {
+    pdl_prologue();
     const int64_t total = batch * M * N;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int64_t b = i / (M * N), r = (i / N) % M, c = i % N;
@@ -349,6 +354,7 @@ template <class T>
 __global__ void __launch_bounds__(256)
 splitk_reduce_warp_kernel(const T* __restrict__ ws, int splits, int64_t split_stride, T* __restrict__ C, int64_t M,
                           int64_t N, Strides3 sC, int64_t batch, int accumulate) {
+    pdl_prologue();
     const int lane = threadIdx.x & 31;
     const int64_t total = batch * M * N;
     for (int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); i < total; i += (int64_t)gridDim.x * 8) {
@@ -372,13 +378,13 @@ int launch_splitk_reduce(const T* ws, int splits, T* C, int64_t batch, int64_t M
     if (total == 0) return EML_OK;
     if (total <= 8192 && splits >= 16) {
         int blocks = (int)((total + 7) / 8);
-        splitk_reduce_warp_kernel<T><<<blocks, 256, 0, stream>>>(ws, splits, total, C, M, N, sC, batch, accumulate ? 1 : 0);
+        launch_k(splitk_reduce_warp_kernel<T>, dim3(blocks), dim3(256), 0, stream, ws, splits, total, C, M, N, sC, batch, accumulate ? 1 : 0);
         count_launch();
         return check_launch("split-K reduce (warp per element)");
     }
     int64_t want = (total + 255) / 256;
     int blocks = (int)(want < 148 * 8 ? want : 148 * 8);
-    splitk_reduce_kernel<T><<<blocks, 256, 0, stream>>>(ws, splits, total, C, M, N, sC, batch, accumulate ? 1 : 0);
+    launch_k(splitk_reduce_kernel<T>, dim3(blocks), dim3(256), 0, stream, ws, splits, total, C, M, N, sC, batch, accumulate ? 1 : 0);
     count_launch();
     return check_launch("split-K reduce");
 }

@@ -81,6 +81,7 @@ __device__ __forceinline__ void split_tf32(float x, float& big, float& small) {
 __global__ void __launch_bounds__(256)
 split_pack_kernel(const float* __restrict__ src, float* __restrict__ big, float* __restrict__ small, int64_t MN,
                   int64_t K, int64_t MNp, int64_t Kp, int64_t sb, int64_t smn, int64_t sk, int k_fast) {
+    pdl_prologue();
     __shared__ float tile[32][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
     const int64_t k0 = (int64_t)blockIdx.x * 32, mn0 = (int64_t)blockIdx.y * 32, b = blockIdx.z;
@@ -139,6 +140,7 @@ template <bool K_FAST>
 __global__ void __launch_bounds__(256)
 split_pack_vec_kernel(const float* __restrict__ src, float* __restrict__ big, float* __restrict__ small, int64_t MN,
                       int64_t K, int64_t MNp, int64_t Kp, int64_t sb, int64_t s_slow) {
+    pdl_prologue();
     const int tid = threadIdx.x;
     const int64_t k0 = (int64_t)blockIdx.x * 64, mn0 = (int64_t)blockIdx.y * 64, b = blockIdx.z;
     const float* s = src + b * sb;
@@ -188,12 +190,12 @@ int launch_split_pack(const float* src, float* big, float* small, int64_t batch,
     const bool al = (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (sb & 3) == 0;
     dim3 vgrid((unsigned)((Kp + 63) / 64), (unsigned)((MNp + 63) / 64), (unsigned)batch);
     if (al && sk == 1 && (smn & 3) == 0) {
-        split_pack_vec_kernel<true><<<vgrid, 256, 0, stream>>>(src, big, small, MN, K, MNp, Kp, sb, smn);
+        launch_k(split_pack_vec_kernel<true>, dim3(vgrid), dim3(256), 0, stream, src, big, small, MN, K, MNp, Kp, sb, smn);
     } else if (al && smn == 1 && (sk & 3) == 0) {
-        split_pack_vec_kernel<false><<<vgrid, 256, 0, stream>>>(src, big, small, MN, K, MNp, Kp, sb, sk);
+        launch_k(split_pack_vec_kernel<false>, dim3(vgrid), dim3(256), 0, stream, src, big, small, MN, K, MNp, Kp, sb, sk);
     } else {
         dim3 grid((unsigned)(Kp / 32), (unsigned)(MNp / 32), (unsigned)batch);
-        split_pack_kernel<<<grid, 256, 0, stream>>>(src, big, small, MN, K, MNp, Kp, sb, smn, sk, sk == 1);
+        launch_k(split_pack_kernel, dim3(grid), dim3(256), 0, stream, src, big, small, MN, K, MNp, Kp, sb, smn, sk, sk == 1);
     }
     count_launch();
     return check_launch("tf32x3 split/pack");
@@ -211,6 +213,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 tf32x3_kernel(const __grid_constant__ Maps maps, float* __restrict__ C, int64_t M, int64_t N, int64_t ldc,
               int64_t strideC, int kblocks_total, int kblocks_per_split, int accumulate, float* __restrict__ ws,
               int64_t ws_split_stride) {
+    pdl_prologue();
     using cfg = Cfg<BN>;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -411,6 +414,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 tf32x3_pair_kernel(const __grid_constant__ Maps maps, float* __restrict__ C, int64_t M, int64_t N, int64_t ldc,
                    int64_t strideC, int kblocks_total, int kblocks_per_split, int splits, int tiles_m, int tiles_n,
                    int work_items, int accumulate, float* __restrict__ ws, int64_t ws_split_stride) {
+    pdl_prologue();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* full = reinterpret_cast<uint64_t*>(base + (size_t)STAGES * STAGE_BYTES);
@@ -600,7 +604,7 @@ int launch(const Maps& maps, float* C, int64_t batch, int64_t M, int64_t N, int6
     if (items > 0x7fffffffLL) EML_BAD_ARG("tf32x3: too many work items");
     int clusters = sms / 2;
     if (items < clusters) clusters = (int)items;
-    tf32x3_pair_kernel<<<2 * clusters, THREADS, SMEM_BYTES, stream>>>(
+    launch_k(tf32x3_pair_kernel, dim3(2 * clusters), dim3(THREADS), SMEM_BYTES, stream, 
         maps, C, M, N, ldc, strideC, kblocks, per_split, used_splits, tiles_m, tiles_n, (int)items, accumulate ? 1 : 0, ws,
         batch * M * N);
     count_launch();
@@ -636,7 +640,7 @@ int launch_tile(const Maps& maps, float* C, int64_t batch, int64_t M, int64_t N,
     int per_split = (kblocks + splits - 1) / splits;
     int used_splits = (kblocks + per_split - 1) / per_split;  // every split owns >= 1 k block
     dim3 grid((unsigned)tiles, (unsigned)batch, (unsigned)used_splits);
-    kern<<<grid, GEMM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(maps, C, M, N, ldc, strideC, kblocks, per_split,
+    launch_k(kern, dim3(grid), dim3(GEMM_THREADS), Cfg<BN>::SMEM_BYTES, stream, maps, C, M, N, ldc, strideC, kblocks, per_split,
                                                               accumulate ? 1 : 0, ws, batch * M * N);
     count_launch();
     EML_TRY(check_launch("tf32x3_tcgen05"));

@@ -644,6 +644,7 @@ int eml_tape_capture_begin(eml_tape* t) {
     t->capture_len = t->len;
     t->capture_nodes = t->nodes.size();
     stream_alloc_forbid_new(true);
+    pdl_suppress(true);  // recorded kernels take plain stream-order edges
     return EML_OK;
 }
 
@@ -657,6 +658,7 @@ int eml_tape_capture_end(eml_tape* t, eml_graph** out) {
     }
     t->capturing = false;
     stream_alloc_forbid_new(false);
+    pdl_suppress(false);
     cudaGraph_t graph = nullptr;
     cudaError_t e = cudaStreamEndCapture(t->stream, &graph);
     if (e != cudaSuccess || !graph) {
