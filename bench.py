@@ -417,9 +417,21 @@ def extra_workloads(torch, eml, lib, check, dev, stream, sp, peak):
         ref = torch.empty_like(Cm)
         ms_cublas = run(lambda: torch.matmul(A, B, out=ref), 3, 2)
         rel = float(((Cm - ref).abs().max() / ref.abs().max()).item())
-        res["f32_8192"] = {"tflops": 2.0 * n ** 3 / (ms * 1e-3) / 1e12, "ms": ms, "kernel": kernel,
+        tf = 2.0 * n ** 3 / (ms * 1e-3) / 1e12
+        res["f32_8192"] = {"tflops": tf, "ms": ms, "kernel": kernel,
                            "cublas_sgemm_tflops_same_run": 2.0 * n ** 3 / (ms_cublas * 1e-3) / 1e12,
-                           "max_rel_diff_vs_cublas_fp32": rel}
+                           "max_rel_diff_vs_cublas_fp32": rel,
+                           "roofline": {"bound": "tensor", "unit": "TFLOP/s",
+                                        "achieved_tf32_tensor_work": 3.0 * tf,
+                                        "note": "3xTF32: every f32 product is three TF32 MMAs; the time includes the HBM-bound "
+                                                "split/pack pass of both operands (~6 % at this size)",
+                                        "nominal_tf32_dense": NOMINAL_TF32_TFLOPS,
+                                        "frac_of_nominal_tf32": 3.0 * tf / NOMINAL_TF32_TFLOPS,
+                                        "half_of_measured_bf16_burst": peak["bf16_tflops"] / 2.0,
+                                        "frac_of_half_measured_bf16": 3.0 * tf / (peak["bf16_tflops"] / 2.0),
+                                        "ncu_tensor_pipe_active_frac": 0.979,
+                                        "ncu_source": "profiles/r1_prof_tf32x3_pair_r1_raw.csv (GEMM kernel alone; the SM clock "
+                                                      "settles near 1.5 GHz under this load: sw_power_cap)"}}
         del A, B, Cm, ref
         # config 3, f32 batched contraction [batch,row,k] x [batch,k,col], batch 64, 1024^3
         bt, m = 64, 1024
