@@ -3,6 +3,7 @@
 #include <cstring>
 
 #include "common.h"
+#include "host_staging.h"
 
 namespace eml {
 
@@ -151,8 +152,9 @@ inline bool nonneg(Strides3 s) { return s.b >= 0 && s.r >= 0 && s.c >= 0; }
 //            chain, so this equals one launch over the whole K);
 //   phase 2 (B resident): the remaining rows in row panels -- A panel p+1 uploads and C panel p-1 downloads
 //            while panel p is multiplied.
-// Three streams (H2D, compute, D2H) ordered by events.  Host buffers should be pinned (eml_host_alloc, or
-// cudaHostRegister by the caller) for the copies to be truly asynchronous; pageable memory still works.
+// Three streams (H2D, compute, D2H) ordered by events.  Page-locked caller buffers (eml_host_alloc) are copied
+// directly; pageable ones (a Rust Vec<T>, a numpy array) go through the StagedCopier's ring of page-locked slots
+// filled / drained by a thread pool, so the copies stay asynchronous either way.
 template <class T>
 int gemm_host_pipelined(DeviceCtx* ctx, const T* A, const T* B, T* C, int64_t M, int64_t N, int64_t K, int64_t lda,
                         int64_t ldb, int64_t ldc) {
@@ -193,13 +195,13 @@ int gemm_host_pipelined(DeviceCtx* ctx, const T* A, const T* B, T* C, int64_t M,
     int64_t R = whole_waves(1152, M - M1 > 0 ? M - M1 : 1);  // row panel of phase 2 (the last one takes the rest)
     if (R < tile) R = tile;
     NoSplitK no_split;  // same bits as one device launch over the whole problem
+    StagedCopier mover(ctx);
 
     // the previous call's work on these streams is complete (every call ends with a synchronize)
     for (int64_t k0 = 0, q = 0; k0 < K; k0 += kq, q++) {
         const int64_t k1 = k0 + kq < K ? k0 + kq : K;
-        EML_CUDA(cudaMemcpy2DAsync(dB + k0 * N, N * es, B + k0 * ldb, ldb * es, N * es, k1 - k0,
-                                   cudaMemcpyHostToDevice, in));
-        EML_CUDA(cudaMemcpy2DAsync(dA + k0, K * es, A + k0, lda * es, (k1 - k0) * es, M1, cudaMemcpyHostToDevice, in));
+        EML_TRY(mover.h2d(dB + k0 * N, N * es, B + k0 * ldb, ldb * es, N * es, k1 - k0, in));
+        EML_TRY(mover.h2d(dA + k0, K * es, A + k0, lda * es, (k1 - k0) * es, M1, in));
         cudaEvent_t e = next_event();
         EML_CUDA(cudaEventRecord(e, in));
         EML_CUDA(cudaStreamWaitEvent(cs, e, 0));
@@ -210,12 +212,11 @@ int gemm_host_pipelined(DeviceCtx* ctx, const T* A, const T* B, T* C, int64_t M,
         cudaEvent_t e = next_event();
         EML_CUDA(cudaEventRecord(e, cs));
         EML_CUDA(cudaStreamWaitEvent(out, e, 0));
-        EML_CUDA(cudaMemcpy2DAsync(C, ldc * es, dC, N * es, N * es, M1, cudaMemcpyDeviceToHost, out));
+        EML_TRY(mover.d2h(C, ldc * es, dC, N * es, N * es, M1, out));
     }
     for (int64_t r0 = M1; r0 < M; r0 += R) {
         const int64_t r1 = r0 + R < M ? r0 + R : M;
-        EML_CUDA(cudaMemcpy2DAsync(dA + r0 * K, K * es, A + r0 * lda, lda * es, K * es, r1 - r0, cudaMemcpyHostToDevice,
-                                   in));
+        EML_TRY(mover.h2d(dA + r0 * K, K * es, A + r0 * lda, lda * es, K * es, r1 - r0, in));
         cudaEvent_t e = next_event();
         EML_CUDA(cudaEventRecord(e, in));
         EML_CUDA(cudaStreamWaitEvent(cs, e, 0));
@@ -224,9 +225,9 @@ int gemm_host_pipelined(DeviceCtx* ctx, const T* A, const T* B, T* C, int64_t M,
         cudaEvent_t d = next_event();
         EML_CUDA(cudaEventRecord(d, cs));
         EML_CUDA(cudaStreamWaitEvent(out, d, 0));
-        EML_CUDA(cudaMemcpy2DAsync(C + r0 * ldc, ldc * es, dC + r0 * N, N * es, N * es, r1 - r0, cudaMemcpyDeviceToHost,
-                                   out));
+        EML_TRY(mover.d2h(C + r0 * ldc, ldc * es, dC + r0 * N, N * es, N * es, r1 - r0, out));
     }
+    EML_TRY(mover.finish());
     EML_CUDA(cudaStreamSynchronize(out));
     EML_CUDA(cudaStreamSynchronize(cs));
     EML_CUDA(cudaStreamSynchronize(in));

@@ -1,0 +1,221 @@
+// host_staging.cu -- see host_staging.h
+#include "host_staging.h"
+
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <cstring>
+#include <functional>
+#include <mutex>
+#include <thread>
+
+namespace eml {
+
+bool host_pointer_is_pinned(const void* p) {
+    cudaPointerAttributes attr{};
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged;
+}
+
+namespace {
+
+// A tiny persistent pool: run(n, fn) calls fn(0..n-1) over the workers and the calling thread.
+class CopyPool {
+  public:
+    static CopyPool& get() {
+        static CopyPool* pool = new CopyPool();  // never destroyed: its detached workers outlive static destruction
+        return *pool;
+    }
+    void run(int64_t n, const std::function<void(int64_t)>& fn) {
+        if (n <= 0) return;
+        if (n == 1 || workers_.empty()) {
+            for (int64_t i = 0; i < n; i++) fn(i);
+            return;
+        }
+        std::unique_lock<std::mutex> lock(mu_);
+        fn_ = &fn;
+        total_ = n;
+        next_.store(0);
+        done_ = 0;
+        generation_++;
+        lock.unlock();
+        cv_.notify_all();
+        work();
+        lock.lock();
+        idle_.wait(lock, [&] { return done_ == (int)workers_.size(); });
+        fn_ = nullptr;
+    }
+
+  private:
+    CopyPool() {
+        unsigned hw = std::thread::hardware_concurrency();
+        int n = hw > 2 ? (int)std::min(7u, hw - 1) : 0;
+        for (int i = 0; i < n; i++) workers_.emplace_back([this] { loop(); });
+        for (auto& t : workers_) t.detach();
+    }
+    void work() {
+        for (;;) {
+            int64_t i = next_.fetch_add(1);
+            if (i >= total_) break;
+            (*fn_)(i);
+        }
+    }
+    void loop() {
+        uint64_t seen = 0;
+        for (;;) {
+            std::unique_lock<std::mutex> lock(mu_);
+            cv_.wait(lock, [&] { return generation_ != seen; });
+            seen = generation_;
+            lock.unlock();
+            work();
+            lock.lock();
+            if (++done_ == (int)workers_.size()) idle_.notify_one();
+        }
+    }
+    std::mutex mu_;
+    std::condition_variable cv_, idle_;
+    std::vector<std::thread> workers_;
+    const std::function<void(int64_t)>* fn_ = nullptr;
+    int64_t total_ = 0;
+    std::atomic<int64_t> next_{0};
+    int done_ = 0;
+    uint64_t generation_ = 0;
+};
+
+constexpr int SLOTS = 8;
+constexpr size_t SLOT_BYTES = size_t(16) << 20;
+
+struct Ring {
+    void* slot[SLOTS] = {};
+    cudaEvent_t ev[SLOTS] = {};
+    bool in_flight[SLOTS] = {};
+};
+std::mutex g_ring_mu;
+std::vector<std::pair<int, Ring*>> g_rings;  // per device
+
+int ring_for(int device, Ring** out) {
+    std::lock_guard<std::mutex> lock(g_ring_mu);
+    for (auto& r : g_rings)
+        if (r.first == device) {
+            *out = r.second;
+            return EML_OK;
+        }
+    auto* r = new Ring();
+    for (int i = 0; i < SLOTS; i++) {
+        EML_CUDA(cudaHostAlloc(&r->slot[i], SLOT_BYTES, cudaHostAllocDefault));
+        EML_CUDA(cudaEventCreateWithFlags(&r->ev[i], cudaEventDisableTiming));
+    }
+    g_rings.emplace_back(device, r);
+    *out = r;
+    return EML_OK;
+}
+
+}  // namespace
+
+void parallel_copy_rows(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, int64_t rows) {
+    if (rows <= 0 || width == 0) return;
+    // blocks of whole rows, ~512 KB each
+    int64_t rows_per_block = std::max<int64_t>(1, (int64_t)((size_t(512) << 10) / width));
+    int64_t blocks = (rows + rows_per_block - 1) / rows_per_block;
+    CopyPool::get().run(blocks, [&](int64_t b) {
+        int64_t r0 = b * rows_per_block, r1 = std::min(rows, r0 + rows_per_block);
+        if (dpitch == width && spitch == width) {
+            memcpy((char*)dst + r0 * width, (const char*)src + r0 * width, (size_t)(r1 - r0) * width);
+        } else {
+            for (int64_t r = r0; r < r1; r++) memcpy((char*)dst + r * dpitch, (const char*)src + r * spitch, width);
+        }
+    });
+}
+
+int StagedCopier::acquire(int* slot) {
+    Ring* ring = nullptr;
+    EML_TRY(ring_for(ctx_->device, &ring));
+    const int s = next_++ % SLOTS;
+    // a pending device-to-host chunk in this slot must reach the caller's memory first
+    for (size_t i = 0; i < pending_.size(); i++)
+        if (pending_[i].slot == s) {
+            Pending p = pending_[i];
+            pending_.erase(pending_.begin() + i);
+            EML_TRY(complete(p));
+            break;
+        }
+    if (ring->in_flight[s]) {
+        EML_CUDA(cudaEventSynchronize(ring->ev[s]));
+        ring->in_flight[s] = false;
+    }
+    *slot = s;
+    return EML_OK;
+}
+
+int StagedCopier::complete(const Pending& p) {
+    Ring* ring = nullptr;
+    EML_TRY(ring_for(ctx_->device, &ring));
+    EML_CUDA(cudaEventSynchronize(ring->ev[p.slot]));
+    ring->in_flight[p.slot] = false;
+    parallel_copy_rows(p.dst, p.dpitch, ring->slot[p.slot], p.width, p.width, p.rows);
+    return EML_OK;
+}
+
+int StagedCopier::h2d(void* dst_dev, size_t dpitch, const void* src_host, size_t spitch, size_t width, int64_t rows,
+                      cudaStream_t stream) {
+    if (rows <= 0 || width == 0) return EML_OK;
+    if (host_pointer_is_pinned(src_host)) {
+        EML_CUDA(cudaMemcpy2DAsync(dst_dev, dpitch, src_host, spitch, width, rows, cudaMemcpyHostToDevice, stream));
+        return EML_OK;
+    }
+    if (width > SLOT_BYTES) EML_BAD_ARG("staged copy: a row of %zu bytes does not fit a staging slot", width);
+    Ring* ring = nullptr;
+    EML_TRY(ring_for(ctx_->device, &ring));
+    const int64_t chunk = std::max<int64_t>(1, (int64_t)(SLOT_BYTES / width));
+    for (int64_t r0 = 0; r0 < rows; r0 += chunk) {
+        const int64_t n = std::min(chunk, rows - r0);
+        int s;
+        EML_TRY(acquire(&s));
+        parallel_copy_rows(ring->slot[s], width, (const char*)src_host + r0 * spitch, spitch, width, n);
+        EML_CUDA(cudaMemcpy2DAsync((char*)dst_dev + r0 * dpitch, dpitch, ring->slot[s], width, width, n,
+                                   cudaMemcpyHostToDevice, stream));
+        EML_CUDA(cudaEventRecord(ring->ev[s], stream));
+        ring->in_flight[s] = true;
+    }
+    return EML_OK;
+}
+
+int StagedCopier::d2h(void* dst_host, size_t dpitch, const void* src_dev, size_t spitch, size_t width, int64_t rows,
+                      cudaStream_t stream) {
+    if (rows <= 0 || width == 0) return EML_OK;
+    if (host_pointer_is_pinned(dst_host)) {
+        EML_CUDA(cudaMemcpy2DAsync(dst_host, dpitch, src_dev, spitch, width, rows, cudaMemcpyDeviceToHost, stream));
+        return EML_OK;
+    }
+    if (width > SLOT_BYTES) EML_BAD_ARG("staged copy: a row of %zu bytes does not fit a staging slot", width);
+    Ring* ring = nullptr;
+    EML_TRY(ring_for(ctx_->device, &ring));
+    const int64_t chunk = std::max<int64_t>(1, (int64_t)(SLOT_BYTES / width));
+    for (int64_t r0 = 0; r0 < rows; r0 += chunk) {
+        const int64_t n = std::min(chunk, rows - r0);
+        int s;
+        EML_TRY(acquire(&s));
+        EML_CUDA(cudaMemcpy2DAsync(ring->slot[s], width, (const char*)src_dev + r0 * spitch, spitch, width, n,
+                                   cudaMemcpyDeviceToHost, stream));
+        EML_CUDA(cudaEventRecord(ring->ev[s], stream));
+        ring->in_flight[s] = true;
+        pending_.push_back(Pending{s, (char*)dst_host + r0 * dpitch, dpitch, width, n});
+    }
+    return EML_OK;
+}
+
+int StagedCopier::finish() {
+    int rc = EML_OK;
+    while (!pending_.empty()) {
+        Pending p = pending_.front();
+        pending_.erase(pending_.begin());
+        int r = complete(p);
+        if (r != EML_OK) rc = r;
+    }
+    return rc;
+}
+
+}  // namespace eml
