@@ -180,6 +180,12 @@ template <class T>
 int launch_splitk_reduce(const T* ws, int splits, T* C, int64_t batch, int64_t M, int64_t N, Strides3 sC,
                          bool accumulate, cudaStream_t stream);
 
+// in-kernel split variant of the f32 tensor-core GEMM (no pack pass); *handled = false when TMA cannot read the
+// operands in place (alignment), in which case the packed path runs
+int launch_gemm_tf32x3_fused(DeviceCtx* ctx, const float* A, const float* B, float* C, int64_t batch, int64_t M,
+                             int64_t N, int64_t K, Strides3 sA, Strides3 sB, Strides3 sC, int splits, bool accumulate,
+                             cudaStream_t stream, bool* handled);
+
 template <class T>
 int launch_einsum2(const T* A, const T* B, T* out, int n_out, const int64_t* out_len, const int64_t* a_out_stride,
                    const int64_t* b_out_stride, int n_sum, const int64_t* sum_len, const int64_t* a_sum_stride,

@@ -34,6 +34,7 @@
 
 #include "common.h"
 #include "sm100.cuh"
+#include "tf32_split.cuh"
 
 namespace eml {
 
@@ -59,24 +60,8 @@ struct Cfg {
 // 32 x 32 tiles through shared memory so both the read (along whichever source index is contiguous)
 // and the write (along k) are coalesced.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float to_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
-// x = big + small with both TF32-representable.  Non-finite and near-overflow values must not manufacture NaNs the
-// reference would not produce: rounding FLT_MAX-sized values up to infinity is replaced by truncation, and an
-// infinite x has a zero small part (inf - inf would be NaN).
-__device__ __forceinline__ void split_tf32(float x, float& big, float& small) {
-    if ((__float_as_uint(x) & 0x7f800000u) == 0x7f000000u) {
-        // top binade (|x| >= 2^127): round both parts toward zero so that big + small never reaches 2^128
-        big = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
-        small = __uint_as_float(__float_as_uint(x - big) & 0xffffe000u);
-        return;
-    }
-    big = to_tf32(x);
-    small = isfinite(x) ? to_tf32(x - big) : (isnan(x) ? x : 0.0f);
-}
+// the split itself lives in tf32_split.cuh (shared with the in-kernel converters of gemm_tf32x3_fused.cu)
+__device__ __forceinline__ void split_tf32(float x, float& big, float& small) { tf32::split(x, big, small); }
 
 __global__ void __launch_bounds__(256)
 split_pack_kernel(const float* __restrict__ src, float* __restrict__ big, float* __restrict__ small, int64_t MN,
@@ -128,10 +113,7 @@ __device__ __forceinline__ float4 load4_guarded(const float* p, int64_t first, i
 }
 __device__ __forceinline__ void store_split4(float* big, float* small, float4 v) {
     float4 hi, lo;
-    split_tf32(v.x, hi.x, lo.x);
-    split_tf32(v.y, hi.y, lo.y);
-    split_tf32(v.z, hi.z, lo.z);
-    split_tf32(v.w, hi.w, lo.w);
+    tf32::split4(v, hi, lo);
     *reinterpret_cast<float4*>(big) = hi;
     *reinterpret_cast<float4*>(small) = lo;
 }
@@ -809,6 +791,22 @@ int launch_gemm_tf32x3_f32(DeviceCtx* ctx, const float* A, const float* B, float
 
     uint64_t a_id = 0, b_id = 0;
     take_pack_identity(&a_id, &b_id);
+    // Small outputs: the pack pass moves 12 (M + N) K bytes at HBM speed while the GEMM does 2 M N K flops, so its
+    // share grows as M N / (M + N) shrinks (a third of the time for batched 1024^3).  There the variant that splits
+    // inside the kernel wins although its main loop is slower (shared-memory bound, measured 230 vs 280 TFLOP/s):
+    //   2 M N K (1/230e12 - 1/280e12)  <  12 (M + N) K / 6e12      <=>      M N / (M + N) < 1290
+    // It needs >= 24 k blocks per tile to amortise its unoverlapped epilogue, and is pointless when a packed operand
+    // is cached (identity hints from the tape).  EML_SGEMM_FUSED=1 forces it wherever it can run, =0 disables it.
+    if (use_pair) {
+        const char* fe = getenv("EML_SGEMM_FUSED");
+        const bool pays = a_id == 0 && b_id == 0 && kblocks >= 24 * splits && M * N < 1290 * (M + N);
+        const bool want = fe ? fe[0] == '1' : pays;
+        if (want) {
+            bool fused = false;
+            EML_TRY(launch_gemm_tf32x3_fused(ctx, A, B, C, batch, M, N, K, sA, sB, sC, splits, accumulate, stream, &fused));
+            if (fused) return EML_OK;
+        }
+    }
     TempBuf a_scratch, b_scratch, wsbuf;
     float *a_big, *a_small, *b_big, *b_small;
     EML_TRY(packed_operand(a_id, A, batch, M, K, Mp, Kp, sA.b, sA.r, sA.c, a_scratch, stream, &a_big, &a_small));

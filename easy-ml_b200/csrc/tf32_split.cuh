@@ -1,0 +1,58 @@
+// tf32_split.cuh -- the big/small TF32 split of the 3xTF32 f32 GEMM, shared by the pack pass (gemm_tf32x3.cu) and the
+// in-kernel converters (gemm_tf32x3_fused.cu) so that both produce the same bits.
+#pragma once
+#include <cstdint>
+
+namespace eml {
+namespace tf32 {
+
+// round to nearest, ties away from zero, to a 10-bit mantissa (what cvt.rna.tf32.f32 computes for finite values):
+// an integer add on the magnitude bits.  Only valid below the top binade (the carry must not reach the exponent's
+// all-ones pattern) -- callers check.
+__device__ __forceinline__ float rna_finite(float x) {
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+}
+
+// x = big + small with both TF32-representable.  Non-finite and near-overflow values must not manufacture NaNs the
+// reference would not produce: rounding FLT_MAX-sized values up to infinity is replaced by truncation, and an
+// infinite x has a zero small part (inf - inf would be NaN).
+__device__ __forceinline__ void split_special(float x, float& big, float& small) {
+    // |x| >= 2^127, infinite or NaN
+    if ((__float_as_uint(x) & 0x7f800000u) == 0x7f000000u) {
+        // top binade: round both parts toward zero so that big + small never reaches 2^128
+        big = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+        small = __uint_as_float(__float_as_uint(x - big) & 0xffffe000u);
+        return;
+    }
+    big = x;                          // inf or NaN
+    small = (x != x) ? x : 0.0f;
+}
+
+__device__ __forceinline__ bool ordinary(float x) { return fabsf(x) < 0x1p127f; }  // false for NaN
+
+__device__ __forceinline__ void split(float x, float& big, float& small) {
+    if (ordinary(x)) {
+        big = rna_finite(x);
+        small = rna_finite(x - big);  // |x - big| <= 2^-11 |x|: exact difference, far from overflow
+    } else {
+        split_special(x, big, small);
+    }
+}
+
+// four at once: one rarely-taken branch for the whole vector keeps the common path at ~6 instructions per element
+__device__ __forceinline__ void split4(float4 v, float4& hi, float4& lo) {
+    if (ordinary(v.x) && ordinary(v.y) && ordinary(v.z) && ordinary(v.w)) {
+        hi.x = rna_finite(v.x); lo.x = rna_finite(v.x - hi.x);
+        hi.y = rna_finite(v.y); lo.y = rna_finite(v.y - hi.y);
+        hi.z = rna_finite(v.z); lo.z = rna_finite(v.z - hi.z);
+        hi.w = rna_finite(v.w); lo.w = rna_finite(v.w - hi.w);
+    } else {
+        split(v.x, hi.x, lo.x);
+        split(v.y, hi.y, lo.y);
+        split(v.z, hi.z, lo.z);
+        split(v.w, hi.w, lo.w);
+    }
+}
+
+}  // namespace tf32
+}  // namespace eml

@@ -1,0 +1,133 @@
+"""The f32 tensor-core GEMM has two operand pipelines: a split/pack pass followed by TMA loads of the packed planes
+(gemm_tf32x3.cu), and an in-kernel split of raw f32 tiles (gemm_tf32x3_fused.cu) that the dispatcher picks for
+small outputs.  Both use the same split (tf32_split.cuh), issue the same MMAs in the same order and chunk the
+accumulation identically, so their results must agree BIT FOR BIT; each is also checked against the north star's
+bound  tol * sum_k |a_k b_k|  (tol 1e-5).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import easy_ml_b200 as eml
+from easy_ml_b200._ffi import check, lib
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+TOL = 1e-5
+
+
+def vp(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def s3(*s):
+    return (C.c_int64 * 3)(*s)
+
+
+class forced:
+    """EML_SGEMM_FUSED=1 (in-kernel split wherever it can run) / =0 (always pack) for the calls inside."""
+
+    def __init__(self, value):
+        self.value = value
+
+    def __enter__(self):
+        self.old = os.environ.get("EML_SGEMM_FUSED")
+        os.environ["EML_SGEMM_FUSED"] = self.value
+
+    def __exit__(self, *exc):
+        if self.old is None:
+            del os.environ["EML_SGEMM_FUSED"]
+        else:
+            os.environ["EML_SGEMM_FUSED"] = self.old
+
+
+def stored(x, transposed):
+    # same logical (batch, rows, cols) tensor, physically transposed when asked
+    return x.transpose(1, 2).contiguous().transpose(1, 2) if transposed else x.contiguous()
+
+
+def contract(a, b, c0=None):
+    batch, m, k = a.shape
+    n = b.shape[2]
+    c = torch.zeros((batch, m, n), device="cuda", dtype=torch.float32) if c0 is None else c0.clone()
+    check(lib.eml_contract_f32_dev(vp(a), vp(b), vp(c), batch, m, n, k, s3(*a.stride()), s3(*b.stride()),
+                                   s3(*c.stride()), 0 if c0 is None else 1, None))
+    torch.cuda.synchronize()
+    return c
+
+
+SHAPES = [(1, 512, 512, 64), (1, 300, 500, 700), (3, 260, 384, 200), (2, 1024, 1024, 2048), (1, 132, 4100, 36),
+          (1, 200, 136, 8192),  # few tiles, long K: deterministic split-K inside both kernels
+          (1, 1024, 768, 1028)]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, False), (True, True)])
+def test_in_kernel_split_matches_packed_bitwise(shape, ta, tb):
+    batch, m, n, k = shape
+    if (m if ta else k) % 4 or (k if tb else n) % 4:
+        pytest.skip("TMA reads raw operands in place only when rows are 16-byte multiples")
+    g = torch.Generator(device="cuda").manual_seed(hash((shape, ta, tb)) & 0xFFFF)
+    a = stored(torch.randn(batch, m, k, generator=g, device="cuda"), ta)
+    b = stored(torch.randn(batch, k, n, generator=g, device="cuda"), tb)
+    with forced("0"):
+        ref = contract(a, b)
+    with forced("1"):
+        got = contract(a, b)
+    assert eml.last_kernel() == "tf32x3_tcgen05"
+    assert torch.equal(ref, got)
+    exact = a.double() @ b.double()
+    bound = TOL * (a.double().abs() @ b.double().abs())
+    assert bool(((got.double() - exact).abs() <= bound).all())
+
+
+def test_in_kernel_split_accumulates_into_c():
+    g = torch.Generator(device="cuda").manual_seed(11)
+    a = torch.randn(1, 512, 320, generator=g, device="cuda")
+    b = torch.randn(1, 320, 384, generator=g, device="cuda")
+    c0 = torch.randn(1, 512, 384, generator=g, device="cuda")
+    with forced("0"):
+        ref = contract(a, b, c0)
+    with forced("1"):
+        got = contract(a, b, c0)
+    assert torch.equal(ref, got)
+    assert not torch.equal(got, contract(a, b))
+
+
+def test_in_kernel_split_special_values():
+    """inf / NaN / FLT_MAX-sized inputs take the split's slow path; both pipelines must treat them alike."""
+    g = torch.Generator(device="cuda").manual_seed(12)
+    a = torch.randn(1, 256, 64, generator=g, device="cuda")
+    b = torch.randn(1, 64, 256, generator=g, device="cuda")
+    fmax = float(np.finfo(np.float32).max)
+    a[0, 3, 5] = fmax
+    a[0, 7, 1] = -fmax
+    a[0, 9, 0] = float("nan")
+    b[0, 2, 200] = 3.0e38
+    b[0, 4, 17] = float("inf")
+    with forced("0"):
+        ref = contract(a, b)
+    with forced("1"):
+        got = contract(a, b)
+    assert torch.equal(torch.isnan(ref), torch.isnan(got))
+    ok = ~torch.isnan(ref)
+    assert torch.equal(ref[ok], got[ok])
+    assert bool(torch.isnan(got[0, 9]).all())          # the NaN row stays NaN
+    assert bool(torch.isfinite(got[0, 0]).sum() >= 254)  # ordinary rows are untouched except the inf / 3e38 columns
+
+
+def test_dispatcher_picks_in_kernel_split_for_small_batched_outputs():
+    """BASELINE config 3 (batch x 1024^3) is where the pack pass costs a third of the time: the default dispatch
+    must produce the in-kernel-split result there (same bits either way, so ask the library which kernel ran)."""
+    a = torch.randn(8, 1024, 1024, device="cuda")
+    b = torch.randn(8, 1024, 1024, device="cuda")
+    os.environ.pop("EML_SGEMM_FUSED", None)
+    before = eml.kernel_launches()
+    c = contract(a, b)
+    launches = eml.kernel_launches() - before
+    assert launches == 1, f"expected the single fused launch, saw {launches} (pack passes ran)"
+    with forced("0"):
+        assert torch.equal(c, contract(a, b))
