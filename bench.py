@@ -440,8 +440,12 @@ def extra_workloads(torch, eml, lib, check, dev, stream, sp, peak):
         Z = torch.empty((bt, m, m), device=dev, dtype=torch.float32)
         s = (C.c_int64 * 3)(m * m, m, 1)
         ms = run(lambda: check(lib.eml_contract_f32_dev(vp(X), vp(Y), vp(Z), bt, m, m, m, s, s, s, 0, sp)))
+        before = eml.kernel_launches()
+        check(lib.eml_contract_f32_dev(vp(X), vp(Y), vp(Z), bt, m, m, m, s, s, s, 0, sp))
         res["f32_batched_64x1024"] = {"tflops": 2.0 * bt * m ** 3 / (ms * 1e-3) / 1e12, "ms": ms,
-                                      "kernel": eml.last_kernel()}
+                                      "kernel": eml.last_kernel(),
+                                      # 1 = operands split inside the GEMM kernel; 3 = two split/pack passes + GEMM
+                                      "launches_per_call": eml.kernel_launches() - before}
         del X, Y, Z
         torch.cuda.empty_cache()
     except Exception as e:  # an extra must never take the headline down

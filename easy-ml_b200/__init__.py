@@ -3,12 +3,14 @@ include/easyml_b200.h.  Import as `importlib.import_module("easy-ml_b200")` or v
 `import easy_ml_b200`.
 
 Layout: csrc/ (CUDA kernels + the C ABI), lib/ (built libeasyml_b200.so), _ffi.py (ctypes binding),
-host.py (Python mirror of the reference operator API), host/ (C++ mirror), rust/ (the `cuda` feature shim).
+host.py + distributions.py (Python mirror of the reference operator API and of the GEMM callers), host/ (C++ mirror), rust/ (the `cuda` feature shim).
 """
 from . import _ffi  # raises ImportError when the CUDA library is not built: there is no fallback
 from ._ffi import EmlError, NoDeviceError, BadArgError, StateError, OPS, lib
 from .host import (Derivatives, Einsum, InconsistentDimensionLengthError, Matrix, Panic, PinnedBuffer, RecordMatrix,
                    RecordTensor, RecordedStep, Tensor, WengertList, sgd_update, wait_arrival)
+from .distributions import (Gaussian, MultivariateGaussian, MultivariateGaussianError, MultivariateGaussianTensor,
+                            cholesky_decomposition)
 
 
 def device_count():

@@ -199,6 +199,74 @@ def covariance(x, feature_axis):
     return out
 
 
+
+def cholesky(a):
+    """cholesky_decomposition_less_generic, src/linear_algebra.rs:1048-1101: literal triple loop, None when the
+    input is not square or a diagonal entry would not be positive."""
+    a = np.asarray(a)
+    n = a.shape[0]
+    if a.ndim != 2 or a.shape[1] != n:
+        return None
+    t = a.dtype.type
+    low = np.zeros((n, n), dtype=a.dtype)
+    for i in range(n):
+        for j in range(i + 1):
+            s = t(0)
+            for k in range(j):
+                s = s + low[i, k] * low[j, k]
+            if i == j:
+                entry_squared = a[i, j] - s
+                if entry_squared <= t(0):
+                    return None
+                low[i, j] = np.sqrt(entry_squared)
+            else:
+                low[i, j] = (a[i, j] - s) / low[j, j]
+    return low
+
+
+def gaussian_draw(mean, variance, source, max_samples, dtype):
+    """Gaussian::draw, src/distributions.rs:205-237: Box-Muller over pairs pulled from `source` (a Python iterator),
+    the surplus sample of the last pair popped; None when the source runs out."""
+    t = np.dtype(dtype).type
+    two = t(1) + t(1)
+    minus_two = -two
+    two_pi = two * t(np.pi)
+    standard_deviation = np.sqrt(t(variance))
+    samples = []
+    while len(samples) < max_samples:
+        try:
+            u, v = t(next(source)), t(next(source))
+        except StopIteration:
+            return None
+        z1 = np.sqrt(minus_two * np.log(u)) * np.cos(two_pi * v)
+        z2 = np.sqrt(minus_two * np.log(u)) * np.sin(two_pi * v)
+        samples.append(z1 * standard_deviation + t(mean))
+        samples.append(z2 * standard_deviation + t(mean))
+    if len(samples) > max_samples:
+        samples.pop()
+    return np.array(samples, dtype=dtype)
+
+
+def multivariate_gaussian_draw(mean, covariance, source, max_samples):
+    """draw_tensor_samples, src/distributions.rs:484-540: one `mean + L * z` matrix-vector product per sample row
+    (the product through matrix_mul, i.e. the reference's scalar_product order)."""
+    covariance = np.asarray(covariance)
+    dtype = covariance.dtype
+    mean = np.asarray(mean, dtype=dtype)
+    low = cholesky(covariance)
+    if low is None:
+        return None
+    n = mean.shape[0]
+    source = iter(source)
+    drawn = np.zeros((max_samples, n), dtype=dtype)
+    for row in range(max_samples):
+        z = gaussian_draw(0, 1, source, n, dtype)
+        if z is None:
+            return None
+        drawn[row] = mean + matrix_mul(low, z.reshape(n, 1))[:, 0]
+    return drawn
+
+
 class Tape:
     """The literal scalar WengertList (src/differentiation.rs:327-352)."""
 

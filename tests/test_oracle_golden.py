@@ -248,3 +248,38 @@ def test_einsum_n_goldens(orc, golden, dtype):
     with pytest.raises(orc.InconsistentDimensionLengthError):
         orc.einsum_n([np.zeros((2, 3), dtype), np.zeros((4, 2), dtype), np.zeros((2, 2), dtype)],
                      [["a", "b"], ["b", "c"], ["c", "d"]], ["a", "d"])
+
+
+# ---- next row: Cholesky and the multivariate Gaussian draw (callers of `*`) ----------------------
+def test_cholesky_goldens(orc, golden):
+    for g in golden["cholesky"]:
+        dtype = np.float32 if g["exact"] else np.float64
+        a = np.array(g["a"], dtype=dtype)
+        low = orc.cholesky(a)
+        expect = np.array(g["expect"], dtype=dtype)
+        if g["exact"]:
+            assert np.array_equal(low, expect), g["cite"]
+            assert np.array_equal(orc.matrix_mul(low, np.ascontiguousarray(low.T)), a), g["cite"]  # L L^T == A exactly
+        else:
+            assert np.abs(low - expect).sum() < g["abs_sum_tolerance"], g["cite"]
+            assert np.abs(orc.matrix_mul(low, np.ascontiguousarray(low.T)) - a).sum() < g["abs_sum_tolerance"]
+    assert orc.cholesky(np.array([[1.0, 2.0], [2.0, 1.0]])) is None      # not positive definite
+    assert orc.cholesky(np.zeros((2, 3))) is None                        # not square
+
+
+def test_multivariate_gaussian_draw_golden(orc, golden):
+    """tests/distributions.rs:48-220: the reference's own assertions on its fixed random source."""
+    g = golden["multivariate_gaussian"]
+    mean = np.array(g["mean"])
+    cov = np.array(g["covariance"])
+    drawn = orc.multivariate_gaussian_draw(mean, cov, g["source"], g["max_samples"])
+    assert drawn.shape == (25, 3)
+    for f in range(3):
+        feature_mean = drawn[:, f].sum() / g["max_samples"]
+        sd = np.sqrt(cov[f, f])
+        assert mean[f] - 0.5 * sd < feature_mean < mean[f] + 0.5 * sd, g["cite"]
+    # N = 3 is odd: every sample consumes 4 numbers, so one number fewer than 100 is not enough
+    assert orc.multivariate_gaussian_draw(mean, cov, g["source"][:99], g["max_samples"]) is None
+    # a single Gaussian::draw keeps the surplus sample only when max_samples is even (:230-236)
+    assert len(orc.gaussian_draw(1.0, 2.0, iter(g["source"]), 5, np.float64)) == 5
+    assert orc.gaussian_draw(1.0, 2.0, iter(g["source"][:5]), 5, np.float64) is None
