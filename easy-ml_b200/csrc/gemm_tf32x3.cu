@@ -793,13 +793,15 @@ int launch_gemm_tf32x3_f32(DeviceCtx* ctx, const float* A, const float* B, float
     take_pack_identity(&a_id, &b_id);
     // Small outputs: the pack pass moves 12 (M + N) K bytes at HBM speed while the GEMM does 2 M N K flops, so its
     // share grows as M N / (M + N) shrinks (a third of the time for batched 1024^3).  There the variant that splits
-    // inside the kernel wins although its main loop is slower (shared-memory bound, measured 230 vs 280 TFLOP/s):
-    //   2 M N K (1/230e12 - 1/280e12)  <  12 (M + N) K / 6e12      <=>      M N / (M + N) < 1290
-    // It needs >= 24 k blocks per tile to amortise its unoverlapped epilogue, and is pointless when a packed operand
-    // is cached (identity hints from the tape).  EML_SGEMM_FUSED=1 forces it wherever it can run, =0 disables it.
+    // inside the kernel wins although its main loop is slower (shared-memory-bandwidth bound, measured 240 vs
+    // 280 TFLOP/s):
+    //   2 M N K (1/240e12 - 1/280e12)  <  12 (M + N) K / 6e12      <=>      M N / (M + N) < 1680
+    // (measured break-even: 4096^2, where M N / (M + N) = 2048).  It needs >= 24 k blocks per tile to amortise its
+    // unoverlapped epilogue, and is pointless when a packed operand is cached (identity hints from the tape).
+    // EML_SGEMM_FUSED=1 forces it wherever it can run, =0 disables it.
     if (use_pair) {
         const char* fe = getenv("EML_SGEMM_FUSED");
-        const bool pays = a_id == 0 && b_id == 0 && kblocks >= 24 * splits && M * N < 1290 * (M + N);
+        const bool pays = a_id == 0 && b_id == 0 && kblocks >= 24 * splits && M * N < 1680 * (M + N);
         const bool want = fe ? fe[0] == '1' : pays;
         if (want) {
             bool fused = false;

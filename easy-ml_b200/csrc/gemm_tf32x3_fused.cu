@@ -4,9 +4,11 @@
 // (BASELINE config 3: batch 64, 1024^3).  Here the raw f32 operand tiles are brought in by TMA, fourteen
 // warps split them in shared memory into the big / small TF32 tiles (K-major, 128-byte swizzled: exactly what TMA
 // with SWIZZLE_128B would have written from packed planes) and the same tcgen05.mma.cta_group::2 pipeline consumes
-// them.  Shared-memory traffic per 32-wide k block rises from 160 KB to 224 KB per SM (raw in, raw read, big/small
-// written, MMA reads), a ~88 % ceiling for the tensor pipe, so the dispatcher uses this kernel for short and medium
-// K, where not running the pack wins, and keeps the packed path for long K.
+// them.  Shared-memory traffic per 32-wide k block and SM rises from 160 KB (packed planes in by TMA, MMA operand
+// reads) to 224 KB (raw in by TMA, raw read, big/small written, MMA reads): 1792 cycles of the 128 B/clk shared
+// memory pipe against 1536 cycles of MMA issue, so the tensor pipe cannot exceed 86 % here (measured 75 %, with the
+// shared-memory pipe 87 % busy).  That is why the dispatcher only uses this kernel where not running the pack pass
+// buys more than the slower main loop costs (small outputs), and keeps the packed path elsewhere.
 //
 // Per CTA of a pair:    warp 0      one lane issues the TMA loads of the raw tiles (3-stage ring)
 //                       warp 1      TMEM allocation; leader CTA: one lane issues the MMAs (M=256, N=256, K=8)
@@ -98,6 +100,15 @@ __device__ __forceinline__ void convert_block(const uint8_t* __restrict__ raw, u
                                    rf[(4 * k4 + 2) * HALF + row], rf[(4 * k4 + 3) * HALF + row]);
             }
         }
+        // one test for the whole group: the common path below it is branch free, so the group's twelve
+        // independent split chains interleave (a per-vector branch serialised them: measured 0.15 IPC per warp)
+        bool ordinary = true;
+#pragma unroll
+        for (int i = 0; i < GROUP_TASKS; i++) {
+            const int t = cw + CONV_WARPS * (g + i);
+            if (g + i >= MAX_TASKS || t >= TASKS) continue;
+            ordinary &= tf32::ordinary4(v[i]);
+        }
 #pragma unroll
         for (int i = 0; i < GROUP_TASKS; i++) {
             const int t = cw + CONV_WARPS * (g + i);
@@ -106,7 +117,10 @@ __device__ __forceinline__ void convert_block(const uint8_t* __restrict__ raw, u
             const bool kin = is_b ? B_KIN : A_KIN;
             const int tt = t & 31;
             float4 hi, lo;
-            tf32::split4(v[i], hi, lo);
+            if (ordinary)
+                tf32::split4_ordinary(v[i], hi, lo);
+            else
+                tf32::split4_any(v[i], hi, lo);
             int off;
             if (kin) {
                 off = (tt * 32 + lane) * 16;

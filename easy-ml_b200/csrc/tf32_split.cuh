@@ -39,19 +39,30 @@ __device__ __forceinline__ void split(float x, float& big, float& small) {
     }
 }
 
+__device__ __forceinline__ bool ordinary4(float4 v) {
+    return ordinary(v.x) & ordinary(v.y) & ordinary(v.z) & ordinary(v.w);
+}
+// the common case: no branch, four independent dependency chains
+__device__ __forceinline__ void split4_ordinary(float4 v, float4& hi, float4& lo) {
+    hi.x = rna_finite(v.x); lo.x = rna_finite(v.x - hi.x);
+    hi.y = rna_finite(v.y); lo.y = rna_finite(v.y - hi.y);
+    hi.z = rna_finite(v.z); lo.z = rna_finite(v.z - hi.z);
+    hi.w = rna_finite(v.w); lo.w = rna_finite(v.w - hi.w);
+}
+// the rare case: a vector holding an infinity, a NaN or a value >= 2^127 (a real function call here costs the
+// converters their register allocation: measured 30 % slower)
+__device__ __forceinline__ void split4_any(float4 v, float4& hi, float4& lo) {
+    split(v.x, hi.x, lo.x);
+    split(v.y, hi.y, lo.y);
+    split(v.z, hi.z, lo.z);
+    split(v.w, hi.w, lo.w);
+}
 // four at once: one rarely-taken branch for the whole vector keeps the common path at ~6 instructions per element
 __device__ __forceinline__ void split4(float4 v, float4& hi, float4& lo) {
-    if (ordinary(v.x) && ordinary(v.y) && ordinary(v.z) && ordinary(v.w)) {
-        hi.x = rna_finite(v.x); lo.x = rna_finite(v.x - hi.x);
-        hi.y = rna_finite(v.y); lo.y = rna_finite(v.y - hi.y);
-        hi.z = rna_finite(v.z); lo.z = rna_finite(v.z - hi.z);
-        hi.w = rna_finite(v.w); lo.w = rna_finite(v.w - hi.w);
-    } else {
-        split(v.x, hi.x, lo.x);
-        split(v.y, hi.y, lo.y);
-        split(v.z, hi.z, lo.z);
-        split(v.w, hi.w, lo.w);
-    }
+    if (ordinary4(v))
+        split4_ordinary(v, hi, lo);
+    else
+        split4_any(v, hi, lo);
 }
 
 }  // namespace tf32
