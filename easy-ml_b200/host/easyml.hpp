@@ -14,6 +14,7 @@
 #include <cstdint>
 #include <map>
 #include <memory>
+#include <cmath>
 #include <optional>
 #include <sstream>
 #include <stdexcept>
@@ -119,6 +120,98 @@ class Matrix {
     }
     int64_t rows_, cols_;
     std::vector<T> data_;
+};
+
+// ------------------------------------------------------------------------------------------------ GEMM callers
+// linear_algebra::cholesky_decomposition, src/linear_algebra.rs:1008-1101 (Cholesky-Banachiewicz, row by row).
+// Host side, as in the reference: O(N^3 / 3) sequential work on the small covariance matrix.
+template <class T>
+std::optional<Matrix<T>> cholesky_decomposition(const Matrix<T>& a) {
+    const int64_t n = a.rows();
+    if (a.columns() != n) return std::nullopt;
+    std::vector<T> low((size_t)(n * n), T(0));
+    for (int64_t i = 0; i < n; i++)
+        for (int64_t j = 0; j <= i; j++) {
+            T sum = T(0);
+            for (int64_t k = 0; k < j; k++) sum = sum + low[i * n + k] * low[j * n + k];
+            if (i == j) {
+                const T entry_squared = a.get(i, j) - sum;
+                if (entry_squared <= T(0)) return std::nullopt;  // :1087: not positive definite
+                low[i * n + j] = std::sqrt(entry_squared);
+            } else {
+                low[i * n + j] = (a.get(i, j) - sum) / low[j * n + j];
+            }
+        }
+    return Matrix<T>(n, n, std::move(low));
+}
+
+// easy_ml::distributions::Gaussian, src/distributions.rs:131-250.  `Source` is any callable returning
+// std::optional<T> (the reference's `Iterator<Item = T>`: nullopt = exhausted).
+template <class T>
+struct Gaussian {
+    T mean, variance;
+    // draw, :205-237: Box-Muller over pairs; the surplus sample of the last pair is popped
+    template <class Source>
+    std::optional<std::vector<T>> draw(Source& source, size_t max_samples) const {
+        const T two = T(1) + T(1), minus_two = -two, two_pi = two * T(3.14159265358979323846264338327950288L);
+        const T standard_deviation = std::sqrt(variance);
+        std::vector<T> samples;
+        samples.reserve(max_samples + 1);
+        while (samples.size() < max_samples) {
+            const std::optional<T> u = source();
+            if (!u) return std::nullopt;
+            const std::optional<T> v = source();
+            if (!v) return std::nullopt;
+            const T z1 = std::sqrt(minus_two * std::log(*u)) * std::cos(two_pi * *v);
+            const T z2 = std::sqrt(minus_two * std::log(*u)) * std::sin(two_pi * *v);
+            samples.push_back(z1 * standard_deviation + mean);
+            samples.push_back(z2 * standard_deviation + mean);
+        }
+        if (samples.size() > max_samples) samples.pop_back();
+        return samples;
+    }
+};
+
+// easy_ml::distributions::MultivariateGaussian, src/distributions.rs:262-369.  The reference's draw_tensor_samples
+// (:484-540) runs one `mean + L * z` matrix-vector product per sample; here the standard-normal vectors are stacked
+// as the rows of Z (the source is consumed in the same order) and ONE product Z * L^T goes through the drop-in
+// contraction, L addressed with transposed strides: element (m, n) is the same scalar product in the same k order.
+template <class T>
+class MultivariateGaussian {
+  public:
+    MultivariateGaussian(Matrix<T> mean, Matrix<T> covariance) : mean_(std::move(mean)), cov_(std::move(covariance)) {
+        if (mean_.columns() != 1) throw Panic("Mean must be a column vector");
+        if (cov_.rows() != cov_.columns()) throw Panic("Supplied 'covariance' matrix is not square");
+        if (mean_.rows() != cov_.rows()) throw Panic("Means must be same length as covariance matrix");
+    }
+    const Matrix<T>& mean() const { return mean_; }
+    const Matrix<T>& covariance() const { return cov_; }
+
+    template <class Source>
+    std::optional<Matrix<T>> draw(Source& source, int64_t max_samples) const {
+        const std::optional<Matrix<T>> lower = cholesky_decomposition(cov_);
+        if (!lower) return std::nullopt;
+        const int64_t n = mean_.rows();
+        const Gaussian<T> normal{T(0), T(1)};
+        std::vector<T> z((size_t)(max_samples * n));
+        for (int64_t m = 0; m < max_samples; m++) {
+            const std::optional<std::vector<T>> row = normal.draw(source, (size_t)n);
+            if (!row) return std::nullopt;
+            std::copy(row->begin(), row->end(), z.begin() + m * n);
+        }
+        std::vector<T> drawn((size_t)(max_samples * n));
+        const int64_t sz[3] = {0, n, 1}, sl[3] = {0, 1, n}, sd[3] = {0, n, 1};
+        if constexpr (detail::is_f32<T>)
+            detail::check(eml_contract_f32(z.data(), lower->data().data(), drawn.data(), 1, max_samples, n, n, sz, sl, sd));
+        else
+            detail::check(eml_contract_f64(z.data(), lower->data().data(), drawn.data(), 1, max_samples, n, n, sz, sl, sd));
+        for (int64_t m = 0; m < max_samples; m++)
+            for (int64_t f = 0; f < n; f++) drawn[m * n + f] = mean_.get(f, 0) + drawn[m * n + f];  // :528
+        return Matrix<T>(max_samples, n, std::move(drawn));
+    }
+
+  private:
+    Matrix<T> mean_, cov_;
 };
 
 // ------------------------------------------------------------------------------------------------ Tensor
