@@ -128,3 +128,42 @@ class ShardedGemm:
             else:
                 dist.all_gather_into_tensor(c_full, c_slab)  # in place: the slab is a view into c_full
         return c_full[:p.m]
+
+
+class ShardedBatchContraction:
+    """out[b] = x[b] * y[b] with the batch dimension sharded (BASELINE config 3 over several GPUs, SURVEY.md
+    section 8e: "the natural split is the batch dimension, no collective but the gather").
+
+    Einsum2::to computes every output element from one batch index of each input
+    (src/tensors/einsum.rs:908-980), so batches are independent units: rank r owns the contiguous batches
+    row_range(batch, world, r), both operands are generated / resident per shard, and nothing is exchanged while
+    computing.  gather="none" leaves the result sharded (what a caller that keeps working per shard wants);
+    gather="nccl" delivers every shard to every rank with one in-place all-gather.
+
+    x_shard : [slab, M, K], y_shard : [slab, K, N]   this rank's batches (entries past the end are ignored)
+    out_full: [world * slab, M, N]                   rank r's results land in out_full[r * slab : (r + 1) * slab]
+    contract(x_view, y_view, out_view) computes the batched product of the views on the device.
+    """
+
+    def __init__(self, batch, world, rank, dist, contract, gather="none"):
+        assert gather in ("none", "nccl")
+        self.batch, self.world, self.rank, self.dist, self.contract, self.gather = batch, world, rank, dist, contract, gather
+
+    @property
+    def slab(self):
+        return rows_per_rank(self.batch, self.world)
+
+    @property
+    def my_batches(self):
+        return row_range(self.batch, self.world, self.rank)
+
+    def step(self, x_shard, y_shard, out_full):
+        first, last = self.my_batches
+        n = last - first
+        h = self.slab
+        mine = out_full[self.rank * h:(self.rank + 1) * h]
+        if n > 0:
+            self.contract(x_shard[:n], y_shard[:n], mine[:n])
+        if self.world > 1 and self.gather == "nccl":
+            self.dist.all_gather_into_tensor(out_full, mine)  # in place: the shard is a view into out_full
+        return out_full[:self.batch] if self.gather == "nccl" or self.world == 1 else mine[:n]

@@ -113,3 +113,52 @@ def test_k_panels_cover_k_once():
             assert ps[0][0] == 0 and ps[-1][1] == k
             assert all(a[1] == b[0] for a, b in zip(ps, ps[1:]))
             assert all(b > a for a, b in ps)
+
+
+def _batch_worker(rank, world, port, batch, gather, out):
+    from easy_ml_b200.sharded import ShardedBatchContraction
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(99)
+        x_full = torch.randint(-8, 9, (batch, 5, 7), generator=g).double()
+        y_full = torch.randint(-8, 9, (batch, 7, 3), generator=g).double()
+        calls = []
+
+        def contract(x, y, o):
+            calls.append(x.shape[0])
+            o.copy_(torch.bmm(x, y))
+
+        op = ShardedBatchContraction(batch, world, rank, dist, contract, gather=gather)
+        first, last = op.my_batches
+        h = op.slab
+        x = torch.zeros((h, 5, 7), dtype=torch.float64)
+        y = torch.zeros((h, 7, 3), dtype=torch.float64)
+        x[:last - first] = x_full[first:last]
+        y[:last - first] = y_full[first:last]
+        out_full = torch.full((world * h, 5, 3), -1.0, dtype=torch.float64)
+        got = op.step(x, y, out_full)
+        want = torch.bmm(x_full, y_full)
+        if gather == "nccl":
+            ok = torch.equal(got, want)
+        else:  # result stays sharded: this rank's batches only, nobody else's slot touched
+            ok = torch.equal(got, want[first:last])
+            others = torch.cat([out_full[:rank * h], out_full[(rank + 1) * h:]])
+            ok = ok and bool(torch.all(others == -1.0))
+        ok = ok and calls == ([last - first] if last > first else [])
+        out[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,batch,gather", [(2, 8, "nccl"), (2, 5, "nccl"), (3, 2, "nccl"), (2, 7, "none")])
+def test_batch_sharded_contraction_over_gloo(world, batch, gather):
+    """BASELINE config 3 across ranks: contiguous batch shards, no exchange while computing, optional gather;
+    ragged (batch not divisible by the world size) and more ranks than batches."""
+    port = _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_batch_worker, args=(world, port, batch, gather, out), nprocs=world, join=True)
+        assert all(out.get(r) for r in range(world)), dict(out)
