@@ -512,6 +512,14 @@ def hbm_kernels(torch, lib, check, dev, stream, sp, peak, run):
     line("chain_rule_accumulate", ms, 4, "dparent += dout * deriv: 3 reads + 1 write")
     ms = run(lambda: check(lib.eml_sgd_f32_dev(vp(x), vp(d), C.c_float(1e-9), n, sp)))
     line("sgd_update", ms, 3, "w -= lr * d: 2 reads + 1 write")
+    # Matrix::transpose / Tensor::reorder on device buffers (8192 x 16384 f32 and a rank-4 permutation of the same
+    # 2^27 elements): 1 read + 1 write, both coalesced through 32 x 32 shared-memory tiles
+    i64s = lambda *v: (C.c_int64 * len(v))(*v)
+    ms = run(lambda: check(lib.eml_reorder_f32_dev(vp(x), vp(y), 2, i64s(16384, 8192), i64s(1, 16384), sp)))
+    line("transpose_8192x16384", ms, 2, "out[c][r] = in[r][c]: 1 read + 1 write")
+    ms = run(lambda: check(lib.eml_reorder_f32_dev(vp(x), vp(y), 4, i64s(128, 64, 128, 128),
+                                                   i64s(1, 128 * 128 * 128, 128, 128 * 128), sp)))
+    line("reorder_rank4_dcab", ms, 2, "Tensor::reorder of [a=64, b=128, c=128, d=128] to [d, a, c, b]: 1 read + 1 write")
     del y, d
     # split/pack pass of the 3xTF32 GEMM: 1 read + 2 writes per operand element (timed through a GEMM whose
     # own work is negligible: M = 128, so the B operand's pack dominates)

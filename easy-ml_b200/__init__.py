@@ -9,6 +9,7 @@ from . import _ffi  # raises ImportError when the CUDA library is not built: the
 from ._ffi import EmlError, NoDeviceError, BadArgError, StateError, OPS, lib
 from .host import (Derivatives, Einsum, InconsistentDimensionLengthError, Matrix, Panic, PinnedBuffer, RecordMatrix,
                    RecordTensor, RecordedStep, Tensor, WengertList, sgd_update, wait_arrival)
+from .device import DeviceMatrix, DeviceTensor
 from .distributions import (Gaussian, MultivariateGaussian, MultivariateGaussianError, MultivariateGaussianTensor,
                             cholesky_decomposition)
 

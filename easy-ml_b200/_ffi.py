@@ -55,6 +55,8 @@ SIGNATURES = {
     "eml_last_kernel": (C.c_char_p, []),
     "eml_alloc": (cint, [C.POINTER(vp), C.c_size_t]),
     "eml_free": (cint, [vp]),
+    "eml_alloc_async": (cint, [C.POINTER(vp), C.c_size_t, vp]),
+    "eml_free_async": (cint, [vp, C.c_size_t, vp]),
     "eml_upload": (cint, [vp, vp, C.c_size_t]),
     "eml_download": (cint, [vp, vp, C.c_size_t]),
     "eml_sync": (cint, []),
@@ -120,6 +122,7 @@ for sfx, ct in (("f32", C.c_float), ("f64", C.c_double)):
         f"eml_binary_{sfx}_dev": (cint, [cint, vp, vp, vp, vp, vp, i64, vp]),
         f"eml_chain_{sfx}_dev": (cint, [vp, vp, vp, i64, vp]),
         f"eml_sgd_{sfx}_dev": (cint, [vp, vp, ct, i64, vp]),
+        f"eml_reorder_{sfx}_dev": (cint, [vp, vp, cint, pi64, pi64, vp]),
     })
 
 for _name, (_res, _args) in SIGNATURES.items():

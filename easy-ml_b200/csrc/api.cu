@@ -534,6 +534,16 @@ int eml_free(void* dptr) {
     if (dptr) EML_CUDA(cudaFree(dptr));
     return EML_OK;
 }
+int eml_alloc_async(void** dptr, size_t bytes, void* stream) {
+    DeviceCtx* ctx = nullptr;
+    EML_TRY(get_ctx(&ctx));
+    if (!dptr) EML_BAD_ARG("alloc_async: null out pointer");
+    return stream_alloc(dptr, bytes ? bytes : 16, (cudaStream_t)stream);
+}
+int eml_free_async(void* dptr, size_t bytes, void* stream) {
+    if (dptr) stream_free(dptr, bytes ? bytes : 16, (cudaStream_t)stream);
+    return EML_OK;
+}
 int eml_upload(void* dst, const void* src, size_t bytes) {
     DeviceCtx* ctx = nullptr;
     EML_TRY(get_ctx(&ctx));
@@ -721,6 +731,16 @@ int eml_sgd_f32_dev(float* w, const float* d, float lr, int64_t n, void* stream)
 int eml_sgd_f64_dev(double* w, const double* d, double lr, int64_t n, void* stream) {
     EML_STREAM_OR_CTX(st);
     return launch_sgd<double>(w, d, lr, n, st);
+}
+int eml_reorder_f32_dev(const float* in, float* out, int rank, const int64_t* out_lens, const int64_t* in_strides,
+                        void* stream) {
+    EML_STREAM_OR_CTX(st);
+    return launch_reorder<float>(in, out, rank, out_lens, in_strides, st);
+}
+int eml_reorder_f64_dev(const double* in, double* out, int rank, const int64_t* out_lens, const int64_t* in_strides,
+                        void* stream) {
+    EML_STREAM_OR_CTX(st);
+    return launch_reorder<double>(in, out, rank, out_lens, in_strides, st);
 }
 
 }  // extern "C"

@@ -180,6 +180,11 @@ template <class T>
 int launch_splitk_reduce(const T* ws, int splits, T* C, int64_t batch, int64_t M, int64_t N, Strides3 sC,
                          bool accumulate, cudaStream_t stream);
 
+// out (row-major over out_lens) [i] = in[sum_d i_d * in_strides[d]]  (reorder.cu)
+template <class T>
+int launch_reorder(const T* in, T* out, int rank, const int64_t* out_lens, const int64_t* in_strides,
+                   cudaStream_t stream);
+
 // in-kernel split variant of the f32 tensor-core GEMM (no pack pass); *handled = false when TMA cannot read the
 // operands in place (alignment), in which case the packed path runs
 int launch_gemm_tf32x3_fused(DeviceCtx* ctx, const float* A, const float* B, float* C, int64_t batch, int64_t M,

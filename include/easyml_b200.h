@@ -166,6 +166,12 @@ int eml_gemm_exact_f64(const double* A, const double* B, double* C, int64_t M, i
  * ------------------------------------------------------------------------------------------- */
 int eml_alloc(void** dptr, size_t bytes);
 int eml_free(void* dptr);
+/* Stream-ordered device memory from the library's per-(device, stream, size) block cache (the one the tape's
+ * containers and all scratch use): a block may be reused by work enqueued LATER on the SAME stream without any
+ * synchronisation, and in steady state no CUDA allocator call is made.  For device-resident containers whose
+ * intermediates come and go with every operator (easy-ml_b200/device.py).  `bytes` at free = `bytes` at alloc. */
+int eml_alloc_async(void** dptr, size_t bytes, void* stream);
+int eml_free_async(void* dptr, size_t bytes, void* stream);
 int eml_upload(void* dst_dev, const void* src_host, size_t bytes);   /* blocking */
 int eml_download(void* dst_host, const void* src_dev, size_t bytes); /* blocking */
 int eml_sync(void);                                                  /* current device */
@@ -238,6 +244,15 @@ int eml_chain_f64_dev(const double* dout, const double* deriv, double* dparent, 
  * src/neural_networks.rs:418-420, as one kernel. */
 int eml_sgd_f32_dev(float* w, const float* d, float lr, int64_t n, void* stream);
 int eml_sgd_f64_dev(double* w, const double* d, double lr, int64_t n, void* stream);
+/* Tensor::reorder / Tensor::transpose (src/tensors/mod.rs:1473-1600, data movement of TensorAccess::iter) and
+ * Matrix::transpose (src/matrices/mod.rs:1277-1330) on device buffers:
+ *   out (row-major, lengths out_lens[rank]) [i_0 .. i_{rank-1}] = in[sum_d i_d * in_strides[d]]
+ * rank 1..6; strides in elements, >= 0.  Coalesced on both sides (32 x 32 shared-memory tiles) whenever the input
+ * has a unit-stride dimension.  `out` must not overlap `in`. */
+int eml_reorder_f32_dev(const float* in, float* out, int rank, const int64_t* out_lens, const int64_t* in_strides,
+                        void* stream);
+int eml_reorder_f64_dev(const double* in, double* out, int rank, const int64_t* out_lens, const int64_t* in_strides,
+                        void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Tier 3 -- device-resident reverse-mode tape (RecordTensor / RecordMatrix / WengertList)
