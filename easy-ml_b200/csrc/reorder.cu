@@ -4,7 +4,7 @@
 //
 // A permutation of a contiguous tensor always leaves one output dimension whose INPUT stride is 1.  When that is
 // the last output dimension, consecutive threads read and write consecutive addresses already.  Otherwise the
-// kernel moves 32 x 32 tiles spanned by (that dimension, the last output dimension) through shared memory, so the
+// kernel moves 64 x 64 tiles spanned by (that dimension, the last output dimension) through shared memory, so the
 // reads run along the input's contiguous index and the writes along the output's: both coalesced.
 #include "common.h"
 
@@ -37,15 +37,21 @@ reorder_gather_kernel(const T* __restrict__ in, T* __restrict__ out, Dims d, int
     }
 }
 
-// tile over (dimension `a`: input stride 1, the last dimension `z`: output stride 1); blockIdx.z walks the rest
+// tile over (dimension `a`: input stride 1, the last dimension `z`: output stride 1); blockIdx.z walks the rest.
+// 64 x 64 tiles, 16 elements per thread, every load of a tile issued before the first store to shared memory:
+// 16 KB (f32) / 32 KB (f64) in flight per CTA, 256-byte (f32) runs on both sides.
+constexpr int TILE = 64, TILE_ROWS_PER_PASS = 4;  // 256 threads = 64 x 4
 template <class T>
-__global__ void __launch_bounds__(256)
-reorder_tiled_kernel(const T* __restrict__ in, T* __restrict__ out, Dims d, int a, int64_t rest_total) {
+__global__ void __launch_bounds__(256, 4)
+reorder_tiled_kernel(const T* __restrict__ in, T* __restrict__ out, Dims d, int a, int64_t rest_total, int64_t len_z,
+                     int64_t len_a, int64_t istr_z, int64_t ostr_a) {
+    // (the four scalars are d.len[z], d.len[a], d.istr[z], d.ostr[a]: indexing the parameter struct with a run-time
+    //  index would make the compiler copy it to local memory)
     pdl_prologue();
-    __shared__ T tile[32][33];
+    __shared__ T tile[TILE][TILE + 1];
     const int z = d.rank - 1;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
-    const int64_t z0 = (int64_t)blockIdx.x * 32, a0 = (int64_t)blockIdx.y * 32;
+    const int tx = threadIdx.x & (TILE - 1), ty = threadIdx.x / TILE;
+    const int64_t z0 = (int64_t)blockIdx.x * TILE, a0 = (int64_t)blockIdx.y * TILE;
     for (int64_t rest = blockIdx.z; rest < rest_total; rest += gridDim.z) {
         int64_t r = rest, src = 0, dst = 0;
 #pragma unroll
@@ -57,16 +63,23 @@ reorder_tiled_kernel(const T* __restrict__ in, T* __restrict__ out, Dims d, int 
                 dst += ix * d.ostr[k];
             }
         }
+        T v[TILE / TILE_ROWS_PER_PASS];
+        const bool a_ok = a0 + tx < len_a;
+        const T* ip = in + src + (z0 + ty) * istr_z + a0 + tx;  // istr[a] == 1
 #pragma unroll
-        for (int j = ty; j < 32; j += 8) {
-            const int64_t iz = z0 + j, ia = a0 + tx;
-            if (iz < d.len[z] && ia < d.len[a]) tile[j][tx] = in[src + iz * d.istr[z] + ia];  // istr[a] == 1
+        for (int p = 0; p < TILE / TILE_ROWS_PER_PASS; p++) {
+            v[p] = (a_ok && z0 + ty + p * TILE_ROWS_PER_PASS < len_z) ? *ip : T(0);
+            ip += TILE_ROWS_PER_PASS * istr_z;
         }
-        __syncthreads();
 #pragma unroll
-        for (int j = ty; j < 32; j += 8) {
-            const int64_t ia = a0 + j, iz = z0 + tx;
-            if (iz < d.len[z] && ia < d.len[a]) out[dst + ia * d.ostr[a] + iz] = tile[tx][j];
+        for (int p = 0; p < TILE / TILE_ROWS_PER_PASS; p++) tile[ty + p * TILE_ROWS_PER_PASS][tx] = v[p];
+        __syncthreads();
+        const bool z_ok = z0 + tx < len_z;
+        T* op = out + dst + (a0 + ty) * ostr_a + z0 + tx;
+#pragma unroll
+        for (int p = 0; p < TILE / TILE_ROWS_PER_PASS; p++) {
+            if (z_ok && a0 + ty + p * TILE_ROWS_PER_PASS < len_a) *op = tile[tx][ty + p * TILE_ROWS_PER_PASS];
+            op += TILE_ROWS_PER_PASS * ostr_a;
         }
         __syncthreads();
     }
@@ -95,10 +108,11 @@ int launch_reorder(const T* in, T* out, int rank, const int64_t* out_lens, const
             if (d.istr[k] == 1 && d.len[k] > 1) a = k;
     if (a >= 0 && d.len[rank - 1] > 1) {
         const int64_t rest = total / (d.len[a] * d.len[rank - 1]);
-        const int64_t gx = (d.len[rank - 1] + 31) / 32, gy = (d.len[a] + 31) / 32;
+        const int64_t gx = (d.len[rank - 1] + TILE - 1) / TILE, gy = (d.len[a] + TILE - 1) / TILE;
         if (gx <= 0x7fffffff && gy <= 65535) {
             const unsigned gz = (unsigned)(rest < 65535 ? rest : 65535);
-            EML_CUDA(launch_k(reorder_tiled_kernel<T>, dim3((unsigned)gx, (unsigned)gy, gz), dim3(256), 0, stream, in, out, d, a, rest));
+            EML_CUDA(launch_k(reorder_tiled_kernel<T>, dim3((unsigned)gx, (unsigned)gy, gz), dim3(256), 0, stream, in, out, d, a, rest,
+                              d.len[rank - 1], d.len[a], d.istr[rank - 1], d.ostr[a]));
             count_launch();
             set_last_kernel("reorder_tiled");
             return check_launch("reorder (tiled)");
