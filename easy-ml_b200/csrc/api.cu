@@ -112,6 +112,12 @@ int contract_dev(DeviceCtx* ctx, const T* A, const T* B, T* C, int64_t batch, in
         // problem C^T = B^T A^T with the same kernels
         bool handled = false;
         int rc;
+        // C = G * G^T (the covariance's Gram matrix): A(i, k) and B(k, j) read the same buffer through mirrored
+        // strides, so C is symmetric -- the kernels compute the tiles on and above the diagonal only (and the f32
+        // path packs G once), then the upper triangle is mirrored.  Worth it from 4 x 4 tiles of 128 up.
+        const bool gram = (const void*)A == (const void*)B && batch == 1 && M == N && M >= 512 && !accumulate &&
+                          sA.r == sB.c && sA.c == sB.r && sC.c == 1;
+        if (gram) request_upper_only();
         if (sC.c != 1 && sC.r == 1) {
             set_pack_identity(id_b, id_a);  // the operands swap roles in the transposed problem
             Strides3 tA{sB.b, sB.c, sB.r}, tB{sA.b, sA.c, sA.r}, tC{sC.b, sC.c, sC.r};
@@ -121,8 +127,10 @@ int contract_dev(DeviceCtx* ctx, const T* A, const T* B, T* C, int64_t batch, in
             rc = tensor_core_path<T>(ctx, A, B, C, batch, M, N, K, sA, sB, sC, accumulate, stream, &handled);
         }
         take_pack_identity(&id_a, &id_b);  // whatever the kernel did not consume must not leak into a later call
+        take_upper_only_request();
+        const bool mirrored = take_upper_only_done();
         EML_TRY(rc);
-        if (handled) return EML_OK;
+        if (handled) return mirrored ? launch_mirror_upper<T>(C, M, sC.r, stream) : EML_OK;
     }
     if (!exact && N <= 16 && sA.c == 1 && M >= 256 && K >= 64)
         return launch_gemm_skinny<T>(A, B, C, batch, M, N, K, sA, sB, sC, accumulate, stream);

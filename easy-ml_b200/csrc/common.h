@@ -158,6 +158,17 @@ void set_remote_c(double* const* ptrs, int n);
 bool remote_c_pending();
 void clear_remote_c();
 
+// Symmetric products (C = G * G^T: the covariance's Gram matrix).  contract_dev recognises them from its arguments
+// (A and B are the same buffer read through mirrored strides) and asks the NEXT tensor-core launch on this thread to
+// compute only the tiles on and above the diagonal; a kernel that did so says so, and contract_dev then mirrors the
+// upper triangle into the lower one (which also makes the result exactly symmetric, as the reference's is).
+void request_upper_only();
+bool take_upper_only_request();  // reads and clears
+void mark_upper_only_done();
+bool take_upper_only_done();     // reads and clears
+template <class T>
+int launch_mirror_upper(T* C, int64_t n, int64_t ldc, cudaStream_t stream);  // C[j][i] = C[i][j] for i < j
+
 // Split/pack cache of the f32 tensor-core GEMM.  An operand whose contents never change (a constant record
 // container: the NN's inputs) is identified by a non-zero id; its packed TF32 planes are then kept and reused by
 // later calls with the same id, shape and strides (the NN step packs X twice per step otherwise).  The ids are

@@ -277,15 +277,27 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    constexpr int GROUP = 8;
-    int tile = blockIdx.x;
-    int tiles_per_group = GROUP * tiles_n;
-    int group = tile / tiles_per_group;
-    int first_m = group * GROUP;
-    int group_rows = tiles_m - first_m < GROUP ? tiles_m - first_m : GROUP;
-    int in_group = tile % tiles_per_group;
-    const int tm = first_m + in_group % group_rows;
-    const int tn = in_group / group_rows;
+    int tm, tn;
+    if (tiles_n == 0) {
+        // symmetric output (C = G * G^T): only the tiles on and above the diagonal, row by row
+        int t = blockIdx.x;
+        tm = 0;
+        while (t >= tiles_m - tm) {
+            t -= tiles_m - tm;
+            tm++;
+        }
+        tn = tm + t;
+    } else {
+        constexpr int GROUP = 8;
+        int tile = blockIdx.x;
+        int tiles_per_group = GROUP * tiles_n;
+        int group = tile / tiles_per_group;
+        int first_m = group * GROUP;
+        int group_rows = tiles_m - first_m < GROUP ? tiles_m - first_m : GROUP;
+        int in_group = tile % tiles_per_group;
+        tm = first_m + in_group % group_rows;
+        tn = in_group / group_rows;
+    }
     const int batch = blockIdx.y;
     const int ktiles = (int)((K + TBK - 1) / TBK);
 
@@ -438,7 +450,8 @@ int operand_map(CUtensorMap* map, const double* base, bool kin, int64_t mn, int6
 
 template <bool A_KIN, bool B_KIN>
 int launch(const double* A, const double* B, double* C, int64_t batch, int64_t M, int64_t N, int64_t K, int64_t lda,
-           int64_t ldb, int64_t ldc, int64_t stA, int64_t stB, int64_t stC, bool accumulate, cudaStream_t stream) {
+           int64_t ldb, int64_t ldc, int64_t stA, int64_t stB, int64_t stC, bool accumulate, cudaStream_t stream,
+           bool upper_only) {
     CUtensorMap mapA, mapB;
     EML_TRY(operand_map(&mapA, A, A_KIN, M, K, lda, batch, stA));
     EML_TRY(operand_map(&mapB, B, B_KIN, N, K, ldb, batch, stB));
@@ -452,6 +465,11 @@ int launch(const double* A, const double* B, double* C, int64_t batch, int64_t M
     }
     int64_t tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
     dim3 grid((unsigned)(tiles_m * tiles_n), (unsigned)batch);
+    if (upper_only) {  // the kernel reads tiles_n == 0 as "tiles on and above the diagonal only"
+        grid.x = (unsigned)(tiles_m * (tiles_m + 1) / 2);
+        tiles_n = 0;
+        mark_upper_only_done();
+    }
     const Remote remote = t_remote;
     t_remote.n = 0;  // consumed: the caller checks remote_c_pending() to see whether a kernel took them
     launch_k(kern, dim3(grid), dim3(TTHREADS), T_SMEM_BYTES, stream, mapA, mapB, C, M, N, K, ldc, stC, (int)tiles_m, (int)tiles_n,
@@ -542,14 +560,16 @@ int launch_gemm_dmma_f64(DeviceCtx*, const double* A, const double* B, double* C
     const char* forced = getenv("EML_DGEMM_KERNEL");
     const bool force_cpasync = forced && std::string(forced) == "cpasync";
     bool tma_ok = vec && !force_cpasync && al16(C) && ((A_KIN ? K : M) % 4 == 0) && ((B_KIN ? K : N) % 4 == 0);
+    // C = G * G^T requested by contract_dev: the TMA kernel computes the tiles on and above the diagonal only
+    const bool upper = take_upper_only_request() && tma_ok && M == N && !accumulate && !remote_c_pending();
     if (tma_ok) {
         if (A_KIN && !B_KIN)
-            return tma::launch<true, false>(A, B, C, batch, M, N, K, lda, ldb, ldc, sA.b, sB.b, sC.b, accumulate, stream);
+            return tma::launch<true, false>(A, B, C, batch, M, N, K, lda, ldb, ldc, sA.b, sB.b, sC.b, accumulate, stream, upper);
         if (A_KIN && B_KIN)
-            return tma::launch<true, true>(A, B, C, batch, M, N, K, lda, ldb, ldc, sA.b, sB.b, sC.b, accumulate, stream);
+            return tma::launch<true, true>(A, B, C, batch, M, N, K, lda, ldb, ldc, sA.b, sB.b, sC.b, accumulate, stream, upper);
         if (!A_KIN && !B_KIN)
-            return tma::launch<false, false>(A, B, C, batch, M, N, K, lda, ldb, ldc, sA.b, sB.b, sC.b, accumulate, stream);
-        return tma::launch<false, true>(A, B, C, batch, M, N, K, lda, ldb, ldc, sA.b, sB.b, sC.b, accumulate, stream);
+            return tma::launch<false, false>(A, B, C, batch, M, N, K, lda, ldb, ldc, sA.b, sB.b, sC.b, accumulate, stream, upper);
+        return tma::launch<false, true>(A, B, C, batch, M, N, K, lda, ldb, ldc, sA.b, sB.b, sC.b, accumulate, stream, upper);
     }
 #define EML_D(AK, BKK)                                                                                          \
     return vec ? launch_variant<AK, BKK, 2>(A, B, C, batch, M, N, K, lda, ldb, ldc, sA.b, sB.b, sC.b, accumulate, \

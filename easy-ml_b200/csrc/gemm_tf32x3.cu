@@ -374,10 +374,24 @@ struct Work {
     int tm, tn, batch, split;
 };
 
+// tiles_n == 0: symmetric output -- only the tiles on and above the diagonal of a tiles_m x tiles_m grid, row by row
 __device__ __forceinline__ Work decode(int w, int tiles_m, int tiles_n, int splits) {
     Work k;
     k.split = w % splits;
     int t = w / splits;
+    if (tiles_n == 0) {
+        const int tri = tiles_m * (tiles_m + 1) / 2;
+        k.batch = t / tri;
+        t %= tri;
+        int tm = 0;
+        while (t >= tiles_m - tm) {
+            t -= tiles_m - tm;
+            tm++;
+        }
+        k.tm = tm;
+        k.tn = tm + t;
+        return k;
+    }
     const int tiles = tiles_m * tiles_n;
     k.batch = t / tiles;
     t %= tiles;
@@ -571,7 +585,7 @@ tf32x3_pair_kernel(const __grid_constant__ Maps maps, float* __restrict__ C, int
 }
 
 int launch(const Maps& maps, float* C, int64_t batch, int64_t M, int64_t N, int64_t ldc, int64_t strideC, int kblocks,
-           int splits, int sms, bool accumulate, float* ws, cudaStream_t stream) {
+           int splits, int sms, bool accumulate, float* ws, cudaStream_t stream, bool upper_only = false) {
     static thread_local int configured_dev = -1;
     int dev = 0;
     EML_CUDA(cudaGetDevice(&dev));
@@ -579,10 +593,11 @@ int launch(const Maps& maps, float* C, int64_t batch, int64_t M, int64_t N, int6
         EML_CUDA(cudaFuncSetAttribute(tf32x3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
         configured_dev = dev;
     }
-    const int tiles_m = (int)((M + PM - 1) / PM), tiles_n = (int)((N + PN - 1) / PN);
+    const int tiles_m = (int)((M + PM - 1) / PM), tiles_n = upper_only ? 0 : (int)((N + PN - 1) / PN);
     const int per_split = (kblocks + splits - 1) / splits;
     const int used_splits = (kblocks + per_split - 1) / per_split;
-    const int64_t items = (int64_t)batch * tiles_m * tiles_n * used_splits;
+    const int64_t tiles = upper_only ? (int64_t)tiles_m * (tiles_m + 1) / 2 : (int64_t)tiles_m * tiles_n;
+    const int64_t items = (int64_t)batch * tiles * used_splits;
     if (items > 0x7fffffffLL) EML_BAD_ARG("tf32x3: too many work items");
     int clusters = sms / 2;
     if (items < clusters) clusters = (int)items;
@@ -758,13 +773,16 @@ int launch_gemm_tf32x3_f32(DeviceCtx* ctx, const float* A, const float* B, float
     const int64_t tiles_m = (M + BM - 1) / BM;
     // CTA-pair persistent kernel for outputs wider and taller than one 128-row tile
     const bool use_pair = M > 128 && N > 128 && !(forced && std::string(forced) == "1cta");
+    // C = G * G^T (requested by contract_dev): tiles on and above the diagonal only, and one packed copy of G
+    const bool upper_only = take_upper_only_request() && use_pair && M == N && !accumulate;
     int BN, splits = 1;
     int64_t Mp, Np;
     if (use_pair) {
         BN = pair::PN;
         Mp = round_up(M, pair::PM);
         Np = round_up(N, pair::PN);
-        const int64_t tiles = (Mp / pair::PM) * (Np / pair::PN) * batch;
+        const int64_t tm_ = Mp / pair::PM;
+        const int64_t tiles = (upper_only ? tm_ * (tm_ + 1) / 2 : tm_ * (Np / pair::PN)) * batch;
         const int clusters = sms / 2;
         if (tiles * 2 <= clusters && kblocks >= 8) {  // too few tiles for 74 SM pairs: deterministic split-K
             splits = (int)(clusters / tiles);
@@ -799,7 +817,7 @@ int launch_gemm_tf32x3_f32(DeviceCtx* ctx, const float* A, const float* B, float
     // (measured break-even: 4096^2, where M N / (M + N) = 2048).  It needs >= 24 k blocks per tile to amortise its
     // unoverlapped epilogue, and is pointless when a packed operand is cached (identity hints from the tape).
     // EML_SGEMM_FUSED=1 forces it wherever it can run, =0 disables it.
-    if (use_pair) {
+    if (use_pair && !upper_only) {
         const char* fe = getenv("EML_SGEMM_FUSED");
         const bool pays = a_id == 0 && b_id == 0 && kblocks >= 24 * splits && M * N < 1680 * (M + N);
         const bool want = fe ? fe[0] == '1' : pays;
@@ -813,7 +831,12 @@ int launch_gemm_tf32x3_f32(DeviceCtx* ctx, const float* A, const float* B, float
     float *a_big, *a_small, *b_big, *b_small;
     EML_TRY(packed_operand(a_id, A, batch, M, K, Mp, Kp, sA.b, sA.r, sA.c, a_scratch, stream, &a_big, &a_small));
     // B element (k, n) at B[k*sB.r + n*sB.c]: its "mn" index is n
-    EML_TRY(packed_operand(b_id, B, batch, N, K, Np, Kp, sB.b, sB.c, sB.r, b_scratch, stream, &b_big, &b_small));
+    if (upper_only) {  // B is the same matrix read through mirrored strides: the planes just packed serve both sides
+        b_big = a_big;
+        b_small = a_small;
+    } else {
+        EML_TRY(packed_operand(b_id, B, batch, N, K, Np, Kp, sB.b, sB.c, sB.r, b_scratch, stream, &b_big, &b_small));
+    }
     float* ws = nullptr;
     if (splits > 1) {
         EML_TRY(wsbuf.alloc(sizeof(float) * (size_t)splits * (size_t)(batch * M * N), stream));
@@ -827,8 +850,11 @@ int launch_gemm_tf32x3_f32(DeviceCtx* ctx, const float* A, const float* B, float
     EML_TRY(plane_map(&maps.b_big, b_big, Np, Kp, batch, b_box));
     EML_TRY(plane_map(&maps.b_small, b_small, Np, Kp, batch, b_box));
     set_last_kernel("tf32x3_tcgen05");
-    if (use_pair)
-        return pair::launch(maps, C, batch, M, N, sC.r, sC.b, kblocks, splits, sms, accumulate, ws, stream);
+    if (use_pair) {
+        EML_TRY(pair::launch(maps, C, batch, M, N, sC.r, sC.b, kblocks, splits, sms, accumulate, ws, stream, upper_only));
+        if (upper_only) mark_upper_only_done();
+        return EML_OK;
+    }
     if (BN == 256) return launch_tile<256>(maps, C, batch, M, N, sC.r, sC.b, kblocks, splits, accumulate, ws, stream);
     return launch_tile<128>(maps, C, batch, M, N, sC.r, sC.b, kblocks, splits, accumulate, ws, stream);
 }

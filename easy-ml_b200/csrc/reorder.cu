@@ -126,6 +126,40 @@ int launch_reorder(const T* in, T* out, int rank, const int64_t* out_lens, const
     return check_launch("reorder (gather)");
 }
 
+namespace {
+// C[j][i] = C[i][j] for every i < j: 32 x 32 tiles on and above the diagonal are read along their rows and written,
+// transposed through shared memory, along the rows of the mirrored tile
+template <class T>
+__global__ void __launch_bounds__(256)
+mirror_upper_kernel(T* __restrict__ C, int64_t n, int64_t ldc) {
+    pdl_prologue();
+    if (blockIdx.x < blockIdx.y) return;  // tile column < tile row: below the diagonal
+    __shared__ T tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t i0 = (int64_t)blockIdx.y * 32, j0 = (int64_t)blockIdx.x * 32;
+#pragma unroll
+    for (int r = ty; r < 32; r += 8)
+        if (i0 + r < n && j0 + tx < n) tile[r][tx] = C[(i0 + r) * ldc + j0 + tx];
+    __syncthreads();
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const int64_t row = j0 + r, col = i0 + tx;  // element (row, col) of the lower triangle <- tile[tx][r] = C[col][row]
+        if (row < n && col < row) C[row * ldc + col] = tile[tx][r];
+    }
+}
+}  // namespace
+
+template <class T>
+int launch_mirror_upper(T* C, int64_t n, int64_t ldc, cudaStream_t stream) {
+    const int64_t t = (n + 31) / 32;
+    if (t > 65535) EML_BAD_ARG("mirror: matrix too large");
+    EML_CUDA(launch_k(mirror_upper_kernel<T>, dim3((unsigned)t, (unsigned)t), dim3(256), 0, stream, C, n, ldc));
+    count_launch();
+    return check_launch("mirror upper triangle");
+}
+template int launch_mirror_upper<float>(float*, int64_t, int64_t, cudaStream_t);
+template int launch_mirror_upper<double>(double*, int64_t, int64_t, cudaStream_t);
+
 template int launch_reorder<float>(const float*, float*, int, const int64_t*, const int64_t*, cudaStream_t);
 template int launch_reorder<double>(const double*, double*, int, const int64_t*, const int64_t*, cudaStream_t);
 

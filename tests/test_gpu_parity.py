@@ -810,3 +810,43 @@ def test_sgemm_non_finite_and_huge_values():
     clean[:5, :] = False
     clean[:, :5] = False
     assert np.allclose(got[clean], b[clean], rtol=1e-6, atol=0) and finite.sum() > 0
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("axis", [1, 0])
+def test_gram_products_compute_the_upper_triangle_and_mirror_it(orc, dtype, axis):
+    """C = G * G^T (A and B are the same buffer read through mirrored strides): the tensor-core kernels compute
+    only the tiles on and above the diagonal and the upper triangle is mirrored.  On and above the diagonal the
+    numbers are those of the ordinary product of two separate buffers, the result is exactly symmetric (as the
+    reference's covariance is), and the covariance entry points (which go through it) still meet the bound."""
+    torch = pytest.importorskip("torch")
+    tdt = torch.float64 if dtype == np.float64 else torch.float32
+    f, s = 2304, 700  # 18 tiles of 128 / 9 pair tiles of 256: enough tiles that no split-K reformulation kicks in
+    g = torch.Generator(device="cuda").manual_seed(77 + axis)
+    G = torch.rand((s, f) if axis == 1 else (f, s), generator=g, device="cuda", dtype=tdt) - 0.3
+    fn = lib.eml_contract_f64_dev if dtype == np.float64 else lib.eml_contract_f32_dev
+    s3 = lambda *v: (C.c_int64 * 3)(*v)
+    vp = lambda t: C.c_void_p(t.data_ptr())
+    # A(i, k), B(k, j): feature-major reading of G on both sides
+    sa, sb = ((0, 1, f), (0, f, 1)) if axis == 1 else ((0, s, 1), (0, 1, s))
+    out = torch.full((f, f), float("nan"), device="cuda", dtype=tdt)
+    before = eml.kernel_launches()
+    check(fn(vp(G), vp(G), vp(out), 1, f, f, s, s3(*sa), s3(*sb), s3(0, f, 1), 0, None))
+    launches = eml.kernel_launches() - before
+    G2 = G.clone()
+    full = torch.empty((f, f), device="cuda", dtype=tdt)
+    check(fn(vp(G), vp(G2), vp(full), 1, f, f, s, s3(*sa), s3(*sb), s3(0, f, 1), 0, None))
+    torch.cuda.synchronize()
+    assert torch.equal(out, out.T)                                   # exactly symmetric
+    iu = torch.triu_indices(f, f, device="cuda")
+    assert torch.equal(out[iu[0], iu[1]], full[iu[0], iu[1]])        # same numbers on and above the diagonal
+    assert launches == (2 if dtype == np.float64 else 3), launches   # (one pack +) GEMM + mirror
+    # through the covariance entry point, against the oracle
+    x = G.cpu().numpy()
+    got = (eml.Matrix(x).covariance_column_features() if axis == 1 else eml.Matrix(x).covariance_row_features()).data
+    assert np.array_equal(got, got.T)
+    ref = orc.covariance(x[:, :48] if axis == 1 else x[:48], axis).astype(np.float64)
+    x64 = x.astype(np.float64)
+    xc = x64 - x64.mean(axis=0 if axis == 1 else 1, keepdims=True)
+    scale = (np.abs(xc).T @ np.abs(xc) if axis == 1 else np.abs(xc) @ np.abs(xc).T) / s
+    assert np.all(np.abs(got[:48, :48].astype(np.float64) - ref) <= TOL[np.dtype(dtype)] * scale[:48, :48] + 1e-30)
