@@ -205,9 +205,39 @@ int gemm_host_pipelined(DeviceCtx* ctx, const T* A, const T* B, T* C, int64_t M,
     NoSplitK no_split;  // same bits as one device launch over the whole problem
     StagedCopier mover(ctx);
 
+    // K panels of phase 1: the first one is split in two so that the GPU starts after half a panel's upload
+    std::vector<int64_t> kcut{0};
+    {
+        const int64_t half = round_to(kq / 2, 32);
+        if (half > 0 && 2 * half <= kq && K > kq) kcut.push_back(half);
+        for (int64_t k = kq; k < K; k += kq) kcut.push_back(k);
+        kcut.push_back(K);
+    }
+    // Row panels of phase 2: panels of R rows, except that the LAST one is small (its download is the only copy
+    // nothing hides) -- the smallest slab that still fills its waves to 85 % -- and the rows that do not fit the
+    // pattern go to the first panel.
+    std::vector<int64_t> rcut{M1};
+    if (M > M1) {
+        const int64_t rest_rows = M - M1;
+        int64_t tail = 0;
+        for (int64_t r = 1; r * tile * 4 <= R; r++) {
+            const int64_t tiles = r * tiles_n;
+            if ((double)tiles / (double)(((tiles + quantum - 1) / quantum) * quantum) >= 0.85) {
+                tail = r * tile;
+                break;
+            }
+        }
+        if (tail == 0 || rest_rows < R + tail) tail = 0;
+        const int64_t body = rest_rows - tail;
+        const int64_t first = body - (body > R ? ((body - R) / R) * R : 0);  // R + remainder (or everything)
+        for (int64_t r = M1 + first; r < M - tail; r += R) rcut.push_back(r);
+        if (tail) rcut.push_back(M - tail);
+        rcut.push_back(M);
+    }
+
     // the previous call's work on these streams is complete (every call ends with a synchronize)
-    for (int64_t k0 = 0, q = 0; k0 < K; k0 += kq, q++) {
-        const int64_t k1 = k0 + kq < K ? k0 + kq : K;
+    for (size_t q = 0; q + 1 < kcut.size(); q++) {
+        const int64_t k0 = kcut[q], k1 = kcut[q + 1];
         EML_TRY(mover.h2d(dB + k0 * N, N * es, B + k0 * ldb, ldb * es, N * es, k1 - k0, in));
         EML_TRY(mover.h2d(dA + k0, K * es, A + k0, lda * es, (k1 - k0) * es, M1, in));
         cudaEvent_t e = next_event();
@@ -222,8 +252,8 @@ int gemm_host_pipelined(DeviceCtx* ctx, const T* A, const T* B, T* C, int64_t M,
         EML_CUDA(cudaStreamWaitEvent(out, e, 0));
         EML_TRY(mover.d2h(C, ldc * es, dC, N * es, N * es, M1, out));
     }
-    for (int64_t r0 = M1; r0 < M; r0 += R) {
-        const int64_t r1 = r0 + R < M ? r0 + R : M;
+    for (size_t p = 0; p + 1 < rcut.size(); p++) {
+        const int64_t r0 = rcut[p], r1 = rcut[p + 1];
         EML_TRY(mover.h2d(dA + r0 * K, K * es, A + r0 * lda, lda * es, K * es, r1 - r0, in));
         cudaEvent_t e = next_event();
         EML_CUDA(cudaEventRecord(e, in));
