@@ -122,6 +122,112 @@ class Matrix {
     std::vector<T> data_;
 };
 
+// ------------------------------------------------------------------------------------------------ DeviceMatrix
+// Matrix<T> with its numbers in HBM: the same operators and panics as Matrix<T>, but an expression such as
+// ((a * b) + c).transpose() or the QR loop r = h * r; q = q * h (src/linear_algebra.rs:1531,1535) never leaves the
+// device.  `*` is the device contraction, `+ - neg` and the scalar forms the HBM-bound elementwise kernels
+// (src/matrices/operations.rs:41-163,1347-1552: one IEEE operation per element, bit-exact), transpose the tiled
+// reorder kernel (src/matrices/mod.rs:1277-1300).  Buffers come from the library's stream-ordered block cache
+// (eml_alloc_async on the default stream, where every operator is enqueued): no allocator call in steady state.
+template <class T>
+class DeviceMatrix {
+  public:
+    explicit DeviceMatrix(const Matrix<T>& m) : DeviceMatrix(m.rows(), m.columns()) {
+        detail::check(eml_copy_async(ptr_, m.data().data(), bytes(), nullptr));
+        detail::check(eml_sync());  // the source may be a temporary
+    }
+    DeviceMatrix(DeviceMatrix&& o) noexcept : rows_(o.rows_), cols_(o.cols_), ptr_(o.ptr_) { o.ptr_ = nullptr; }
+    DeviceMatrix& operator=(DeviceMatrix&& o) noexcept {
+        if (this != &o) {
+            release();
+            rows_ = o.rows_, cols_ = o.cols_, ptr_ = o.ptr_;
+            o.ptr_ = nullptr;
+        }
+        return *this;
+    }
+    DeviceMatrix(const DeviceMatrix&) = delete;
+    DeviceMatrix& operator=(const DeviceMatrix&) = delete;
+    ~DeviceMatrix() { release(); }
+
+    int64_t rows() const { return rows_; }
+    int64_t columns() const { return cols_; }
+    Matrix<T> to_host() const {
+        std::vector<T> out((size_t)(rows_ * cols_));
+        detail::check(eml_copy_async(out.data(), ptr_, bytes(), nullptr));
+        detail::check(eml_sync());
+        return Matrix<T>(rows_, cols_, std::move(out));
+    }
+
+    DeviceMatrix operator*(const DeviceMatrix& right) const {  // matrix_view_multiplication, operations.rs:165-196
+        if (cols_ != right.rows_) {
+            std::ostringstream m;
+            m << "Mismatched Matrices, left is " << rows_ << "x" << cols_ << ", right is " << right.rows_ << "x"
+              << right.cols_ << ", * is only defined for MxN * NxL";
+            throw Panic(m.str());
+        }
+        DeviceMatrix out(rows_, right.cols_);
+        const int64_t sa[3] = {0, cols_, 1}, sb[3] = {0, right.cols_, 1}, sc[3] = {0, right.cols_, 1};
+        if constexpr (detail::is_f32<T>)
+            detail::check(eml_contract_f32_dev(ptr_, right.ptr_, out.ptr_, 1, rows_, right.cols_, cols_, sa, sb, sc, 0, nullptr));
+        else
+            detail::check(eml_contract_f64_dev(ptr_, right.ptr_, out.ptr_, 1, rows_, right.cols_, cols_, sa, sb, sc, 0, nullptr));
+        return out;
+    }
+    DeviceMatrix operator+(const DeviceMatrix& o) const { return binary(EML_OP_ADD, o, "+"); }  // :41-72
+    DeviceMatrix operator-(const DeviceMatrix& o) const { return binary(EML_OP_SUB, o, "-"); }  // :76-107
+    DeviceMatrix operator-() const { return unary(EML_OP_NEG, T(0)); }
+    DeviceMatrix operator+(T c) const { return unary(EML_OP_ADD_C, c); }                        // :1347-1552
+    DeviceMatrix operator-(T c) const { return unary(EML_OP_SUB_C, c); }
+    DeviceMatrix operator*(T c) const { return unary(EML_OP_MUL_C, c); }
+    DeviceMatrix operator/(T c) const { return unary(EML_OP_DIV_C, c); }
+    DeviceMatrix transpose() const {  // Matrix::transpose, src/matrices/mod.rs:1277-1300
+        DeviceMatrix out(cols_, rows_);
+        const int64_t lens[2] = {cols_, rows_}, strides[2] = {1, cols_};
+        if constexpr (detail::is_f32<T>)
+            detail::check(eml_reorder_f32_dev(ptr_, out.ptr_, 2, lens, strides, nullptr));
+        else
+            detail::check(eml_reorder_f64_dev(ptr_, out.ptr_, 2, lens, strides, nullptr));
+        return out;
+    }
+
+  private:
+    DeviceMatrix(int64_t rows, int64_t cols) : rows_(rows), cols_(cols) {
+        detail::require_float<T>();
+        void* p = nullptr;
+        detail::check(eml_alloc_async(&p, bytes(), nullptr));
+        ptr_ = static_cast<T*>(p);
+    }
+    size_t bytes() const { return sizeof(T) * (size_t)(rows_ * cols_); }
+    void release() {
+        if (ptr_) eml_free_async(ptr_, bytes(), nullptr);
+        ptr_ = nullptr;
+    }
+    DeviceMatrix unary(int op, T c) const {
+        DeviceMatrix out(rows_, cols_);
+        if constexpr (detail::is_f32<T>)
+            detail::check(eml_unary_f32_dev(op, c, ptr_, out.ptr_, nullptr, rows_ * cols_, nullptr));
+        else
+            detail::check(eml_unary_f64_dev(op, c, ptr_, out.ptr_, nullptr, rows_ * cols_, nullptr));
+        return out;
+    }
+    DeviceMatrix binary(int op, const DeviceMatrix& o, const char* symbol) const {
+        if (rows_ != o.rows_ || cols_ != o.cols_) {
+            std::ostringstream m;
+            m << "Mismatched matrices, left is " << rows_ << "x" << cols_ << ", right is " << o.rows_ << "x" << o.cols_
+              << ", " << symbol << " is only defined for MxN " << symbol << " MxN";
+            throw Panic(m.str());
+        }
+        DeviceMatrix out(rows_, cols_);
+        if constexpr (detail::is_f32<T>)
+            detail::check(eml_binary_f32_dev(op, ptr_, o.ptr_, out.ptr_, nullptr, nullptr, rows_ * cols_, nullptr));
+        else
+            detail::check(eml_binary_f64_dev(op, ptr_, o.ptr_, out.ptr_, nullptr, nullptr, rows_ * cols_, nullptr));
+        return out;
+    }
+    int64_t rows_, cols_;
+    T* ptr_ = nullptr;
+};
+
 // ------------------------------------------------------------------------------------------------ GEMM callers
 // linear_algebra::cholesky_decomposition, src/linear_algebra.rs:1008-1101 (Cholesky-Banachiewicz, row by row).
 // Host side, as in the reference: O(N^3 / 3) sequential work on the small covariance matrix.

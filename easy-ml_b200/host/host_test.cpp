@@ -182,6 +182,24 @@ static void distribution_goldens() {
            "Mean must be a column vector");
 }
 
+// Device-resident operator chains: same numbers as the host-operand operators, same panics
+template <class T>
+static void device_matrix_checks() {
+    Matrix<T> a(3, 2, {1, 2, 3, 4, 5, 6}), b(2, 3, {1, 2, 3, 4, 5, 6}), c(3, 3, {1, 0, 0, 0, 1, 0, 0, 0, 1});
+    DeviceMatrix<T> da(a), db(b), dc(c);
+    EXPECT((da * db).to_host() == a * b);                                            // tests/matrices.rs:161-166
+    EXPECT(((da * db) + dc).to_host() == Matrix<T>(3, 3, {10, 12, 15, 19, 27, 33, 29, 40, 52}));
+    EXPECT((da * db - dc).transpose().to_host() == Matrix<T>(3, 3, {8, 19, 29, 12, 25, 40, 15, 33, 50}));
+    EXPECT((-da).to_host() == Matrix<T>(3, 2, {-1, -2, -3, -4, -5, -6}));
+    EXPECT((da * T(2) + T(1)).to_host() == Matrix<T>(3, 2, {3, 5, 7, 9, 11, 13}));
+    EXPECT((da / T(2) - T(1)).to_host() == Matrix<T>(3, 2, {T(-0.5), 0, T(0.5), 1, T(1.5), 2}));
+    EXPECT(da.transpose().to_host() == Matrix<T>(2, 3, {1, 3, 5, 2, 4, 6}));
+    EXPECT(panic_text([&] { (void)(da * da); }) ==
+           "Mismatched Matrices, left is 3x2, right is 3x2, * is only defined for MxN * NxL");
+    EXPECT(panic_text([&] { (void)(da + db); }) ==
+           "Mismatched matrices, left is 3x2, right is 2x3, + is only defined for MxN + MxN");
+}
+
 int main() {
     int n = 0;
     if (eml_init(&n) != EML_OK) {
@@ -205,6 +223,8 @@ int main() {
     record_goldens<float>();
     record_goldens<double>();
     distribution_goldens();
+    device_matrix_checks<float>();
+    device_matrix_checks<double>();
     if (failures) {
         std::fprintf(stderr, "%d check(s) failed\n", failures);
         return 1;
