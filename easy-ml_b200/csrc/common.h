@@ -222,6 +222,8 @@ int launch_binary(int op, const T* x, const T* y, T* z, T* dzdx, T* dzdy, int64_
 template <class T>
 int launch_chain(const T* dout, const T* deriv, T* dparent, int64_t n, cudaStream_t stream);
 template <class T>
+int launch_chain_ex(const T* dout, const T* deriv, T c, T* dparent, bool overwrite, int64_t n, cudaStream_t stream);
+template <class T>
 int launch_sgd(T* w, const T* d, T lr, int64_t n, cudaStream_t stream);
 // out[i] = w[i] - lr * d[i] (the same update into a fresh container, one pass)
 template <class T>

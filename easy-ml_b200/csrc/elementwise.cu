@@ -141,6 +141,9 @@ binary_kernel(const T* __restrict__ x, const T* __restrict__ y, T* __restrict__ 
 }
 
 // MODE 0: dparent += dout*deriv   1: w -= lr*d  (lr in c)   2: out = c   3: dst += src   4: out = b - lr*a
+//      5: dparent = dout*deriv + 0   6: dparent += dout*c   7: dparent = dout*c + 0
+// (5 and 7 are the FIRST contribution to a derivative that the reference holds as 0 at that point: 0 + x, so a
+//  product of -0 still ends up as +0; the buffer needs no zero fill and is not read)
 template <class T, int MODE, bool VEC>
 __global__ void __launch_bounds__(EW_THREADS)
 axpy_kernel(T c, const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, int64_t n) {
@@ -151,8 +154,8 @@ axpy_kernel(T c, const T* __restrict__ a, const T* __restrict__ b, T* __restrict
         if (VEC && i + V <= n) {
             T av[Vec<T>::N], bv[Vec<T>::N], ov[Vec<T>::N];
             if (MODE != 2) vload<T>(a + i, av);
-            if (MODE == 0 || MODE == 4) vload<T>(b + i, bv);
-            if (MODE != 2 && MODE != 4) vload<T>(out + i, ov);
+            if (MODE == 0 || MODE == 4 || MODE == 5) vload<T>(b + i, bv);
+            if (MODE == 0 || MODE == 1 || MODE == 3 || MODE == 6) vload<T>(out + i, ov);
 #pragma unroll
             for (int j = 0; j < Vec<T>::N; j++) {
                 if (MODE == 0) ov[j] = ov[j] + av[j] * bv[j];
@@ -160,6 +163,9 @@ axpy_kernel(T c, const T* __restrict__ a, const T* __restrict__ b, T* __restrict
                 if (MODE == 2) ov[j] = c;
                 if (MODE == 3) ov[j] = ov[j] + av[j];
                 if (MODE == 4) ov[j] = bv[j] - av[j] * c;
+                if (MODE == 5) ov[j] = av[j] * bv[j] + T(0);
+                if (MODE == 6) ov[j] = ov[j] + av[j] * c;
+                if (MODE == 7) ov[j] = av[j] * c + T(0);
             }
             vstore<T>(out + i, ov);
         } else {
@@ -170,6 +176,9 @@ axpy_kernel(T c, const T* __restrict__ a, const T* __restrict__ b, T* __restrict
                 if (MODE == 2) out[q] = c;
                 if (MODE == 3) out[q] = out[q] + a[q];
                 if (MODE == 4) out[q] = b[q] - a[q] * c;
+                if (MODE == 5) out[q] = a[q] * b[q] + T(0);
+                if (MODE == 6) out[q] = out[q] + a[q] * c;
+                if (MODE == 7) out[q] = a[q] * c + T(0);
             }
         }
     }
@@ -491,6 +500,15 @@ template <class T>
 int launch_chain(const T* dout, const T* deriv, T* dparent, int64_t n, cudaStream_t stream) {
     return launch_axpy<T, 0>(T(0), dout, deriv, dparent, n, stream);
 }
+// dparent (+)= dout * deriv with deriv an array or (deriv == nullptr) the constant c; overwrite = first contribution
+template <class T>
+int launch_chain_ex(const T* dout, const T* deriv, T c, T* dparent, bool overwrite, int64_t n, cudaStream_t stream) {
+    if (deriv)
+        return overwrite ? launch_axpy<T, 5>(T(0), dout, deriv, dparent, n, stream)
+                         : launch_axpy<T, 0>(T(0), dout, deriv, dparent, n, stream);
+    return overwrite ? launch_axpy<T, 7>(c, dout, nullptr, dparent, n, stream)
+                     : launch_axpy<T, 6>(c, dout, nullptr, dparent, n, stream);
+}
 template <class T>
 int launch_sgd(T* w, const T* d, T lr, int64_t n, cudaStream_t stream) {
     return launch_axpy<T, 1>(lr, d, nullptr, w, n, stream);
@@ -646,6 +664,7 @@ int launch_einsum_n(int n_ops, const T* const* x, T* out, int n_out, const int64
     template int launch_unary<T>(int, T, const T*, T*, T*, int64_t, cudaStream_t);                               \
     template int launch_binary<T>(int, const T*, const T*, T*, T*, T*, int64_t, cudaStream_t);                   \
     template int launch_chain<T>(const T*, const T*, T*, int64_t, cudaStream_t);                                 \
+    template int launch_chain_ex<T>(const T*, const T*, T, T*, bool, int64_t, cudaStream_t);                     \
     template int launch_sgd<T>(T*, const T*, T, int64_t, cudaStream_t);                                          \
     template int launch_sgd_out<T>(T*, const T*, const T*, T, int64_t, cudaStream_t);                            \
     template int launch_fill<T>(T*, T, int64_t, cudaStream_t);                                                   \

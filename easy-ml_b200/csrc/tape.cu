@@ -72,6 +72,10 @@ struct Node {
     int p0 = -1, p1 = -1;
     bool p0_tracked = false, p1_tracked = false;
     Buf a, b;  // matmul: parent numbers A, B.  unary: a = dy/dx.  binary: a = dz/dx, b = dz/dy.
+    // elementwise rules whose derivative is the same number for every element (-x, x +- c, x * c, x / c, c - x,
+    // x + y, x - y): no derivative array is written in the forward pass or read in the sweep
+    bool a_const = false, b_const = false;
+    double a_c = 0, b_c = 0;
     // index of element e of the produced container on the reference tape
     int64_t index_of(int64_t e) const {
         if (kind == Kind::MATMUL && K > 1) return base + e * (2 * K - 1) + 2 * K - 2;
@@ -280,8 +284,17 @@ int tape_unary(eml_tape* t, int op, double cst, eml_val hx, eml_val* out) {
         nd.count = nd.n = n;
         nd.p0 = nx;
         nd.p0_tracked = true;
-        EML_TRY(new_buf(sizeof(T) * n, t->stream, &nd.a));
-        EML_TRY(launch_unary<T>(op, (T)cst, (const T*)x->numbers->p, (T*)y.numbers->p, (T*)nd.a->p, n, t->stream));
+        // the same expressions as unary_rule (csrc/elementwise.cu), evaluated in T
+        const T c = (T)cst;
+        switch (nx >= 0 ? op : -1) {  // (a parent carrying Index 0 keeps the array: its sweep is a dot product)
+            case EML_OP_NEG: case EML_OP_C_SUB: nd.a_const = true; nd.a_c = (double)(-T(1)); break;
+            case EML_OP_ADD_C: case EML_OP_SUB_C: nd.a_const = true; nd.a_c = (double)T(1); break;
+            case EML_OP_MUL_C: nd.a_const = true; nd.a_c = (double)c; break;
+            case EML_OP_DIV_C: nd.a_const = true; nd.a_c = (double)(T(1) / c); break;
+            default: break;
+        }
+        if (!nd.a_const) EML_TRY(new_buf(sizeof(T) * n, t->stream, &nd.a));
+        EML_TRY(launch_unary<T>(op, c, (const T*)x->numbers->p, (T*)y.numbers->p, nd.a ? (T*)nd.a->p : nullptr, n, t->stream));
         t->len += n;
         t->nodes.push_back(nd);
         y.tracked = true;
@@ -324,8 +337,11 @@ int tape_binary(eml_tape* t, int op, eml_val hx, eml_val hy, eml_val* out) {
         nd.p1 = ny;
         nd.p0_tracked = x->tracked;  // binary_x_history / binary_y_history / binary_both_history
         nd.p1_tracked = y->tracked;
-        if (nd.p0_tracked) EML_TRY(new_buf(sizeof(T) * n, t->stream, &nd.a));
-        if (nd.p1_tracked) EML_TRY(new_buf(sizeof(T) * n, t->stream, &nd.b));
+        if ((op == EML_OP_ADD || op == EML_OP_SUB) && nd.p0_tracked && nx >= 0) nd.a_const = true, nd.a_c = 1.0;
+        if ((op == EML_OP_ADD || op == EML_OP_SUB) && nd.p1_tracked && ny >= 0)
+            nd.b_const = true, nd.b_c = op == EML_OP_ADD ? 1.0 : -1.0;
+        if (nd.p0_tracked && !nd.a_const) EML_TRY(new_buf(sizeof(T) * n, t->stream, &nd.a));
+        if (nd.p1_tracked && !nd.b_const) EML_TRY(new_buf(sizeof(T) * n, t->stream, &nd.b));
         EML_TRY(launch_binary<T>(op, xp, yp, (T*)z.numbers->p, nd.a ? (T*)nd.a->p : nullptr,
                                  nd.b ? (T*)nd.b->p : nullptr, n, t->stream));
         t->len += n;
@@ -377,7 +393,35 @@ int tape_sweep(eml_tape* t, eml_val hv, int64_t row, int64_t col, eml_derivs** o
     }
     Buf arena;
     EML_TRY(new_buf(total, st, &arena));
-    EML_CUDA(cudaMemsetAsync(arena->p, 0, total, st));
+    // vec![0; len]: a node's derivatives only need the zero fill when something ADDS into them first.  The sweep
+    // visits consumers in descending order, so the first contribution to node p comes from its highest consumer; when
+    // that is an elementwise rule, it writes  0 + dout * deriv  instead (same bits) and p is neither cleared nor read.
+    const int n_nodes = (int)t->nodes.size();
+    std::vector<int> first_consumer(n_nodes, -1);
+    for (int i = 0; i < n_nodes; i++) {
+        const Node& nd = t->nodes[i];
+        if (nd.kind == Kind::VARIABLES) continue;
+        const bool uses0 = nd.kind == Kind::BINARY ? nd.p0_tracked : true, uses1 = nd.kind == Kind::BINARY ? nd.p1_tracked : nd.kind == Kind::MATMUL;
+        if (uses0 && nd.p0 >= 0) first_consumer[nd.p0] = i;
+        if (uses1 && nd.p1 >= 0) first_consumer[nd.p1] = i;
+    }
+    std::vector<char> written(n_nodes, 0);
+    for (int i = 0; i < n_nodes; i++) {
+        const int c = first_consumer[i];
+        const bool overwritten_first = c >= 0 && t->nodes[c].kind != Kind::MATMUL && i != nv;
+        written[i] = !overwritten_first;  // "written" = holds defined numbers (zeros) before the sweep
+    }
+    EML_CUDA(cudaMemsetAsync(arena->p, 0, 256, st));
+    for (int i = 0; i < n_nodes;) {
+        if (!written[i]) {
+            i++;
+            continue;
+        }
+        int j = i;
+        while (j + 1 < n_nodes && written[j + 1]) j++;
+        EML_CUDA(cudaMemsetAsync((char*)arena->p + offs[i], 0, (j + 1 < n_nodes ? offs[j + 1] : total) - offs[i], st));
+        i = j + 1;
+    }
     for (size_t i = 0; i < t->nodes.size(); i++) d->grads[i] = view_of(arena, offs[i], sizeof(T) * (size_t)t->nodes[i].n);
     // contributions to reference index 0 from parents that carry Index 0 (constants)
     T* const slot0_ptr = static_cast<T*>(arena->p);
@@ -389,29 +433,32 @@ int tape_sweep(eml_tape* t, eml_val hv, int64_t row, int64_t col, eml_derivs** o
         EML_TRY(launch_fill<T>(slot0_ptr, T(1), 1, st));
         slot0_used = true;
     }
+    // dparent (+)= g * (deriv array | constant): the first contribution to an uncleared buffer overwrites
+    auto contribute = [&](int p, const T* g, const Buf& deriv, bool is_const, double c, int64_t n) -> int {
+        const bool overwrite = !written[p];
+        written[p] = 1;
+        return launch_chain_ex<T>(g, is_const ? nullptr : (const T*)deriv->p, (T)c, (T*)d->grads[p]->p, overwrite, n, st);
+    };
 
     for (int i = (int)t->nodes.size() - 1; i >= 0; i--) {
         const Node& nd = t->nodes[i];
         const T* g = (const T*)d->grads[i]->p;
         if (nd.kind == Kind::VARIABLES) continue;
         if (nd.kind == Kind::UNARY) {
-            if (!nd.a) {  // derivative is exactly 1 for every element (x - constant): dparent += dout
-                if (nd.p0 >= 0)
-                    EML_TRY(launch_add_inplace<T>((T*)d->grads[nd.p0]->p, g, nd.n, st));
-                else {
-                    EML_TRY(launch_reduce_sum<T>(t->ctx, g, nd.n, slot0_ptr, true, st));
-                    slot0_used = true;
-                }
-            } else if (nd.p0 >= 0)
-                EML_TRY(launch_chain<T>(g, (const T*)nd.a->p, (T*)d->grads[nd.p0]->p, nd.n, st));
-            else {
+            const bool unit = !nd.a && !nd.a_const;  // the in-place SGD node of a recorded step: derivative 1
+            if (nd.p0 >= 0)
+                EML_TRY(contribute(nd.p0, g, nd.a, nd.a_const || unit, unit ? 1.0 : nd.a_c, nd.n));
+            else if (!nd.a) {
+                EML_TRY(launch_reduce_sum<T>(t->ctx, g, nd.n, slot0_ptr, true, st));
+                slot0_used = true;
+            } else {
                 EML_TRY(launch_dot_accumulate<T>(t->ctx, g, (const T*)nd.a->p, nd.n, slot0_ptr, true, st));
                 slot0_used = true;
             }
         } else if (nd.kind == Kind::BINARY) {
             if (nd.p0_tracked) {
                 if (nd.p0 >= 0)
-                    EML_TRY(launch_chain<T>(g, (const T*)nd.a->p, (T*)d->grads[nd.p0]->p, nd.n, st));
+                    EML_TRY(contribute(nd.p0, g, nd.a, nd.a_const, nd.a_c, nd.n));
                 else {
                     EML_TRY(launch_dot_accumulate<T>(t->ctx, g, (const T*)nd.a->p, nd.n, slot0_ptr, true, st));
                     slot0_used = true;
@@ -419,7 +466,7 @@ int tape_sweep(eml_tape* t, eml_val hv, int64_t row, int64_t col, eml_derivs** o
             }
             if (nd.p1_tracked) {
                 if (nd.p1 >= 0)
-                    EML_TRY(launch_chain<T>(g, (const T*)nd.b->p, (T*)d->grads[nd.p1]->p, nd.n, st));
+                    EML_TRY(contribute(nd.p1, g, nd.b, nd.b_const, nd.b_c, nd.n));
                 else {
                     EML_TRY(launch_dot_accumulate<T>(t->ctx, g, (const T*)nd.b->p, nd.n, slot0_ptr, true, st));
                     slot0_used = true;

@@ -850,3 +850,35 @@ def test_gram_products_compute_the_upper_triangle_and_mirror_it(orc, dtype, axis
     xc = x64 - x64.mean(axis=0 if axis == 1 else 1, keepdims=True)
     scale = (np.abs(xc).T @ np.abs(xc) if axis == 1 else np.abs(xc) @ np.abs(xc).T) / s
     assert np.all(np.abs(got[:48, :48].astype(np.float64) - ref) <= TOL[np.dtype(dtype)] * scale[:48, :48] + 1e-30)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_sweep_first_contribution_overwrites_like_zero_plus_x(orc, dtype):
+    """The sweep does not clear derivative buffers whose first contribution comes from an elementwise rule: it
+    writes 0 + dout * deriv instead.  Every observable must stay the reference's: the whole derivative vector
+    equals the oracle's scalar tape bit for bit on exactly representable data, including +0 (not -0) where a
+    zero derivative meets a negative rule, derivatives taken of an INTERMEDIATE (later nodes contribute zeros to
+    it and must not wipe the seed), and a parent that is used twice by one rule and again by a later one."""
+    x0 = np.array([[1.0, -2.0, 0.5], [4.0, 0.25, -8.0]], dtype)
+    hist = eml.WengertList(dtype)
+    X = eml.RecordTensor.variables(hist, eml.Tensor([("r", 2), ("c", 3)], x0))
+    neg = -X                                   # constant derivative -1: no derivative array
+    sq = neg.elementwise_multiply(neg)         # one rule, the same parent twice
+    mix = (sq - neg) * 0.5 + 2.0               # x - y (1, -1), * c, + c
+    out = mix / 4.0 - X                        # / c, and X used again by a later rule
+
+    tape = orc.Tape(dtype)
+    ox = tape.variables(x0)
+    oneg = tape.unary(0, ox)
+    osq = tape.binary(34, oneg, oneg, mode=3)
+    omix = tape.unary(6, tape.unary(8, tape.binary(33, osq, oneg, mode=3), 0.5), 2.0)
+    oout = tape.binary(33, tape.unary(9, omix, 4.0), ox, mode=3)
+    assert len(hist) == len(tape) and np.array_equal(out.indexes(), oout[1])
+    assert np.array_equal(out.numbers().data, oout[0])
+
+    for target, otarget in ((out, oout), (mix, omix), (neg, oneg)):   # the output and two intermediates
+        for (i, j) in ((0, 0), (1, 2)):
+            got = np.asarray(target.derivatives_for([i, j]).to_vec(), dtype)
+            want = np.asarray(tape.derivatives(otarget[1][i, j]), dtype)
+            assert np.array_equal(got, want), (i, j)
+            assert np.array_equal(np.signbit(got), np.signbit(want)), "a -0 where the reference holds +0"
