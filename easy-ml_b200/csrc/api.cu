@@ -28,32 +28,23 @@ struct Threshold<float> {
 template <class T>
 int tensor_core_path(DeviceCtx* ctx, const T* A, const T* B, T* C, int64_t batch, int64_t M, int64_t N,
                      int64_t K, Strides3 sA, Strides3 sB, Strides3 sC, bool accumulate, cudaStream_t stream,
-                     bool* handled);
+                     bool* handled, GemmOptions* opt);
 template <>
 int tensor_core_path<double>(DeviceCtx* ctx, const double* A, const double* B, double* C, int64_t batch,
                              int64_t M, int64_t N, int64_t K, Strides3 sA, Strides3 sB, Strides3 sC,
-                             bool accumulate, cudaStream_t stream, bool* handled) {
-    return launch_gemm_dmma_f64(ctx, A, B, C, batch, M, N, K, sA, sB, sC, accumulate, stream, handled);
+                             bool accumulate, cudaStream_t stream, bool* handled, GemmOptions* opt) {
+    return launch_gemm_dmma_f64(ctx, A, B, C, batch, M, N, K, sA, sB, sC, accumulate, stream, handled, opt);
 }
 template <>
 int tensor_core_path<float>(DeviceCtx* ctx, const float* A, const float* B, float* C, int64_t batch, int64_t M,
                             int64_t N, int64_t K, Strides3 sA, Strides3 sB, Strides3 sC, bool accumulate,
-                            cudaStream_t stream, bool* handled) {
-    return launch_gemm_tf32x3_f32(ctx, A, B, C, batch, M, N, K, sA, sB, sC, accumulate, stream, handled);
+                            cudaStream_t stream, bool* handled, GemmOptions* opt) {
+    return launch_gemm_tf32x3_f32(ctx, A, B, C, batch, M, N, K, sA, sB, sC, accumulate, stream, handled, opt);
 }
 
 }  // namespace
 
 namespace {
-// set around launches whose bits must not depend on how the caller partitioned the rows (the pipelined
-// host GEMM equals a single device launch bit for bit)
-thread_local bool t_no_split_k = false;
-struct NoSplitK {
-    bool prev;
-    NoSplitK() : prev(t_no_split_k) { t_no_split_k = true; }
-    ~NoSplitK() { t_no_split_k = prev; }
-};
-
 template <class T>
 struct SplitK;
 // f64: the DMMA kernels have no split of their own.  f32: gemm_tf32x3.cu splits inside its own launch, so
@@ -70,10 +61,11 @@ struct SplitK<float> {
 
 template <class T>
 int contract_dev(DeviceCtx* ctx, const T* A, const T* B, T* C, int64_t batch, int64_t M, int64_t N, int64_t K,
-                 Strides3 sA, Strides3 sB, Strides3 sC, bool accumulate, bool exact, cudaStream_t stream) {
-    // pack-cache hints belong to THIS call only: take them now, hand them to the f32 tensor-core kernel below
-    uint64_t id_a = 0, id_b = 0;
-    take_pack_identity(&id_a, &id_b);
+                 Strides3 sA, Strides3 sB, Strides3 sC, bool accumulate, bool exact, cudaStream_t stream,
+                 GemmOptions* opt) {
+    GemmOptions local;
+    if (!opt) opt = &local;
+    opt->remote_done = opt->upper_done = false;
     // tall-skinny A^T * B (N <= 16, A contiguous along m, long K): its own chunked kernel
     if (!exact && batch == 1 && N >= 1 && N <= 16 && sA.r == 1 && sA.c != 1 && K >= 256 && M >= 32 && A && B && C)
         return launch_gemm_skinny_tn<T>(ctx, A, B, C, M, N, K, sA, sB, sC, accumulate, stream);
@@ -81,7 +73,7 @@ int contract_dev(DeviceCtx* ctx, const T* A, const T* B, T* C, int64_t batch, in
     // L[1 x batch] * d[batch x 10], dW2 = H^T[512 x batch] * dY[batch x 10], ...): K is cut into S equal
     // chunks which run as S "batches" of one launch into a workspace [S][M][N]; a fixed-order reduction
     // adds them.  S depends on the shape only, so results stay bit-identical run to run.
-    if (!exact && !t_no_split_k && batch == 1 && M > 0 && N > 0 && K >= 512 && A && B && C &&
+    if (!exact && !opt->no_split_k && batch == 1 && M > 0 && N > 0 && K >= 512 && A && B && C &&
         SplitK<T>::wanted(M, N, K)) {
         const bool tc = Threshold<T>::tensor_core(M, N, K);
         const int64_t tile = tc ? 128 : 64, min_chunk = tc ? 256 : 64;
@@ -115,22 +107,20 @@ int contract_dev(DeviceCtx* ctx, const T* A, const T* B, T* C, int64_t batch, in
         // C = G * G^T (the covariance's Gram matrix): A(i, k) and B(k, j) read the same buffer through mirrored
         // strides, so C is symmetric -- the kernels compute the tiles on and above the diagonal only (and the f32
         // path packs G once), then the upper triangle is mirrored.  Worth it from 4 x 4 tiles of 128 up.
-        const bool gram = (const void*)A == (const void*)B && batch == 1 && M == N && M >= 512 && !accumulate &&
-                          sA.r == sB.c && sA.c == sB.r && sC.c == 1;
-        if (gram) request_upper_only();
+        opt->upper_only = (const void*)A == (const void*)B && batch == 1 && M == N && M >= 512 && !accumulate &&
+                          sA.r == sB.c && sA.c == sB.r && sC.c == 1 && opt->n_remote == 0;
         if (sC.c != 1 && sC.r == 1) {
-            set_pack_identity(id_b, id_a);  // the operands swap roles in the transposed problem
+            GemmOptions swapped = *opt;  // the operands swap roles in the transposed problem
+            swapped.a_id = opt->b_id;
+            swapped.b_id = opt->a_id;
             Strides3 tA{sB.b, sB.c, sB.r}, tB{sA.b, sA.c, sA.r}, tC{sC.b, sC.c, sC.r};
-            rc = tensor_core_path<T>(ctx, B, A, C, batch, N, M, K, tA, tB, tC, accumulate, stream, &handled);
+            rc = tensor_core_path<T>(ctx, B, A, C, batch, N, M, K, tA, tB, tC, accumulate, stream, &handled, &swapped);
+            opt->remote_done = swapped.remote_done;
         } else {
-            set_pack_identity(id_a, id_b);
-            rc = tensor_core_path<T>(ctx, A, B, C, batch, M, N, K, sA, sB, sC, accumulate, stream, &handled);
+            rc = tensor_core_path<T>(ctx, A, B, C, batch, M, N, K, sA, sB, sC, accumulate, stream, &handled, opt);
         }
-        take_pack_identity(&id_a, &id_b);  // whatever the kernel did not consume must not leak into a later call
-        take_upper_only_request();
-        const bool mirrored = take_upper_only_done();
         EML_TRY(rc);
-        if (handled) return mirrored ? launch_mirror_upper<T>(C, M, sC.r, stream) : EML_OK;
+        if (handled) return opt->upper_done ? launch_mirror_upper<T>(C, M, sC.r, stream) : EML_OK;
     }
     if (!exact && N <= 16 && sA.c == 1 && M >= 256 && K >= 64)
         return launch_gemm_skinny<T>(A, B, C, batch, M, N, K, sA, sB, sC, accumulate, stream);
@@ -138,9 +128,9 @@ int contract_dev(DeviceCtx* ctx, const T* A, const T* B, T* C, int64_t batch, in
 }
 
 template int contract_dev<float>(DeviceCtx*, const float*, const float*, float*, int64_t, int64_t, int64_t,
-                                 int64_t, Strides3, Strides3, Strides3, bool, bool, cudaStream_t);
+                                 int64_t, Strides3, Strides3, Strides3, bool, bool, cudaStream_t, GemmOptions*);
 template int contract_dev<double>(DeviceCtx*, const double*, const double*, double*, int64_t, int64_t, int64_t,
-                                  int64_t, Strides3, Strides3, Strides3, bool, bool, cudaStream_t);
+                                  int64_t, Strides3, Strides3, Strides3, bool, bool, cudaStream_t, GemmOptions*);
 
 namespace {
 
@@ -202,7 +192,8 @@ int gemm_host_pipelined(DeviceCtx* ctx, const T* A, const T* B, T* C, int64_t M,
     if (M1 > M) M1 = M;
     int64_t R = whole_waves(1152, M - M1 > 0 ? M - M1 : 1);  // row panel of phase 2 (the last one takes the rest)
     if (R < tile) R = tile;
-    NoSplitK no_split;  // same bits as one device launch over the whole problem
+    GemmOptions same_bits;  // same bits as one device launch over the whole problem
+    same_bits.no_split_k = true;
     StagedCopier mover(ctx);
 
     // K panels of phase 1: the first one is split in two so that the GPU starts after half a panel's upload
@@ -244,7 +235,7 @@ int gemm_host_pipelined(DeviceCtx* ctx, const T* A, const T* B, T* C, int64_t M,
         EML_CUDA(cudaEventRecord(e, in));
         EML_CUDA(cudaStreamWaitEvent(cs, e, 0));
         EML_TRY(contract_dev<T>(ctx, dA + k0, dB + k0 * N, dC, 1, M1, N, k1 - k0, Strides3{0, K, 1}, Strides3{0, N, 1},
-                                Strides3{0, N, 1}, q > 0, false, cs));
+                                Strides3{0, N, 1}, q > 0, false, cs, &same_bits));
     }
     {
         cudaEvent_t e = next_event();
@@ -259,7 +250,7 @@ int gemm_host_pipelined(DeviceCtx* ctx, const T* A, const T* B, T* C, int64_t M,
         EML_CUDA(cudaEventRecord(e, in));
         EML_CUDA(cudaStreamWaitEvent(cs, e, 0));
         EML_TRY(contract_dev<T>(ctx, dA + r0 * K, dB, dC + r0 * N, 1, r1 - r0, N, K, Strides3{0, K, 1},
-                                Strides3{0, N, 1}, Strides3{0, N, 1}, false, false, cs));
+                                Strides3{0, N, 1}, Strides3{0, N, 1}, false, false, cs, &same_bits));
         cudaEvent_t d = next_event();
         EML_CUDA(cudaEventRecord(d, cs));
         EML_CUDA(cudaStreamWaitEvent(out, d, 0));
@@ -604,13 +595,13 @@ int eml_gemm_f64_scatter_dev(const double* A, const double* B, double* C, int64_
     if (n_remote < 0 || n_remote > 7 || (n_remote && !c_remote)) EML_BAD_ARG("scatter: 0..7 remote destinations");
     if (lda < K || ldb < N || ldc < N) EML_BAD_ARG("gemm: leading dimension smaller than the row length");
     cudaStream_t st = (cudaStream_t)stream;
-    NoSplitK no_split;  // the rows must carry the same bits as an unsharded launch
-    set_remote_c(c_remote, n_remote);
-    int rc = contract_dev<double>(ctx, A, B, C, 1, M, N, K, Strides3{0, lda, 1}, Strides3{0, ldb, 1},
-                                  Strides3{0, ldc, 1}, accumulate != 0, false, st);
-    bool pending = remote_c_pending();
-    clear_remote_c();
-    EML_TRY(rc);
+    GemmOptions opt;
+    opt.no_split_k = true;  // the rows must carry the same bits as an unsharded launch
+    opt.remote_c = c_remote;
+    opt.n_remote = n_remote;
+    EML_TRY(contract_dev<double>(ctx, A, B, C, 1, M, N, K, Strides3{0, lda, 1}, Strides3{0, ldb, 1},
+                                 Strides3{0, ldc, 1}, accumulate != 0, false, st, &opt));
+    const bool pending = n_remote > 0 && !opt.remote_done;
     if (pending)  // a kernel without the fused epilogue ran (unaligned / tiny shape): copy the rows instead
         for (int r = 0; r < n_remote; r++)
             EML_CUDA(cudaMemcpy2DAsync(c_remote[r], ldc * sizeof(double), C, ldc * sizeof(double), N * sizeof(double),

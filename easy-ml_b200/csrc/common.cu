@@ -41,22 +41,6 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 int64_t launches() { return g_launches.load(std::memory_order_relaxed); }
 void set_last_kernel(const char* name) { t_kernel = name; }
-
-namespace {
-thread_local bool t_upper_requested = false, t_upper_done = false;
-}
-void request_upper_only() { t_upper_requested = true; }
-bool take_upper_only_request() {
-    const bool r = t_upper_requested;
-    t_upper_requested = false;
-    return r;
-}
-void mark_upper_only_done() { t_upper_done = true; }
-bool take_upper_only_done() {
-    const bool r = t_upper_done;
-    t_upper_done = false;
-    return r;
-}
 const char* last_kernel() { return t_kernel; }
 
 namespace {

@@ -121,12 +121,34 @@ struct Strides3 {
     int64_t b, r, c;  // batch, row, column strides in elements
 };
 
+// Per-call options of the contraction dispatcher and what the kernel it chose reports back.
+struct GemmOptions {
+    // ---- in ----
+    // Split/pack cache of the f32 tensor-core GEMM: an operand whose contents never change (a constant record
+    // container: the NN's inputs) is identified by a non-zero id; its packed TF32 planes are kept and reused by later
+    // calls with the same id, shape and strides.  pack_cache_drop forgets an id when its buffer dies.
+    uint64_t a_id = 0, b_id = 0;
+    // The result's bits must not depend on how the caller partitioned the problem (row panels of the pipelined host
+    // GEMM, slabs of the sharded GEMM): no split-K reformulation.
+    bool no_split_k = false;
+    // Fused all-gather: up to 7 peer-mapped copies of C; the f64 TMA kernel stores every finished tile to them too.
+    double* const* remote_c = nullptr;
+    int n_remote = 0;
+    // Set by contract_dev itself for C = G * G^T (A and B the same buffer read through mirrored strides): compute the
+    // tiles on and above the diagonal only (contract_dev mirrors the upper triangle afterwards).
+    bool upper_only = false;
+    // ---- out ----
+    bool remote_done = false;  // the kernel that ran stored the tiles to the peers
+    bool upper_done = false;   // the kernel that ran computed the upper triangle only
+};
+
 // ---- kernels (one translation unit each) ----
 // general strided batched contraction C[b,m,n] (+)= sum_k A[b,m,k] B[b,k,n]; dispatches between the
 // tensor-core kernels and the SIMT kernel.  exact = reference operation order, bit-exact.
 template <class T>
 int contract_dev(DeviceCtx* ctx, const T* A, const T* B, T* C, int64_t batch, int64_t M, int64_t N, int64_t K,
-                 Strides3 sA, Strides3 sB, Strides3 sC, bool accumulate, bool exact, cudaStream_t stream);
+                 Strides3 sA, Strides3 sB, Strides3 sC, bool accumulate, bool exact, cudaStream_t stream,
+                 GemmOptions* opt = nullptr);
 
 template <class T>
 int launch_gemm_simt(const T* A, const T* B, T* C, int64_t batch, int64_t M, int64_t N, int64_t K, Strides3 sA,
@@ -146,44 +168,25 @@ int launch_gemm_skinny_tn(DeviceCtx* ctx, const T* A, const T* B, T* C, int64_t 
 // supports (caller falls through to another GPU kernel).
 int launch_gemm_dmma_f64(DeviceCtx* ctx, const double* A, const double* B, double* C, int64_t batch, int64_t M,
                          int64_t N, int64_t K, Strides3 sA, Strides3 sB, Strides3 sC, bool accumulate,
-                         cudaStream_t stream, bool* handled);
+                         cudaStream_t stream, bool* handled, GemmOptions* opt);
 
 // measured FP64 tensor-pipe (DMMA) peak of the current device, TFLOP/s (register-resident chains)
 int measure_dmma_peak(DeviceCtx* ctx, double* tflops);
 
-// Fused all-gather: register up to 7 peer-mapped copies of C for the NEXT f64 GEMM launch on this thread; the
-// TMA DMMA kernel stores every finished tile to them too.  remote_c_pending() stays true when the dispatch
-// took a kernel without that epilogue (the caller then copies the rows itself).
-void set_remote_c(double* const* ptrs, int n);
-bool remote_c_pending();
-void clear_remote_c();
-
-// Symmetric products (C = G * G^T: the covariance's Gram matrix).  contract_dev recognises them from its arguments
-// (A and B are the same buffer read through mirrored strides) and asks the NEXT tensor-core launch on this thread to
-// compute only the tiles on and above the diagonal; a kernel that did so says so, and contract_dev then mirrors the
-// upper triangle into the lower one (which also makes the result exactly symmetric, as the reference's is).
-void request_upper_only();
-bool take_upper_only_request();  // reads and clears
-void mark_upper_only_done();
-bool take_upper_only_done();     // reads and clears
+// C[j][i] = C[i][j] for i < j (after a GEMM that computed the tiles on and above the diagonal only; it also makes the
+// result exactly symmetric, as the reference's element-by-element covariance is)
 template <class T>
 int launch_mirror_upper(T* C, int64_t n, int64_t ldc, cudaStream_t stream);  // C[j][i] = C[i][j] for i < j
 
-// Split/pack cache of the f32 tensor-core GEMM.  An operand whose contents never change (a constant record
-// container: the NN's inputs) is identified by a non-zero id; its packed TF32 planes are then kept and reused by
-// later calls with the same id, shape and strides (the NN step packs X twice per step otherwise).  The ids are
-// thread-local hints consumed by the NEXT contract_dev call on this thread; pack_cache_drop forgets an id when its
-// buffer dies.
+// Split/pack cache of the f32 tensor-core GEMM (see GemmOptions::a_id / b_id)
 uint64_t new_buffer_identity();
-void set_pack_identity(uint64_t a_id, uint64_t b_id);
-void take_pack_identity(uint64_t* a_id, uint64_t* b_id);  // reads and clears
 void pack_cache_drop(uint64_t id);
 void pack_cache_release_all();
 
 // f32 3xTF32 on tcgen05 + TMEM, operands staged by TMA (pack kernel splits into big/small parts).
 int launch_gemm_tf32x3_f32(DeviceCtx* ctx, const float* A, const float* B, float* C, int64_t batch, int64_t M,
                            int64_t N, int64_t K, Strides3 sA, Strides3 sB, Strides3 sC, bool accumulate,
-                           cudaStream_t stream, bool* handled);
+                           cudaStream_t stream, bool* handled, GemmOptions* opt);
 
 // C[b][m][n] (+)= sum over splits (ascending) of ws[s][b][m][n]: the fixed-order reduction behind every
 // split-K path (deterministic: no atomics).  ws is dense; C is strided.

@@ -249,7 +249,6 @@ struct Remote {
     double* p[7];
     int n;
 };
-thread_local Remote t_remote = {{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}, 0};
 
 // 8 consumer warps (two warpgroups) + one producer warpgroup (one lane of it works).  The register file is
 // re-split with setmaxnreg: a 384-thread CTA compiles to <= 168 registers per thread, the consumers need
@@ -451,7 +450,7 @@ int operand_map(CUtensorMap* map, const double* base, bool kin, int64_t mn, int6
 template <bool A_KIN, bool B_KIN>
 int launch(const double* A, const double* B, double* C, int64_t batch, int64_t M, int64_t N, int64_t K, int64_t lda,
            int64_t ldb, int64_t ldc, int64_t stA, int64_t stB, int64_t stC, bool accumulate, cudaStream_t stream,
-           bool upper_only) {
+           bool upper_only, GemmOptions* opt) {
     CUtensorMap mapA, mapB;
     EML_TRY(operand_map(&mapA, A, A_KIN, M, K, lda, batch, stA));
     EML_TRY(operand_map(&mapB, B, B_KIN, N, K, ldb, batch, stB));
@@ -468,10 +467,14 @@ int launch(const double* A, const double* B, double* C, int64_t batch, int64_t M
     if (upper_only) {  // the kernel reads tiles_n == 0 as "tiles on and above the diagonal only"
         grid.x = (unsigned)(tiles_m * (tiles_m + 1) / 2);
         tiles_n = 0;
-        mark_upper_only_done();
+        opt->upper_done = true;
     }
-    const Remote remote = t_remote;
-    t_remote.n = 0;  // consumed: the caller checks remote_c_pending() to see whether a kernel took them
+    Remote remote{};
+    if (opt && opt->n_remote > 0) {  // fused all-gather: tell the caller this kernel delivers the tiles itself
+        remote.n = opt->n_remote < 7 ? opt->n_remote : 7;
+        for (int i = 0; i < remote.n; i++) remote.p[i] = opt->remote_c[i];
+        opt->remote_done = true;
+    }
     launch_k(kern, dim3(grid), dim3(TTHREADS), T_SMEM_BYTES, stream, mapA, mapB, C, M, N, K, ldc, stC, (int)tiles_m, (int)tiles_n,
                                                    accumulate ? 1 : 0, remote);
     count_launch();
@@ -528,16 +531,9 @@ int measure_dmma_peak(DeviceCtx* ctx, double* tflops) {
     return check_launch("dmma_peak");
 }
 
-void set_remote_c(double* const* ptrs, int n) {
-    tma::t_remote.n = n;
-    for (int i = 0; i < n && i < 7; i++) tma::t_remote.p[i] = ptrs[i];
-}
-bool remote_c_pending() { return tma::t_remote.n != 0; }
-void clear_remote_c() { tma::t_remote.n = 0; }
-
 int launch_gemm_dmma_f64(DeviceCtx*, const double* A, const double* B, double* C, int64_t batch, int64_t M,
                          int64_t N, int64_t K, Strides3 sA, Strides3 sB, Strides3 sC, bool accumulate,
-                         cudaStream_t stream, bool* handled) {
+                         cudaStream_t stream, bool* handled, GemmOptions* opt) {
     *handled = false;
     if (batch == 0 || M == 0 || N == 0) {
         *handled = true;
@@ -561,15 +557,15 @@ int launch_gemm_dmma_f64(DeviceCtx*, const double* A, const double* B, double* C
     const bool force_cpasync = forced && std::string(forced) == "cpasync";
     bool tma_ok = vec && !force_cpasync && al16(C) && ((A_KIN ? K : M) % 4 == 0) && ((B_KIN ? K : N) % 4 == 0);
     // C = G * G^T requested by contract_dev: the TMA kernel computes the tiles on and above the diagonal only
-    const bool upper = take_upper_only_request() && tma_ok && M == N && !accumulate && !remote_c_pending();
+    const bool upper = opt && opt->upper_only && tma_ok && M == N && !accumulate && opt->n_remote == 0;
     if (tma_ok) {
         if (A_KIN && !B_KIN)
-            return tma::launch<true, false>(A, B, C, batch, M, N, K, lda, ldb, ldc, sA.b, sB.b, sC.b, accumulate, stream, upper);
+            return tma::launch<true, false>(A, B, C, batch, M, N, K, lda, ldb, ldc, sA.b, sB.b, sC.b, accumulate, stream, upper, opt);
         if (A_KIN && B_KIN)
-            return tma::launch<true, true>(A, B, C, batch, M, N, K, lda, ldb, ldc, sA.b, sB.b, sC.b, accumulate, stream, upper);
+            return tma::launch<true, true>(A, B, C, batch, M, N, K, lda, ldb, ldc, sA.b, sB.b, sC.b, accumulate, stream, upper, opt);
         if (!A_KIN && !B_KIN)
-            return tma::launch<false, false>(A, B, C, batch, M, N, K, lda, ldb, ldc, sA.b, sB.b, sC.b, accumulate, stream, upper);
-        return tma::launch<false, true>(A, B, C, batch, M, N, K, lda, ldb, ldc, sA.b, sB.b, sC.b, accumulate, stream, upper);
+            return tma::launch<false, false>(A, B, C, batch, M, N, K, lda, ldb, ldc, sA.b, sB.b, sC.b, accumulate, stream, upper, opt);
+        return tma::launch<false, true>(A, B, C, batch, M, N, K, lda, ldb, ldc, sA.b, sB.b, sC.b, accumulate, stream, upper, opt);
     }
 #define EML_D(AK, BKK)                                                                                          \
     return vec ? launch_variant<AK, BKK, 2>(A, B, C, batch, M, N, K, lda, ldb, ldc, sA.b, sB.b, sC.b, accumulate, \

@@ -651,7 +651,6 @@ int launch_tile(const Maps& maps, float* C, int64_t batch, int64_t M, int64_t N,
 // split/pack cache for immutable operands (see common.h)
 // ------------------------------------------------------------------------------------------------
 namespace {
-thread_local uint64_t t_pack_id[2] = {0, 0};
 std::atomic<uint64_t> g_next_identity{1};
 
 struct PackKey {
@@ -724,15 +723,6 @@ int packed_operand(uint64_t id, const float* src, int64_t batch, int64_t MN, int
 }  // namespace
 
 uint64_t new_buffer_identity() { return g_next_identity.fetch_add(1); }
-void set_pack_identity(uint64_t a_id, uint64_t b_id) {
-    t_pack_id[0] = a_id;
-    t_pack_id[1] = b_id;
-}
-void take_pack_identity(uint64_t* a_id, uint64_t* b_id) {
-    *a_id = t_pack_id[0];
-    *b_id = t_pack_id[1];
-    t_pack_id[0] = t_pack_id[1] = 0;
-}
 void pack_cache_drop(uint64_t id) {
     if (!id) return;
     std::lock_guard<std::mutex> lock(g_pack_mu);
@@ -756,7 +746,7 @@ void pack_cache_release_all() {
 
 int launch_gemm_tf32x3_f32(DeviceCtx* ctx, const float* A, const float* B, float* C, int64_t batch, int64_t M,
                            int64_t N, int64_t K, Strides3 sA, Strides3 sB, Strides3 sC, bool accumulate,
-                           cudaStream_t stream, bool* handled) {
+                           cudaStream_t stream, bool* handled, GemmOptions* opt) {
     *handled = false;
     if (batch == 0 || M == 0 || N == 0) {
         *handled = true;
@@ -774,7 +764,7 @@ int launch_gemm_tf32x3_f32(DeviceCtx* ctx, const float* A, const float* B, float
     // CTA-pair persistent kernel for outputs wider and taller than one 128-row tile
     const bool use_pair = M > 128 && N > 128 && !(forced && std::string(forced) == "1cta");
     // C = G * G^T (requested by contract_dev): tiles on and above the diagonal only, and one packed copy of G
-    const bool upper_only = take_upper_only_request() && use_pair && M == N && !accumulate;
+    const bool upper_only = opt && opt->upper_only && use_pair && M == N && !accumulate;
     int BN, splits = 1;
     int64_t Mp, Np;
     if (use_pair) {
@@ -807,8 +797,7 @@ int launch_gemm_tf32x3_f32(DeviceCtx* ctx, const float* A, const float* B, float
         Np = round_up(N, BN);
     }
 
-    uint64_t a_id = 0, b_id = 0;
-    take_pack_identity(&a_id, &b_id);
+    const uint64_t a_id = opt ? opt->a_id : 0, b_id = opt ? opt->b_id : 0;
     // Small outputs: the pack pass moves 12 (M + N) K bytes at HBM speed while the GEMM does 2 M N K flops, so its
     // share grows as M N / (M + N) shrinks (a third of the time for batched 1024^3).  There the variant that splits
     // inside the kernel wins although its main loop is slower (shared-memory-bandwidth bound, measured 240 vs
@@ -852,7 +841,7 @@ int launch_gemm_tf32x3_f32(DeviceCtx* ctx, const float* A, const float* B, float
     set_last_kernel("tf32x3_tcgen05");
     if (use_pair) {
         EML_TRY(pair::launch(maps, C, batch, M, N, sC.r, sC.b, kblocks, splits, sms, accumulate, ws, stream, upper_only));
-        if (upper_only) mark_upper_only_done();
+        if (upper_only) opt->upper_done = true;
         return EML_OK;
     }
     if (BN == 256) return launch_tile<256>(maps, C, batch, M, N, sC.r, sC.b, kblocks, splits, accumulate, ws, stream);

@@ -231,9 +231,11 @@ int tape_matmul(eml_tape* t, eml_val ha, eml_val hb, eml_val* out) {
     c.rows = M;
     c.cols = N;
     EML_TRY(new_buf(sizeof(T) * M * N, t->stream, &c.numbers));
-    set_pack_identity(a->numbers->identity, b->numbers->identity);
+    GemmOptions ids;  // constant operands keep their packed planes across steps
+    ids.a_id = a->numbers->identity;
+    ids.b_id = b->numbers->identity;
     EML_TRY(contract_dev<T>(t->ctx, (const T*)a->numbers->p, (const T*)b->numbers->p, (T*)c.numbers->p, 1, M, N, K,
-                            Strides3{0, K, 1}, Strides3{0, N, 1}, Strides3{0, N, 1}, false, false, t->stream));
+                            Strides3{0, K, 1}, Strides3{0, N, 1}, Strides3{0, N, 1}, false, false, t->stream, &ids));
     // history = lhs's else rhs's (reference container_operations.rs:1357-1361); with a history every
     // product is recorded with BOTH operands as parents (:1291-1296), whatever their own history
     c.tracked = a->tracked || b->tracked;
@@ -477,9 +479,10 @@ int tape_sweep(eml_tape* t, eml_val hv, int64_t row, int64_t col, eml_derivs** o
             const T* A = (const T*)nd.a->p;
             const T* B = (const T*)nd.b->p;
             if (nd.p0 >= 0) {
-                set_pack_identity(0, nd.b->identity);
+                GemmOptions ids;
+                ids.b_id = nd.b->identity;
                 EML_TRY(contract_dev<T>(t->ctx, g, B, (T*)d->grads[nd.p0]->p, 1, M, K, N, Strides3{0, N, 1},
-                                        Strides3{0, 1, N}, Strides3{0, K, 1}, true, false, st));
+                                        Strides3{0, 1, N}, Strides3{0, K, 1}, true, false, st, &ids));
             } else {
                 // every element of A carries Index 0: derivatives[0] += sum_ik (G B^T)[i,k]
                 //   = sum_j colsum(G)[j] * colsum(B)[j]
@@ -492,9 +495,10 @@ int tape_sweep(eml_tape* t, eml_val hv, int64_t row, int64_t col, eml_derivs** o
                 slot0_used = true;
             }
             if (nd.p1 >= 0) {
-                set_pack_identity(nd.a->identity, 0);
+                GemmOptions ids;
+                ids.a_id = nd.a->identity;
                 EML_TRY(contract_dev<T>(t->ctx, A, g, (T*)d->grads[nd.p1]->p, 1, K, N, M, Strides3{0, 1, K},
-                                        Strides3{0, N, 1}, Strides3{0, N, 1}, true, false, st));
+                                        Strides3{0, N, 1}, Strides3{0, N, 1}, true, false, st, &ids));
             } else {
                 // derivatives[0] += sum_kj (A^T G)[k,j] = sum_i rowsum(A)[i] * rowsum(G)[i]
                 TempBuf ra, rg;
