@@ -882,3 +882,42 @@ def test_sweep_first_contribution_overwrites_like_zero_plus_x(orc, dtype):
             want = np.asarray(tape.derivatives(otarget[1][i, j]), dtype)
             assert np.array_equal(got, want), (i, j)
             assert np.array_equal(np.signbit(got), np.signbit(want)), "a -0 where the reference holds +0"
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_batched_host_contraction_pipelines_over_batch_chunks(dtype):
+    """eml_contract_* from HOST buffers with many independent batches cuts the batch range into chunks whose upload,
+    product and download overlap.  f64: same bits as the device-resident call on the same numbers (f32: the
+    tensor-core kernel's deterministic split-K choice depends on how many tiles a launch holds, so a chunked and an
+    unchunked call may round differently -- both within the bound); ragged last chunk (21 batches -> chunks of 3),
+    padded batch / row strides, pageable (numpy) memory; elements of C's buffer that belong to no batch (the
+    padding between batches) stay untouched."""
+    torch = pytest.importorskip("torch")
+    bt, m, k, n = 21, 384, 520, 640
+    r = rng(61)
+    lda, ldb = k + 8, n + 4                       # padded rows
+    sa_b, sb_b, sc_b = m * lda + 64, k * ldb + 32, m * n + 128   # padded batches (C rows dense: m * n per batch)
+    a = uniform(r, (bt * sa_b,), dtype)
+    b = uniform(r, (bt * sb_b,), dtype)
+    c = np.full(bt * sc_b, -7.0, dtype)
+    sfx = "f32" if dtype == np.float32 else "f64"
+    s3 = lambda *v: (C.c_int64 * 3)(*v)
+    check(getattr(lib, f"eml_contract_{sfx}")(ptr(a), ptr(b), ptr(c), bt, m, n, k, s3(sa_b, lda, 1), s3(sb_b, ldb, 1),
+                                             s3(sc_b, n, 1)))
+    ta, tb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    tc = torch.full((bt * sc_b,), -7.0, device="cuda", dtype=ta.dtype)
+    vp = lambda t: C.c_void_p(t.data_ptr())
+    check(getattr(lib, f"eml_contract_{sfx}_dev")(vp(ta), vp(tb), vp(tc), bt, m, n, k, s3(sa_b, lda, 1), s3(sb_b, ldb, 1),
+                                                 s3(sc_b, n, 1), 0, None))
+    torch.cuda.synchronize()
+    if dtype == np.float64:
+        assert np.array_equal(c, tc.cpu().numpy())
+    else:
+        assert np.allclose(c, tc.cpu().numpy(), rtol=0, atol=1e-4)
+    cv = c.reshape(bt, sc_b)
+    assert np.all(cv[:, m * n:] == -7.0)          # the gaps between batches were not written
+    for i in (0, 5, 20):
+        av = a[i * sa_b:i * sa_b + m * lda].reshape(m, lda)[:, :k].astype(np.float64)
+        bv = b[i * sb_b:i * sb_b + k * ldb].reshape(k, ldb)[:, :n].astype(np.float64)
+        bound = TOL[np.dtype(dtype)] * (np.abs(av) @ np.abs(bv))
+        assert np.all(np.abs(cv[i, :m * n].reshape(m, n).astype(np.float64) - av @ bv) <= bound)
