@@ -435,9 +435,14 @@ int launch_gemm_tf32x3_fused(DeviceCtx* ctx, const float* A, const float* B, flo
     const int64_t lda = A_KIN ? sA.r : sA.c, ldb = B_KIN ? sB.c : sB.r;
     if (!al16(A) || !al16(B) || (lda & 3) || (ldb & 3) || (batch > 1 && ((sA.b & 3) || (sB.b & 3)))) return EML_OK;
     if (lda < 1 || ldb < 1) return EML_OK;
+    // a broadcast operand (batch stride 0) or overlapping batches cannot be described to TMA: the pack pass can
+    if (batch > 1 && (sA.b < (A_KIN ? (M - 1) * lda + K : (K - 1) * lda + M) ||
+                      sB.b < (B_KIN ? (N - 1) * ldb + K : (K - 1) * ldb + N)))
+        return EML_OK;
     fz::Maps maps;
-    EML_TRY(fz::raw_map(&maps.a, A, A_KIN, M, K, lda, batch, sA.b));
-    EML_TRY(fz::raw_map(&maps.b, B, B_KIN, N, K, ldb, batch, sB.b));
+    // (a descriptor the driver refuses -- extents or strides outside its limits -- also means "not this kernel")
+    if (fz::raw_map(&maps.a, A, A_KIN, M, K, lda, batch, sA.b) != EML_OK) return EML_OK;
+    if (fz::raw_map(&maps.b, B, B_KIN, N, K, ldb, batch, sB.b) != EML_OK) return EML_OK;
     const int kblocks = (int)((K + fz::BK - 1) / fz::BK);
     TempBuf wsbuf;
     float* ws = nullptr;

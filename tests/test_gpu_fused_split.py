@@ -131,3 +131,32 @@ def test_dispatcher_picks_in_kernel_split_for_small_batched_outputs():
     assert launches == 1, f"expected the single fused launch, saw {launches} (pack passes ran)"
     with forced("0"):
         assert torch.equal(c, contract(a, b))
+
+
+def test_broadcast_operand_falls_back_to_the_packed_path():
+    """`batch row k, k col -> batch row col`: B has no batch dimension (batch stride 0).  TMA cannot describe a
+    zero stride, so the in-kernel-split kernel must decline and the packed path (whose pack pass reads any strides)
+    must produce the product -- whatever the dispatcher's cost model preferred."""
+    g = torch.Generator(device="cuda").manual_seed(31)
+    bt, m, k, n = 6, 512, 1024, 512
+    a = torch.randn(bt, m, k, generator=g, device="cuda")
+    w = torch.randn(k, n, generator=g, device="cuda")
+    for mode in (None, "1"):
+        if mode is None:
+            os.environ.pop("EML_SGEMM_FUSED", None)
+        else:
+            os.environ["EML_SGEMM_FUSED"] = mode
+        c = torch.empty(bt, m, n, device="cuda")
+        check(lib.eml_contract_f32_dev(vp(a), vp(w), vp(c), bt, m, n, k, s3(*a.stride()), s3(0, n, 1), s3(*c.stride()),
+                                       0, None))
+        torch.cuda.synchronize()
+        exact = a.double() @ w.double()
+        bound = TOL * (a.double().abs() @ w.double().abs())
+        assert bool(((c.double() - exact).abs() <= bound).all())
+    os.environ.pop("EML_SGEMM_FUSED", None)
+    # the named-dimension front end reaches the same case
+    x = eml.Tensor([("batch", bt), ("row", m), ("k", k)], a.cpu().numpy())
+    y = eml.Tensor([("k", k), ("col", n)], w.cpu().numpy())
+    out = eml.Einsum.with_2(x, y).to(["batch", "row", "col"])
+    assert out.shape() == [("batch", bt), ("row", m), ("col", n)]
+    assert np.allclose(out.data, exact.cpu().numpy(), rtol=0, atol=float(bound.max()))
