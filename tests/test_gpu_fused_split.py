@@ -154,6 +154,14 @@ def test_broadcast_operand_falls_back_to_the_packed_path():
         bound = TOL * (a.double().abs() @ w.double().abs())
         assert bool(((c.double() - exact).abs() <= bound).all())
     os.environ.pop("EML_SGEMM_FUSED", None)
+    # f64: the TMA kernel declines the zero stride too (the cp.async kernel takes it)
+    c64 = torch.empty(bt, m, n, device="cuda", dtype=torch.float64)
+    a64, w64 = a.double(), w.double()
+    check(lib.eml_contract_f64_dev(vp(a64), vp(w64), vp(c64), bt, m, n, k, s3(*a64.stride()), s3(0, n, 1),
+                                   s3(*c64.stride()), 0, None))
+    torch.cuda.synchronize()
+    assert eml.last_kernel() == "dmma_f64"
+    assert bool(((c64 - exact).abs() <= 1e-12 * (a64.abs() @ w64.abs())).all())
     # the named-dimension front end reaches the same case
     x = eml.Tensor([("batch", bt), ("row", m), ("k", k)], a.cpu().numpy())
     y = eml.Tensor([("k", k), ("col", n)], w.cpu().numpy())
