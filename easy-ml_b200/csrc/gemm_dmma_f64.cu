@@ -558,6 +558,8 @@ int launch_gemm_dmma_f64(DeviceCtx*, const double* A, const double* B, double* C
     bool tma_ok = vec && !force_cpasync && al16(C) && ((A_KIN ? K : M) % 4 == 0) && ((B_KIN ? K : N) % 4 == 0);
     // a broadcast operand (batch stride 0) cannot be described to TMA; the cp.async kernel just adds the stride
     if (batch > 1 && (sA.b <= 0 || sB.b <= 0)) tma_ok = false;
+    // likewise rows that overlap (leading dimension shorter than the row: a broadcast along m / n / k)
+    if (lda < (A_KIN ? K : M) || ldb < (B_KIN ? K : N)) tma_ok = false;
     // C = G * G^T requested by contract_dev: the TMA kernel computes the tiles on and above the diagonal only
     const bool upper = opt && opt->upper_only && tma_ok && M == N && !accumulate && opt->n_remote == 0;
     if (tma_ok) {

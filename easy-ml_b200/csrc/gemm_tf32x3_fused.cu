@@ -434,7 +434,7 @@ int launch_gemm_tf32x3_fused(DeviceCtx* ctx, const float* A, const float* B, flo
     const bool A_KIN = a_kin, B_KIN = !b_nin;
     const int64_t lda = A_KIN ? sA.r : sA.c, ldb = B_KIN ? sB.c : sB.r;
     if (!al16(A) || !al16(B) || (lda & 3) || (ldb & 3) || (batch > 1 && ((sA.b & 3) || (sB.b & 3)))) return EML_OK;
-    if (lda < 1 || ldb < 1) return EML_OK;
+    if (lda < (A_KIN ? K : M) || ldb < (B_KIN ? K : N)) return EML_OK;  // overlapping rows (a broadcast): pack path
     // a broadcast operand (batch stride 0) or overlapping batches cannot be described to TMA: the pack pass can
     if (batch > 1 && (sA.b < (A_KIN ? (M - 1) * lda + K : (K - 1) * lda + M) ||
                       sB.b < (B_KIN ? (N - 1) * ldb + K : (K - 1) * ldb + N)))

@@ -134,3 +134,29 @@ def test_host_gemm_fuzz(orc):
             bound = tol * (np.abs(av).astype(np.float64) @ np.abs(bv).astype(np.float64)) + 1e-300
             assert np.all(np.abs(c[:, :n].astype(np.float64) - want) <= bound), (dtype, m, n, k, la, lb, lc)
             assert np.all(c[:, n:] == 9.0)
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_broadcast_strides_reach_a_kernel_that_can_take_them(dtype):
+    """Zero strides (an operand broadcast along the batch, its rows or its columns) are legal views for the C ABI
+    but not for TMA descriptors: every such case must be routed to a kernel that reads plain strides."""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    bt, m, n, k = 3, 256, 320, 288
+    tol = 1e-12 if dtype == torch.float64 else 1e-5
+    f = lib.eml_contract_f64_dev if dtype == torch.float64 else lib.eml_contract_f32_dev
+    a = torch.rand((bt, m, k), generator=g, device="cuda", dtype=dtype) * 2 - 1
+    b = torch.rand((bt, k, n), generator=g, device="cuda", dtype=dtype) * 2 - 1
+    cases = {
+        "A shared by every batch": ((0, k, 1), (k * n, n, 1), a[0].expand(bt, m, k), b),
+        "B shared by every batch": ((m * k, k, 1), (0, n, 1), a, b[0].expand(bt, k, n)),
+        "every row of A the same": ((m * k, 0, 1), (k * n, n, 1), a[:, :1].expand(bt, m, k), b),
+        "every column of B the same": ((m * k, k, 1), (k * n, n, 0), a, b[:, :, :1].expand(bt, k, n)),
+        "every row of B the same": ((m * k, k, 1), (k * n, 0, 1), a, b[:, :1].expand(bt, k, n)),
+    }
+    for name, (sa, sb, av, bv) in cases.items():
+        c = torch.empty((bt, m, n), device="cuda", dtype=dtype)
+        check(f(vp(a), vp(b), vp(c), bt, m, n, k, s3(*sa), s3(*sb), s3(m * n, n, 1), 0, None))
+        torch.cuda.synchronize()
+        exact = av.double() @ bv.double()
+        bound = tol * (av.double().abs() @ bv.double().abs()) + 1e-300
+        assert bool(((c.double() - exact).abs() <= bound).all()), name
