@@ -7,6 +7,7 @@
 #include <cstring>
 #include <functional>
 #include <mutex>
+#include <cstdlib>
 #include <thread>
 
 namespace eml {
@@ -51,8 +52,13 @@ class CopyPool {
 
   private:
     CopyPool() {
+        // the caller's thread copies too; EML_COPY_THREADS overrides the total (1 = no workers)
         unsigned hw = std::thread::hardware_concurrency();
-        int n = hw > 2 ? (int)std::min(7u, hw - 1) : 0;
+        int n = hw > 2 ? (int)std::min(15u, hw - 1) : 0;
+        if (const char* e = getenv("EML_COPY_THREADS")) {
+            const int want = atoi(e);
+            if (want >= 1 && want <= 64) n = want - 1;
+        }
         for (int i = 0; i < n; i++) workers_.emplace_back([this] { loop(); });
         for (auto& t : workers_) t.detach();
     }
