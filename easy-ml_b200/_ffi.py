@@ -61,6 +61,7 @@ SIGNATURES = {
     "eml_download": (cint, [vp, vp, C.c_size_t]),
     "eml_sync": (cint, []),
     "eml_gemm_f64_scatter_dev": (cint, [vp, vp, vp, i64, i64, i64, i64, i64, i64, cint, C.POINTER(vp), cint, vp]),
+    "eml_gemm_f64_sliced_dev": (cint, [vp, vp, vp, i64, i64, i64, i64, i64, i64, cint, C.POINTER(cint), vp]),
     "eml_ipc_export": (cint, [vp, vp]),
     "eml_ipc_open": (cint, [vp, C.POINTER(vp)]),
     "eml_ipc_close": (cint, [vp]),

@@ -811,6 +811,12 @@ int eml_sgd_f64_dev(double* w, const double* d, double lr, int64_t n, void* stre
     EML_STREAM_OR_CTX(st);
     return launch_sgd<double>(w, d, lr, n, st);
 }
+int eml_gemm_f64_sliced_dev(const double* A, const double* B, double* C, int64_t M, int64_t N, int64_t K, int64_t lda,
+                            int64_t ldb, int64_t ldc, int slices, int* path, void* stream) {
+    EML_STREAM_OR_CTX(st);
+    if (!A || !B || !C) EML_BAD_ARG("sliced gemm: null operand");
+    return gemm_f64_sliced_dev(ctx, A, B, C, M, N, K, lda, ldb, ldc, slices, path, st);
+}
 int eml_reorder_f32_dev(const float* in, float* out, int rank, const int64_t* out_lens, const int64_t* in_strides,
                         void* stream) {
     EML_STREAM_OR_CTX(st);

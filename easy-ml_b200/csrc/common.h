@@ -170,6 +170,10 @@ int launch_gemm_dmma_f64(DeviceCtx* ctx, const double* A, const double* B, doubl
                          int64_t N, int64_t K, Strides3 sA, Strides3 sB, Strides3 sC, bool accumulate,
                          cudaStream_t stream, bool* handled, GemmOptions* opt);
 
+// f64 GEMM through error-free int8 slicing (gemm_sliced_f64.cu); *path = 1 sliced, 0 fell back to the DMMA kernel
+int gemm_f64_sliced_dev(DeviceCtx* ctx, const double* A, const double* B, double* C, int64_t M, int64_t N, int64_t K,
+                        int64_t lda, int64_t ldb, int64_t ldc, int slices, int* path, cudaStream_t stream);
+
 // measured FP64 tensor-pipe (DMMA) peak of the current device, TFLOP/s (register-resident chains)
 int measure_dmma_peak(DeviceCtx* ctx, double* tflops);
 
