@@ -170,7 +170,19 @@ int launch_gemm_dmma_f64(DeviceCtx* ctx, const double* A, const double* B, doubl
                          int64_t N, int64_t K, Strides3 sA, Strides3 sB, Strides3 sC, bool accumulate,
                          cudaStream_t stream, bool* handled, GemmOptions* opt);
 
-// f64 GEMM through error-free int8 slicing (gemm_sliced_f64.cu); *path = 1 sliced, 0 fell back to the DMMA kernel
+// f64 GEMM through error-free int8 slicing (gemm_sliced_f64.cu).  An operand is prepared once (exponent scan + slice
+// planes) and can serve several products (the pipelined host GEMM slices B once for all of its row panels).
+struct SlicedSide {
+    TempBuf planes, ints, scales;  // [slices + 1][mn][Kp] int8; exponents (+ the `bad` word); 2^(e + 1) per row / column
+    int64_t mn = 0, K = 0, Kp = 0;
+    int slices = 0;
+};
+bool sliced_shape_ok(int64_t M, int64_t N, int64_t K, int slices);
+int sliced_prepare(const double* X, bool rows_of_a, int64_t mn, int64_t K, int64_t ld, int slices, cudaStream_t stream,
+                   SlicedSide* out);
+int sliced_multiply(DeviceCtx* ctx, const SlicedSide& a, const SlicedSide& b, double* C, int64_t ldc, int* path,
+                    cudaStream_t stream);
+// *path = 1 sliced, 0 fell back to the DMMA kernel
 int gemm_f64_sliced_dev(DeviceCtx* ctx, const double* A, const double* B, double* C, int64_t M, int64_t N, int64_t K,
                         int64_t lda, int64_t ldb, int64_t ldc, int slices, int* path, cudaStream_t stream);
 

@@ -394,64 +394,96 @@ int launch(const Maps& maps, double* C, int64_t M, int64_t N, int64_t K, int64_t
 }  // namespace sl
 }  // namespace
 
+// One operand cut into slice planes: A's rows (k contiguous in the source) or B's columns (n contiguous in the source).
+// `bad` (device int) is raised by the exponent scan for Inf / NaN / extreme exponents.
+int sliced_prepare(const double* X, bool rows_of_a, int64_t mn, int64_t K, int64_t ld, int slices, cudaStream_t stream,
+                   SlicedSide* out) {
+    using namespace sl;
+    out->mn = mn;
+    out->K = K;
+    out->Kp = (K + BKB - 1) / BKB * BKB;
+    out->slices = slices;
+    EML_TRY(out->planes.alloc((size_t)(slices + 1) * mn * out->Kp, stream));
+    EML_TRY(out->ints.alloc(sizeof(int) * (size_t)(mn + 8), stream));
+    EML_TRY(out->scales.alloc(sizeof(double) * (size_t)(mn + 2), stream));
+    int* expo = out->ints.as<int>();
+    int* bad = expo + mn;
+    EML_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), stream));
+    if (rows_of_a) {
+        if (mn > 65535) EML_BAD_ARG("sliced gemm: more than 65535 rows in one call");
+        EML_CUDA(launch_k(row_exponent_kernel, dim3((unsigned)((mn + 7) / 8)), dim3(256), 0, stream, X, mn, K, ld, expo, bad));
+        EML_CUDA(launch_k(scale_kernel, dim3((unsigned)((mn + 255) / 256)), dim3(256), 0, stream, expo, out->scales.as<double>(), mn));
+        EML_CUDA(launch_k(slice_rows_kernel, dim3((unsigned)((out->Kp / 4 + 255) / 256), (unsigned)mn), dim3(256), 0, stream, X,
+                          mn, K, ld, expo, out->planes.as<int8_t>(), out->Kp, slices));
+        count_launch(3);
+    } else {
+        const int64_t rpb = 256;
+        EML_CUDA(launch_k(fill_int_kernel, dim3((unsigned)((mn + 255) / 256)), dim3(256), 0, stream, expo, ZERO_ROW, mn));
+        EML_CUDA(launch_k(col_exponent_kernel, dim3((unsigned)((mn + 255) / 256), (unsigned)((K + rpb - 1) / rpb)), dim3(256), 0,
+                          stream, X, K, mn, ld, rpb, expo, bad));
+        EML_CUDA(launch_k(scale_kernel, dim3((unsigned)((mn + 255) / 256)), dim3(256), 0, stream, expo, out->scales.as<double>(), mn));
+        EML_CUDA(launch_k(slice_cols_kernel, dim3((unsigned)(out->Kp / 128), (unsigned)((mn + 31) / 32)), dim3(256), 0, stream, X,
+                          K, mn, ld, expo, out->planes.as<int8_t>(), out->Kp, slices));
+        count_launch(4);
+    }
+    return check_launch("sliced f64 GEMM (slicing)");
+}
+
+// C = A * B from prepared operands.  *path = 1: the guard proved the contract and the sliced kernel wrote C;
+// *path = 0: nothing was written (the caller runs the DMMA kernel).  Synchronises `stream` once (the guard's verdict).
+int sliced_multiply(DeviceCtx* ctx, const SlicedSide& a, const SlicedSide& b, double* C, int64_t ldc, int* path,
+                    cudaStream_t stream) {
+    using namespace sl;
+    *path = 0;
+    const int64_t M = a.mn, N = b.mn, K = a.K;
+    const int slices = a.slices;
+    Maps maps;
+    EML_TRY(plane_map(&maps.a, a.planes.as<int8_t>(), M, K, a.Kp, slices + 1));
+    EML_TRY(plane_map(&maps.b, b.planes.as<int8_t>(), N, K, b.Kp, slices + 1));
+    const int sms = ctx ? ctx->sm_count : 148;
+    int* a_exp = a.ints.as<int>();
+    int* b_exp = b.ints.as<int>();
+    int* flag = a_exp + M;  // A's `bad` word doubles as the guard's flag; B's is read separately
+    // guard: every sum_k floor(64|x|) floor(64|y|) >= K (s + 2) 2^(12 - 7s) / 0.9e-12
+    const double thr = ceil((double)K * (slices + 2) * ldexp(1.0, 12 - 7 * slices) / 0.9e-12);
+    if (thr >= 2.0e9) return EML_OK;
+    EML_TRY(launch<true>(maps, C, M, N, K, ldc, slices, a.scales.as<double>(), b.scales.as<double>(), a_exp, b_exp, (int)thr,
+                         flag, sms, stream));
+    int host_flags[2] = {0, 0};
+    EML_CUDA(cudaMemcpyAsync(&host_flags[0], flag, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    EML_CUDA(cudaMemcpyAsync(&host_flags[1], b_exp + N, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    EML_CUDA(cudaStreamSynchronize(stream));
+    if (host_flags[0] != 0 || host_flags[1] != 0) return EML_OK;
+    EML_TRY(launch<false>(maps, C, M, N, K, ldc, slices, a.scales.as<double>(), b.scales.as<double>(), a_exp, b_exp, 0, flag,
+                          sms, stream));
+    set_last_kernel("sliced_int8_f64");
+    *path = 1;
+    return EML_OK;
+}
+
+bool sliced_shape_ok(int64_t M, int64_t N, int64_t K, int slices) {
+    // int32 accumulators hold `slices` pair products of K terms of at most 2^12 each
+    return (int64_t)slices * K * 4096 < (int64_t(1) << 31) && M >= 256 && N >= 256 && K >= 256 && M <= 65535;
+}
+
 // C = A * B, row-major f64 on the device.  *path = 1 when the int8-sliced kernel produced C, 0 when the operands did
 // not pass the guard (or the shape is outside the kernel's range) and the DMMA kernel ran instead.
 int gemm_f64_sliced_dev(DeviceCtx* ctx, const double* A, const double* B, double* C, int64_t M, int64_t N, int64_t K,
                         int64_t lda, int64_t ldb, int64_t ldc, int slices, int* path, cudaStream_t stream) {
-    using namespace sl;
     if (path) *path = 0;
     if (slices == 0) slices = 8;
-    if (slices < 6 || slices > MAX_SLICES) EML_BAD_ARG("sliced gemm: 6..%d slices (got %d)", MAX_SLICES, slices);
+    if (slices < 6 || slices > sl::MAX_SLICES) EML_BAD_ARG("sliced gemm: 6..%d slices (got %d)", sl::MAX_SLICES, slices);
     if (M < 1 || N < 1 || K < 1 || lda < K || ldb < N || ldc < N) EML_BAD_ARG("sliced gemm: bad shape");
-    auto fallback = [&]() {
+    int took = 0;
+    if (sliced_shape_ok(M, N, K, slices)) {
+        SlicedSide a, b;
+        EML_TRY(sliced_prepare(A, true, M, K, lda, slices, stream, &a));
+        EML_TRY(sliced_prepare(B, false, N, K, ldb, slices, stream, &b));
+        EML_TRY(sliced_multiply(ctx, a, b, C, ldc, &took, stream));
+    }
+    if (!took)
         return contract_dev<double>(ctx, A, B, C, 1, M, N, K, Strides3{0, lda, 1}, Strides3{0, ldb, 1}, Strides3{0, ldc, 1},
                                     false, false, stream);
-    };
-    // int32 accumulators hold `slices` pair products of K terms of at most 2^12 each
-    if ((int64_t)slices * K * 4096 >= (int64_t(1) << 31) || M < 256 || N < 256 || K < 256 || M > 65535) return fallback();
-    const int64_t Kp = (K + BKB - 1) / BKB * BKB;
-    const int planes = slices + 1;
-    TempBuf a_planes, b_planes, ints, scales;
-    EML_TRY(a_planes.alloc((size_t)planes * M * Kp, stream));
-    EML_TRY(b_planes.alloc((size_t)planes * N * Kp, stream));
-    EML_TRY(ints.alloc(sizeof(int) * (size_t)(M + N + 8), stream));
-    const int64_t Me = (M + 1) & ~int64_t(1);  // keeps the column scales 16-byte aligned
-    EML_TRY(scales.alloc(sizeof(double) * (size_t)(Me + N), stream));
-    int* row_exp = ints.as<int>();
-    int* col_exp = row_exp + M;
-    int* flag = col_exp + N;
-    double* row_scale = scales.as<double>();
-    double* col_scale = row_scale + Me;
-    // exponents
-    EML_CUDA(launch_k(fill_int_kernel, dim3((unsigned)((N + 8 + 255) / 256)), dim3(256), 0, stream, col_exp, ZERO_ROW, N));
-    EML_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), stream));
-    EML_CUDA(launch_k(row_exponent_kernel, dim3((unsigned)((M + 7) / 8)), dim3(256), 0, stream, A, M, K, lda, row_exp, flag));
-    const int64_t rpb = 256;
-    EML_CUDA(launch_k(col_exponent_kernel, dim3((unsigned)((N + 255) / 256), (unsigned)((K + rpb - 1) / rpb)), dim3(256), 0,
-                      stream, B, K, N, ldb, rpb, col_exp, flag));
-    EML_CUDA(launch_k(scale_kernel, dim3((unsigned)((M + 255) / 256)), dim3(256), 0, stream, row_exp, row_scale, M));
-    EML_CUDA(launch_k(scale_kernel, dim3((unsigned)((N + 255) / 256)), dim3(256), 0, stream, col_exp, col_scale, N));
-    // slices
-    EML_CUDA(launch_k(slice_rows_kernel, dim3((unsigned)((Kp / 4 + 255) / 256), (unsigned)M), dim3(256), 0, stream, A, M, K,
-                      lda, row_exp, a_planes.as<int8_t>(), Kp, slices));
-    EML_CUDA(launch_k(slice_cols_kernel, dim3((unsigned)(Kp / 128), (unsigned)((N + 31) / 32)), dim3(256), 0, stream, B, K, N,
-                      ldb, col_exp, b_planes.as<int8_t>(), Kp, slices));
-    count_launch(7);
-    EML_TRY(check_launch("sliced f64 GEMM (slicing)"));
-    Maps maps;
-    EML_TRY(plane_map(&maps.a, a_planes.as<int8_t>(), M, K, Kp, planes));
-    EML_TRY(plane_map(&maps.b, b_planes.as<int8_t>(), N, K, Kp, planes));
-    const int sms = ctx ? ctx->sm_count : 148;
-    // guard: every sum_k floor(64|x|) floor(64|y|) >= K (s + 2) 2^(12 - 7s) / 0.9e-12
-    const double thr = ceil((double)K * (slices + 2) * ldexp(1.0, 12 - 7 * slices) / 0.9e-12);
-    if (thr >= 2.0e9) return fallback();
-    EML_TRY(launch<true>(maps, C, M, N, K, ldc, slices, row_scale, col_scale, row_exp, col_exp, (int)thr, flag, sms, stream));
-    int host_flag = 0;
-    EML_CUDA(cudaMemcpyAsync(&host_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, stream));
-    EML_CUDA(cudaStreamSynchronize(stream));
-    if (host_flag != 0) return fallback();
-    EML_TRY(launch<false>(maps, C, M, N, K, ldc, slices, row_scale, col_scale, row_exp, col_exp, 0, flag, sms, stream));
-    set_last_kernel("sliced_int8_f64");
     if (path) *path = 1;
     return EML_OK;
 }
