@@ -174,6 +174,24 @@ class DeviceMatrix:
                         f"{other.rows()}x{other.columns()}, * is only defined for MxN * NxL")
         return DeviceMatrix(self._a.matmul(other._a))
 
+    def mul_sliced(self, other, slices=8):
+        """The same product as `*` through error-free int8 slices on the INT8 tensor cores (eml_gemm_f64_sliced_dev,
+        f64 only): about twice the speed of the FP64 pipe for large matrices.  A guard proves the path's 1e-12
+        contract for these operands first; when it cannot, the FP64 kernel runs.  Returns (product, used_slices)."""
+        if not isinstance(other, DeviceMatrix):
+            raise TypeError("both operands must be DeviceMatrix")
+        if self._a.dtype != np.float64 or other._a.dtype != np.float64:
+            raise TypeError("mul_sliced is defined for f64 matrices")
+        if self.columns() != other.rows():
+            raise Panic(f"Mismatched Matrices, left is {self.rows()}x{self.columns()}, right is "
+                        f"{other.rows()}x{other.columns()}, * is only defined for MxN * NxL")
+        m, k, n = self.rows(), self.columns(), other.columns()
+        out = _DeviceArray((m, n), np.float64)
+        path = C.c_int(0)
+        check(lib.eml_gemm_f64_sliced_dev(self._a.ptr, other._a.ptr, out.ptr, m, n, k, k, n, n, int(slices),
+                                          C.byref(path), None))
+        return DeviceMatrix(out), bool(path.value)
+
     def transpose(self):
         """Matrix::transpose, src/matrices/mod.rs:1277-1300."""
         return DeviceMatrix(self._a.reorder((1, 0)))

@@ -120,3 +120,17 @@ def test_more_slices_never_hurt_and_the_default_beats_the_fp64_kernel():
     check(lib.eml_gemm_f64_dev(vp(a), vp(b), vp(cd), 1024, 1024, 1024, 1024, 1024, 1024, None))
     torch.cuda.synchronize()
     assert ratios[8] < worst_ratio(cd, a, b, rows)   # 55-bit slices + exact integer sums: tighter than FMA chains
+
+
+def test_device_matrix_front_end():
+    r = np.random.default_rng(12)
+    a, b = r.uniform(-1, 1, (600, 700)), r.uniform(-1, 1, (700, 520))
+    da, db = eml.DeviceMatrix.from_host(eml.Matrix(a)), eml.DeviceMatrix.from_host(eml.Matrix(b))
+    prod, used = da.mul_sliced(db)
+    assert used and prod.size() == (600, 520)
+    exact = a.astype(np.longdouble) @ b.astype(np.longdouble)
+    bound = 1e-12 * (np.abs(a).astype(np.longdouble) @ np.abs(b).astype(np.longdouble))
+    assert np.all(np.abs(prod.to_host().data.astype(np.longdouble) - exact) <= 1e-2 * bound)
+    assert np.allclose(prod.to_host().data, (da * db).to_host().data, rtol=0, atol=1e-12)
+    with pytest.raises(eml.Panic, match="Mismatched Matrices, left is 600x700, right is 600x700"):
+        da.mul_sliced(da)
