@@ -180,9 +180,9 @@ struct SlicedSide {
 bool sliced_shape_ok(int64_t M, int64_t N, int64_t K, int slices);
 int sliced_prepare(const double* X, bool rows_of_a, int64_t mn, int64_t K, int64_t ld, int slices, cudaStream_t stream,
                    SlicedSide* out);
-int sliced_multiply(DeviceCtx* ctx, const SlicedSide& a, const SlicedSide& b, double* C, int64_t ldc, int* path,
-                    cudaStream_t stream);
-// *path = 1 sliced, 0 fell back to the DMMA kernel
+int sliced_multiply(DeviceCtx* ctx, const SlicedSide& a, const SlicedSide& b, double* C, int64_t ldc, int use_slices,
+                    int* path, cudaStream_t stream);
+// *path = number of slices the sliced kernel used, 0 = fell back to the DMMA kernel
 int gemm_f64_sliced_dev(DeviceCtx* ctx, const double* A, const double* B, double* C, int64_t M, int64_t N, int64_t K,
                         int64_t lda, int64_t ldb, int64_t ldc, int slices, int* path, cudaStream_t stream);
 

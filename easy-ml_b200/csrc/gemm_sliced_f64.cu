@@ -200,8 +200,8 @@ struct Maps {
 
 // GUARD = false: for every tile, the diagonals d = s-1 .. 0; per diagonal the pairs (p, d - p) accumulate in one int32
 //                TMEM accumulator; the epilogue adds  acc * R_i S_j 2^(-12 - 7d)  into C (the first diagonal writes).
-// GUARD = true : one product, planes (s, s) = floor(64 |x|), floor(64 |y|); the epilogue compares every sum with
-//                `threshold` and raises *flag when one is smaller (zero rows / columns exempt).
+// GUARD = true : one product, planes (s, s) = floor(64 |x|), floor(64 |y|); the epilogue leaves the smallest sum in
+//                flag[1] (zero rows / columns exempt): the host compares it with the threshold of each slice count.
 template <bool GUARD>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 sliced_kernel(const __grid_constant__ Maps maps, double* __restrict__ C, int64_t M, int64_t N, int64_t ldc, int kblocks,
@@ -316,7 +316,7 @@ sliced_kernel(const __grid_constant__ Maps maps, double* __restrict__ C, int64_t
                 tc_fence_after();
                 const uint32_t t0 = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * PN + half * 128);
                 const double w = ldexp(rs, -12 - 7 * d);  // R_i 2^(-12 - 7d): a power of two, exact
-                bool low = false;
+                int lowest = INT_MAX;
 #pragma unroll 1
                 for (int c = 0; c < 4; c++) {
                     uint32_t v[32];
@@ -328,7 +328,7 @@ sliced_kernel(const __grid_constant__ Maps maps, double* __restrict__ C, int64_t
                         if (!row_zero) {
 #pragma unroll
                             for (int j = 0; j < 32; j++)
-                                if (col0 + j < N && col_exp[col0 + j] != ZERO_ROW && (int)v[j] < threshold) low = true;
+                                if (col0 + j < N && col_exp[col0 + j] != ZERO_ROW) lowest = min(lowest, (int)v[j]);
                         }
                     } else {
                         double* p = C + row * ldc + col0;
@@ -351,7 +351,11 @@ sliced_kernel(const __grid_constant__ Maps maps, double* __restrict__ C, int64_t
                         }
                     }
                 }
-                if (GUARD && low) atomicOr(flag, 2);
+                if (GUARD) {
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) lowest = min(lowest, __shfl_xor_sync(0xffffffffu, lowest, o));
+                    if (lane == 0 && lowest != INT_MAX) atomicMin(flag + 1, lowest);
+                }
                 // (the next diagonal of this tile is read back by the same thread: program order is enough)
                 tc_fence_before();
                 __syncwarp();
@@ -429,35 +433,50 @@ int sliced_prepare(const double* X, bool rows_of_a, int64_t mn, int64_t K, int64
     return check_launch("sliced f64 GEMM (slicing)");
 }
 
-// C = A * B from prepared operands.  *path = 1: the guard proved the contract and the sliced kernel wrote C;
+// C = A * B from prepared operands, using `use_slices` of the prepared slices (0 = as few as the guard can prove,
+// at least 7).  *path = number of slices used when the guard proved the contract and the sliced kernel wrote C;
 // *path = 0: nothing was written (the caller runs the DMMA kernel).  Synchronises `stream` once (the guard's verdict).
-int sliced_multiply(DeviceCtx* ctx, const SlicedSide& a, const SlicedSide& b, double* C, int64_t ldc, int* path,
-                    cudaStream_t stream) {
+int sliced_multiply(DeviceCtx* ctx, const SlicedSide& a, const SlicedSide& b, double* C, int64_t ldc, int use_slices,
+                    int* path, cudaStream_t stream) {
     using namespace sl;
     *path = 0;
     const int64_t M = a.mn, N = b.mn, K = a.K;
-    const int slices = a.slices;
+    const int prepared = a.slices;
     Maps maps;
-    EML_TRY(plane_map(&maps.a, a.planes.as<int8_t>(), M, K, a.Kp, slices + 1));
-    EML_TRY(plane_map(&maps.b, b.planes.as<int8_t>(), N, K, b.Kp, slices + 1));
+    EML_TRY(plane_map(&maps.a, a.planes.as<int8_t>(), M, K, a.Kp, prepared + 1));
+    EML_TRY(plane_map(&maps.b, b.planes.as<int8_t>(), N, K, b.Kp, prepared + 1));
     const int sms = ctx ? ctx->sm_count : 148;
     int* a_exp = a.ints.as<int>();
     int* b_exp = b.ints.as<int>();
-    int* flag = a_exp + M;  // A's `bad` word doubles as the guard's flag; B's is read separately
-    // guard: every sum_k floor(64|x|) floor(64|y|) >= K (s + 2) 2^(12 - 7s) / 0.9e-12
-    const double thr = ceil((double)K * (slices + 2) * ldexp(1.0, 12 - 7 * slices) / 0.9e-12);
-    if (thr >= 2.0e9) return EML_OK;
-    EML_TRY(launch<true>(maps, C, M, N, K, ldc, slices, a.scales.as<double>(), b.scales.as<double>(), a_exp, b_exp, (int)thr,
+    int* flag = a_exp + M;  // [0]: A's `bad` word, [1]: the guard's minimum; B's `bad` word is read separately
+    EML_CUDA(launch_k(fill_int_kernel, dim3(1), dim3(32), 0, stream, flag + 1, INT_MAX, (int64_t)1));
+    // guard: the smallest sum_k floor(64|x|) floor(64|y|) over the elements of C.  The guard kernel reads plane
+    // `prepared` (the floor planes) whatever the slice count that will be used.
+    EML_TRY(launch<true>(maps, C, M, N, K, ldc, prepared, a.scales.as<double>(), b.scales.as<double>(), a_exp, b_exp, 0,
                          flag, sms, stream));
-    int host_flags[2] = {0, 0};
-    EML_CUDA(cudaMemcpyAsync(&host_flags[0], flag, sizeof(int), cudaMemcpyDeviceToHost, stream));
-    EML_CUDA(cudaMemcpyAsync(&host_flags[1], b_exp + N, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    int host_flags[3] = {0, 0, 0};
+    EML_CUDA(cudaMemcpyAsync(&host_flags[0], flag, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    EML_CUDA(cudaMemcpyAsync(&host_flags[2], b_exp + N, sizeof(int), cudaMemcpyDeviceToHost, stream));
     EML_CUDA(cudaStreamSynchronize(stream));
-    if (host_flags[0] != 0 || host_flags[1] != 0) return EML_OK;
-    EML_TRY(launch<false>(maps, C, M, N, K, ldc, slices, a.scales.as<double>(), b.scales.as<double>(), a_exp, b_exp, 0, flag,
-                          sms, stream));
+    if (host_flags[0] != 0 || host_flags[2] != 0) return EML_OK;  // Inf / NaN / extreme exponents
+    // s slices are proven when every sum >= K (s + 2) 2^(12 - 7s) / 0.9e-12   (and the int32 sums cannot overflow)
+    auto proven = [&](int s) {
+        return (double)host_flags[1] >= ceil((double)K * (s + 2) * ldexp(1.0, 12 - 7 * s) / 0.9e-12) &&
+               (int64_t)s * K * 4096 < (int64_t(1) << 31);
+    };
+    int s = 0;
+    if (use_slices > 0) {
+        if (use_slices <= prepared && proven(use_slices)) s = use_slices;
+    } else {
+        for (int c = 7; c <= prepared && !s; c++)
+            if (proven(c)) s = c;
+    }
+    if (!s) return EML_OK;
+    // the digits of an s-slice expansion are the first s digits of the prepared one; plane `prepared` is not touched
+    EML_TRY(launch<false>(maps, C, M, N, K, ldc, s, a.scales.as<double>(), b.scales.as<double>(), a_exp, b_exp, 0, flag, sms,
+                          stream));
     set_last_kernel("sliced_int8_f64");
-    *path = 1;
+    *path = s;
     return EML_OK;
 }
 
@@ -471,20 +490,21 @@ bool sliced_shape_ok(int64_t M, int64_t N, int64_t K, int slices) {
 int gemm_f64_sliced_dev(DeviceCtx* ctx, const double* A, const double* B, double* C, int64_t M, int64_t N, int64_t K,
                         int64_t lda, int64_t ldb, int64_t ldc, int slices, int* path, cudaStream_t stream) {
     if (path) *path = 0;
-    if (slices == 0) slices = 8;
-    if (slices < 6 || slices > sl::MAX_SLICES) EML_BAD_ARG("sliced gemm: 6..%d slices (got %d)", sl::MAX_SLICES, slices);
+    if (slices != 0 && (slices < 6 || slices > sl::MAX_SLICES))
+        EML_BAD_ARG("sliced gemm: 6..%d slices, or 0 for as few as the guard can prove (got %d)", sl::MAX_SLICES, slices);
     if (M < 1 || N < 1 || K < 1 || lda < K || ldb < N || ldc < N) EML_BAD_ARG("sliced gemm: bad shape");
+    const int prepare = slices ? slices : 8;
     int took = 0;
-    if (sliced_shape_ok(M, N, K, slices)) {
+    if (sliced_shape_ok(M, N, K, slices ? slices : 7)) {
         SlicedSide a, b;
-        EML_TRY(sliced_prepare(A, true, M, K, lda, slices, stream, &a));
-        EML_TRY(sliced_prepare(B, false, N, K, ldb, slices, stream, &b));
-        EML_TRY(sliced_multiply(ctx, a, b, C, ldc, &took, stream));
+        EML_TRY(sliced_prepare(A, true, M, K, lda, prepare, stream, &a));
+        EML_TRY(sliced_prepare(B, false, N, K, ldb, prepare, stream, &b));
+        EML_TRY(sliced_multiply(ctx, a, b, C, ldc, slices, &took, stream));
     }
     if (!took)
         return contract_dev<double>(ctx, A, B, C, 1, M, N, K, Strides3{0, lda, 1}, Strides3{0, ldb, 1}, Strides3{0, ldc, 1},
                                     false, false, stream);
-    if (path) *path = 1;
+    if (path) *path = took;
     return EML_OK;
 }
 

@@ -174,10 +174,11 @@ class DeviceMatrix:
                         f"{other.rows()}x{other.columns()}, * is only defined for MxN * NxL")
         return DeviceMatrix(self._a.matmul(other._a))
 
-    def mul_sliced(self, other, slices=8):
+    def mul_sliced(self, other, slices=0):
         """The same product as `*` through error-free int8 slices on the INT8 tensor cores (eml_gemm_f64_sliced_dev,
         f64 only): about twice the speed of the FP64 pipe for large matrices.  A guard proves the path's 1e-12
-        contract for these operands first; when it cannot, the FP64 kernel runs.  Returns (product, used_slices)."""
+        contract for these operands first; when it cannot, the FP64 kernel runs.  `slices` = 0 uses as few slices as the
+        guard can prove (7 or 8).  Returns (product, number of slices used or 0 for the FP64 kernel)."""
         if not isinstance(other, DeviceMatrix):
             raise TypeError("both operands must be DeviceMatrix")
         if self._a.dtype != np.float64 or other._a.dtype != np.float64:
@@ -190,7 +191,7 @@ class DeviceMatrix:
         path = C.c_int(0)
         check(lib.eml_gemm_f64_sliced_dev(self._a.ptr, other._a.ptr, out.ptr, m, n, k, k, n, n, int(slices),
                                           C.byref(path), None))
-        return DeviceMatrix(out), bool(path.value)
+        return DeviceMatrix(out), int(path.value)
 
     def transpose(self):
         """Matrix::transpose, src/matrices/mod.rs:1277-1300."""

@@ -245,12 +245,14 @@ int eml_chain_f64_dev(const double* dout, const double* deriv, double* dparent, 
 int eml_sgd_f32_dev(float* w, const float* d, float lr, int64_t n, void* stream);
 int eml_sgd_f64_dev(double* w, const double* d, double lr, int64_t n, void* stream);
 /* C = A*B (row-major f64, device pointers), the product of matrix_view_multiplication (src/matrices/operations.rs:165-196),
- * computed beyond the FP64 pipe: both operands are cut into `slices` (6..10, 0 = 8) signed 7-bit slices relative to
+ * computed beyond the FP64 pipe: both operands are cut into `slices` (6..10; 0 = as few as the guard can prove, at
+ * least 7, at most 8) signed 7-bit slices relative to
  * their row / column maxima (exact), the slice products run as int8 GEMMs on the INT8 tensor cores with exact int32
  * sums, and the diagonals are recombined in f64.  A guard pass first PROVES, for these operands, that the truncation
  * stays within the path's contract |C - ref| <= 1e-12 sum_k |a_ik b_kj| for every element; when it cannot (wide dynamic
  * range inside a row / column, Inf / NaN, extreme exponents, K too long for int32) the DMMA kernel runs instead.
- * *path (may be NULL): 1 = sliced kernel, 0 = DMMA kernel.  Opt-in: eml_gemm_f64* never take this route. */
+ * *path (may be NULL): the number of slices the sliced kernel used, 0 = DMMA kernel.  Opt-in: eml_gemm_f64* never
+ * take this route. */
 int eml_gemm_f64_sliced_dev(const double* A, const double* B, double* C, int64_t M, int64_t N, int64_t K, int64_t lda,
                             int64_t ldb, int64_t ldc, int slices, int* path, void* stream);
 /* Tensor::reorder / Tensor::transpose (src/tensors/mod.rs:1473-1600, data movement of TensorAccess::iter) and
