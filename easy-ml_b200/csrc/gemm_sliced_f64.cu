@@ -55,6 +55,14 @@ __device__ __forceinline__ void umma_i8_pair(uint32_t tmem_d, uint64_t desc_a, u
         : "memory");
 }
 
+// unbiased exponent from the bit pattern (the library ilogb costs ~20 instructions per element): zero -> ZERO_ROW,
+// subnormals report -1023 (the scan flags |exponent| > 900 anyway), Inf / NaN report 1024
+__device__ __forceinline__ int exponent_of(double v) {
+    const int hi = __double2hiint(v) & 0x7fffffff;
+    if ((hi | __double2loint(v)) == 0) return ZERO_ROW;
+    return (hi >> 20) - 1023;
+}
+
 // ---------------------------------------------------------------- exponents of the rows of A / columns of B
 // out[r] = largest ilogb over the row, ZERO_ROW for an all-zero row; *bad |= 1 for Inf / NaN / |exponent| > 900
 __global__ void __launch_bounds__(256)
@@ -65,11 +73,14 @@ row_exponent_kernel(const double* __restrict__ X, int64_t rows, int64_t cols, in
     const int64_t r = (int64_t)blockIdx.x * 8 + warp;
     if (r >= rows) return;
     int e = ZERO_ROW, flag = 0;
-    for (int64_t c = lane; c < cols; c += 32) {
-        const double v = X[r * ld + c];
-        if (!(fabs(v) <= 1.7e308)) flag = 1;  // Inf or NaN
-        if (v != 0.0) e = max(e, ilogb(v));
+    const double* row = X + r * ld;
+    int64_t c = lane;
+    for (; c + 96 < cols; c += 128) {  // four loads in flight per lane
+        const double v0 = row[c], v1 = row[c + 32], v2 = row[c + 64], v3 = row[c + 96];
+        e = max(max(e, exponent_of(v0)), max(max(exponent_of(v1), exponent_of(v2)), exponent_of(v3)));
     }
+    for (; c < cols; c += 32) e = max(e, exponent_of(row[c]));
+    if (e == 1024) flag = 1;  // Inf or NaN
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         e = max(e, __shfl_xor_sync(0xffffffffu, e, o));
@@ -90,11 +101,13 @@ col_exponent_kernel(const double* __restrict__ X, int64_t rows, int64_t cols, in
     const int64_t r0 = (int64_t)blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
     if (c >= cols) return;
     int e = ZERO_ROW, flag = 0;
-    for (int64_t r = r0; r < r1; r++) {
-        const double v = X[r * ld + c];
-        if (!(fabs(v) <= 1.7e308)) flag = 1;
-        if (v != 0.0) e = max(e, ilogb(v));
+    int64_t r = r0;
+    for (; r + 3 < r1; r += 4) {
+        const double v0 = X[r * ld + c], v1 = X[(r + 1) * ld + c], v2 = X[(r + 2) * ld + c], v3 = X[(r + 3) * ld + c];
+        e = max(max(e, exponent_of(v0)), max(max(exponent_of(v1), exponent_of(v2)), exponent_of(v3)));
     }
+    for (; r < r1; r++) e = max(e, exponent_of(X[r * ld + c]));
+    if (e == 1024) flag = 1;
     if (e != ZERO_ROW) atomicMax(out + c, e);
     if (flag || (e != ZERO_ROW && (e > 900 || e < -900))) atomicOr(bad, 1);
 }
@@ -103,43 +116,47 @@ __global__ void fill_int_kernel(int* p, int v, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
 }
-// scale[r] = 2^(e_r + 1) (1 for a zero row)
-__global__ void scale_kernel(const int* __restrict__ e, double* __restrict__ scale, int64_t n) {
+// scale[r] = 2^(e_r + 1) (1 for a zero row), inv[r] = 2^-(e_r + 1): both exact powers of two
+__global__ void scale_kernel(const int* __restrict__ e, double* __restrict__ scale, double* __restrict__ inv, int64_t n) {
     pdl_prologue();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) scale[i] = e[i] == ZERO_ROW ? 1.0 : ldexp(1.0, e[i] + 1);
+    if (i < n) {
+        const int x = e[i] == ZERO_ROW || e[i] > 1000 || e[i] < -1000 ? -1 : e[i];
+        scale[i] = ldexp(1.0, x + 1);
+        inv[i] = ldexp(1.0, -(x + 1));
+    }
 }
 
 // ---------------------------------------------------------------- slicing
 // digits of x in (-1, 1): x = sum_p d[p] 2^(-6 - 7p) + rho; plane `slices` = floor(64 |x|) (the guard's lower bound)
 __device__ __forceinline__ void digits(double x, int slices, int8_t (&d)[MAX_SLICES], int8_t& guard) {
     double t = x * 64.0;
-    guard = (int8_t)(int)floor(fabs(t));  // 0..63
+    guard = (int8_t)__double2int_rz(fabs(t));  // floor: 0..63
+    constexpr double MAGIC = 6755399441055744.0;  // 1.5 * 2^52: (t + MAGIC) - MAGIC rounds to the nearest integer
 #pragma unroll
     for (int p = 0; p < MAX_SLICES; p++) {
         d[p] = 0;
         if (p < slices) {
-            const double r = rint(t);
-            d[p] = (int8_t)(int)r;
+            const double r = __dsub_rn(__dadd_rn(t, MAGIC), MAGIC);
+            d[p] = (int8_t)__double2int_rz(r);
             t = (t - r) * 128.0;
         }
     }
 }
 // k-contiguous source (A, row-major M x K): planes[p][row][k], row stride Kp bytes.  One thread = 4 consecutive k.
 __global__ void __launch_bounds__(256)
-slice_rows_kernel(const double* __restrict__ X, int64_t rows, int64_t K, int64_t ld, const int* __restrict__ expo,
+slice_rows_kernel(const double* __restrict__ X, int64_t rows, int64_t K, int64_t ld, const double* __restrict__ inv,
                   int8_t* __restrict__ planes, int64_t Kp, int slices) {
     pdl_prologue();
     const int64_t k4 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
     const int64_t r = blockIdx.y;
     if (k4 >= Kp) return;
-    const int e = expo[r];
-    const int sh = e == ZERO_ROW ? 0 : -(e + 1);
+    const double is = inv[r];
     int8_t d[4][MAX_SLICES], g[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         const double v = (k4 + j < K) ? X[r * ld + k4 + j] : 0.0;
-        digits(ldexp(v, sh), slices, d[j], g[j]);
+        digits(v * is, slices, d[j], g[j]);
     }
     const int64_t plane = rows * Kp;
     int8_t* out = planes + r * Kp + k4;
@@ -151,20 +168,19 @@ slice_rows_kernel(const double* __restrict__ X, int64_t rows, int64_t K, int64_t
 // n-contiguous source (B, row-major K x N): planes[p][n][k] -- transposed through shared memory.
 // Block tile: 128 k x 32 n.
 __global__ void __launch_bounds__(256)
-slice_cols_kernel(const double* __restrict__ X, int64_t K, int64_t N, int64_t ld, const int* __restrict__ expo,
+slice_cols_kernel(const double* __restrict__ X, int64_t K, int64_t N, int64_t ld, const double* __restrict__ inv,
                   int8_t* __restrict__ planes, int64_t Kp, int slices) {
     pdl_prologue();
     __shared__ int8_t tile[MAX_SLICES + 1][32][132];  // [plane][n][k], row padded to 132 bytes
     const int64_t k0 = (int64_t)blockIdx.x * 128, n0 = (int64_t)blockIdx.y * 32;
     const int tn = threadIdx.x & 31, tk = threadIdx.x >> 5;  // 32 n x 8 k per pass
     const int64_t n = n0 + tn;
-    const int e = n < N ? expo[n] : ZERO_ROW;
-    const int sh = e == ZERO_ROW ? 0 : -(e + 1);
+    const double is = n < N ? inv[n] : 1.0;
     for (int kk = tk; kk < 128; kk += 8) {
         const int64_t k = k0 + kk;
         const double v = (n < N && k < K) ? X[k * ld + n] : 0.0;
         int8_t d[MAX_SLICES], g;
-        digits(ldexp(v, sh), slices, d, g);
+        digits(v * is, slices, d, g);
 #pragma unroll
         for (int p = 0; p < MAX_SLICES; p++)
             if (p < slices) tile[p][tn][kk] = d[p];
@@ -409,25 +425,27 @@ int sliced_prepare(const double* X, bool rows_of_a, int64_t mn, int64_t K, int64
     out->slices = slices;
     EML_TRY(out->planes.alloc((size_t)(slices + 1) * mn * out->Kp, stream));
     EML_TRY(out->ints.alloc(sizeof(int) * (size_t)(mn + 8), stream));
-    EML_TRY(out->scales.alloc(sizeof(double) * (size_t)(mn + 2), stream));
+    const int64_t mne = (mn + 1) & ~int64_t(1);
+    EML_TRY(out->scales.alloc(sizeof(double) * (size_t)(2 * mne), stream));
+    double* inv = out->scales.as<double>() + mne;
     int* expo = out->ints.as<int>();
     int* bad = expo + mn;
     EML_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), stream));
     if (rows_of_a) {
         if (mn > 65535) EML_BAD_ARG("sliced gemm: more than 65535 rows in one call");
         EML_CUDA(launch_k(row_exponent_kernel, dim3((unsigned)((mn + 7) / 8)), dim3(256), 0, stream, X, mn, K, ld, expo, bad));
-        EML_CUDA(launch_k(scale_kernel, dim3((unsigned)((mn + 255) / 256)), dim3(256), 0, stream, expo, out->scales.as<double>(), mn));
+        EML_CUDA(launch_k(scale_kernel, dim3((unsigned)((mn + 255) / 256)), dim3(256), 0, stream, expo, out->scales.as<double>(), inv, mn));
         EML_CUDA(launch_k(slice_rows_kernel, dim3((unsigned)((out->Kp / 4 + 255) / 256), (unsigned)mn), dim3(256), 0, stream, X,
-                          mn, K, ld, expo, out->planes.as<int8_t>(), out->Kp, slices));
+                          mn, K, ld, inv, out->planes.as<int8_t>(), out->Kp, slices));
         count_launch(3);
     } else {
         const int64_t rpb = 256;
         EML_CUDA(launch_k(fill_int_kernel, dim3((unsigned)((mn + 255) / 256)), dim3(256), 0, stream, expo, ZERO_ROW, mn));
         EML_CUDA(launch_k(col_exponent_kernel, dim3((unsigned)((mn + 255) / 256), (unsigned)((K + rpb - 1) / rpb)), dim3(256), 0,
                           stream, X, K, mn, ld, rpb, expo, bad));
-        EML_CUDA(launch_k(scale_kernel, dim3((unsigned)((mn + 255) / 256)), dim3(256), 0, stream, expo, out->scales.as<double>(), mn));
+        EML_CUDA(launch_k(scale_kernel, dim3((unsigned)((mn + 255) / 256)), dim3(256), 0, stream, expo, out->scales.as<double>(), inv, mn));
         EML_CUDA(launch_k(slice_cols_kernel, dim3((unsigned)(out->Kp / 128), (unsigned)((mn + 31) / 32)), dim3(256), 0, stream, X,
-                          K, mn, ld, expo, out->planes.as<int8_t>(), out->Kp, slices));
+                          K, mn, ld, inv, out->planes.as<int8_t>(), out->Kp, slices));
         count_launch(4);
     }
     return check_launch("sliced f64 GEMM (slicing)");
