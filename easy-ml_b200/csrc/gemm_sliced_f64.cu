@@ -278,7 +278,7 @@ sliced_kernel(const __grid_constant__ Maps maps, double* __restrict__ C, int64_t
                                 // flight share their operand panels through L2 only while they stream the same planes
                                 // (measured: 14.2 -> 12.5 ms at 8192^3; meeting four times per pair gains nothing
                                 // more).  Every CTA of this persistent grid is resident, so the wait cannot deadlock.
-                                unsigned int* ctr = step_counters + (wave * 64 + (GUARD ? 0 : (slices - 1 - d) * 8 + p));
+                                unsigned int* ctr = step_counters + (wave * (MAX_SLICES * MAX_SLICES) + (GUARD ? 0 : (slices - 1 - d) * MAX_SLICES + p));
                                 atomicAdd(ctr, 1u);
                                 unsigned int seen;
                                 do {
@@ -513,7 +513,7 @@ int sliced_multiply(DeviceCtx* ctx, const SlicedSide& a, const SlicedSide& b, do
     if (!getenv("EML_SLICED_NO_LOCKSTEP")) {
         const int64_t tiles = ((M + PM - 1) / PM) * ((N + PN - 1) / PN);
         const int64_t clusters = tiles < sms / 2 ? tiles : sms / 2;
-        const size_t bytes = sizeof(unsigned int) * 64 * (size_t)((tiles + clusters - 1) / clusters);
+        const size_t bytes = sizeof(unsigned int) * MAX_SLICES * MAX_SLICES * (size_t)((tiles + clusters - 1) / clusters);
         EML_TRY(counters.alloc(bytes, stream));
         EML_CUDA(cudaMemsetAsync(counters.p, 0, bytes, stream));
         ctr = counters.as<unsigned int>();
