@@ -393,8 +393,8 @@ def main():
             out["roofline"].update({
                 "kernel": "sliced_int8_f64" if s_used else kernel_name, "slices_used": s_used, "slice_products": pairs_run,
                 "achieved": int8_tops, "peak": 4500.0, "unit": "TOP/s (int8)", "frac": (int8_tops or 0.0) / 4500.0,
-                "peak_source": "nominal dense INT8 tensor peak of B200 (4.5 POP/s); the kernel is power-bound at ~1.24 GHz",
-                "traffic": 58.2e9 if n == 8192 else None, "traffic_source": "profiles/r1_prof_sliced_int8_f64_r1_raw.csv",
+                "peak_source": "nominal dense INT8 tensor peak of B200 (4.5 POP/s); the kernel is power-bound (1.46 GHz under ncu)",
+                "traffic": 21.3e9 if n == 8192 and s_used == 7 else None, "traffic_source": "profiles/r1_prof_sliced_int8_f64_r1_raw.csv",
                 "f64_equivalent_tflops": achieved, "fp64_pipe_peak_tflops": fp64_peak})
         if not args.no_extra:
             out["extra"] = extra_workloads(torch, eml, lib, check, dev, stream, sp, peak)
