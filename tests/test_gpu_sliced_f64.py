@@ -137,3 +137,30 @@ def test_device_matrix_front_end():
     assert np.allclose(prod.to_host().data, (da * db).to_host().data, rtol=0, atol=1e-12)
     with pytest.raises(eml.Panic, match="Mismatched Matrices, left is 600x700, right is 600x700"):
         da.mul_sliced(da)
+
+
+@pytest.mark.parametrize("decades", [1, 3, 5, 7, 9, 12, 16])
+@pytest.mark.parametrize("sparsity", [0.0, 0.6])
+def test_guard_is_sound_on_wide_dynamic_ranges(decades, sparsity):
+    """Magnitudes log-uniform over `decades` decades inside every row / column, optionally with most entries zero: the
+    wider the spread, the less the row-maximum scaling can represent.  Whatever the guard decides, EVERY element of the
+    result must meet the contract (checked against a long-double product of the whole matrix); and it must not refuse
+    the benign cases."""
+    m, n, k = 320, 288, 512
+    r = np.random.default_rng(1000 * decades + int(10 * sparsity))
+    def draw(shape):
+        mag = 10.0 ** (-decades * r.random(shape))
+        x = mag * r.choice([-1.0, 1.0], shape)
+        if sparsity:
+            x[r.random(shape) < sparsity] = 0.0
+        return x
+    a, b = draw((m, k)), draw((k, n))
+    ta, tb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    exact = a.astype(np.longdouble) @ b.astype(np.longdouble)
+    bound = 1e-12 * (np.abs(a).astype(np.longdouble) @ np.abs(b).astype(np.longdouble))
+    for slices in (0, 8, 10):
+        c, path = sliced(ta, tb, slices)
+        err = np.abs(c.cpu().numpy().astype(np.longdouble) - exact)
+        assert np.all(err <= bound), (decades, sparsity, slices, path, float((err / (bound + 1e-300)).max()))
+        if decades <= 3 and sparsity == 0.0:
+            assert path >= 7, "a benign spread must not be refused"
