@@ -541,7 +541,10 @@ int gemm_f64_sliced_dev(DeviceCtx* ctx, const double* A, const double* B, double
     if (M < 1 || N < 1 || K < 1 || lda < K || ldb < N || ldc < N) EML_BAD_ARG("sliced gemm: bad shape");
     const int prepare = slices ? slices : 8;
     int took = 0;
-    if (sliced_shape_ok(M, N, K, slices ? slices : 7)) {
+    // the guard's verdict is read on the host: a stream that is being captured into a graph cannot be synchronised
+    cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
+    EML_CUDA(cudaStreamIsCapturing(stream, &capturing));
+    if (capturing == cudaStreamCaptureStatusNone && sliced_shape_ok(M, N, K, slices ? slices : 7)) {
         SlicedSide a, b;
         EML_TRY(sliced_prepare(A, true, M, K, lda, prepare, stream, &a));
         EML_TRY(sliced_prepare(B, false, N, K, ldb, prepare, stream, &b));
