@@ -173,6 +173,24 @@ class DeviceMatrix {
             detail::check(eml_contract_f64_dev(ptr_, right.ptr_, out.ptr_, 1, rows_, right.cols_, cols_, sa, sb, sc, 0, nullptr));
         return out;
     }
+    // The same product through error-free int8 slices on the INT8 tensor cores (f64 only; eml_gemm_f64_sliced_dev):
+    // about twice the FP64 pipe for large matrices.  A guard proves the path's 1e-12 contract for these operands or the
+    // FP64 kernel runs; *slices_used (optional) reports which (0 = FP64 kernel).  slices = 0: the fewest the guard proves.
+    DeviceMatrix mul_sliced(const DeviceMatrix& right, int slices = 0, int* slices_used = nullptr) const {
+        static_assert(std::is_same<T, double>::value, "mul_sliced is defined for f64 matrices");
+        if (cols_ != right.rows_) {
+            std::ostringstream m;
+            m << "Mismatched Matrices, left is " << rows_ << "x" << cols_ << ", right is " << right.rows_ << "x"
+              << right.cols_ << ", * is only defined for MxN * NxL";
+            throw Panic(m.str());
+        }
+        DeviceMatrix out(rows_, right.cols_);
+        int used = 0;
+        detail::check(eml_gemm_f64_sliced_dev(ptr_, right.ptr_, out.ptr_, rows_, right.cols_, cols_, cols_, right.cols_,
+                                              right.cols_, slices, &used, nullptr));
+        if (slices_used) *slices_used = used;
+        return out;
+    }
     DeviceMatrix operator+(const DeviceMatrix& o) const { return binary(EML_OP_ADD, o, "+"); }  // :41-72
     DeviceMatrix operator-(const DeviceMatrix& o) const { return binary(EML_OP_SUB, o, "-"); }  // :76-107
     DeviceMatrix operator-() const { return unary(EML_OP_NEG, T(0)); }

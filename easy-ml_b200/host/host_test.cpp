@@ -200,6 +200,25 @@ static void device_matrix_checks() {
            "Mismatched matrices, left is 3x2, right is 2x3, + is only defined for MxN + MxN");
 }
 
+// f64 product through int8 slices: exact on small integers, falls back (slices_used = 0) below the kernel's range
+static void sliced_product_checks() {
+    const int n = 320;
+    std::vector<double> a((size_t)n * n), b((size_t)n * n);
+    for (int i = 0; i < n * n; i++) {
+        a[i] = (double)((i * 7 + 3) % 17 - 8);
+        b[i] = (double)((i * 5 + 1) % 13 - 6);
+    }
+    Matrix<double> A(n, n, a), B(n, n, b);
+    DeviceMatrix<double> dA(A), dB(B);
+    int used = -1;
+    Matrix<double> fast = dA.mul_sliced(dB, 0, &used).to_host();
+    EXPECT(used >= 7);
+    EXPECT(fast == (dA * dB).to_host());  // integer data: both kernels are exact
+    Matrix<double> s1(2, 2, {1, 2, 3, 4});
+    DeviceMatrix<double> d1(s1);
+    EXPECT(d1.mul_sliced(d1, 0, &used).to_host() == Matrix<double>(2, 2, {7, 10, 15, 22}) && used == 0);
+}
+
 int main() {
     int n = 0;
     if (eml_init(&n) != EML_OK) {
@@ -225,6 +244,7 @@ int main() {
     distribution_goldens();
     device_matrix_checks<float>();
     device_matrix_checks<double>();
+    sliced_product_checks();
     if (failures) {
         std::fprintf(stderr, "%d check(s) failed\n", failures);
         return 1;
