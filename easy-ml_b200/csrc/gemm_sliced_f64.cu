@@ -280,11 +280,13 @@ sliced_kernel(const __grid_constant__ Maps maps, double* __restrict__ C, int64_t
                                 // more).  Every CTA of this persistent grid is resident, so the wait cannot deadlock.
                                 unsigned int* ctr = step_counters + (wave * (MAX_SLICES * MAX_SLICES) + (GUARD ? 0 : (slices - 1 - d) * MAX_SLICES + p));
                                 atomicAdd(ctr, 1u);
-                                unsigned int seen;
+                                // (bounded: the rendezvous is an optimisation -- if the others do not show up within
+                                //  ~1 s, e.g. because another context holds some SMs, carry on alone)
+                                unsigned int seen, spins = 0;
                                 do {
                                     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
-                                    if (seen < 2u * in_wave) __nanosleep(100);
-                                } while (seen < 2u * in_wave);
+                                    if (seen < 2u * in_wave) __nanosleep(200);
+                                } while (seen < 2u * in_wave && ++spins < 5000000u);
                             }
                             const int s = n % STAGES;
                             if (n >= STAGES) mbar_wait(&empty[s], ((n / STAGES) - 1) & 1);
