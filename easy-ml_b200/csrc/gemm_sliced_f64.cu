@@ -131,8 +131,40 @@ __global__ void scale_kernel(const int* __restrict__ e, double* __restrict__ sca
 // ---------------------------------------------------------------- slicing
 // digits of x in (-1, 1): x = sum_p d[p] 2^(-6 - 7p) + rho; plane `slices` = floor(64 |x|) (the guard's lower bound)
 __device__ __forceinline__ void digits(double x, int slices, int8_t (&d)[MAX_SLICES], int8_t& guard) {
+    guard = (int8_t)__double2int_rz(fabs(x) * 64.0);  // floor: 0..63
+    if (slices == 7 || slices == 8) {
+        // Fixed point in two 32-bit halves, digits on the integer pipe (the FP64-arithmetic form below costs ~160
+        // instructions per element and made this kernel issue-bound):
+        //   x 2^27 = H + r,  H = round(x 2^27) (four digits, weights 2^-6 .. 2^-27),  |r| <= 1/2 exactly representable;
+        //   L = round(r 2^(7 (s - 4)))  (the remaining s - 4 digits).
+        // Balanced base-128 digits from the least significant end: d in [-64, 63], the leading one of each half in
+        // [-64, 64].  Dropping trailing digits leaves |rest| <= 2^(-7 s') (1 + 2^-7) for the s' kept: within the
+        // (s + 2) 2^(-7s) budget of the error analysis.
+        const double xs = x * 134217728.0;  // 2^27
+        int H = __double2int_rn(xs);
+        int L = __double2int_rn((xs - (double)H) * (slices == 8 ? 268435456.0 : 2097152.0));  // 2^28 / 2^21
+#pragma unroll
+        for (int p = 7; p >= 5; p--) {
+            d[p] = 0;
+            if (p < slices) {
+                const int low = ((L + 64) & 127) - 64;
+                d[p] = (int8_t)low;
+                L = (L - low) >> 7;
+            }
+        }
+        d[4] = (int8_t)L;
+#pragma unroll
+        for (int p = 3; p >= 1; p--) {
+            const int low = ((H + 64) & 127) - 64;
+            d[p] = (int8_t)low;
+            H = (H - low) >> 7;
+        }
+        d[0] = (int8_t)H;
+#pragma unroll
+        for (int p = 8; p < MAX_SLICES; p++) d[p] = 0;
+        return;
+    }
     double t = x * 64.0;
-    guard = (int8_t)__double2int_rz(fabs(t));  // floor: 0..63
     constexpr double MAGIC = 6755399441055744.0;  // 1.5 * 2^52: (t + MAGIC) - MAGIC rounds to the nearest integer
 #pragma unroll
     for (int p = 0; p < MAX_SLICES; p++) {
