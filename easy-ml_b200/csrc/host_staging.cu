@@ -36,6 +36,9 @@ class CopyPool {
             for (int64_t i = 0; i < n; i++) fn(i);
             return;
         }
+        // one job at a time: the job state below (fn_, total_, next_, done_, generation_) is shared with the workers, and
+        // callers driving different devices from different threads are not serialised by any per-device mutex
+        std::lock_guard<std::mutex> job(run_mu_);
         std::unique_lock<std::mutex> lock(mu_);
         fn_ = &fn;
         total_ = n;
@@ -81,6 +84,7 @@ class CopyPool {
             if (++done_ == (int)workers_.size()) idle_.notify_one();
         }
     }
+    std::mutex run_mu_;  // held by the caller for a whole job
     std::mutex mu_;
     std::condition_variable cv_, idle_;
     std::vector<std::thread> workers_;
@@ -123,8 +127,19 @@ int ring_for(int device, Ring** out) {
 
 void parallel_copy_rows(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, int64_t rows) {
     if (rows <= 0 || width == 0) return;
+    constexpr size_t BLOCK = size_t(512) << 10;
+    if (width >= 2 * BLOCK) {
+        // wide rows: every row is cut into ~512 KB pieces so that a single long row still spreads over the pool
+        const int64_t pieces = (int64_t)((width + BLOCK - 1) / BLOCK);
+        CopyPool::get().run(rows * pieces, [&](int64_t t) {
+            const int64_t r = t / pieces;
+            const size_t off = (size_t)(t % pieces) * BLOCK, len = std::min(BLOCK, width - off);
+            memcpy((char*)dst + r * dpitch + off, (const char*)src + r * spitch + off, len);
+        });
+        return;
+    }
     // blocks of whole rows, ~512 KB each
-    int64_t rows_per_block = std::max<int64_t>(1, (int64_t)((size_t(512) << 10) / width));
+    int64_t rows_per_block = std::max<int64_t>(1, (int64_t)(BLOCK / width));
     int64_t blocks = (rows + rows_per_block - 1) / rows_per_block;
     CopyPool::get().run(blocks, [&](int64_t b) {
         int64_t r0 = b * rows_per_block, r1 = std::min(rows, r0 + rows_per_block);
@@ -172,7 +187,15 @@ int StagedCopier::h2d(void* dst_dev, size_t dpitch, const void* src_host, size_t
         EML_CUDA(cudaMemcpy2DAsync(dst_dev, dpitch, src_host, spitch, width, rows, cudaMemcpyHostToDevice, stream));
         return EML_OK;
     }
-    if (width > SLOT_BYTES) EML_BAD_ARG("staged copy: a row of %zu bytes does not fit a staging slot", width);
+    if (width > SLOT_BYTES) {
+        // a row wider than a slot (one whole batch element of a batched contraction, a very long matrix row): cut it
+        // into slot-sized pieces, each travelling as a one-row copy
+        for (int64_t r = 0; r < rows; r++)
+            for (size_t off = 0; off < width; off += SLOT_BYTES)
+                EML_TRY(h2d((char*)dst_dev + r * dpitch + off, dpitch, (const char*)src_host + r * spitch + off, spitch,
+                            std::min(SLOT_BYTES, width - off), 1, stream));
+        return EML_OK;
+    }
     Ring* ring = nullptr;
     EML_TRY(ring_for(ctx_->device, &ring));
     const int64_t chunk = std::max<int64_t>(1, (int64_t)(SLOT_BYTES / width));
@@ -196,7 +219,13 @@ int StagedCopier::d2h(void* dst_host, size_t dpitch, const void* src_dev, size_t
         EML_CUDA(cudaMemcpy2DAsync(dst_host, dpitch, src_dev, spitch, width, rows, cudaMemcpyDeviceToHost, stream));
         return EML_OK;
     }
-    if (width > SLOT_BYTES) EML_BAD_ARG("staged copy: a row of %zu bytes does not fit a staging slot", width);
+    if (width > SLOT_BYTES) {
+        for (int64_t r = 0; r < rows; r++)
+            for (size_t off = 0; off < width; off += SLOT_BYTES)
+                EML_TRY(d2h((char*)dst_host + r * dpitch + off, dpitch, (const char*)src_dev + r * spitch + off, spitch,
+                            std::min(SLOT_BYTES, width - off), 1, stream));
+        return EML_OK;
+    }
     Ring* ring = nullptr;
     EML_TRY(ring_for(ctx_->device, &ring));
     const int64_t chunk = std::max<int64_t>(1, (int64_t)(SLOT_BYTES / width));

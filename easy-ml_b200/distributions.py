@@ -37,7 +37,7 @@ def cholesky_decomposition(matrix):
                     return None
                 low[i, j] = np.sqrt(entry_squared)
             else:
-                low[i, j] = (a[i, j] - s) / low[j, j]
+                low[i, j] = (a[i, j] - s) * (dt(1) / low[j, j])  # :1093-1096: reciprocal, then multiply (two roundings)
     return Matrix(low) if isinstance(matrix, Matrix) else low
 
 

@@ -263,7 +263,9 @@ std::optional<Matrix<T>> cholesky_decomposition(const Matrix<T>& a) {
                 if (entry_squared <= T(0)) return std::nullopt;  // :1087: not positive definite
                 low[i * n + j] = std::sqrt(entry_squared);
             } else {
-                low[i * n + j] = (a.get(i, j) - sum) / low[j * n + j];
+                // :1093-1096: `(a - sum) * (T::one() / L[j][j])` -- reciprocal first, then a multiply (two roundings)
+                const T reciprocal = T(1) / low[j * n + j];
+                low[i * n + j] = (a.get(i, j) - sum) * reciprocal;
             }
         }
     return Matrix<T>(n, n, std::move(low));

@@ -220,7 +220,7 @@ def cholesky(a):
                     return None
                 low[i, j] = np.sqrt(entry_squared)
             else:
-                low[i, j] = (a[i, j] - s) / low[j, j]
+                low[i, j] = (a[i, j] - s) * (t(1) / low[j, j])  # :1093-1096: reciprocal, then multiply (two roundings)
     return low
 
 

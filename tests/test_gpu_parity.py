@@ -921,3 +921,55 @@ def test_batched_host_contraction_pipelines_over_batch_chunks(dtype):
         bv = b[i * sb_b:i * sb_b + k * ldb].reshape(k, ldb)[:, :n].astype(np.float64)
         bound = TOL[np.dtype(dtype)] * (np.abs(av) @ np.abs(bv))
         assert np.all(np.abs(cv[i, :m * n].reshape(m, n).astype(np.float64) - av @ bv) <= bound)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_batched_host_contraction_with_batches_wider_than_a_staging_slot(dtype):
+    """Pageable (numpy) operands whose single batch element exceeds the 16 MB page-locked staging slot
+    (4 x 2100 x 2100 f32 = 17.6 MB per batch, f64 twice that): the staged copier cuts such a 'row' into slot-sized
+    pieces.  The reference computes these shapes (Einsum2::to, src/tensors/einsum.rs:908-980), so must the drop-in."""
+    bt, m = 4, 2100
+    r = rng(62)
+    a = uniform(r, (bt, m, m), dtype)
+    b = uniform(r, (bt, m, m), dtype)
+    c = np.empty((bt, m, m), dtype)
+    sfx = "f32" if dtype == np.float32 else "f64"
+    s3 = lambda *v: (C.c_int64 * 3)(*v)
+    check(getattr(lib, f"eml_contract_{sfx}")(ptr(a), ptr(b), ptr(c), bt, m, m, m, s3(m * m, m, 1), s3(m * m, m, 1),
+                                             s3(m * m, m, 1)))
+    for i in (0, 3):
+        rows = np.array([0, 1, 777, m - 1])
+        av, bv = a[i][rows].astype(np.float64), b[i].astype(np.float64)
+        bound = TOL[np.dtype(dtype)] * (np.abs(av) @ np.abs(bv))
+        assert np.all(np.abs(c[i][rows].astype(np.float64) - av @ bv) <= bound)
+
+
+def test_concurrent_pageable_host_calls_on_two_devices():
+    """Two host threads, each driving its own GPU with pageable operands large enough for the pipelined path: the copy
+    thread pool is shared by the whole process and must serve both without mixing their jobs."""
+    import threading
+
+    torch = pytest.importorskip("torch")
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    r = rng(63)
+    a, b = uniform(r, (2304, 1024), np.float64), uniform(r, (1024, 1280), np.float64)
+    want = gemm(a, b)
+    errors = []
+
+    def worker(dev):
+        try:
+            torch.cuda.set_device(dev)
+            for _ in range(4):
+                if not np.array_equal(gemm(a, b), want):
+                    errors.append(f"device {dev}: mismatch")
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(d,)) for d in (0, 1)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    torch.cuda.set_device(0)
+    assert not errors, errors

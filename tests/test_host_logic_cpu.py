@@ -23,6 +23,9 @@ def test_cholesky_restatement_matches_oracle_and_goldens(orc, golden):
         spd = (x.T @ x / (3 * n) + 0.1 * np.eye(n)).astype(dtype)
         assert np.array_equal(distributions.cholesky_decomposition(spd), orc.cholesky(spd))
     assert distributions.cholesky_decomposition(eml.Matrix(np.array([[1.0, 2.0], [2.0, 1.0]]))) is None
+    # (a - sum) * (1 / L[j][j]), two roundings (src/linear_algebra.rs:1093-1096): 5 * fl(1/3) != fl(5/3)
+    low = distributions.cholesky_decomposition(np.array([[9.0, 5.0], [5.0, 10.0]]))
+    assert low[1, 0].hex() == float.fromhex("0x1.aaaaaaaaaaaaap+0").hex() and low[1, 0] != 5.0 / 3.0
     assert distributions.cholesky_decomposition(np.zeros((2, 3))) is None
 
 

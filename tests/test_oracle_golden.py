@@ -267,6 +267,31 @@ def test_cholesky_goldens(orc, golden):
     assert orc.cholesky(np.zeros((2, 3))) is None                        # not square
 
 
+def test_cholesky_off_diagonal_is_reciprocal_then_multiply(orc):
+    """The reference computes L[i][j] = (a - sum) * (T::one() / L[j][j]) (src/linear_algebra.rs:1093-1096): a reciprocal
+    and a multiply, TWO roundings -- not one division.  [[9, 5], [5, 10]]: L00 = 3 and L10 = 5 * fl(1/3), which rounds
+    to 0x3FFAAAAAAAAAAAAA, while 5/3 rounds to 0x3FFAAAAAAAAAAAAB.  The expected bits are derived here with exact
+    rationals (float(Fraction) is correctly rounded), independently of the oracle's arithmetic."""
+    from fractions import Fraction
+    import struct
+
+    bits = lambda x: struct.unpack("<Q", struct.pack("<d", float(x)))[0]
+    reciprocal = float(Fraction(1, 3))                       # fl(1 / 3)
+    two_roundings = float(Fraction(5) * Fraction(reciprocal))  # fl(5 * fl(1/3))
+    one_rounding = float(Fraction(5, 3))
+    assert bits(two_roundings) == 0x3FFAAAAAAAAAAAAA and bits(one_rounding) == 0x3FFAAAAAAAAAAAAB
+    low = orc.cholesky(np.array([[9.0, 5.0], [5.0, 10.0]]))
+    assert low[0, 0] == 3.0 and bits(low[1, 0]) == bits(two_roundings)
+    # third row: the sum is taken before the reciprocal multiply, L22's radicand uses the two-rounding entries
+    a = np.array([[9.0, 5.0, 7.0], [5.0, 10.0, 2.0], [7.0, 2.0, 20.0]])
+    low = orc.cholesky(a)
+    l10, l20 = two_roundings, float(Fraction(7) * Fraction(reciprocal))
+    l11 = float(np.sqrt(np.float64(float(Fraction(10) - Fraction(float(Fraction(l10) * Fraction(l10)))))))
+    s = float(Fraction(0) + Fraction(float(Fraction(l20) * Fraction(l10))))
+    l21 = float(Fraction(float(Fraction(2) - Fraction(s))) * Fraction(float(Fraction(1) / Fraction(l11))))
+    assert (low[1, 0], low[2, 0], low[1, 1], low[2, 1]) == (l10, l20, l11, l21)
+
+
 def test_multivariate_gaussian_draw_golden(orc, golden):
     """tests/distributions.rs:48-220: the reference's own assertions on its fixed random source."""
     g = golden["multivariate_gaussian"]
