@@ -69,6 +69,12 @@ int contract_dev(DeviceCtx* ctx, const T* A, const T* B, T* C, int64_t batch, in
     // tall-skinny A^T * B (N <= 16, A contiguous along m, long K): its own chunked kernel
     if (!exact && batch == 1 && N >= 1 && N <= 16 && sA.r == 1 && sA.c != 1 && K >= 256 && M >= 32 && A && B && C)
         return launch_gemm_skinny_tn<T>(ctx, A, B, C, M, N, K, sA, sB, sC, accumulate, stream);
+    // thin products (M <= 4 rows against a dense row-major B, long K): one launch, ticketed fixed-order finish
+    if (!exact && batch == 1 && A && B && C && K >= 256 && thin_shape(M, N, K) && sB.c == 1 && sB.r == N)
+        return launch_thin_fwd<T>(A, sA.r, sA.c, B, M, N, K, C, sC.r, sC.c, accumulate, stream);
+    // short contraction, wide dense output (dH = dY * W2^T of an output layer): B in shared memory, no split
+    if (!exact && batch == 1 && A && B && C && sA.c == 1 && sC.c == 1 && smallk_shape(M, N, K, sizeof(T)))
+        return launch_gemm_smallk<T>(A, sA.r, B, sB.r, sB.c, C, sC.r, M, N, K, accumulate, stream);
     // Deterministic split-K for outputs with too few tiles for 148 SMs and a long K (the loss reduction
     // L[1 x batch] * d[batch x 10], dW2 = H^T[512 x batch] * dY[batch x 10], ...): K is cut into S equal
     // chunks which run as S "batches" of one launch into a workspace [S][M][N]; a fixed-order reduction

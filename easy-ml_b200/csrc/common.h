@@ -266,6 +266,24 @@ int launch_center(const T* x, const T* sums, int64_t samples, int64_t rows, int6
 template <class T>
 int launch_dot_accumulate(DeviceCtx* ctx, const T* x, const T* y, int64_t n, T* out, bool accumulate,
                           cudaStream_t stream);
+// zero-initialised, self-resetting ticket counters of a stream (single-pass deterministic reductions)
+int stream_tickets(cudaStream_t stream, unsigned** out);
+// tape_kernels.cu: the reference's constant-operand sums, thin (M <= 4) products, short-contraction products
+template <class T>
+int launch_quirk_cols(const T* G, int64_t gm, const T* B, int64_t bm, int64_t N, T* out, cudaStream_t stream);
+template <class T>
+int launch_quirk_rows(const T* A, int64_t K, const T* G, int64_t N, int64_t M, T* out, cudaStream_t stream);
+bool thin_shape(int64_t M, int64_t N, int64_t K);
+template <class T>
+int launch_thin_fwd(const T* A, int64_t sAr, int64_t sAc, const T* B, int64_t M, int64_t N, int64_t K, T* C, int64_t sCr,
+                    int64_t sCc, bool accumulate, cudaStream_t stream);
+template <class T>
+int launch_thin_bwd(const T* G, const T* A, const T* B, int64_t M, int64_t N, int64_t K, T* dA, bool over_a, T* dB,
+                    bool over_b, bool quirk_a, bool quirk_b, T* slot0, cudaStream_t stream);
+bool smallk_shape(int64_t M, int64_t N, int64_t K, size_t elem);
+template <class T>
+int launch_gemm_smallk(const T* A, int64_t lda, const T* B, int64_t sBr, int64_t sBc, T* C, int64_t ldc, int64_t M, int64_t N,
+                       int64_t K, bool accumulate, cudaStream_t stream);
 // dst[i] = src[idx(i)] strided gather/scatter helpers for matmul-output derivative vectors
 template <class T>
 int launch_add_inplace(T* dst, const T* src, int64_t n, cudaStream_t stream);

@@ -11,6 +11,7 @@
 #include <utility>
 
 #include "common.h"
+#include "ew_rules.cuh"
 
 namespace eml {
 
@@ -24,66 +25,6 @@ inline int ew_grid(int64_t n, int per_thread) {
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     return (int)blocks;
-}
-
-// 16-byte vectors: float4 / double2
-template <class T>
-struct Vec;
-template <>
-struct Vec<float> {
-    using type = float4;
-    static constexpr int N = 4;
-};
-template <>
-struct Vec<double> {
-    using type = double2;
-    static constexpr int N = 2;
-};
-
-template <class T>
-__device__ __forceinline__ void vload(const T* p, T (&v)[Vec<T>::N]) {
-    typename Vec<T>::type t = *reinterpret_cast<const typename Vec<T>::type*>(p);
-    const T* e = reinterpret_cast<const T*>(&t);
-#pragma unroll
-    for (int i = 0; i < Vec<T>::N; i++) v[i] = e[i];
-}
-template <class T>
-__device__ __forceinline__ void vstore(T* p, const T (&v)[Vec<T>::N]) {
-    typename Vec<T>::type t;
-    T* e = reinterpret_cast<T*>(&t);
-#pragma unroll
-    for (int i = 0; i < Vec<T>::N; i++) e[i] = v[i];
-    *reinterpret_cast<typename Vec<T>::type*>(p) = t;
-}
-
-inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
-
-// ---- rules (reference src/differentiation/functions.rs) ----
-template <class T, int OP>
-__device__ __forceinline__ void unary_rule(T c, T x, T& y, T& d) {
-    if (OP == EML_OP_NEG) { y = -x; d = -T(1); }
-    else if (OP == EML_OP_SIN) { y = sin(x); d = cos(x); }
-    else if (OP == EML_OP_COS) { y = cos(x); d = -sin(x); }
-    else if (OP == EML_OP_EXP) { y = exp(x); d = y; }
-    else if (OP == EML_OP_LN) { y = log(x); d = T(1) / x; }
-    else if (OP == EML_OP_SQRT) { y = sqrt(x); d = T(1) / ((T(1) + T(1)) * y); }
-    else if (OP == EML_OP_ADD_C) { y = x + c; d = T(1); }
-    else if (OP == EML_OP_SUB_C) { y = x - c; d = T(1); }
-    else if (OP == EML_OP_MUL_C) { y = x * c; d = c; }
-    else if (OP == EML_OP_DIV_C) { y = x / c; d = T(1) / c; }
-    else if (OP == EML_OP_POW_C) { y = pow(x, c); d = c * pow(x, c - T(1)); }
-    else if (OP == EML_OP_C_SUB) { y = c - x; d = -T(1); }
-    else if (OP == EML_OP_C_DIV) { y = c / x; d = -c / (x * x); }
-    else if (OP == EML_OP_C_POW) { y = pow(c, x); d = y * log(c); }
-}
-
-template <class T, int OP>
-__device__ __forceinline__ void binary_rule(T x, T y, T& z, T& dx, T& dy) {
-    if (OP == EML_OP_ADD) { z = x + y; dx = T(1); dy = T(1); }
-    else if (OP == EML_OP_SUB) { z = x - y; dx = T(1); dy = -T(1); }
-    else if (OP == EML_OP_MUL) { z = x * y; dx = y; dy = x; }
-    else if (OP == EML_OP_DIV) { z = x / y; dx = T(1) / y; dy = -x / (y * y); }
-    else if (OP == EML_OP_POW) { z = pow(x, y); dx = y * pow(x, y - T(1)); dy = z * log(x); }
 }
 
 template <class T, int OP, bool VEC>
@@ -465,6 +406,8 @@ int launch_axpy(T c, const T* a, const T* b, T* out, int64_t n, cudaStream_t str
 }
 
 }  // namespace
+
+int stream_tickets(cudaStream_t stream, unsigned** out) { return ticket_counters(stream, out); }
 
 template <class T>
 int launch_unary(int op, T c, const T* x, T* y, T* dydx, int64_t n, cudaStream_t stream) {

@@ -12,7 +12,10 @@
 #include <memory>
 #include <vector>
 
+#include <cstdlib>
+
 #include "common.h"
+#include "ew_fused.h"
 
 namespace eml {
 
@@ -76,6 +79,13 @@ struct Node {
     // x + y, x - y): no derivative array is written in the forward pass or read in the sweep
     bool a_const = false, b_const = false;
     double a_c = 0, b_c = 0;
+    // ---- member of a fused elementwise group (evaluated lazily, see Group) ----
+    int group = -1;        // index into the tape's groups of this epoch; -1: evaluated eagerly, one kernel per node
+    int op = -1;           // EML_OP_*
+    double c = 0;          // scalar operand
+    int xn = -1, yn = -1;  // operand produced by a node of the SAME group (its node id); else the numbers below
+    Buf xin, yin;          // operand numbers living outside the group (kept alive: the backward pass recomputes)
+    Buf value;             // this node's numbers once somebody needed them (null: interior, never stored)
     // index of element e of the produced container on the reference tape
     int64_t index_of(int64_t e) const {
         if (kind == Kind::MATMUL && K > 1) return base + e * (2 * K - 1) + 2 * K - 2;
@@ -87,6 +97,19 @@ struct Node {
         if (kind == Kind::MATMUL && K > 1) return (index - base) / (2 * K - 1);
         return index - base;
     }
+};
+
+// A fused elementwise group: a run of CONSECUTIVE tape nodes, all container-level unary / binary rules over
+// containers of one element count.  While the group is open its containers have no numbers yet; the first use that
+// needs numbers (a matmul operand, a read, the sweep, ...) flushes it: ONE kernel evaluates the whole run and stores
+// only the containers that are still held.  In the sweep the group is again ONE kernel (ew_fused.cu).  Consecutive
+// node ids make the fused backward equivalent to visiting the nodes one by one in descending order: nothing else can
+// contribute to a derivative between two nodes of the run.
+struct Group {
+    int first = 0, last = -1;
+    int64_t n = 0;
+    bool flushed = false;
+    std::vector<eml_val> owner;  // per node: the container handle waiting for its numbers (-1: released meanwhile)
 };
 
 }  // namespace
@@ -103,7 +126,11 @@ struct eml_derivs {
     int64_t len = 0;
     uint64_t epoch = 0;
     std::vector<Node> nodes;  // copies of the metadata (buffers shared)
+    std::vector<Group> groups;
     std::vector<Buf> grads;   // per node, n elements
+    // per node: its derivatives are in `grads`.  Interior nodes of a fused group are not stored by the sweep (nobody
+    // holds a container for them); Derivatives::at(index) / Vec::from(Derivatives) materialise them on demand.
+    std::vector<char> have;
 };
 
 struct eml_graph {
@@ -123,6 +150,9 @@ struct eml_tape {
     int64_t len = 0;
     uint64_t epoch = 1;
     std::vector<Node> nodes;
+    std::vector<Group> groups;
+    int open = -1;  // the group still accepting nodes (its containers have no numbers yet), or -1
+    bool fuse = true;  // EML_FUSE=0: one kernel per elementwise node (the comparison path of the parity tests)
     std::vector<Value> values;
     std::vector<eml_val> free_slots;
     std::mutex mu;
@@ -180,6 +210,270 @@ int live_node(eml_tape* t, const Value& v, bool* stale) {
     return v.node;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Fused elementwise groups: program construction (the kernels are in ew_fused.cu)
+// ---------------------------------------------------------------------------------------------------------------
+inline bool is_unary_op(int op) { return op < EML_OP_ADD; }
+
+// Forward structure of a group: leaves (distinct outside buffers), operand sources, value slots.
+// Returns false when the group does not fit the program format.
+bool program_structure(const std::vector<Node>& nodes, const Group& g, EwProgram* p) {
+    *p = EwProgram{};
+    const int n_ops = g.last - g.first + 1;
+    if (n_ops > EW_MAX_OPS) return false;
+    p->n_ops = n_ops;
+    p->n = g.n;
+    p->seed_elem = -1;
+    bool needs_slot[EW_MAX_OPS] = {};
+    auto leaf = [&](const Buf& b) -> int {  // index of the leaf, -1: too many
+        for (int l = 0; l < p->n_in; l++)
+            if (p->in[l] == b->p) return l;
+        if (p->n_in == EW_MAX_IN) return -1;
+        p->in[p->n_in] = b->p;
+        return p->n_in++;
+    };
+    for (int k = 0; k < n_ops; k++) {
+        const Node& nd = nodes[g.first + k];
+        EwOp& o = p->ops[k];
+        o.op = (uint64_t)ew_dense_op(nd.op);
+        o.c = nd.c;
+        o.save = o.da_slot = o.db_slot = -1;
+        if (nd.xn >= 0) {
+            const int j = nd.xn - g.first;
+            if (j == k - 1) o.a_src = EW_SRC_PREV;
+            else o.a_src = EW_SRC_SLOT, o.a_idx = (uint64_t)j, needs_slot[j] = true;  // a_idx: node for now
+        } else {
+            const int l = leaf(nd.xin);
+            if (l < 0) return false;
+            o.a_src = EW_SRC_LEAF, o.a_idx = (uint64_t)l;
+        }
+        if (is_unary_op(nd.op)) continue;
+        if (nd.yn >= 0) {
+            const int j = nd.yn - g.first;
+            if (j == k - 1) o.b_src = EW_SRC_PREV;
+            else o.b_src = EW_SRC_SLOT, o.b_idx = (uint64_t)j, needs_slot[j] = true;
+        } else {
+            const int l = leaf(nd.yin);
+            if (l < 0) return false;
+            o.b_src = EW_SRC_LEAF, o.b_idx = (uint64_t)l;
+        }
+    }
+    for (int k = 0; k < n_ops; k++)
+        if (needs_slot[k]) p->ops[k].save = p->n_slots++;
+    for (int k = 0; k < n_ops; k++) {  // node -> slot
+        EwOp& o = p->ops[k];
+        if (o.a_src == EW_SRC_SLOT) o.a_idx = (uint64_t)p->ops[o.a_idx].save;
+        if (o.b_src == EW_SRC_SLOT) o.b_idx = (uint64_t)p->ops[o.b_idx].save;
+    }
+    return p->n_slots <= EW_MAX_SLOTS;
+}
+
+// which sides of node nd take part in the sweep, and whether their derivative is one number for every element
+inline void sweep_sides(const Node& nd, bool* a, bool* b) {
+    *a = nd.kind == Kind::UNARY ? true : nd.p0_tracked;
+    *b = nd.kind == Kind::BINARY && nd.p1_tracked;
+}
+
+// worst case of the slots the backward program of this group may need, whatever the sweep looks like
+bool group_fits(const std::vector<Node>& nodes, const Group& g) {
+    EwProgram p;
+    if (!program_structure(nodes, g, &p)) return false;
+    int slots = p.n_slots + p.n_ops + p.n_in;  // values + one accumulator per node + one per leaf
+    for (int i = g.first; i <= g.last; i++) {
+        bool a, b;
+        sweep_sides(nodes[i], &a, &b);
+        if (a && !nodes[i].a_const) slots++;
+        if (b && !nodes[i].b_const) slots++;
+    }
+    return slots <= EW_MAX_SLOTS;
+}
+
+// Backward program of group g inside one sweep.
+//   written[i]: the arena already holds defined numbers for node i (zero fill or earlier contributions)
+//   have[i]   : node i's FINAL derivatives are in the arena
+//   remat     : after the sweep, store the derivatives of the nodes the sweep kept in registers only; nothing outside
+//               the group is touched and nodes whose derivatives are final are read, not accumulated again
+template <class T>
+int group_backward(const std::vector<Node>& nodes, const Group& g, const std::vector<Buf>& grads,
+                   std::vector<char>& written, std::vector<char>& have, int seed_node, int64_t seed_elem, bool remat,
+                   cudaStream_t st) {
+    EwProgram p;
+    if (!program_structure(nodes, g, &p)) {
+        set_error("internal: a fused elementwise group does not fit its program");
+        return EML_ERR_STATE;
+    }
+    const int n_ops = p.n_ops;
+    p.seed_elem = seed_elem;
+    int refs[EW_MAX_OPS] = {};           // in-group references to node k from sides that contribute
+    bool next_only[EW_MAX_OPS];           // ... all of them from op k + 1
+    for (int k = 0; k < n_ops; k++) next_only[k] = true;
+    bool frozen[EW_MAX_OPS];
+    for (int k = 0; k < n_ops; k++) frozen[k] = remat && have[g.first + k];
+    auto contributes_to = [&](int k, int target_node, bool tracked) {
+        if (!tracked || target_node < 0) return false;
+        return !frozen[target_node - g.first];
+    };
+    for (int k = 0; k < n_ops; k++) {
+        const Node& nd = nodes[g.first + k];
+        bool a, b;
+        sweep_sides(nd, &a, &b);
+        if (contributes_to(k, nd.xn, a)) refs[nd.xn - g.first]++, next_only[nd.xn - g.first] &= (nd.xn - g.first == k - 1);
+        if (contributes_to(k, nd.yn, b)) refs[nd.yn - g.first]++, next_only[nd.yn - g.first] &= (nd.yn - g.first == k - 1);
+    }
+    // where each node's own derivative starts and lives
+    for (int k = 0; k < n_ops; k++) {
+        const int id = g.first + k;
+        EwOp& o = p.ops[k];
+        p.gptr[k] = grads[id]->p;
+        if (frozen[k]) o.g_init = EW_INIT_LOAD;
+        else if (!remat && id == seed_node && !written[id]) o.g_init = EW_INIT_SEED;
+        else o.g_init = written[id] ? EW_INIT_LOAD : EW_INIT_ZERO;
+        if (refs[k] == 0) o.g_src = EW_G_DIRECT;
+        else if (refs[k] == 1 && next_only[k] && o.g_init == EW_INIT_ZERO) o.g_src = EW_G_CARRY;
+        else o.g_src = EW_G_SLOT, o.g_idx = (uint64_t)p.n_slots++;
+        const bool changed = refs[k] > 0 || o.g_init != EW_INIT_LOAD;
+        if (remat) o.g_store = !have[id];
+        else o.g_store = nodes[id].value && changed;
+    }
+    // contributions of each side
+    auto leaf_grad = [&](int parent) -> int {
+        for (int l = 0; l < p.n_leafgrad; l++)
+            if (p.lg[l].ptr == grads[parent]->p) return p.lg[l].slot;
+        EwLeafGrad& lg = p.lg[p.n_leafgrad++];
+        lg.ptr = grads[parent]->p;
+        lg.slot = (int8_t)p.n_slots++;
+        lg.overwrite = !written[parent];
+        written[parent] = 1;
+        return lg.slot;
+    };
+    for (int k = 0; k < n_ops; k++) {
+        const Node& nd = nodes[g.first + k];
+        EwOp& o = p.ops[k];
+        bool a, b;
+        sweep_sides(nd, &a, &b);
+        o.a_const = nd.a_const, o.ca = nd.a_c;
+        o.b_const = nd.b_const, o.cb = nd.b_c;
+        for (int side = 0; side < 2; side++) {
+            const bool tracked = side ? b : a;
+            const int in_group = side ? nd.yn : nd.xn, parent = side ? nd.p1 : nd.p0;
+            uint8_t tgt = EW_TGT_NONE, idx = 0;
+            if (tracked && in_group >= 0) {
+                const int j = in_group - g.first;
+                if (!frozen[j]) {
+                    if (p.ops[j].g_src == EW_G_CARRY) tgt = EW_TGT_CARRY;
+                    else tgt = EW_TGT_SLOT, idx = p.ops[j].g_idx;
+                }
+            } else if (tracked && parent >= 0 && !remat) {
+                bool known = false;
+                for (int l = 0; l < p.n_leafgrad; l++) known |= p.lg[l].ptr == grads[parent]->p;
+                if (!known && p.n_leafgrad == EW_MAX_IN) {
+                    set_error("internal: too many tracked inputs in a fused elementwise group");
+                    return EML_ERR_STATE;
+                }
+                tgt = EW_TGT_SLOT, idx = (uint8_t)leaf_grad(parent);
+            }
+            const bool is_const = side ? nd.b_const : nd.a_const;
+            int dslot = -1;
+            if (tgt != EW_TGT_NONE && !is_const) dslot = p.n_slots++;
+            if (side) o.b_tgt = tgt, o.b_tgt_idx = idx, o.db_slot = dslot;
+            else o.a_tgt = tgt, o.a_tgt_idx = idx, o.da_slot = dslot;
+        }
+    }
+    if (p.n_slots > EW_MAX_SLOTS) {
+        set_error("internal: a fused elementwise group needs %d slots", p.n_slots);
+        return EML_ERR_STATE;
+    }
+    bool anything = p.n_leafgrad > 0;
+    for (int k = 0; k < n_ops; k++) anything |= p.ops[k].g_store != 0;
+    if (anything) EML_TRY(launch_ew_backward<T>(p, st));
+    for (int k = 0; k < n_ops; k++) {
+        const int id = g.first + k;
+        if (p.ops[k].g_store) have[id] = 1, written[id] = 1;
+        else if (!remat) have[id] = nodes[id].value && written[id];  // stored containers whose arena entry is final
+    }
+    return EML_OK;
+}
+
+// Gives every still-held container of the open group its numbers: one kernel for the whole run.
+template <class T>
+int flush_open(eml_tape* t) {
+    if (t->open < 0) return EML_OK;
+    Group& g = t->groups[t->open];
+    t->open = -1;
+    g.flushed = true;
+    EwProgram p;
+    if (!program_structure(t->nodes, g, &p)) {
+        set_error("internal: a fused elementwise group does not fit its program");
+        return EML_ERR_STATE;
+    }
+    bool any = false;
+    for (int k = 0; k < p.n_ops; k++) {
+        const eml_val h = g.owner[k];
+        if (h < 0) continue;  // released before anybody needed its numbers: never stored
+        Buf b;
+        EML_TRY(new_buf(sizeof(T) * (size_t)g.n, t->stream, &b));
+        t->values[h].numbers = b;
+        t->nodes[g.first + k].value = b;
+        p.ops[k].out = 1;
+        p.out[k] = b->p;
+        any = true;
+    }
+    if (any) EML_TRY(launch_ew_forward<T>(p, t->stream));
+    return EML_OK;
+}
+
+int flush(eml_tape* t) { return t->dtype == EML_F32 ? flush_open<float>(t) : flush_open<double>(t); }
+
+// Appends one lazily evaluated elementwise node (already filled in except for the group bookkeeping) and the container
+// that will receive its numbers.  x / y: the operand containers (y null for unary rules).
+template <class T>
+int append_lazy(eml_tape* t, Node nd, Value* x, Value* y, Value&& result, eml_val* out) {
+    const int64_t n = nd.n;
+    auto operand_in_open_group = [&](Value* v) { return v && !v->numbers; };
+    // try to extend the open group
+    bool extended = false;
+    if (t->open >= 0) {
+        Group& g = t->groups[t->open];
+        if (g.last == (int)t->nodes.size() - 1 && g.n == n) {
+            nd.group = t->open;
+            nd.xn = operand_in_open_group(x) ? x->node : -1;
+            nd.yn = operand_in_open_group(y) ? y->node : -1;
+            nd.xin = nd.xn < 0 ? x->numbers : nullptr;
+            nd.yin = (y && nd.yn < 0) ? y->numbers : nullptr;
+            t->nodes.push_back(nd);
+            g.last++;
+            if (group_fits(t->nodes, g)) {
+                extended = true;
+            } else {
+                g.last--;
+                t->nodes.pop_back();
+            }
+        }
+    }
+    if (!extended) {
+        EML_TRY(flush_open<T>(t));  // the operands (held by the caller) now have numbers
+        Group g;
+        g.first = g.last = (int)t->nodes.size();
+        g.n = n;
+        t->groups.push_back(g);
+        t->open = (int)t->groups.size() - 1;
+        nd.group = t->open;
+        nd.xn = nd.yn = -1;
+        nd.xin = x->numbers;
+        nd.yin = y ? y->numbers : nullptr;
+        t->nodes.push_back(nd);
+    }
+    t->len += nd.count;
+    result.tracked = true;
+    result.node = (int)t->nodes.size() - 1;
+    result.epoch = t->epoch;
+    const eml_val h = put_value(t, std::move(result));
+    t->groups[t->open].owner.push_back(h);
+    *out = h;
+    return EML_OK;
+}
+
 template <class T>
 int new_container(eml_tape* t, const void* src, bool src_on_device, int64_t rows, int64_t cols, bool variables,
                   eml_val* out) {
@@ -187,6 +481,7 @@ int new_container(eml_tape* t, const void* src, bool src_on_device, int64_t rows
                                           (long long)rows, (long long)cols);
     if (!src || !out) EML_BAD_ARG("null argument");
     if (!src_on_device) EML_TRY(not_while_capturing(t, "creating a container from host memory"));
+    EML_TRY(flush_open<T>(t));
     Value v;
     v.rows = rows;
     v.cols = cols;
@@ -227,6 +522,7 @@ int tape_matmul(eml_tape* t, eml_val ha, eml_val hb, eml_val* out) {
         return EML_ERR_STATE;
     }
     const int64_t M = a->rows, K = a->cols, N = b->cols;
+    EML_TRY(flush_open<T>(t));  // the operands may be containers of the open elementwise group
     Value c;
     c.rows = M;
     c.cols = N;
@@ -266,6 +562,7 @@ template <class T>
 int tape_unary(eml_tape* t, int op, double cst, eml_val hx, eml_val* out) {
     Value* x;
     EML_TRY(get_value(t, hx, &x));
+    if (op < EML_OP_NEG || op > EML_OP_C_POW) EML_BAD_ARG("unknown unary op %d", op);
     bool stale;
     int nx = live_node(t, *x, &stale);
     if (stale) {
@@ -276,33 +573,40 @@ int tape_unary(eml_tape* t, int op, double cst, eml_val hx, eml_val* out) {
     y.rows = x->rows;
     y.cols = x->cols;
     const int64_t n = x->n();
-    EML_TRY(new_buf(sizeof(T) * n, t->stream, &y.numbers));
     if (!x->tracked) {  // history None -> constants (reference container_record/mod.rs:852)
+        EML_TRY(new_buf(sizeof(T) * n, t->stream, &y.numbers));
         EML_TRY(launch_unary<T>(op, (T)cst, (const T*)x->numbers->p, (T*)y.numbers->p, (T*)nullptr, n, t->stream));
-    } else {
-        Node nd;
-        nd.kind = Kind::UNARY;
-        nd.base = t->len;
-        nd.count = nd.n = n;
-        nd.p0 = nx;
-        nd.p0_tracked = true;
-        // the same expressions as unary_rule (csrc/elementwise.cu), evaluated in T
-        const T c = (T)cst;
-        switch (nx >= 0 ? op : -1) {  // (a parent carrying Index 0 keeps the array: its sweep is a dot product)
-            case EML_OP_NEG: case EML_OP_C_SUB: nd.a_const = true; nd.a_c = (double)(-T(1)); break;
-            case EML_OP_ADD_C: case EML_OP_SUB_C: nd.a_const = true; nd.a_c = (double)T(1); break;
-            case EML_OP_MUL_C: nd.a_const = true; nd.a_c = (double)c; break;
-            case EML_OP_DIV_C: nd.a_const = true; nd.a_c = (double)(T(1) / c); break;
-            default: break;
-        }
-        if (!nd.a_const) EML_TRY(new_buf(sizeof(T) * n, t->stream, &nd.a));
-        EML_TRY(launch_unary<T>(op, c, (const T*)x->numbers->p, (T*)y.numbers->p, nd.a ? (T*)nd.a->p : nullptr, n, t->stream));
-        t->len += n;
-        t->nodes.push_back(nd);
-        y.tracked = true;
-        y.node = (int)t->nodes.size() - 1;
-        y.epoch = t->epoch;
+        *out = put_value(t, std::move(y));
+        return EML_OK;
     }
+    Node nd;
+    nd.kind = Kind::UNARY;
+    nd.base = t->len;
+    nd.count = nd.n = n;
+    nd.p0 = nx;
+    nd.p0_tracked = true;
+    nd.op = op;
+    nd.c = cst;
+    // the same expressions as unary_rule (csrc/ew_rules.cuh), evaluated in T
+    const T c = (T)cst;
+    switch (nx >= 0 ? op : -1) {  // (a parent carrying Index 0 keeps the array: its sweep is a dot product)
+        case EML_OP_NEG: case EML_OP_C_SUB: nd.a_const = true; nd.a_c = (double)(-T(1)); break;
+        case EML_OP_ADD_C: case EML_OP_SUB_C: nd.a_const = true; nd.a_c = (double)T(1); break;
+        case EML_OP_MUL_C: nd.a_const = true; nd.a_c = (double)c; break;
+        case EML_OP_DIV_C: nd.a_const = true; nd.a_c = (double)(T(1) / c); break;
+        default: break;
+    }
+    if (t->fuse && nx >= 0) return append_lazy<T>(t, nd, x, nullptr, std::move(y), out);
+    // one kernel per node: value and derivative array now
+    EML_TRY(flush_open<T>(t));
+    EML_TRY(new_buf(sizeof(T) * n, t->stream, &y.numbers));
+    if (!nd.a_const) EML_TRY(new_buf(sizeof(T) * n, t->stream, &nd.a));
+    EML_TRY(launch_unary<T>(op, c, (const T*)x->numbers->p, (T*)y.numbers->p, nd.a ? (T*)nd.a->p : nullptr, n, t->stream));
+    t->len += n;
+    t->nodes.push_back(nd);
+    y.tracked = true;
+    y.node = (int)t->nodes.size() - 1;
+    y.epoch = t->epoch;
     *out = put_value(t, std::move(y));
     return EML_OK;
 }
@@ -312,6 +616,7 @@ int tape_binary(eml_tape* t, int op, eml_val hx, eml_val hy, eml_val* out) {
     Value *x, *y;
     EML_TRY(get_value(t, hx, &x));
     EML_TRY(get_value(t, hy, &y));
+    if (op < EML_OP_ADD || op > EML_OP_POW) EML_BAD_ARG("unknown binary op %d", op);
     if (x->rows != y->rows || x->cols != y->cols)
         EML_BAD_ARG("Record containers must have the same shape for a binary operation: (left: %lldx%lld, right: %lldx%lld)",
                     (long long)x->rows, (long long)x->cols, (long long)y->rows, (long long)y->cols);
@@ -325,35 +630,49 @@ int tape_binary(eml_tape* t, int op, eml_val hx, eml_val hy, eml_val* out) {
     z.rows = x->rows;
     z.cols = x->cols;
     const int64_t n = x->n();
-    EML_TRY(new_buf(sizeof(T) * n, t->stream, &z.numbers));
-    const T* xp = (const T*)x->numbers->p;
-    const T* yp = (const T*)y->numbers->p;
     if (!x->tracked && !y->tracked) {  // (None, None) reference mod.rs:984
-        EML_TRY(launch_binary<T>(op, xp, yp, (T*)z.numbers->p, (T*)nullptr, (T*)nullptr, n, t->stream));
-    } else {
-        Node nd;
-        nd.kind = Kind::BINARY;
-        nd.base = t->len;
-        nd.count = nd.n = n;
-        nd.p0 = nx;
-        nd.p1 = ny;
-        nd.p0_tracked = x->tracked;  // binary_x_history / binary_y_history / binary_both_history
-        nd.p1_tracked = y->tracked;
-        if ((op == EML_OP_ADD || op == EML_OP_SUB) && nd.p0_tracked && nx >= 0) nd.a_const = true, nd.a_c = 1.0;
-        if ((op == EML_OP_ADD || op == EML_OP_SUB) && nd.p1_tracked && ny >= 0)
-            nd.b_const = true, nd.b_c = op == EML_OP_ADD ? 1.0 : -1.0;
-        if (nd.p0_tracked && !nd.a_const) EML_TRY(new_buf(sizeof(T) * n, t->stream, &nd.a));
-        if (nd.p1_tracked && !nd.b_const) EML_TRY(new_buf(sizeof(T) * n, t->stream, &nd.b));
-        EML_TRY(launch_binary<T>(op, xp, yp, (T*)z.numbers->p, nd.a ? (T*)nd.a->p : nullptr,
-                                 nd.b ? (T*)nd.b->p : nullptr, n, t->stream));
-        t->len += n;
-        t->nodes.push_back(nd);
-        z.tracked = true;
-        z.node = (int)t->nodes.size() - 1;
-        z.epoch = t->epoch;
+        EML_TRY(new_buf(sizeof(T) * n, t->stream, &z.numbers));
+        EML_TRY(launch_binary<T>(op, (const T*)x->numbers->p, (const T*)y->numbers->p, (T*)z.numbers->p, (T*)nullptr,
+                                 (T*)nullptr, n, t->stream));
+        *out = put_value(t, std::move(z));
+        return EML_OK;
     }
+    Node nd;
+    nd.kind = Kind::BINARY;
+    nd.base = t->len;
+    nd.count = nd.n = n;
+    nd.p0 = nx;
+    nd.p1 = ny;
+    nd.p0_tracked = x->tracked;  // binary_x_history / binary_y_history / binary_both_history
+    nd.p1_tracked = y->tracked;
+    nd.op = op;
+    if ((op == EML_OP_ADD || op == EML_OP_SUB) && nd.p0_tracked && nx >= 0) nd.a_const = true, nd.a_c = 1.0;
+    if ((op == EML_OP_ADD || op == EML_OP_SUB) && nd.p1_tracked && ny >= 0)
+        nd.b_const = true, nd.b_c = op == EML_OP_ADD ? 1.0 : -1.0;
+    if (t->fuse && (!nd.p0_tracked || nx >= 0) && (!nd.p1_tracked || ny >= 0))
+        return append_lazy<T>(t, nd, x, y, std::move(z), out);
+    EML_TRY(flush_open<T>(t));
+    EML_TRY(new_buf(sizeof(T) * n, t->stream, &z.numbers));
+    if (nd.p0_tracked && !nd.a_const) EML_TRY(new_buf(sizeof(T) * n, t->stream, &nd.a));
+    if (nd.p1_tracked && !nd.b_const) EML_TRY(new_buf(sizeof(T) * n, t->stream, &nd.b));
+    EML_TRY(launch_binary<T>(op, (const T*)x->numbers->p, (const T*)y->numbers->p, (T*)z.numbers->p,
+                             nd.a ? (T*)nd.a->p : nullptr, nd.b ? (T*)nd.b->p : nullptr, n, t->stream));
+    t->len += n;
+    t->nodes.push_back(nd);
+    z.tracked = true;
+    z.node = (int)t->nodes.size() - 1;
+    z.epoch = t->epoch;
     *out = put_value(t, std::move(z));
     return EML_OK;
+}
+
+// Does the sweep of matmul node c WRITE (0 + sum, not +=) the derivatives of its parent `parent` when it is the first
+// to contribute to them?  True for the kernels that start their fma chain from +0 themselves: the thin (M <= 4)
+// backward, and dA = G * B^T through the short-contraction kernel.  (Such a parent needs no zero fill and is not read.)
+bool matmul_overwrites(const Node& c, int parent, size_t elem) {
+    if (c.p0 == c.p1) return false;
+    if (thin_shape(c.M, c.N, c.K)) return true;
+    return parent == c.p0 && smallk_shape(c.M, c.K, c.N, elem);
 }
 
 // The reverse sweep over macro nodes.
@@ -376,6 +695,7 @@ int tape_sweep(eml_tape* t, eml_val hv, int64_t row, int64_t col, eml_derivs** o
         set_error("the WengertList is empty: index out of bounds in the reference");
         return EML_ERR_STATE;
     }
+    EML_TRY(flush_open<T>(t));
     cudaStream_t st = t->stream;
     auto d = std::make_unique<eml_derivs>();
     d->tape = t;
@@ -385,6 +705,8 @@ int tape_sweep(eml_tape* t, eml_val hv, int64_t row, int64_t col, eml_derivs** o
     d->len = t->len;
     d->epoch = t->epoch;
     d->nodes = t->nodes;
+    d->groups = t->groups;
+    d->have.assign(t->nodes.size(), 1);
     // vec![0; len] (:627): one arena for every node's derivatives (+ the Index-0 slot), one memset
     d->grads.resize(t->nodes.size());
     std::vector<size_t> offs(t->nodes.size() + 1);
@@ -408,9 +730,18 @@ int tape_sweep(eml_tape* t, eml_val hv, int64_t row, int64_t col, eml_derivs** o
         if (uses1 && nd.p1 >= 0) first_consumer[nd.p1] = i;
     }
     std::vector<char> written(n_nodes, 0);
+    bool seed_in_kernel = false;
     for (int i = 0; i < n_nodes; i++) {
         const int c = first_consumer[i];
-        const bool overwritten_first = c >= 0 && t->nodes[c].kind != Kind::MATMUL && i != nv;
+        const int grp = t->nodes[i].group;
+        if (grp >= 0 && (c < 0 || t->nodes[c].group == grp)) {
+            // every contribution comes from inside its own fused group: that kernel starts it from zero (or the seed)
+            written[i] = 0;
+            if (i == nv) seed_in_kernel = true;
+            continue;
+        }
+        const bool overwritten_first = c >= 0 && i != nv &&
+                                       (t->nodes[c].kind != Kind::MATMUL || matmul_overwrites(t->nodes[c], i, sizeof(T)));
         written[i] = !overwritten_first;  // "written" = holds defined numbers (zeros) before the sweep
     }
     EML_CUDA(cudaMemsetAsync(arena->p, 0, 256, st));
@@ -429,7 +760,9 @@ int tape_sweep(eml_tape* t, eml_val hv, int64_t row, int64_t col, eml_derivs** o
     T* const slot0_ptr = static_cast<T*>(arena->p);
     bool slot0_used = false;
     // derivatives[self.index] = 1  (:630)
-    if (nv >= 0) {
+    if (nv >= 0 && seed_in_kernel) {
+        // the seed is an argument of the fused group's kernel
+    } else if (nv >= 0) {
         EML_TRY(launch_fill<T>((T*)d->grads[nv]->p + (row * v->cols + col), T(1), 1, st));
     } else {
         EML_TRY(launch_fill<T>(slot0_ptr, T(1), 1, st));
@@ -446,6 +779,12 @@ int tape_sweep(eml_tape* t, eml_val hv, int64_t row, int64_t col, eml_derivs** o
         const Node& nd = t->nodes[i];
         const T* g = (const T*)d->grads[i]->p;
         if (nd.kind == Kind::VARIABLES) continue;
+        if (nd.group >= 0) {  // the whole run [first, last] in one kernel
+            const Group& grp = t->groups[nd.group];
+            EML_TRY(group_backward<T>(t->nodes, grp, d->grads, written, d->have, nv, row * v->cols + col, false, st));
+            i = grp.first;
+            continue;
+        }
         if (nd.kind == Kind::UNARY) {
             const bool unit = !nd.a && !nd.a_const;  // the in-place SGD node of a recorded step: derivative 1
             if (nd.p0 >= 0)
@@ -478,20 +817,28 @@ int tape_sweep(eml_tape* t, eml_val hv, int64_t row, int64_t col, eml_derivs** o
             const int64_t M = nd.M, N = nd.N, K = nd.K;
             const T* A = (const T*)nd.a->p;
             const T* B = (const T*)nd.b->p;
+            if (thin_shape(M, N, K) && nd.p0 != nd.p1) {
+                // the whole node in one launch: both products and / or the constant-operand sums
+                T* dA = nd.p0 >= 0 ? (T*)d->grads[nd.p0]->p : nullptr;
+                T* dB = nd.p1 >= 0 ? (T*)d->grads[nd.p1]->p : nullptr;
+                const bool over_a = dA && !written[nd.p0], over_b = dB && !written[nd.p1];
+                if (dA) written[nd.p0] = 1;
+                if (dB) written[nd.p1] = 1;
+                EML_TRY(launch_thin_bwd<T>(g, A, B, M, N, K, dA, over_a, dB, over_b, nd.p0 < 0, nd.p1 < 0, slot0_ptr, st));
+                slot0_used |= nd.p0 < 0 || nd.p1 < 0;
+                continue;
+            }
             if (nd.p0 >= 0) {
                 GemmOptions ids;
                 ids.b_id = nd.b->identity;
+                const bool over = !written[nd.p0];  // only when matmul_overwrites() promised a kernel that starts from +0
+                written[nd.p0] = 1;
                 EML_TRY(contract_dev<T>(t->ctx, g, B, (T*)d->grads[nd.p0]->p, 1, M, K, N, Strides3{0, N, 1},
-                                        Strides3{0, 1, N}, Strides3{0, K, 1}, true, false, st, &ids));
+                                        Strides3{0, 1, N}, Strides3{0, K, 1}, !over, false, st, &ids));
             } else {
                 // every element of A carries Index 0: derivatives[0] += sum_ik (G B^T)[i,k]
                 //   = sum_j colsum(G)[j] * colsum(B)[j]
-                TempBuf cg, cb;
-                EML_TRY(cg.alloc(sizeof(T) * N, st));
-                EML_TRY(cb.alloc(sizeof(T) * N, st));
-                EML_TRY(launch_col_sums<T>(g, M, N, cg.as<T>(), st));
-                EML_TRY(launch_col_sums<T>(B, K, N, cb.as<T>(), st));
-                EML_TRY(launch_dot_accumulate<T>(t->ctx, cg.as<T>(), cb.as<T>(), N, slot0_ptr, true, st));
+                EML_TRY(launch_quirk_cols<T>(g, M, B, K, N, slot0_ptr, st));
                 slot0_used = true;
             }
             if (nd.p1 >= 0) {
@@ -501,12 +848,7 @@ int tape_sweep(eml_tape* t, eml_val hv, int64_t row, int64_t col, eml_derivs** o
                                         Strides3{0, N, 1}, Strides3{0, N, 1}, true, false, st, &ids));
             } else {
                 // derivatives[0] += sum_kj (A^T G)[k,j] = sum_i rowsum(A)[i] * rowsum(G)[i]
-                TempBuf ra, rg;
-                EML_TRY(ra.alloc(sizeof(T) * M, st));
-                EML_TRY(rg.alloc(sizeof(T) * M, st));
-                EML_TRY(launch_row_sums<T>(A, M, K, ra.as<T>(), st));
-                EML_TRY(launch_row_sums<T>(g, M, N, rg.as<T>(), st));
-                EML_TRY(launch_dot_accumulate<T>(t->ctx, ra.as<T>(), rg.as<T>(), M, slot0_ptr, true, st));
+                EML_TRY(launch_quirk_rows<T>(A, K, g, N, M, slot0_ptr, st));
                 slot0_used = true;
             }
         }
@@ -548,6 +890,7 @@ int eml_tape_create(int dtype, eml_tape** out) {
     t->device = ctx->device;
     t->ctx = ctx;
     t->stream = ctx->stream;
+    if (const char* e = getenv("EML_FUSE")) t->fuse = !(e[0] == '0');
     *out = t;
     return EML_OK;
 }
@@ -569,7 +912,9 @@ int eml_tape_len(eml_tape* t, int64_t* len) {
 int eml_tape_clear(eml_tape* t) {
     EML_TRY(check_tape(t));
     std::lock_guard<std::mutex> lock(t->mu);
+    EML_TRY(flush(t));  // containers created before the clear stay usable as numbers
     t->nodes.clear();
+    t->groups.clear();
     t->len = 0;
     t->epoch++;
     return EML_OK;
@@ -606,6 +951,7 @@ int eml_tape_reset(eml_tape* t, eml_val h) {
     Value* v;
     EML_TRY(get_value(t, h, &v));
     if (!v->tracked) return EML_OK;  // history None => noop (reference mod.rs:351)
+    EML_TRY(flush(t));
     Node nd;
     nd.kind = Kind::VARIABLES;
     nd.base = t->len;
@@ -622,6 +968,12 @@ int eml_val_release(eml_tape* t, eml_val h) {
     std::lock_guard<std::mutex> lock(t->mu);
     Value* v;
     EML_TRY(get_value(t, h, &v));
+    if (!v->numbers && t->open >= 0) {
+        // a container of the open group dropped before anybody needed its numbers: they will never be stored
+        Group& g = t->groups[t->open];
+        if (v->epoch == t->epoch && v->node >= g.first && v->node <= g.last && g.owner[v->node - g.first] == h)
+            g.owner[v->node - g.first] = -1;
+    }
     *v = Value();
     t->free_slots.push_back(h);
     return EML_OK;
@@ -644,6 +996,7 @@ int eml_val_numbers(eml_tape* t, eml_val h, void* host_out) {
     Value* v;
     EML_TRY(get_value(t, h, &v));
     EML_TRY(not_while_capturing(t, "eml_val_numbers"));
+    EML_TRY(flush(t));
     EML_CUDA(cudaMemcpyAsync(host_out, v->numbers->p, esize(t->dtype) * v->n(), cudaMemcpyDeviceToHost, t->stream));
     EML_CUDA(cudaStreamSynchronize(t->stream));
     return EML_OK;
@@ -655,6 +1008,7 @@ int eml_val_numbers_async(eml_tape* t, eml_val h, void* pinned_host_out, void** 
     std::lock_guard<std::mutex> lock(t->mu);
     Value* v;
     EML_TRY(get_value(t, h, &v));
+    EML_TRY(flush(t));
     EML_CUDA(cudaMemcpyAsync(pinned_host_out, v->numbers->p, esize(t->dtype) * v->n(), cudaMemcpyDeviceToHost, t->stream));
     if (arrival && t->capturing) {
         *arrival = nullptr;  // inside a recorded step the arrival comes from eml_graph_launch
@@ -679,6 +1033,10 @@ int eml_arrival_wait(void* arrival) {
 int eml_tape_sync(eml_tape* t) {
     EML_TRY(check_tape(t));
     EML_TRY(not_while_capturing(t, "eml_tape_sync"));
+    {
+        std::lock_guard<std::mutex> lock(t->mu);
+        EML_TRY(flush(t));
+    }
     EML_CUDA(cudaStreamSynchronize(t->stream));
     return EML_OK;
 }
@@ -690,6 +1048,7 @@ int eml_tape_capture_begin(eml_tape* t) {
         set_error("a step is already being captured on this tape");
         return EML_ERR_STATE;
     }
+    EML_TRY(flush(t));  // work requested before the recording is not part of it
     EML_CUDA(cudaStreamBeginCapture(t->stream, cudaStreamCaptureModeThreadLocal));
     t->capturing = true;
     t->capture_len = t->len;
@@ -707,11 +1066,16 @@ int eml_tape_capture_end(eml_tape* t, eml_graph** out) {
         set_error("no capture in progress on this tape");
         return EML_ERR_STATE;
     }
+    const int flushed = flush(t);  // work requested inside the recording belongs to it
     t->capturing = false;
     stream_alloc_forbid_new(false);
     pdl_suppress(false);
     cudaGraph_t graph = nullptr;
     cudaError_t e = cudaStreamEndCapture(t->stream, &graph);
+    if (flushed != EML_OK) {
+        if (graph) cudaGraphDestroy(graph);
+        return flushed;
+    }
     if (e != cudaSuccess || !graph) {
         cudaGetLastError();
         set_error("the step could not be captured: %s", cudaGetErrorString(e));
@@ -777,6 +1141,8 @@ int eml_val_device_ptr(eml_tape* t, eml_val h, void** dev) {
     std::lock_guard<std::mutex> lock(t->mu);
     Value* v;
     EML_TRY(get_value(t, h, &v));
+    EML_TRY(check_tape(t));
+    EML_TRY(flush(t));
     *dev = v->numbers->p;
     return EML_OK;
 }
@@ -820,6 +1186,16 @@ int eml_derivs_len(eml_derivs* d, int64_t* len) {
     return EML_OK;
 }
 
+// Derivatives of a node the sweep kept in registers only (interior of a fused elementwise group, no container held):
+// run the group's backward program once more, storing them (nothing else is touched).
+static int ensure_have(eml_derivs* d, int n) {
+    if (d->have[n]) return EML_OK;
+    const Group& g = d->groups[d->nodes[n].group];
+    std::vector<char> written(d->have);
+    if (d->dtype == EML_F32) return group_backward<float>(d->nodes, g, d->grads, written, d->have, -1, -1, true, d->stream);
+    return group_backward<double>(d->nodes, g, d->grads, written, d->have, -1, -1, true, d->stream);
+}
+
 static int derivs_not_while_capturing(eml_derivs* d) {
     if (d && d->tape && d->tape->capturing) {
         set_error("reading derivatives on the host blocks on the device and cannot be part of a recorded step");
@@ -835,6 +1211,7 @@ int eml_derivs_at(eml_derivs* d, int64_t index, double* out) {
     if (n < 0) EML_BAD_ARG("index out of bounds: the len is %lld but the index is %lld", (long long)d->len, (long long)index);
     int64_t e = d->nodes[n].element_of(index);
     EML_CUDA(cudaSetDevice(d->device));
+    EML_TRY(ensure_have(d, n));
     if (d->dtype == EML_F32) {
         float f;
         EML_CUDA(cudaMemcpyAsync(&f, (const float*)d->grads[n]->p + e, 4, cudaMemcpyDeviceToHost, d->stream));
@@ -862,6 +1239,7 @@ static int derivs_at_val(eml_derivs* d, eml_val h, void* dst, bool dst_on_device
     }
     cudaMemcpyKind kind = dst_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
     if (n >= 0) {
+        EML_TRY(ensure_have(d, n));
         EML_CUDA(cudaMemcpyAsync(dst, d->grads[n]->p, es * v->n(), kind, d->stream));
     } else {
         // every Index is 0: each element reads derivatives[0]
@@ -888,6 +1266,7 @@ int eml_derivs_to_host(eml_derivs* d, void* host_out) {
     std::vector<char> tmp;
     for (size_t i = 0; i < d->nodes.size(); i++) {
         const Node& nd = d->nodes[i];
+        EML_TRY(ensure_have(d, (int)i));
         tmp.resize(es * nd.n);
         EML_CUDA(cudaMemcpyAsync(tmp.data(), d->grads[i]->p, es * nd.n, cudaMemcpyDeviceToHost, d->stream));
         EML_CUDA(cudaStreamSynchronize(d->stream));
@@ -909,6 +1288,7 @@ int eml_tape_sgd_update(eml_tape* t, eml_val hw, eml_derivs* d, double lr) {
     std::lock_guard<std::mutex> lock(t->mu);
     Value* w;
     EML_TRY(get_value(t, hw, &w));
+    EML_TRY(flush(t));
     if (!w->tracked || w->node < 0 || w->epoch != t->epoch || d->epoch != t->epoch || w->node >= (int)d->nodes.size()) {
         set_error("sgd_update: container is not a tracked variable of the computation these derivatives belong to");
         return EML_ERR_STATE;
