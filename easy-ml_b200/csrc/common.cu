@@ -53,7 +53,15 @@ bool pdl_enabled() {
     }();
     return on && !t_pdl_suppressed;
 }
-void pdl_suppress(bool suppress) { t_pdl_suppressed = suppress; }
+void pdl_suppress(bool suppress) {
+    // EML_GRAPH_PDL=1: keep programmatic dependent launch inside recorded steps too (the capture turns the launch
+    // attribute into programmatic graph edges)
+    static const bool keep_in_graphs = [] {
+        const char* e = getenv("EML_GRAPH_PDL");
+        return e && e[0] == '1';
+    }();
+    t_pdl_suppressed = suppress && !keep_in_graphs;
+}
 
 int check_launch(const char* what) {
     cudaError_t e = cudaGetLastError();

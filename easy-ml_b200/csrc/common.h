@@ -247,6 +247,19 @@ int launch_sgd(T* w, const T* d, T lr, int64_t n, cudaStream_t stream);
 // out[i] = w[i] - lr * d[i] (the same update into a fresh container, one pass)
 template <class T>
 int launch_sgd_out(T* out, const T* w, const T* d, T lr, int64_t n, cudaStream_t stream);
+// several weight updates in one launch (a training step updates every layer's weights back to back)
+constexpr int SGD_BATCH_MAX = 8;
+struct SgdBatch {
+    int count = 0;
+    void* out[SGD_BATCH_MAX];
+    const void* w[SGD_BATCH_MAX];
+    const void* d[SGD_BATCH_MAX];
+    const void* slot0[SGD_BATCH_MAX];  // non-null: element 0's derivative still lacks the sum parked beside the arena
+    int64_t n[SGD_BATCH_MAX];
+    double lr[SGD_BATCH_MAX];
+};
+template <class T>
+int launch_sgd_batch(const SgdBatch& b, cudaStream_t stream);
 // out[i] = value (fill), used by the tape (seeding, zeroing is cudaMemsetAsync)
 template <class T>
 int launch_fill(T* out, T value, int64_t n, cudaStream_t stream);

@@ -409,6 +409,41 @@ int launch_axpy(T c, const T* a, const T* b, T* out, int64_t n, cudaStream_t str
 
 int stream_tickets(cudaStream_t stream, unsigned** out) { return ticket_counters(stream, out); }
 
+namespace {
+// out[i] = w[i] - (d[i] [+ slot0 for i == 0]) * lr for up to SGD_BATCH_MAX containers in one launch (blockIdx.y picks
+// the container); the same separately rounded operations as the single-container kernel (axpy_kernel MODE 1 / 4)
+template <class T>
+__global__ void __launch_bounds__(EW_THREADS) sgd_batch_kernel(const __grid_constant__ SgdBatch b) {
+    pdl_prologue();
+    const int y = blockIdx.y;
+    T* out = static_cast<T*>(b.out[y]);
+    const T* w = static_cast<const T*>(b.w[y]);
+    const T* d = static_cast<const T*>(b.d[y]);
+    const T lr = (T)b.lr[y];
+    const int64_t n = b.n[y];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        T g = d[i];
+        if (i == 0 && b.slot0[y]) g = g + static_cast<const T*>(b.slot0[y])[0];
+        out[i] = w[i] - g * lr;
+    }
+}
+}  // namespace
+
+template <class T>
+int launch_sgd_batch(const SgdBatch& b, cudaStream_t stream) {
+    if (b.count < 1) return EML_OK;
+    int64_t most = 0;
+    for (int y = 0; y < b.count; y++) most = b.n[y] > most ? b.n[y] : most;
+    int64_t blocks = (most + EW_THREADS - 1) / EW_THREADS;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    launch_k(sgd_batch_kernel<T>, dim3((unsigned)blocks, (unsigned)b.count), dim3(EW_THREADS), 0, stream, b);
+    count_launch();
+    return check_launch("sgd");
+}
+template int launch_sgd_batch<float>(const SgdBatch&, cudaStream_t);
+template int launch_sgd_batch<double>(const SgdBatch&, cudaStream_t);
+
 template <class T>
 int launch_unary(int op, T c, const T* x, T* y, T* dydx, int64_t n, cudaStream_t stream) {
     if (n <= 0) return EML_OK;

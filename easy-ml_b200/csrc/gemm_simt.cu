@@ -8,6 +8,8 @@
 // reference src/tensors/operations.rs:441-445): first product seeds the sum, then k ascending with a
 // separately rounded multiply and add -- no FMA.  k tiles are walked in ascending order, so the chain
 // per element is exactly the sequential one.
+#include <type_traits>
+
 #include "common.h"
 
 namespace eml {
@@ -290,9 +292,90 @@ gemm_skinny_tn_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __res
 }
 }  // namespace
 
+// The same product when one CTA can own EVERY output row (M <= 256 * TNW_MT): a CTA walks one k range, each thread
+// keeps TNW_MT rows x N accumulators, so a k row of A (M contiguous elements) is read once, by one CTA, with all of a
+// thread's loads of eight k rows in flight, and B's chunk is staged once per CTA (no barrier inside the k loop).
+namespace {
+constexpr int TNW_MT = 4, TNW_KC = 128;
+
+template <class T, int MT>
+__global__ void __launch_bounds__(TN_THREADS)
+gemm_tn_wide_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ ws, int64_t M, int N, int64_t K,
+                    int64_t a_k_stride, Strides3 sB, int64_t k_per_block) {
+    pdl_prologue();
+    __shared__ T sB_[TNW_KC][SK_NMAX];
+    const int64_t kb0 = (int64_t)blockIdx.x * k_per_block, kb1 = kb0 + k_per_block < K ? kb0 + k_per_block : K;
+    T acc[MT][SK_NMAX];
+#pragma unroll
+    for (int i = 0; i < MT; i++)
+#pragma unroll
+        for (int n = 0; n < SK_NMAX; n++) acc[i][n] = T(0);
+    for (int64_t k0 = kb0; k0 < kb1; k0 += TNW_KC) {
+        const int kc = (int)(kb1 - k0 < TNW_KC ? kb1 - k0 : TNW_KC);
+        __syncthreads();
+        for (int e = threadIdx.x; e < kc * N; e += TN_THREADS) {
+            const int k = e / N, n = e % N;
+            sB_[k][n] = B[(k0 + k) * sB.r + n * sB.c];
+        }
+        __syncthreads();
+        const T* a = A + k0 * a_k_stride + threadIdx.x;
+        for (int k = 0; k < kc; k += 8) {  // eight k rows in flight per thread; rows past the chunk read as zero
+            T av[8][MT];
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+#pragma unroll
+                for (int i = 0; i < MT; i++)
+                    av[j][i] = (k + j < kc && threadIdx.x + i * TN_THREADS < M) ? a[(k + j) * a_k_stride + i * TN_THREADS] : T(0);
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                if (k + j >= kc) break;
+#pragma unroll
+                for (int n = 0; n < SK_NMAX; n++)
+                    if (n < N) {
+                        const T b = sB_[k + j][n];
+#pragma unroll
+                        for (int i = 0; i < MT; i++) acc[i][n] = fma(av[j][i], b, acc[i][n]);
+                    }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < MT; i++) {
+        const int64_t m = threadIdx.x + i * TN_THREADS;
+        if (m < M) {
+            T* out = ws + ((int64_t)blockIdx.x * M + m) * N;
+#pragma unroll
+            for (int n = 0; n < SK_NMAX; n++)
+                if (n < N) out[n] = acc[i][n];
+        }
+    }
+}
+}  // namespace
+
 template <class T>
 int launch_gemm_skinny_tn(DeviceCtx* ctx, const T* A, const T* B, T* C, int64_t M, int64_t N, int64_t K, Strides3 sA,
                           Strides3 sB, Strides3 sC, bool accumulate, cudaStream_t stream) {
+    if (M <= (int64_t)TN_THREADS * TNW_MT) {
+        const int64_t sms = ctx ? ctx->sm_count : 148;
+        int64_t blocks = 2 * sms;  // two CTAs per SM (latency hiding); the partials (blocks x M x N) stay small
+        if (blocks > (K + 15) / 16) blocks = (K + 15) / 16;
+        if (blocks < 1) blocks = 1;
+        const int64_t k_per_block = (K + blocks - 1) / blocks;
+        blocks = (K + k_per_block - 1) / k_per_block;
+        TempBuf ws;
+        EML_TRY(ws.alloc(sizeof(T) * (size_t)(blocks * M * N), stream));
+        const int mt = (int)((M + TN_THREADS - 1) / TN_THREADS);
+        auto go = [&](auto kernel) {
+            launch_k(kernel, dim3((unsigned)blocks), dim3(TN_THREADS), 0, stream, A, B, ws.as<T>(), M, (int)N, K, sA.c, sB, k_per_block);
+        };
+        if (mt == 1) go(gemm_tn_wide_kernel<T, 1>);
+        else if (mt == 2) go(gemm_tn_wide_kernel<T, 2>);
+        else go(gemm_tn_wide_kernel<T, 4>);
+        count_launch();
+        set_last_kernel("skinny_tn");
+        EML_TRY(check_launch("gemm_tn_wide"));
+        return launch_splitk_reduce<T>(ws.as<T>(), (int)blocks, C, 1, M, N, sC, accumulate, stream);
+    }
     const int64_t m_blocks = (M + TN_THREADS - 1) / TN_THREADS;
     const int64_t sms = ctx ? ctx->sm_count : 148;
     int64_t chunks = (2 * sms + m_blocks - 1) / m_blocks;  // ~2 CTAs per SM
@@ -314,11 +397,104 @@ template int launch_gemm_skinny_tn<float>(DeviceCtx*, const float*, const float*
 template int launch_gemm_skinny_tn<double>(DeviceCtx*, const double*, const double*, double*, int64_t, int64_t, int64_t,
                                            Strides3, Strides3, Strides3, bool, cudaStream_t);
 
+// The common case of the skinny product -- one dense row-major B[K x N] small enough to live in L1, K a multiple of
+// 32 lanes x one 16-byte vector (an output layer: H[8192 x 512] * W2[512 x 10]).  A lane owns VEC consecutive k of
+// every 32 * VEC; the VEC rows of B it needs are VEC * N CONSECUTIVE numbers of the row-major B, i.e. N 16-byte loads
+// (served by L1: every warp reads the same 20 KB), kept in registers while the warp's ROWS rows of A stream by -- no
+// shared memory, no staging prologue, no index arithmetic in the loop.  N is a template parameter so that the
+// accumulators and B's slice are registers.  One fixed shuffle tree per output; deterministic.
+namespace {
+constexpr int SKR_ROWS = 4;
+
+template <class T, int N>
+__global__ void __launch_bounds__(SK_THREADS)
+gemm_skinny_rows_kernel(const T* __restrict__ A, const T* __restrict__ B, T* C, int64_t M, int K, int64_t lda, Strides3 sC,
+                        int accumulate) {
+    pdl_prologue();
+    constexpr int VEC = 16 / sizeof(T);
+    using V4 = typename std::conditional<sizeof(T) == 4, float4, double2>::type;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int steps = K / (32 * VEC);
+    const int64_t groups = (M + SKR_ROWS - 1) / SKR_ROWS;
+    for (int64_t grp = (int64_t)blockIdx.x * SK_WARPS + warp; grp < groups; grp += (int64_t)gridDim.x * SK_WARPS) {
+        const int64_t m0 = grp * SKR_ROWS;
+        T acc[SKR_ROWS][N];
+#pragma unroll
+        for (int r = 0; r < SKR_ROWS; r++)
+#pragma unroll
+            for (int n = 0; n < N; n++) acc[r][n] = T(0);
+        for (int s = 0; s < steps; s++) {
+            const int k0 = (s * 32 + lane) * VEC;
+            V4 av[SKR_ROWS];
+#pragma unroll
+            for (int r = 0; r < SKR_ROWS; r++)
+                if (m0 + r < M) av[r] = *reinterpret_cast<const V4*>(A + (m0 + r) * lda + k0);
+            V4 bv[N];  // B[k0 .. k0 + VEC)[0 .. N): VEC * N consecutive numbers
+            const V4* bp = reinterpret_cast<const V4*>(B + (int64_t)k0 * N);
+#pragma unroll
+            for (int q = 0; q < N; q++) bv[q] = __ldg(bp + q);
+            const T* be = reinterpret_cast<const T*>(bv);
+#pragma unroll
+            for (int r = 0; r < SKR_ROWS; r++) {
+                if (m0 + r >= M) break;
+                const T* ae = reinterpret_cast<const T*>(&av[r]);
+#pragma unroll
+                for (int v = 0; v < VEC; v++)
+#pragma unroll
+                    for (int n = 0; n < N; n++) acc[r][n] = fma(ae[v], be[v * N + n], acc[r][n]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < SKR_ROWS; r++)
+#pragma unroll
+            for (int n = 0; n < N; n++) {
+                T v = acc[r][n];
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+                if (lane == 0 && m0 + r < M) {
+                    T* p = C + (m0 + r) * sC.r + n * sC.c;
+                    *p = accumulate ? *p + v : v;
+                }
+            }
+    }
+}
+
+template <class T, int N>
+int launch_skinny_rows(const T* A, const T* B, T* C, int64_t M, int64_t K, int64_t lda, Strides3 sC, bool accumulate,
+                       cudaStream_t stream) {
+    int64_t blocks = ((M + SKR_ROWS - 1) / SKR_ROWS + SK_WARPS - 1) / SK_WARPS;
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    launch_k(gemm_skinny_rows_kernel<T, N>, dim3((unsigned)blocks), dim3(SK_THREADS), 0, stream, A, B, C, M, (int)K, lda, sC,
+             accumulate ? 1 : 0);
+    count_launch();
+    set_last_kernel("skinny_n");
+    return check_launch("gemm_skinny_rows");
+}
+}  // namespace
+
 template <class T>
 int launch_gemm_skinny(const T* A, const T* B, T* C, int64_t batch, int64_t M, int64_t N, int64_t K, Strides3 sA,
                        Strides3 sB, Strides3 sC, bool accumulate, cudaStream_t stream) {
+    constexpr int64_t VEC = 16 / sizeof(T);
+    if (batch == 1 && sA.c == 1 && sB.c == 1 && sB.r == N && K % (32 * VEC) == 0 && sA.r % VEC == 0 &&
+        (reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0 &&
+        K * N * (int64_t)sizeof(T) <= (int64_t(64) << 10)) {
+        switch (N) {
+#define EML_SKR(NN) \
+    case NN:        \
+        return launch_skinny_rows<T, NN>(A, B, C, M, K, sA.r, sC, accumulate, stream);
+            EML_SKR(1) EML_SKR(2) EML_SKR(3) EML_SKR(4) EML_SKR(5) EML_SKR(6) EML_SKR(7) EML_SKR(8) EML_SKR(9) EML_SKR(10)
+            EML_SKR(11) EML_SKR(12) EML_SKR(13) EML_SKR(14) EML_SKR(15) EML_SKR(16)
+#undef EML_SKR
+            default: break;
+        }
+    }
     int64_t blocks = ((M + SK_WARPS - 1) / SK_WARPS) * batch;
-    if (blocks > 148 * 6) blocks = 148 * 6;
+    // staging B costs a block as much as several rows of A: when it is staged once per block (K fits one chunk),
+    // fewer, longer-lived blocks win
+    const bool stage_once = K <= (int64_t)(2048 / sizeof(T)) && batch == 1;
+    const int64_t cap = stage_once ? 148 * 2 : 148 * 6;
+    if (blocks > cap) blocks = cap;
     launch_k(gemm_skinny_kernel<T>, dim3((unsigned)blocks), dim3(SK_THREADS), 0, stream, A, B, C, batch, M, (int)N, K, sA, sB, sC,
                                                                        accumulate ? 1 : 0);
     count_launch();
@@ -341,7 +517,14 @@ splitk_reduce_kernel(const T* __restrict__ ws, int splits, int64_t split_stride,
         int64_t b = i / (M * N), r = (i / N) % M, c = i % N;
         T* p = C + b * sC.b + r * sC.r + c * sC.c;
         T acc = accumulate ? *p : T(0);
-        for (int s = 0; s < splits; s++) acc += ws[(int64_t)s * split_stride + i];
+        for (int s = 0; s < splits; s += 8) {  // eight loads in flight, added in split order
+            T v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) v[u] = s + u < splits ? ws[(int64_t)(s + u) * split_stride + i] : T(0);
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+                if (s + u < splits) acc += v[u];
+        }
         *p = acc;
     }
 }
@@ -359,7 +542,13 @@ splitk_reduce_warp_kernel(const T* __restrict__ ws, int splits, int64_t split_st
     const int64_t total = batch * M * N;
     for (int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); i < total; i += (int64_t)gridDim.x * 8) {
         T acc = T(0);
-        for (int s = lane; s < splits; s += 32) acc += ws[(int64_t)s * split_stride + i];
+        for (int s = lane; s < splits; s += 32 * 8) {  // eight loads in flight per lane, added in split order
+            T v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) v[u] = s + 32 * u < splits ? ws[(int64_t)(s + 32 * u) * split_stride + i] : T(0);
+#pragma unroll
+            for (int u = 0; u < 8; u++) acc += v[u];
+        }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
         if (lane == 0) {
@@ -371,11 +560,67 @@ splitk_reduce_warp_kernel(const T* __restrict__ ws, int splits, int64_t split_st
 }
 }  // namespace
 
+namespace {
+// Few outputs, MANY splits (one partial per CTA of a k-parallel kernel: 5120 outputs x 296 partials): consecutive
+// threads take consecutive outputs (coalesced; one warp per output reads one useful number per 32-byte sector), a CTA
+// adds one contiguous range of splits in order, and the CTA that draws the last ticket of its output block adds the
+// ranges in order.  The ranges depend on the shape only: a fixed order.
+template <class T>
+__global__ void __launch_bounds__(256)
+splitk_reduce_2level_kernel(const T* __restrict__ ws, int splits, int per_range, int64_t total, T* part, unsigned* tickets,
+                            T* __restrict__ C, int64_t M, int64_t N, Strides3 sC, int accumulate) {
+    pdl_prologue();
+    __shared__ bool last;
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int s0 = blockIdx.y * per_range, s1 = s0 + per_range < splits ? s0 + per_range : splits;
+    if (i < total) {
+        T acc = T(0);
+        for (int s = s0; s < s1; s += 8) {
+            T v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) v[u] = s + u < s1 ? ws[(int64_t)(s + u) * total + i] : T(0);
+#pragma unroll
+            for (int u = 0; u < 8; u++) acc += v[u];
+        }
+        part[(int64_t)blockIdx.y * total + i] = acc;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicInc(tickets + blockIdx.x, gridDim.y - 1) == gridDim.y - 1;
+    __syncthreads();
+    if (!last || i >= total) return;
+    __threadfence();
+    T acc = T(0);
+    for (int r = 0; r < (int)gridDim.y; r += 8) {
+        T v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) v[u] = r + u < (int)gridDim.y ? __ldcg(part + (int64_t)(r + u) * total + i) : T(0);
+#pragma unroll
+        for (int u = 0; u < 8; u++) acc += v[u];
+    }
+    const int64_t b = i / (M * N), rr = (i / N) % M, c = i % N;
+    T* p = C + b * sC.b + rr * sC.r + c * sC.c;
+    *p = accumulate ? *p + acc : acc;
+}
+}  // namespace
+
 template <class T>
 int launch_splitk_reduce(const T* ws, int splits, T* C, int64_t batch, int64_t M, int64_t N, Strides3 sC,
                          bool accumulate, cudaStream_t stream) {
     int64_t total = batch * M * N;
     if (total == 0) return EML_OK;
+    if (total <= 65536 && splits >= 64 && (total + 255) / 256 <= 4096) {
+        const int ranges = 16, per_range = (splits + ranges - 1) / ranges;
+        const int used = (splits + per_range - 1) / per_range;
+        TempBuf part;
+        EML_TRY(part.alloc(sizeof(T) * (size_t)(used * total), stream));
+        unsigned* tickets = nullptr;
+        EML_TRY(stream_tickets(stream, &tickets));
+        launch_k(splitk_reduce_2level_kernel<T>, dim3((unsigned)((total + 255) / 256), (unsigned)used), dim3(256), 0, stream, ws,
+                 splits, per_range, total, part.as<T>(), tickets, C, M, N, sC, accumulate ? 1 : 0);
+        count_launch();
+        return check_launch("split-K reduce (two level)");
+    }
     if (total <= 8192 && splits >= 16) {
         int blocks = (int)((total + 7) / 8);
         launch_k(splitk_reduce_warp_kernel<T>, dim3(blocks), dim3(256), 0, stream, ws, splits, total, C, M, N, sC, batch, accumulate ? 1 : 0);

@@ -131,6 +131,11 @@ struct eml_derivs {
     // per node: its derivatives are in `grads`.  Interior nodes of a fused group are not stored by the sweep (nobody
     // holds a container for them); Derivatives::at(index) / Vec::from(Derivatives) materialise them on demand.
     std::vector<char> have;
+    // The reference's constant-operand sums belong to derivatives[0] (element 0 of the first node).  The sweep leaves
+    // them in the arena's first slot; they are added on first use (a host read) or on the fly by the weight update,
+    // which saves a launch per step.
+    Buf arena;
+    bool slot0_pending = false;
 };
 
 struct eml_graph {
@@ -152,6 +157,15 @@ struct eml_tape {
     std::vector<Node> nodes;
     std::vector<Group> groups;
     int open = -1;  // the group still accepting nodes (its containers have no numbers yet), or -1
+    // weight updates requested but not launched yet: consecutive eml_tape_sgd_update calls go out as ONE kernel
+    struct PendingSgd {
+        Buf out, w, arena;
+        const void* d;
+        const void* slot0;
+        int64_t n;
+        double lr;
+    };
+    std::vector<PendingSgd> sgd;
     bool fuse = true;  // EML_FUSE=0: one kernel per elementwise node (the comparison path of the parity tests)
     std::vector<Value> values;
     std::vector<eml_val> free_slots;
@@ -397,7 +411,32 @@ int group_backward(const std::vector<Node>& nodes, const Group& g, const std::ve
 
 // Gives every still-held container of the open group its numbers: one kernel for the whole run.
 template <class T>
+int flush_sgd(eml_tape* t) {
+    for (size_t i = 0; i < t->sgd.size(); i += SGD_BATCH_MAX) {
+        SgdBatch b;
+        for (size_t j = i; j < t->sgd.size() && j < i + SGD_BATCH_MAX; j++) {
+            const auto& u = t->sgd[j];
+            const int y = b.count++;
+            b.out[y] = u.out->p, b.w[y] = u.w->p, b.d[y] = u.d, b.slot0[y] = u.slot0, b.n[y] = u.n, b.lr[y] = u.lr;
+        }
+        EML_TRY(launch_sgd_batch<T>(b, t->stream));
+    }
+    t->sgd.clear();
+    return EML_OK;
+}
+
+template <class T>
+int flush_groups(eml_tape* t);
+
+template <class T>
 int flush_open(eml_tape* t) {
+    // (updates requested earlier come first: a group opened after them reads the updated weights)
+    if (!t->sgd.empty()) EML_TRY(flush_sgd<T>(t));
+    return flush_groups<T>(t);
+}
+
+template <class T>
+int flush_groups(eml_tape* t) {
     if (t->open < 0) return EML_OK;
     Group& g = t->groups[t->open];
     t->open = -1;
@@ -853,10 +892,9 @@ int tape_sweep(eml_tape* t, eml_val hv, int64_t row, int64_t col, eml_derivs** o
             }
         }
     }
-    if (slot0_used) {
-        // reference index 0 is element 0 of the first node
-        EML_TRY(launch_add_inplace<T>((T*)d->grads[0]->p, slot0_ptr, 1, st));
-    }
+    // reference index 0 is element 0 of the first node: added on first use (fold_slot0) or by the weight update
+    d->arena = arena;
+    d->slot0_pending = slot0_used;
     *out = d.release();
     return EML_OK;
 }
@@ -1196,6 +1234,14 @@ static int ensure_have(eml_derivs* d, int n) {
     return group_backward<double>(d->nodes, g, d->grads, written, d->have, -1, -1, true, d->stream);
 }
 
+static int fold_slot0(eml_derivs* d) {
+    if (!d->slot0_pending) return EML_OK;
+    EML_TRY(flush(d->tape));  // a queued weight update reads derivatives[0] and the parked sum separately
+    d->slot0_pending = false;
+    if (d->dtype == EML_F32) return launch_add_inplace<float>((float*)d->grads[0]->p, (const float*)d->arena->p, 1, d->stream);
+    return launch_add_inplace<double>((double*)d->grads[0]->p, (const double*)d->arena->p, 1, d->stream);
+}
+
 static int derivs_not_while_capturing(eml_derivs* d) {
     if (d && d->tape && d->tape->capturing) {
         set_error("reading derivatives on the host blocks on the device and cannot be part of a recorded step");
@@ -1211,6 +1257,7 @@ int eml_derivs_at(eml_derivs* d, int64_t index, double* out) {
     if (n < 0) EML_BAD_ARG("index out of bounds: the len is %lld but the index is %lld", (long long)d->len, (long long)index);
     int64_t e = d->nodes[n].element_of(index);
     EML_CUDA(cudaSetDevice(d->device));
+    EML_TRY(fold_slot0(d));
     EML_TRY(ensure_have(d, n));
     if (d->dtype == EML_F32) {
         float f;
@@ -1232,6 +1279,7 @@ static int derivs_at_val(eml_derivs* d, eml_val h, void* dst, bool dst_on_device
     Value* v;
     EML_TRY(get_value(t, h, &v));
     size_t es = esize(d->dtype);
+    EML_TRY(fold_slot0(d));
     int n = v->node;
     if (n >= 0 && (v->epoch != d->epoch || n >= (int)d->nodes.size())) {
         set_error("container does not belong to the computation these derivatives were taken from");
@@ -1262,6 +1310,10 @@ int eml_derivs_to_host(eml_derivs* d, void* host_out) {
     if (d->len > (int64_t(1) << 28))
         EML_BAD_ARG("derivs_to_host: the reference tape would have %lld entries; materialising it is refused", (long long)d->len);
     EML_CUDA(cudaSetDevice(d->device));
+    {
+        std::lock_guard<std::mutex> lock(d->tape->mu);
+        EML_TRY(fold_slot0(d));
+    }
     size_t es = esize(d->dtype);
     std::vector<char> tmp;
     for (size_t i = 0; i < d->nodes.size(); i++) {
@@ -1288,48 +1340,44 @@ int eml_tape_sgd_update(eml_tape* t, eml_val hw, eml_derivs* d, double lr) {
     std::lock_guard<std::mutex> lock(t->mu);
     Value* w;
     EML_TRY(get_value(t, hw, &w));
-    EML_TRY(flush(t));
+    // containers of the open group get their numbers now; updates already queued stay queued (they go out together)
+    // unless this one reads what one of them writes
+    bool chained = false;
+    for (const auto& u : t->sgd) chained |= w->numbers && u.out == w->numbers;
+    if (chained) EML_TRY(flush(t));
+    else EML_TRY(t->dtype == EML_F32 ? flush_groups<float>(t) : flush_groups<double>(t));
     if (!w->tracked || w->node < 0 || w->epoch != t->epoch || d->epoch != t->epoch || w->node >= (int)d->nodes.size()) {
         set_error("sgd_update: container is not a tracked variable of the computation these derivatives belong to");
         return EML_ERR_STATE;
     }
+    EML_TRY(ensure_have(d, w->node));
     const int64_t n = w->n();
     size_t es = esize(t->dtype);
-    if (t->capturing) {
-        // recorded step: the update happens in place, so a replay finds the weights where the last one left them
-        Node nd;
-        nd.kind = Kind::UNARY;
-        nd.base = t->len;
-        nd.count = nd.n = n;
-        nd.p0 = w->node;
-        nd.p0_tracked = true;
-        if (t->dtype == EML_F32)
-            EML_TRY(launch_sgd<float>((float*)w->numbers->p, (const float*)d->grads[w->node]->p, (float)lr, n, t->stream));
-        else
-            EML_TRY(launch_sgd<double>((double*)w->numbers->p, (const double*)d->grads[w->node]->p, lr, n, t->stream));
-        t->len += n;
-        t->nodes.push_back(nd);
-        w->node = (int)t->nodes.size() - 1;
-        return EML_OK;
-    }
-    // x - (derivatives[&x] * lr): a new container (the nodes that captured the old numbers keep them)
-    Buf fresh;
-    EML_TRY(new_buf(es * n, t->stream, &fresh));
+    // x - (derivatives[&x] * lr): Record - T => append_unary(x.index, 1) per element (nd.a stays null = derivative 1)
     Node nd;
-    nd.kind = Kind::UNARY;  // Record - T => append_unary(x.index, 1): nd.a stays null = derivative 1 everywhere
+    nd.kind = Kind::UNARY;
     nd.base = t->len;
     nd.count = nd.n = n;
     nd.p0 = w->node;
     nd.p0_tracked = true;
-    if (t->dtype == EML_F32)
-        EML_TRY(launch_sgd_out<float>((float*)fresh->p, (const float*)w->numbers->p,
-                                      (const float*)d->grads[w->node]->p, (float)lr, n, t->stream));
-    else
-        EML_TRY(launch_sgd_out<double>((double*)fresh->p, (const double*)w->numbers->p,
-                                       (const double*)d->grads[w->node]->p, lr, n, t->stream));
+    eml_tape::PendingSgd u;
+    u.w = w->numbers;
+    if (t->capturing) {
+        // recorded step: the update happens in place, so a replay finds the weights where the last one left them
+        u.out = w->numbers;
+    } else {
+        // eagerly: a new container (the nodes that captured the old numbers keep them)
+        EML_TRY(new_buf(es * n, t->stream, &u.out));
+    }
+    u.arena = d->arena;
+    u.d = d->grads[w->node]->p;
+    u.slot0 = (d->slot0_pending && w->node == 0) ? d->arena->p : nullptr;  // derivatives[0] + the parked sum, on the fly
+    u.n = n;
+    u.lr = lr;
+    w->numbers = u.out;
+    t->sgd.push_back(std::move(u));
     t->len += n;
     t->nodes.push_back(nd);
-    w->numbers = fresh;
     w->node = (int)t->nodes.size() - 1;
     return EML_OK;
 }

@@ -41,12 +41,36 @@ __device__ __forceinline__ T block_sum(T v, T* smem /* >= 8 */) {
 // true in every thread of exactly one block: the one that drew the last ticket (the counter resets itself)
 __device__ __forceinline__ bool last_block(unsigned* ticket, unsigned blocks) {
     __shared__ bool last;
+    if (blocks == 1) {  // nobody to wait for: no fence, no atomic round trip
+        __syncthreads();
+        return true;
+    }
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) last = atomicInc(ticket, blocks - 1) == blocks - 1;
     __syncthreads();
     if (last) __threadfence();
     return last;
+}
+
+// sum of X[r * stride + c] for r = first, first + step, ... < end, in that order.  Eight loads are issued before the
+// first add (out-of-range ones are replaced by +0): a loop with one dependent load per iteration pays the full memory
+// latency per element, which is what bounds these small reductions.
+template <class T>
+__device__ __forceinline__ T strided_sum(const T* __restrict__ X, int64_t first, int64_t end, int64_t step, int64_t stride,
+                                         int64_t c) {
+    T acc = T(0);
+    for (int64_t r = first; r < end; r += 8 * step) {
+        T v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int64_t rr = r + u * step;
+            v[u] = rr < end ? __ldcg(X + rr * stride + c) : T(0);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) acc += v[u];
+    }
+    return acc;
 }
 
 // partial[c] = sum over rows [r0, r1) of X[r * N + c] for all c < N; a block-wide, fixed-order column sum.
@@ -58,10 +82,7 @@ __device__ __forceinline__ void block_col_sums(const T* __restrict__ X, int64_t 
     if (N <= TK_THREADS) {
         const int L = TK_THREADS / (int)N, rl = t / (int)N, c = t % (int)N;
         T acc = T(0);
-        if (rl < L) {
-#pragma unroll 8
-            for (int64_t r = r0 + rl; r < r1; r += L) acc += X[r * N + c];
-        }
+        if (rl < L) acc = strided_sum<T>(X, r0 + rl, r1, L, N, c);
         __syncthreads();
         smem[t] = acc;
         __syncthreads();
@@ -71,12 +92,7 @@ __device__ __forceinline__ void block_col_sums(const T* __restrict__ X, int64_t 
             partial[t] = tot;
         }
     } else {
-        for (int64_t c = t; c < N; c += TK_THREADS) {
-            T acc = T(0);
-#pragma unroll 8
-            for (int64_t r = r0; r < r1; r++) acc += X[r * N + c];
-            partial[c] = acc;
-        }
+        for (int64_t c = t; c < N; c += TK_THREADS) partial[c] = strided_sum<T>(X, r0, r1, 1, N, c);
     }
 }
 
@@ -87,17 +103,7 @@ __device__ __forceinline__ T tile_col_sum(const T* __restrict__ X, int64_t r0, i
                                           T (*smem)[33]) {
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     T acc = T(0);
-    if (active) {
-        int64_t r = r0 + ty;
-        for (; r + 56 < r1; r += 64) {
-            T v[8];
-#pragma unroll
-            for (int u = 0; u < 8; u++) v[u] = X[(r + 8 * u) * N + c];
-#pragma unroll
-            for (int u = 0; u < 8; u++) acc += v[u];
-        }
-        for (; r < r1; r += 8) acc += X[r * N + c];
-    }
+    if (active) acc = strided_sum<T>(X, r0 + ty, r1, 8, N, c);
     __syncthreads();
     smem[ty][tx] = acc;
     __syncthreads();
@@ -138,11 +144,10 @@ quirk_cols_kernel(const T* __restrict__ G, int64_t gm, int64_t g_rows, const T* 
     __threadfence();
     // chunks in order (eight row lanes take every eighth chunk, then the lanes in order)
     T gs = T(0), bs = T(0);
-    if (active)
-        for (int i = ty; i < (int)gridDim.y; i += 8) {
-            gs += __ldcg(partial_g + (int64_t)i * N + c);
-            bs += __ldcg(partial_b + (int64_t)i * N + c);
-        }
+    if (active) {
+        gs = strided_sum<T>(partial_g, ty, gridDim.y, 8, N, c);
+        bs = strided_sum<T>(partial_b, ty, gridDim.y, 8, N, c);
+    }
     __syncthreads();
     smem[ty][tx] = gs;
     __syncthreads();
@@ -183,9 +188,7 @@ quirk_rows_kernel(const T* __restrict__ A, int64_t K, const T* __restrict__ G, i
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     T acc = T(0);
     for (int64_t i = (int64_t)blockIdx.x * 8 + w; i < M; i += (int64_t)gridDim.x * 8) {
-        T ra = T(0), rg = T(0);
-        for (int64_t k = lane; k < K; k += 32) ra += A[i * K + k];
-        for (int64_t j = lane; j < N; j += 32) rg += G[i * N + j];
+        T ra = strided_sum<T>(A + i * K, lane, K, 32, 1, 0), rg = strided_sum<T>(G + i * N, lane, N, 32, 1, 0);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             ra += __shfl_xor_sync(0xffffffffu, ra, o);
@@ -224,12 +227,20 @@ thin_fwd_kernel(const T* __restrict__ A, int64_t sAr, int64_t sAc, const T* __re
 #pragma unroll
     for (int i = 0; i < TH_M; i++) acc[i] = T(0);
     if (rl < L) {
-#pragma unroll 4
-        for (int64_t k = k0 + rl; k < k1; k += L) {
-            const T bv = B[k * N + c];
+        for (int64_t k = k0 + rl; k < k1; k += 4 * (int64_t)L) {  // four k per batch: all loads before the first fma
+            T bv[4], av[4][TH_M];
 #pragma unroll
-            for (int i = 0; i < TH_M; i++)
-                if (i < M) acc[i] = fma(A[i * sAr + k * sAc], bv, acc[i]);
+            for (int u = 0; u < 4; u++) {
+                const int64_t kk = k + (int64_t)u * L;
+                bv[u] = kk < k1 ? B[kk * N + c] : T(0);
+#pragma unroll
+                for (int i = 0; i < TH_M; i++) av[u][i] = (i < M && kk < k1) ? A[i * sAr + kk * sAc] : T(0);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+#pragma unroll
+                for (int i = 0; i < TH_M; i++)
+                    if (i < M) acc[i] = fma(av[u][i], bv[u], acc[i]);
         }
     }
 #pragma unroll
@@ -283,13 +294,13 @@ thin_bwd_kernel(const T* __restrict__ G, const T* __restrict__ A, const T* __res
             }
     }
     if (dB) {
-        const int64_t lo = k0 * N, hi = k1 * N;
-        for (int64_t e = lo + t; e < hi; e += TK_THREADS) {
-            const int64_t k = e / N;
-            const int j = (int)(e % N);
-            T acc = over_b ? T(0) : dB[e];
+        const int span = (int)((k1 - k0) * N);  // <= k_per_block * 256
+        for (int e = t; e < span; e += TK_THREADS) {
+            const int64_t k = k0 + e / N;
+            const int j = e % N;
+            T acc = over_b ? T(0) : dB[k0 * N + e];
             for (int i = 0; i < M; i++) acc = fma(A[i * K + k], sG[i * N + j], acc);
-            dB[e] = acc;
+            dB[k0 * N + e] = acc;
         }
     }
     if (!quirk_a && !quirk_b) return;
@@ -349,9 +360,17 @@ gemm_smallk_kernel(const T* __restrict__ A, int64_t lda, const T* __restrict__ B
         }
     }
     __syncthreads();
-    const int64_t nv = N / V, total = M * nv;
-    for (int64_t v = (int64_t)blockIdx.x * TK_THREADS + threadIdx.x; v < total; v += (int64_t)gridDim.x * TK_THREADS) {
-        const int64_t m = v / nv, n = (v % nv) * V;
+    // a block takes `rows_per_pass` whole rows per pass when a row has at most 256 vectors (no division in the loop);
+    // wider rows: one row per pass, threads stride over its vectors
+    const int nv = (int)(N / V);
+    const int rows_per_pass = nv <= TK_THREADS ? TK_THREADS / nv : 1;
+    const int my_row = nv <= TK_THREADS ? (int)threadIdx.x / nv : 0;
+    const int my_first = nv <= TK_THREADS ? (int)threadIdx.x % nv : (int)threadIdx.x;
+    const bool idle = nv <= TK_THREADS && my_row >= rows_per_pass;
+    for (int64_t m0 = (int64_t)blockIdx.x * rows_per_pass; m0 < M && !idle; m0 += (int64_t)gridDim.x * rows_per_pass)
+    for (int vi = my_first; vi < nv; vi += TK_THREADS) {
+        const int64_t m = m0 + my_row, n = (int64_t)vi * V;
+        if (m >= M) break;
         T acc[V];
         T* cp = C + m * ldc + n;
         if (accumulate) {
@@ -403,8 +422,9 @@ int launch_quirk_cols(const T* G, int64_t gm, const T* B, int64_t bm, int64_t N,
     if (col_blocks > 4095) EML_BAD_ARG("constant-operand sums: more than %d columns", 4095 * 32);
     // row chunks: ~2 CTAs per SM over the whole grid, at least 64 rows of the taller matrix each
     const int64_t rows = gm > bm ? gm : bm;
-    int64_t chunks = (2 * 148 + col_blocks - 1) / col_blocks;
+    int64_t chunks = (4 * 148 + col_blocks - 1) / col_blocks;  // short chunks: a few batches of loads per thread
     if (chunks > (rows + 63) / 64) chunks = (rows + 63) / 64;
+    if (chunks > 256) chunks = 256;
     if (chunks < 1) chunks = 1;
     const int64_t g_rows = (gm + chunks - 1) / chunks, b_rows = (bm + chunks - 1) / chunks;
     TempBuf partial;
@@ -478,6 +498,76 @@ int launch_thin_bwd(const T* G, const T* A, const T* B, int64_t M, int64_t N, in
     return check_launch("thin product backward");
 }
 
+namespace {
+// The same product with this thread's slice of B (KT x V numbers) held in REGISTERS: a thread owns one 16-byte vector
+// of output columns and walks down the rows, so per output vector it issues K broadcast loads of A, K * V fmas and one
+// 16-byte store -- no shared-memory traffic, no index arithmetic in the loop.  K <= KT <= 16.
+template <class T, int V, int KT>
+__global__ void __launch_bounds__(TK_THREADS)
+gemm_smallk_reg_kernel(const T* __restrict__ A, int64_t lda, const T* __restrict__ B, int64_t sBr, int64_t sBc, T* __restrict__ C,
+                       int64_t ldc, int64_t M, int64_t N, int K, int accumulate) {
+    pdl_prologue();
+    using V4 = typename std::conditional<sizeof(T) == 4, float4, double2>::type;
+    const int nv = (int)(N / V);                       // vectors per row (<= 256)
+    const int lanes = TK_THREADS / nv;                 // rows a CTA handles per pass
+    const int my_row = (int)threadIdx.x / nv, my_vec = (int)threadIdx.x % nv;
+    extern __shared__ __align__(16) unsigned char smk_raw[];
+    T* sB = reinterpret_cast<T*>(smk_raw);
+    // B(k, n) = B[k + n * K] (a row-major [N][K] matrix read transposed: dH = dY * W2^T): copied as it lies, with
+    // 16-byte loads and no index arithmetic; a thread's K x V slice is then V * K consecutive numbers
+    const int total_b = K * (int)N;
+    for (int e0 = 0; e0 < total_b; e0 += 4 * TK_THREADS) {
+        T v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int e = e0 + u * TK_THREADS + (int)threadIdx.x;
+            v[u] = e < total_b ? B[e] : T(0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int e = e0 + u * TK_THREADS + (int)threadIdx.x;
+            if (e < total_b) sB[e] = v[u];
+        }
+    }
+    __syncthreads();
+    if (my_row >= lanes) return;
+    const int64_t n = (int64_t)my_vec * V;
+    T b[KT][V];
+#pragma unroll
+    for (int k = 0; k < KT; k++)
+#pragma unroll
+        for (int j = 0; j < V; j++) b[k][j] = k < K ? sB[((int)n + j) * K + k] : T(0);
+    for (int64_t m = (int64_t)blockIdx.x * lanes + my_row; m < M; m += (int64_t)gridDim.x * lanes) {
+        const T* a = A + m * lda;
+        T* cp = C + m * ldc + n;
+        T av[KT];
+#pragma unroll
+        for (int k = 0; k < KT; k++) av[k] = k < K ? __ldg(a + k) : T(0);
+        T acc[V];
+        if (accumulate) {
+            const V4 c4 = *reinterpret_cast<const V4*>(cp);
+            const T* ce = reinterpret_cast<const T*>(&c4);
+#pragma unroll
+            for (int j = 0; j < V; j++) acc[j] = ce[j];
+        } else {
+#pragma unroll
+            for (int j = 0; j < V; j++) acc[j] = T(0);
+        }
+#pragma unroll
+        for (int k = 0; k < KT; k++)
+            if (k < K) {
+#pragma unroll
+                for (int j = 0; j < V; j++) acc[j] = fma(av[k], b[k][j], acc[j]);
+            }
+        V4 o4;
+        T* oe = reinterpret_cast<T*>(&o4);
+#pragma unroll
+        for (int j = 0; j < V; j++) oe[j] = acc[j];
+        *reinterpret_cast<V4*>(cp) = o4;
+    }
+}
+}  // namespace
+
 bool smallk_shape(int64_t M, int64_t N, int64_t K, size_t elem) {
     return K >= 1 && K <= SMK_MAX_K && N >= 64 && M >= 64 && (size_t)(K * N) * elem <= (size_t(48) << 10);
 }
@@ -490,7 +580,22 @@ int launch_gemm_smallk(const T* A, int64_t lda, const T* B, int64_t sBr, int64_t
     const int64_t total = vec ? M * (N / VN) : M * N;
     int64_t blocks = (total + TK_THREADS - 1) / TK_THREADS;
     if (blocks > 148 * 4) blocks = 148 * 4;  // persistent: B is staged once per block
+    if (blocks > M) blocks = M;
     const size_t smem = sizeof(T) * (size_t)(K * N);
+    if (vec && K <= 16 && N / VN <= TK_THREADS && sBr == 1 && sBc == K) {
+        const int64_t lanes = TK_THREADS / (N / VN);
+        int64_t rb = (M + lanes - 1) / lanes;
+        if (rb > 148 * 2) rb = 148 * 2;  // persistent: B is staged once per CTA
+        if (K <= 8)
+            launch_k(gemm_smallk_reg_kernel<T, VN, 8>, dim3((unsigned)rb), dim3(TK_THREADS), smem, stream, A, lda, B, sBr, sBc, C, ldc, M,
+                     N, (int)K, accumulate ? 1 : 0);
+        else
+            launch_k(gemm_smallk_reg_kernel<T, VN, 16>, dim3((unsigned)rb), dim3(TK_THREADS), smem, stream, A, lda, B, sBr, sBc, C, ldc,
+                     M, N, (int)K, accumulate ? 1 : 0);
+        count_launch();
+        set_last_kernel("small_k");
+        return check_launch("short-contraction product");
+    }
     if (vec)
         launch_k(gemm_smallk_kernel<T, VN>, dim3((unsigned)blocks), dim3(TK_THREADS), smem, stream, A, lda, B, sBr, sBc, C, ldc, M, N,
                  (int)K, accumulate ? 1 : 0);
