@@ -60,6 +60,8 @@ SIGNATURES = {
     "eml_upload": (cint, [vp, vp, C.c_size_t]),
     "eml_download": (cint, [vp, vp, C.c_size_t]),
     "eml_sync": (cint, []),
+    "eml_gemm_f64_sharded": (cint, [cint, vp, vp, vp, i64, i64, i64, i64, i64, i64]),
+    "eml_gemm_f32_sharded": (cint, [cint, vp, vp, vp, i64, i64, i64, i64, i64, i64]),
     "eml_gemm_f64_scatter_dev": (cint, [vp, vp, vp, i64, i64, i64, i64, i64, i64, cint, C.POINTER(vp), cint, vp]),
     "eml_gemm_f64_sliced_dev": (cint, [vp, vp, vp, i64, i64, i64, i64, i64, i64, cint, C.POINTER(cint), vp]),
     "eml_ipc_export": (cint, [vp, vp]),

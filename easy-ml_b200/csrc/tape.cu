@@ -1174,7 +1174,7 @@ int eml_val_indexes(eml_tape* t, eml_val h, int64_t* host_out) {
     return EML_OK;
 }
 
-int eml_val_device_ptr(eml_tape* t, eml_val h, void** dev) {
+int eml_val_device_ptr(eml_tape* t, eml_val h, const void** dev) {
     if (!t || !dev) EML_BAD_ARG("null argument");
     std::lock_guard<std::mutex> lock(t->mu);
     Value* v;

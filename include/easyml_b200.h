@@ -94,6 +94,19 @@ int eml_gemm_f32(const float* A, const float* B, float* C, int64_t M, int64_t N,
 int eml_gemm_f64(const double* A, const double* B, double* C, int64_t M, int64_t N, int64_t K, int64_t lda,
                  int64_t ldb, int64_t ldc);
 
+/* The same product over the first n_gpus GPUs of this box, one call from one host thread (BASELINE config 5: f64
+ * 32768 x 32768 on 2 / 4 / 8 B200).  Replaces, for large operands, matrix_view_multiplication
+ * src/matrices/operations.rs:165-196: rows of C are independent (:187-194), so A and C are cut into contiguous row
+ * slabs, one per GPU, and B is needed everywhere.  Every GPU uploads its own slab of A and 1 / n_gpus of B over its own
+ * PCIe link; the pieces of B are exchanged GPU to GPU over NVLink (copy engines) in K panels, each panel's product
+ * starting as soon as its pieces are in; finished row panels of C are downloaded while the next one is multiplied.  No
+ * cross-GPU reduction: the result carries the bits of eml_gemm_* on one GPU.  Host pointers (pageable or page-locked),
+ * blocking.  EML_ERR_BAD_ARG when n_gpus exceeds the number of CUDA devices. */
+int eml_gemm_f64_sharded(int n_gpus, const double* A, const double* B, double* C, int64_t M, int64_t N, int64_t K,
+                         int64_t lda, int64_t ldb, int64_t ldc);
+int eml_gemm_f32_sharded(int n_gpus, const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K,
+                         int64_t lda, int64_t ldb, int64_t ldc);
+
 /* Strided-batched contraction  C[b,m,n] = sum_k A[b,m,k] * B[b,k,n].
  * sA = element strides of A for (batch, m, k); sB for (batch, k, n); sC for (batch, m, n).
  * Replaces Einsum2::to, src/tensors/einsum.rs:908-980, for every name pattern that classifies into
@@ -311,7 +324,11 @@ int eml_val_numbers_async(eml_tape* t, eml_val v, void* pinned_host_out, void** 
 /* Blocks until the copy that produced `arrival` has landed, then releases the handle. */
 int eml_arrival_wait(void* arrival);
 int eml_tape_sync(eml_tape* t);
-int eml_val_device_ptr(eml_tape* t, eml_val v, void** dev_numbers); /* borrowed; valid until release */
+/* Borrowed pointer to v's numbers on the device: valid until v is released, and READ-ONLY -- containers are immutable
+ * (operators and the weight update produce fresh ones) and a constant's split / packed TF32 planes are cached under
+ * its identity, so writing through this pointer would leave later products on stale planes.  New input data for a
+ * recorded step goes through eml_tape_constants_dev. */
+int eml_val_device_ptr(eml_tape* t, eml_val v, const void** dev_numbers);
 
 /* record_tensor_matrix_multiply / record_matrix_matrix_multiply,
  * container_operations.rs:1318-1381,:1494-1531 (+ the 8 Mul impls): c = a * b. */
