@@ -122,27 +122,44 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_block_sample(a_host, b_host, budget_s, threads):
-    """Times the oracle's Matrix::mul restatement on a block C[0:rows, 0:cols] of the SAME product (every element of
-    C costs the same 2K flop; B keeps its full width, so the reference's strided column walk is preserved), sized
-    for about `budget_s` seconds.  Returns (tflops, rows, cols, seconds)."""
+CPU_ROWS_PER_THREAD, CPU_COLS = 32, 512
+
+
+def cpu_block_shape(n, threads):
+    """The block of C both arms time: 32 rows per host thread x 512 columns of the SAME product (every element of C
+    costs the same 2K flop; B keeps its full width, so the reference's strided column walk is preserved).  One shape,
+    a function of (n, threads) only -- round 1 let each arm size its own block and the two figures differed 2.3x."""
+    return CPU_ROWS_PER_THREAD * threads, min(n, CPU_COLS)
+
+
+def cpu_block_run(a_host, b_host, threads, reps=1):
+    """Seconds per pass (mean over `reps`) of the oracle's Matrix::mul restatement on the block for `threads` threads."""
     import oracle
 
-    n = b_host.shape[1]
+    rows, cols = cpu_block_shape(b_host.shape[1], threads)
+    rows = min(rows, a_host.shape[0])
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        oracle.matrix_mul_block(a_host, b_host, (0, rows), (0, cols), threads=threads)
+    return (time.perf_counter() - t0) / reps, rows, cols
+
+
+def cpu_baseline(a_host, b_host):
+    """cpu_baseline of the JSON line: the reference algorithm on ONE core (the reference is single-threaded: the
+    primary figure of SURVEY.md 8d) and on all host threads (what the reference arm runs; rows are independent, so an
+    OpenMP-style row split leaves the bits unchanged)."""
     k = a_host.shape[1]
-    rows = min(a_host.shape[0], threads)
-    cols = min(n, 64)
-    t0 = time.perf_counter()
-    oracle.matrix_mul_block(a_host, b_host, (0, rows), (0, cols), threads=threads)
-    t1 = max(time.perf_counter() - t0, 1e-4)
-    elems = rows * cols * budget_s / t1                      # elements of C that fit the budget
-    cols = int(max(64, min(n, elems // rows // 64 * 64)))
-    if cols == n:
-        rows = int(max(rows, min(a_host.shape[0], elems // n)))
-    t0 = time.perf_counter()
-    oracle.matrix_mul_block(a_host, b_host, (0, rows), (0, cols), threads=threads)
-    dt = time.perf_counter() - t0
-    return 2.0 * rows * cols * k / dt / 1e12, rows, cols, dt
+    threads = os.cpu_count() or 1
+    cpu_block_run(a_host, b_host, threads)  # warm: page in B, spin up the pool
+    dt_all, rows, cols = cpu_block_run(a_host, b_host, threads, reps=2)
+    dt_one, rows1, cols1 = cpu_block_run(a_host, b_host, 1, reps=2)
+    all_tf = 2.0 * rows * cols * k / dt_all / 1e12
+    one_tf = 2.0 * rows1 * cols1 * k / dt_one / 1e12
+    return {"value": all_tf, "unit": "TFLOP/s", "cores": threads, "kind": "port",
+            "sample": f"block C[0:{rows}, 0:{cols}] of the same product, {dt_all:.2f} s per pass ({CPU_ROWS_PER_THREAD} rows per "
+                      f"thread x {cols} columns: the shape the reference arm times too); every element of C costs the same 2K flop",
+            "one_core": {"value": one_tf, "unit": "TFLOP/s", "cores": 1,
+                         "sample": f"block C[0:{rows1}, 0:{cols1}], {dt_one:.2f} s per pass; the reference itself is single-threaded"}}
 
 
 def run_reference(args):
@@ -159,19 +176,15 @@ def run_reference(args):
     threads = os.cpu_count() or 1
     rng = np.random.default_rng(0x5EED0002)
     b = rng.uniform(-1, 1, (n, n))
-    a = rng.uniform(-1, 1, (max(threads, 64), n))
-    total_steps = args.steps + args.warmup
-    per_step = max(1.0, min(10.0, 90.0 / total_steps))     # the whole run stays within a few minutes
-    _, rows, cols, _ = cpu_block_sample(a, b, per_step, threads)
+    rows, cols = cpu_block_shape(n, threads)
+    a = rng.uniform(-1, 1, (rows, n))
     for _ in range(args.warmup):
-        oracle.matrix_mul_block(a, b, (0, rows), (0, cols), threads=threads)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        oracle.matrix_mul_block(a, b, (0, rows), (0, cols), threads=threads)
-    dt = (time.perf_counter() - t0) / args.steps
+        cpu_block_run(a, b, threads)
+    dt, rows, cols = cpu_block_run(a, b, threads, reps=args.steps)
     tflops = 2.0 * rows * cols * n / dt / 1e12
-    sample = (f"block C[0:{rows}, 0:{cols}] of the {n}x{n} product per step (every element costs the same 2K flop); "
-              f"the full product extrapolates to {dt * n * n / (rows * cols):.0f} s")
+    sample = (f"block C[0:{rows}, 0:{cols}] of the {n}x{n} product per step ({CPU_ROWS_PER_THREAD} rows per thread x {cols} "
+              f"columns, the shape cpu_baseline of the other arm times too; every element costs the same 2K flop); the "
+              f"full product extrapolates to {dt * n * n / (rows * cols):.0f} s")
     line = {
         "impl": "reference", "metric": "f64 matmul throughput", "value": tflops, "unit": "TFLOP/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
@@ -334,32 +347,38 @@ def main():
             torch.cuda.synchronize()
             digests.add(hashlib.sha256(Cm[:256].cpu().numpy().tobytes()).hexdigest())
 
-        # e2e: host-pointer C ABI, pinned host buffers, copies inside the timed region
+        # e2e: the host-pointer C ABI with the copies inside the timed region, over `--steps` calls after one warm call.
+        # The drop-in's operands are Rust Vec<T>s, i.e. PAGEABLE memory: that is the headline e2e; page-locked caller
+        # buffers (eml_host_alloc, what a shim backing Matrix storage with pinned memory would pass) are beside it.
+        def e2e_measure(Ah, Bh, Ch):
+            def call():
+                check(lib.eml_gemm_f64(vp(Ah), vp(Bh), vp(Ch), n, n, n, n, n, n))
+
+            call()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                call()
+            torch.cuda.synchronize()
+            ms_ = (time.perf_counter() - t0) / args.steps * 1e3
+            ok = bool(torch.equal(Ch[:64], Cm[:64].cpu()))
+            if args.f64_path == "sliced":  # the host entry stays on the FP64 kernel: agreement within the contract, not in bits
+                bound = 1e-12 * (Ah[:64].abs().double() @ Bh.abs().double())
+                ok = bool(((Ch[:64] - Cm[:64].cpu()).abs() <= 2 * bound).all())
+            return ms_, ok
+
         Ah = torch.empty((n, n), dtype=f64, pin_memory=True)
         Bh = torch.empty((n, n), dtype=f64, pin_memory=True)
         Ch = torch.empty((n, n), dtype=f64, pin_memory=True)
         Ah.copy_(A)
         Bh.copy_(B)
         torch.cuda.synchronize()
-
-        def e2e_step():
-            check(lib.eml_gemm_f64(vp(Ah), vp(Bh), vp(Ch), n, n, n, n, n, n))
-
-        e2e_steps = max(2, min(args.steps, 3))
-        e2e_step()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            e2e_step()
-        torch.cuda.synchronize()
-        e2e_ms = (time.perf_counter() - t0) / e2e_steps * 1e3
-        e2e_ok = bool(torch.equal(Ch[:64], Cm[:64].cpu()))
-        if args.f64_path == "sliced":  # the host entry stays on the FP64 kernel: agreement is within the contract, not in bits
-            bound = 1e-12 * (Ah[:64].abs().double() @ Bh.abs().double())
-            e2e_ok = bool(((Ch[:64] - Cm[:64].cpu()).abs() <= 2 * bound).all())
-
-        threads = os.cpu_count() or 1
-        cpu_tf, cpu_rows, cpu_cols, cpu_s = cpu_block_sample(Ah.numpy(), Bh.numpy(), 12.0, threads)
+        pinned_ms, pinned_ok = e2e_measure(Ah, Bh, Ch)
+        Ap, Bp = Ah.numpy().copy(), Bh.numpy().copy()          # ordinary (pageable) host memory
+        Cp = np.empty((n, n))
+        e2e_ms, e2e_ok = e2e_measure(torch.from_numpy(Ap), torch.from_numpy(Bp), torch.from_numpy(Cp))
+        e2e_ok = e2e_ok and pinned_ok
+        del Ap, Bp, Cp
 
         out = {
             "metric": "f64 matmul throughput", "value": value, "unit": "TFLOP/s", "n_gpus": 1, "steps": args.steps,
@@ -367,7 +386,12 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(n, 1),
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": flop / (e2e_ms * 1e-3) / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": 2 * n * n * 8,
-                    "d2h_bytes_per_step": n * n * 8, "ms_per_step": e2e_ms, "matches_device_result": e2e_ok},
+                    "d2h_bytes_per_step": n * n * 8, "ms_per_step": e2e_ms, "matches_device_result": e2e_ok,
+                    "host_memory": "pageable (what the reference API's Vec<T> is): staged through page-locked slots by a copy "
+                                   "thread pool, overlapped with the product",
+                    "calls_timed": args.steps,
+                    "page_locked": {"value": flop / (pinned_ms * 1e-3) / 1e12, "ms_per_step": pinned_ms,
+                                    "host_memory": "page-locked caller buffers: direct DMA"}},
             "roofline": {"bound": "tensor", "kernel": kernel_name, "achieved": achieved, "peak": fp64_peak,
                          "unit": "TFLOP/s", "frac": achieved / fp64_peak, "nominal_peak": NOMINAL_FP64_TFLOPS,
                          "frac_of_nominal": achieved / NOMINAL_FP64_TFLOPS,
@@ -379,9 +403,7 @@ def main():
                          "cublas_dgemm_tflops_same_run": cublas_tf, "frac_of_cublas": achieved / cublas_tf,
                          "kernel_ms": kernel_ms, "algorithmic_flop_per_launch": flop,
                          "algorithmic_bytes_per_launch": 3 * n * n * 8},
-            "cpu_baseline": {"value": cpu_tf, "unit": "TFLOP/s", "cores": threads, "kind": "port",
-                             "sample": f"block C[0:{cpu_rows}, 0:{cpu_cols}] of the same product ({cpu_s:.1f} s); every "
-                                       "element of C costs the same 2K flop"},
+            "cpu_baseline": cpu_baseline(Ah.numpy(), Bh.numpy()),
             "parity": {"max_rel_diff_vs_cublas": max_rel, "bit_identical_runs": len(digests) == 1},
         }
         if args.f64_path == "sliced":
@@ -933,17 +955,100 @@ def sharded(args, torch, dist, eml, lib, check, dev, stream, sp, rank, world, ti
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         gather_check = bool(ok.item() == 1.0)
         del Cref
+    # ---- end to end from HOST buffers and the same problem on ONE GPU: rank 0 alone, the other ranks stay idle ----
+    # e2e is the drop-in's call: eml_gemm_f64_sharded(world, A, B, C) from one host thread of one process; every GPU
+    # uploads its slab of A and 1/world of B over its own PCIe link, B's pieces are exchanged over NVLink, C's slabs are
+    # downloaded -- all inside the timed region.  The other ranks wait on the rendezvous store (a host-side wait: an
+    # NCCL barrier would spin on their SMs while rank 0's call computes there).
+    import numpy as np
+
+    store = dist.distributed_c10d._get_default_store()
+    torch.cuda.synchronize()
+    dist.barrier()
+    e2e, t1_ms = None, None
+    host_gb = 3 * n * n * 8 / 1e9
+    try:
+        import psutil
+
+        avail_gb = psutil.virtual_memory().available / 1e9
+    except Exception:  # noqa: BLE001
+        avail_gb = 0.0
+    if rank == 0 and avail_gb < 1.5 * host_gb:
+        e2e = {"value": value, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+               "note": f"host-buffer e2e skipped: {host_gb:.0f} GB of page-locked host memory needed, {avail_gb:.0f} GB available"}
+        store.set("eml_e2e_done", "1")
+    elif rank == 0:
+        flop_n = 2.0 * n * n * n
+        # T1: the identical n x n product on one GPU, operands in HBM (efficiency = T1 / (g * Tg))
+        gen.manual_seed(0x5EED0007)
+        A1 = torch.rand((n, n), generator=gen, device=dev, dtype=f64) * 2 - 1
+        C1 = Cfull[:n]
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        check(lib.eml_gemm_f64_dev(vp(A1[:256]), vp(B), vp(C1[:256]), 256, n, n, n, n, n, sp))  # warm
+        a0.record(stream)
+        check(lib.eml_gemm_f64_dev(vp(A1), vp(B), vp(C1), n, n, n, n, n, n, sp))
+        a1.record(stream)
+        torch.cuda.synchronize()
+        t1_ms = a0.elapsed_time(a1)
+        want_rows = C1[:128].cpu()
+        # host buffers: page-locked (direct DMA on every link) and pageable (a Rust Vec<T>)
+        Ah = torch.empty((n, n), dtype=f64, pin_memory=True)
+        Bh = torch.empty((n, n), dtype=f64, pin_memory=True)
+        Ch = torch.empty((n, n), dtype=f64, pin_memory=True)
+        Ah.copy_(A1)
+        Bh.copy_(B)
+        torch.cuda.synchronize()
+        del A1
+
+        def host_call(a_, b_, c_):
+            check(lib.eml_gemm_f64_sharded(world, vp(a_), vp(b_), vp(c_), n, n, n, n, n, n))
+
+        def measure(a_, b_, c_, calls):
+            host_call(a_, b_, c_)
+            t0 = time.perf_counter()
+            for _ in range(calls):
+                host_call(a_, b_, c_)
+            return (time.perf_counter() - t0) / calls * 1e3
+
+        calls = max(1, min(args.steps, 3))
+        pinned_ms = measure(Ah, Bh, Ch, calls)
+        same = bool(torch.equal(Ch[:128], want_rows))
+        last_rows = bool(torch.isfinite(Ch[n - 128:]).all())
+        entry = f"eml_gemm_f64_sharded({world}, host A, host B, host C): one call, one host thread, {world} GPUs"
+        if avail_gb >= 2.6 * host_gb:
+            Ap, Bp, Cp = Ah.numpy().copy(), Bh.numpy().copy(), np.empty((n, n))
+            pageable_ms = measure(torch.from_numpy(Ap), torch.from_numpy(Bp), torch.from_numpy(Cp), calls)
+            same = same and bool(np.array_equal(Cp[:128], want_rows.numpy())) and bool(np.array_equal(Cp[n - 128:], Ch[n - 128:].numpy()))
+            e2e = {"value": flop_n / (pageable_ms * 1e-3) / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": 2 * n * n * 8,
+                   "d2h_bytes_per_step": n * n * 8, "ms_per_step": pageable_ms, "calls_timed": calls, "entry_point": entry,
+                   "host_memory": "pageable (what the reference API's Vec<T> is)",
+                   "page_locked": {"value": flop_n / (pinned_ms * 1e-3) / 1e12, "ms_per_step": pinned_ms},
+                   "bits_equal_to_one_gpu": same and last_rows}
+            del Ap, Bp, Cp
+        else:
+            e2e = {"value": flop_n / (pinned_ms * 1e-3) / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": 2 * n * n * 8,
+                   "d2h_bytes_per_step": n * n * 8, "ms_per_step": pinned_ms, "calls_timed": calls, "entry_point": entry,
+                   "host_memory": "page-locked (not enough host memory for a second, pageable set of operands)",
+                   "bits_equal_to_one_gpu": same and last_rows}
+        del Ah, Bh, Ch
+        store.set("eml_e2e_done", "1")
+    else:
+        store.wait(["eml_e2e_done"])
+    dist.barrier()
+    if e2e is None:
+        e2e = {"value": value, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     return {
         "metric": "f64 matmul throughput", "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "t1_same_problem_ms": t1_ms,
+        "scaling_efficiency_same_problem": (t1_ms / (world * ms)) if t1_ms else None,
         "dtype": "f64", "data": "synthetic",
         "config": workload_config(n, world, "fused into the GEMM epilogue: peer stores over NVLink" if fused
                                   else "ncclAllGather",
                                   "copy-engine pull over NVLink" if args.bcast == "ce" else "ncclBroadcast"),
         "clocks": clocks,
         "gpu_launches": int(launches),
-        "e2e": {"value": value, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-                "note": "sharded run keeps operands in HBM; host-pointer e2e is reported by the 1-GPU run"},
+        "e2e": e2e,
         "roofline": {"bound": "tensor", "kernel": "dmma_f64_tma", "achieved": achieved, "peak": fp64_peak,
                      "unit": "TFLOP/s", "frac": achieved / fp64_peak, "traffic": None,
                      "peak_source": "measured in this run on rank 0's GPU: register-resident DMMA loop (per GPU); "
