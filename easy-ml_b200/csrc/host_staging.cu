@@ -10,6 +10,10 @@
 #include <cstdlib>
 #include <thread>
 
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
+
 namespace eml {
 
 bool host_pointer_is_pinned(const void* p) {
@@ -22,6 +26,45 @@ bool host_pointer_is_pinned(const void* p) {
 }
 
 namespace {
+
+// Staging copies move every byte exactly once and nobody reads the destination soon (the DMA engine reads a slot from
+// memory; the caller reads C much later), so the destination is written with non-temporal stores: no read-for-ownership
+// of the destination lines (a third less memory traffic than memcpy's cached stores) and the caches keep the sources.
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) void copy_streaming_avx2(char* dst, const char* src, size_t n) {
+    while (n && (reinterpret_cast<uintptr_t>(dst) & 31)) {
+        *dst++ = *src++;
+        n--;
+    }
+    size_t blocks = n / 128;
+    for (size_t i = 0; i < blocks; i++) {
+        const __m256i a = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src));
+        const __m256i b = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + 32));
+        const __m256i c = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + 64));
+        const __m256i d = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + 96));
+        _mm256_stream_si256(reinterpret_cast<__m256i*>(dst), a);
+        _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + 32), b);
+        _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + 64), c);
+        _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + 96), d);
+        src += 128;
+        dst += 128;
+    }
+    n -= blocks * 128;
+    if (n) memcpy(dst, src, n);
+    _mm_sfence();
+}
+#endif
+
+void copy_bytes(void* dst, const void* src, size_t n) {
+#if defined(__x86_64__)
+    static const bool avx2 = __builtin_cpu_supports("avx2") && !(getenv("EML_COPY_NT") && getenv("EML_COPY_NT")[0] == '0');
+    if (avx2 && n >= 4096) {
+        copy_streaming_avx2(static_cast<char*>(dst), static_cast<const char*>(src), n);
+        return;
+    }
+#endif
+    memcpy(dst, src, n);
+}
 
 // A tiny persistent pool: run(n, fn) calls fn(0..n-1) over the workers and the calling thread.
 class CopyPool {
@@ -57,7 +100,7 @@ class CopyPool {
     CopyPool() {
         // the caller's thread copies too; EML_COPY_THREADS overrides the total (1 = no workers)
         unsigned hw = std::thread::hardware_concurrency();
-        int n = hw > 2 ? (int)std::min(15u, hw - 1) : 0;
+        int n = hw > 2 ? (int)std::min(31u, hw - 1) : 0;
         if (const char* e = getenv("EML_COPY_THREADS")) {
             const int want = atoi(e);
             if (want >= 1 && want <= 64) n = want - 1;
@@ -134,7 +177,7 @@ void parallel_copy_rows(void* dst, size_t dpitch, const void* src, size_t spitch
         CopyPool::get().run(rows * pieces, [&](int64_t t) {
             const int64_t r = t / pieces;
             const size_t off = (size_t)(t % pieces) * BLOCK, len = std::min(BLOCK, width - off);
-            memcpy((char*)dst + r * dpitch + off, (const char*)src + r * spitch + off, len);
+            copy_bytes((char*)dst + r * dpitch + off, (const char*)src + r * spitch + off, len);
         });
         return;
     }
@@ -144,9 +187,9 @@ void parallel_copy_rows(void* dst, size_t dpitch, const void* src, size_t spitch
     CopyPool::get().run(blocks, [&](int64_t b) {
         int64_t r0 = b * rows_per_block, r1 = std::min(rows, r0 + rows_per_block);
         if (dpitch == width && spitch == width) {
-            memcpy((char*)dst + r0 * width, (const char*)src + r0 * width, (size_t)(r1 - r0) * width);
+            copy_bytes((char*)dst + r0 * width, (const char*)src + r0 * width, (size_t)(r1 - r0) * width);
         } else {
-            for (int64_t r = r0; r < r1; r++) memcpy((char*)dst + r * dpitch, (const char*)src + r * spitch, width);
+            for (int64_t r = r0; r < r1; r++) copy_bytes((char*)dst + r * dpitch, (const char*)src + r * spitch, width);
         }
     });
 }
