@@ -85,6 +85,8 @@ SIGNATURES = {
     "eml_tape_constants": (cint, [vp, vp, i64, i64, pi64]),
     "eml_tape_variables_dev": (cint, [vp, vp, i64, i64, pi64]),
     "eml_tape_constants_dev": (cint, [vp, vp, i64, i64, pi64]),
+    "eml_tape_from_existing": (cint, [vp, vp, vp, i64, i64, cint, pi64]),
+    "eml_tape_range": (cint, [vp, i64, i64, i64, i64, i64, cint, pi64]),
     "eml_tape_reset": (cint, [vp, i64]),
     "eml_val_release": (cint, [vp, i64]),
     "eml_val_shape": (cint, [vp, i64, pi64, pi64, C.POINTER(cint)]),

@@ -286,6 +286,9 @@ template <class T>
 int launch_quirk_cols(const T* G, int64_t gm, const T* B, int64_t bm, int64_t N, T* out, cudaStream_t stream);
 template <class T>
 int launch_quirk_rows(const T* A, int64_t K, const T* G, int64_t N, int64_t M, T* out, cudaStream_t stream);
+template <class T>
+int launch_scatter_segments(const T* g, const int* perm, const int* seg_start, int n_seg, T* arena, const int64_t* seg_off,
+                            cudaStream_t stream);
 bool thin_shape(int64_t M, int64_t N, int64_t K);
 template <class T>
 int launch_thin_fwd(const T* A, int64_t sAr, int64_t sAc, const T* B, int64_t M, int64_t N, int64_t K, T* C, int64_t sCr,

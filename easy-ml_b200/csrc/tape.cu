@@ -9,6 +9,8 @@
 // without the entries ever existing.  Sweep of a matmul node = two GEMMs; of an elementwise node = one
 // fused multiply-accumulate pass.
 #include <algorithm>
+#include <cstring>
+#include <numeric>
 #include <memory>
 #include <vector>
 
@@ -52,7 +54,20 @@ int new_buf(size_t bytes, cudaStream_t s, Buf* out) {
     return EML_OK;
 }
 
-enum class Kind { VARIABLES, UNARY, BINARY, MATMUL };
+enum class Kind { VARIABLES, UNARY, BINARY, MATMUL, VIEW };
+
+// The (T, Index) pairs of a container built by RecordTensor::from_existing / RecordMatrix::from_existing (reference
+// container_record/mod.rs:219-224, :508): any index per element -- a range or mask of another container, a row of a
+// constants matrix re-wrapped with a history (every Index 0: src/neural_networks.rs:105-120), duplicates allowed.
+// In the sweep the container's derivatives are collected densely (like a node's) and then scattered:
+// derivatives[index[e]] += g[e], all elements carrying one index summed in ascending element order by one thread.
+struct IndexMap {
+    std::vector<int64_t> idx;      // per element, row-major
+    bool all_equal = false;        // every element carries idx[0] (the re-wrapped constants of the NN examples)
+    int n_seg = 0;                 // distinct indexes
+    std::vector<int64_t> seg_idx;  // the distinct indexes, ascending
+    Buf perm, seg_start;           // device: elements grouped by index (int32), segment boundaries (int32, n_seg + 1)
+};
 
 // A record container: numbers on the device + how its elements map to tape indexes.
 struct Value {
@@ -61,6 +76,7 @@ struct Value {
     bool tracked = false;  // history.is_some()
     int node = -1;         // producing node in the CURRENT epoch; -1: every Index is 0 (constants)
     uint64_t epoch = 0;    // tape epoch the node id belongs to
+    std::shared_ptr<IndexMap> map;  // from_existing: the indexes of the elements (node = the VIEW node when tracked)
     bool alive = false;
     int64_t n() const { return rows * cols; }
 };
@@ -86,6 +102,7 @@ struct Node {
     int xn = -1, yn = -1;  // operand produced by a node of the SAME group (its node id); else the numbers below
     Buf xin, yin;          // operand numbers living outside the group (kept alive: the backward pass recomputes)
     Buf value;             // this node's numbers once somebody needed them (null: interior, never stored)
+    std::shared_ptr<IndexMap> map;  // Kind::VIEW: where the container's derivatives go (stands for NO tape entries)
     // index of element e of the produced container on the reference tape
     int64_t index_of(int64_t e) const {
         if (kind == Kind::MATMUL && K > 1) return base + e * (2 * K - 1) + 2 * K - 2;
@@ -136,6 +153,7 @@ struct eml_derivs {
     // which saves a launch per step.
     Buf arena;
     bool slot0_pending = false;
+    std::vector<std::vector<int64_t>> scatter_offsets;  // host copies of uploaded scatter targets (kept until freed)
 };
 
 struct eml_graph {
@@ -546,6 +564,76 @@ int new_container(eml_tape* t, const void* src, bool src_on_device, int64_t rows
     return EML_OK;
 }
 
+int node_of_index(const std::vector<Node>& nodes, int64_t index);
+
+// Classifies the indexes of a re-wrapped container and, when it takes part in sweeps, prepares the grouping of its
+// elements by index on the device.
+int build_index_map(eml_tape* t, std::vector<int64_t>&& idx, bool tracked, std::shared_ptr<IndexMap>* out) {
+    auto map = std::make_shared<IndexMap>();
+    map->idx = std::move(idx);
+    const int64_t n = (int64_t)map->idx.size();
+    map->all_equal = true;
+    for (int64_t e = 1; e < n && map->all_equal; e++) map->all_equal = map->idx[e] == map->idx[0];
+    if (tracked) {
+        if (n > 0x7fffffffLL) EML_BAD_ARG("from_existing: too many elements");
+        std::vector<int> perm((size_t)n);
+        std::iota(perm.begin(), perm.end(), 0);
+        if (!map->all_equal)
+            std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return map->idx[a] < map->idx[b]; });
+        std::vector<int> seg_start;
+        for (int64_t j = 0; j < n; j++)
+            if (j == 0 || map->idx[perm[j]] != map->idx[perm[j - 1]]) {
+                seg_start.push_back((int)j);
+                map->seg_idx.push_back(map->idx[perm[j]]);
+            }
+        seg_start.push_back((int)n);
+        map->n_seg = (int)map->seg_idx.size();
+        // every index must be the Index of a container element that exists on the list right now (the reference does
+        // not check and panics with an out-of-bounds index when derivatives are taken)
+        for (int64_t index : map->seg_idx) {
+            const int nd = node_of_index(t->nodes, index);
+            if (nd < 0) EML_BAD_ARG("from_existing: index %lld is not on the WengertList (its length is %lld)", (long long)index, (long long)t->len);
+            if (t->nodes[nd].index_of(t->nodes[nd].element_of(index)) != index)
+                EML_BAD_ARG("from_existing: index %lld is an entry inside a matrix product, not the Index of a container element", (long long)index);
+        }
+        if (!map->all_equal) {
+            EML_TRY(not_while_capturing(t, "re-wrapping a container with arbitrary indexes"));
+            EML_TRY(new_buf(sizeof(int) * (size_t)n, t->stream, &map->perm));
+            EML_TRY(new_buf(sizeof(int) * seg_start.size(), t->stream, &map->seg_start));
+            EML_CUDA(cudaMemcpyAsync(map->perm->p, perm.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, t->stream));
+            EML_CUDA(cudaMemcpyAsync(map->seg_start->p, seg_start.data(), sizeof(int) * seg_start.size(), cudaMemcpyHostToDevice, t->stream));
+            EML_CUDA(cudaStreamSynchronize(t->stream));  // the host vectors die with this call
+        }
+    }
+    *out = map;
+    return EML_OK;
+}
+
+// the container of a from_existing call: numbers already on the device
+int put_view(eml_tape* t, Buf numbers, int64_t rows, int64_t cols, std::shared_ptr<IndexMap> map, bool tracked, eml_val* out) {
+    Value v;
+    v.rows = rows;
+    v.cols = cols;
+    v.numbers = numbers;
+    v.map = map;
+    v.tracked = tracked;
+    if (tracked) {
+        Node nd;
+        nd.kind = Kind::VIEW;  // no tape entries: from_existing appends nothing to the list
+        nd.base = t->len;
+        nd.count = 0;
+        nd.n = rows * cols;
+        nd.map = map;
+        t->nodes.push_back(nd);
+        v.node = (int)t->nodes.size() - 1;
+        v.epoch = t->epoch;
+    } else {
+        v.numbers->identity = new_buffer_identity();  // history None: constants
+    }
+    *out = put_value(t, std::move(v));
+    return EML_OK;
+}
+
 template <class T>
 int tape_matmul(eml_tape* t, eml_val ha, eml_val hb, eml_val* out) {
     Value *a, *b;
@@ -705,6 +793,54 @@ int tape_binary(eml_tape* t, int op, eml_val hx, eml_val hy, eml_val* out) {
     return EML_OK;
 }
 
+// node whose entries contain reference tape index `index` (-1: out of range)
+int node_of_index(const std::vector<Node>& nodes, int64_t index) {
+    if (nodes.empty() || index < 0) return -1;
+    int lo = 0, hi = (int)nodes.size() - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) / 2;
+        if (nodes[mid].base <= index) lo = mid;
+        else hi = mid - 1;
+    }
+    while (lo > 0 && nodes[lo].count == 0) lo--;  // a view stands for no entries
+    if (index < nodes[lo].base || index >= nodes[lo].base + nodes[lo].count) return -1;
+    return lo;
+}
+
+// The sweep of a re-wrapped container: its densely collected derivatives g are added to derivatives[index[e]].
+template <class T>
+int scatter_view(eml_tape* t, eml_derivs* d, const Node& nd, const T* g, const Buf& arena, const std::vector<size_t>& offs,
+                 cudaStream_t st) {
+    const IndexMap& map = *nd.map;
+    auto target = [&](int64_t index, int64_t* elem_off) -> int {  // offset (elements of T) inside the arena
+        const int n = node_of_index(d->nodes, index);
+        if (n < 0) {
+            set_error("index out of bounds: the len is %lld but the index is %lld", (long long)d->len, (long long)index);
+            return EML_ERR_STATE;
+        }
+        *elem_off = (int64_t)(offs[n] / sizeof(T)) + d->nodes[n].element_of(index);
+        return EML_OK;
+    };
+    if (map.all_equal) {
+        int64_t off;
+        EML_TRY(target(map.idx[0], &off));
+        return launch_reduce_sum<T>(t->ctx, g, nd.n, static_cast<T*>(arena->p) + off, true, st);
+    }
+    if (t->capturing) {
+        set_error("a container re-wrapped with arbitrary indexes cannot be swept inside a recorded step (its scatter targets "
+                  "are uploaded per sweep)");
+        return EML_ERR_STATE;
+    }
+    d->scatter_offsets.emplace_back(map.n_seg);
+    std::vector<int64_t>& off = d->scatter_offsets.back();
+    for (int sgm = 0; sgm < map.n_seg; sgm++) EML_TRY(target(map.seg_idx[sgm], &off[sgm]));
+    TempBuf dev_off;
+    EML_TRY(dev_off.alloc(sizeof(int64_t) * (size_t)map.n_seg, st));
+    EML_CUDA(cudaMemcpyAsync(dev_off.p, off.data(), sizeof(int64_t) * (size_t)map.n_seg, cudaMemcpyHostToDevice, st));
+    return launch_scatter_segments<T>(g, (const int*)map.perm->p, (const int*)map.seg_start->p, map.n_seg,
+                                      static_cast<T*>(arena->p), dev_off.as<int64_t>(), st);
+}
+
 // Does the sweep of matmul node c WRITE (0 + sum, not +=) the derivatives of its parent `parent` when it is the first
 // to contribute to them?  True for the kernels that start their fma chain from +0 themselves: the thin (M <= 4)
 // backward, and dA = G * B^T through the short-contraction kernel.  (Such a parent needs no zero fill and is not read.)
@@ -764,6 +900,13 @@ int tape_sweep(eml_tape* t, eml_val hv, int64_t row, int64_t col, eml_derivs** o
     for (int i = 0; i < n_nodes; i++) {
         const Node& nd = t->nodes[i];
         if (nd.kind == Kind::VARIABLES) continue;
+        if (nd.kind == Kind::VIEW) {  // its derivatives are ADDED to the nodes its indexes point into
+            for (int64_t index : nd.map->seg_idx) {
+                const int target = node_of_index(t->nodes, index);
+                if (target >= 0) first_consumer[target] = i;
+            }
+            continue;
+        }
         const bool uses0 = nd.kind == Kind::BINARY ? nd.p0_tracked : true, uses1 = nd.kind == Kind::BINARY ? nd.p1_tracked : nd.kind == Kind::MATMUL;
         if (uses0 && nd.p0 >= 0) first_consumer[nd.p0] = i;
         if (uses1 && nd.p1 >= 0) first_consumer[nd.p1] = i;
@@ -779,7 +922,7 @@ int tape_sweep(eml_tape* t, eml_val hv, int64_t row, int64_t col, eml_derivs** o
             if (i == nv) seed_in_kernel = true;
             continue;
         }
-        const bool overwritten_first = c >= 0 && i != nv &&
+        const bool overwritten_first = c >= 0 && i != nv && t->nodes[c].kind != Kind::VIEW &&
                                        (t->nodes[c].kind != Kind::MATMUL || matmul_overwrites(t->nodes[c], i, sizeof(T)));
         written[i] = !overwritten_first;  // "written" = holds defined numbers (zeros) before the sweep
     }
@@ -818,6 +961,10 @@ int tape_sweep(eml_tape* t, eml_val hv, int64_t row, int64_t col, eml_derivs** o
         const Node& nd = t->nodes[i];
         const T* g = (const T*)d->grads[i]->p;
         if (nd.kind == Kind::VARIABLES) continue;
+        if (nd.kind == Kind::VIEW) {
+            EML_TRY(scatter_view<T>(t, d.get(), nd, g, arena, offs, st));
+            continue;
+        }
         if (nd.group >= 0) {  // the whole run [first, last] in one kernel
             const Group& grp = t->groups[nd.group];
             EML_TRY(group_backward<T>(t->nodes, grp, d->grads, written, d->have, nv, row * v->cols + col, false, st));
@@ -901,15 +1048,7 @@ int tape_sweep(eml_tape* t, eml_val hv, int64_t row, int64_t col, eml_derivs** o
 
 int find_node(const eml_derivs* d, int64_t index) {
     if (index < 0 || index >= d->len) return -1;
-    int lo = 0, hi = (int)d->nodes.size() - 1;
-    while (lo < hi) {
-        int mid = (lo + hi + 1) / 2;
-        if (d->nodes[mid].base <= index)
-            lo = mid;
-        else
-            hi = mid - 1;
-    }
-    return lo;
+    return node_of_index(d->nodes, index);
 }
 
 }  // namespace
@@ -983,6 +1122,58 @@ int eml_tape_constants_dev(eml_tape* t, const void* dev, int64_t rows, int64_t c
                          new_container<double>(t, dev, true, rows, cols, false, out));
 }
 
+int eml_tape_from_existing(eml_tape* t, const void* host_numbers, const int64_t* host_indexes, int64_t rows, int64_t cols,
+                           int has_history, eml_val* out) {
+    EML_TRY(check_tape(t));
+    if (!host_numbers || !host_indexes || !out) EML_BAD_ARG("null argument");
+    if (rows < 1 || cols < 1) EML_BAD_ARG("container shape %lldx%lld: Easy ML containers have at least one element",
+                                          (long long)rows, (long long)cols);
+    std::lock_guard<std::mutex> lock(t->mu);
+    EML_TRY(not_while_capturing(t, "creating a container from host memory"));
+    EML_TRY(flush(t));
+    std::shared_ptr<IndexMap> map;
+    EML_TRY(build_index_map(t, std::vector<int64_t>(host_indexes, host_indexes + rows * cols), has_history != 0, &map));
+    Buf numbers;
+    const size_t bytes = esize(t->dtype) * (size_t)(rows * cols);
+    EML_TRY(new_buf(bytes, t->stream, &numbers));
+    EML_CUDA(cudaMemcpyAsync(numbers->p, host_numbers, bytes, cudaMemcpyHostToDevice, t->stream));
+    EML_CUDA(cudaStreamSynchronize(t->stream));
+    return put_view(t, numbers, rows, cols, map, has_history != 0, out);
+}
+
+int eml_tape_range(eml_tape* t, eml_val src, int64_t row0, int64_t n_rows, int64_t col0, int64_t n_cols, int has_history,
+                   eml_val* out) {
+    EML_TRY(check_tape(t));
+    if (!out) EML_BAD_ARG("null argument");
+    std::lock_guard<std::mutex> lock(t->mu);
+    Value* v;
+    EML_TRY(get_value(t, src, &v));
+    if (row0 < 0 || col0 < 0 || n_rows < 1 || n_cols < 1 || row0 + n_rows > v->rows || col0 + n_cols > v->cols)
+        EML_BAD_ARG("range [%lld, +%lld) x [%lld, +%lld) does not fit a %lldx%lld container", (long long)row0, (long long)n_rows,
+                    (long long)col0, (long long)n_cols, (long long)v->rows, (long long)v->cols);
+    bool stale;
+    const int n = live_node(t, *v, &stale);
+    if (stale) {
+        set_error("container was not reset after WengertList::clear(); its indexes are stale");
+        return EML_ERR_STATE;
+    }
+    EML_TRY(flush(t));
+    std::vector<int64_t> idx((size_t)(n_rows * n_cols));
+    for (int64_t r = 0; r < n_rows; r++)
+        for (int64_t c = 0; c < n_cols; c++) {
+            const int64_t e = (row0 + r) * v->cols + col0 + c;
+            idx[(size_t)(r * n_cols + c)] = v->map ? v->map->idx[(size_t)e] : (n < 0 ? 0 : t->nodes[n].index_of(e));
+        }
+    std::shared_ptr<IndexMap> map;
+    EML_TRY(build_index_map(t, std::move(idx), has_history != 0, &map));
+    const size_t es = esize(t->dtype);
+    Buf numbers;
+    EML_TRY(new_buf(es * (size_t)(n_rows * n_cols), t->stream, &numbers));
+    EML_CUDA(cudaMemcpy2DAsync(numbers->p, n_cols * es, (const char*)v->numbers->p + (row0 * v->cols + col0) * es, v->cols * es,
+                               n_cols * es, n_rows, cudaMemcpyDeviceToDevice, t->stream));
+    return put_view(t, numbers, n_rows, n_cols, map, has_history != 0, out);
+}
+
 int eml_tape_reset(eml_tape* t, eml_val h) {
     EML_TRY(check_tape(t));
     std::lock_guard<std::mutex> lock(t->mu);
@@ -998,6 +1189,7 @@ int eml_tape_reset(eml_tape* t, eml_val h) {
     t->nodes.push_back(nd);
     v->node = (int)t->nodes.size() - 1;
     v->epoch = t->epoch;
+    v->map.reset();  // renumbered start + i: an ordinary variables container from here on
     return EML_OK;
 }
 
@@ -1170,6 +1362,10 @@ int eml_val_indexes(eml_tape* t, eml_val h, int64_t* host_out) {
         set_error("container was not reset after WengertList::clear(); its indexes are stale");
         return EML_ERR_STATE;
     }
+    if (v->map) {
+        memcpy(host_out, v->map->idx.data(), sizeof(int64_t) * (size_t)v->n());
+        return EML_OK;
+    }
     for (int64_t e = 0; e < v->n(); e++) host_out[e] = n < 0 ? 0 : t->nodes[n].index_of(e);
     return EML_OK;
 }
@@ -1286,6 +1482,37 @@ static int derivs_at_val(eml_derivs* d, eml_val h, void* dst, bool dst_on_device
         return EML_ERR_STATE;
     }
     cudaMemcpyKind kind = dst_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    if (v->map) {
+        // a re-wrapped container: element e reads derivatives[index[e]] (Derivatives::at_tensor looks every Index up)
+        const IndexMap& map = *v->map;
+        std::vector<int64_t> distinct = map.seg_idx;
+        if (distinct.empty()) {  // history None: no grouping was prepared
+            distinct = map.idx;
+            std::sort(distinct.begin(), distinct.end());
+            distinct.erase(std::unique(distinct.begin(), distinct.end()), distinct.end());
+        }
+        std::vector<char> got(es * distinct.size());
+        for (size_t sgm = 0; sgm < distinct.size(); sgm++) {
+            const int tn = find_node(d, distinct[sgm]);
+            if (tn < 0) EML_BAD_ARG("index out of bounds: the len is %lld but the index is %lld", (long long)d->len, (long long)distinct[sgm]);
+            EML_TRY(ensure_have(d, tn));
+            EML_CUDA(cudaMemcpyAsync(got.data() + es * sgm, (const char*)d->grads[tn]->p + es * d->nodes[tn].element_of(distinct[sgm]), es,
+                                     cudaMemcpyDeviceToHost, d->stream));
+        }
+        EML_CUDA(cudaStreamSynchronize(d->stream));
+        std::vector<char> host(es * (size_t)v->n());
+        for (int64_t e = 0; e < v->n(); e++) {
+            const size_t sgm = std::lower_bound(distinct.begin(), distinct.end(), map.idx[(size_t)e]) - distinct.begin();
+            memcpy(host.data() + es * e, got.data() + es * sgm, es);
+        }
+        if (dst_on_device) {
+            EML_CUDA(cudaMemcpyAsync(dst, host.data(), host.size(), cudaMemcpyHostToDevice, d->stream));
+            EML_CUDA(cudaStreamSynchronize(d->stream));
+        } else {
+            memcpy(dst, host.data(), host.size());
+        }
+        return EML_OK;
+    }
     if (n >= 0) {
         EML_TRY(ensure_have(d, n));
         EML_CUDA(cudaMemcpyAsync(dst, d->grads[n]->p, es * v->n(), kind, d->stream));
@@ -1318,6 +1545,7 @@ int eml_derivs_to_host(eml_derivs* d, void* host_out) {
     std::vector<char> tmp;
     for (size_t i = 0; i < d->nodes.size(); i++) {
         const Node& nd = d->nodes[i];
+        if (nd.kind == Kind::VIEW) continue;  // stands for no entries
         EML_TRY(ensure_have(d, (int)i));
         tmp.resize(es * nd.n);
         EML_CUDA(cudaMemcpyAsync(tmp.data(), d->grads[i]->p, es * nd.n, cudaMemcpyDeviceToHost, d->stream));
@@ -1346,7 +1574,7 @@ int eml_tape_sgd_update(eml_tape* t, eml_val hw, eml_derivs* d, double lr) {
     for (const auto& u : t->sgd) chained |= w->numbers && u.out == w->numbers;
     if (chained) EML_TRY(flush(t));
     else EML_TRY(t->dtype == EML_F32 ? flush_groups<float>(t) : flush_groups<double>(t));
-    if (!w->tracked || w->node < 0 || w->epoch != t->epoch || d->epoch != t->epoch || w->node >= (int)d->nodes.size()) {
+    if (!w->tracked || w->node < 0 || w->map || w->epoch != t->epoch || d->epoch != t->epoch || w->node >= (int)d->nodes.size()) {
         set_error("sgd_update: container is not a tracked variable of the computation these derivatives belong to");
         return EML_ERR_STATE;
     }

@@ -454,6 +454,33 @@ int launch_quirk_rows(const T* A, int64_t K, const T* G, int64_t N, int64_t M, T
     return check_launch("constant-operand row sums");
 }
 
+namespace {
+// derivatives[index] += sum of g over the elements of a re-wrapped container that carry that index: one thread per
+// DISTINCT index walks its elements (perm groups them, ascending element order) -- a fixed order, no atomics
+template <class T>
+__global__ void __launch_bounds__(TK_THREADS)
+scatter_segments_kernel(const T* __restrict__ g, const int* __restrict__ perm, const int* __restrict__ seg_start, int n_seg,
+                        T* arena, const int64_t* __restrict__ seg_off) {
+    pdl_prologue();
+    for (int sgm = blockIdx.x * TK_THREADS + threadIdx.x; sgm < n_seg; sgm += gridDim.x * TK_THREADS) {
+        T acc = T(0);
+        for (int j = seg_start[sgm]; j < seg_start[sgm + 1]; j++) acc += g[perm[j]];
+        arena[seg_off[sgm]] = arena[seg_off[sgm]] + acc;
+    }
+}
+}  // namespace
+
+template <class T>
+int launch_scatter_segments(const T* g, const int* perm, const int* seg_start, int n_seg, T* arena, const int64_t* seg_off,
+                            cudaStream_t stream) {
+    if (n_seg < 1) return EML_OK;
+    int blocks = (n_seg + TK_THREADS - 1) / TK_THREADS;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    launch_k(scatter_segments_kernel<T>, dim3(blocks), dim3(TK_THREADS), 0, stream, g, perm, seg_start, n_seg, arena, seg_off);
+    count_launch();
+    return check_launch("derivative scatter of a re-wrapped container");
+}
+
 bool thin_shape(int64_t M, int64_t N, int64_t K) { return M >= 1 && M <= TH_M && N >= 1 && N <= TH_N && K >= 1; }
 
 namespace {
@@ -608,6 +635,7 @@ int launch_gemm_smallk(const T* A, int64_t lda, const T* B, int64_t sBr, int64_t
 }
 
 #define EML_INST(T)                                                                                                       \
+    template int launch_scatter_segments<T>(const T*, const int*, const int*, int, T*, const int64_t*, cudaStream_t);     \
     template int launch_quirk_cols<T>(const T*, int64_t, const T*, int64_t, int64_t, T*, cudaStream_t);                   \
     template int launch_quirk_rows<T>(const T*, int64_t, const T*, int64_t, int64_t, T*, cudaStream_t);                   \
     template int launch_thin_fwd<T>(const T*, int64_t, int64_t, const T*, int64_t, int64_t, int64_t, T*, int64_t, int64_t, \

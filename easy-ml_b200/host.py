@@ -532,6 +532,25 @@ class _RecordContainer:
         check(f(owner._h, _ptr(a), rows, cols, C.byref(v)))
         return cls(owner, v.value, shape, history)
 
+    @classmethod
+    def _from_existing(cls, owner, history, shape, numbers, indexes):
+        """RecordContainer::from_existing (container_record/mod.rs:219-224, :508): any (number, Index) pairs."""
+        a = np.ascontiguousarray(np.asarray(numbers, dtype=owner.dtype))
+        idx = np.ascontiguousarray(np.asarray(indexes, dtype=np.int64))
+        if a.shape != idx.shape:
+            raise Panic("from_existing: numbers and indexes must have the same shape")
+        rows = int(np.prod(a.shape[:-1])) if a.ndim > 1 else 1
+        cols = a.shape[-1] if a.ndim >= 1 else 1
+        v = C.c_int64()
+        check(lib.eml_tape_from_existing(owner._h, _ptr(a), _ptr(idx), rows, cols, 1 if history is not None else 0, C.byref(v)))
+        return cls(owner, v.value, shape, history)
+
+    def _range(self, row0, n_rows, col0, n_cols, shape, history):
+        """from_existing over a MatrixRange / TensorRange of this container: numbers copied on the device, indexes follow."""
+        v = C.c_int64()
+        check(lib.eml_tape_range(self._owner._h, self._v, row0, n_rows, col0, n_cols, 1 if history is not None else 0, C.byref(v)))
+        return type(self)(self._owner, v.value, shape, history)
+
     def history(self):
         return self.history_list
 
@@ -652,6 +671,35 @@ class RecordTensor(_RecordContainer):
     def constants(tensor, owner):  # mod.rs:115-128 (owner = the list whose device holds the numbers)
         return RecordTensor._create(owner, None, tensor.shape(), tensor.data, False)
 
+    @staticmethod
+    def from_existing(history, shape, numbers, indexes, owner=None):
+        """RecordTensor::from_existing(history, TensorView<(T, Index)>), mod.rs:219-224.  `history` None = constants;
+        `owner` names the list whose device holds the numbers when history is None."""
+        return RecordTensor._from_existing(history if history is not None else owner, history, list(shape), numbers, indexes)
+
+    def range(self, ranges, history="same"):
+        """RecordTensor::from_existing(history, TensorView::from(TensorRange::from(self, ranges))) for rank <= 2:
+        `ranges` maps dimension names to (start, stop) (the doc example at mod.rs:205-217).  history: "same" keeps this
+        container's, None makes constants, or a WengertList."""
+        hist = self.history_list if history == "same" else history
+        lens, names = self._lens(), [n for n, _ in self._shape]
+        if len(lens) > 2:
+            raise TypeError("range of a record tensor: rank 1 and 2 containers only")
+        spans = [(0, l) for l in lens]
+        for name, (a, b) in dict(ranges).items():
+            if name not in names:
+                raise Panic(f"Invalid dimension name {name!r} for tensor of shape {_shape_debug(self._shape)}")
+            d = names.index(name)
+            a, b = max(0, a), min(lens[d], b)
+            if b <= a:
+                raise Panic("range would leave no elements")
+            spans[d] = (a, b)
+        if len(lens) == 1:
+            spans = [(0, 1)] + spans
+        (r0, r1), (c0, c1) = spans
+        new_shape = [(n, b - a) for n, (a, b) in zip(names, spans[-len(lens):])]
+        return self._range(r0, r1 - r0, c0, c1 - c0, new_shape, hist)
+
     def shape(self):
         return list(self._shape)
 
@@ -703,6 +751,24 @@ class RecordMatrix(_RecordContainer):
     @staticmethod
     def constants(matrix, owner):  # mod.rs:392
         return RecordMatrix._create(owner, None, matrix.size(), matrix.data, False)
+
+    @staticmethod
+    def from_existing(history, numbers, indexes, owner=None):
+        """RecordMatrix::from_existing(history, MatrixView<(T, Index)>), mod.rs:508."""
+        a = np.asarray(numbers)
+        return RecordMatrix._from_existing(history if history is not None else owner, history, tuple(a.shape), numbers, indexes)
+
+    def range(self, rows, columns, history="same"):
+        """RecordMatrix::from_existing(history, MatrixView::from(MatrixRange::from(self, IndexRange::new(start, length),
+        IndexRange::new(start, length)))) -- how the reference's examples take one input row at a time
+        (src/neural_networks.rs:105-120)."""
+        hist = self.history_list if history == "same" else history
+        (r0, nr), (c0, nc) = rows, columns
+        r0, c0 = min(r0, self._shape[0]), min(c0, self._shape[1])
+        nr, nc = min(nr, self._shape[0] - r0), min(nc, self._shape[1] - c0)
+        if nr < 1 or nc < 1:
+            raise Panic("range would leave no elements")
+        return self._range(r0, nr, c0, nc, (nr, nc), hist)
 
     def _lens(self):
         return list(self._shape)

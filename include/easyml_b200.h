@@ -310,6 +310,21 @@ int eml_tape_constants(eml_tape* t, const void* host_numbers, int64_t rows, int6
 /* same, adopting a device buffer the caller already filled (copied; async on the tape's stream) */
 int eml_tape_constants_dev(eml_tape* t, const void* dev_numbers, int64_t rows, int64_t cols, eml_val* out);
 int eml_tape_variables_dev(eml_tape* t, const void* dev_numbers, int64_t rows, int64_t cols, eml_val* out);
+/* RecordTensor::from_existing / RecordMatrix::from_existing, container_record/mod.rs:219-224, :508: a container made of
+ * ANY (number, Index) pairs -- rows*cols numbers and rows*cols tape indexes, row-major -- typically the elements of
+ * a range / mask / resize of other containers; duplicates allowed.  has_history != 0 is `Some(&list)`: the container
+ * takes part in sweeps and the derivative of element e is added to derivatives[indexes[e]] (elements sharing an index
+ * are summed in ascending element order: deterministic); every index must then be the Index of a container element
+ * currently on the list.  has_history == 0 is `None`: a constant whose elements still report their indexes.  Nothing
+ * is appended to the list.  The reference's examples re-wrap every row of a constants matrix this way
+ * (src/neural_networks.rs:105-120: all indexes 0 with the weights' history). */
+int eml_tape_from_existing(eml_tape* t, const void* host_numbers, const int64_t* host_indexes, int64_t rows, int64_t cols,
+                           int has_history, eml_val* out);
+/* The same for a rectangular range of a container that already lives on the device -- from_existing over
+ * MatrixRange / TensorRange (src/matrices/views/ranges.rs, src/tensors/views/ranges.rs): numbers are copied on the
+ * device, indexes follow the source's elements. */
+int eml_tape_range(eml_tape* t, eml_val src, int64_t row0, int64_t n_rows, int64_t col0, int64_t n_cols, int has_history,
+                   eml_val* out);
 /* RecordTensor::reset, mod.rs:349-365: re-append rows*cols nullary entries and renumber start + i. */
 int eml_tape_reset(eml_tape* t, eml_val v);
 int eml_val_release(eml_tape* t, eml_val v); /* drop a container (its node stays while referenced) */
