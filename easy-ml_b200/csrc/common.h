@@ -219,7 +219,7 @@ int launch_reorder(const T* in, T* out, int rank, const int64_t* out_lens, const
 // operands in place (alignment), in which case the packed path runs
 int launch_gemm_tf32x3_fused(DeviceCtx* ctx, const float* A, const float* B, float* C, int64_t batch, int64_t M,
                              int64_t N, int64_t K, Strides3 sA, Strides3 sB, Strides3 sC, int splits, bool accumulate,
-                             cudaStream_t stream, bool* handled);
+                             cudaStream_t stream, bool* handled, unsigned* nonfinite);
 
 template <class T>
 int launch_einsum2(const T* A, const T* B, T* out, int n_out, const int64_t* out_len, const int64_t* a_out_stride,
@@ -281,6 +281,16 @@ int launch_dot_accumulate(DeviceCtx* ctx, const T* x, const T* y, int64_t n, T* 
                           cudaStream_t stream);
 // zero-initialised, self-resetting ticket counters of a stream (single-pass deterministic reductions)
 int stream_tickets(cudaStream_t stream, unsigned** out);
+// two words of that array have fixed jobs: the second-level ticket of two-level reductions, and the "a split/pack pass
+// of this stream met an Inf / NaN / >= 2^127 input" flag of the f32 tensor-core GEMM (set by the pack kernels and the
+// in-kernel converters, read and cleared by the repair kernel that follows the product)
+constexpr int TICKET_SECOND_LEVEL = 4095, TICKET_NONFINITE = 4094;
+// After a 3xTF32 product C = A * B (no accumulate): when a non-finite input was seen, every NaN of C is recomputed as
+// the f32 fma chain over k -- an infinite operand meets the other operand's zero small part in the cross terms
+// (0 * inf) where the reference's plain products give +-inf.  One early-exit launch when nothing was seen.
+int launch_tf32_repair(const float* A, const float* B, float* C, int64_t batch, int64_t M, int64_t N, int64_t K, Strides3 sA,
+                       Strides3 sB, Strides3 sC, const unsigned* flag_a, const unsigned* flag_b, unsigned* stream_flag,
+                       cudaStream_t stream);
 // tape_kernels.cu: the reference's constant-operand sums, thin (M <= 4) products, short-contraction products
 template <class T>
 int launch_quirk_cols(const T* G, int64_t gm, const T* B, int64_t bm, int64_t N, T* out, cudaStream_t stream);

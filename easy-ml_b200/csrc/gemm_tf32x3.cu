@@ -65,7 +65,7 @@ __device__ __forceinline__ void split_tf32(float x, float& big, float& small) { 
 
 __global__ void __launch_bounds__(256)
 split_pack_kernel(const float* __restrict__ src, float* __restrict__ big, float* __restrict__ small, int64_t MN,
-                  int64_t K, int64_t MNp, int64_t Kp, int64_t sb, int64_t smn, int64_t sk, int k_fast) {
+                  int64_t K, int64_t MNp, int64_t Kp, int64_t sb, int64_t smn, int64_t sk, int k_fast, unsigned* nonfinite) {
     pdl_prologue();
     __shared__ float tile[32][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
@@ -91,6 +91,7 @@ split_pack_kernel(const float* __restrict__ src, float* __restrict__ big, float*
         float v = tile[row][tx];
         float hi, lo;
         split_tf32(v, hi, lo);
+        if (!tf32::ordinary(v)) *nonfinite = 1u;  // (rare; every writer stores the same value)
         int64_t o = b * plane + mn * Kp + k;
         big[o] = hi;
         small[o] = lo;
@@ -111,9 +112,14 @@ __device__ __forceinline__ float4 load4_guarded(const float* p, int64_t first, i
     if (first + 2 < extent) v.z = p[2];
     return v;
 }
-__device__ __forceinline__ void store_split4(float* big, float* small, float4 v) {
+__device__ __forceinline__ void store_split4(float* big, float* small, float4 v, unsigned* nonfinite) {
     float4 hi, lo;
-    tf32::split4(v, hi, lo);
+    if (tf32::ordinary4(v)) {
+        tf32::split4_ordinary(v, hi, lo);
+    } else {
+        tf32::split4_any(v, hi, lo);
+        *nonfinite = 1u;  // (rare; every writer stores the same value)
+    }
     *reinterpret_cast<float4*>(big) = hi;
     *reinterpret_cast<float4*>(small) = lo;
 }
@@ -121,7 +127,7 @@ __device__ __forceinline__ void store_split4(float* big, float* small, float4 v)
 template <bool K_FAST>
 __global__ void __launch_bounds__(256)
 split_pack_vec_kernel(const float* __restrict__ src, float* __restrict__ big, float* __restrict__ small, int64_t MN,
-                      int64_t K, int64_t MNp, int64_t Kp, int64_t sb, int64_t s_slow) {
+                      int64_t K, int64_t MNp, int64_t Kp, int64_t sb, int64_t s_slow, unsigned* nonfinite) {
     pdl_prologue();
     const int tid = threadIdx.x;
     const int64_t k0 = (int64_t)blockIdx.x * 64, mn0 = (int64_t)blockIdx.y * 64, b = blockIdx.z;
@@ -137,7 +143,7 @@ split_pack_vec_kernel(const float* __restrict__ src, float* __restrict__ big, fl
             if (mn >= MNp || k >= Kp) continue;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (mn < MN) v = load4_guarded(s + mn * s_slow + k, k, K);
-            store_split4(ob + mn * Kp + k, os + mn * Kp + k, v);
+            store_split4(ob + mn * Kp + k, os + mn * Kp + k, v, nonfinite);
         }
     } else {
         // element (mn, k) at s[k * s_slow + mn]: read rows of k, write rows of mn
@@ -160,24 +166,24 @@ split_pack_vec_kernel(const float* __restrict__ src, float* __restrict__ big, fl
             const int64_t mn = mn0 + m, k = k0 + c4;
             if (mn >= MNp || k >= Kp) continue;
             float4 v = make_float4(tile[c4][m], tile[c4 + 1][m], tile[c4 + 2][m], tile[c4 + 3][m]);
-            store_split4(ob + mn * Kp + k, os + mn * Kp + k, v);
+            store_split4(ob + mn * Kp + k, os + mn * Kp + k, v, nonfinite);
         }
     }
 }
 
 // one operand: vector kernel when the source allows 128-bit loads, the scalar tile kernel otherwise
 int launch_split_pack(const float* src, float* big, float* small, int64_t batch, int64_t MN, int64_t K, int64_t MNp,
-                      int64_t Kp, int64_t sb, int64_t smn, int64_t sk, cudaStream_t stream) {
+                      int64_t Kp, int64_t sb, int64_t smn, int64_t sk, unsigned* nonfinite, cudaStream_t stream) {
     if (MNp / 32 > 65535 || batch > 65535) EML_BAD_ARG("tf32x3: operand too large for the pack grid");
     const bool al = (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (sb & 3) == 0;
     dim3 vgrid((unsigned)((Kp + 63) / 64), (unsigned)((MNp + 63) / 64), (unsigned)batch);
     if (al && sk == 1 && (smn & 3) == 0) {
-        launch_k(split_pack_vec_kernel<true>, dim3(vgrid), dim3(256), 0, stream, src, big, small, MN, K, MNp, Kp, sb, smn);
+        launch_k(split_pack_vec_kernel<true>, dim3(vgrid), dim3(256), 0, stream, src, big, small, MN, K, MNp, Kp, sb, smn, nonfinite);
     } else if (al && smn == 1 && (sk & 3) == 0) {
-        launch_k(split_pack_vec_kernel<false>, dim3(vgrid), dim3(256), 0, stream, src, big, small, MN, K, MNp, Kp, sb, sk);
+        launch_k(split_pack_vec_kernel<false>, dim3(vgrid), dim3(256), 0, stream, src, big, small, MN, K, MNp, Kp, sb, sk, nonfinite);
     } else {
         dim3 grid((unsigned)(Kp / 32), (unsigned)(MNp / 32), (unsigned)batch);
-        launch_k(split_pack_kernel, dim3(grid), dim3(256), 0, stream, src, big, small, MN, K, MNp, Kp, sb, smn, sk, sk == 1);
+        launch_k(split_pack_kernel, dim3(grid), dim3(256), 0, stream, src, big, small, MN, K, MNp, Kp, sb, smn, sk, sk == 1, nonfinite);
     }
     count_launch();
     return check_launch("tf32x3 split/pack");
@@ -682,16 +688,20 @@ void pack_evict_locked(const PackKey& key) {
 }
 
 // big / small planes of one operand: from the cache when `id` is set (packing on a miss), else into `scratch`
+// *flag: where this operand's "non-finite input seen" word lives -- the stream's shared word for a scratch pack (the
+// repair kernel clears it), a word behind the planes for a cached operand (it describes the cached planes for as long
+// as they live)
 int packed_operand(uint64_t id, const float* src, int64_t batch, int64_t MN, int64_t K, int64_t MNp, int64_t Kp,
                    int64_t sb, int64_t smn, int64_t sk, TempBuf& scratch, cudaStream_t stream, float** big,
-                   float** small) {
+                   float** small, unsigned* stream_flag, const unsigned** flag) {
     const size_t plane = (size_t)(batch * MNp * Kp);
-    const size_t bytes = sizeof(float) * 2 * plane;
+    const size_t bytes = sizeof(float) * 2 * plane + 256;  // + the cached operand's flag word
     if (id == 0) {
         EML_TRY(scratch.alloc(bytes, stream));
         *big = scratch.as<float>();
         *small = *big + plane;
-        return launch_split_pack(src, *big, *small, batch, MN, K, MNp, Kp, sb, smn, sk, stream);
+        *flag = stream_flag;
+        return launch_split_pack(src, *big, *small, batch, MN, K, MNp, Kp, sb, smn, sk, stream_flag, stream);
     }
     int dev = 0;
     EML_CUDA(cudaGetDevice(&dev));
@@ -702,6 +712,7 @@ int packed_operand(uint64_t id, const float* src, int64_t batch, int64_t MN, int
         if (it != g_pack.end()) {
             *big = it->second.planes;
             *small = *big + plane;
+            *flag = reinterpret_cast<const unsigned*>(*big + 2 * plane);
             return EML_OK;
         }
     }
@@ -709,7 +720,10 @@ int packed_operand(uint64_t id, const float* src, int64_t batch, int64_t MN, int
     EML_TRY(stream_alloc(&p, bytes, stream));
     *big = static_cast<float*>(p);
     *small = *big + plane;
-    EML_TRY(launch_split_pack(src, *big, *small, batch, MN, K, MNp, Kp, sb, smn, sk, stream));
+    unsigned* own_flag = reinterpret_cast<unsigned*>(*big + 2 * plane);
+    *flag = own_flag;
+    EML_CUDA(cudaMemsetAsync(own_flag, 0, sizeof(unsigned), stream));
+    EML_TRY(launch_split_pack(src, *big, *small, batch, MN, K, MNp, Kp, sb, smn, sk, own_flag, stream));
     std::lock_guard<std::mutex> lock(g_pack_mu);
     while (g_pack_bytes + bytes > PACK_CACHE_LIMIT && !g_pack_order.empty()) {
         pack_evict_locked(g_pack_order.front());
@@ -812,19 +826,31 @@ int launch_gemm_tf32x3_f32(DeviceCtx* ctx, const float* A, const float* B, float
         const bool want = fe ? fe[0] == '1' : pays;
         if (want) {
             bool fused = false;
-            EML_TRY(launch_gemm_tf32x3_fused(ctx, A, B, C, batch, M, N, K, sA, sB, sC, splits, accumulate, stream, &fused));
-            if (fused) return EML_OK;
+            unsigned* tk = nullptr;
+            EML_TRY(stream_tickets(stream, &tk));
+            EML_TRY(launch_gemm_tf32x3_fused(ctx, A, B, C, batch, M, N, K, sA, sB, sC, splits, accumulate, stream, &fused,
+                                             tk + TICKET_NONFINITE));
+            if (fused) {
+                if (!accumulate)
+                    EML_TRY(launch_tf32_repair(A, B, C, batch, M, N, K, sA, sB, sC, nullptr, nullptr, tk + TICKET_NONFINITE, stream));
+                return EML_OK;
+            }
         }
     }
     TempBuf a_scratch, b_scratch, wsbuf;
     float *a_big, *a_small, *b_big, *b_small;
-    EML_TRY(packed_operand(a_id, A, batch, M, K, Mp, Kp, sA.b, sA.r, sA.c, a_scratch, stream, &a_big, &a_small));
+    unsigned* tickets = nullptr;
+    EML_TRY(stream_tickets(stream, &tickets));
+    unsigned* stream_flag = tickets + TICKET_NONFINITE;
+    const unsigned *a_flag = nullptr, *b_flag = nullptr;
+    EML_TRY(packed_operand(a_id, A, batch, M, K, Mp, Kp, sA.b, sA.r, sA.c, a_scratch, stream, &a_big, &a_small, stream_flag, &a_flag));
     // B element (k, n) at B[k*sB.r + n*sB.c]: its "mn" index is n
     if (upper_only) {  // B is the same matrix read through mirrored strides: the planes just packed serve both sides
         b_big = a_big;
         b_small = a_small;
+        b_flag = a_flag;
     } else {
-        EML_TRY(packed_operand(b_id, B, batch, N, K, Np, Kp, sB.b, sB.c, sB.r, b_scratch, stream, &b_big, &b_small));
+        EML_TRY(packed_operand(b_id, B, batch, N, K, Np, Kp, sB.b, sB.c, sB.r, b_scratch, stream, &b_big, &b_small, stream_flag, &b_flag));
     }
     float* ws = nullptr;
     if (splits > 1) {
@@ -842,10 +868,60 @@ int launch_gemm_tf32x3_f32(DeviceCtx* ctx, const float* A, const float* B, float
     if (use_pair) {
         EML_TRY(pair::launch(maps, C, batch, M, N, sC.r, sC.b, kblocks, splits, sms, accumulate, ws, stream, upper_only));
         if (upper_only) opt->upper_done = true;
-        return EML_OK;
+    } else if (BN == 256) {
+        EML_TRY(launch_tile<256>(maps, C, batch, M, N, sC.r, sC.b, kblocks, splits, accumulate, ws, stream));
+    } else {
+        EML_TRY(launch_tile<128>(maps, C, batch, M, N, sC.r, sC.b, kblocks, splits, accumulate, ws, stream));
     }
-    if (BN == 256) return launch_tile<256>(maps, C, batch, M, N, sC.r, sC.b, kblocks, splits, accumulate, ws, stream);
-    return launch_tile<128>(maps, C, batch, M, N, sC.r, sC.b, kblocks, splits, accumulate, ws, stream);
+    // (an accumulating launch has already folded the product into C's previous contents: nothing to recompute from;
+    //  the upper-triangle launch is mirrored afterwards by the caller, and repaired NaNs stay symmetric only if both
+    //  halves are recomputed: run the repair on the full matrix after the mirror is not possible here, so skip it)
+    if (!accumulate && !upper_only)
+        EML_TRY(launch_tf32_repair(A, B, C, batch, M, N, K, sA, sB, sC, a_flag, b_flag, stream_flag, stream));
+    return EML_OK;
+}
+
+namespace {
+__global__ void __launch_bounds__(256)
+tf32_repair_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C, int64_t batch, int64_t M,
+                   int64_t N, int64_t K, Strides3 sA, Strides3 sB, Strides3 sC, const unsigned* flag_a,
+                   const unsigned* flag_b, unsigned* stream_flag, unsigned* ticket) {
+    pdl_prologue();
+    // every block reads the flags, then draws a ticket; the block drawing the last one clears the stream's shared word
+    // (all the others have read it by then)
+    __shared__ unsigned seen;
+    if (threadIdx.x == 0) {
+        seen = ((flag_a && *flag_a) || (flag_b && *flag_b) || *stream_flag) ? 1u : 0u;
+        __threadfence();
+        if (atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1) *stream_flag = 0u;
+    }
+    __syncthreads();
+    if (!seen) return;
+    const int64_t total = batch * M * N;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = e / (M * N), i = (e / N) % M, j = e % N;
+        float* c = C + b * sC.b + i * sC.r + j * sC.c;
+        if (*c == *c) continue;  // only NaNs can be artefacts of the split (0 * inf in a cross term, inf - inf between terms)
+        const float* a = A + b * sA.b + i * sA.r;
+        const float* bb = B + b * sB.b + j * sB.c;
+        float acc = 0.0f;
+        for (int64_t k = 0; k < K; k++) acc = fmaf(a[k * sA.c], bb[k * sB.r], acc);
+        *c = acc;
+    }
+}
+}  // namespace
+
+int launch_tf32_repair(const float* A, const float* B, float* C, int64_t batch, int64_t M, int64_t N, int64_t K, Strides3 sA,
+                       Strides3 sB, Strides3 sC, const unsigned* flag_a, const unsigned* flag_b, unsigned* stream_flag,
+                       cudaStream_t stream) {
+    int64_t blocks = (batch * M * N + 255) / 256;
+    if (blocks > 148) blocks = 148;  // nothing to do in the common case; the rare repair is a slow path anyway
+    unsigned* tickets = nullptr;
+    EML_TRY(stream_tickets(stream, &tickets));
+    launch_k(tf32_repair_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, A, B, C, batch, M, N, K, sA, sB, sC,
+             flag_a == stream_flag ? nullptr : flag_a, flag_b == stream_flag ? nullptr : flag_b, stream_flag, tickets);
+    count_launch();
+    return check_launch("tf32 non-finite repair");
 }
 
 }  // namespace eml

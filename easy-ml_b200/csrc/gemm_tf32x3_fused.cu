@@ -77,7 +77,7 @@ __device__ __forceinline__ Work decode(int w, int tiles_m, int tiles_n, int spli
 constexpr int TASKS = 64, MAX_TASKS = (TASKS + CONV_WARPS - 1) / CONV_WARPS, GROUP_TASKS = 3;
 template <bool A_KIN, bool B_KIN>
 __device__ __forceinline__ void convert_block(const uint8_t* __restrict__ raw, uint8_t* __restrict__ op, int cw,
-                                              int lane) {
+                                              int lane, unsigned* nonfinite) {
 #pragma unroll
     for (int g = 0; g < MAX_TASKS; g += GROUP_TASKS) {
         float4 v[GROUP_TASKS];
@@ -109,6 +109,7 @@ __device__ __forceinline__ void convert_block(const uint8_t* __restrict__ raw, u
             if (g + i >= MAX_TASKS || t >= TASKS) continue;
             ordinary &= tf32::ordinary4(v[i]);
         }
+        if (!ordinary) *nonfinite = 1u;  // the repair kernel after the product recomputes the NaNs the split can cause
 #pragma unroll
         for (int i = 0; i < GROUP_TASKS; i++) {
             const int t = cw + CONV_WARPS * (g + i);
@@ -139,7 +140,7 @@ template <bool A_KIN, bool B_KIN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 tf32x3_fused_kernel(const __grid_constant__ Maps maps, float* __restrict__ C, int64_t M, int64_t N, int64_t ldc,
                     int64_t strideC, int kblocks_total, int per_split, int splits, int tiles_m, int tiles_n,
-                    int work_items, int accumulate, float* __restrict__ ws, int64_t ws_split_stride) {
+                    int work_items, int accumulate, float* __restrict__ ws, int64_t ws_split_stride, unsigned* nonfinite) {
     pdl_prologue();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -260,7 +261,7 @@ tf32x3_fused_kernel(const __grid_constant__ Maps maps, float* __restrict__ C, in
             mbar_wait(&raw_full[rs], (n / RAW_STAGES) & 1);
             if (n >= OP_STAGES) mbar_wait(&op_empty[os], ((n / OP_STAGES) - 1) & 1);
             convert_block<A_KIN, B_KIN>(raw_ring + (size_t)rs * RAW_STAGE_BYTES, op_ring + (size_t)os * OP_STAGE_BYTES,
-                                        cw, lane);
+                                        cw, lane, nonfinite);
             fence_proxy_async();  // this lane's tile writes become visible to the tensor core (async proxy)
             __syncwarp();
             if (lane == 0) {
@@ -393,7 +394,7 @@ int raw_map(CUtensorMap* map, const float* base, bool kin, int64_t rows, int64_t
 
 template <bool A_KIN, bool B_KIN>
 int launch(const Maps& maps, float* C, int64_t batch, int64_t M, int64_t N, int64_t ldc, int64_t strideC, int kblocks,
-           int splits, int sms, bool accumulate, float* ws, cudaStream_t stream) {
+           int splits, int sms, bool accumulate, float* ws, cudaStream_t stream, unsigned* nonfinite) {
     auto kern = tf32x3_fused_kernel<A_KIN, B_KIN>;
     static thread_local int configured_dev = -1;
     int dev = 0;
@@ -410,7 +411,7 @@ int launch(const Maps& maps, float* C, int64_t batch, int64_t M, int64_t N, int6
     int clusters = sms / 2;
     if (items < clusters) clusters = (int)items;
     EML_CUDA(launch_k(kern, dim3(2 * clusters), dim3(THREADS), SMEM_BYTES, stream, maps, C, M, N, ldc, strideC, kblocks,
-                      per_split, used_splits, tiles_m, tiles_n, (int)items, accumulate ? 1 : 0, ws, batch * M * N));
+                      per_split, used_splits, tiles_m, tiles_n, (int)items, accumulate ? 1 : 0, ws, batch * M * N, nonfinite));
     count_launch();
     EML_TRY(check_launch("tf32x3_tcgen05 (fused split)"));
     if (ws) EML_TRY(launch_splitk_reduce<float>(ws, used_splits, C, batch, M, N, Strides3{strideC, ldc, 1}, accumulate, stream));
@@ -426,7 +427,7 @@ inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) =
 // Returns with *handled = false when the operands do not meet TMA's alignment rules (the packed path takes over).
 int launch_gemm_tf32x3_fused(DeviceCtx* ctx, const float* A, const float* B, float* C, int64_t batch, int64_t M,
                              int64_t N, int64_t K, Strides3 sA, Strides3 sB, Strides3 sC, int splits, bool accumulate,
-                             cudaStream_t stream, bool* handled) {
+                             cudaStream_t stream, bool* handled, unsigned* nonfinite) {
     *handled = false;
     const bool a_kin = sA.c == 1, a_min = sA.r == 1;
     const bool b_nin = sB.c == 1, b_kin = sB.r == 1;
@@ -453,10 +454,10 @@ int launch_gemm_tf32x3_fused(DeviceCtx* ctx, const float* A, const float* B, flo
     const int sms = ctx ? ctx->sm_count : 148;
     *handled = true;
     set_last_kernel("tf32x3_tcgen05");
-    if (A_KIN && !B_KIN) return fz::launch<true, false>(maps, C, batch, M, N, sC.r, sC.b, kblocks, splits, sms, accumulate, ws, stream);
-    if (A_KIN && B_KIN) return fz::launch<true, true>(maps, C, batch, M, N, sC.r, sC.b, kblocks, splits, sms, accumulate, ws, stream);
-    if (!A_KIN && !B_KIN) return fz::launch<false, false>(maps, C, batch, M, N, sC.r, sC.b, kblocks, splits, sms, accumulate, ws, stream);
-    return fz::launch<false, true>(maps, C, batch, M, N, sC.r, sC.b, kblocks, splits, sms, accumulate, ws, stream);
+    if (A_KIN && !B_KIN) return fz::launch<true, false>(maps, C, batch, M, N, sC.r, sC.b, kblocks, splits, sms, accumulate, ws, stream, nonfinite);
+    if (A_KIN && B_KIN) return fz::launch<true, true>(maps, C, batch, M, N, sC.r, sC.b, kblocks, splits, sms, accumulate, ws, stream, nonfinite);
+    if (!A_KIN && !B_KIN) return fz::launch<false, false>(maps, C, batch, M, N, sC.r, sC.b, kblocks, splits, sms, accumulate, ws, stream, nonfinite);
+    return fz::launch<false, true>(maps, C, batch, M, N, sC.r, sC.b, kblocks, splits, sms, accumulate, ws, stream, nonfinite);
 }
 
 }  // namespace eml

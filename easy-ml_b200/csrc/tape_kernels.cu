@@ -167,7 +167,7 @@ quirk_cols_kernel(const T* __restrict__ G, int64_t gm, int64_t g_rows, const T* 
     }
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) last = atomicInc(tickets + 4095, gridDim.x - 1) == gridDim.x - 1;
+    if (threadIdx.x == 0) last = atomicInc(tickets + TICKET_SECOND_LEVEL, gridDim.x - 1) == gridDim.x - 1;
     __syncthreads();
     if (!last) return;
     __threadfence();
@@ -419,7 +419,7 @@ template <class T>
 int launch_quirk_cols(const T* G, int64_t gm, const T* B, int64_t bm, int64_t N, T* out, cudaStream_t stream) {
     if (gm < 1 || bm < 1 || N < 1) return EML_OK;
     const int64_t col_blocks = (N + 31) / 32;
-    if (col_blocks > 4095) EML_BAD_ARG("constant-operand sums: more than %d columns", 4095 * 32);
+    if (col_blocks > TICKET_NONFINITE) EML_BAD_ARG("constant-operand sums: more than %d columns", TICKET_NONFINITE * 32);
     // row chunks: ~2 CTAs per SM over the whole grid, at least 64 rows of the taller matrix each
     const int64_t rows = gm > bm ? gm : bm;
     int64_t chunks = (4 * 148 + col_blocks - 1) / col_blocks;  // short chunks: a few batches of loads per thread

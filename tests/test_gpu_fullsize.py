@@ -153,11 +153,20 @@ def test_config4_nn_step_batch_8192():
     want_g1 = X64.T @ dh
     assert abs(float(loss.numbers().data[0, 0]) - want_loss) <= 1e-5 * want_loss
     # the reference's constant-operand quirk routes the constants' would-be gradient into derivatives[0],
-    # i.e. into w1[0,0]'s slot (container_operations.rs:1291-1296): exclude that one element
+    # i.e. into w1[0,0]'s slot (container_operations.rs:1291-1296): that element is checked against its own closed form
     mask = np.ones_like(g1, dtype=bool)
     mask[0, 0] = False
     scale1 = np.abs(X64).T @ np.abs(dh)
     assert np.all(np.abs(g1.astype(np.float64) - want_g1)[mask] <= (2e-5 * scale1 + 1e-9)[mask])
+    # derivatives[0] = dW1[0,0]
+    #   + sum_ik (dZ1 W1^T)[i,k]           X is a constant operand of X * W1: its whole would-be gradient
+    #   + sum_kj (dS^T sq)...= loss        L (ones row) is a constant operand of L * sq: sum_j dS[j] colsum(sq)[j], dS = 1/batch
+    #   + sum_k  S[k] dT = loss            R (ones column) is a constant operand of S * R: dT = 1/batch
+    want_d0 = want_g1[0, 0] + float((dh @ W164.T).sum()) + 2.0 * want_loss
+    scale_d0 = scale1[0, 0] + float((np.abs(dh) @ np.abs(W164).T).sum()) + 2.0 * want_loss
+    assert abs(float(g1[0, 0]) - want_d0) <= 2e-5 * scale_d0
+    assert abs(float(d.at_index(0)) - want_d0) <= 2e-5 * scale_d0
+    assert abs(want_d0 - want_g1[0, 0]) > 100 * 2e-5 * scale1[0, 0]   # the quirk is far outside dW1[0,0]'s own tolerance
     assert np.all(np.abs(g2.astype(np.float64) - want_g2) <= 2e-5 * (np.abs(h).T @ np.abs(do)) + 1e-9)
 
 

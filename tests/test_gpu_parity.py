@@ -787,11 +787,14 @@ def test_gemm_scatter_epilogue_writes_every_destination(m, n, k, aligned):
     assert torch.equal(dst, a)
 
 
-def test_sgemm_non_finite_and_huge_values():
-    """inf, nan and near-FLT_MAX entries through the 3xTF32 path.  Near-overflow values must stay finite (the split
-    truncates instead of rounding FLT_MAX up to infinity).  Documented deviation: an infinite entry comes out
-    non-finite but possibly as NaN where the reference gives +-inf, because the OTHER operand's zero small part
-    meets it (0 * inf) in the cross terms of the split; nan propagates as nan."""
+def test_sgemm_non_finite_and_huge_values(orc):
+    """inf, nan and near-FLT_MAX entries through the 3xTF32 path behave as in the reference's plain f32 products:
+    an infinite entry gives +-inf (not the NaN its meeting the other operand's zero small part would give: the split
+    passes flag non-finite inputs and a repair pass recomputes the NaNs as f32 fma chains), NaN stays NaN, and where
+    the reference itself produces NaN (inf - inf, 0 * inf) so does the GPU.  Near-overflow values stay finite (the
+    split truncates instead of rounding FLT_MAX up to infinity).  Host entry point and device-resident entry point,
+    the packed kernels and the in-kernel-split kernel."""
+    torch = pytest.importorskip("torch")
     m = n = k = 256
     a = np.zeros((m, k), np.float32)
     b = np.zeros((k, n), np.float32)
@@ -799,17 +802,47 @@ def test_sgemm_non_finite_and_huge_values():
     b[:] = rng(2700).uniform(-1, 1, (k, n)).astype(np.float32)
     b[0, 0], b[1, 1], b[2, 2], b[3, 3] = np.inf, -np.inf, np.nan, np.finfo(np.float32).max
     b[4, 4] = -np.finfo(np.float32).max
+    a[7, 9] = np.inf                               # row 7 of C: b[7, :] + inf * b[9, :]  -> +-inf by the sign of b[9, j]
+    a[8, 0], a[8, 1] = 1.0, 1.0                    # C[8, 0] = b[8, 0] + inf + b[1, 0] = inf; C[8, 1] = ... - inf
     with np.errstate(all="ignore"):
+        want = orc.matrix_mul(a, b, threads=4)     # the reference's own arithmetic on these operands
         got = gemm(a, b)
     assert eml.last_kernel() == "tf32x3_tcgen05"
-    assert not np.isfinite(got[0, 0]) and not np.isfinite(got[1, 1]) and np.isnan(got[2, 2])
+    assert got[0, 0] == np.inf and got[1, 1] == -np.inf and np.isnan(got[2, 2])
     assert np.isfinite(got[3, 3]) and got[3, 3] >= np.float32(3.4e38) and got[4, 4] <= np.float32(-3.4e38)
-    finite = np.isfinite(b)
-    # every other entry of the rows / columns without special values is the usual f32-accurate copy of B
-    clean = np.ones_like(b, dtype=bool)
-    clean[:5, :] = False
-    clean[:, :5] = False
-    assert np.allclose(got[clean], b[clean], rtol=1e-6, atol=0) and finite.sum() > 0
+    nonfinite = ~np.isfinite(want)
+    assert nonfinite.sum() >= 256 + 4
+    assert np.array_equal(np.isnan(got), np.isnan(want))                       # NaN exactly where the reference has NaN
+    assert np.array_equal(got[nonfinite & ~np.isnan(want)], want[nonfinite & ~np.isnan(want)])   # +-inf with its sign
+    clean = np.isfinite(want)
+    clean[3, 3] = clean[4, 4] = False
+    assert np.allclose(got[clean], want[clean], rtol=1e-5, atol=1e-6)
+    # device-resident call, a larger product that takes the CTA-pair kernel, and a clean product afterwards (the
+    # stream's flag has been cleared: nothing is recomputed, same bits as before any non-finite input was seen)
+    r = rng(2701)
+    a2, b2 = uniform(r, (512, 384), np.float32), uniform(r, (384, 640), np.float32)
+    before = gemm(a2, b2)
+    a3 = a2.copy()
+    a3[5, 17], a3[300, 0] = -np.inf, np.inf
+    with np.errstate(all="ignore"):
+        want3 = orc.matrix_mul(a3, b2, threads=4)
+        got3 = gemm(a3, b2)
+    assert np.array_equal(np.isnan(got3), np.isnan(want3))
+    inf3 = np.isinf(want3)
+    assert inf3.sum() == 2 * 640 and np.array_equal(got3[inf3], want3[inf3])
+    assert np.array_equal(gemm(a2, b2), before)
+    # the batched contraction whose kernel splits in shared memory (config 3's path)
+    x = torch.rand((4, 1024, 1024), device="cuda") - 0.5
+    y = torch.rand((4, 1024, 1024), device="cuda") - 0.5
+    x[2, 100, 7] = float("inf")
+    out = torch.empty((4, 1024, 1024), device="cuda")
+    s3 = lambda t: (C.c_int64 * 3)(*t.stride())
+    vp = lambda t: C.c_void_p(t.data_ptr())
+    check(lib.eml_contract_f32_dev(vp(x), vp(y), vp(out), 4, 1024, 1024, 1024, s3(x), s3(y), s3(out), 0, None))
+    torch.cuda.synchronize()
+    row = out[2, 100]
+    assert bool(torch.isinf(row).all()) and bool((torch.sign(row) == torch.sign(y[2, 7])).all())
+    assert bool(torch.isfinite(out[2, 99]).all()) and bool(torch.isfinite(out[3]).all())
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
