@@ -7,7 +7,7 @@ host.py + distributions.py (Python mirror of the reference operator API and of t
 """
 from . import _ffi  # raises ImportError when the CUDA library is not built: there is no fallback
 from ._ffi import EmlError, NoDeviceError, BadArgError, StateError, OPS, lib
-from .host import (Derivatives, Einsum, InconsistentDimensionLengthError, Matrix, Panic, PinnedBuffer, RecordMatrix,
+from .host import (Derivatives, Einsum, InconsistentDimensionLengthError, Matrix, Panic, PinnedBuffer, Record, RecordMatrix,
                    RecordTensor, RecordedStep, Tensor, WengertList, sgd_update, wait_arrival)
 from .device import DeviceMatrix, DeviceTensor
 from .distributions import (Gaussian, MultivariateGaussian, MultivariateGaussianError, MultivariateGaussianTensor,

@@ -87,6 +87,10 @@ SIGNATURES = {
     "eml_tape_constants_dev": (cint, [vp, vp, i64, i64, pi64]),
     "eml_tape_from_existing": (cint, [vp, vp, vp, i64, i64, cint, pi64]),
     "eml_tape_range": (cint, [vp, i64, i64, i64, i64, i64, cint, pi64]),
+    "eml_tape_append_nullary": (cint, [vp, pi64]),
+    "eml_tape_append_unary": (cint, [vp, i64, C.c_double, pi64]),
+    "eml_tape_append_binary": (cint, [vp, i64, C.c_double, i64, C.c_double, pi64]),
+    "eml_tape_derivatives_at": (cint, [vp, i64, C.POINTER(vp)]),
     "eml_tape_reset": (cint, [vp, i64]),
     "eml_val_release": (cint, [vp, i64]),
     "eml_val_shape": (cint, [vp, i64, pi64, pi64, C.POINTER(cint)]),

@@ -299,6 +299,9 @@ int launch_quirk_rows(const T* A, int64_t K, const T* G, int64_t N, int64_t M, T
 template <class T>
 int launch_scatter_segments(const T* g, const int* perm, const int* seg_start, int n_seg, T* arena, const int64_t* seg_off,
                             cudaStream_t stream);
+template <class T>
+int launch_scalar_run(T* arena, int64_t self_off, int64_t n, const int64_t* lp, const int64_t* rp, const T* ld, const T* rd,
+                      cudaStream_t stream);
 bool thin_shape(int64_t M, int64_t N, int64_t K);
 template <class T>
 int launch_thin_fwd(const T* A, int64_t sAr, int64_t sAc, const T* B, int64_t M, int64_t N, int64_t K, T* C, int64_t sCr,

@@ -54,7 +54,17 @@ int new_buf(size_t bytes, cudaStream_t s, Buf* out) {
     return EML_OK;
 }
 
-enum class Kind { VARIABLES, UNARY, BINARY, MATMUL, VIEW };
+enum class Kind { VARIABLES, UNARY, BINARY, MATMUL, VIEW, SCALARS };
+
+// A run of consecutive SCALAR tape entries -- what the scalar Record operators append one at a time
+// (WengertList::append_nullary / append_unary / append_binary, reference src/differentiation.rs:811-878) -- so that
+// scalar Records and containers share one list and one index space (the reference's network examples fold container
+// outputs into scalar Records, src/neural_networks.rs:105-131).  Entries are kept on the host; the sweep uploads a run
+// and walks it with one thread in descending order: exactly the reference's loop (:632-645), bit for bit.
+struct ScalarRun {
+    std::vector<int64_t> lp, rp;
+    std::vector<double> ld, rd;
+};
 
 // The (T, Index) pairs of a container built by RecordTensor::from_existing / RecordMatrix::from_existing (reference
 // container_record/mod.rs:219-224, :508): any index per element -- a range or mask of another container, a row of a
@@ -103,6 +113,7 @@ struct Node {
     Buf xin, yin;          // operand numbers living outside the group (kept alive: the backward pass recomputes)
     Buf value;             // this node's numbers once somebody needed them (null: interior, never stored)
     std::shared_ptr<IndexMap> map;  // Kind::VIEW: where the container's derivatives go (stands for NO tape entries)
+    std::shared_ptr<ScalarRun> run;  // Kind::SCALARS: the entries (the first `n` of the run belong to this copy of the node)
     // index of element e of the produced container on the reference tape
     int64_t index_of(int64_t e) const {
         if (kind == Kind::MATMUL && K > 1) return base + e * (2 * K - 1) + 2 * K - 2;
@@ -841,6 +852,45 @@ int scatter_view(eml_tape* t, eml_derivs* d, const Node& nd, const T* g, const B
                                       static_cast<T*>(arena->p), dev_off.as<int64_t>(), st);
 }
 
+// The sweep of a run of scalar entries: parents resolved to arena offsets on the host, one thread walks the run.
+template <class T>
+int sweep_scalars(eml_tape* t, eml_derivs* d, const Node& nd, int64_t self_off, const Buf& arena, const std::vector<size_t>& offs,
+                  cudaStream_t st) {
+    if (t->capturing) {
+        set_error("scalar Record entries cannot be swept inside a recorded step (the run is uploaded per sweep)");
+        return EML_ERR_STATE;
+    }
+    const size_t n = (size_t)nd.n;
+    d->scatter_offsets.emplace_back(2 * n);
+    std::vector<int64_t>& off = d->scatter_offsets.back();
+    int cached = -1;
+    auto resolve = [&](int64_t index, int64_t* out) -> int {
+        if (cached < 0 || index < d->nodes[cached].base || index >= d->nodes[cached].base + d->nodes[cached].count)
+            cached = node_of_index(d->nodes, index);
+        if (cached < 0) {
+            set_error("index out of bounds: the len is %lld but the index is %lld", (long long)d->len, (long long)index);
+            return EML_ERR_STATE;
+        }
+        *out = (int64_t)(offs[cached] / sizeof(T)) + d->nodes[cached].element_of(index);
+        return EML_OK;
+    };
+    std::vector<T> der(2 * n);
+    for (size_t e = 0; e < n; e++) {
+        EML_TRY(resolve(nd.run->lp[e], &off[e]));
+        EML_TRY(resolve(nd.run->rp[e], &off[n + e]));
+        der[e] = (T)nd.run->ld[e];
+        der[n + e] = (T)nd.run->rd[e];
+    }
+    TempBuf dev_off, dev_der;
+    EML_TRY(dev_off.alloc(sizeof(int64_t) * 2 * n, st));
+    EML_TRY(dev_der.alloc(sizeof(T) * 2 * n, st));
+    EML_CUDA(cudaMemcpyAsync(dev_off.p, off.data(), sizeof(int64_t) * 2 * n, cudaMemcpyHostToDevice, st));
+    EML_CUDA(cudaMemcpyAsync(dev_der.p, der.data(), sizeof(T) * 2 * n, cudaMemcpyHostToDevice, st));
+    EML_CUDA(cudaStreamSynchronize(st));  // `der` dies with this call
+    return launch_scalar_run<T>(static_cast<T*>(arena->p), self_off, (int64_t)n, dev_off.as<int64_t>(), dev_off.as<int64_t>() + n,
+                                dev_der.as<T>(), dev_der.as<T>() + n, st);
+}
+
 // Does the sweep of matmul node c WRITE (0 + sum, not +=) the derivatives of its parent `parent` when it is the first
 // to contribute to them?  True for the kernels that start their fma chain from +0 themselves: the thin (M <= 4)
 // backward, and dA = G * B^T through the short-contraction kernel.  (Such a parent needs no zero fill and is not read.)
@@ -851,6 +901,9 @@ bool matmul_overwrites(const Node& c, int parent, size_t elem) {
 }
 
 // The reverse sweep over macro nodes.
+template <class T>
+int sweep_from(eml_tape* t, int nv, int64_t seed_elem, eml_derivs** out);
+
 template <class T>
 int tape_sweep(eml_tape* t, eml_val hv, int64_t row, int64_t col, eml_derivs** out) {
     Value* v;
@@ -871,6 +924,13 @@ int tape_sweep(eml_tape* t, eml_val hv, int64_t row, int64_t col, eml_derivs** o
         return EML_ERR_STATE;
     }
     EML_TRY(flush_open<T>(t));
+    return sweep_from<T>(t, nv, row * v->cols + col, out);
+}
+
+// Record::try_derivatives (reference src/differentiation.rs:623-648) seeded at element `seed_elem` of node `nv`
+// (nv < 0: a container whose every Index is 0).
+template <class T>
+int sweep_from(eml_tape* t, int nv, int64_t seed_elem, eml_derivs** out) {
     cudaStream_t st = t->stream;
     auto d = std::make_unique<eml_derivs>();
     d->tape = t;
@@ -907,6 +967,16 @@ int tape_sweep(eml_tape* t, eml_val hv, int64_t row, int64_t col, eml_derivs** o
             }
             continue;
         }
+        if (nd.kind == Kind::SCALARS) {  // every entry adds to its parents' entries
+            int last = -1;
+            for (int64_t e = 0; e < nd.n; e++)
+                for (int64_t index : {nd.run->lp[(size_t)e], nd.run->rp[(size_t)e]}) {
+                    if (last >= 0 && index >= t->nodes[last].base && index < t->nodes[last].base + t->nodes[last].count) continue;
+                    last = node_of_index(t->nodes, index);
+                    if (last >= 0) first_consumer[last] = i;
+                }
+            continue;
+        }
         const bool uses0 = nd.kind == Kind::BINARY ? nd.p0_tracked : true, uses1 = nd.kind == Kind::BINARY ? nd.p1_tracked : nd.kind == Kind::MATMUL;
         if (uses0 && nd.p0 >= 0) first_consumer[nd.p0] = i;
         if (uses1 && nd.p1 >= 0) first_consumer[nd.p1] = i;
@@ -922,7 +992,7 @@ int tape_sweep(eml_tape* t, eml_val hv, int64_t row, int64_t col, eml_derivs** o
             if (i == nv) seed_in_kernel = true;
             continue;
         }
-        const bool overwritten_first = c >= 0 && i != nv && t->nodes[c].kind != Kind::VIEW &&
+        const bool overwritten_first = c >= 0 && i != nv && t->nodes[c].kind != Kind::VIEW && t->nodes[c].kind != Kind::SCALARS &&
                                        (t->nodes[c].kind != Kind::MATMUL || matmul_overwrites(t->nodes[c], i, sizeof(T)));
         written[i] = !overwritten_first;  // "written" = holds defined numbers (zeros) before the sweep
     }
@@ -945,7 +1015,7 @@ int tape_sweep(eml_tape* t, eml_val hv, int64_t row, int64_t col, eml_derivs** o
     if (nv >= 0 && seed_in_kernel) {
         // the seed is an argument of the fused group's kernel
     } else if (nv >= 0) {
-        EML_TRY(launch_fill<T>((T*)d->grads[nv]->p + (row * v->cols + col), T(1), 1, st));
+        EML_TRY(launch_fill<T>((T*)d->grads[nv]->p + seed_elem, T(1), 1, st));
     } else {
         EML_TRY(launch_fill<T>(slot0_ptr, T(1), 1, st));
         slot0_used = true;
@@ -965,9 +1035,13 @@ int tape_sweep(eml_tape* t, eml_val hv, int64_t row, int64_t col, eml_derivs** o
             EML_TRY(scatter_view<T>(t, d.get(), nd, g, arena, offs, st));
             continue;
         }
+        if (nd.kind == Kind::SCALARS) {
+            EML_TRY(sweep_scalars<T>(t, d.get(), nd, (int64_t)(offs[i] / sizeof(T)), arena, offs, st));
+            continue;
+        }
         if (nd.group >= 0) {  // the whole run [first, last] in one kernel
             const Group& grp = t->groups[nd.group];
-            EML_TRY(group_backward<T>(t->nodes, grp, d->grads, written, d->have, nv, row * v->cols + col, false, st));
+            EML_TRY(group_backward<T>(t->nodes, grp, d->grads, written, d->have, nv, seed_elem, false, st));
             i = grp.first;
             continue;
         }
@@ -1172,6 +1246,52 @@ int eml_tape_range(eml_tape* t, eml_val src, int64_t row0, int64_t n_rows, int64
     EML_CUDA(cudaMemcpy2DAsync(numbers->p, n_cols * es, (const char*)v->numbers->p + (row0 * v->cols + col0) * es, v->cols * es,
                                n_cols * es, n_rows, cudaMemcpyDeviceToDevice, t->stream));
     return put_view(t, numbers, n_rows, n_cols, map, has_history != 0, out);
+}
+
+static int append_scalar(eml_tape* t, int64_t lp, double ld, int64_t rp, double rd, int64_t* index) {
+    EML_TRY(check_tape(t));
+    if (!index) EML_BAD_ARG("null argument");
+    std::lock_guard<std::mutex> lock(t->mu);
+    if (lp < 0 || rp < 0 || lp > t->len || rp > t->len)  // (== len: the entry's own index, which append_nullary never uses)
+        EML_BAD_ARG("scalar entry: parent index out of bounds (the len is %lld)", (long long)t->len);
+    if (t->nodes.empty() || t->nodes.back().kind != Kind::SCALARS || t->open >= 0) {
+        EML_TRY(flush(t));
+        Node nd;
+        nd.kind = Kind::SCALARS;
+        nd.base = t->len;
+        nd.run = std::make_shared<ScalarRun>();
+        t->nodes.push_back(nd);
+    }
+    Node& nd = t->nodes.back();
+    nd.run->lp.push_back(lp);
+    nd.run->rp.push_back(rp);
+    nd.run->ld.push_back(ld);
+    nd.run->rd.push_back(rd);
+    nd.n = ++nd.count;
+    *index = t->len++;
+    return EML_OK;
+}
+
+int eml_tape_append_nullary(eml_tape* t, int64_t* index) { return append_scalar(t, 0, 0.0, 0, 0.0, index); }
+int eml_tape_append_unary(eml_tape* t, int64_t parent, double derivative, int64_t* index) {
+    return append_scalar(t, parent, derivative, 0, 0.0, index);
+}
+int eml_tape_append_binary(eml_tape* t, int64_t left_parent, double left_derivative, int64_t right_parent,
+                           double right_derivative, int64_t* index) {
+    return append_scalar(t, left_parent, left_derivative, right_parent, right_derivative, index);
+}
+
+int eml_tape_derivatives_at(eml_tape* t, int64_t index, eml_derivs** out) {
+    EML_TRY(check_tape(t));
+    if (!out) EML_BAD_ARG("null argument");
+    std::lock_guard<std::mutex> lock(t->mu);
+    EML_TRY(flush(t));
+    const int nv = node_of_index(t->nodes, index);
+    if (nv < 0) EML_BAD_ARG("index out of bounds: the len is %lld but the index is %lld", (long long)t->len, (long long)index);
+    const int64_t elem = t->nodes[nv].element_of(index);
+    if (t->nodes[nv].index_of(elem) != index)
+        EML_BAD_ARG("index %lld is an entry inside a matrix product, not a Record's", (long long)index);
+    return TAPE_DISPATCH(t, sweep_from<float>(t, nv, elem, out), sweep_from<double>(t, nv, elem, out));
 }
 
 int eml_tape_reset(eml_tape* t, eml_val h) {

@@ -481,6 +481,31 @@ int launch_scatter_segments(const T* g, const int* perm, const int* seg_start, i
     return check_launch("derivative scatter of a re-wrapped container");
 }
 
+namespace {
+// the reference's reverse loop (src/differentiation.rs:632-645) over one run of scalar entries: sequential by nature
+// (an entry's parents may be earlier entries of the same run), so one thread walks it
+template <class T>
+__global__ void scalar_run_kernel(T* arena, int64_t self_off, int64_t n, const int64_t* __restrict__ lp, const int64_t* __restrict__ rp,
+                                  const T* __restrict__ ld, const T* __restrict__ rd) {
+    pdl_prologue();
+    if (blockIdx.x || threadIdx.x) return;
+    for (int64_t e = n - 1; e >= 0; e--) {
+        const T g = arena[self_off + e];
+        arena[lp[e]] = arena[lp[e]] + g * ld[e];
+        arena[rp[e]] = arena[rp[e]] + g * rd[e];
+    }
+}
+}  // namespace
+
+template <class T>
+int launch_scalar_run(T* arena, int64_t self_off, int64_t n, const int64_t* lp, const int64_t* rp, const T* ld, const T* rd,
+                      cudaStream_t stream) {
+    if (n < 1) return EML_OK;
+    launch_k(scalar_run_kernel<T>, dim3(1), dim3(32), 0, stream, arena, self_off, n, lp, rp, ld, rd);
+    count_launch();
+    return check_launch("scalar entries of the sweep");
+}
+
 bool thin_shape(int64_t M, int64_t N, int64_t K) { return M >= 1 && M <= TH_M && N >= 1 && N <= TH_N && K >= 1; }
 
 namespace {
@@ -635,6 +660,7 @@ int launch_gemm_smallk(const T* A, int64_t lda, const T* B, int64_t sBr, int64_t
 }
 
 #define EML_INST(T)                                                                                                       \
+    template int launch_scalar_run<T>(T*, int64_t, int64_t, const int64_t*, const int64_t*, const T*, const T*, cudaStream_t); \
     template int launch_scatter_segments<T>(const T*, const int*, const int*, int, T*, const int64_t*, cudaStream_t);     \
     template int launch_quirk_cols<T>(const T*, int64_t, const T*, int64_t, int64_t, T*, cudaStream_t);                   \
     template int launch_quirk_rows<T>(const T*, int64_t, const T*, int64_t, int64_t, T*, cudaStream_t);                   \

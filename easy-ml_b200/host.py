@@ -503,6 +503,88 @@ class PinnedBuffer:
             self._p = None
 
 
+class Record:
+    """easy_ml::differentiation::Record<T> (src/differentiation.rs:452-476): a number, an optional list, a tape index.
+    The operators follow src/differentiation/record_operations.rs (history None on a side -> append_unary with the
+    other side's rule, both Some -> append_binary) with the rules of src/differentiation/functions.rs; entries go to the
+    same device-backed list the containers use, so a Record taken from a container element
+    (RecordContainer::get_as_record) and folded with scalar arithmetic differentiates through both."""
+
+    __slots__ = ("number", "history", "index")
+
+    def __init__(self, number, history=None, index=0):
+        self.number, self.history, self.index = number, history, index
+
+    @staticmethod
+    def variable(x, history):  # :489-495: append_nullary
+        i = C.c_int64()
+        check(lib.eml_tape_append_nullary(history._h, C.byref(i)))
+        return Record(history.dtype.type(x), history, i.value)
+
+    @staticmethod
+    def constant(x, dtype=np.float64):  # :479-485
+        return Record(np.dtype(dtype).type(x), None, 0)
+
+    def reset(self):  # :512-520
+        if self.history is not None:
+            i = C.c_int64()
+            check(lib.eml_tape_append_nullary(self.history._h, C.byref(i)))
+            self.index = i.value
+
+    def _unary(self, number, derivative):
+        i = C.c_int64()
+        check(lib.eml_tape_append_unary(self.history._h, self.index, float(derivative), C.byref(i)))
+        return Record(number, self.history, i.value)
+
+    @staticmethod
+    def _binary(x, y, number, dx, dy):
+        _same_list(x.history, y.history)
+        i = C.c_int64()
+        check(lib.eml_tape_append_binary(x.history._h, x.index, float(dx), y.index, float(dy), C.byref(i)))
+        return Record(number, x.history, i.value)
+
+    def _coerce(self, o):
+        return o if isinstance(o, Record) else Record(type(self.number)(o), None, 0)
+
+    def _apply(self, o, z, dx, dy):
+        if self.history is None and o.history is None:
+            return Record(z)
+        if o.history is None:
+            return self._unary(z, dx)
+        if self.history is None:
+            return o._unary(z, dy)
+        return Record._binary(self, o, z, dx, dy)
+
+    def __add__(self, o):
+        o = self._coerce(o)
+        z = self.number + o.number
+        one = type(z)(1)
+        return self._apply(o, z, one, one)
+
+    def __sub__(self, o):
+        o = self._coerce(o)
+        z = self.number - o.number
+        one = type(z)(1)
+        return self._apply(o, z, one, -one)
+
+    def __mul__(self, o):
+        o = self._coerce(o)
+        return self._apply(o, self.number * o.number, o.number, self.number)
+
+    def __truediv__(self, o):
+        o = self._coerce(o)
+        z = self.number / o.number
+        one = type(z)(1)
+        return self._apply(o, z, one / o.number, -self.number / (o.number * o.number))
+
+    def derivatives(self):  # :606-648
+        if self.history is None:
+            raise Panic("Record has no WengertList to find derivatives from")
+        d = C.c_void_p()
+        check(lib.eml_tape_derivatives_at(self.history._h, self.index, C.byref(d)))
+        return Derivatives(self.history, d)
+
+
 def _same_list(a, b):
     if a is not None and b is not None and a is not b:
         raise Panic("Record containers must be using the same WengertList")
@@ -580,6 +662,11 @@ class _RecordContainer:
         out = np.empty(r * c, dtype=np.int64)
         check(lib.eml_val_indexes(self._owner._h, self._v, _ptr(out)))
         return out.reshape(self._lens())
+
+    def get_as_record(self, *position):
+        """RecordContainer::get_as_record (container_record/mod.rs:2569 / matrix :2511): element as a scalar Record."""
+        number = self._numbers()[tuple(position)]
+        return Record(number, self.history_list, int(self.indexes()[tuple(position)]))
 
     def reset(self):
         check(lib.eml_tape_reset(self._owner._h, self._v))
@@ -815,6 +902,9 @@ class Derivatives:
         n = C.c_int64()
         check(lib.eml_derivs_len(self._d, C.byref(n)))
         return n.value
+
+    def at(self, record):  # Derivatives::at(&record), src/differentiation.rs:387-392
+        return self.at_index(record.index)
 
     def at_index(self, index):  # Derivatives::at / Index<&Record>
         out = C.c_double()

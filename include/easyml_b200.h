@@ -325,6 +325,18 @@ int eml_tape_from_existing(eml_tape* t, const void* host_numbers, const int64_t*
  * device, indexes follow the source's elements. */
 int eml_tape_range(eml_tape* t, eml_val src, int64_t row0, int64_t n_rows, int64_t col0, int64_t n_cols, int has_history,
                    eml_val* out);
+/* The SCALAR Record operators on the same list: WengertList::append_nullary / append_unary / append_binary, reference
+ * src/differentiation.rs:811-878 (what Record::variable, and +, -, *, / ... between Records, record_operations.rs, push).
+ * *index = the new entry's tape index.  Scalar entries and containers share one index space, so Records taken from
+ * container elements and folded with scalar arithmetic (src/neural_networks.rs:105-131) differentiate through both.
+ * The sweep walks a run of scalar entries in the reference's own order: bit-exact for purely scalar tapes. */
+int eml_tape_append_nullary(eml_tape* t, int64_t* index);
+int eml_tape_append_unary(eml_tape* t, int64_t parent, double derivative, int64_t* index);
+int eml_tape_append_binary(eml_tape* t, int64_t left_parent, double left_derivative, int64_t right_parent,
+                           double right_derivative, int64_t* index);
+/* Record::derivatives / try_derivatives (src/differentiation.rs:606-648) of the Record at tape index `index`
+ * (a scalar Record's index, or a container element's). */
+int eml_tape_derivatives_at(eml_tape* t, int64_t index, eml_derivs** out);
 /* RecordTensor::reset, mod.rs:349-365: re-append rows*cols nullary entries and renumber start + i. */
 int eml_tape_reset(eml_tape* t, eml_val v);
 int eml_val_release(eml_tape* t, eml_val v); /* drop a container (its node stays while referenced) */

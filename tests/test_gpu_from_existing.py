@@ -117,3 +117,76 @@ def test_from_existing_rejects_indexes_that_are_not_on_the_list():
     eml.RecordTensor.variables(hist, eml.Tensor([("r", 1), ("c", 2)], np.ones((1, 2))))
     with pytest.raises(eml.BadArgError):
         eml.RecordTensor.from_existing(hist, [("a", 1), ("b", 2)], np.ones((1, 2)), np.array([[0, 2]]))
+
+
+# ------------------------------------------------------------------ scalar Records on the same list
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_scalar_records_alone_are_bit_exact_with_the_reference_sweep(orc, dtype):
+    """Record::variable, +, -, *, / between Records (src/differentiation/record_operations.rs) on the device-backed list:
+    the sweep walks scalar entries in the reference's own order, so every derivative equals the oracle's literal tape
+    bit for bit."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(__file__))
+    from scalar_record import Rec
+
+    r = np.random.default_rng(21)
+    vals = r.uniform(0.5, 2.0, 6).astype(dtype)
+    hist = eml.WengertList(dtype)
+    tape = orc.Tape(dtype)
+    xs = [eml.Record.variable(v, hist) for v in vals]
+    os_ = [Rec.variable(v, tape) for v in vals]
+
+    def f(v):
+        a = v[0] * v[1] + v[2] / v[3]
+        b = (a - v[4]) * (a + 2.5) / (v[5] * v[5])
+        return b * a - (a / b) + (v[0] - 3.0) * v[0]
+
+    y, oy = f(xs), f(os_)
+    assert y.index == oy.index and len(hist) == len(tape) and y.number == oy.number
+    d, od = y.derivatives(), tape.derivatives(oy.index)
+    assert np.array_equal(d.to_vec(), od)
+    assert all(d.at(x) == od[o.index] for x, o in zip(xs, os_))
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_network_example_mixes_container_products_and_scalar_records(orc, dtype):
+    """mean_squared_loss_training, src/neural_networks.rs:95-131: each input row is re-wrapped (from_existing), goes
+    through the layers' container products, its single output is taken out as a scalar Record, and the squared errors are
+    folded with scalar Record arithmetic.  One list, one index space, one sweep."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(__file__))
+    from scalar_record import Rec
+
+    r = np.random.default_rng(22)
+    n, din, dh = 4, 3, 5
+    x = r.uniform(0, 1, (n, din)).astype(dtype)
+    labels = r.uniform(0, 1, (1, n)).astype(dtype)
+    w1 = r.uniform(-0.5, 0.5, (din, dh)).astype(dtype)
+    w2 = r.uniform(-0.5, 0.5, (dh, 1)).astype(dtype)
+    hist = eml.WengertList(dtype)
+    tape = orc.Tape(dtype)
+    W1, ow1 = eml.RecordMatrix.variables(hist, eml.Matrix(w1)), tape.variables(w1)
+    W2, ow2 = eml.RecordMatrix.variables(hist, eml.Matrix(w2)), tape.variables(w2)
+    X, ox = eml.RecordMatrix.constants(eml.Matrix(x), hist), orc.Tape.constants(x, dtype)
+    Y, oy = eml.RecordMatrix.constants(eml.Matrix(labels), hist), orc.Tape.constants(labels, dtype)
+    acc, oacc = eml.Record.constant(0.0, dtype), Rec.constant(0.0, dtype)
+    for row in range(n):
+        inp = X.range((row, 1), (0, din), history=hist)
+        out = ((inp * W1) * 0.5) * W2                                   # 1 x 1 container
+        oinp = (ox[0][row:row + 1], ox[1][row:row + 1])
+        oout = tape.matmul(tape.unary(8, tape.matmul(oinp, ow1), 0.5), ow2)
+        output = out.get_as_record(0, 0)
+        ooutput = Rec(oout[0][0, 0], tape, int(oout[1][0, 0]))
+        correct = Y.get_as_record(0, row)                               # a constant: history None
+        ocorrect = Rec(oy[0][0, row], None, 0)
+        assert output.index == ooutput.index and correct.history is None
+        acc = acc + (correct - output) * (correct - output)
+        oacc = oacc + (ocorrect - ooutput) * (ocorrect - ooutput)
+    loss, oloss = acc / float(n), oacc / float(n)
+    assert loss.index == oloss.index and len(hist) == len(tape)
+    rtol = 2e-5 if dtype == np.float32 else 1e-12
+    assert abs(float(loss.number) - float(oloss.number)) <= rtol * abs(float(oloss.number))
+    d, od = loss.derivatives(), tape.derivatives(oloss.index)
+    g1, want1 = d.at_matrix(W1).data, od[ow1[1]]
+    assert close(g1.ravel()[1:], want1.ravel()[1:], dtype) and close(np.array(g1[0, 0]), np.array(want1[0, 0]), dtype)
+    assert close(d.at_matrix(W2).data, od[ow2[1]], dtype)
