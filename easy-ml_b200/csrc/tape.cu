@@ -1252,7 +1252,11 @@ static int append_scalar(eml_tape* t, int64_t lp, double ld, int64_t rp, double 
     EML_TRY(check_tape(t));
     if (!index) EML_BAD_ARG("null argument");
     std::lock_guard<std::mutex> lock(t->mu);
-    if (lp < 0 || rp < 0 || lp > t->len || rp > t->len)  // (== len: the entry's own index, which append_nullary never uses)
+    // a missing parent is the entry's OWN index with derivative 0, as in the reference (:811-846): "won't be needed but
+    // will always be valid"
+    if (lp == -1) lp = t->len;
+    if (rp == -1) rp = t->len;
+    if (lp < 0 || rp < 0 || lp > t->len || rp > t->len)
         EML_BAD_ARG("scalar entry: parent index out of bounds (the len is %lld)", (long long)t->len);
     if (t->nodes.empty() || t->nodes.back().kind != Kind::SCALARS || t->open >= 0) {
         EML_TRY(flush(t));
@@ -1272,12 +1276,14 @@ static int append_scalar(eml_tape* t, int64_t lp, double ld, int64_t rp, double 
     return EML_OK;
 }
 
-int eml_tape_append_nullary(eml_tape* t, int64_t* index) { return append_scalar(t, 0, 0.0, 0, 0.0, index); }
+int eml_tape_append_nullary(eml_tape* t, int64_t* index) { return append_scalar(t, -1, 0.0, -1, 0.0, index); }
 int eml_tape_append_unary(eml_tape* t, int64_t parent, double derivative, int64_t* index) {
-    return append_scalar(t, parent, derivative, 0, 0.0, index);
+    if (parent < 0) EML_BAD_ARG("scalar entry: negative parent index");
+    return append_scalar(t, parent, derivative, -1, 0.0, index);
 }
 int eml_tape_append_binary(eml_tape* t, int64_t left_parent, double left_derivative, int64_t right_parent,
                            double right_derivative, int64_t* index) {
+    if (left_parent < 0 || right_parent < 0) EML_BAD_ARG("scalar entry: negative parent index");
     return append_scalar(t, left_parent, left_derivative, right_parent, right_derivative, index);
 }
 

@@ -10,27 +10,39 @@
 #![cfg(feature = "cuda")]
 #![allow(dead_code)]
 
+pub(crate) mod einsum;
 pub(crate) mod ffi;
+pub(crate) mod record;
 
 use core::ffi::c_int;
 
 /// Which implementation a numeric type takes.  `Mul` is implemented once for every `T: Numeric` through blanket
 /// impls (src/numeric.rs:153-164) and stable Rust has no specialisation; `T` is not `'static` either
-/// (`Record<'a, _>`), so `TypeId` is out.  `type_name` is monomorphised and constant-folded.
+/// (`Record<'a, _>`), so `TypeId` is out, and `type_name`'s output is explicitly not guaranteed by std.  The robust
+/// form is an associated const: `ZeroOne` -- a supertrait of `Numeric` that every numeric type implements by hand
+/// (src/numeric.rs:179-243) -- gains `#[doc(hidden)] const CUDA_KIND: Kind = Kind::GENERIC`, and its `f32` / `f64`
+/// impls override it (patches/numeric.rs).  `Kind` is public but lives in this private module, so no downstream
+/// crate can name it: nobody outside the crate can claim to be `f32` (the "sealed" pattern), and the pointer casts
+/// below are sound.
 #[derive(Clone, Copy, PartialEq, Eq, Debug)]
-pub(crate) enum Kind {
-    Generic,
-    F32,
-    F64,
+pub struct Kind(u8);
+
+impl Kind {
+    pub const GENERIC: Kind = Kind(0);
+    pub const F32: Kind = Kind(1);
+    pub const F64: Kind = Kind(2);
 }
 
+/// `T::CUDA_KIND`, resolved at compile time (the `if` below folds away for every other type).
 #[inline(always)]
-pub(crate) fn kind_of<T>() -> Kind {
-    match core::any::type_name::<T>() {
-        "f32" => Kind::F32,
-        "f64" => Kind::F64,
-        _ => Kind::Generic,
-    }
+pub(crate) fn kind_of<T: crate::numeric::ZeroOne>() -> Kind {
+    T::CUDA_KIND
+}
+
+/// f32 / f64 take the device path.
+#[inline(always)]
+pub(crate) fn on_device<T: crate::numeric::ZeroOne>() -> bool {
+    T::CUDA_KIND != Kind::GENERIC
 }
 
 /// Non-zero code -> panic with the library's thread-local message.
@@ -57,34 +69,34 @@ unsafe fn cast_mut<T, U>(s: &mut [T]) -> *mut U {
 /// C[m x n] = A[m x k] * B[k x n], row-major contiguous.  `T` must be f32 or f64 (checked by the caller with
 /// `kind_of`).  Replaces the loop of matrix_view_multiplication (src/matrices/operations.rs:185-195) and of
 /// tensor_view_matrix_product (src/tensors/operations.rs:506-518).
-pub(crate) fn gemm<T>(a: &[T], b: &[T], c: &mut [T], m: usize, n: usize, k: usize) {
+pub(crate) fn gemm<T: crate::numeric::ZeroOne>(a: &[T], b: &[T], c: &mut [T], m: usize, n: usize, k: usize) {
     assert!(a.len() == m * k && b.len() == k * n && c.len() == m * n);
     let (m, n, k) = (m as i64, n as i64, k as i64);
     unsafe {
         match kind_of::<T>() {
             Kind::F32 => check(ffi::eml_gemm_f32(cast(a), cast(b), cast_mut(c), m, n, k, k, n, n)),
             Kind::F64 => check(ffi::eml_gemm_f64(cast(a), cast(b), cast_mut(c), m, n, k, k, n, n)),
-            Kind::Generic => unreachable!("gemm is only dispatched for f32 / f64"),
+            _ => unreachable!("gemm is only dispatched for f32 / f64"),
         }
     }
 }
 
 /// Strided batched contraction C[b,m,n] = sum_k A[b,m,k] B[b,k,n]; strides in elements for (batch, row, column).
 /// Replaces the loop nest of Einsum2::to (src/tensors/einsum.rs:931-975) for GEMM-shaped name patterns.
-pub(crate) fn contract<T>(a: &[T], b: &[T], c: &mut [T], dims: [usize; 4], sa: [i64; 3], sb: [i64; 3], sc: [i64; 3]) {
+pub(crate) fn contract<T: crate::numeric::ZeroOne>(a: &[T], b: &[T], c: &mut [T], dims: [usize; 4], sa: [i64; 3], sb: [i64; 3], sc: [i64; 3]) {
     let [batch, m, n, k] = dims.map(|d| d as i64);
     unsafe {
         match kind_of::<T>() {
             Kind::F32 => check(ffi::eml_contract_f32(cast(a), cast(b), cast_mut(c), batch, m, n, k, sa.as_ptr(), sb.as_ptr(), sc.as_ptr())),
             Kind::F64 => check(ffi::eml_contract_f64(cast(a), cast(b), cast_mut(c), batch, m, n, k, sa.as_ptr(), sb.as_ptr(), sc.as_ptr())),
-            Kind::Generic => unreachable!(),
+            _ => unreachable!(),
         }
     }
 }
 
 /// Generic N-operand einsum (1..=6 operands) in the reference's exact order: bit-exact (Einsum1, Einsum3..6, and
 /// the two-operand patterns that are not GEMMs).  `out_strides` is `[n_ops][n_out]`, `sum_strides` `[n_ops][n_sum]`.
-pub(crate) fn einsum_n<T>(xs: &[&[T]], out: &mut [T], out_len: &[i64], out_strides: &[i64], sum_len: &[i64], sum_strides: &[i64]) {
+pub(crate) fn einsum_n<T: crate::numeric::ZeroOne>(xs: &[&[T]], out: &mut [T], out_len: &[i64], out_strides: &[i64], sum_len: &[i64], sum_strides: &[i64]) {
     let elems: Vec<i64> = xs.iter().map(|x| x.len() as i64).collect();
     unsafe {
         match kind_of::<T>() {
@@ -98,18 +110,18 @@ pub(crate) fn einsum_n<T>(xs: &[&[T]], out: &mut [T], out_len: &[i64], out_strid
                 check(ffi::eml_einsum_n_f64(xs.len() as c_int, ptrs.as_ptr(), elems.as_ptr(), cast_mut(out), out_len.len() as c_int,
                                             out_len.as_ptr(), out_strides.as_ptr(), sum_len.len() as c_int, sum_len.as_ptr(), sum_strides.as_ptr()))
             }
-            Kind::Generic => unreachable!(),
+            _ => unreachable!(),
         }
     }
 }
 
 /// covariance_column_features / covariance_row_features / covariance (src/linear_algebra.rs:615-832).
-pub(crate) fn covariance<T>(x: &[T], rows: usize, cols: usize, feature_axis: usize, out: &mut [T]) {
+pub(crate) fn covariance<T: crate::numeric::ZeroOne>(x: &[T], rows: usize, cols: usize, feature_axis: usize, out: &mut [T]) {
     unsafe {
         match kind_of::<T>() {
             Kind::F32 => check(ffi::eml_covariance_f32(cast(x), rows as i64, cols as i64, cols as i64, feature_axis as c_int, cast_mut(out))),
             Kind::F64 => check(ffi::eml_covariance_f64(cast(x), rows as i64, cols as i64, cols as i64, feature_axis as c_int, cast_mut(out))),
-            Kind::Generic => unreachable!(),
+            _ => unreachable!(),
         }
     }
 }
@@ -121,7 +133,7 @@ pub(crate) struct DeviceTape {
 }
 
 impl DeviceTape {
-    pub(crate) fn new<T>() -> Self {
+    pub(crate) fn new<T: crate::numeric::ZeroOne>() -> Self {
         let mut raw = core::ptr::null_mut();
         let dtype = if kind_of::<T>() == Kind::F32 { ffi::EML_F32 } else { ffi::EML_F64 };
         check(unsafe { ffi::eml_tape_create(dtype, &mut raw) });
@@ -191,6 +203,40 @@ impl DeviceTape {
     pub(crate) fn release(&self, v: ffi::EmlVal) {
         check(unsafe { ffi::eml_val_release(self.raw, v) });
     }
+    /// RecordTensor::from_existing / RecordMatrix::from_existing (mod.rs:219-224, :508): any (number, Index) pairs
+    pub(crate) fn from_existing<T>(&self, numbers: &[T], indexes: &[usize], rows: usize, cols: usize, has_history: bool) -> ffi::EmlVal {
+        assert!(numbers.len() == rows * cols && indexes.len() == rows * cols);
+        let idx: Vec<i64> = indexes.iter().map(|&i| i as i64).collect();
+        let mut v = 0;
+        check(unsafe {
+            ffi::eml_tape_from_existing(self.raw, numbers.as_ptr().cast(), idx.as_ptr(), rows as i64, cols as i64, has_history as c_int, &mut v)
+        });
+        v
+    }
+    /// WengertList::append_nullary (src/differentiation.rs:811-823)
+    pub(crate) fn append_nullary(&self) -> usize {
+        let mut i = 0i64;
+        check(unsafe { ffi::eml_tape_append_nullary(self.raw, &mut i) });
+        i as usize
+    }
+    /// WengertList::append_unary (:828-846)
+    pub(crate) fn append_unary(&self, parent: usize, derivative: f64) -> usize {
+        let mut i = 0i64;
+        check(unsafe { ffi::eml_tape_append_unary(self.raw, parent as i64, derivative, &mut i) });
+        i as usize
+    }
+    /// WengertList::append_binary (:855-878)
+    pub(crate) fn append_binary(&self, lp: usize, ld: f64, rp: usize, rd: f64) -> usize {
+        let mut i = 0i64;
+        check(unsafe { ffi::eml_tape_append_binary(self.raw, lp as i64, ld, rp as i64, rd, &mut i) });
+        i as usize
+    }
+    /// Record::try_derivatives (:623-648) from the Record at tape index `index`
+    pub(crate) fn derivatives_at(&self, index: usize) -> DeviceDerivatives {
+        let mut d = core::ptr::null_mut();
+        check(unsafe { ffi::eml_tape_derivatives_at(self.raw, index as i64, &mut d) });
+        DeviceDerivatives { raw: d }
+    }
 }
 
 impl Drop for DeviceTape {
@@ -215,6 +261,14 @@ impl DeviceDerivatives {
     pub(crate) fn at_container<T: Clone + Default>(&self, v: ffi::EmlVal, n: usize) -> Vec<T> {
         let mut out = vec![T::default(); n];
         check(unsafe { ffi::eml_derivs_at_val(self.raw, v, out.as_mut_ptr().cast()) });
+        out
+    }
+    /// `Vec::from(Derivatives)` (src/differentiation.rs:405-414)
+    pub(crate) fn to_vec<T: Clone + Default>(&self) -> Vec<T> {
+        let mut n = 0i64;
+        check(unsafe { ffi::eml_derivs_len(self.raw, &mut n) });
+        let mut out = vec![T::default(); n as usize];
+        check(unsafe { ffi::eml_derivs_to_host(self.raw, out.as_mut_ptr().cast()) });
         out
     }
 }

@@ -126,3 +126,77 @@ def test_rust_ffi_bindings_are_generated_from_the_header():
         if os.path.exists(out + ".check"):
             os.remove(out + ".check")
         gen.OUT = out
+
+
+def _rust_sources():
+    base = os.path.join(ROOT, "easy-ml_b200", "rust")
+    out = []
+    for d, _, files in os.walk(base):
+        out += [os.path.join(d, f) for f in files if f.endswith(".rs")]
+    return sorted(out)
+
+
+def _strip_rust(text):
+    """Source with comments, string literals and char literals blanked (lifetimes such as 'a are kept)."""
+    import re
+
+    text = re.sub(r"/\*.*?\*/", lambda m: " " * len(m.group(0)), text, flags=re.S)
+    text = re.sub(r"//[^\n]*", "", text)
+    text = re.sub(r'"(?:\\.|[^"\\])*"', '""', text, flags=re.S)
+    text = re.sub(r"'(?:\\.|[^'\\])'", "' '", text)
+    return text
+
+
+def test_rust_shim_is_syntactically_sane_and_only_uses_symbols_that_exist():
+    """There is no Rust toolchain in this image, so the shim cannot be compiled here.  What can be checked is checked:
+    brackets balance in every .rs file, every `ffi::` function or constant the hand-written modules use is declared in
+    the generated bindings, and every `crate::cuda::` item the dispatch sites call is defined by the module."""
+    import re
+
+    files = _rust_sources()
+    assert any(f.endswith("dispatch_sites.rs") for f in files) and any(f.endswith("einsum.rs") for f in files)
+    ffi = open(os.path.join(ROOT, "easy-ml_b200", "rust", "src", "cuda", "ffi.rs")).read()
+    declared = set(re.findall(r"pub fn (eml_\w+)\(", ffi)) | set(re.findall(r"pub const (EML_\w+):", ffi)) | {
+        "EmlVal", "EmlTape", "EmlDerivs", "EmlGraph"}
+    defined = set()
+    for f in files:
+        if os.sep + "cuda" + os.sep in f:
+            src = _strip_rust(open(f).read())
+            defined |= set(re.findall(r"pub(?:\(crate\))?\s+(?:unsafe\s+)?(?:fn|struct|enum|mod|trait|const)\s+(\w+)", src))
+    for f in files:
+        src = _strip_rust(open(f).read())
+        depth = {"(": 0, "[": 0, "{": 0}
+        pairs = {")": "(", "]": "[", "}": "{"}
+        for ch in src:
+            if ch in depth:
+                depth[ch] += 1
+            elif ch in pairs:
+                depth[pairs[ch]] -= 1
+                assert depth[pairs[ch]] >= 0, f"{f}: unbalanced {ch}"
+        assert all(v == 0 for v in depth.values()), f"{f}: unbalanced brackets {depth}"
+        if f.endswith("ffi.rs"):
+            continue
+        for name in re.findall(r"(?<![:\w])ffi::(\w+)", src):  # (not core::ffi::c_int)
+            assert name in declared, f"{f}: ffi::{name} is not in the generated bindings"
+        for path in re.findall(r"crate::cuda::((?:\w+::)*\w+)", src):
+            for part in path.split("::"):
+                if part in ("Kind", "GENERIC", "F32", "F64") or part[0].isupper() and part in defined:
+                    continue
+                assert part in defined, f"{f}: crate::cuda::{path} -- `{part}` is not defined in src/cuda"
+
+
+def test_static_library_is_built_and_exports_the_abi():
+    """north_star: "a thin extern "C" layer over a CUDA static library built for sm_100a by build.rs" -- the Makefile
+    archives the same objects as libeasyml_b200.a; every declared entry point must be defined in it."""
+    import re
+    import subprocess
+
+    lib_a = os.path.join(ROOT, "easy-ml_b200", "lib", "libeasyml_b200.a")
+    assert os.path.exists(lib_a), "run `make -C easy-ml_b200/csrc` (build() does)"
+    header = open(os.path.join(ROOT, "include", "easyml_b200.h")).read()
+    names = set(re.findall(r"^(?:int|void|int64_t|const char\*)\s+(eml_\w+)\(", header, flags=re.M))
+    syms = subprocess.run(["nm", "--defined-only", lib_a], capture_output=True, text=True, check=True).stdout
+    have = set(re.findall(r" T (eml_\w+)", syms))
+    assert names <= have, sorted(names - have)
+    build_rs = open(os.path.join(ROOT, "easy-ml_b200", "rust", "build.rs")).read()
+    assert "static=easyml_b200" in build_rs and "dylib=easyml_b200" not in build_rs
