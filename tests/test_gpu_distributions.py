@@ -85,7 +85,8 @@ def test_large_draw_is_one_tensor_core_product(orc):
     source = r.uniform(1e-6, 1.0, samples * features).astype(np.float32)
     before = eml.kernel_launches()
     got = eml.MultivariateGaussian(eml.Matrix(mean.reshape(-1, 1)), eml.Matrix(cov)).draw(source, samples)
-    assert eml.last_kernel() == "tf32x3_tcgen05" and eml.kernel_launches() - before <= 4
+    # (two split/pack passes, the product, at most one split-K reduction, the early-exit non-finite repair)
+    assert eml.last_kernel() == "tf32x3_tcgen05" and eml.kernel_launches() - before <= 5
     assert got.size() == (samples, features)
     low = orc.cholesky(cov)
     rows = [0, 1, 2047, 4095]

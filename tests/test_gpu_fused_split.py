@@ -128,7 +128,8 @@ def test_dispatcher_picks_in_kernel_split_for_small_batched_outputs():
     before = eml.kernel_launches()
     c = contract(a, b)
     launches = eml.kernel_launches() - before
-    assert launches == 1, f"expected the single fused launch, saw {launches} (pack passes ran)"
+    # the fused product + the early-exit repair of non-finite inputs; the packed path would need two pack passes more
+    assert launches == 2, f"expected the fused launch and its repair, saw {launches} (pack passes ran)"
     with forced("0"):
         assert torch.equal(c, contract(a, b))
 
