@@ -66,7 +66,10 @@ void copy_bytes(void* dst, const void* src, size_t n) {
     memcpy(dst, src, n);
 }
 
-// A tiny persistent pool: run(n, fn) calls fn(0..n-1) over the workers and the calling thread.
+// A tiny persistent pool: run(n, fn) calls fn(0..n-1) over the workers and the calling thread.  A staging job is short
+// (16-32 MB: a few hundred microseconds at the 85 GB/s sixteen cores copy here), so a condition-variable wake-up per job
+// (~50-100 us for fifteen sleepers) would halve the throughput: workers SPIN for a short while after a job before they go
+// to sleep, and the caller spins for their completion.
 class CopyPool {
   public:
     static CopyPool& get() {
@@ -79,24 +82,33 @@ class CopyPool {
             for (int64_t i = 0; i < n; i++) fn(i);
             return;
         }
-        // one job at a time: the job state below (fn_, total_, next_, done_, generation_) is shared with the workers, and
-        // callers driving different devices from different threads are not serialised by any per-device mutex
+        // one job at a time: the job state below is shared with the workers, and callers driving different devices from
+        // different threads are not serialised by any per-device mutex
         std::lock_guard<std::mutex> job(run_mu_);
-        std::unique_lock<std::mutex> lock(mu_);
         fn_ = &fn;
         total_ = n;
-        next_.store(0);
-        done_ = 0;
-        generation_++;
-        lock.unlock();
-        cv_.notify_all();
+        next_.store(0, std::memory_order_relaxed);
+        done_.store(0, std::memory_order_relaxed);
+        generation_.fetch_add(1, std::memory_order_release);
+        if (sleepers_.load(std::memory_order_acquire) > 0) {
+            std::lock_guard<std::mutex> lock(mu_);
+            cv_.notify_all();
+        }
         work();
-        lock.lock();
-        idle_.wait(lock, [&] { return done_ == (int)workers_.size(); });
+        const int workers = (int)workers_.size();
+        for (int spins = 0; done_.load(std::memory_order_acquire) != workers; spins++) {
+            if (spins > 2000) std::this_thread::yield();
+            else cpu_relax();
+        }
         fn_ = nullptr;
     }
 
   private:
+    static void cpu_relax() {
+#if defined(__x86_64__)
+        _mm_pause();
+#endif
+    }
     CopyPool() {
         // the caller's thread copies too; EML_COPY_THREADS overrides the total (1 = no workers)
         unsigned hw = std::thread::hardware_concurrency();
@@ -110,7 +122,7 @@ class CopyPool {
     }
     void work() {
         for (;;) {
-            int64_t i = next_.fetch_add(1);
+            int64_t i = next_.fetch_add(1, std::memory_order_relaxed);
             if (i >= total_) break;
             (*fn_)(i);
         }
@@ -118,28 +130,39 @@ class CopyPool {
     void loop() {
         uint64_t seen = 0;
         for (;;) {
-            std::unique_lock<std::mutex> lock(mu_);
-            cv_.wait(lock, [&] { return generation_ != seen; });
-            seen = generation_;
-            lock.unlock();
+            // spin ~100 us for the next job of the same call, then sleep
+            bool woke = false;
+            for (int spins = 0; spins < 20000; spins++) {
+                if (generation_.load(std::memory_order_acquire) != seen) {
+                    woke = true;
+                    break;
+                }
+                cpu_relax();
+            }
+            if (!woke) {
+                std::unique_lock<std::mutex> lock(mu_);
+                sleepers_.fetch_add(1, std::memory_order_release);
+                cv_.wait(lock, [&] { return generation_.load(std::memory_order_acquire) != seen; });
+                sleepers_.fetch_sub(1, std::memory_order_release);
+            }
+            seen = generation_.load(std::memory_order_acquire);
             work();
-            lock.lock();
-            if (++done_ == (int)workers_.size()) idle_.notify_one();
+            done_.fetch_add(1, std::memory_order_release);
         }
     }
     std::mutex run_mu_;  // held by the caller for a whole job
     std::mutex mu_;
-    std::condition_variable cv_, idle_;
+    std::condition_variable cv_;
     std::vector<std::thread> workers_;
     const std::function<void(int64_t)>* fn_ = nullptr;
     int64_t total_ = 0;
     std::atomic<int64_t> next_{0};
-    int done_ = 0;
-    uint64_t generation_ = 0;
+    std::atomic<int> done_{0}, sleepers_{0};
+    std::atomic<uint64_t> generation_{0};
 };
 
 constexpr int SLOTS = 8;
-constexpr size_t SLOT_BYTES = size_t(16) << 20;
+constexpr size_t SLOT_BYTES = size_t(32) << 20;
 
 struct Ring {
     void* slot[SLOTS] = {};
