@@ -102,6 +102,7 @@ SIGNATURES = {
     "eml_tape_capture_end": (cint, [vp, C.POINTER(vp)]),
     "eml_graph_launch": (cint, [vp, C.POINTER(vp)]),
     "eml_graph_destroy": (cint, [vp]),
+    "eml_graph_profile": (cint, [vp, cint, C.c_char_p, i64]),
     "eml_val_indexes": (cint, [vp, i64, vp]),
     "eml_val_device_ptr": (cint, [vp, i64, C.POINTER(vp)]),
     "eml_tape_matmul": (cint, [vp, i64, i64, pi64]),

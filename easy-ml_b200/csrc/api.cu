@@ -66,15 +66,33 @@ int contract_dev(DeviceCtx* ctx, const T* A, const T* B, T* C, int64_t batch, in
     GemmOptions local;
     if (!opt) opt = &local;
     opt->remote_done = opt->upper_done = false;
+    // ACC_ZERO_PLUS (see GemmOptions::zero_plus): kernels that cannot write `0 + product` get their zeros here
+    const bool zp = accumulate && opt->zero_plus;
+    if (zp && !(batch == 1 && sC.c == 1 && sC.r == N && C)) EML_BAD_ARG("contract: zero_plus needs a dense C");
+    const int acc_mode = zp ? ACC_ZERO_PLUS : (accumulate ? ACC_ADD : ACC_WRITE);
+    auto zeros_first = [&]() -> int {
+        if (!zp) return EML_OK;
+        const size_t bytes = sizeof(T) * (size_t)(M * N);
+        if (((reinterpret_cast<uintptr_t>(C) | bytes) & 15) == 0) {
+            ZeroRanges z;
+            z.count = 1, z.p[0] = C, z.bytes[0] = bytes;
+            return launch_zero_ranges(z, stream);
+        }
+        EML_CUDA(cudaMemsetAsync(C, 0, bytes, stream));
+        return EML_OK;
+    };
     // tall-skinny A^T * B (N <= 16, A contiguous along m, long K): its own chunked kernel
     if (!exact && batch == 1 && N >= 1 && N <= 16 && sA.r == 1 && sA.c != 1 && K >= 256 && M >= 32 && A && B && C)
-        return launch_gemm_skinny_tn<T>(ctx, A, B, C, M, N, K, sA, sB, sC, accumulate, stream);
+        return launch_gemm_skinny_tn<T>(ctx, A, B, C, M, N, K, sA, sB, sC, acc_mode, stream);
     // thin products (M <= 4 rows against a dense row-major B, long K): one launch, ticketed fixed-order finish
-    if (!exact && batch == 1 && A && B && C && K >= 256 && thin_shape(M, N, K) && sB.c == 1 && sB.r == N)
+    if (!exact && batch == 1 && A && B && C && K >= 256 && thin_shape(M, N, K) && sB.c == 1 && sB.r == N) {
+        EML_TRY(zeros_first());
         return launch_thin_fwd<T>(A, sA.r, sA.c, B, M, N, K, C, sC.r, sC.c, accumulate, stream);
+    }
     // short contraction, wide dense output (dH = dY * W2^T of an output layer): B in shared memory, no split
+    // (its fma chain starts from +0 when it does not accumulate: that IS 0 + product)
     if (!exact && batch == 1 && A && B && C && sA.c == 1 && sC.c == 1 && smallk_shape(M, N, K, sizeof(T)))
-        return launch_gemm_smallk<T>(A, sA.r, B, sB.r, sB.c, C, sC.r, M, N, K, accumulate, stream);
+        return launch_gemm_smallk<T>(A, sA.r, B, sB.r, sB.c, C, sC.r, M, N, K, accumulate && !zp, stream);
     // Deterministic split-K for outputs with too few tiles for 148 SMs and a long K (the loss reduction
     // L[1 x batch] * d[batch x 10], dW2 = H^T[512 x batch] * dY[batch x 10], ...): K is cut into S equal
     // chunks which run as S "batches" of one launch into a workspace [S][M][N]; a fixed-order reduction
@@ -95,7 +113,7 @@ int contract_dev(DeviceCtx* ctx, const T* A, const T* B, T* C, int64_t batch, in
                 EML_TRY(ws.alloc(sizeof(T) * (size_t)(S * M * N), stream));
                 EML_TRY(contract_dev<T>(ctx, A, B, ws.as<T>(), S, M, N, Kc, Strides3{Kc * sA.c, sA.r, sA.c},
                                         Strides3{Kc * sB.r, sB.r, sB.c}, Strides3{M * N, N, 1}, false, false, stream));
-                return launch_splitk_reduce<T>(ws.as<T>(), (int)S, C, 1, M, N, sC, accumulate, stream);
+                return launch_splitk_reduce<T>(ws.as<T>(), (int)S, C, 1, M, N, sC, acc_mode, stream);
             }
         }
     }
@@ -115,6 +133,8 @@ int contract_dev(DeviceCtx* ctx, const T* A, const T* B, T* C, int64_t batch, in
         // path packs G once), then the upper triangle is mirrored.  Worth it from 4 x 4 tiles of 128 up.
         opt->upper_only = (const void*)A == (const void*)B && batch == 1 && M == N && M >= 512 && !accumulate &&
                           sA.r == sB.c && sA.c == sB.r && sC.c == 1 && opt->n_remote == 0;
+        // (the f32 kernels honour zero_plus themselves -- their split-K launches end in the reduction; f64: zeros first)
+        if (sizeof(T) == 8) EML_TRY(zeros_first());
         if (sC.c != 1 && sC.r == 1) {
             GemmOptions swapped = *opt;  // the operands swap roles in the transposed problem
             swapped.a_id = opt->b_id;
@@ -127,7 +147,9 @@ int contract_dev(DeviceCtx* ctx, const T* A, const T* B, T* C, int64_t batch, in
         }
         EML_TRY(rc);
         if (handled) return opt->upper_done ? launch_mirror_upper<T>(C, M, sC.r, stream) : EML_OK;
+        if (sizeof(T) == 8) opt->zero_plus = false;  // (already zeroed above; the kernels below accumulate)
     }
+    if (opt->zero_plus) EML_TRY(zeros_first());
     if (!exact && N <= 16 && sA.c == 1 && M >= 256 && K >= 64)
         return launch_gemm_skinny<T>(A, B, C, batch, M, N, K, sA, sB, sC, accumulate, stream);
     return launch_gemm_simt<T>(A, B, C, batch, M, N, K, sA, sB, sC, accumulate, exact, stream);
@@ -737,6 +759,7 @@ int eml_sync(void) {
     DeviceCtx* ctx = nullptr;
     EML_TRY(get_ctx(&ctx));
     EML_CUDA(cudaDeviceSynchronize());
+    trace_dump();
     return EML_OK;
 }
 

@@ -63,7 +63,52 @@ void pdl_suppress(bool suppress) {
     t_pdl_suppressed = suppress && !keep_in_graphs;
 }
 
+namespace {
+struct TraceMark {
+    const char* what;
+    cudaStream_t stream;
+    cudaEvent_t ev;
+};
+std::mutex g_trace_mu;
+std::vector<TraceMark> g_trace;
+thread_local cudaStream_t t_last_stream = nullptr;
+bool trace_on() {
+    static const bool on = [] {
+        const char* e = getenv("EML_TRACE");
+        return e && e[0] == '1';
+    }();
+    return on;
+}
+void trace_mark(const char* what) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(t_last_stream, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return;
+    cudaEvent_t ev;
+    if (cudaEventCreate(&ev) != cudaSuccess) return;
+    cudaEventRecord(ev, t_last_stream);
+    std::lock_guard<std::mutex> lock(g_trace_mu);
+    if (g_trace.size() >= 8192) {
+        for (size_t i = 0; i < 4096; i++) cudaEventDestroy(g_trace[i].ev);
+        g_trace.erase(g_trace.begin(), g_trace.begin() + 4096);
+    }
+    g_trace.push_back(TraceMark{what, t_last_stream, ev});
+}
+}  // namespace
+void trace_note_stream(cudaStream_t stream) { t_last_stream = stream; }
+void trace_dump() {
+    if (!trace_on()) return;
+    std::lock_guard<std::mutex> lock(g_trace_mu);
+    const size_t n = g_trace.size(), first = n > 80 ? n - 80 : 0;
+    for (size_t i = first; i < n; i++) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, g_trace[first].ev, g_trace[i].ev);
+        fprintf(stderr, "trace %9.1f us  stream %p  %s\n", ms * 1e3, (void*)g_trace[i].stream, g_trace[i].what);
+    }
+    for (auto& m : g_trace) cudaEventDestroy(m.ev);
+    g_trace.clear();
+}
+
 int check_launch(const char* what) {
+    if (trace_on()) trace_mark(what);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_error("launch of %s failed: %s", what, cudaGetErrorString(e));

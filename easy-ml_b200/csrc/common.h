@@ -48,6 +48,12 @@ __device__ __forceinline__ void pdl_prologue() {
 #endif
 bool pdl_enabled();
 void pdl_suppress(bool suppress);  // thread-local (graph capture)
+// EML_TRACE=1 (development aid, off by default): check_launch() records a timing event behind every kernel on the stream
+// it was launched on, and eml_sync() prints the completion times of the most recent ones -- a coarse timeline that shows
+// which kernels of the two streams of a sweep overlap.  (The event records get in the way of programmatic dependent
+// launch, so a traced run is slower than a normal one.)
+void trace_note_stream(cudaStream_t stream);
+void trace_dump();
 
 template <class... P, class... A>
 inline cudaError_t launch_k(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, A&&... args) {
@@ -61,6 +67,7 @@ inline cudaError_t launch_k(void (*kernel)(P...), dim3 grid, dim3 block, size_t 
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    trace_note_stream(stream);
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);
 }
 
@@ -137,10 +144,18 @@ struct GemmOptions {
     // Set by contract_dev itself for C = G * G^T (A and B the same buffer read through mirrored strides): compute the
     // tiles on and above the diagonal only (contract_dev mirrors the upper triangle afterwards).
     bool upper_only = false;
+    // With accumulate: C holds NO defined numbers yet -- the result must be what accumulating into zeros would give
+    // (0 + product: the same bits, including +0 where the product is -0), without anybody having written the zeros.
+    // The reverse sweep's first contribution to a derivative buffer.  Paths that end in a split-K reduction write
+    // `0 + sum` there (ACC_ZERO_PLUS); the others zero C themselves first.  C must be dense (row stride N, batch 1).
+    bool zero_plus = false;
     // ---- out ----
     bool remote_done = false;  // the kernel that ran stored the tiles to the peers
     bool upper_done = false;   // the kernel that ran computed the upper triangle only
 };
+
+// how a kernel's result meets what C holds
+constexpr int ACC_WRITE = 0, ACC_ADD = 1, ACC_ZERO_PLUS = 2;
 
 // ---- kernels (one translation unit each) ----
 // general strided batched contraction C[b,m,n] (+)= sum_k A[b,m,k] B[b,k,n]; dispatches between the
@@ -162,7 +177,7 @@ int launch_gemm_skinny(const T* A, const T* B, T* C, int64_t batch, int64_t M, i
 // N <= 16, A contiguous along m (A^T stored row-major), long K: per-k-chunk partials + fixed-order reduction
 template <class T>
 int launch_gemm_skinny_tn(DeviceCtx* ctx, const T* A, const T* B, T* C, int64_t M, int64_t N, int64_t K, Strides3 sA,
-                          Strides3 sB, Strides3 sC, bool accumulate, cudaStream_t stream);
+                          Strides3 sB, Strides3 sC, int accumulate /* ACC_* */, cudaStream_t stream);
 
 // f64 tensor-core (DMMA) kernel.  Returns EML_OK and sets *handled=false when the layout is not one it
 // supports (caller falls through to another GPU kernel).
@@ -208,7 +223,7 @@ int launch_gemm_tf32x3_f32(DeviceCtx* ctx, const float* A, const float* B, float
 // split-K path (deterministic: no atomics).  ws is dense; C is strided.
 template <class T>
 int launch_splitk_reduce(const T* ws, int splits, T* C, int64_t batch, int64_t M, int64_t N, Strides3 sC,
-                         bool accumulate, cudaStream_t stream);
+                         int accumulate /* ACC_* */, cudaStream_t stream);
 
 // out (row-major over out_lens) [i] = in[sum_d i_d * in_strides[d]]  (reorder.cu)
 template <class T>
@@ -254,15 +269,35 @@ struct SgdBatch {
     void* out[SGD_BATCH_MAX];
     const void* w[SGD_BATCH_MAX];
     const void* d[SGD_BATCH_MAX];
-    const void* slot0[SGD_BATCH_MAX];  // non-null: element 0's derivative still lacks the sum parked beside the arena
+    const void* slot0[SGD_BATCH_MAX];  // non-null: element 0's derivative still lacks the sums parked beside the arena
+    int slot0_n[SGD_BATCH_MAX];        // ... the in-order fold of this many slots
     int64_t n[SGD_BATCH_MAX];
     double lr[SGD_BATCH_MAX];
+    // rider: a few bytes (the step's loss) stored straight into page-locked host memory by one extra block row of the
+    // same launch -- the read-back of a training step then costs no launch of its own
+    const void* copy_src = nullptr;
+    void* copy_dst = nullptr;
+    size_t copy_bytes = 0;
 };
 template <class T>
 int launch_sgd_batch(const SgdBatch& b, cudaStream_t stream);
-// out[i] = value (fill), used by the tape (seeding, zeroing is cudaMemsetAsync)
+// out[i] = value (fill), used by the tape (seeding)
 template <class T>
 int launch_fill(T* out, T value, int64_t n, cudaStream_t stream);
+// Zero fill of several ranges in ONE kernel (pointers and byte counts multiples of 16).  The sweep's vec![0; len] used
+// to be cudaMemsetAsync calls: between kernels of one stream a memset breaks the programmatic-dependent-launch chain,
+// and as a node of a recorded step it costs far more than a kernel node (measured with eml_graph_profile).
+constexpr int ZERO_RANGES_MAX = 8;
+struct ZeroRanges {
+    int count = 0;
+    void* p[ZERO_RANGES_MAX];
+    size_t bytes[ZERO_RANGES_MAX];
+};
+int launch_zero_ranges(const ZeroRanges& z, cudaStream_t stream);
+// dst_host[0..bytes) = src[0..bytes) by a kernel that stores straight into page-locked host memory through its device
+// mapping (a few KB at most: a loss value).  A copy-engine transfer of a few bytes costs several microseconds of
+// stream time and, like a memset, sits badly between kernels.
+int launch_copy_to_host(const void* src, void* dst_host_devptr, size_t bytes, cudaStream_t stream);
 // deterministic full reduction: out[0] (+)= sum_i x[i] (fixed tree); and the column / row sums used by the
 // constant-operand path of the matmul backward.
 template <class T>
@@ -316,5 +351,9 @@ int launch_gemm_smallk(const T* A, int64_t lda, const T* B, int64_t sBr, int64_t
 // dst[i] = src[idx(i)] strided gather/scatter helpers for matmul-output derivative vectors
 template <class T>
 int launch_add_inplace(T* dst, const T* src, int64_t n, cudaStream_t stream);
+// s = ((+0 + slots[0]) + slots[1]) + ... + slots[n-1];  compact: slots[0] = s (dst == slots),
+// else dst[0] = dst[0] + s.  One thread: the order of the additions is the point.
+template <class T>
+int launch_fold_slots(T* dst, const T* slots, int n, bool compact, cudaStream_t stream);
 
 }  // namespace eml

@@ -416,6 +416,15 @@ template <class T>
 __global__ void __launch_bounds__(EW_THREADS) sgd_batch_kernel(const __grid_constant__ SgdBatch b) {
     pdl_prologue();
     const int y = blockIdx.y;
+    if (y == b.count) {  // the rider (see SgdBatch)
+        if (blockIdx.x == 0) {
+            const unsigned char* src = static_cast<const unsigned char*>(b.copy_src);
+            unsigned char* dst = static_cast<unsigned char*>(b.copy_dst);
+            for (size_t i = threadIdx.x; i < b.copy_bytes; i += blockDim.x) dst[i] = src[i];
+            __threadfence_system();
+        }
+        return;
+    }
     T* out = static_cast<T*>(b.out[y]);
     const T* w = static_cast<const T*>(b.w[y]);
     const T* d = static_cast<const T*>(b.d[y]);
@@ -423,7 +432,12 @@ __global__ void __launch_bounds__(EW_THREADS) sgd_batch_kernel(const __grid_cons
     const int64_t n = b.n[y];
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         T g = d[i];
-        if (i == 0 && b.slot0[y]) g = g + static_cast<const T*>(b.slot0[y])[0];
+        if (i == 0 && b.slot0[y]) {  // the parked constant-operand sums, folded in sweep order
+            const T* slots = static_cast<const T*>(b.slot0[y]);
+            T s = T(0);
+            for (int k = 0; k < b.slot0_n[y]; k++) s = s + slots[k];
+            g = g + s;
+        }
         out[i] = w[i] - g * lr;
     }
 }
@@ -437,7 +451,7 @@ int launch_sgd_batch(const SgdBatch& b, cudaStream_t stream) {
     int64_t blocks = (most + EW_THREADS - 1) / EW_THREADS;
     if (blocks > 148 * 8) blocks = 148 * 8;
     if (blocks < 1) blocks = 1;
-    launch_k(sgd_batch_kernel<T>, dim3((unsigned)blocks, (unsigned)b.count), dim3(EW_THREADS), 0, stream, b);
+    launch_k(sgd_batch_kernel<T>, dim3((unsigned)blocks, (unsigned)(b.count + (b.copy_bytes ? 1 : 0))), dim3(EW_THREADS), 0, stream, b);
     count_launch();
     return check_launch("sgd");
 }
@@ -503,6 +517,67 @@ template <class T>
 int launch_add_inplace(T* dst, const T* src, int64_t n, cudaStream_t stream) {
     return launch_axpy<T, 3>(T(0), src, nullptr, dst, n, stream);
 }
+
+namespace {
+__global__ void __launch_bounds__(256) zero_ranges_kernel(const __grid_constant__ ZeroRanges z) {
+    pdl_prologue();
+    const int y = blockIdx.y;
+    uint4* p = static_cast<uint4*>(z.p[y]);
+    const size_t n = z.bytes[y] / 16;
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = zero;
+}
+__global__ void __launch_bounds__(256) copy_to_host_kernel(const unsigned char* __restrict__ src, unsigned char* dst, size_t bytes) {
+    pdl_prologue();
+    for (size_t i = threadIdx.x; i < bytes; i += blockDim.x) dst[i] = src[i];
+    __threadfence_system();
+}
+}  // namespace
+int launch_zero_ranges(const ZeroRanges& z, cudaStream_t stream) {
+    if (z.count < 1) return EML_OK;
+    size_t most = 0;
+    for (int y = 0; y < z.count; y++) {
+        if ((reinterpret_cast<uintptr_t>(z.p[y]) & 15) || (z.bytes[y] & 15)) EML_BAD_ARG("zero fill: range not 16-byte aligned");
+        most = z.bytes[y] > most ? z.bytes[y] : most;
+    }
+    size_t blocks = (most / 16 + 255) / 256;
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    if (blocks < 1) blocks = 1;
+    launch_k(zero_ranges_kernel, dim3((unsigned)blocks, (unsigned)z.count), dim3(256), 0, stream, z);
+    count_launch();
+    return check_launch("zero fill");
+}
+int launch_copy_to_host(const void* src, void* dst_host_devptr, size_t bytes, cudaStream_t stream) {
+    if (bytes < 1) return EML_OK;
+    launch_k(copy_to_host_kernel, dim3(1), dim3(256), 0, stream, static_cast<const unsigned char*>(src),
+             static_cast<unsigned char*>(dst_host_devptr), bytes);
+    count_launch();
+    return check_launch("copy to page-locked host memory");
+}
+
+namespace {
+template <class T>
+__global__ void fold_slots_kernel(T* dst, const T* slots, int n, int compact) {
+    pdl_prologue();
+    if (blockIdx.x || threadIdx.x) return;
+    T s = T(0);
+    for (int k = 0; k < n; k++) s = s + slots[k];
+    if (compact) {
+        dst[0] = s;
+    } else {
+        dst[0] = dst[0] + s;
+    }
+}
+}  // namespace
+template <class T>
+int launch_fold_slots(T* dst, const T* slots, int n, bool compact, cudaStream_t stream) {
+    if (n < 1) return EML_OK;
+    launch_k(fold_slots_kernel<T>, dim3(1), dim3(32), 0, stream, dst, slots, n, compact ? 1 : 0);
+    count_launch();
+    return check_launch("fold of the constant-operand sums");
+}
+template int launch_fold_slots<float>(float*, const float*, int, bool, cudaStream_t);
+template int launch_fold_slots<double>(double*, const double*, int, bool, cudaStream_t);
 
 template <class T>
 int launch_dot(const T* x, int64_t incx, const T* y, int64_t incy, int64_t n, T* out_dev, cudaStream_t stream) {

@@ -354,7 +354,7 @@ gemm_tn_wide_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restr
 
 template <class T>
 int launch_gemm_skinny_tn(DeviceCtx* ctx, const T* A, const T* B, T* C, int64_t M, int64_t N, int64_t K, Strides3 sA,
-                          Strides3 sB, Strides3 sC, bool accumulate, cudaStream_t stream) {
+                          Strides3 sB, Strides3 sC, int accumulate, cudaStream_t stream) {
     if (M <= (int64_t)TN_THREADS * TNW_MT) {
         const int64_t sms = ctx ? ctx->sm_count : 148;
         int64_t blocks = 2 * sms;  // two CTAs per SM (latency hiding); the partials (blocks x M x N) stay small
@@ -393,9 +393,9 @@ int launch_gemm_skinny_tn(DeviceCtx* ctx, const T* A, const T* B, T* C, int64_t 
     return launch_splitk_reduce<T>(ws.as<T>(), (int)chunks, C, 1, M, N, sC, accumulate, stream);
 }
 template int launch_gemm_skinny_tn<float>(DeviceCtx*, const float*, const float*, float*, int64_t, int64_t, int64_t,
-                                          Strides3, Strides3, Strides3, bool, cudaStream_t);
+                                          Strides3, Strides3, Strides3, int, cudaStream_t);
 template int launch_gemm_skinny_tn<double>(DeviceCtx*, const double*, const double*, double*, int64_t, int64_t, int64_t,
-                                           Strides3, Strides3, Strides3, bool, cudaStream_t);
+                                           Strides3, Strides3, Strides3, int, cudaStream_t);
 
 // The common case of the skinny product -- one dense row-major B[K x N] small enough to live in L1, K a multiple of
 // 32 lanes x one 16-byte vector (an output layer: H[8192 x 512] * W2[512 x 10]).  A lane owns VEC consecutive k of
@@ -516,7 +516,7 @@ splitk_reduce_kernel(const T* __restrict__ ws, int splits, int64_t split_stride,
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int64_t b = i / (M * N), r = (i / N) % M, c = i % N;
         T* p = C + b * sC.b + r * sC.r + c * sC.c;
-        T acc = accumulate ? *p : T(0);
+        T acc = accumulate == 1 ? *p : T(0);  // (mode 2, "0 + sum", is this very chain started from +0)
         for (int s = 0; s < splits; s += 8) {  // eight loads in flight, added in split order
             T v[8];
 #pragma unroll
@@ -554,7 +554,7 @@ splitk_reduce_warp_kernel(const T* __restrict__ ws, int splits, int64_t split_st
         if (lane == 0) {
             int64_t b = i / (M * N), r = (i / N) % M, c = i % N;
             T* p = C + b * sC.b + r * sC.r + c * sC.c;
-            *p = accumulate ? *p + acc : acc;
+            *p = accumulate == 1 ? *p + acc : (accumulate == 2 ? T(0) + acc : acc);
         }
     }
 }
@@ -600,13 +600,13 @@ splitk_reduce_2level_kernel(const T* __restrict__ ws, int splits, int per_range,
     }
     const int64_t b = i / (M * N), rr = (i / N) % M, c = i % N;
     T* p = C + b * sC.b + rr * sC.r + c * sC.c;
-    *p = accumulate ? *p + acc : acc;
+    *p = accumulate == 1 ? *p + acc : (accumulate == 2 ? T(0) + acc : acc);
 }
 }  // namespace
 
 template <class T>
 int launch_splitk_reduce(const T* ws, int splits, T* C, int64_t batch, int64_t M, int64_t N, Strides3 sC,
-                         bool accumulate, cudaStream_t stream) {
+                         int accumulate, cudaStream_t stream) {
     int64_t total = batch * M * N;
     if (total == 0) return EML_OK;
     if (total <= 65536 && splits >= 64 && (total + 255) / 256 <= 4096) {
@@ -617,25 +617,25 @@ int launch_splitk_reduce(const T* ws, int splits, T* C, int64_t batch, int64_t M
         unsigned* tickets = nullptr;
         EML_TRY(stream_tickets(stream, &tickets));
         launch_k(splitk_reduce_2level_kernel<T>, dim3((unsigned)((total + 255) / 256), (unsigned)used), dim3(256), 0, stream, ws,
-                 splits, per_range, total, part.as<T>(), tickets, C, M, N, sC, accumulate ? 1 : 0);
+                 splits, per_range, total, part.as<T>(), tickets, C, M, N, sC, accumulate);
         count_launch();
         return check_launch("split-K reduce (two level)");
     }
     if (total <= 8192 && splits >= 16) {
         int blocks = (int)((total + 7) / 8);
-        launch_k(splitk_reduce_warp_kernel<T>, dim3(blocks), dim3(256), 0, stream, ws, splits, total, C, M, N, sC, batch, accumulate ? 1 : 0);
+        launch_k(splitk_reduce_warp_kernel<T>, dim3(blocks), dim3(256), 0, stream, ws, splits, total, C, M, N, sC, batch, accumulate);
         count_launch();
         return check_launch("split-K reduce (warp per element)");
     }
     int64_t want = (total + 255) / 256;
     int blocks = (int)(want < 148 * 8 ? want : 148 * 8);
-    launch_k(splitk_reduce_kernel<T>, dim3(blocks), dim3(256), 0, stream, ws, splits, total, C, M, N, sC, batch, accumulate ? 1 : 0);
+    launch_k(splitk_reduce_kernel<T>, dim3(blocks), dim3(256), 0, stream, ws, splits, total, C, M, N, sC, batch, accumulate);
     count_launch();
     return check_launch("split-K reduce");
 }
-template int launch_splitk_reduce<float>(const float*, int, float*, int64_t, int64_t, int64_t, Strides3, bool,
+template int launch_splitk_reduce<float>(const float*, int, float*, int64_t, int64_t, int64_t, Strides3, int,
                                          cudaStream_t);
-template int launch_splitk_reduce<double>(const double*, int, double*, int64_t, int64_t, int64_t, Strides3, bool,
+template int launch_splitk_reduce<double>(const double*, int, double*, int64_t, int64_t, int64_t, Strides3, int,
                                           cudaStream_t);
 
 template int launch_gemm_simt<float>(const float*, const float*, float*, int64_t, int64_t, int64_t, int64_t,

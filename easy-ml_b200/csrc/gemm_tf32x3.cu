@@ -380,6 +380,22 @@ struct Work {
     int tm, tn, batch, split;
 };
 
+// The non-finite repair (see tf32_repair_kernel below) folded into this kernel's epilogue when the launch writes C itself
+// (no split-K workspace, no accumulation): every CTA reads the operands' "non-finite input seen" words at its start and
+// draws a ticket (the last one clears the stream's shared word, as the separate kernel does); when a word was set, each
+// epilogue thread re-reads the part of the row it has just stored and recomputes the NaNs as f32 fma chains from the
+// unsplit operands.  Saves the separate launch that otherwise follows every product.
+struct RepairArgs {
+    const float* A = nullptr;  // null: not folded
+    const float* B = nullptr;
+    int64_t K = 0;
+    int64_t sAb = 0, sAr = 0, sAc = 0, sBb = 0, sBr = 0, sBc = 0;
+    const unsigned* flag_a = nullptr;
+    const unsigned* flag_b = nullptr;
+    unsigned* stream_flag = nullptr;
+    unsigned* ticket = nullptr;
+};
+
 // tiles_n == 0: symmetric output -- only the tiles on and above the diagonal of a tiles_m x tiles_m grid, row by row
 __device__ __forceinline__ Work decode(int w, int tiles_m, int tiles_n, int splits) {
     Work k;
@@ -415,8 +431,9 @@ __device__ __forceinline__ Work decode(int w, int tiles_m, int tiles_n, int spli
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 tf32x3_pair_kernel(const __grid_constant__ Maps maps, float* __restrict__ C, int64_t M, int64_t N, int64_t ldc,
                    int64_t strideC, int kblocks_total, int kblocks_per_split, int splits, int tiles_m, int tiles_n,
-                   int work_items, int accumulate, float* __restrict__ ws, int64_t ws_split_stride) {
+                   int work_items, int accumulate, float* __restrict__ ws, int64_t ws_split_stride, const RepairArgs rep) {
     pdl_prologue();
+    __shared__ unsigned repair_seen;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* full = reinterpret_cast<uint64_t*>(base + (size_t)STAGES * STAGE_BYTES);
@@ -429,6 +446,11 @@ tf32x3_pair_kernel(const __grid_constant__ Maps maps, float* __restrict__ C, int
     const uint32_t rank = cluster_ctarank();  // 0 = leader
     const int cluster = blockIdx.x >> 1, clusters = gridDim.x >> 1;
 
+    if (threadIdx.x == 32 && rep.A) {
+        repair_seen = ((rep.flag_a && *rep.flag_a) || (rep.flag_b && *rep.flag_b) || *rep.stream_flag) ? 1u : 0u;
+        __threadfence();
+        if (atomicInc(rep.ticket, gridDim.x - 1) == gridDim.x - 1) *rep.stream_flag = 0u;
+    }
     if (threadIdx.x == 0) {
         prefetch_tensormap(&maps.a_big);
         prefetch_tensormap(&maps.a_small);
@@ -580,6 +602,17 @@ tf32x3_pair_kernel(const __grid_constant__ Maps maps, float* __restrict__ C, int
                             if (col0 + j < N) p[j] = add ? p[j] + sum[c * 32 + j] : sum[c * 32 + j];
                     }
                 }
+                if (rep.A && repair_seen) {  // rare: an operand held an Inf / NaN / >= 2^127 value
+                    const float* a = rep.A + (int64_t)wk.batch * rep.sAb + row * rep.sAr;
+                    float* crow = out + row * ld;
+                    for (int64_t col = n0; col < n0 + 128 && col < N; col++) {
+                        if (crow[col] == crow[col]) continue;  // only NaNs can be artefacts of the split
+                        const float* bb = rep.B + (int64_t)wk.batch * rep.sBb + col * rep.sBc;
+                        float acc = 0.0f;
+                        for (int64_t k = 0; k < rep.K; k++) acc = fmaf(a[k * rep.sAc], bb[k * rep.sBr], acc);
+                        crow[col] = acc;
+                    }
+                }
             }
         }
     }
@@ -591,7 +624,8 @@ tf32x3_pair_kernel(const __grid_constant__ Maps maps, float* __restrict__ C, int
 }
 
 int launch(const Maps& maps, float* C, int64_t batch, int64_t M, int64_t N, int64_t ldc, int64_t strideC, int kblocks,
-           int splits, int sms, bool accumulate, float* ws, cudaStream_t stream, bool upper_only = false) {
+           int splits, int sms, int accumulate /* ACC_*; ACC_ZERO_PLUS only with ws */, float* ws, cudaStream_t stream,
+           bool upper_only = false, const RepairArgs* repair = nullptr) {
     static thread_local int configured_dev = -1;
     int dev = 0;
     EML_CUDA(cudaGetDevice(&dev));
@@ -608,8 +642,8 @@ int launch(const Maps& maps, float* C, int64_t batch, int64_t M, int64_t N, int6
     int clusters = sms / 2;
     if (items < clusters) clusters = (int)items;
     launch_k(tf32x3_pair_kernel, dim3(2 * clusters), dim3(THREADS), SMEM_BYTES, stream, 
-        maps, C, M, N, ldc, strideC, kblocks, per_split, used_splits, tiles_m, tiles_n, (int)items, accumulate ? 1 : 0, ws,
-        batch * M * N);
+        maps, C, M, N, ldc, strideC, kblocks, per_split, used_splits, tiles_m, tiles_n, (int)items, accumulate == ACC_ADD ? 1 : 0, ws,
+        batch * M * N, repair ? *repair : RepairArgs{});
     count_launch();
     EML_TRY(check_launch("tf32x3_tcgen05 (CTA pair)"));
     if (ws) EML_TRY(launch_splitk_reduce<float>(ws, used_splits, C, batch, M, N, Strides3{strideC, ldc, 1}, accumulate, stream));
@@ -630,7 +664,7 @@ inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
 template <int BN>
 int launch_tile(const Maps& maps, float* C, int64_t batch, int64_t M, int64_t N, int64_t ldc, int64_t strideC,
-                int kblocks, int splits, bool accumulate, float* ws, cudaStream_t stream) {
+                int kblocks, int splits, int accumulate /* ACC_*; ACC_ZERO_PLUS only with ws */, float* ws, cudaStream_t stream) {
     auto kern = tf32x3_kernel<BN>;
     static thread_local int configured_dev = -1;
     int dev = 0;
@@ -644,7 +678,7 @@ int launch_tile(const Maps& maps, float* C, int64_t batch, int64_t M, int64_t N,
     int used_splits = (kblocks + per_split - 1) / per_split;  // every split owns >= 1 k block
     dim3 grid((unsigned)tiles, (unsigned)batch, (unsigned)used_splits);
     launch_k(kern, dim3(grid), dim3(GEMM_THREADS), Cfg<BN>::SMEM_BYTES, stream, maps, C, M, N, ldc, strideC, kblocks, per_split,
-                                                              accumulate ? 1 : 0, ws, batch * M * N);
+                                                              accumulate == ACC_ADD ? 1 : 0, ws, batch * M * N);
     count_launch();
     EML_TRY(check_launch("tf32x3_tcgen05"));
     if (ws) EML_TRY(launch_splitk_reduce<float>(ws, used_splits, C, batch, M, N, Strides3{strideC, ldc, 1}, accumulate, stream));
@@ -820,6 +854,21 @@ int launch_gemm_tf32x3_f32(DeviceCtx* ctx, const float* A, const float* B, float
     // (measured break-even: 4096^2, where M N / (M + N) = 2048).  It needs >= 24 k blocks per tile to amortise its
     // unoverlapped epilogue, and is pointless when a packed operand is cached (identity hints from the tape).
     // EML_SGEMM_FUSED=1 forces it wherever it can run, =0 disables it.
+    // ACC_ZERO_PLUS (GemmOptions::zero_plus): a split-K launch of the packed kernels ends in the reduction, which writes
+    // 0 + sum; a launch whose epilogue adds into C gets its zeros first
+    const bool zero_plus = accumulate && opt && opt->zero_plus;
+    bool zeroed = false;
+    auto zero_c = [&]() -> int {
+        zeroed = true;
+        const size_t bytes = sizeof(float) * (size_t)(M * N);
+        if (((reinterpret_cast<uintptr_t>(C) | bytes) & 15) == 0) {
+            ZeroRanges z;
+            z.count = 1, z.p[0] = C, z.bytes[0] = bytes;
+            return launch_zero_ranges(z, stream);
+        }
+        EML_CUDA(cudaMemsetAsync(C, 0, bytes, stream));
+        return EML_OK;
+    };
     if (use_pair && !upper_only) {
         const char* fe = getenv("EML_SGEMM_FUSED");
         const bool pays = a_id == 0 && b_id == 0 && kblocks >= 24 * splits && M * N < 1680 * (M + N);
@@ -828,6 +877,7 @@ int launch_gemm_tf32x3_f32(DeviceCtx* ctx, const float* A, const float* B, float
             bool fused = false;
             unsigned* tk = nullptr;
             EML_TRY(stream_tickets(stream, &tk));
+            if (zero_plus) EML_TRY(zero_c());
             EML_TRY(launch_gemm_tf32x3_fused(ctx, A, B, C, batch, M, N, K, sA, sB, sC, splits, accumulate, stream, &fused,
                                              tk + TICKET_NONFINITE));
             if (fused) {
@@ -836,6 +886,11 @@ int launch_gemm_tf32x3_f32(DeviceCtx* ctx, const float* A, const float* B, float
                 return EML_OK;
             }
         }
+    }
+    int acc_mode = accumulate ? ACC_ADD : ACC_WRITE;
+    if (zero_plus && !zeroed) {
+        if (splits > 1) acc_mode = ACC_ZERO_PLUS;
+        else EML_TRY(zero_c());
     }
     TempBuf a_scratch, b_scratch, wsbuf;
     float *a_big, *a_small, *b_big, *b_small;
@@ -865,18 +920,30 @@ int launch_gemm_tf32x3_f32(DeviceCtx* ctx, const float* A, const float* B, float
     EML_TRY(plane_map(&maps.b_big, b_big, Np, Kp, batch, b_box));
     EML_TRY(plane_map(&maps.b_small, b_small, Np, Kp, batch, b_box));
     set_last_kernel("tf32x3_tcgen05");
+    bool repair_folded = false;
     if (use_pair) {
-        EML_TRY(pair::launch(maps, C, batch, M, N, sC.r, sC.b, kblocks, splits, sms, accumulate, ws, stream, upper_only));
+        pair::RepairArgs rep;
+        if (!accumulate && !upper_only && !ws) {  // the kernel stores C itself: the repair rides in its epilogue
+            rep.A = A, rep.B = B, rep.K = K;
+            rep.sAb = sA.b, rep.sAr = sA.r, rep.sAc = sA.c, rep.sBb = sB.b, rep.sBr = sB.r, rep.sBc = sB.c;
+            rep.flag_a = a_flag == stream_flag ? nullptr : a_flag;
+            rep.flag_b = b_flag == stream_flag ? nullptr : b_flag;
+            rep.stream_flag = stream_flag;
+            rep.ticket = tickets;
+            repair_folded = true;
+        }
+        EML_TRY(pair::launch(maps, C, batch, M, N, sC.r, sC.b, kblocks, splits, sms, acc_mode, ws, stream, upper_only,
+                             repair_folded ? &rep : nullptr));
         if (upper_only) opt->upper_done = true;
     } else if (BN == 256) {
-        EML_TRY(launch_tile<256>(maps, C, batch, M, N, sC.r, sC.b, kblocks, splits, accumulate, ws, stream));
+        EML_TRY(launch_tile<256>(maps, C, batch, M, N, sC.r, sC.b, kblocks, splits, acc_mode, ws, stream));
     } else {
-        EML_TRY(launch_tile<128>(maps, C, batch, M, N, sC.r, sC.b, kblocks, splits, accumulate, ws, stream));
+        EML_TRY(launch_tile<128>(maps, C, batch, M, N, sC.r, sC.b, kblocks, splits, acc_mode, ws, stream));
     }
     // (an accumulating launch has already folded the product into C's previous contents: nothing to recompute from;
     //  the upper-triangle launch is mirrored afterwards by the caller, and repaired NaNs stay symmetric only if both
     //  halves are recomputed: run the repair on the full matrix after the mirror is not possible here, so skip it)
-    if (!accumulate && !upper_only)
+    if (!accumulate && !upper_only && !repair_folded)
         EML_TRY(launch_tf32_repair(A, B, C, batch, M, N, K, sA, sB, sC, a_flag, b_flag, stream_flag, stream));
     return EML_OK;
 }

@@ -12,6 +12,7 @@
 #include <cstring>
 #include <numeric>
 #include <memory>
+#include <string>
 #include <vector>
 
 #include <cstdlib>
@@ -164,6 +165,7 @@ struct eml_derivs {
     // which saves a launch per step.
     Buf arena;
     bool slot0_pending = false;
+    int slot0_n = 0;  // the parked sum is the in-order fold of this many slots at the head of the arena (see sweep_from)
     std::vector<std::vector<int64_t>> scatter_offsets;  // host copies of uploaded scatter targets (kept until freed)
 };
 
@@ -191,11 +193,24 @@ struct eml_tape {
         Buf out, w, arena;
         const void* d;
         const void* slot0;
+        int slot0_n;
         int64_t n;
         double lr;
     };
     std::vector<PendingSgd> sgd;
+    // a small asynchronous read-back requested while updates are queued rides in their launch (SgdBatch rider)
+    Buf rider_src;
+    void* rider_dst = nullptr;
+    size_t rider_bytes = 0;
     bool fuse = true;  // EML_FUSE=0: one kernel per elementwise node (the comparison path of the parity tests)
+    // Second stream of the reverse sweep: the two products of a matmul node (dA, dB) and the constant-operand sums are
+    // independent of each other, so the one nothing downstream waits for (a leaf's weight gradient, a sum parked for
+    // derivatives[0]) runs here while the main stream carries on with the chain towards the inputs.  Forked and joined
+    // with events inside one sweep, so a recorded step captures it as parallel graph branches.  EML_SIDE=0: one stream.
+    // Two of them: [0] takes products, [1] the sums -- a sum queued behind a product would start late, and once a
+    // tensor-core GEMM owns the SMs (its CTAs take the whole register file) nothing else gets in until it is done.
+    cudaStream_t side[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
     std::vector<Value> values;
     std::vector<eml_val> free_slots;
     std::mutex mu;
@@ -446,7 +461,11 @@ int flush_sgd(eml_tape* t) {
         for (size_t j = i; j < t->sgd.size() && j < i + SGD_BATCH_MAX; j++) {
             const auto& u = t->sgd[j];
             const int y = b.count++;
-            b.out[y] = u.out->p, b.w[y] = u.w->p, b.d[y] = u.d, b.slot0[y] = u.slot0, b.n[y] = u.n, b.lr[y] = u.lr;
+            b.out[y] = u.out->p, b.w[y] = u.w->p, b.d[y] = u.d, b.slot0[y] = u.slot0, b.slot0_n[y] = u.slot0_n, b.n[y] = u.n, b.lr[y] = u.lr;
+        }
+        if (t->rider_src && i + SGD_BATCH_MAX >= t->sgd.size()) {  // the last launch carries the rider
+            b.copy_src = t->rider_src->p, b.copy_dst = t->rider_dst, b.copy_bytes = t->rider_bytes;
+            t->rider_src.reset();
         }
         EML_TRY(launch_sgd_batch<T>(b, t->stream));
     }
@@ -894,10 +913,10 @@ int sweep_scalars(eml_tape* t, eml_derivs* d, const Node& nd, int64_t self_off, 
 // Does the sweep of matmul node c WRITE (0 + sum, not +=) the derivatives of its parent `parent` when it is the first
 // to contribute to them?  True for the kernels that start their fma chain from +0 themselves: the thin (M <= 4)
 // backward, and dA = G * B^T through the short-contraction kernel.  (Such a parent needs no zero fill and is not read.)
-bool matmul_overwrites(const Node& c, int parent, size_t elem) {
-    if (c.p0 == c.p1) return false;
-    if (thin_shape(c.M, c.N, c.K)) return true;
-    return parent == c.p0 && smallk_shape(c.M, c.K, c.N, elem);
+bool matmul_overwrites(const Node&, int, size_t) {
+    // every product of the sweep can now be the first contribution: the thin kernels and the short-contraction kernel
+    // start their fma chains from +0, the others are asked for 0 + product (GemmOptions::zero_plus)
+    return true;
 }
 
 // The reverse sweep over macro nodes.
@@ -945,7 +964,9 @@ int sweep_from(eml_tape* t, int nv, int64_t seed_elem, eml_derivs** out) {
     // vec![0; len] (:627): one arena for every node's derivatives (+ the Index-0 slot), one memset
     d->grads.resize(t->nodes.size());
     std::vector<size_t> offs(t->nodes.size() + 1);
-    size_t total = 256;  // [0, 256): slot0
+    // [0, SLOT_BYTES): the sums that belong to derivatives[0] (contributions of parents carrying Index 0), one slot each
+    constexpr size_t SLOT_BYTES = 1024;
+    size_t total = SLOT_BYTES;
     for (size_t i = 0; i < t->nodes.size(); i++) {
         offs[i] = total;
         total += (sizeof(T) * (size_t)t->nodes[i].n + 255) & ~size_t(255);
@@ -996,29 +1017,72 @@ int sweep_from(eml_tape* t, int nv, int64_t seed_elem, eml_derivs** out) {
                                        (t->nodes[c].kind != Kind::MATMUL || matmul_overwrites(t->nodes[c], i, sizeof(T)));
         written[i] = !overwritten_first;  // "written" = holds defined numbers (zeros) before the sweep
     }
-    EML_CUDA(cudaMemsetAsync(arena->p, 0, 256, st));
-    for (int i = 0; i < n_nodes;) {
-        if (!written[i]) {
-            i++;
-            continue;
+    {   // (the slots at the head of the arena are written, not added to: no zeros needed there)
+        ZeroRanges z;
+        for (int i = 0; i < n_nodes;) {
+            if (!written[i]) {
+                i++;
+                continue;
+            }
+            int j = i;
+            while (j + 1 < n_nodes && written[j + 1]) j++;
+            if (z.count == ZERO_RANGES_MAX) {
+                EML_TRY(launch_zero_ranges(z, st));
+                z.count = 0;
+            }
+            z.p[z.count] = (char*)arena->p + offs[i];
+            z.bytes[z.count++] = (j + 1 < n_nodes ? offs[j + 1] : total) - offs[i];
+            i = j + 1;
         }
-        int j = i;
-        while (j + 1 < n_nodes && written[j + 1]) j++;
-        EML_CUDA(cudaMemsetAsync((char*)arena->p + offs[i], 0, (j + 1 < n_nodes ? offs[j + 1] : total) - offs[i], st));
-        i = j + 1;
+        EML_TRY(launch_zero_ranges(z, st));
     }
     for (size_t i = 0; i < t->nodes.size(); i++) d->grads[i] = view_of(arena, offs[i], sizeof(T) * (size_t)t->nodes[i].n);
-    // contributions to reference index 0 from parents that carry Index 0 (constants)
+    // Contributions to reference index 0 from parents that carry Index 0 (constants).  The reference adds them to
+    // derivatives[0] one after the other in sweep order; here each one is formed in a slot of its own (0 + sum) and the
+    // slots are folded in that order when derivatives[0] is needed -- the same sequence of additions, but a sum may be
+    // computed on the second stream while the main one moves on.
     T* const slot0_ptr = static_cast<T*>(arena->p);
-    bool slot0_used = false;
+    const int max_slots = (int)(SLOT_BYTES / sizeof(T));
+    int n_slots = 0;
+    // ---- second stream (see eml_tape::side) ----
+    const bool side = t->side[0] != nullptr;
+    bool forked[2] = {false, false};
+    std::vector<char> side_busy(n_nodes, 0);  // derivatives of this node have work pending on a second stream
+    auto fork = [&](int which) -> int {  // that stream continues from everything enqueued on the main one so far
+        EML_CUDA(cudaEventRecord(t->ev_fork, st));
+        EML_CUDA(cudaStreamWaitEvent(t->side[which], t->ev_fork, 0));
+        forked[which] = true;
+        return EML_OK;
+    };
+    auto join = [&]() -> int {
+        for (int which = 0; which < 2; which++) {
+            if (!forked[which]) continue;
+            EML_CUDA(cudaEventRecord(t->ev_join[which], t->side[which]));
+            EML_CUDA(cudaStreamWaitEvent(st, t->ev_join[which], 0));
+            forked[which] = false;
+        }
+        std::fill(side_busy.begin(), side_busy.end(), 0);
+        return EML_OK;
+    };
+    auto busy = [&](int n) { return n >= 0 && side_busy[n]; };
+    auto next_slot = [&](T** out) -> int {
+        if (n_slots == max_slots) {  // fold what there is into the first slot and go on from the second
+            EML_TRY(join());
+            EML_TRY(launch_fold_slots<T>(slot0_ptr, slot0_ptr, n_slots, true, st));
+            n_slots = 1;
+        }
+        *out = slot0_ptr + n_slots++;
+        return EML_OK;
+    };
     // derivatives[self.index] = 1  (:630)
     if (nv >= 0 && seed_in_kernel) {
         // the seed is an argument of the fused group's kernel
     } else if (nv >= 0) {
         EML_TRY(launch_fill<T>((T*)d->grads[nv]->p + seed_elem, T(1), 1, st));
     } else {
-        EML_TRY(launch_fill<T>(slot0_ptr, T(1), 1, st));
-        slot0_used = true;
+        T* slot;
+        EML_TRY(next_slot(&slot));
+        EML_TRY(launch_fill<T>(slot, T(1), 1, st));
     }
     // dparent (+)= g * (deriv array | constant): the first contribution to an uncleared buffer overwrites
     auto contribute = [&](int p, const T* g, const Buf& deriv, bool is_const, double c, int64_t n) -> int {
@@ -1031,6 +1095,17 @@ int sweep_from(eml_tape* t, int nv, int64_t seed_elem, eml_derivs** out) {
         const Node& nd = t->nodes[i];
         const T* g = (const T*)d->grads[i]->p;
         if (nd.kind == Kind::VARIABLES) continue;
+        if (forked[0] || forked[1]) {  // anything this node reads or adds to that a second stream is still working on?
+            bool wait = nd.kind == Kind::VIEW || nd.kind == Kind::SCALARS;
+            if (nd.group >= 0) {
+                const Group& grp = t->groups[nd.group];
+                for (int k = grp.first; k <= grp.last && !wait; k++)
+                    wait = busy(k) || busy(t->nodes[k].p0) || busy(t->nodes[k].p1);
+            } else {
+                wait = wait || busy(i) || busy(nd.p0) || busy(nd.p1);
+            }
+            if (wait) EML_TRY(join());
+        }
         if (nd.kind == Kind::VIEW) {
             EML_TRY(scatter_view<T>(t, d.get(), nd, g, arena, offs, st));
             continue;
@@ -1047,30 +1122,31 @@ int sweep_from(eml_tape* t, int nv, int64_t seed_elem, eml_derivs** out) {
         }
         if (nd.kind == Kind::UNARY) {
             const bool unit = !nd.a && !nd.a_const;  // the in-place SGD node of a recorded step: derivative 1
-            if (nd.p0 >= 0)
+            if (nd.p0 >= 0) {
                 EML_TRY(contribute(nd.p0, g, nd.a, nd.a_const || unit, unit ? 1.0 : nd.a_c, nd.n));
-            else if (!nd.a) {
-                EML_TRY(launch_reduce_sum<T>(t->ctx, g, nd.n, slot0_ptr, true, st));
-                slot0_used = true;
             } else {
-                EML_TRY(launch_dot_accumulate<T>(t->ctx, g, (const T*)nd.a->p, nd.n, slot0_ptr, true, st));
-                slot0_used = true;
+                T* slot;
+                EML_TRY(next_slot(&slot));
+                if (!nd.a) EML_TRY(launch_reduce_sum<T>(t->ctx, g, nd.n, slot, false, st));
+                else EML_TRY(launch_dot_accumulate<T>(t->ctx, g, (const T*)nd.a->p, nd.n, slot, false, st));
             }
         } else if (nd.kind == Kind::BINARY) {
             if (nd.p0_tracked) {
-                if (nd.p0 >= 0)
+                if (nd.p0 >= 0) {
                     EML_TRY(contribute(nd.p0, g, nd.a, nd.a_const, nd.a_c, nd.n));
-                else {
-                    EML_TRY(launch_dot_accumulate<T>(t->ctx, g, (const T*)nd.a->p, nd.n, slot0_ptr, true, st));
-                    slot0_used = true;
+                } else {
+                    T* slot;
+                    EML_TRY(next_slot(&slot));
+                    EML_TRY(launch_dot_accumulate<T>(t->ctx, g, (const T*)nd.a->p, nd.n, slot, false, st));
                 }
             }
             if (nd.p1_tracked) {
-                if (nd.p1 >= 0)
+                if (nd.p1 >= 0) {
                     EML_TRY(contribute(nd.p1, g, nd.b, nd.b_const, nd.b_c, nd.n));
-                else {
-                    EML_TRY(launch_dot_accumulate<T>(t->ctx, g, (const T*)nd.b->p, nd.n, slot0_ptr, true, st));
-                    slot0_used = true;
+                } else {
+                    T* slot;
+                    EML_TRY(next_slot(&slot));
+                    EML_TRY(launch_dot_accumulate<T>(t->ctx, g, (const T*)nd.b->p, nd.n, slot, false, st));
                 }
             }
         } else {  // MATMUL: dA += G * B^T, dB += A^T * G
@@ -1084,38 +1160,62 @@ int sweep_from(eml_tape* t, int nv, int64_t seed_elem, eml_derivs** out) {
                 const bool over_a = dA && !written[nd.p0], over_b = dB && !written[nd.p1];
                 if (dA) written[nd.p0] = 1;
                 if (dB) written[nd.p1] = 1;
-                EML_TRY(launch_thin_bwd<T>(g, A, B, M, N, K, dA, over_a, dB, over_b, nd.p0 < 0, nd.p1 < 0, slot0_ptr, st));
-                slot0_used |= nd.p0 < 0 || nd.p1 < 0;
+                T* slot = nullptr;
+                if (nd.p0 < 0 || nd.p1 < 0) EML_TRY(next_slot(&slot));
+                EML_TRY(launch_thin_bwd<T>(g, A, B, M, N, K, dA, over_a, dB, over_b, nd.p0 < 0, nd.p1 < 0, slot, st));
                 continue;
             }
+            // The two halves of the node are independent.  One of them moves to the second stream when nothing of this
+            // sweep waits for it soon: a constant-operand sum (parked in its slot until derivatives[0] is needed), or
+            // the product that ends in a leaf (a variables container: no node below reads it) while the other one
+            // continues the chain.
+            const bool leaf0 = nd.p0 >= 0 && t->nodes[nd.p0].kind == Kind::VARIABLES;
+            const bool leaf1 = nd.p1 >= 0 && t->nodes[nd.p1].kind == Kind::VARIABLES;
+            bool a_on_side = false, b_on_side = false;
+            if (side && nd.p0 != nd.p1) {
+                if (nd.p0 < 0) a_on_side = true;
+                else if (nd.p1 < 0) b_on_side = true;
+                else if (leaf1) b_on_side = true;
+                else if (leaf0) a_on_side = true;
+            }
+            T* slot = nullptr;
+            if (nd.p0 < 0 || nd.p1 < 0) EML_TRY(next_slot(&slot));  // (may join: before the fork)
+            // products to side[0], sums to side[1]
+            const int which = (a_on_side && nd.p0 < 0) || (b_on_side && nd.p1 < 0) ? 1 : 0;
+            if (a_on_side || b_on_side) EML_TRY(fork(which));
+            const cudaStream_t sa = a_on_side ? t->side[which] : st, sb = b_on_side ? t->side[which] : st;
             if (nd.p0 >= 0) {
                 GemmOptions ids;
                 ids.b_id = nd.b->identity;
-                const bool over = !written[nd.p0];  // only when matmul_overwrites() promised a kernel that starts from +0
+                ids.zero_plus = !written[nd.p0];  // the first contribution: 0 + product, nobody cleared the buffer
                 written[nd.p0] = 1;
                 EML_TRY(contract_dev<T>(t->ctx, g, B, (T*)d->grads[nd.p0]->p, 1, M, K, N, Strides3{0, N, 1},
-                                        Strides3{0, 1, N}, Strides3{0, K, 1}, !over, false, st, &ids));
+                                        Strides3{0, 1, N}, Strides3{0, K, 1}, true, false, sa, &ids));
+                if (a_on_side) side_busy[nd.p0] = 1;
             } else {
                 // every element of A carries Index 0: derivatives[0] += sum_ik (G B^T)[i,k]
                 //   = sum_j colsum(G)[j] * colsum(B)[j]
-                EML_TRY(launch_quirk_cols<T>(g, M, B, K, N, slot0_ptr, st));
-                slot0_used = true;
+                EML_TRY(launch_quirk_cols<T>(g, M, B, K, N, slot, sa));
             }
             if (nd.p1 >= 0) {
                 GemmOptions ids;
                 ids.a_id = nd.a->identity;
+                ids.zero_plus = !written[nd.p1];
+                written[nd.p1] = 1;
                 EML_TRY(contract_dev<T>(t->ctx, A, g, (T*)d->grads[nd.p1]->p, 1, K, N, M, Strides3{0, 1, K},
-                                        Strides3{0, N, 1}, Strides3{0, N, 1}, true, false, st, &ids));
+                                        Strides3{0, N, 1}, Strides3{0, N, 1}, true, false, sb, &ids));
+                if (b_on_side) side_busy[nd.p1] = 1;
             } else {
                 // derivatives[0] += sum_kj (A^T G)[k,j] = sum_i rowsum(A)[i] * rowsum(G)[i]
-                EML_TRY(launch_quirk_rows<T>(A, K, g, N, M, slot0_ptr, st));
-                slot0_used = true;
+                EML_TRY(launch_quirk_rows<T>(A, K, g, N, M, slot, sb));
             }
         }
     }
+    EML_TRY(join());
     // reference index 0 is element 0 of the first node: added on first use (fold_slot0) or by the weight update
     d->arena = arena;
-    d->slot0_pending = slot0_used;
+    d->slot0_pending = n_slots > 0;
+    d->slot0_n = n_slots;
     *out = d.release();
     return EML_OK;
 }
@@ -1142,6 +1242,18 @@ int eml_tape_create(int dtype, eml_tape** out) {
     t->ctx = ctx;
     t->stream = ctx->stream;
     if (const char* e = getenv("EML_FUSE")) t->fuse = !(e[0] == '0');
+    const char* se = getenv("EML_SIDE");
+    if (!(se && se[0] == '0')) {
+        cudaError_t e = cudaEventCreateWithFlags(&t->ev_fork, cudaEventDisableTiming);
+        for (int which = 0; which < 2 && e == cudaSuccess; which++) {
+            e = cudaStreamCreateWithFlags(&t->side[which], cudaStreamNonBlocking);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t->ev_join[which], cudaEventDisableTiming);
+        }
+        if (e != cudaSuccess) {
+            delete t;
+            return cuda_fail(e, "second stream of the tape", __FILE__, __LINE__);
+        }
+    }
     *out = t;
     return EML_OK;
 }
@@ -1150,6 +1262,14 @@ int eml_tape_destroy(eml_tape* t) {
     if (!t) return EML_OK;
     check_tape(t);
     cudaStreamSynchronize(t->stream);
+    for (int which = 0; which < 2; which++) {
+        if (t->side[which]) {
+            cudaStreamSynchronize(t->side[which]);
+            cudaStreamDestroy(t->side[which]);
+        }
+        if (t->ev_join[which]) cudaEventDestroy(t->ev_join[which]);
+    }
+    if (t->ev_fork) cudaEventDestroy(t->ev_fork);
     delete t;
     return EML_OK;
 }
@@ -1364,8 +1484,33 @@ int eml_val_numbers_async(eml_tape* t, eml_val h, void* pinned_host_out, void** 
     std::lock_guard<std::mutex> lock(t->mu);
     Value* v;
     EML_TRY(get_value(t, h, &v));
-    EML_TRY(flush(t));
-    EML_CUDA(cudaMemcpyAsync(pinned_host_out, v->numbers->p, esize(t->dtype) * v->n(), cudaMemcpyDeviceToHost, t->stream));
+    {
+        // a few KB (a loss value): stored by a kernel through the buffer's device mapping -- by the queued weight
+        // updates' own launch when there is one and the numbers already exist; anything else, or memory that is not
+        // page-locked / mapped, takes the copy engine
+        const size_t bytes = esize(t->dtype) * (size_t)v->n();
+        void* mapped = nullptr;
+        const bool small = bytes <= 4096 && cudaHostGetDevicePointer(&mapped, pinned_host_out, 0) == cudaSuccess && mapped;
+        const bool riding = small && v->numbers && !t->sgd.empty() && !t->rider_src;
+        if (riding) {
+            t->rider_src = v->numbers;
+            t->rider_dst = mapped;
+            t->rider_bytes = bytes;
+        }
+        const int flushed = flush(t);
+        if (flushed != EML_OK) {
+            t->rider_src.reset();
+            return flushed;
+        }
+        if (riding) {
+            // went out with the updates
+        } else if (small) {
+            EML_TRY(launch_copy_to_host(v->numbers->p, mapped, bytes, t->stream));
+        } else {
+            cudaGetLastError();
+            EML_CUDA(cudaMemcpyAsync(pinned_host_out, v->numbers->p, bytes, cudaMemcpyDeviceToHost, t->stream));
+        }
+    }
     if (arrival && t->capturing) {
         *arrival = nullptr;  // inside a recorded step the arrival comes from eml_graph_launch
     } else if (arrival) {
@@ -1469,6 +1614,78 @@ int eml_graph_launch(eml_graph* g, void** arrival) {
     return EML_OK;
 }
 
+int eml_graph_profile(eml_graph* g, int replays, char* report, int64_t capacity) {
+    if (!g || !g->exec || !report || capacity < 1 || replays < 1) EML_BAD_ARG("graph_profile: bad argument");
+    EML_TRY(check_tape(g->tape));
+    cudaStream_t st = g->tape->stream;
+    size_t n = 0;
+    EML_CUDA(cudaGraphGetNodes(g->graph, nullptr, &n));
+    std::vector<cudaGraphNode_t> nodes(n);
+    if (n) EML_CUDA(cudaGraphGetNodes(g->graph, nodes.data(), &n));
+    cudaEvent_t e0, e1;
+    EML_CUDA(cudaEventCreate(&e0));
+    EML_CUDA(cudaEventCreate(&e1));
+    auto time_us = [&](double* us) -> int {
+        for (int i = 0; i < 3; i++) EML_CUDA(cudaGraphLaunch(g->exec, st));
+        EML_CUDA(cudaEventRecord(e0, st));
+        for (int i = 0; i < replays; i++) EML_CUDA(cudaGraphLaunch(g->exec, st));
+        EML_CUDA(cudaEventRecord(e1, st));
+        EML_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        EML_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        *us = (double)ms * 1e3 / replays;
+        return EML_OK;
+    };
+    std::string out;
+    char line[512];
+    struct K {
+        cudaGraphNode_t node;
+        std::string name;
+    };
+    std::vector<K> kernels;
+    for (cudaGraphNode_t nd : nodes) {
+        cudaGraphNodeType type;
+        EML_CUDA(cudaGraphNodeGetType(nd, &type));
+        if (type == cudaGraphNodeTypeMemcpy || type == cudaGraphNodeTypeMemset) {
+            kernels.push_back(K{nd, type == cudaGraphNodeTypeMemcpy ? "(memcpy node)" : "(memset node)"});
+            continue;
+        }
+        if (type != cudaGraphNodeTypeKernel) continue;
+        cudaKernelNodeParams kp{};
+        EML_CUDA(cudaGraphKernelNodeGetParams(nd, &kp));
+        const char* name = nullptr;
+        if (cudaFuncGetName(&name, kp.func) != cudaSuccess || !name) name = "?", cudaGetLastError();
+        kernels.push_back(K{nd, name});
+    }
+    double whole = 0, base = 0;
+    EML_TRY(time_us(&whole));
+    // the weight updates stay off from here on: with a kernel missing the step computes garbage, and garbage must not
+    // accumulate in the weights (non-finite weights would send the f32 products down their repair path)
+    for (const K& k : kernels)
+        if (k.name.find("sgd") != std::string::npos) EML_CUDA(cudaGraphNodeSetEnabled(g->exec, k.node, 0));
+    EML_TRY(time_us(&base));
+    snprintf(line, sizeof line, "%.2f\tus per replay, %zu nodes (%zu kernels)\n%.2f\tus per replay without the weight updates\n", whole,
+             n, kernels.size(), base);
+    out += line;
+    for (const K& k : kernels) {
+        if (k.name.find("sgd") != std::string::npos) continue;
+        EML_CUDA(cudaGraphNodeSetEnabled(g->exec, k.node, 0));
+        double us = 0;
+        EML_TRY(time_us(&us));
+        EML_CUDA(cudaGraphNodeSetEnabled(g->exec, k.node, 1));
+        snprintf(line, sizeof line, "%+.2f\t%s\n", us - base, k.name.substr(0, 160).c_str());
+        out += line;
+    }
+    for (const K& k : kernels)
+        if (k.name.find("sgd") != std::string::npos) EML_CUDA(cudaGraphNodeSetEnabled(g->exec, k.node, 1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    const size_t len = out.size() < (size_t)capacity - 1 ? out.size() : (size_t)capacity - 1;
+    memcpy(report, out.data(), len);
+    report[len] = 0;
+    return EML_OK;
+}
+
 int eml_graph_destroy(eml_graph* g) {
     if (!g) return EML_OK;
     if (g->exec) cudaGraphExecDestroy(g->exec);
@@ -1560,8 +1777,8 @@ static int fold_slot0(eml_derivs* d) {
     if (!d->slot0_pending) return EML_OK;
     EML_TRY(flush(d->tape));  // a queued weight update reads derivatives[0] and the parked sum separately
     d->slot0_pending = false;
-    if (d->dtype == EML_F32) return launch_add_inplace<float>((float*)d->grads[0]->p, (const float*)d->arena->p, 1, d->stream);
-    return launch_add_inplace<double>((double*)d->grads[0]->p, (const double*)d->arena->p, 1, d->stream);
+    if (d->dtype == EML_F32) return launch_fold_slots<float>((float*)d->grads[0]->p, (const float*)d->arena->p, d->slot0_n, false, d->stream);
+    return launch_fold_slots<double>((double*)d->grads[0]->p, (const double*)d->arena->p, d->slot0_n, false, d->stream);
 }
 
 static int derivs_not_while_capturing(eml_derivs* d) {
@@ -1725,7 +1942,8 @@ int eml_tape_sgd_update(eml_tape* t, eml_val hw, eml_derivs* d, double lr) {
     }
     u.arena = d->arena;
     u.d = d->grads[w->node]->p;
-    u.slot0 = (d->slot0_pending && w->node == 0) ? d->arena->p : nullptr;  // derivatives[0] + the parked sum, on the fly
+    u.slot0 = (d->slot0_pending && w->node == 0) ? d->arena->p : nullptr;  // derivatives[0] + the parked sums, on the fly
+    u.slot0_n = d->slot0_n;
     u.n = n;
     u.lr = lr;
     w->numbers = u.out;

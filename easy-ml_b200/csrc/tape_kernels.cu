@@ -115,7 +115,7 @@ __device__ __forceinline__ T tile_col_sum(const T* __restrict__ X, int64_t r0, i
 
 // grid (column blocks of 32, row chunks): block (x, y) sums its chunk of G's rows and of B's rows for its 32 columns;
 // the last chunk of a column block (ticket x) adds the chunks in order and forms sum_c gs[c] * bs[c] over its columns;
-// the last column block (ticket MAX - 1) adds those in order into out[0].
+// the last column block (ticket MAX - 1) adds those in order and writes the sum to out[0].
 template <class T>
 __global__ void __launch_bounds__(TK_THREADS)
 quirk_cols_kernel(const T* __restrict__ G, int64_t gm, int64_t g_rows, const T* __restrict__ B, int64_t bm, int64_t b_rows,
@@ -174,11 +174,11 @@ quirk_cols_kernel(const T* __restrict__ G, int64_t gm, int64_t g_rows, const T* 
     if (threadIdx.x == 0) {
         T total = T(0);
         for (int i = 0; i < (int)gridDim.x; i++) total += __ldcg(partial_cb + i);
-        out[0] = out[0] + total;
+        out[0] = total;  // (a slot of its own: the sweep folds the slots in order)
     }
 }
 
-// out[0] += sum_i rowsum(A)[i] * rowsum(G)[i]; one warp per row, rows of a warp in ascending order
+// out[0] = sum_i rowsum(A)[i] * rowsum(G)[i]; one warp per row, rows of a warp in ascending order
 template <class T>
 __global__ void __launch_bounds__(TK_THREADS)
 quirk_rows_kernel(const T* __restrict__ A, int64_t K, const T* __restrict__ G, int64_t N, int64_t M, T* partial,
@@ -208,7 +208,7 @@ quirk_rows_kernel(const T* __restrict__ A, int64_t K, const T* __restrict__ G, i
     T v = T(0);
     for (int i = threadIdx.x; i < (int)gridDim.x; i += TK_THREADS) v += __ldcg(partial + i);
     const T total = block_sum<T>(v, smem);
-    if (threadIdx.x == 0) out[0] = out[0] + total;
+    if (threadIdx.x == 0) out[0] = total;  // (a slot of its own: the sweep folds the slots in order)
 }
 
 // ---- thin products: M <= TH_M rows --------------------------------------------------------------------------------
@@ -337,7 +337,7 @@ thin_bwd_kernel(const T* __restrict__ G, const T* __restrict__ A, const T* __res
     if (t == 0) {
         T total = T(0);
         for (int i = 0; i < TK_THREADS / 32; i++) total += smem[i];
-        slot0[0] = slot0[0] + total;
+        slot0[0] = total;  // (a slot of its own: the sweep folds the slots in order)
     }
 }
 

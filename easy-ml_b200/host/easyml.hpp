@@ -18,6 +18,7 @@
 #include <optional>
 #include <sstream>
 #include <stdexcept>
+#include <cstring>
 #include <string>
 #include <type_traits>
 #include <utility>
@@ -683,6 +684,13 @@ class RecordedStep {
         void* arrival = nullptr;
         detail::check(eml_graph_launch(g_, &arrival));
         return arrival;
+    }
+    // development aid: critical-path cost of every kernel of the step (see eml_graph_profile); the model is garbage after
+    std::string profile(int replays = 200) const {
+        std::string report(1 << 16, '\0');
+        detail::check(eml_graph_profile(g_, replays, report.data(), (int64_t)report.size()));
+        report.resize(std::strlen(report.c_str()));
+        return report;
     }
 
   private:

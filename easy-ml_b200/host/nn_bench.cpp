@@ -107,6 +107,7 @@ static Result run(int batch, int steps, bool graph) {
         detail::check(eml_sync());
         r.ms_per_step = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() / steps * 1e3;
         r.launches_per_step = double(eml_kernel_launches() - l1) / steps;
+        if (std::getenv("NN_PROFILE")) std::fprintf(stderr, "%s", g0.profile(200).c_str());
     }
     if (!graph) r.launches_per_step = double(eml_kernel_launches() - l0) / steps;
     r.first = first;

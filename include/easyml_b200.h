@@ -404,6 +404,14 @@ int eml_tape_capture_begin(eml_tape* t);
 int eml_tape_capture_end(eml_tape* t, eml_graph** out);
 int eml_graph_launch(eml_graph* g, void** arrival);
 int eml_graph_destroy(eml_graph* g);
+/* Development aid (no counterpart in the reference): what each kernel of a recorded step costs on the step's critical
+ * path.  Times `replays` replays of the graph, then `replays` more per kernel node with that node switched off, and
+ * writes a NUL-terminated text report (first two lines: microseconds per replay with and without the weight updates; then
+ * one line per kernel, "<change in microseconds>\t<kernel name>") into report[0..capacity).  A negative number is what
+ * the step would gain if that kernel cost nothing; kernels that overlap others show less than their own duration.
+ * The step computes garbage while a kernel is off (weight updates are kept off meanwhile): use it on a model you are
+ * about to throw away. */
+int eml_graph_profile(eml_graph* g, int replays, char* report, int64_t capacity);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,232 @@
+"""The reverse sweep's second stream (csrc/tape.cu, eml_tape::side) against the single-stream sweep, bit for bit.
+
+Record::try_derivatives (reference src/differentiation.rs:623-648) walks the list once, sequentially.  On the device the
+two products of a matmul node (dA = G B^T, dB = A^T G; record_scalar_product's two parents per product, reference
+container_operations.rs:1291-1296) are independent, and so are the sums a constant operand sends to derivatives[0]:
+the half nothing downstream waits for runs on a second stream.  That may not change a single bit: every derivative,
+derivatives[0] (the parked sums are folded in sweep order, also when there are more of them than slots), the updated
+weights and a recorded step's replays are compared with EML_SIDE=0; the constant-operand sums are also checked against
+the oracle's literal scalar tape.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import easy_ml_b200 as eml
+
+pytestmark = pytest.mark.gpu
+
+DTYPES = [np.float32, np.float64]
+
+
+def tape(dtype, side):
+    old = os.environ.get("EML_SIDE")
+    os.environ["EML_SIDE"] = "1" if side else "0"
+    try:
+        return eml.WengertList(dtype)  # the switch is read when the list is created
+    finally:
+        if old is None:
+            del os.environ["EML_SIDE"]
+        else:
+            os.environ["EML_SIDE"] = old
+
+
+def T(names, a):
+    return eml.Tensor(list(zip(names, a.shape)), a)
+
+
+def same_bits(a, b):
+    a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+    return a.shape == b.shape and a.dtype == b.dtype and a.tobytes() == b.tobytes()
+
+
+def sigmoid(z):
+    return ((-z).exp() + 1.0).div_swapped(1.0)
+
+
+def both(dtype, program):
+    res = [program(tape(dtype, side)) for side in (True, False)]
+    assert res[0].keys() == res[1].keys()
+    for k in res[0]:
+        assert same_bits(res[0][k], res[1][k]), f"{k}: the two-stream sweep differs from the single-stream sweep"
+    return res[0]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("n,i,h,o", [(96, 40, 24, 10), (520, 300, 260, 12)])
+def test_three_layer_network_with_a_shared_weight(dtype, n, i, h, o):
+    """Inputs constant (their sums go to derivatives[0] on the second stream), every weight a leaf (its gradient product
+    goes to the second stream), one weight used by three products (a later use has to wait for the earlier one's
+    product on the second stream).  (520, 300, 260) takes the tensor-core kernels."""
+    r = np.random.default_rng(11)
+    x = r.uniform(0, 1, (n, i)).astype(dtype)
+    lab = np.eye(o, dtype=dtype)[r.integers(0, o, n)]
+    w1 = r.uniform(-0.3, 0.3, (i, h)).astype(dtype)
+    wh = r.uniform(-0.3, 0.3, (h, h)).astype(dtype)
+    w2 = r.uniform(-0.3, 0.3, (h, o)).astype(dtype)
+
+    def program(hist):
+        W1 = eml.RecordTensor.variables(hist, T("ih", w1))
+        WH = eml.RecordTensor.variables(hist, T("hg", wh))
+        W2 = eml.RecordTensor.variables(hist, T("ho", w2))
+        X = eml.RecordTensor.constants(T("ni", x), hist)
+        Y = eml.RecordTensor.constants(T("no", lab), hist)
+        L = eml.RecordTensor.constants(T("un", np.ones((1, n), dtype)), hist)
+        R = eml.RecordTensor.constants(T("ov", np.ones((o, 1), dtype)), hist)
+        out = {}
+        for step in range(2):
+            a1 = sigmoid(X * W1)
+            a2 = sigmoid(a1 * WH)
+            a3 = sigmoid(a2 * WH)            # WH again: both products add into the same derivatives
+            a4 = a3 * WH                     # ... and a third use
+            mix = sigmoid(a4) - a2           # a2 has two consumers
+            y = sigmoid(mix * W2)
+            diff = y - Y
+            loss = ((L * diff.elementwise_multiply(diff)) * R) / float(n)
+            d = loss.derivatives_for([0, 0])
+            out[f"g1_{step}"] = d.at_tensor(W1).data
+            out[f"gh_{step}"] = d.at_tensor(WH).data
+            out[f"g2_{step}"] = d.at_tensor(W2).data
+            out[f"d0_{step}"] = np.array(d.at_index(0))
+            out[f"loss_{step}"] = loss.numbers().data.copy()
+            eml.sgd_update(W1, d, 0.5)
+            eml.sgd_update(WH, d, 0.5)
+            eml.sgd_update(W2, d, 0.5)
+            hist.clear()
+            W1.reset()
+            WH.reset()
+            W2.reset()
+        out["w1"] = W1.numbers().data
+        out["wh"] = WH.numbers().data
+        out["w2"] = W2.numbers().data
+        return out
+
+    both(dtype, program)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_variables_times_computed_and_computed_times_variables(dtype):
+    """The leaf may be the LEFT operand (W * H layouts) and both operands may be leaves."""
+    r = np.random.default_rng(12)
+    a = r.uniform(-1, 1, (48, 20)).astype(dtype)
+    b = r.uniform(-1, 1, (20, 36)).astype(dtype)
+    c = r.uniform(-1, 1, (36, 7)).astype(dtype)
+
+    def program(hist):
+        A = eml.RecordTensor.variables(hist, T("mk", a))
+        B = eml.RecordTensor.variables(hist, T("kn", b))
+        Cc = eml.RecordTensor.variables(hist, T("np", c))
+        ab = A * B                      # both leaves
+        h = sigmoid(ab)
+        out = (h * Cc).elementwise_multiply(h * Cc)    # Cc: leaf on the right, twice
+        d = out.derivatives_for([5, 3])
+        return {"ga": d.at_tensor(A).data, "gb": d.at_tensor(B).data, "gc": d.at_tensor(Cc).data}
+
+    both(dtype, program)
+
+    wl = r.uniform(-1, 1, (30, 48)).astype(dtype)
+
+    def program2(hist):
+        WL = eml.RecordTensor.variables(hist, T("om", wl))
+        A = eml.RecordTensor.variables(hist, T("mk", a))
+        B = eml.RecordTensor.constants(T("kn", b), hist)
+        hcomp = sigmoid(A * B)          # constant on the right: row-sum form of the parked sum
+        y = WL * hcomp                  # leaf on the left
+        d = y.derivatives_for([2, 2])
+        return {"gwl": d.at_tensor(WL).data, "ga": d.at_tensor(A).data, "d0": np.array(d.at_index(0))}
+
+    both(dtype, program2)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("m", [3, 6])
+def test_more_constant_operand_sums_than_slots(orc, dtype, m):
+    """300 products with a constant operand in one sweep: more parked sums than the arena has slots (256 f32, 128 f64),
+    so they are folded on the way.  m = 3 takes the thin kernels, m = 6 the column-sum kernel on the second stream.
+    derivatives[0] is the in-order sum of all of them: compared with the oracle's scalar tape."""
+    r = np.random.default_rng(13)
+    k, n, count = 5, 4, 300
+    xs = [r.uniform(-1, 1, (m, k)).astype(dtype) for _ in range(count)]
+    w = r.uniform(-1, 1, (k, n)).astype(dtype)
+
+    def program(hist):
+        W = eml.RecordTensor.variables(hist, T("kn", w))
+        acc = None
+        for x in xs:
+            c = eml.RecordTensor.constants(T("mk", x), hist) * W
+            acc = c if acc is None else acc + c
+        sq = acc.elementwise_multiply(acc)
+        d = sq.derivatives_for([m - 1, 1])
+        return {"gw": d.at_tensor(W).data, "d0": np.array(d.at_index(0))}
+
+    got = both(dtype, program)
+
+    t = orc.Tape(dtype)
+    ow = t.variables(w)
+    oacc = None
+    for x in xs:
+        oc = t.matmul(orc.Tape.constants(x, dtype), ow)
+        oacc = oc if oacc is None else t.binary(32, oacc, oc, mode=3)
+    osq = t.binary(34, oacc, oacc, mode=3)
+    od = t.derivatives(osq[1][m - 1, 1])
+    rtol = 2e-4 if dtype == np.float32 else 1e-11
+    scale = float(np.abs(od).max())
+    assert np.allclose(got["gw"], od[ow[1]], rtol=rtol, atol=rtol * scale)
+    # derivatives[0] = W[0, 0]'s own derivative + every constant operand's sum
+    assert np.allclose(float(got["d0"]), float(od[0]), rtol=rtol, atol=rtol * scale * count)
+
+
+def test_recorded_step_with_the_second_stream_replays_bit_for_bit():
+    """Fork and join are captured as parallel branches of the CUDA graph."""
+    r = np.random.default_rng(14)
+    n, i, h, o = 256, 64, 32, 10
+    x = r.uniform(0, 1, (n, i)).astype(np.float32)
+    lab = np.eye(o, dtype=np.float32)[r.integers(0, o, n)]
+    w1 = r.uniform(-0.5, 0.5, (i, h)).astype(np.float32)
+    w2 = r.uniform(-0.5, 0.5, (h, o)).astype(np.float32)
+
+    def run(recorded, side):
+        hist = tape(np.float32, side)
+        W1 = eml.RecordTensor.variables(hist, T("ih", w1))
+        W2 = eml.RecordTensor.variables(hist, T("ho", w2))
+        X = eml.RecordTensor.constants(T("ni", x), hist)
+        Y = eml.RecordTensor.constants(T("no", lab), hist)
+        L = eml.RecordTensor.constants(T("un", np.ones((1, n), np.float32)), hist)
+        R = eml.RecordTensor.constants(T("ov", np.ones((o, 1), np.float32)), hist)
+        pinned = eml.PinnedBuffer((1,), np.float32)
+
+        def body():
+            out = sigmoid(sigmoid(X * W1) * W2)
+            diff = out - Y
+            loss = ((L * diff.elementwise_multiply(diff)) * R) / float(n)
+            d = loss.derivatives_for([0, 0])
+            eml.sgd_update(W1, d, 0.5)
+            eml.sgd_update(W2, d, 0.5)
+            arrival = loss.numbers_async(pinned)
+            del out, diff, loss, d
+            hist.clear()
+            W1.reset()
+            W2.reset()
+            return arrival
+
+        losses = []
+        for _ in range(2):
+            eml.wait_arrival(body())
+            losses.append(float(pinned.array[0]))
+        if recorded:
+            step = hist.record(body)
+            for _ in range(4):
+                eml.wait_arrival(step.launch())
+                losses.append(float(pinned.array[0]))
+        else:
+            for _ in range(4):
+                eml.wait_arrival(body())
+                losses.append(float(pinned.array[0]))
+        return np.array(losses, np.float32), W1.numbers().data, W2.numbers().data
+
+    base = run(False, False)
+    for recorded, side in ((False, True), (True, True), (True, False)):
+        got = run(recorded, side)
+        for a, b in zip(base, got):
+            assert same_bits(a, b), f"recorded={recorded} side={side}"
