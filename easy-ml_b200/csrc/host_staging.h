@@ -38,10 +38,11 @@ class StagedCopier {
         size_t dpitch, width;
         int64_t rows;
     };
-    int acquire(int* slot);
+    int acquire(int dir, int* slot);
     int complete(const Pending& p);
+    int drain_ready();
     DeviceCtx* ctx_;
-    int next_ = 0;
+    int next_[2] = {0, 0};
     std::vector<Pending> pending_;  // device-to-host chunks whose data still sits in a slot
 };
 
