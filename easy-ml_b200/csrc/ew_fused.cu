@@ -521,6 +521,13 @@ int launch_any(const EwProgram& p, cudaStream_t stream) {
     // every pointer of a program comes from the stream-ordered allocator or the sweep's arena (256-byte aligned), so the
     // vector path only needs the element count to be a whole number of 16-byte vectors
     if (p.n % VN != 0) EML_GO(1, 1);
+    // a container too small to give every SM a CTA of 16-byte vectors is latency-bound: one element per thread spreads
+    // it over four times as many threads (NN step: the 8192 x 10 output-layer group, 3 us faster per step)
+    static const bool small_scalar = [] {
+        const char* e = getenv("EML_EW_SMALL_SCALAR");
+        return !(e && e[0] == '0');
+    }();
+    if (small_scalar && p.n < (int64_t)148 * EW_THREADS_FUSED * VN) EML_GO(1, 1);
     switch (unroll_for(p, VN, sizeof(T))) {
         case 4: EML_GO(VN, 4);
         case 2: EML_GO(VN, 2);
