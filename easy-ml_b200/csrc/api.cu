@@ -65,7 +65,7 @@ int contract_dev(DeviceCtx* ctx, const T* A, const T* B, T* C, int64_t batch, in
                  GemmOptions* opt) {
     GemmOptions local;
     if (!opt) opt = &local;
-    opt->remote_done = opt->upper_done = false;
+    opt->remote_done = opt->upper_done = opt->epilogue_done = false;
     // ACC_ZERO_PLUS (see GemmOptions::zero_plus): kernels that cannot write `0 + product` get their zeros here
     const bool zp = accumulate && opt->zero_plus;
     if (zp && !(batch == 1 && sC.c == 1 && sC.r == N && C)) EML_BAD_ARG("contract: zero_plus needs a dense C");
@@ -139,6 +139,7 @@ int contract_dev(DeviceCtx* ctx, const T* A, const T* B, T* C, int64_t batch, in
             GemmOptions swapped = *opt;  // the operands swap roles in the transposed problem
             swapped.a_id = opt->b_id;
             swapped.b_id = opt->a_id;
+            swapped.epilogue = nullptr;  // (its outputs are laid out like C, not like C^T)
             Strides3 tA{sB.b, sB.c, sB.r}, tB{sA.b, sA.c, sA.r}, tC{sC.b, sC.c, sC.r};
             rc = tensor_core_path<T>(ctx, B, A, C, batch, N, M, K, tA, tB, tC, accumulate, stream, &handled, &swapped);
             opt->remote_done = swapped.remote_done;

@@ -128,6 +128,19 @@ struct Strides3 {
     int64_t b, r, c;  // batch, row, column strides in elements
 };
 
+// A run of container-level unary operators applied to a product's output INSIDE the GEMM epilogue (f32 CTA-pair kernel):
+// the tape hands over the fused elementwise group that follows a matmul (RecordTensor::unary chains, reference
+// container_operations.rs:1644-1804 / swapped.rs:36-45) when it is one of the whitelisted straight-line chains -- the
+// reference examples' sigmoid, 1 / (1 + e^-x), as neg, exp, + c, c / x.  C itself is always stored (the sweep recomputes
+// the chain from it); out[k] != null: op k's container is held by somebody and is stored too.  Same rules, same
+// -fmad=false arithmetic as the elementwise kernels: bit-identical to running the group as its own kernel.
+struct EpilogueChain {
+    int n_ops = 0;
+    int op[4] = {0, 0, 0, 0};      // EML_OP_*
+    float c[4] = {0, 0, 0, 0};     // scalar operands
+    float* out[4] = {nullptr, nullptr, nullptr, nullptr};  // dense, row stride N
+};
+
 // Per-call options of the contraction dispatcher and what the kernel it chose reports back.
 struct GemmOptions {
     // ---- in ----
@@ -149,7 +162,10 @@ struct GemmOptions {
     // The reverse sweep's first contribution to a derivative buffer.  Paths that end in a split-K reduction write
     // `0 + sum` there (ACC_ZERO_PLUS); the others zero C themselves first.  C must be dense (row stride N, batch 1).
     bool zero_plus = false;
+    // Elementwise chain for the epilogue (see EpilogueChain); honoured only by the kernel that stores C itself
+    const EpilogueChain* epilogue = nullptr;
     // ---- out ----
+    bool epilogue_done = false;  // the chain's containers were written by the GEMM
     bool remote_done = false;  // the kernel that ran stored the tiles to the peers
     bool upper_done = false;   // the kernel that ran computed the upper triangle only
 };

@@ -35,6 +35,7 @@
 #include "common.h"
 #include "sm100.cuh"
 #include "tf32_split.cuh"
+#include "ew_rules.cuh"
 
 namespace eml {
 
@@ -428,10 +429,13 @@ __device__ __forceinline__ Work decode(int w, int tiles_m, int tiles_n, int spli
     return k;
 }
 
+// EPI: 0 = plain; 1 = the sigmoid chain (neg, exp, + c, c / x) applied to the finished tile in the epilogue (EpilogueChain)
+template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 tf32x3_pair_kernel(const __grid_constant__ Maps maps, float* __restrict__ C, int64_t M, int64_t N, int64_t ldc,
                    int64_t strideC, int kblocks_total, int kblocks_per_split, int splits, int tiles_m, int tiles_n,
-                   int work_items, int accumulate, float* __restrict__ ws, int64_t ws_split_stride, const RepairArgs rep) {
+                   int work_items, int accumulate, float* __restrict__ ws, int64_t ws_split_stride, const RepairArgs rep,
+                   const EpilogueChain epi) {
     pdl_prologue();
     __shared__ unsigned repair_seen;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -613,6 +617,43 @@ tf32x3_pair_kernel(const __grid_constant__ Maps maps, float* __restrict__ C, int
                         crow[col] = acc;
                     }
                 }
+                if constexpr (EPI == 1) {
+                    // the elementwise chain on the tile just stored (one batch, dense outputs with row stride N)
+                    const bool reread = rep.A && repair_seen;  // (repaired elements live in C, not in the registers)
+                    const bool ovec = (N & 3) == 0;
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        const int64_t col0 = n0 + c * 32;
+                        if (col0 >= N) continue;
+                        const float* zrow = out + row * ld + col0;
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; j4++) {
+                            float y[4][4];  // [op][lane of the vector]
+#pragma unroll
+                            for (int e = 0; e < 4; e++) {
+                                const int j = 4 * j4 + e;
+                                float x = sum[c * 32 + j], d;
+                                if (reread && col0 + j < N) x = zrow[j];
+                                unary_rule<float, EML_OP_NEG>(epi.c[0], x, y[0][e], d);
+                                unary_rule<float, EML_OP_EXP>(epi.c[1], y[0][e], y[1][e], d);
+                                unary_rule<float, EML_OP_ADD_C>(epi.c[2], y[1][e], y[2][e], d);
+                                unary_rule<float, EML_OP_C_DIV>(epi.c[3], y[2][e], y[3][e], d);
+                            }
+#pragma unroll
+                            for (int k = 0; k < 4; k++) {
+                                if (!epi.out[k]) continue;
+                                float* q = epi.out[k] + row * N + col0 + 4 * j4;
+                                if (ovec && col0 + 4 * j4 + 4 <= N) {
+                                    *reinterpret_cast<float4*>(q) = make_float4(y[k][0], y[k][1], y[k][2], y[k][3]);
+                                } else {
+#pragma unroll
+                                    for (int e = 0; e < 4; e++)
+                                        if (col0 + 4 * j4 + e < N) q[e] = y[k][e];
+                                }
+                            }
+                        }
+                    }
+                }
             }
         }
     }
@@ -625,12 +666,13 @@ tf32x3_pair_kernel(const __grid_constant__ Maps maps, float* __restrict__ C, int
 
 int launch(const Maps& maps, float* C, int64_t batch, int64_t M, int64_t N, int64_t ldc, int64_t strideC, int kblocks,
            int splits, int sms, int accumulate /* ACC_*; ACC_ZERO_PLUS only with ws */, float* ws, cudaStream_t stream,
-           bool upper_only = false, const RepairArgs* repair = nullptr) {
+           bool upper_only = false, const RepairArgs* repair = nullptr, const EpilogueChain* epi = nullptr) {
     static thread_local int configured_dev = -1;
     int dev = 0;
     EML_CUDA(cudaGetDevice(&dev));
     if (configured_dev != dev) {
-        EML_CUDA(cudaFuncSetAttribute(tf32x3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        EML_CUDA(cudaFuncSetAttribute(tf32x3_pair_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        EML_CUDA(cudaFuncSetAttribute(tf32x3_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
         configured_dev = dev;
     }
     const int tiles_m = (int)((M + PM - 1) / PM), tiles_n = upper_only ? 0 : (int)((N + PN - 1) / PN);
@@ -641,9 +683,14 @@ int launch(const Maps& maps, float* C, int64_t batch, int64_t M, int64_t N, int6
     if (items > 0x7fffffffLL) EML_BAD_ARG("tf32x3: too many work items");
     int clusters = sms / 2;
     if (items < clusters) clusters = (int)items;
-    launch_k(tf32x3_pair_kernel, dim3(2 * clusters), dim3(THREADS), SMEM_BYTES, stream, 
-        maps, C, M, N, ldc, strideC, kblocks, per_split, used_splits, tiles_m, tiles_n, (int)items, accumulate == ACC_ADD ? 1 : 0, ws,
-        batch * M * N, repair ? *repair : RepairArgs{});
+    if (epi)
+        launch_k(tf32x3_pair_kernel<1>, dim3(2 * clusters), dim3(THREADS), SMEM_BYTES, stream, maps, C, M, N, ldc, strideC, kblocks,
+                 per_split, used_splits, tiles_m, tiles_n, (int)items, accumulate == ACC_ADD ? 1 : 0, ws, batch * M * N,
+                 repair ? *repair : RepairArgs{}, *epi);
+    else
+        launch_k(tf32x3_pair_kernel<0>, dim3(2 * clusters), dim3(THREADS), SMEM_BYTES, stream, maps, C, M, N, ldc, strideC, kblocks,
+                 per_split, used_splits, tiles_m, tiles_n, (int)items, accumulate == ACC_ADD ? 1 : 0, ws, batch * M * N,
+                 repair ? *repair : RepairArgs{}, EpilogueChain{});
     count_launch();
     EML_TRY(check_launch("tf32x3_tcgen05 (CTA pair)"));
     if (ws) EML_TRY(launch_splitk_reduce<float>(ws, used_splits, C, batch, M, N, Strides3{strideC, ldc, 1}, accumulate, stream));
@@ -932,8 +979,18 @@ int launch_gemm_tf32x3_f32(DeviceCtx* ctx, const float* A, const float* B, float
             rep.ticket = tickets;
             repair_folded = true;
         }
+        // an elementwise chain handed over by the tape: only the launch that stores C itself, one batch, the whitelisted
+        // chain (anything else: the caller runs the group as its own kernel)
+        const EpilogueChain* epi = nullptr;
+        if (opt && opt->epilogue && !accumulate && !upper_only && !ws && batch == 1) {
+            const EpilogueChain& e = *opt->epilogue;
+            if (e.n_ops == 4 && e.op[0] == EML_OP_NEG && e.op[1] == EML_OP_EXP && e.op[2] == EML_OP_ADD_C && e.op[3] == EML_OP_C_DIV) {
+                epi = &e;
+                opt->epilogue_done = true;
+            }
+        }
         EML_TRY(pair::launch(maps, C, batch, M, N, sC.r, sC.b, kblocks, splits, sms, acc_mode, ws, stream, upper_only,
-                             repair_folded ? &rep : nullptr));
+                             repair_folded ? &rep : nullptr, epi));
         if (upper_only) opt->upper_done = true;
     } else if (BN == 256) {
         EML_TRY(launch_tile<256>(maps, C, batch, M, N, sC.r, sC.b, kblocks, splits, acc_mode, ws, stream));

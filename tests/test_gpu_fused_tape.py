@@ -268,3 +268,52 @@ def test_recorded_step_with_fused_groups_replays_bit_for_bit():
     lr, w1r, w2r = run(True)
     assert same_bits(le, lr) and same_bits(w1e, w1r) and same_bits(w2e, w2r)
     assert le[-1] < le[0]
+
+
+def _env_tape(dtype, **env):
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update({k: str(v) for k, v in env.items()})
+    try:
+        return eml.WengertList(dtype)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                del os.environ[k]
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.parametrize("special", [False, True])
+@pytest.mark.parametrize("n,i,h", [(1024, 200, 384), (520, 128, 260), (8192, 784, 512)])
+def test_activation_chain_rides_in_the_gemm_epilogue(n, i, h, special):
+    """sigmoid(X * W) at shapes the f32 CTA-pair kernel computes in one launch per tile (no split-K): the product is
+    deferred, the four-operator group that follows it goes into the GEMM's epilogue (one launch fewer) and the numbers,
+    the derivatives and every Index are those of the separate kernels (EML_EPILOGUE=0) and of one kernel per node
+    (EML_FUSE=0), bit for bit -- also where the non-finite repair rewrites elements of the product (an infinite input)."""
+    r = np.random.default_rng(21)
+    x = r.uniform(-1, 1, (n, i)).astype(np.float32)
+    w = r.uniform(-0.5, 0.5, (i, h)).astype(np.float32)
+    if special:
+        x[3, 5] = np.inf
+        x[n - 1, 0] = -np.inf
+        w[7, 9] = np.float32(3.0e38)
+
+    def program(hist):
+        before = eml.kernel_launches()
+        W = eml.RecordTensor.variables(hist, eml.Tensor([("i", i), ("h", h)], w))
+        X = eml.RecordTensor.constants(eml.Tensor([("n", n), ("i", i)], x), hist)
+        z = X * W
+        y = sigmoid(z)
+        yv = y.numbers().data.copy()
+        zv = z.numbers().data.copy()
+        launches = eml.kernel_launches() - before
+        d = y.derivatives_for([n // 2, h - 1])
+        return {"y": yv, "z": zv, "gw": d.at_tensor(W).data, "idx": y.indexes(), "len": np.array(len(hist)),
+                "launches": launches}
+
+    fused = program(_env_tape(np.float32, EML_FUSE=1, EML_EPILOGUE=1))
+    separate = program(_env_tape(np.float32, EML_FUSE=1, EML_EPILOGUE=0))
+    per_node = program(_env_tape(np.float32, EML_FUSE=0))
+    assert_same(fused, separate)
+    assert_same(fused, per_node)
+    assert fused["launches"] == separate["launches"] - 1, "the activation did not go into the GEMM epilogue"
