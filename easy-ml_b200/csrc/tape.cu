@@ -214,6 +214,7 @@ struct eml_tape {
         int64_t M = 0, N = 0, K = 0;
     } mm;
     bool defer_matmul = false;
+    bool zero_plus = true;  // EML_ZERO_PLUS=0: products accumulate into zero-filled buffers (see matmul_overwrites)
     // a small asynchronous read-back requested while updates are queued rides in their launch (SgdBatch rider)
     Buf rider_src;
     void* rider_dst = nullptr;
@@ -972,10 +973,14 @@ int sweep_scalars(eml_tape* t, eml_derivs* d, const Node& nd, int64_t self_off, 
 // Does the sweep of matmul node c WRITE (0 + sum, not +=) the derivatives of its parent `parent` when it is the first
 // to contribute to them?  True for the kernels that start their fma chain from +0 themselves: the thin (M <= 4)
 // backward, and dA = G * B^T through the short-contraction kernel.  (Such a parent needs no zero fill and is not read.)
-bool matmul_overwrites(const Node&, int, size_t) {
-    // every product of the sweep can now be the first contribution: the thin kernels and the short-contraction kernel
-    // start their fma chains from +0, the others are asked for 0 + product (GemmOptions::zero_plus)
-    return true;
+bool matmul_overwrites(const Node& c, int parent, size_t elem, bool zero_plus) {
+    // every product of the sweep can be the first contribution: the thin kernels and the short-contraction kernel start
+    // their fma chains from +0, the others are asked for 0 + product (GemmOptions::zero_plus).  EML_ZERO_PLUS=0 (the
+    // comparison path of the tests): only the former, everything else accumulates into a zero-filled buffer.
+    if (zero_plus) return true;
+    if (c.p0 == c.p1) return false;
+    if (thin_shape(c.M, c.N, c.K)) return true;
+    return parent == c.p0 && smallk_shape(c.M, c.K, c.N, elem);
 }
 
 // The reverse sweep over macro nodes.
@@ -1073,7 +1078,7 @@ int sweep_from(eml_tape* t, int nv, int64_t seed_elem, eml_derivs** out) {
             continue;
         }
         const bool overwritten_first = c >= 0 && i != nv && t->nodes[c].kind != Kind::VIEW && t->nodes[c].kind != Kind::SCALARS &&
-                                       (t->nodes[c].kind != Kind::MATMUL || matmul_overwrites(t->nodes[c], i, sizeof(T)));
+                                       (t->nodes[c].kind != Kind::MATMUL || matmul_overwrites(t->nodes[c], i, sizeof(T), t->zero_plus));
         written[i] = !overwritten_first;  // "written" = holds defined numbers (zeros) before the sweep
     }
     {   // (the slots at the head of the arena are written, not added to: no zeros needed there)
@@ -1302,6 +1307,7 @@ int eml_tape_create(int dtype, eml_tape** out) {
     t->stream = ctx->stream;
     if (const char* e = getenv("EML_FUSE")) t->fuse = !(e[0] == '0');
     if (const char* e = getenv("EML_EPILOGUE")) t->defer_matmul = e[0] == '1';
+    if (const char* e = getenv("EML_ZERO_PLUS")) t->zero_plus = !(e[0] == '0');
     const char* se = getenv("EML_SIDE");
     if (!(se && se[0] == '0')) {
         cudaError_t e = cudaEventCreateWithFlags(&t->ev_fork, cudaEventDisableTiming);

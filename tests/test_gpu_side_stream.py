@@ -230,3 +230,49 @@ def test_recorded_step_with_the_second_stream_replays_bit_for_bit():
         got = run(recorded, side)
         for a, b in zip(base, got):
             assert same_bits(a, b), f"recorded={recorded} side={side}"
+
+
+def tape_env(dtype, **env):
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update({k: str(v) for k, v in env.items()})
+    try:
+        return eml.WengertList(dtype)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                del os.environ[k]
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("n,i,h,o", [
+    (96, 40, 24, 10),        # FMA kernels, thin and short-contraction products
+    (520, 300, 260, 12),     # tensor-core products with split-K (f32) / DMMA (f64), tall-skinny A^T B
+    (1024, 2048, 2048, 300), # f32: the in-kernel-split GEMM and the CTA-pair kernel without split-K
+])
+def test_first_contributions_of_products_need_no_zero_fill(dtype, n, i, h, o):
+    """vec![0; len] (reference src/differentiation.rs:627) is not materialised for buffers a product reaches first: the
+    product is asked for 0 + sum (GemmOptions::zero_plus).  Compared bit for bit -- signs of zero included: X has an
+    all-zero column, so a whole row of dW1 is a sum of signed zeros -- with accumulation into zero-filled buffers
+    (EML_ZERO_PLUS=0)."""
+    r = np.random.default_rng(17)
+    x = r.uniform(-1, 1, (n, i)).astype(dtype)
+    x[:, 3] = 0.0
+    w1 = r.uniform(-0.05, 0.05, (i, h)).astype(dtype)
+    w2 = r.uniform(-0.05, 0.05, (h, o)).astype(dtype)
+
+    def program(hist):
+        W1 = eml.RecordTensor.variables(hist, T("ih", w1))
+        W2 = eml.RecordTensor.variables(hist, T("ho", w2))
+        X = eml.RecordTensor.variables(hist, T("ni", x))
+        y = sigmoid(X * W1) * W2
+        out = y.elementwise_multiply(y) - y
+        d = out.derivatives_for([n - 1, o // 2])
+        return {"g1": d.at_tensor(W1).data, "g2": d.at_tensor(W2).data, "gx": d.at_tensor(X).data}
+
+    a = program(tape_env(dtype, EML_ZERO_PLUS=1))
+    b = program(tape_env(dtype, EML_ZERO_PLUS=0))
+    for k in a:
+        assert same_bits(a[k], b[k]), f"{k}: 0 + product differs from accumulating into zeros"
+    assert not np.signbit(a["g1"][3]).any()  # sums of signed zeros added to +0 are +0
