@@ -371,11 +371,15 @@ constexpr int THREADS = (4 + EPI_WARPS) * 32;  // warpgroup 0: producer, MMA iss
 constexpr int CONTROL_REGS = 40, EPILOGUE_REGS = 232;
 // The tensor core adds into its f32 accumulator with truncation (round toward zero): over a long chain of
 // same-sign products the bias grows with the number of MMAs (measured: 5e-4 relative at K = 65536).  So an
-// accumulator is only trusted for FLUSH_KB k blocks (512 k = 192 MMAs, bias < 3e-6 of sum|a b|); then the MMA
-// warp moves to the other TMEM stage and the epilogue warps add the drained partial into a running f32 sum
-// held in REGISTERS (128 columns of one row per thread) with IEEE round-to-nearest adds, under the next
-// chunk's MMAs; C is written once per tile.
-constexpr int FLUSH_KB = 16;
+// accumulator is only trusted for FLUSH_KB k blocks; then the MMA warp moves to the other TMEM stage and the epilogue
+// warps add the drained partial into a running f32 sum held in REGISTERS (128 columns of one row per thread) with
+// IEEE round-to-nearest adds, under the next chunk's MMAs; C is written once per tile.
+// Measured bias on all-positive data (scripts/err_probe.py), relative to the exact result: with the truncating big /
+// small split of tf32_split.cuh -- every one of the three product terms has the sign of a b, so nothing cancels --
+// 2.2e-6 per 128 k of chain; 8 k blocks = 256 k keep it at 4.4e-6 (max 5.8e-6 over a 2048^3 product), inside the
+// 1e-5 sum|a b| contract with room for the split's own 1.9e-6.  (Round 1 split by rounding, which halves the bias
+// per k, and flushed every 16 k blocks: the same figures.)
+constexpr int FLUSH_KB = 8;
 
 struct Work {
     int tm, tn, batch, split;
@@ -885,7 +889,7 @@ int launch_gemm_tf32x3_f32(DeviceCtx* ctx, const float* A, const float* B, float
             if (splits > kblocks / 4) splits = kblocks / 4;
             if (splits < 1) splits = 1;
         }
-        // bound the truncating TMEM accumulation chain (see pair::FLUSH_KB): at most 16 k blocks per split
+        // bound the truncating TMEM accumulation chain (see pair::FLUSH_KB): at most 8 k blocks per split
         const int min_splits = (kblocks + pair::FLUSH_KB - 1) / pair::FLUSH_KB;
         if (splits < min_splits) splits = min_splits;
         Mp = round_up(M, BM);

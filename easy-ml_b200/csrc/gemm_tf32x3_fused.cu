@@ -1,24 +1,30 @@
 // gemm_tf32x3_fused.cu -- 3xTF32 f32 GEMM with the big/small split done INSIDE the kernel (no split/pack pass).
 //
 // The split/pack pass of gemm_tf32x3.cu is HBM-bound; it costs 6 % at K = 8192 but a third of the time at K = 1024
-// (BASELINE config 3: batch 64, 1024^3).  Here the raw f32 operand tiles are brought in by TMA, fourteen
-// warps split them in shared memory into the big / small TF32 tiles (K-major, 128-byte swizzled: exactly what TMA
-// with SWIZZLE_128B would have written from packed planes) and the same tcgen05.mma.cta_group::2 pipeline consumes
-// them.  Shared-memory traffic per 32-wide k block and SM rises from 160 KB (packed planes in by TMA, MMA operand
-// reads) to 224 KB (raw in by TMA, raw read, big/small written, MMA reads): 1792 cycles of the 128 B/clk shared
-// memory pipe against 1536 cycles of MMA issue, so the tensor pipe cannot exceed 86 % here (measured 75 %, with the
-// shared-memory pipe 87 % busy).  That is why the dispatcher only uses this kernel where not running the pack pass
-// buys more than the slower main loop costs (small outputs), and keeps the packed path elsewhere.
+// (BASELINE config 3: batch 64, 1024^3).  Here TMA brings in the RAW f32 operand tiles and the tensor core reads them
+// as they are: tcgen05.mma.kind::tf32 ignores the low 13 mantissa bits of an operand word, i.e. it sees
+// big = trunc_tf32(x) (tf32_split.cuh; measured, scripts/probe/tf32_operand_probe.cu).  Fourteen warps only compute the
+// SMALL tiles, small = rna(x - big), elementwise and layout preserving, and the same tcgen05.mma.cta_group::2 pipeline
+// forms As Bb + Ab Bs + Ab Bb with Ab, Bb read from the raw tiles.
 //
-// Per CTA of a pair:    warp 0      one lane issues the TMA loads of the raw tiles (3-stage ring)
+// Operand layouts in shared memory (both understood by TMA and by the MMA's shared-memory descriptors):
+//   k index contiguous in memory ("K-major"):  [128 rows][32 k], 128-byte rows, SWIZZLE_128B; one TMA box (32 k, 128 rows)
+//   m / n index contiguous ("MN-major"):       [4 groups][32 k][32 rows], 128-byte rows of 32 consecutive m / n,
+//       CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B <-> UMMA layout type 1 (SWIZZLE_128B_BASE32B: 32-byte units XOR (k & 3),
+//       groups of 4 k at SBO = 512 B, the next 32 rows at LBO = 4096 B) -- the only MN-major form kind::tf32 accepts
+//       (the probe: every other layout type reads zeros); four TMA boxes (32 rows, 32 k) per tile.
+//   So an n-contiguous B (the ordinary row-major right operand) needs no transposing conversion any more.
+//
+// Shared-memory pipe per 32-wide k block and SM: 32 KB of raw tiles written by TMA + 32 KB read by the converters +
+// 32 KB of small tiles written + 96 KB read by the MMAs = 192 KB = 1536 cycles of the 128 B/clk pipe -- the same as the
+// 1536 cycles of MMA issue (round 1's version wrote big tiles too: 224 KB = 1792 cycles, tensor pipe 66 % active).
+//
+// Per CTA of a pair:    warp 0      one lane issues the TMA loads of the raw tiles (3-stage ring; a stage holds the raw
+//                                   A and B tiles and their small tiles, and is freed by the commit of its MMAs)
 //                       warp 1      TMEM allocation; leader CTA: one lane issues the MMAs (M=256, N=256, K=8)
 //                       warps 2,3,12..15   converters
 //                       warps 4..11 converters too, and the epilogue: between two conversions they drain a finished
 //                                   512-k accumulator chunk into a register-resident running sum (see gemm_tf32x3.cu)
-// Raw tile of an operand whose k index is contiguous in memory: TMA box (32 k, 128 rows), SWIZZLE_128B -- the
-// converter is a layout-preserving elementwise pass.  Otherwise (m / n contiguous): box (128 rows, 32 k), no swizzle,
-// i.e. [k][row] in shared memory; a converter lane owns one row, gathers four consecutive k and writes one 16-byte
-// chunk at the swizzled position (conflict free on both sides).
 // Ragged M, N, K need no padding: TMA zero-fills out-of-range box elements.
 #include <cstdlib>
 #include <string>
@@ -37,15 +43,14 @@ namespace fz {
 
 constexpr int PM = 256, PN = 256, HALF = 128, BK = 32;
 constexpr int TILE_BYTES = HALF * BK * 4;        // 16 KB
-constexpr int RAW_STAGE_BYTES = 2 * TILE_BYTES;  // A raw, B raw
-constexpr int OP_STAGE_BYTES = 4 * TILE_BYTES;   // A big, A small, B big, B small
-constexpr int RAW_STAGES = 3, OP_STAGES = 2, ACC_STAGES = 2;
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;      // A raw, B raw, A small, B small
+constexpr int STAGES = 3, ACC_STAGES = 2;
 constexpr uint32_t TMEM_COLS = 512;
-constexpr size_t SMEM_BYTES =
-    (size_t)RAW_STAGES * RAW_STAGE_BYTES + (size_t)OP_STAGES * OP_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int CONV_WARPS = 14, EPI_WARPS = 8, THREADS = 16 * 32;
 constexpr int LIGHT_REGS = 64, EPILOGUE_REGS = 192;  // 256 light + 256 epilogue threads: 65536 registers
-constexpr int FLUSH_KB = 16;
+constexpr int FLUSH_KB = 8;  // as in gemm_tf32x3.cu (pair::FLUSH_KB): the two kernels must chunk alike to give the same bits
+constexpr int GROUP_BYTES = 32 * BK * 4;         // MN-major: one group of 32 rows x 32 k = 4 KB
 
 struct Maps {
     CUtensorMap a, b;
@@ -71,13 +76,30 @@ __device__ __forceinline__ Work decode(int w, int tiles_m, int tiles_n, int spli
     return k;
 }
 
-// One k block: the raw A and B tiles -> big / small tiles.  64 warp tasks (a task = 32 lanes x 16 bytes of one
-// tile); converter warp `cw` takes tasks cw, cw + CONV_WARPS, ...  The loads of a group of tasks are issued before
-// the first split so that their latencies overlap.
+// MN-major operand, 128-byte swizzle with 32-byte atoms (UMMA layout type 1), see the header of this file
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128_base32(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(GROUP_BYTES >> 4) << 16;  // LBO: the next 32 rows
+    d |= (uint64_t)(512 >> 4) << 32;          // SBO: the next 4 k
+    d |= (uint64_t)1 << 46;                   // descriptor version (Blackwell)
+    d |= (uint64_t)1 << 61;                   // layout type 1: SWIZZLE_128B_BASE32B
+    return d;
+}
+// descriptor of k step `ks` (8 k) of a tile: K-major +32 bytes inside the 128-byte rows, MN-major +8 rows of 128 bytes
+template <bool KIN>
+__device__ __forceinline__ uint64_t tile_desc(uint32_t tile_addr, int ks) {
+    if (KIN) return umma_desc_k_sw128(tile_addr) + 2 * ks;
+    return umma_desc_mn_sw128_base32(tile_addr + ks * 1024);
+}
+
+// One k block: the raw A and B tiles -> their small tiles, elementwise and layout preserving (whatever the layout).
+// 64 warp tasks (a task = 32 lanes x 16 bytes of one tile); converter warp `cw` takes tasks cw, cw + CONV_WARPS, ...
+// The loads of a group of tasks are issued before the first split so that their latencies overlap.
+// A vector holding an Inf / NaN / >= 2^127 value (rare) also rewrites its raw words with the big parts of
+// tf32::split_special, so that the packed path and this one feed the tensor core the same numbers.
 constexpr int TASKS = 64, MAX_TASKS = (TASKS + CONV_WARPS - 1) / CONV_WARPS, GROUP_TASKS = 3;
-template <bool A_KIN, bool B_KIN>
-__device__ __forceinline__ void convert_block(const uint8_t* __restrict__ raw, uint8_t* __restrict__ op, int cw,
-                                              int lane, unsigned* nonfinite) {
+__device__ __forceinline__ void convert_block(uint8_t* __restrict__ stage, int cw, int lane, unsigned* nonfinite) {
 #pragma unroll
     for (int g = 0; g < MAX_TASKS; g += GROUP_TASKS) {
         float4 v[GROUP_TASKS];
@@ -85,20 +107,7 @@ __device__ __forceinline__ void convert_block(const uint8_t* __restrict__ raw, u
         for (int i = 0; i < GROUP_TASKS; i++) {
             const int t = cw + CONV_WARPS * (g + i);
             if (g + i >= MAX_TASKS || t >= TASKS) continue;
-            const bool is_b = t >= 32;
-            const bool kin = is_b ? B_KIN : A_KIN;
-            const int tt = t & 31;
-            const uint8_t* src = raw + (is_b ? TILE_BYTES : 0);
-            if (kin) {
-                // the tile is already [row][32 k] 128-byte swizzled: elementwise, layout preserving
-                v[i] = *reinterpret_cast<const float4*>(src + (tt * 32 + lane) * 16);
-            } else {
-                // the tile is [32 k][128 rows]; a lane owns row 32*(tt/8) + lane and gathers k = 4*k4 .. 4*k4+3
-                const float* rf = reinterpret_cast<const float*>(src);
-                const int row = (tt >> 3) * 32 + lane, k4 = tt & 7;
-                v[i] = make_float4(rf[(4 * k4 + 0) * HALF + row], rf[(4 * k4 + 1) * HALF + row],
-                                   rf[(4 * k4 + 2) * HALF + row], rf[(4 * k4 + 3) * HALF + row]);
-            }
+            v[i] = *reinterpret_cast<const float4*>(stage + (t >> 5) * TILE_BYTES + ((t & 31) * 32 + lane) * 16);
         }
         // one test for the whole group: the common path below it is branch free, so the group's twelve
         // independent split chains interleave (a per-vector branch serialised them: measured 0.15 IPC per warp)
@@ -114,24 +123,15 @@ __device__ __forceinline__ void convert_block(const uint8_t* __restrict__ raw, u
         for (int i = 0; i < GROUP_TASKS; i++) {
             const int t = cw + CONV_WARPS * (g + i);
             if (g + i >= MAX_TASKS || t >= TASKS) continue;
-            const bool is_b = t >= 32;
-            const bool kin = is_b ? B_KIN : A_KIN;
-            const int tt = t & 31;
+            const int off = (t >> 5) * TILE_BYTES + ((t & 31) * 32 + lane) * 16;
             float4 hi, lo;
-            if (ordinary)
+            if (ordinary) {
                 tf32::split4_ordinary(v[i], hi, lo);
-            else
-                tf32::split4_any(v[i], hi, lo);
-            int off;
-            if (kin) {
-                off = (tt * 32 + lane) * 16;
             } else {
-                const int row = (tt >> 3) * 32 + lane, k4 = tt & 7;
-                off = row * 128 + ((k4 ^ (row & 7)) << 4);  // SWIZZLE_128B position of chunk k4 of this row
+                tf32::split4_any(v[i], hi, lo);
+                *reinterpret_cast<float4*>(stage + off) = hi;
             }
-            uint8_t* dst = op + (is_b ? 2 * TILE_BYTES : 0);  // A big, A small, B big, B small
-            *reinterpret_cast<float4*>(dst + off) = hi;
-            *reinterpret_cast<float4*>(dst + TILE_BYTES + off) = lo;
+            *reinterpret_cast<float4*>(stage + 2 * TILE_BYTES + off) = lo;
         }
     }
 }
@@ -144,13 +144,11 @@ tf32x3_fused_kernel(const __grid_constant__ Maps maps, float* __restrict__ C, in
     pdl_prologue();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t* raw_ring = base;
-    uint8_t* op_ring = base + (size_t)RAW_STAGES * RAW_STAGE_BYTES;
-    uint64_t* raw_full = reinterpret_cast<uint64_t*>(op_ring + (size_t)OP_STAGES * OP_STAGE_BYTES);
-    uint64_t* raw_empty = raw_full + RAW_STAGES;
-    uint64_t* op_full = raw_empty + RAW_STAGES;
-    uint64_t* op_empty = op_full + OP_STAGES;
-    uint64_t* acc_full = op_empty + OP_STAGES;
+    uint8_t* ring = base;
+    uint64_t* raw_full = reinterpret_cast<uint64_t*>(ring + (size_t)STAGES * STAGE_BYTES);
+    uint64_t* conv_full = raw_full + STAGES;
+    uint64_t* empty = conv_full + STAGES;
+    uint64_t* acc_full = empty + STAGES;
     uint64_t* acc_empty = acc_full + ACC_STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + ACC_STAGES);
 
@@ -161,13 +159,10 @@ tf32x3_fused_kernel(const __grid_constant__ Maps maps, float* __restrict__ C, in
     if (threadIdx.x == 0) {
         prefetch_tensormap(&maps.a);
         prefetch_tensormap(&maps.b);
-        for (int s = 0; s < RAW_STAGES; s++) {
-            mbar_init(&raw_full[s], 1);
-            mbar_init(&raw_empty[s], CONV_WARPS);
-        }
-        for (int s = 0; s < OP_STAGES; s++) {
-            mbar_init(&op_full[s], 2 * CONV_WARPS);  // leader's copy: every converter warp of both CTAs
-            mbar_init(&op_empty[s], 1);
+        for (int s = 0; s < STAGES; s++) {
+            mbar_init(&raw_full[s], 1);                // this CTA's producer arrives, this CTA's bytes land
+            mbar_init(&conv_full[s], 2 * CONV_WARPS);  // leader's copy: every converter warp of both CTAs
+            mbar_init(&empty[s], 1);                   // one multicast commit per use
         }
         for (int a = 0; a < ACC_STAGES; a++) {
             mbar_init(&acc_full[a], 1);
@@ -188,7 +183,7 @@ tf32x3_fused_kernel(const __grid_constant__ Maps maps, float* __restrict__ C, in
     if (warp == 1) {
         // ---------------- MMA issuer (leader CTA only) ----------------
         if (rank == 0 && lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_tf32(PM, PN);
+            constexpr uint32_t idesc = umma_idesc_tf32(PM, PN) | (A_KIN ? 0u : 1u << 15) | (B_KIN ? 0u : 1u << 16);
             int n = 0, it = 0;
             for (int w = cluster; w < work_items; w += clusters) {
                 const Work wk = decode(w, tiles_m, tiles_n, splits);
@@ -200,22 +195,23 @@ tf32x3_fused_kernel(const __grid_constant__ Maps maps, float* __restrict__ C, in
                     tc_fence_after();
                     const uint32_t d = tmem_acc + (uint32_t)as * PN;
                     for (int kb = c0; kb < c1; kb++, n++) {
-                        const int s = n % OP_STAGES;
-                        mbar_wait(&op_full[s], (n / OP_STAGES) & 1);
+                        const int s = n % STAGES;
+                        mbar_wait(&conv_full[s], (n / STAGES) & 1);
                         tc_fence_after();
-                        const uint32_t st = smem_u32(op_ring + (size_t)s * OP_STAGE_BYTES);
-                        const uint64_t a_big = umma_desc_k_sw128(st), a_small = umma_desc_k_sw128(st + TILE_BYTES);
-                        const uint64_t b_big = umma_desc_k_sw128(st + 2 * TILE_BYTES);
-                        const uint64_t b_small = umma_desc_k_sw128(st + 3 * TILE_BYTES);
+                        const uint32_t st = smem_u32(ring + (size_t)s * STAGE_BYTES);
+                        const uint32_t a_big = st, b_big = st + TILE_BYTES, a_small = st + 2 * TILE_BYTES,
+                                       b_small = st + 3 * TILE_BYTES;
                         const uint32_t first = kb != c0;
 #pragma unroll
                         for (int k = 0; k < BK / 8; k++)
-                            umma_tf32_pair(d, a_small + 2 * k, b_big + 2 * k, idesc, first | (uint32_t)k);
+                            umma_tf32_pair(d, tile_desc<A_KIN>(a_small, k), tile_desc<B_KIN>(b_big, k), idesc, first | (uint32_t)k);
 #pragma unroll
-                        for (int k = 0; k < BK / 8; k++) umma_tf32_pair(d, a_big + 2 * k, b_small + 2 * k, idesc, 1);
+                        for (int k = 0; k < BK / 8; k++)
+                            umma_tf32_pair(d, tile_desc<A_KIN>(a_big, k), tile_desc<B_KIN>(b_small, k), idesc, 1);
 #pragma unroll
-                        for (int k = 0; k < BK / 8; k++) umma_tf32_pair(d, a_big + 2 * k, b_big + 2 * k, idesc, 1);
-                        umma_commit_pair(&op_empty[s], 0b11);
+                        for (int k = 0; k < BK / 8; k++)
+                            umma_tf32_pair(d, tile_desc<A_KIN>(a_big, k), tile_desc<B_KIN>(b_big, k), idesc, 1);
+                        umma_commit_pair(&empty[s], 0b11);  // frees the stage (raw and small tiles) in both CTAs
                     }
                     umma_commit_pair(&acc_full[as], 0b11);
                 }
@@ -230,44 +226,44 @@ tf32x3_fused_kernel(const __grid_constant__ Maps maps, float* __restrict__ C, in
                 const int kb0 = wk.split * per_split, kb1 = min(kblocks_total, kb0 + per_split);
                 const int row_a = wk.tm * PM + (int)rank * HALF, row_b = wk.tn * PN + (int)rank * HALF;
                 for (int kb = kb0; kb < kb1; kb++, n++) {
-                    const int s = n % RAW_STAGES;
-                    if (n >= RAW_STAGES) mbar_wait(&raw_empty[s], ((n / RAW_STAGES) - 1) & 1);
-                    uint8_t* st = raw_ring + (size_t)s * RAW_STAGE_BYTES;
-                    mbar_expect_tx(&raw_full[s], RAW_STAGE_BYTES);
+                    const int s = n % STAGES;
+                    if (n >= STAGES) mbar_wait(&empty[s], ((n / STAGES) - 1) & 1);
+                    uint8_t* st = ring + (size_t)s * STAGE_BYTES;
+                    mbar_expect_tx(&raw_full[s], 2 * TILE_BYTES);
                     const int kc = kb * BK;
-                    if (A_KIN)
+                    if (A_KIN) {
                         tma_load_3d(st, &maps.a, &raw_full[s], kc, row_a, wk.batch);
-                    else
-                        tma_load_3d(st, &maps.a, &raw_full[s], row_a, kc, wk.batch);
-                    if (B_KIN)
+                    } else {
+#pragma unroll
+                        for (int g = 0; g < 4; g++) tma_load_3d(st + g * GROUP_BYTES, &maps.a, &raw_full[s], row_a + 32 * g, kc, wk.batch);
+                    }
+                    if (B_KIN) {
                         tma_load_3d(st + TILE_BYTES, &maps.b, &raw_full[s], kc, row_b, wk.batch);
-                    else
-                        tma_load_3d(st + TILE_BYTES, &maps.b, &raw_full[s], row_b, kc, wk.batch);
+                    } else {
+#pragma unroll
+                        for (int g = 0; g < 4; g++)
+                            tma_load_3d(st + TILE_BYTES + g * GROUP_BYTES, &maps.b, &raw_full[s], row_b + 32 * g, kc, wk.batch);
+                    }
                 }
             }
         }
     } else {
-        // ---------------- converters: raw ring -> big / small operand ring ----------------
+        // ---------------- converters: small tiles of the stage the TMA has just filled ----------------
         // warps 2, 3, 12..15 do nothing else; the epilogue warps 4..11 convert too and drain an accumulator
-        // chunk two k blocks after its last block was converted (its MMAs have completed by then: the operand
-        // ring is two stages deep, so the conversion of block n + 2 waits for the MMAs of block n anyway)
+        // chunk two k blocks after its last block was converted (its MMAs have completed by then: the conversion of
+        // block n + 3 waits for the MMAs of block n anyway, through the producer's wait on the stage)
         int total = 0;  // k blocks this cluster processes, over all its work items
         for (int w = cluster; w < work_items; w += clusters) {
             const int kb0 = (w % splits) * per_split;
             total += min(kblocks_total, kb0 + per_split) - kb0;
         }
         auto convert_step = [&](int n, int cw) {
-            const int rs = n % RAW_STAGES, os = n % OP_STAGES;
-            mbar_wait(&raw_full[rs], (n / RAW_STAGES) & 1);
-            if (n >= OP_STAGES) mbar_wait(&op_empty[os], ((n / OP_STAGES) - 1) & 1);
-            convert_block<A_KIN, B_KIN>(raw_ring + (size_t)rs * RAW_STAGE_BYTES, op_ring + (size_t)os * OP_STAGE_BYTES,
-                                        cw, lane, nonfinite);
+            const int s = n % STAGES;
+            mbar_wait(&raw_full[s], (n / STAGES) & 1);
+            convert_block(ring + (size_t)s * STAGE_BYTES, cw, lane, nonfinite);
             fence_proxy_async();  // this lane's tile writes become visible to the tensor core (async proxy)
             __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(&raw_empty[rs]);
-                mbar_arrive_cluster(&op_full[os], 0);
-            }
+            if (lane == 0) mbar_arrive_cluster(&conv_full[s], 0);
         };
         if (!is_epilogue) {
             const int cw = warp < 4 ? warp - 2 : warp - 10;  // 0..5
@@ -372,7 +368,8 @@ tf32x3_fused_kernel(const __grid_constant__ Maps maps, float* __restrict__ C, in
     if (warp == 1) tmem_dealloc_pair(tmem_acc, TMEM_COLS);
 }
 
-// raw operand tensor map.  KIN: element (row, k) at base[b*sb + row*ld + k]; else at base[b*sb + k*ld + row]
+// raw operand tensor map.  KIN: element (row, k) at base[b*sb + row*ld + k], box (32 k, 128 rows), SWIZZLE_128B;
+// else at base[b*sb + k*ld + row], box (32 rows, 32 k), 128-byte swizzle with 32-byte atoms (see the header)
 int raw_map(CUtensorMap* map, const float* base, bool kin, int64_t rows, int64_t K, int64_t ld, int64_t batch,
             int64_t sb) {
     uint64_t dims[3], strides[2];
@@ -382,14 +379,14 @@ int raw_map(CUtensorMap* map, const float* base, bool kin, int64_t rows, int64_t
         box[0] = BK; box[1] = HALF;
     } else {
         dims[0] = (uint64_t)rows; dims[1] = (uint64_t)K;
-        box[0] = HALF; box[1] = BK;
+        box[0] = 32; box[1] = BK;
     }
     dims[2] = (uint64_t)batch;
     box[2] = 1;
     strides[0] = (uint64_t)ld * 4;
     strides[1] = (uint64_t)(batch > 1 ? sb : 4) * 4;
     return make_tensor_map(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box,
-                           kin ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE);
+                           kin ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
 }
 
 template <bool A_KIN, bool B_KIN>
