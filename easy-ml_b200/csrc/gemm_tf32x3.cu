@@ -360,6 +360,7 @@ constexpr int PM = 256, PN = 256;           // tile of one CTA pair
 constexpr int HALF = 128;                   // rows of A / columns of B staged by one CTA
 constexpr int TILE_BYTES = HALF * BK * 4;   // 16 KB
 constexpr int STAGE_BYTES = 4 * TILE_BYTES; // A big, A small, B big, B small: 64 KB
+constexpr int GROUP_BYTES = 32 * BK * 4;    // MN-major tile: one group of 32 rows x 32 k
 constexpr int STAGES = 3;
 constexpr int ACC_STAGES = 2;
 constexpr uint32_t TMEM_COLS = 512;         // 2 accumulator stages x 256 columns
@@ -434,7 +435,10 @@ __device__ __forceinline__ Work decode(int w, int tiles_m, int tiles_n, int spli
 }
 
 // EPI: 0 = plain; 1 = the sigmoid chain (neg, exp, + c, c / x) applied to the finished tile in the epilogue (EpilogueChain)
-template <int EPI>
+// A_KIN / B_KIN: the operand's tiles are K-major ([128 rows][32 k], SWIZZLE_128B: packed planes, or a k-contiguous
+// matrix read in place) or MN-major ([4 groups][32 k][32 rows], 128-byte swizzle with 32-byte atoms: an m / n-contiguous
+// matrix read in place -- see sm100.cuh).  "big" may be the RAW f32 matrix: kind::tf32 truncates the low 13 bits itself.
+template <int EPI, bool A_KIN, bool B_KIN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 tf32x3_pair_kernel(const __grid_constant__ Maps maps, float* __restrict__ C, int64_t M, int64_t N, int64_t ldc,
                    int64_t strideC, int kblocks_total, int kblocks_per_split, int splits, int tiles_m, int tiles_n,
@@ -497,17 +501,33 @@ tf32x3_pair_kernel(const __grid_constant__ Maps maps, float* __restrict__ C, int
                     uint8_t* st = base + (size_t)s * STAGE_BYTES;
                     if (rank == 0) mbar_expect_tx(&full[s], 2 * STAGE_BYTES);
                     const int kc = kb * BK;
-                    tma_load_3d_pair(st, &maps.a_big, &full[s], kc, row_a, wk.batch);
-                    tma_load_3d_pair(st + TILE_BYTES, &maps.a_small, &full[s], kc, row_a, wk.batch);
-                    tma_load_3d_pair(st + 2 * TILE_BYTES, &maps.b_big, &full[s], kc, row_b, wk.batch);
-                    tma_load_3d_pair(st + 3 * TILE_BYTES, &maps.b_small, &full[s], kc, row_b, wk.batch);
+                    if (A_KIN) {
+                        tma_load_3d_pair(st, &maps.a_big, &full[s], kc, row_a, wk.batch);
+                        tma_load_3d_pair(st + TILE_BYTES, &maps.a_small, &full[s], kc, row_a, wk.batch);
+                    } else {
+#pragma unroll
+                        for (int g = 0; g < 4; g++) {
+                            tma_load_3d_pair(st + g * GROUP_BYTES, &maps.a_big, &full[s], row_a + 32 * g, kc, wk.batch);
+                            tma_load_3d_pair(st + TILE_BYTES + g * GROUP_BYTES, &maps.a_small, &full[s], row_a + 32 * g, kc, wk.batch);
+                        }
+                    }
+                    if (B_KIN) {
+                        tma_load_3d_pair(st + 2 * TILE_BYTES, &maps.b_big, &full[s], kc, row_b, wk.batch);
+                        tma_load_3d_pair(st + 3 * TILE_BYTES, &maps.b_small, &full[s], kc, row_b, wk.batch);
+                    } else {
+#pragma unroll
+                        for (int g = 0; g < 4; g++) {
+                            tma_load_3d_pair(st + 2 * TILE_BYTES + g * GROUP_BYTES, &maps.b_big, &full[s], row_b + 32 * g, kc, wk.batch);
+                            tma_load_3d_pair(st + 3 * TILE_BYTES + g * GROUP_BYTES, &maps.b_small, &full[s], row_b + 32 * g, kc, wk.batch);
+                        }
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         // ---------------- MMA issuer (leader CTA only) ----------------
         if (rank == 0 && lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_tf32(PM, PN);
+            constexpr uint32_t idesc = umma_idesc_tf32(PM, PN) | (A_KIN ? 0u : UMMA_IDESC_A_MN) | (B_KIN ? 0u : UMMA_IDESC_B_MN);
             int n = 0, it = 0;  // it counts accumulator uses (one per k chunk)
             for (int w = cluster; w < work_items; w += clusters) {
                 const Work wk = decode(w, tiles_m, tiles_n, splits);
@@ -524,17 +544,18 @@ tf32x3_pair_kernel(const __grid_constant__ Maps maps, float* __restrict__ C, int
                         mbar_wait(&full[s], (n / STAGES) & 1);
                         tc_fence_after();
                         const uint32_t st = smem_u32(base + (size_t)s * STAGE_BYTES);
-                        const uint64_t a_big = umma_desc_k_sw128(st), a_small = umma_desc_k_sw128(st + TILE_BYTES);
-                        const uint64_t b_big = umma_desc_k_sw128(st + 2 * TILE_BYTES);
-                        const uint64_t b_small = umma_desc_k_sw128(st + 3 * TILE_BYTES);
+                        const uint32_t a_big = st, a_small = st + TILE_BYTES, b_big = st + 2 * TILE_BYTES, b_small = st + 3 * TILE_BYTES;
                         const uint32_t first = kb != c0;
 #pragma unroll
                         for (int k = 0; k < BK / 8; k++)
-                            umma_tf32_pair(d, a_small + 2 * k, b_big + 2 * k, idesc, first | (uint32_t)k);
+                            umma_tf32_pair(d, umma_tile_desc_f32<A_KIN>(a_small, k), umma_tile_desc_f32<B_KIN>(b_big, k), idesc,
+                                           first | (uint32_t)k);
 #pragma unroll
-                        for (int k = 0; k < BK / 8; k++) umma_tf32_pair(d, a_big + 2 * k, b_small + 2 * k, idesc, 1);
+                        for (int k = 0; k < BK / 8; k++)
+                            umma_tf32_pair(d, umma_tile_desc_f32<A_KIN>(a_big, k), umma_tile_desc_f32<B_KIN>(b_small, k), idesc, 1);
 #pragma unroll
-                        for (int k = 0; k < BK / 8; k++) umma_tf32_pair(d, a_big + 2 * k, b_big + 2 * k, idesc, 1);
+                        for (int k = 0; k < BK / 8; k++)
+                            umma_tf32_pair(d, umma_tile_desc_f32<A_KIN>(a_big, k), umma_tile_desc_f32<B_KIN>(b_big, k), idesc, 1);
                         umma_commit_pair(&empty[s], 0b11);  // frees the stage in both CTAs
                     }
                     umma_commit_pair(&acc_full[as], 0b11);  // this chunk's partial is complete: wake both epilogues
@@ -670,13 +691,23 @@ tf32x3_pair_kernel(const __grid_constant__ Maps maps, float* __restrict__ C, int
 
 int launch(const Maps& maps, float* C, int64_t batch, int64_t M, int64_t N, int64_t ldc, int64_t strideC, int kblocks,
            int splits, int sms, int accumulate /* ACC_*; ACC_ZERO_PLUS only with ws */, float* ws, cudaStream_t stream,
-           bool upper_only = false, const RepairArgs* repair = nullptr, const EpilogueChain* epi = nullptr) {
+           bool upper_only = false, const RepairArgs* repair = nullptr, const EpilogueChain* epi = nullptr, bool a_kin = true,
+           bool b_kin = true) {
     static thread_local int configured_dev = -1;
     int dev = 0;
     EML_CUDA(cudaGetDevice(&dev));
+    using Kernel = void (*)(const Maps, float*, int64_t, int64_t, int64_t, int64_t, int, int, int, int, int, int, int, float*, int64_t,
+                            const RepairArgs, const EpilogueChain);
+    static const Kernel kernels[2][2][2] = {
+        {{tf32x3_pair_kernel<0, false, false>, tf32x3_pair_kernel<0, false, true>},
+         {tf32x3_pair_kernel<0, true, false>, tf32x3_pair_kernel<0, true, true>}},
+        {{tf32x3_pair_kernel<1, false, false>, tf32x3_pair_kernel<1, false, true>},
+         {tf32x3_pair_kernel<1, true, false>, tf32x3_pair_kernel<1, true, true>}}};
     if (configured_dev != dev) {
-        EML_CUDA(cudaFuncSetAttribute(tf32x3_pair_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-        EML_CUDA(cudaFuncSetAttribute(tf32x3_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        for (int e = 0; e < 2; e++)
+            for (int a = 0; a < 2; a++)
+                for (int b = 0; b < 2; b++)
+                    EML_CUDA(cudaFuncSetAttribute(kernels[e][a][b], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
         configured_dev = dev;
     }
     const int tiles_m = (int)((M + PM - 1) / PM), tiles_n = upper_only ? 0 : (int)((N + PN - 1) / PN);
@@ -687,14 +718,9 @@ int launch(const Maps& maps, float* C, int64_t batch, int64_t M, int64_t N, int6
     if (items > 0x7fffffffLL) EML_BAD_ARG("tf32x3: too many work items");
     int clusters = sms / 2;
     if (items < clusters) clusters = (int)items;
-    if (epi)
-        launch_k(tf32x3_pair_kernel<1>, dim3(2 * clusters), dim3(THREADS), SMEM_BYTES, stream, maps, C, M, N, ldc, strideC, kblocks,
-                 per_split, used_splits, tiles_m, tiles_n, (int)items, accumulate == ACC_ADD ? 1 : 0, ws, batch * M * N,
-                 repair ? *repair : RepairArgs{}, *epi);
-    else
-        launch_k(tf32x3_pair_kernel<0>, dim3(2 * clusters), dim3(THREADS), SMEM_BYTES, stream, maps, C, M, N, ldc, strideC, kblocks,
-                 per_split, used_splits, tiles_m, tiles_n, (int)items, accumulate == ACC_ADD ? 1 : 0, ws, batch * M * N,
-                 repair ? *repair : RepairArgs{}, EpilogueChain{});
+    launch_k(kernels[epi ? 1 : 0][a_kin ? 1 : 0][b_kin ? 1 : 0], dim3(2 * clusters), dim3(THREADS), SMEM_BYTES, stream, maps, C, M, N, ldc,
+             strideC, kblocks, per_split, used_splits, tiles_m, tiles_n, (int)items, accumulate == ACC_ADD ? 1 : 0, ws, batch * M * N,
+             repair ? *repair : RepairArgs{}, epi ? *epi : EpilogueChain{});
     count_launch();
     EML_TRY(check_launch("tf32x3_tcgen05 (CTA pair)"));
     if (ws) EML_TRY(launch_splitk_reduce<float>(ws, used_splits, C, batch, M, N, Strides3{strideC, ldc, 1}, accumulate, stream));
@@ -815,6 +841,132 @@ int packed_operand(uint64_t id, const float* src, int64_t batch, int64_t MN, int
         g_pack_order.pop_front();
     }
     g_pack[key] = PackEntry{*big, bytes};
+    g_pack_order.push_back(key);
+    g_pack_bytes += bytes;
+    return EML_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// "Direct" operands of the CTA-pair kernel: the tensor core reads the caller's f32 matrix itself as the big part
+// (kind::tf32 truncates the low 13 mantissa bits, which is how tf32_split.cuh defines big), in place, whichever of
+// its two indexes is contiguous (K-major / MN-major tiles, see sm100.cuh).  Only the SMALL parts are materialised:
+// one plane with the matrix's own layout -- an elementwise pass that reads 4 and writes 4 bytes per element (the
+// full pack: 4 + 8, through a transposing tile when the operand is m / n-contiguous).  Needs what TMA needs: a
+// 16-byte aligned base, a leading dimension (and batch stride) that is a multiple of 4 elements, rows that do not
+// overlap.  Everything else takes the packed planes.  EML_SGEMM_DIRECT=0 switches it off (comparison path: same bits).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+small_plane_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t rows, int64_t cols, int64_t ld_src,
+                   int64_t ld_dst, int64_t sb_src, int64_t sb_dst, unsigned* nonfinite) {
+    pdl_prologue();
+    const int64_t vec_per_row = ld_dst / 4;  // ld_dst is a multiple of 4 >= cols
+    const int64_t total = rows * vec_per_row;
+    const float* s = src + (int64_t)blockIdx.y * sb_src;
+    float* d = dst + (int64_t)blockIdx.y * sb_dst;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / vec_per_row, c = (i % vec_per_row) * 4;
+        const float4 v = load4_guarded(s + r * ld_src + c, c, cols);
+        float4 hi, lo;
+        if (tf32::ordinary4(v)) {
+            tf32::split4_ordinary(v, hi, lo);
+        } else {
+            tf32::split4_any(v, hi, lo);
+            *nonfinite = 1u;
+        }
+        *reinterpret_cast<float4*>(d + r * ld_dst + c) = lo;
+    }
+}
+
+struct DirectOperand {
+    bool kin = true;         // k contiguous (K-major tiles) or mn contiguous (MN-major tiles)
+    int64_t rows = 0, cols = 0, ld = 0, ld_small = 0;  // as stored: kin: rows = MN, cols = K; else rows = K, cols = MN
+};
+
+bool direct_enabled() {  // (read per call: the tests compare both paths in one process)
+    const char* e = getenv("EML_SGEMM_DIRECT");
+    return !(e && e[0] == '0');
+}
+
+// element (b, mn, k) of the operand at src[b*sb + mn*smn + k*sk]
+bool direct_possible(const float* src, int64_t batch, int64_t MN, int64_t K, int64_t sb, int64_t smn, int64_t sk, DirectOperand* out) {
+    if (!direct_enabled()) return false;
+    const bool kin = sk == 1 && (smn != 1 || MN == 1), min = smn == 1 && sk != 1;
+    if (!kin && !min) return false;
+    DirectOperand d;
+    d.kin = kin;
+    d.rows = kin ? MN : K;
+    d.cols = kin ? K : MN;
+    d.ld = kin ? smn : sk;
+    if ((reinterpret_cast<uintptr_t>(src) & 15) || (d.ld & 3) || d.ld < d.cols) return false;
+    if (batch > 1 && ((sb & 3) || sb < (d.rows - 1) * d.ld + d.cols)) return false;
+    if (d.ld > (int64_t(1) << 36) || MN > 0x7fffffffLL || K > 0x7fffffffLL) return false;
+    d.ld_small = (d.cols + 3) / 4 * 4;
+    *out = d;
+    return true;
+}
+
+// tensor map of a direct operand (the caller's matrix, or its small plane with leading dimension ld)
+int direct_map(CUtensorMap* map, const float* base, const DirectOperand& d, int64_t ld, int64_t batch, int64_t sb) {
+    uint64_t dims[3] = {(uint64_t)d.cols, (uint64_t)d.rows, (uint64_t)batch};
+    uint64_t strides[2] = {(uint64_t)ld * 4, (uint64_t)(batch > 1 ? sb : 4) * 4};
+    uint32_t box[3] = {(uint32_t)(d.kin ? BK : 32), (uint32_t)(d.kin ? pair::HALF : BK), 1};
+    return make_tensor_map(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box,
+                           d.kin ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+}
+
+int launch_small_plane(const float* src, float* dst, const DirectOperand& d, int64_t batch, int64_t sb, unsigned* nonfinite,
+                       cudaStream_t stream) {
+    const int64_t total = d.rows * (d.ld_small / 4);
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    launch_k(small_plane_kernel, dim3((unsigned)blocks, (unsigned)batch), dim3(256), 0, stream, src, dst, d.rows, d.cols, d.ld, d.ld_small,
+             sb, d.rows * d.ld_small, nonfinite);
+    count_launch();
+    return check_launch("tf32x3 small-part plane");
+}
+
+// the small plane of a direct operand: from the cache when `id` is set (computing it on a miss), else into `scratch`
+int small_operand(uint64_t id, const float* src, const DirectOperand& d, int64_t batch, int64_t sb, TempBuf& scratch,
+                  cudaStream_t stream, float** small, unsigned* stream_flag, const unsigned** flag) {
+    const size_t plane = (size_t)(batch * d.rows * d.ld_small);
+    const size_t bytes = sizeof(float) * plane + 256;  // + the cached operand's flag word
+    if (id == 0) {
+        EML_TRY(scratch.alloc(bytes, stream));
+        *small = scratch.as<float>();
+        *flag = stream_flag;
+        return launch_small_plane(src, *small, d, batch, sb, stream_flag, stream);
+    }
+    int dev = 0;
+    EML_CUDA(cudaGetDevice(&dev));
+    // (kind of entry: mnp = -1 marks a small-only plane with the operand's own layout)
+    PackKey key{id, dev, stream, d.rows, d.cols, -1, d.ld_small, batch, sb, d.ld, d.kin ? 1 : 0};
+    {
+        std::lock_guard<std::mutex> lock(g_pack_mu);
+        auto it = g_pack.find(key);
+        if (it != g_pack.end()) {
+            *small = it->second.planes;
+            *flag = reinterpret_cast<const unsigned*>(*small + plane);
+            return EML_OK;
+        }
+    }
+    void* p = nullptr;
+    EML_TRY(stream_alloc(&p, bytes, stream));
+    *small = static_cast<float*>(p);
+    unsigned* own_flag = reinterpret_cast<unsigned*>(*small + plane);
+    *flag = own_flag;
+    {
+        ZeroRanges z;
+        z.count = 1, z.p[0] = own_flag, z.bytes[0] = 16;
+        EML_TRY(launch_zero_ranges(z, stream));
+    }
+    EML_TRY(launch_small_plane(src, *small, d, batch, sb, own_flag, stream));
+    std::lock_guard<std::mutex> lock(g_pack_mu);
+    while (g_pack_bytes + bytes > PACK_CACHE_LIMIT && !g_pack_order.empty()) {
+        pack_evict_locked(g_pack_order.front());
+        g_pack_order.pop_front();
+    }
+    g_pack[key] = PackEntry{*small, bytes};
     g_pack_order.push_back(key);
     g_pack_bytes += bytes;
     return EML_OK;
@@ -944,17 +1096,29 @@ int launch_gemm_tf32x3_f32(DeviceCtx* ctx, const float* A, const float* B, float
         else EML_TRY(zero_c());
     }
     TempBuf a_scratch, b_scratch, wsbuf;
-    float *a_big, *a_small, *b_big, *b_small;
+    float *a_big = nullptr, *a_small = nullptr, *b_big = nullptr, *b_small = nullptr;
     unsigned* tickets = nullptr;
     EML_TRY(stream_tickets(stream, &tickets));
     unsigned* stream_flag = tickets + TICKET_NONFINITE;
     const unsigned *a_flag = nullptr, *b_flag = nullptr;
-    EML_TRY(packed_operand(a_id, A, batch, M, K, Mp, Kp, sA.b, sA.r, sA.c, a_scratch, stream, &a_big, &a_small, stream_flag, &a_flag));
+    // CTA-pair kernel: an operand TMA can read in place is not packed -- the matrix itself is the big part (see
+    // DirectOperand); the 128-row kernels and operands TMA cannot describe take the packed planes
+    DirectOperand da, db;
+    const bool a_direct = use_pair && direct_possible(A, batch, M, K, sA.b, sA.r, sA.c, &da);
     // B element (k, n) at B[k*sB.r + n*sB.c]: its "mn" index is n
-    if (upper_only) {  // B is the same matrix read through mirrored strides: the planes just packed serve both sides
+    const bool b_direct = use_pair && direct_possible(B, batch, N, K, sB.b, sB.c, sB.r, &db);
+    if (a_direct) {
+        EML_TRY(small_operand(a_id, A, da, batch, sA.b, a_scratch, stream, &a_small, stream_flag, &a_flag));
+    } else {
+        EML_TRY(packed_operand(a_id, A, batch, M, K, Mp, Kp, sA.b, sA.r, sA.c, a_scratch, stream, &a_big, &a_small, stream_flag, &a_flag));
+    }
+    if (upper_only && a_direct == b_direct) {
+        // B is the same matrix read through mirrored strides: the plane(s) just made serve both sides
         b_big = a_big;
         b_small = a_small;
         b_flag = a_flag;
+    } else if (b_direct) {
+        EML_TRY(small_operand(b_id, B, db, batch, sB.b, b_scratch, stream, &b_small, stream_flag, &b_flag));
     } else {
         EML_TRY(packed_operand(b_id, B, batch, N, K, Np, Kp, sB.b, sB.c, sB.r, b_scratch, stream, &b_big, &b_small, stream_flag, &b_flag));
     }
@@ -966,10 +1130,26 @@ int launch_gemm_tf32x3_f32(DeviceCtx* ctx, const float* A, const float* B, float
 
     Maps maps;
     const int b_box = use_pair ? pair::HALF : BN;  // rows of B one TMA box brings in
-    EML_TRY(plane_map(&maps.a_big, a_big, Mp, Kp, batch, BM));
-    EML_TRY(plane_map(&maps.a_small, a_small, Mp, Kp, batch, BM));
-    EML_TRY(plane_map(&maps.b_big, b_big, Np, Kp, batch, b_box));
-    EML_TRY(plane_map(&maps.b_small, b_small, Np, Kp, batch, b_box));
+    bool maps_ok = true;
+    if (a_direct) {
+        maps_ok = direct_map(&maps.a_big, A, da, da.ld, batch, sA.b) == EML_OK &&
+                  direct_map(&maps.a_small, a_small, da, da.ld_small, batch, da.rows * da.ld_small) == EML_OK;
+    } else {
+        EML_TRY(plane_map(&maps.a_big, a_big, Mp, Kp, batch, BM));
+        EML_TRY(plane_map(&maps.a_small, a_small, Mp, Kp, batch, BM));
+    }
+    if (b_direct) {
+        maps_ok = maps_ok && direct_map(&maps.b_big, B, db, db.ld, batch, sB.b) == EML_OK &&
+                  direct_map(&maps.b_small, b_small, db, db.ld_small, batch, db.rows * db.ld_small) == EML_OK;
+    } else {
+        EML_TRY(plane_map(&maps.b_big, b_big, Np, Kp, batch, b_box));
+        EML_TRY(plane_map(&maps.b_small, b_small, Np, Kp, batch, b_box));
+    }
+    if (!maps_ok) {
+        set_error("tf32x3: the driver refused a tensor map of an operand read in place (set EML_SGEMM_DIRECT=0)");
+        return EML_ERR_CUDA;
+    }
+    const bool a_kin = a_direct ? da.kin : true, b_kin = b_direct ? db.kin : true;
     set_last_kernel("tf32x3_tcgen05");
     bool repair_folded = false;
     if (use_pair) {
@@ -994,7 +1174,7 @@ int launch_gemm_tf32x3_f32(DeviceCtx* ctx, const float* A, const float* B, float
             }
         }
         EML_TRY(pair::launch(maps, C, batch, M, N, sC.r, sC.b, kblocks, splits, sms, acc_mode, ws, stream, upper_only,
-                             repair_folded ? &rep : nullptr, epi));
+                             repair_folded ? &rep : nullptr, epi, a_kin, b_kin));
         if (upper_only) opt->upper_done = true;
     } else if (BN == 256) {
         EML_TRY(launch_tile<256>(maps, C, batch, M, N, sC.r, sC.b, kblocks, splits, acc_mode, ws, stream));

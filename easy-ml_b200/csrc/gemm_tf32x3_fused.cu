@@ -76,22 +76,8 @@ __device__ __forceinline__ Work decode(int w, int tiles_m, int tiles_n, int spli
     return k;
 }
 
-// MN-major operand, 128-byte swizzle with 32-byte atoms (UMMA layout type 1), see the header of this file
-__device__ __forceinline__ uint64_t umma_desc_mn_sw128_base32(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-    d |= (uint64_t)(GROUP_BYTES >> 4) << 16;  // LBO: the next 32 rows
-    d |= (uint64_t)(512 >> 4) << 32;          // SBO: the next 4 k
-    d |= (uint64_t)1 << 46;                   // descriptor version (Blackwell)
-    d |= (uint64_t)1 << 61;                   // layout type 1: SWIZZLE_128B_BASE32B
-    return d;
-}
-// descriptor of k step `ks` (8 k) of a tile: K-major +32 bytes inside the 128-byte rows, MN-major +8 rows of 128 bytes
 template <bool KIN>
-__device__ __forceinline__ uint64_t tile_desc(uint32_t tile_addr, int ks) {
-    if (KIN) return umma_desc_k_sw128(tile_addr) + 2 * ks;
-    return umma_desc_mn_sw128_base32(tile_addr + ks * 1024);
-}
+__device__ __forceinline__ uint64_t tile_desc(uint32_t tile_addr, int ks) { return umma_tile_desc_f32<KIN>(tile_addr, ks); }
 
 // One k block: the raw A and B tiles -> their small tiles, elementwise and layout preserving (whatever the layout).
 // 64 warp tasks (a task = 32 lanes x 16 bytes of one tile); converter warp `cw` takes tasks cw, cw + CONV_WARPS, ...
@@ -183,7 +169,7 @@ tf32x3_fused_kernel(const __grid_constant__ Maps maps, float* __restrict__ C, in
     if (warp == 1) {
         // ---------------- MMA issuer (leader CTA only) ----------------
         if (rank == 0 && lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_tf32(PM, PN) | (A_KIN ? 0u : 1u << 15) | (B_KIN ? 0u : 1u << 16);
+            constexpr uint32_t idesc = umma_idesc_tf32(PM, PN) | (A_KIN ? 0u : UMMA_IDESC_A_MN) | (B_KIN ? 0u : UMMA_IDESC_B_MN);
             int n = 0, it = 0;
             for (int w = cluster; w < work_items; w += clusters) {
                 const Work wk = decode(w, tiles_m, tiles_n, splits);

@@ -194,6 +194,30 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;                            // layout type: SWIZZLE_128B
     return d;
 }
+// Shared-memory matrix descriptor, MN-major 32-bit operand (m / n index contiguous): [groups of 32 rows][k][32 rows],
+// 128-byte rows, 128-byte swizzle with 32-byte atoms = UMMA layout type 1 (SWIZZLE_128B_BASE32B) = what TMA's
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B writes from a box (32 rows, k).  32-byte units are XORed with (k & 3); the next
+// 4 k are SBO = 512 B further, the next 32 rows LBO = group_bytes further.  It is the ONLY MN-major form kind::tf32
+// accepts (scripts/probe/tf32_operand_probe.cu: every other layout type reads zeros).
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128_base32(uint32_t smem_addr, uint32_t group_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(group_bytes >> 4) << 16;  // LBO
+    d |= (uint64_t)(512 >> 4) << 32;          // SBO
+    d |= (uint64_t)1 << 46;                   // descriptor version (Blackwell)
+    d |= (uint64_t)1 << 61;                   // layout type 1
+    return d;
+}
+// descriptor of k step `ks` (8 k) of a 128-row x 32-k f32 tile: K-major (128-byte rows of k, SWIZZLE_128B) +32 bytes
+// inside the rows; MN-major (four groups of [32 k][32 rows]) +8 rows of 128 bytes
+template <bool KIN>
+__device__ __forceinline__ uint64_t umma_tile_desc_f32(uint32_t tile_addr, int ks) {
+    if (KIN) return umma_desc_k_sw128(tile_addr) + 2 * ks;
+    return umma_desc_mn_sw128_base32(tile_addr + ks * 1024, 32 * 32 * 4);
+}
+// instruction descriptor bits: operand A / B is MN-major
+constexpr uint32_t UMMA_IDESC_A_MN = 1u << 15, UMMA_IDESC_B_MN = 1u << 16;
+
 // Instruction descriptor for kind::tf32, f32 accumulate, both operands K-major, shape M x N (K = 8).
 __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
     return (1u << 4)                 // c_format  = F32

@@ -169,3 +169,70 @@ def test_broadcast_operand_falls_back_to_the_packed_path():
     out = eml.Einsum.with_2(x, y).to(["batch", "row", "col"])
     assert out.shape() == [("batch", bt), ("row", m), ("col", n)]
     assert np.allclose(out.data, exact.cpu().numpy(), rtol=0, atol=float(bound.max()))
+
+
+class direct:
+    """EML_SGEMM_DIRECT=1 (the CTA-pair kernel reads operands TMA can describe in place: raw matrix as the big part,
+    a small-part plane with the matrix's own layout) / =0 (packed big + small planes) for the calls inside."""
+
+    def __init__(self, value):
+        self.value = value
+
+    def __enter__(self):
+        self.old = os.environ.get("EML_SGEMM_DIRECT")
+        os.environ["EML_SGEMM_DIRECT"] = self.value
+
+    def __exit__(self, *exc):
+        if self.old is None:
+            del os.environ["EML_SGEMM_DIRECT"]
+        else:
+            os.environ["EML_SGEMM_DIRECT"] = self.old
+
+
+@pytest.mark.parametrize("shape", SHAPES + [(1, 2048, 2304, 520), (1, 784, 512, 8192)])
+@pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, False), (True, True)])
+def test_operands_read_in_place_match_packed_planes_bitwise(shape, ta, tb):
+    """The packed path's big plane holds trunc(x) -- exactly what kind::tf32 makes of the raw word -- so reading the
+    caller's matrix itself as the big operand (K-major or MN-major tiles by its contiguous index) gives the same bits,
+    with one small-part plane per operand instead of two padded, possibly transposed planes.  Ragged shapes (zero fill
+    by TMA), batches, split-K, and rows TMA cannot read in place (not 16-byte multiples: that operand stays packed)."""
+    batch, m, n, k = shape
+    g = torch.Generator(device="cuda").manual_seed(hash((shape, ta, tb, "d")) & 0xFFFF)
+    a = stored(torch.randn(batch, m, k, generator=g, device="cuda"), ta)
+    b = stored(torch.randn(batch, k, n, generator=g, device="cuda"), tb)
+    with forced("0"):
+        with direct("0"):
+            before = eml.kernel_launches()
+            ref = contract(a, b)
+            packed_launches = eml.kernel_launches() - before
+        with direct("1"):
+            before = eml.kernel_launches()
+            got = contract(a, b)
+            direct_launches = eml.kernel_launches() - before
+    assert eml.last_kernel() == "tf32x3_tcgen05"
+    assert torch.equal(ref, got)
+    assert direct_launches <= packed_launches
+    exact = a.double() @ b.double()
+    bound = TOL * (a.double().abs() @ b.double().abs())
+    assert bool(((got.double() - exact).abs() <= bound).all())
+
+
+def test_operands_read_in_place_special_values_and_accumulate():
+    g = torch.Generator(device="cuda").manual_seed(13)
+    a = torch.randn(1, 512, 320, generator=g, device="cuda")
+    b = torch.randn(1, 320, 384, generator=g, device="cuda")
+    c0 = torch.randn(1, 512, 384, generator=g, device="cuda")
+    fmax = float(np.finfo(np.float32).max)
+    a[0, 3, 5] = fmax
+    a[0, 9, 0] = float("nan")
+    b[0, 4, 17] = float("inf")
+    b[0, 2, 200] = -3.0e38
+    with forced("0"):
+        with direct("0"):
+            ref, ref_acc = contract(a, b), contract(a, b, c0)
+        with direct("1"):
+            got, got_acc = contract(a, b), contract(a, b, c0)
+    for r, x in ((ref, got), (ref_acc, got_acc)):
+        assert torch.equal(torch.isnan(r), torch.isnan(x))
+        ok = ~torch.isnan(r)
+        assert torch.equal(r[ok], x[ok])
