@@ -226,6 +226,9 @@ template <class T>
 int launch_mirror_upper(T* C, int64_t n, int64_t ldc, cudaStream_t stream);  // C[j][i] = C[i][j] for i < j
 
 // Split/pack cache of the f32 tensor-core GEMM (see GemmOptions::a_id / b_id)
+// (gemm_tf32x3.cu) the plane a producer kernel fills for a later product's B operand; *plane = nullptr: not possible
+int tf32x3_reserve_small_plane_b(uint64_t id, const float* src, int64_t rows, int64_t cols, cudaStream_t stream, float** plane,
+                                 unsigned** flag);
 uint64_t new_buffer_identity();
 void pack_cache_drop(uint64_t id);
 void pack_cache_release_all();
@@ -289,6 +292,12 @@ struct SgdBatch {
     int slot0_n[SGD_BATCH_MAX];        // ... the in-order fold of this many slots
     int64_t n[SGD_BATCH_MAX];
     double lr[SGD_BATCH_MAX];
+    // f32 only: also write the small-part plane of the updated weights (tf32x3_reserve_small_plane_b): the next forward
+    // product then finds it and needs no pass of its own.  The job's CTAs count themselves on ticket[y] (and whether
+    // they met a non-finite value); the last one writes the plane's flag word.
+    float* small[SGD_BATCH_MAX] = {};
+    unsigned* small_flag[SGD_BATCH_MAX] = {};
+    unsigned* tickets = nullptr;
     // rider: a few bytes (the step's loss) stored straight into page-locked host memory by one extra block row of the
     // same launch -- the read-back of a training step then costs no launch of its own
     const void* copy_src = nullptr;

@@ -12,6 +12,7 @@
 
 #include "common.h"
 #include "ew_rules.cuh"
+#include "tf32_split.cuh"
 
 namespace eml {
 
@@ -430,6 +431,8 @@ __global__ void __launch_bounds__(EW_THREADS) sgd_batch_kernel(const __grid_cons
     const T* d = static_cast<const T*>(b.d[y]);
     const T lr = (T)b.lr[y];
     const int64_t n = b.n[y];
+    float* small = sizeof(T) == 4 ? b.small[y] : nullptr;
+    int unusual = 0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         T g = d[i];
         if (i == 0 && b.slot0[y]) {  // the parked constant-operand sums, folded in sweep order
@@ -438,7 +441,25 @@ __global__ void __launch_bounds__(EW_THREADS) sgd_batch_kernel(const __grid_cons
             for (int k = 0; k < b.slot0_n[y]; k++) s = s + slots[k];
             g = g + s;
         }
-        out[i] = w[i] - g * lr;
+        const T v = w[i] - g * lr;
+        out[i] = v;
+        if (small) {
+            float hi, lo;
+            tf32::split((float)v, hi, lo);
+            small[i] = lo;
+            unusual |= !tf32::ordinary((float)v);
+        }
+    }
+    if (small) {  // the last CTA of this job writes the plane's "non-finite value seen" word
+        unusual = __syncthreads_or(unusual);
+        if (threadIdx.x == 0) {
+            const unsigned add = unusual ? 0x10001u : 1u;
+            const unsigned before = atomicAdd(b.tickets + y, add);
+            if ((before & 0xffffu) + 1u == gridDim.x) {
+                *b.small_flag[y] = ((before + add) >> 16) ? 1u : 0u;
+                b.tickets[y] = 0u;
+            }
+        }
     }
 }
 }  // namespace

@@ -14,6 +14,7 @@
 #include "common.h"
 #include "ew_fused.h"
 #include "ew_rules.cuh"
+#include "tf32_split.cuh"
 
 namespace eml {
 
@@ -405,6 +406,19 @@ __global__ void __launch_bounds__(EW_THREADS_FUSED) chain_backward_kernel(const 
         ld_all<T, V, U>(static_cast<const T*>(p.in[0]) + i, ok, x);
         chain_backward<T, V, U, 0, (int)sizeof...(OPS), OPS...>(p, x, g, i, ok);
         if (p.n_leafgrad > 0) st_all<T, V, U>(static_cast<T*>(p.lg[0].ptr) + i, ok, g);
+        if constexpr (sizeof(T) == 4) {
+            if (p.n_leafgrad > 0 && p.lg_small) {  // the TF32 small parts of what was just stored (tf32_split.cuh)
+#pragma unroll
+                for (int u = 0; u < U; u++)
+#pragma unroll
+                    for (int j = 0; j < V; j++) {
+                        float hi, lo;
+                        tf32::split(g.v[u][j], hi, lo);
+                        g.v[u][j] = lo;
+                    }
+                st_all<T, V, U>(p.lg_small + i, ok, g);
+            }
+        }
     }
 }
 
@@ -466,6 +480,17 @@ int chain_dispatch(const EwProgram& p, cudaStream_t stream, bool* handled) {
         return chain_go<T, BWD, EML_OP_NEG, EML_OP_EXP, EML_OP_ADD_C, EML_OP_C_DIV>(p, stream);
     *handled = false;
     return EML_OK;
+}
+
+bool chain_whitelisted(const EwProgram& p) {
+    static const bool off = [] {
+        const char* e = getenv("EML_EW_CHAINS");
+        return e && e[0] == '0';
+    }();
+    if (off || !is_unary_chain(p)) return false;
+    if (p.n_ops == 1) return true;
+    return p.n_ops == 4 && p.ops[0].op == EML_OP_NEG && p.ops[1].op == EML_OP_EXP && p.ops[2].op == EML_OP_ADD_C &&
+           p.ops[3].op == EML_OP_C_DIV;
 }
 
 template <class K>
@@ -537,6 +562,8 @@ int launch_any(const EwProgram& p, cudaStream_t stream) {
 }
 
 }  // namespace
+
+bool ew_backward_writes_small(const EwProgram& p) { return chain_whitelisted(p) && p.n_leafgrad == 1; }
 
 template <class T>
 int launch_ew_forward(const EwProgram& p, cudaStream_t stream) { return launch_any<T, false>(p, stream); }

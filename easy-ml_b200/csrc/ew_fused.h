@@ -68,8 +68,14 @@ struct EwProgram {
     void* out[EW_MAX_OPS];   // forward outputs (per op)
     void* gptr[EW_MAX_OPS];  // backward: per op, its derivatives in the sweep's arena (EW_G_LOAD / g_store)
     EwLeafGrad lg[EW_MAX_IN];
+    // f32 straight-line chains only (ew_backward_writes_small): next to the derivatives of the (single) input container
+    // also store their TF32 small parts, element for element -- the plane the backward GEMM that reads these derivatives
+    // as its B operand would otherwise compute in a pass of its own (tf32x3_reserve_small_plane_b)
+    float* lg_small;
     EwOp ops[EW_MAX_OPS];
 };
+// true when launch_ew_backward<float>(p) runs a kernel that honours p.lg_small
+bool ew_backward_writes_small(const EwProgram& p);
 
 template <class T>
 int launch_ew_forward(const EwProgram& p, cudaStream_t stream);

@@ -973,6 +973,41 @@ int small_operand(uint64_t id, const float* src, const DirectOperand& d, int64_t
 }
 }  // namespace
 
+// Reserves (or finds) the small-part plane that a later product will look up for the dense row-major matrix `src`
+// [rows x cols] under identity `id` when it reads it in place as its B operand (k = row index, n contiguous), so
+// that the kernel which PRODUCES src can write the plane itself, element i of the plane next to element i of src --
+// a weight update, the sweep kernel of an activation -- and the product finds it in the cache instead of launching
+// the small-part pass.  *plane = nullptr: not possible for this matrix (cols not a multiple of 4, alignment, ...).
+// The flag word behind the plane is the reader's "non-finite input seen" word: the producer must set it.
+int tf32x3_reserve_small_plane_b(uint64_t id, const float* src, int64_t rows, int64_t cols, cudaStream_t stream, float** plane,
+                                 unsigned** flag) {
+    *plane = nullptr;
+    if (flag) *flag = nullptr;
+    DirectOperand d;
+    if (!id || (cols & 3) || !direct_possible(src, 1, cols, rows, 0, 1, cols, &d) || d.kin || d.ld_small != cols) return EML_OK;
+    int dev = 0;
+    EML_CUDA(cudaGetDevice(&dev));
+    PackKey key{id, dev, stream, d.rows, d.cols, -1, d.ld_small, 1, 0, d.ld, 0};
+    const size_t n = (size_t)(d.rows * d.ld_small);
+    const size_t bytes = sizeof(float) * n + 256;
+    std::lock_guard<std::mutex> lock(g_pack_mu);
+    auto it = g_pack.find(key);
+    if (it == g_pack.end()) {
+        void* p = nullptr;
+        EML_TRY(stream_alloc(&p, bytes, stream));
+        while (g_pack_bytes + bytes > PACK_CACHE_LIMIT && !g_pack_order.empty()) {
+            pack_evict_locked(g_pack_order.front());
+            g_pack_order.pop_front();
+        }
+        it = g_pack.emplace(key, PackEntry{static_cast<float*>(p), bytes}).first;
+        g_pack_order.push_back(key);
+        g_pack_bytes += bytes;
+    }
+    *plane = it->second.planes;
+    if (flag) *flag = reinterpret_cast<unsigned*>(*plane + n);
+    return EML_OK;
+}
+
 uint64_t new_buffer_identity() { return g_next_identity.fetch_add(1); }
 void pack_cache_drop(uint64_t id) {
     if (!id) return;

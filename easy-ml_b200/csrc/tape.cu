@@ -30,7 +30,11 @@ struct DevBuf {
     cudaStream_t s = nullptr;
     std::shared_ptr<DevBuf> parent;  // set for a view into another buffer (the view owns nothing)
     uint64_t identity = 0;           // non-zero: immutable constant whose packed TF32 planes may be cached
+    // non-zero: the weight update that produced these numbers also wrote their TF32 small-part plane for the NEXT forward
+    // product (cached under this id, looked up only by a forward product that reads the container as its right operand)
+    uint64_t plane_id = 0;
     ~DevBuf() {
+        if (plane_id) pack_cache_drop(plane_id);
         if (identity) pack_cache_drop(identity);
         if (p && !parent) stream_free(p, bytes, s);
     }
@@ -88,6 +92,7 @@ struct Value {
     int node = -1;         // producing node in the CURRENT epoch; -1: every Index is 0 (constants)
     uint64_t epoch = 0;    // tape epoch the node id belongs to
     std::shared_ptr<IndexMap> map;  // from_existing: the indexes of the elements (node = the VIEW node when tracked)
+    bool b_of_tc_product = false;   // was the right operand of a product the f32 CTA-pair kernel computes (see sgd_update)
     bool alive = false;
     int64_t n() const { return rows * cols; }
 };
@@ -196,6 +201,8 @@ struct eml_tape {
         int slot0_n;
         int64_t n;
         double lr;
+        float* small = nullptr;          // f32: the small-part plane of the updated weights, and its flag word
+        unsigned* small_flag = nullptr;
     };
     std::vector<PendingSgd> sgd;
     // A product whose launch is deferred to the next flush: when the operators that follow it form a fused elementwise
@@ -214,6 +221,7 @@ struct eml_tape {
         int64_t M = 0, N = 0, K = 0;
     } mm;
     bool defer_matmul = false;
+    bool fuse_packs = true;  // EML_FUSE_PACKS=0: producers do not write small-part planes for the products that follow
     bool zero_plus = true;  // EML_ZERO_PLUS=0: products accumulate into zero-filled buffers (see matmul_overwrites)
     // a small asynchronous read-back requested while updates are queued rides in their launch (SgdBatch rider)
     Buf rider_src;
@@ -372,7 +380,7 @@ bool group_fits(const std::vector<Node>& nodes, const Group& g) {
 template <class T>
 int group_backward(const std::vector<Node>& nodes, const Group& g, const std::vector<Buf>& grads,
                    std::vector<char>& written, std::vector<char>& have, int seed_node, int64_t seed_elem, bool remat,
-                   cudaStream_t st) {
+                   cudaStream_t st, float* lg_small = nullptr, bool* small_written = nullptr) {
     EwProgram p;
     if (!program_structure(nodes, g, &p)) {
         set_error("internal: a fused elementwise group does not fit its program");
@@ -461,6 +469,10 @@ int group_backward(const std::vector<Node>& nodes, const Group& g, const std::ve
     }
     bool anything = p.n_leafgrad > 0;
     for (int k = 0; k < n_ops; k++) anything |= p.ops[k].g_store != 0;
+    if (lg_small && sizeof(T) == 4 && ew_backward_writes_small(p)) {
+        p.lg_small = lg_small;
+        if (small_written) *small_written = true;
+    }
     if (anything) EML_TRY(launch_ew_backward<T>(p, st));
     for (int k = 0; k < n_ops; k++) {
         const int id = g.first + k;
@@ -479,7 +491,9 @@ int flush_sgd(eml_tape* t) {
             const auto& u = t->sgd[j];
             const int y = b.count++;
             b.out[y] = u.out->p, b.w[y] = u.w->p, b.d[y] = u.d, b.slot0[y] = u.slot0, b.slot0_n[y] = u.slot0_n, b.n[y] = u.n, b.lr[y] = u.lr;
+            b.small[y] = u.small, b.small_flag[y] = u.small_flag;
         }
+        EML_TRY(stream_tickets(t->stream, &b.tickets));
         if (t->rider_src && i + SGD_BATCH_MAX >= t->sgd.size()) {  // the last launch carries the rider
             b.copy_src = t->rider_src->p, b.copy_dst = t->rider_dst, b.copy_bytes = t->rider_bytes;
             t->rider_src.reset();
@@ -743,7 +757,8 @@ int tape_matmul(eml_tape* t, eml_val ha, eml_val hb, eml_val* out) {
     t->mm.b = b->numbers;
     t->mm.c = c.numbers;
     t->mm.a_id = a->numbers->identity;  // constant operands keep their packed planes across steps
-    t->mm.b_id = b->numbers->identity;
+    t->mm.b_id = b->numbers->identity ? b->numbers->identity : b->numbers->plane_id;
+    b->b_of_tc_product = sizeof(T) == 4 && M > 128 && N > 128 && K >= 32 && M * N * K >= (int64_t(1) << 24);
     t->mm.M = M, t->mm.N = N, t->mm.K = K;
     // deferred only where the epilogue could take the chain (f32, tracked, a shape of the CTA-pair kernel) and the
     // tape fuses at all; everything else goes out now
@@ -1042,13 +1057,19 @@ int sweep_from(eml_tape* t, int nv, int64_t seed_elem, eml_derivs** out) {
     // that is an elementwise rule, it writes  0 + dout * deriv  instead (same bits) and p is neither cleared nor read.
     const int n_nodes = (int)t->nodes.size();
     std::vector<int> first_consumer(n_nodes, -1);
+    std::vector<int> lowest_consumer(n_nodes, -1);  // the consumer the sweep visits LAST (-2: not a plain node / group)
+    auto consumed_by = [&](int target, int consumer, bool plain) {
+        first_consumer[target] = consumer;
+        if (!plain) lowest_consumer[target] = -2;
+        else if (lowest_consumer[target] == -1) lowest_consumer[target] = consumer;  // nodes are visited in ascending order here
+    };
     for (int i = 0; i < n_nodes; i++) {
         const Node& nd = t->nodes[i];
         if (nd.kind == Kind::VARIABLES) continue;
         if (nd.kind == Kind::VIEW) {  // its derivatives are ADDED to the nodes its indexes point into
             for (int64_t index : nd.map->seg_idx) {
                 const int target = node_of_index(t->nodes, index);
-                if (target >= 0) first_consumer[target] = i;
+                if (target >= 0) consumed_by(target, i, false);
             }
             continue;
         }
@@ -1058,14 +1079,17 @@ int sweep_from(eml_tape* t, int nv, int64_t seed_elem, eml_derivs** out) {
                 for (int64_t index : {nd.run->lp[(size_t)e], nd.run->rp[(size_t)e]}) {
                     if (last >= 0 && index >= t->nodes[last].base && index < t->nodes[last].base + t->nodes[last].count) continue;
                     last = node_of_index(t->nodes, index);
-                    if (last >= 0) first_consumer[last] = i;
+                    if (last >= 0) consumed_by(last, i, false);
                 }
             continue;
         }
         const bool uses0 = nd.kind == Kind::BINARY ? nd.p0_tracked : true, uses1 = nd.kind == Kind::BINARY ? nd.p1_tracked : nd.kind == Kind::MATMUL;
-        if (uses0 && nd.p0 >= 0) first_consumer[nd.p0] = i;
-        if (uses1 && nd.p1 >= 0) first_consumer[nd.p1] = i;
+        if (uses0 && nd.p0 >= 0) consumed_by(nd.p0, i, true);
+        if (uses1 && nd.p1 >= 0) consumed_by(nd.p1, i, true);
     }
+    // small-part planes written by the sweep kernel of an elementwise group for the backward GEMM that reads the same
+    // derivatives as its right operand (per matmul node: the cache identity, 0 = none)
+    std::vector<uint64_t> presmall(n_nodes, 0);
     std::vector<char> written(n_nodes, 0);
     bool seed_in_kernel = false;
     for (int i = 0; i < n_nodes; i++) {
@@ -1180,7 +1204,31 @@ int sweep_from(eml_tape* t, int nv, int64_t seed_elem, eml_derivs** out) {
         }
         if (nd.group >= 0) {  // the whole run [first, last] in one kernel
             const Group& grp = t->groups[nd.group];
-            EML_TRY(group_backward<T>(t->nodes, grp, d->grads, written, d->have, nv, seed_elem, false, st));
+            // The group's input is the output of a product whose sweep comes next and reads these derivatives as the
+            // right operand of dB = A^T G on THIS stream, and the group is the last to contribute to them: its kernel
+            // writes their TF32 small parts too, and that GEMM finds the plane instead of making it (f32 only).
+            float* lg_small = nullptr;
+            uint64_t gid = 0;
+            const int par = t->nodes[grp.first].p0;
+            if (sizeof(T) == 4 && t->fuse_packs && par >= 0 && t->nodes[par].kind == Kind::MATMUL && t->nodes[par].p1 >= 0 &&
+                t->nodes[par].p0 != t->nodes[par].p1 && lowest_consumer[par] >= grp.first && lowest_consumer[par] <= grp.last &&
+                grp.n == t->nodes[par].n) {
+                const Node& mm = t->nodes[par];
+                const bool leaf1 = t->nodes[mm.p1].kind == Kind::VARIABLES;
+                const bool db_on_main = !side || mm.p0 < 0 || !leaf1;  // (the rule of the matmul branch below)
+                // dB = A^T[K x M] * G[M x N]: the CTA-pair kernel takes it when both output extents exceed a tile
+                const bool tc = mm.K > 128 && mm.N > 128 && mm.M >= 32 && mm.M * mm.N * mm.K >= (int64_t(1) << 24);
+                if (db_on_main && tc && !thin_shape(mm.M, mm.N, mm.K)) {
+                    gid = new_buffer_identity();
+                    EML_TRY(tf32x3_reserve_small_plane_b(gid, (const float*)d->grads[par]->p, mm.M, mm.N, st, &lg_small, nullptr));
+                }
+            }
+            bool small_written = false;
+            EML_TRY(group_backward<T>(t->nodes, grp, d->grads, written, d->have, nv, seed_elem, false, st, lg_small, &small_written));
+            if (gid) {
+                if (small_written) presmall[par] = gid;
+                else pack_cache_drop(gid);
+            }
             i = grp.first;
             continue;
         }
@@ -1264,6 +1312,7 @@ int sweep_from(eml_tape* t, int nv, int64_t seed_elem, eml_derivs** out) {
             if (nd.p1 >= 0) {
                 GemmOptions ids;
                 ids.a_id = nd.a->identity;
+                ids.b_id = sb == st ? presmall[i] : 0;  // the small parts of g, written by the group that produced g
                 ids.zero_plus = !written[nd.p1];
                 written[nd.p1] = 1;
                 EML_TRY(contract_dev<T>(t->ctx, A, g, (T*)d->grads[nd.p1]->p, 1, K, N, M, Strides3{0, 1, K},
@@ -1276,6 +1325,7 @@ int sweep_from(eml_tape* t, int nv, int64_t seed_elem, eml_derivs** out) {
         }
     }
     EML_TRY(join());
+    for (uint64_t id : presmall) pack_cache_drop(id);  // (stream-ordered: the planes outlive the products enqueued above)
     // reference index 0 is element 0 of the first node: added on first use (fold_slot0) or by the weight update
     d->arena = arena;
     d->slot0_pending = n_slots > 0;
@@ -1308,6 +1358,7 @@ int eml_tape_create(int dtype, eml_tape** out) {
     if (const char* e = getenv("EML_FUSE")) t->fuse = !(e[0] == '0');
     if (const char* e = getenv("EML_EPILOGUE")) t->defer_matmul = e[0] == '1';
     if (const char* e = getenv("EML_ZERO_PLUS")) t->zero_plus = !(e[0] == '0');
+    if (const char* e = getenv("EML_FUSE_PACKS")) t->fuse_packs = !(e[0] == '0');
     const char* se = getenv("EML_SIDE");
     if (!(se && se[0] == '0')) {
         cudaError_t e = cudaEventCreateWithFlags(&t->ev_fork, cudaEventDisableTiming);
@@ -2005,6 +2056,11 @@ int eml_tape_sgd_update(eml_tape* t, eml_val hw, eml_derivs* d, double lr) {
     } else {
         // eagerly: a new container (the nodes that captured the old numbers keep them)
         EML_TRY(new_buf(es * n, t->stream, &u.out));
+    }
+    if (t->dtype == EML_F32 && w->b_of_tc_product && t->fuse_packs) {
+        if (!u.out->plane_id) u.out->plane_id = new_buffer_identity();
+        EML_TRY(tf32x3_reserve_small_plane_b(u.out->plane_id, (const float*)u.out->p, w->rows, w->cols, t->stream, &u.small,
+                                             &u.small_flag));
     }
     u.arena = d->arena;
     u.d = d->grads[w->node]->p;
