@@ -45,6 +45,10 @@ __device__ __forceinline__ void pdl_prologue() {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
 }
+// The two halves, for kernels with a set-up worth overlapping with the predecessor's tail (barrier initialisation, TMEM
+// allocation, descriptor prefetch): nothing the predecessor may have written is read before pdl_wait().
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 #endif
 bool pdl_enabled();
 void pdl_suppress(bool suppress);  // thread-local (graph capture)
@@ -164,7 +168,18 @@ struct GemmOptions {
     bool zero_plus = false;
     // Elementwise chain for the epilogue (see EpilogueChain); honoured only by the kernel that stores C itself
     const EpilogueChain* epilogue = nullptr;
+    // The caller can take the partial sums of a deterministic split-K launch instead of C (a first contribution only:
+    // zero_plus, or no accumulation): when the launch would end in the sequential reduction kernel, that kernel is NOT
+    // launched, C is not written, and deferred_* describe what C is:  0 + ws[0] + ws[1] + ...  in that order, partial s
+    // of element i at ws[s * stride + i].  The consumer adds them itself (the weight update of a training step:
+    // sgd_batch_kernel), or launch_splitk_reduce(..., ACC_ZERO_PLUS) materialises C later -- the same bits either way.
+    // The workspace becomes the caller's: stream_free(deferred_ws, deferred_bytes, <the launch's stream>).
+    bool defer_reduce = false;
     // ---- out ----
+    void* deferred_ws = nullptr;
+    size_t deferred_bytes = 0;
+    int deferred_splits = 0;
+    int64_t deferred_stride = 0;
     bool epilogue_done = false;  // the chain's containers were written by the GEMM
     bool remote_done = false;  // the kernel that ran stored the tiles to the peers
     bool upper_done = false;   // the kernel that ran computed the upper triangle only
@@ -240,6 +255,8 @@ int launch_gemm_tf32x3_f32(DeviceCtx* ctx, const float* A, const float* B, float
 
 // C[b][m][n] (+)= sum over splits (ascending) of ws[s][b][m][n]: the fixed-order reduction behind every
 // split-K path (deterministic: no atomics).  ws is dense; C is strided.
+// does launch_splitk_reduce add the partials of an element one after the other (the plain kernel)?
+bool splitk_reduce_is_sequential(int64_t total, int splits);
 template <class T>
 int launch_splitk_reduce(const T* ws, int splits, T* C, int64_t batch, int64_t M, int64_t N, Strides3 sC,
                          int accumulate /* ACC_* */, cudaStream_t stream);
@@ -297,6 +314,11 @@ struct SgdBatch {
     // they met a non-finite value); the last one writes the plane's flag word.
     float* small[SGD_BATCH_MAX] = {};
     unsigned* small_flag[SGD_BATCH_MAX] = {};
+    // non-null: d[y] has not been formed -- it is the deferred split-K reduction 0 + ws[0][i] + ws[1][i] + ... of the
+    // product that computed it (GemmOptions::defer_reduce); the update adds the partials itself, in that order
+    const void* ws[SGD_BATCH_MAX] = {};
+    int ws_splits[SGD_BATCH_MAX] = {};
+    int64_t ws_stride[SGD_BATCH_MAX] = {};
     unsigned* tickets = nullptr;
     // rider: a few bytes (the step's loss) stored straight into page-locked host memory by one extra block row of the
     // same launch -- the read-back of a training step then costs no launch of its own

@@ -433,8 +433,24 @@ __global__ void __launch_bounds__(EW_THREADS) sgd_batch_kernel(const __grid_cons
     const int64_t n = b.n[y];
     float* small = sizeof(T) == 4 ? b.small[y] : nullptr;
     int unusual = 0;
+    const T* ws = static_cast<const T*>(b.ws[y]);
+    const int splits = b.ws_splits[y];
+    const int64_t stride = b.ws_stride[y];
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        T g = d[i];
+        T g;
+        if (ws) {  // the deferred split-K reduction: 0 + partials in split order (splitk_reduce_kernel's chain)
+            g = T(0);
+            for (int s0 = 0; s0 < splits; s0 += 8) {
+                T v[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) v[u] = s0 + u < splits ? ws[(int64_t)(s0 + u) * stride + i] : T(0);
+#pragma unroll
+                for (int u = 0; u < 8; u++)
+                    if (s0 + u < splits) g += v[u];
+            }
+        } else {
+            g = d[i];
+        }
         if (i == 0 && b.slot0[y]) {  // the parked constant-operand sums, folded in sweep order
             const T* slots = static_cast<const T*>(b.slot0[y]);
             T s = T(0);

@@ -341,9 +341,45 @@ __global__ void __launch_bounds__(EW_THREADS_FUSED) chain_forward_kernel(const _
 
 // Recomputes op K (keeping its derivative in registers), descends to the later ops, and on the way back applies the
 // chain rule of op K: on return `g` holds the complete derivative of op K's INPUT (node K - 1, or the leaf).
-template <class T, int V, int U, int K, int N, int OP0, int... REST>
+// EW_INIT_PRODUCT: g[r][c..c+V) = sum_k G[r][k] * B[c..c+V)[k], one fma chain per element from +0, k ascending (the
+// arithmetic of gemm_smallk_reg_kernel / gemm_smallk_kernel).  sBt = B transposed in shared memory ([kc][cols]: a thread
+// reads its V columns of row k as one vector, a warp 32 consecutive vectors); bcol = this thread's first column, fixed for
+// the whole grid-stride loop because a block's stride is a whole number of rows.  G's row is the same for the whole warp
+// (a warp's vectors lie in one row): broadcast loads.
+template <class T, int V, int U>
+__device__ __forceinline__ void product_derivative(const EwProgram& p, int64_t i, const bool (&ok)[U], const T* sBt, int bcol,
+                                                   Lanes<T, V, U>& g) {
+    const T* G = static_cast<const T*>(p.prod_g);
+    const int kc = p.prod_kc;
+    const int64_t cols = p.prod_cols;
+    const T* grow[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        grow[u] = G + (ok[u] ? (i + u * (EW_THREADS_FUSED * V)) / cols : 0) * kc;
+#pragma unroll
+        for (int j = 0; j < V; j++) g.v[u][j] = T(0);
+    }
+    for (int k = 0; k < kc; k++) {
+        T b[V];
+        ld<T, V>(sBt + k * cols + bcol, b);
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const T gv = __ldg(grow[u] + k);
+#pragma unroll
+            for (int j = 0; j < V; j++) g.v[u][j] = fma(gv, b[j], g.v[u][j]);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++)
+        if (!ok[u]) {
+#pragma unroll
+            for (int j = 0; j < V; j++) g.v[u][j] = T(0);
+        }
+}
+
+template <class T, int V, int U, bool PROD, int K, int N, int OP0, int... REST>
 __device__ __forceinline__ void chain_backward(const EwProgram& p, Lanes<T, V, U>& x, Lanes<T, V, U>& g, int64_t i,
-                                               const bool (&ok)[U]) {
+                                               const bool (&ok)[U], const T* sBt, int bcol) {
     const T c = (T)p.ops[K].c;
     Lanes<T, V, U> d;
 #pragma unroll
@@ -356,7 +392,9 @@ __device__ __forceinline__ void chain_backward(const EwProgram& p, Lanes<T, V, U
             d.v[u][j] = dd;
         }
     if constexpr (sizeof...(REST) > 0) {
-        chain_backward<T, V, U, K + 1, N, REST...>(p, x, g, i, ok);  // g: derivative of node K, complete
+        chain_backward<T, V, U, PROD, K + 1, N, REST...>(p, x, g, i, ok, sBt, bcol);  // g: derivative of node K, complete
+    } else if constexpr (PROD) {
+        product_derivative<T, V, U>(p, i, ok, sBt, bcol, g);  // the last node: what its consumer, a short product, owes it
     } else {
         initial_derivative<T, V, U>(p, K, i, ok, g);  // the last node: nothing inside the chain contributes to it
     }
@@ -393,10 +431,23 @@ __device__ __forceinline__ void chain_backward(const EwProgram& p, Lanes<T, V, U
     }
 }
 
-template <class T, int V, int U, int... OPS>
+template <class T, int V, int U, bool PROD, int... OPS>
 __global__ void __launch_bounds__(EW_THREADS_FUSED) chain_backward_kernel(const __grid_constant__ EwProgram p) {
     pdl_prologue();
     constexpr int64_t PER_BLOCK = (int64_t)EW_THREADS_FUSED * V * U;
+    const T* sBt = nullptr;
+    int bcol = 0;
+    if constexpr (PROD) {
+        // B [cols x kc] row-major -> shared memory [kc][cols] (read coalesced; once per persistent CTA)
+        extern __shared__ __align__(16) unsigned char prod_smem[];
+        T* sb = reinterpret_cast<T*>(prod_smem);
+        const int kc = p.prod_kc, cols = (int)p.prod_cols;
+        const T* B = static_cast<const T*>(p.prod_b);
+        for (int e = threadIdx.x; e < cols * kc; e += EW_THREADS_FUSED) sb[(e % kc) * cols + e / kc] = B[e];
+        __syncthreads();
+        sBt = sb;
+        bcol = (int)((int64_t)(threadIdx.x * V) % p.prod_cols);  // (EW_THREADS_FUSED * V) % prod_cols == 0
+    }
     for (int64_t base = (int64_t)blockIdx.x * PER_BLOCK; base < p.n; base += (int64_t)gridDim.x * PER_BLOCK) {
         const int64_t i = base + threadIdx.x * V;
         bool ok[U];
@@ -404,7 +455,7 @@ __global__ void __launch_bounds__(EW_THREADS_FUSED) chain_backward_kernel(const 
         for (int u = 0; u < U; u++) ok[u] = i + u * (EW_THREADS_FUSED * V) < p.n;
         Lanes<T, V, U> x, g;
         ld_all<T, V, U>(static_cast<const T*>(p.in[0]) + i, ok, x);
-        chain_backward<T, V, U, 0, (int)sizeof...(OPS), OPS...>(p, x, g, i, ok);
+        chain_backward<T, V, U, PROD, 0, (int)sizeof...(OPS), OPS...>(p, x, g, i, ok, sBt, bcol);
         if (p.n_leafgrad > 0) st_all<T, V, U>(static_cast<T*>(p.lg[0].ptr) + i, ok, g);
         if constexpr (sizeof(T) == 4) {
             if (p.n_leafgrad > 0 && p.lg_small) {  // the TF32 small parts of what was just stored (tf32_split.cuh)
@@ -421,6 +472,9 @@ __global__ void __launch_bounds__(EW_THREADS_FUSED) chain_backward_kernel(const 
         }
     }
 }
+
+template <class T>
+size_t ew_product_smem(const EwProgram& p) { return sizeof(T) * (size_t)p.prod_cols * (size_t)p.prod_kc; }
 
 template <class K>
 int launch_chain(K kernel, const EwProgram& p, int v, int u, cudaStream_t stream, const char* what) {
@@ -447,11 +501,24 @@ int chain_go(const EwProgram& p, cudaStream_t stream) {
     constexpr int VN = Vec<T>::N;
     const char* what = BWD ? "elementwise chain backward" : "elementwise chain forward";
     if (p.n % VN != 0) {
-        if constexpr (BWD) return launch_chain(chain_backward_kernel<T, 1, 1, OPS...>, p, 1, 1, stream, what);
+        if constexpr (BWD) return launch_chain(chain_backward_kernel<T, 1, 1, false, OPS...>, p, 1, 1, stream, what);
         else return launch_chain(chain_forward_kernel<T, 1, 1, OPS...>, p, 1, 1, stream, what);
     }
-    if constexpr (BWD) return launch_chain(chain_backward_kernel<T, VN, 2, OPS...>, p, VN, 2, stream, what);
-    else return launch_chain(chain_forward_kernel<T, VN, 2, OPS...>, p, VN, 2, stream, what);
+    if constexpr (BWD) {
+        if (p.ops[p.n_ops - 1].g_init == EW_INIT_PRODUCT) {
+            // persistent: B is staged once per CTA
+            const int64_t per_block = (int64_t)EW_THREADS_FUSED * VN * 2;
+            int64_t blocks = (p.n + per_block - 1) / per_block;
+            if (blocks > 148 * 4) blocks = 148 * 4;
+            launch_k(chain_backward_kernel<T, VN, 2, true, OPS...>, dim3((unsigned)blocks), dim3(EW_THREADS_FUSED),
+                     ew_product_smem<T>(p), stream, p);
+            count_launch();
+            return check_launch("elementwise chain backward (product-fed)");
+        }
+        return launch_chain(chain_backward_kernel<T, VN, 2, false, OPS...>, p, VN, 2, stream, what);
+    } else {
+        return launch_chain(chain_forward_kernel<T, VN, 2, OPS...>, p, VN, 2, stream, what);
+    }
 }
 
 // The whitelist: every single rule, and the sigmoid of the reference's network examples.  *handled = false: interpret.
@@ -564,6 +631,18 @@ int launch_any(const EwProgram& p, cudaStream_t stream) {
 }  // namespace
 
 bool ew_backward_writes_small(const EwProgram& p) { return chain_whitelisted(p) && p.n_leafgrad == 1; }
+
+// the straight-line chain kernels with 16-byte vectors: every vector lies in one row, and a block's stride is a whole
+// number of rows (so a thread keeps its columns of B in registers)
+template <class T>
+bool ew_backward_takes_product(const EwProgram& p) {
+    constexpr int VN = Vec<T>::N;
+    return chain_whitelisted(p) && p.n % VN == 0 && p.prod_g && p.prod_b && p.prod_kc >= 1 && p.prod_kc <= EW_PROD_MAX_K &&
+           p.prod_cols > 0 && p.prod_cols % VN == 0 && (EW_THREADS_FUSED * VN) % p.prod_cols == 0 &&
+           ew_product_smem<T>(p) <= (size_t(32) << 10) && p.ops[p.n_ops - 1].g_src == EW_G_DIRECT;
+}
+template bool ew_backward_takes_product<float>(const EwProgram&);
+template bool ew_backward_takes_product<double>(const EwProgram&);
 
 template <class T>
 int launch_ew_forward(const EwProgram& p, cudaStream_t stream) { return launch_any<T, false>(p, stream); }

@@ -19,7 +19,8 @@ constexpr int EW_THREADS_FUSED = 256;
 enum : uint8_t { EW_SRC_NONE = 0, EW_SRC_PREV = 1, EW_SRC_SLOT = 2, EW_SRC_LEAF = 3 };
 enum : uint8_t { EW_TGT_NONE = 0, EW_TGT_SLOT = 1, EW_TGT_CARRY = 2 };
 enum : uint8_t { EW_G_DIRECT = 0, EW_G_SLOT = 1, EW_G_CARRY = 2 };  // where a node's own derivative is held
-enum : uint8_t { EW_INIT_ZERO = 0, EW_INIT_LOAD = 1, EW_INIT_SEED = 2 };  // what it starts from
+enum : uint8_t { EW_INIT_ZERO = 0, EW_INIT_LOAD = 1, EW_INIT_SEED = 2, EW_INIT_PRODUCT = 3 };  // what it starts from
+constexpr int EW_PROD_MAX_K = 16;  // EW_INIT_PRODUCT: longest contraction the backward kernels form on the fly
 
 // One op of a program.  The small fields are bit-fields of two 64-bit words: the kernels index ops[k] with a loop
 // variable, and a constant-bank load per field (the address-divergence pipe) was the top pipe of the first version.
@@ -72,8 +73,22 @@ struct EwProgram {
     // also store their TF32 small parts, element for element -- the plane the backward GEMM that reads these derivatives
     // as its B operand would otherwise compute in a pass of its own (tf32x3_reserve_small_plane_b)
     float* lg_small;
+    // EW_INIT_PRODUCT (the group's last node only): the node's output was the left operand of a product C = H * B with a
+    // short second extent (an output layer: H[8192 x 512] * W2[512 x 10]) and that product is its only consumer, so the
+    // derivatives the sweep owes it are dH = G * B^T with a contraction of prod_kc <= EW_PROD_MAX_K numbers.  The backward
+    // kernel forms them on the fly -- element (r, c) = fma chain over k ascending of G[r][k] * B[c][k] from +0, the
+    // arithmetic of the short-contraction kernel the sweep would otherwise launch -- instead of reading them from the
+    // arena: dH is neither written nor read, and the launch is saved.  prod_cols = row length of the group's containers.
+    const void* prod_g;
+    const void* prod_b;
+    int prod_kc;
+    int64_t prod_cols;
     EwOp ops[EW_MAX_OPS];
 };
+// true when launch_ew_backward<T>(p) runs a kernel that can form the last node's derivatives as that product
+// (p.prod_* filled in, ops[n_ops - 1].g_init not yet switched to EW_INIT_PRODUCT)
+template <class T>
+bool ew_backward_takes_product(const EwProgram& p);
 // true when launch_ew_backward<float>(p) runs a kernel that honours p.lg_small
 bool ew_backward_writes_small(const EwProgram& p);
 

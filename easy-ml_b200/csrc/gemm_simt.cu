@@ -406,14 +406,27 @@ template int launch_gemm_skinny_tn<double>(DeviceCtx*, const double*, const doub
 namespace {
 constexpr int SKR_ROWS = 4;
 
-template <class T, int N>
+// STAGED: B is first copied into shared memory.  A lane's slice of B (VEC rows = N 16-byte units) starts N units after its
+// neighbour's: read from global memory that is 32 different lines per load instruction (N x 32 wavefronts of the L1 per
+// step -- what bounded the first version: 9.7 us for H[8192 x 512] * W2[512 x 10]); in shared memory, with every slice
+// padded to an odd number of units, the same loads are conflict-free.  Persistent blocks stage B once.  Same operations in
+// the same order either way.
+template <class T, int N, bool STAGED>
 __global__ void __launch_bounds__(SK_THREADS)
 gemm_skinny_rows_kernel(const T* __restrict__ A, const T* __restrict__ B, T* C, int64_t M, int K, int64_t lda, Strides3 sC,
                         int accumulate) {
     pdl_prologue();
     constexpr int VEC = 16 / sizeof(T);
+    constexpr int NP = N | 1;  // units per slice in shared memory
     using V4 = typename std::conditional<sizeof(T) == 4, float4, double2>::type;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    extern __shared__ __align__(16) unsigned char skr_smem[];
+    V4* sB = reinterpret_cast<V4*>(skr_smem);
+    if constexpr (STAGED) {
+        const int units = (K / VEC) * N;
+        for (int u = threadIdx.x; u < units; u += SK_THREADS) sB[(u / N) * NP + u % N] = __ldg(reinterpret_cast<const V4*>(B) + u);
+        __syncthreads();
+    }
     const int steps = K / (32 * VEC);
     const int64_t groups = (M + SKR_ROWS - 1) / SKR_ROWS;
     for (int64_t grp = (int64_t)blockIdx.x * SK_WARPS + warp; grp < groups; grp += (int64_t)gridDim.x * SK_WARPS) {
@@ -430,9 +443,15 @@ gemm_skinny_rows_kernel(const T* __restrict__ A, const T* __restrict__ B, T* C, 
             for (int r = 0; r < SKR_ROWS; r++)
                 if (m0 + r < M) av[r] = *reinterpret_cast<const V4*>(A + (m0 + r) * lda + k0);
             V4 bv[N];  // B[k0 .. k0 + VEC)[0 .. N): VEC * N consecutive numbers
-            const V4* bp = reinterpret_cast<const V4*>(B + (int64_t)k0 * N);
+            if constexpr (STAGED) {
+                const V4* bp = sB + (s * 32 + lane) * NP;
 #pragma unroll
-            for (int q = 0; q < N; q++) bv[q] = __ldg(bp + q);
+                for (int q = 0; q < N; q++) bv[q] = bp[q];
+            } else {
+                const V4* bp = reinterpret_cast<const V4*>(B + (int64_t)k0 * N);
+#pragma unroll
+                for (int q = 0; q < N; q++) bv[q] = __ldg(bp + q);
+            }
             const T* be = reinterpret_cast<const T*>(bv);
 #pragma unroll
             for (int r = 0; r < SKR_ROWS; r++) {
@@ -463,8 +482,22 @@ template <class T, int N>
 int launch_skinny_rows(const T* A, const T* B, T* C, int64_t M, int64_t K, int64_t lda, Strides3 sC, bool accumulate,
                        cudaStream_t stream) {
     int64_t blocks = ((M + SKR_ROWS - 1) / SKR_ROWS + SK_WARPS - 1) / SK_WARPS;
+    constexpr int VEC = 16 / sizeof(T);
+    const size_t staged_bytes = (size_t)(K / VEC) * (N | 1) * 16;
+    static const bool staging = [] {
+        const char* e = getenv("EML_SKINNY_STAGED");  // =0: B through the L1 (comparison path, same bits)
+        return !(e && e[0] == '0');
+    }();
+    if (staging && staged_bytes <= (size_t(48) << 10) && blocks >= 8) {
+        if (blocks > 148 * 2) blocks = 148 * 2;  // persistent: B is staged once per block
+        launch_k(gemm_skinny_rows_kernel<T, N, true>, dim3((unsigned)blocks), dim3(SK_THREADS), staged_bytes, stream, A, B, C, M, (int)K,
+                 lda, sC, accumulate ? 1 : 0);
+        count_launch();
+        set_last_kernel("skinny_n");
+        return check_launch("gemm_skinny_rows");
+    }
     if (blocks > 148 * 4) blocks = 148 * 4;
-    launch_k(gemm_skinny_rows_kernel<T, N>, dim3((unsigned)blocks), dim3(SK_THREADS), 0, stream, A, B, C, M, (int)K, lda, sC,
+    launch_k(gemm_skinny_rows_kernel<T, N, false>, dim3((unsigned)blocks), dim3(SK_THREADS), 0, stream, A, B, C, M, (int)K, lda, sC,
              accumulate ? 1 : 0);
     count_launch();
     set_last_kernel("skinny_n");
@@ -603,6 +636,12 @@ splitk_reduce_2level_kernel(const T* __restrict__ ws, int splits, int per_range,
     *p = accumulate == 1 ? *p + acc : (accumulate == 2 ? T(0) + acc : acc);
 }
 }  // namespace
+
+bool splitk_reduce_is_sequential(int64_t total, int splits) {
+    if (total <= 65536 && splits >= 64 && (total + 255) / 256 <= 4096) return false;  // two-level
+    if (total <= 8192 && splits >= 16) return false;                                  // warp per element
+    return true;
+}
 
 template <class T>
 int launch_splitk_reduce(const T* ws, int splits, T* C, int64_t batch, int64_t M, int64_t N, Strides3 sC,

@@ -364,8 +364,8 @@ constexpr int GROUP_BYTES = 32 * BK * 4;    // MN-major tile: one group of 32 ro
 constexpr int STAGES = 3;
 constexpr int ACC_STAGES = 2;
 constexpr uint32_t TMEM_COLS = 512;         // 2 accumulator stages x 256 columns
-constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int EPI_WARPS = 8;                 // warp = (TMEM lane quarter, column half)
+constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int THREADS = (4 + EPI_WARPS) * 32;  // warpgroup 0: producer, MMA issuer, 2 idle; warpgroups 1-2: epilogue
 // 384 threads compile to <= 168 registers; the epilogue keeps 128 sums + 32 loaded values per thread, so the
 // register file is re-split with setmaxnreg: 4*32*40 + 8*32*232 = 64512 <= 65536
@@ -444,8 +444,17 @@ tf32x3_pair_kernel(const __grid_constant__ Maps maps, float* __restrict__ C, int
                    int64_t strideC, int kblocks_total, int kblocks_per_split, int splits, int tiles_m, int tiles_n,
                    int work_items, int accumulate, float* __restrict__ ws, int64_t ws_split_stride, const RepairArgs rep,
                    const EpilogueChain epi) {
-    pdl_prologue();
+    // programmatic dependent launch: barriers, TMEM and the descriptor prefetch are set up while the predecessor is still
+    // running; nothing it wrote is read before pdl_wait() below
+    pdl_launch_dependents();
     __shared__ unsigned repair_seen;
+#ifdef EML_PAIR_TIMING
+    __shared__ long long ts[16];
+    const long long t_entry = clock64();
+#define TS(i) do { if (blockIdx.x == EML_PAIR_TIMING) ts[i] = clock64() - t_entry; } while (0)
+#else
+#define TS(i) do { } while (0)
+#endif
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* full = reinterpret_cast<uint64_t*>(base + (size_t)STAGES * STAGE_BYTES);
@@ -458,11 +467,6 @@ tf32x3_pair_kernel(const __grid_constant__ Maps maps, float* __restrict__ C, int
     const uint32_t rank = cluster_ctarank();  // 0 = leader
     const int cluster = blockIdx.x >> 1, clusters = gridDim.x >> 1;
 
-    if (threadIdx.x == 32 && rep.A) {
-        repair_seen = ((rep.flag_a && *rep.flag_a) || (rep.flag_b && *rep.flag_b) || *rep.stream_flag) ? 1u : 0u;
-        __threadfence();
-        if (atomicInc(rep.ticket, gridDim.x - 1) == gridDim.x - 1) *rep.stream_flag = 0u;
-    }
     if (threadIdx.x == 0) {
         prefetch_tensormap(&maps.a_big);
         prefetch_tensormap(&maps.a_small);
@@ -480,10 +484,19 @@ tf32x3_pair_kernel(const __grid_constant__ Maps maps, float* __restrict__ C, int
     }
     __syncwarp();
     if (warp == 1) tmem_alloc_pair(tmem_slot, TMEM_COLS);
+    if (threadIdx.x == 0) TS(0);
+    pdl_wait();  // the predecessor has completed and flushed: global memory may be read from here on
+    if (threadIdx.x == 0) TS(1);
+    if (threadIdx.x == 32 && rep.A) {
+        repair_seen = ((rep.flag_a && *rep.flag_a) || (rep.flag_b && *rep.flag_b) || *rep.stream_flag) ? 1u : 0u;
+        __threadfence();
+        if (atomicInc(rep.ticket, gridDim.x - 1) == gridDim.x - 1) *rep.stream_flag = 0u;
+    }
     tc_fence_before();
     cluster_sync_all();  // barriers of BOTH CTAs are initialised before any remote arrive / multicast commit
     tc_fence_after();
     const uint32_t tmem_acc = *tmem_slot;
+    if (threadIdx.x == 0) TS(2);
 
     if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CONTROL_REGS));
     if (warp == 0) {
@@ -542,6 +555,8 @@ tf32x3_pair_kernel(const __grid_constant__ Maps maps, float* __restrict__ C, int
                     for (int kb = c0; kb < c1; kb++, n++) {
                         const int s = n % STAGES;
                         mbar_wait(&full[s], (n / STAGES) & 1);
+                        if (n == 0) TS(3);
+                        if (n == 3) TS(4);
                         tc_fence_after();
                         const uint32_t st = smem_u32(base + (size_t)s * STAGE_BYTES);
                         const uint32_t a_big = st, a_small = st + TILE_BYTES, b_big = st + 2 * TILE_BYTES, b_small = st + 3 * TILE_BYTES;
@@ -559,6 +574,7 @@ tf32x3_pair_kernel(const __grid_constant__ Maps maps, float* __restrict__ C, int
                         umma_commit_pair(&empty[s], 0b11);  // frees the stage in both CTAs
                     }
                     umma_commit_pair(&acc_full[as], 0b11);  // this chunk's partial is complete: wake both epilogues
+                    TS(5);
                 }
             }
         }
@@ -575,6 +591,7 @@ tf32x3_pair_kernel(const __grid_constant__ Maps maps, float* __restrict__ C, int
             for (int c0 = kb0; c0 < kb1; c0 += FLUSH_KB, it++) {
                 const int as = it & 1;
                 mbar_wait(&acc_full[as], (it >> 1) & 1);
+                if (threadIdx.x == 128) TS(6);
                 tc_fence_after();
                 const uint32_t t0 = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * PN + half * 128);
 #pragma unroll
@@ -593,6 +610,7 @@ tf32x3_pair_kernel(const __grid_constant__ Maps maps, float* __restrict__ C, int
                 tc_fence_before();  // the chunk is in registers: hand the accumulator stage back to the leader
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(&acc_empty[as], 0);
+                if (threadIdx.x == 128) TS(7);
             }
             // one store of the tile
             const int64_t row = (int64_t)wk.tm * PM + (int64_t)rank * HALF + q * 32 + lane;
@@ -631,6 +649,9 @@ tf32x3_pair_kernel(const __grid_constant__ Maps maps, float* __restrict__ C, int
                             if (col0 + j < N) p[j] = add ? p[j] + sum[c * 32 + j] : sum[c * 32 + j];
                     }
                 }
+            }
+            if (threadIdx.x == 128) TS(8);
+            if (row < M) {
                 if (rep.A && repair_seen) {  // rare: an operand held an Inf / NaN / >= 2^127 value
                     const float* a = rep.A + (int64_t)wk.batch * rep.sAb + row * rep.sAr;
                     float* crow = out + row * ld;
@@ -687,12 +708,18 @@ tf32x3_pair_kernel(const __grid_constant__ Maps maps, float* __restrict__ C, int
     tc_fence_before();
     cluster_sync_all();  // no CTA frees TMEM or exits while its peer may still address it
     if (warp == 1) tmem_dealloc_pair(tmem_acc, TMEM_COLS);
+#ifdef EML_PAIR_TIMING
+    if (threadIdx.x == 0 && blockIdx.x == EML_PAIR_TIMING)
+        printf("pair timing kb=%d: setup %lld wait %lld sync %lld | first full %lld 4th full %lld last commit %lld | last acc_full %lld drained %lld stored %lld | end %lld\n",
+               kblocks_per_split, ts[0], ts[1], ts[2], ts[3], ts[4], ts[5], ts[6], ts[7], ts[8], clock64() - t_entry);
+#endif
+#undef TS
 }
 
 int launch(const Maps& maps, float* C, int64_t batch, int64_t M, int64_t N, int64_t ldc, int64_t strideC, int kblocks,
            int splits, int sms, int accumulate /* ACC_*; ACC_ZERO_PLUS only with ws */, float* ws, cudaStream_t stream,
            bool upper_only = false, const RepairArgs* repair = nullptr, const EpilogueChain* epi = nullptr, bool a_kin = true,
-           bool b_kin = true) {
+           bool b_kin = true, bool skip_reduce = false) {
     static thread_local int configured_dev = -1;
     int dev = 0;
     EML_CUDA(cudaGetDevice(&dev));
@@ -723,7 +750,8 @@ int launch(const Maps& maps, float* C, int64_t batch, int64_t M, int64_t N, int6
              repair ? *repair : RepairArgs{}, epi ? *epi : EpilogueChain{});
     count_launch();
     EML_TRY(check_launch("tf32x3_tcgen05 (CTA pair)"));
-    if (ws) EML_TRY(launch_splitk_reduce<float>(ws, used_splits, C, batch, M, N, Strides3{strideC, ldc, 1}, accumulate, stream));
+    if (ws && !skip_reduce)
+        EML_TRY(launch_splitk_reduce<float>(ws, used_splits, C, batch, M, N, Strides3{strideC, ldc, 1}, accumulate, stream));
     return EML_OK;
 }
 
@@ -1208,8 +1236,18 @@ int launch_gemm_tf32x3_f32(DeviceCtx* ctx, const float* A, const float* B, float
                 opt->epilogue_done = true;
             }
         }
+        // the caller adds the partial sums itself (GemmOptions::defer_reduce): a first contribution to a dense C whose
+        // reduction would be the sequential kernel
+        const int used_splits = (kblocks + (kblocks + splits - 1) / splits - 1) / ((kblocks + splits - 1) / splits);
+        const bool defer = ws && opt && opt->defer_reduce && acc_mode != ACC_ADD && !upper_only && batch == 1 && sC.r == N &&
+                           used_splits > 1 && splitk_reduce_is_sequential(M * N, used_splits);
         EML_TRY(pair::launch(maps, C, batch, M, N, sC.r, sC.b, kblocks, splits, sms, acc_mode, ws, stream, upper_only,
-                             repair_folded ? &rep : nullptr, epi, a_kin, b_kin));
+                             repair_folded ? &rep : nullptr, epi, a_kin, b_kin, defer));
+        if (defer) {
+            opt->deferred_ws = wsbuf.p, opt->deferred_bytes = wsbuf.bytes;
+            opt->deferred_splits = used_splits, opt->deferred_stride = M * N;
+            wsbuf.p = nullptr;  // (ownership passes to the caller)
+        }
         if (upper_only) opt->upper_done = true;
     } else if (BN == 256) {
         EML_TRY(launch_tile<256>(maps, C, batch, M, N, sC.r, sC.b, kblocks, splits, acc_mode, ws, stream));

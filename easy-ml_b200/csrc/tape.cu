@@ -172,6 +172,18 @@ struct eml_derivs {
     bool slot0_pending = false;
     int slot0_n = 0;  // the parked sum is the in-order fold of this many slots at the head of the arena (see sweep_from)
     std::vector<std::vector<int64_t>> scatter_offsets;  // host copies of uploaded scatter targets (kept until freed)
+    // per node: the matmul node whose product G * B^T the sweep folded into this node's group kernel instead of storing
+    // it (ProductFeed), or -1; ensure_have launches that product when somebody asks for these derivatives after all
+    std::vector<int> fed_by;
+    // per node: its derivatives are still the partial sums of a split-K product (GemmOptions::defer_reduce) -- a leaf's
+    // weight gradient that nothing else contributes to.  The weight update adds them itself; any other reader gets them
+    // through ensure_have, which launches the reduction (0 + partials in split order: the same bits).
+    struct PendingReduce {
+        Buf ws;
+        int splits = 0;
+        int64_t stride = 0;
+    };
+    std::vector<PendingReduce> reduce;
 };
 
 struct eml_graph {
@@ -203,6 +215,9 @@ struct eml_tape {
         double lr;
         float* small = nullptr;          // f32: the small-part plane of the updated weights, and its flag word
         unsigned* small_flag = nullptr;
+        Buf ws;                          // d is still a deferred split-K reduction (eml_derivs::PendingReduce)
+        int ws_splits = 0;
+        int64_t ws_stride = 0;
     };
     std::vector<PendingSgd> sgd;
     // A product whose launch is deferred to the next flush: when the operators that follow it form a fused elementwise
@@ -221,6 +236,18 @@ struct eml_tape {
         int64_t M = 0, N = 0, K = 0;
     } mm;
     bool defer_matmul = false;
+    // EML_DEFER_REDUCE=1: a split-K weight gradient that only the weight update reads is left as partial sums, and the
+    // update adds them itself (eml_derivs::PendingReduce): one launch fewer, the same bits.  OPT-IN: measured 2 us SLOWER
+    // per NN step (0.1866 against 0.1844 ms) -- the launch that follows the CTA-pair GEMM pays the exposed transition
+    // either way (the GEMM's CTAs hold the whole register file, so nothing of the next kernel is resident early), and
+    // the update then carries the reduction's 14 MB of reads on top.
+    bool defer_reduce = false;
+    // EML_FEED_PRODUCTS=1: a short product of the sweep (dH = dY * W2^T of an output layer) is formed inside the backward
+    // kernel of the group it feeds instead of being launched (ProductFeed).  Built, bit-identical, tested -- and OPT-IN,
+    // because it measured slower on the NN step (0.188 ms against 0.184 ms): with the step's working set resident in the
+    // 126 MB L2 the group kernel is bound by instruction issue, not by the 32 MB of traffic the fusion saves, and the
+    // ten fma per element land on top of the recomputed activation.
+    bool feed_products = false;
     bool fuse_packs = true;  // EML_FUSE_PACKS=0: producers do not write small-part planes for the products that follow
     bool zero_plus = true;  // EML_ZERO_PLUS=0: products accumulate into zero-filled buffers (see matmul_overwrites)
     // a small asynchronous read-back requested while updates are queued rides in their launch (SgdBatch rider)
@@ -377,10 +404,32 @@ bool group_fits(const std::vector<Node>& nodes, const Group& g) {
 //   have[i]   : node i's FINAL derivatives are in the arena
 //   remat     : after the sweep, store the derivatives of the nodes the sweep kept in registers only; nothing outside
 //               the group is touched and nodes whose derivatives are final are read, not accumulated again
+// The derivatives a short product owes the group's last node, formed inside the group's backward kernel instead of by a
+// launch of their own (EwProgram::prod_*, EW_INIT_PRODUCT): G = derivatives of the product's output [rows x kc],
+// B = its right operand [cols x kc] row-major, cols = row length of the group's containers.
+struct ProductFeed {
+    const void* g = nullptr;
+    const void* b = nullptr;
+    int kc = 0;
+    int64_t cols = 0;
+    bool keep = false;  // somebody still holds the last node's container: its derivatives are stored as well
+};
+
+// can the backward kernel of group g take that product?  (decided before the product's launch is skipped)
+template <class T>
+bool group_takes_product(const std::vector<Node>& nodes, const Group& g, const ProductFeed& f, const std::vector<char>& written,
+                         int seed_node) {
+    if (written[g.last] || g.last == seed_node) return false;
+    EwProgram p;
+    if (!program_structure(nodes, g, &p)) return false;
+    p.prod_g = f.g, p.prod_b = f.b, p.prod_kc = f.kc, p.prod_cols = f.cols;
+    return ew_backward_takes_product<T>(p);
+}
+
 template <class T>
 int group_backward(const std::vector<Node>& nodes, const Group& g, const std::vector<Buf>& grads,
                    std::vector<char>& written, std::vector<char>& have, int seed_node, int64_t seed_elem, bool remat,
-                   cudaStream_t st, float* lg_small = nullptr, bool* small_written = nullptr) {
+                   cudaStream_t st, float* lg_small = nullptr, bool* small_written = nullptr, const ProductFeed* feed = nullptr) {
     EwProgram p;
     if (!program_structure(nodes, g, &p)) {
         set_error("internal: a fused elementwise group does not fit its program");
@@ -467,6 +516,16 @@ int group_backward(const std::vector<Node>& nodes, const Group& g, const std::ve
         set_error("internal: a fused elementwise group needs %d slots", p.n_slots);
         return EML_ERR_STATE;
     }
+    if (feed) {  // (group_takes_product said yes: the last node starts from nothing and a chain kernel runs)
+        p.prod_g = feed->g, p.prod_b = feed->b, p.prod_kc = feed->kc, p.prod_cols = feed->cols;
+        EwOp& last = p.ops[n_ops - 1];
+        if (remat || last.g_init != EW_INIT_ZERO || !ew_backward_takes_product<T>(p)) {
+            set_error("internal: a fused elementwise group cannot take the product it was promised");
+            return EML_ERR_STATE;
+        }
+        last.g_init = EW_INIT_PRODUCT;
+        last.g_store = feed->keep ? 1 : 0;
+    }
     bool anything = p.n_leafgrad > 0;
     for (int k = 0; k < n_ops; k++) anything |= p.ops[k].g_store != 0;
     if (lg_small && sizeof(T) == 4 && ew_backward_writes_small(p)) {
@@ -491,6 +550,7 @@ int flush_sgd(eml_tape* t) {
             const auto& u = t->sgd[j];
             const int y = b.count++;
             b.out[y] = u.out->p, b.w[y] = u.w->p, b.d[y] = u.d, b.slot0[y] = u.slot0, b.slot0_n[y] = u.slot0_n, b.n[y] = u.n, b.lr[y] = u.lr;
+            b.ws[y] = u.ws ? u.ws->p : nullptr, b.ws_splits[y] = u.ws_splits, b.ws_stride[y] = u.ws_stride;
             b.small[y] = u.small, b.small_flag[y] = u.small_flag;
         }
         EML_TRY(stream_tickets(t->stream, &b.tickets));
@@ -1091,6 +1151,9 @@ int sweep_from(eml_tape* t, int nv, int64_t seed_elem, eml_derivs** out) {
     // derivatives as its right operand (per matmul node: the cache identity, 0 = none)
     std::vector<uint64_t> presmall(n_nodes, 0);
     std::vector<char> written(n_nodes, 0);
+    d->fed_by.assign(n_nodes, -1);
+    d->reduce.assign(n_nodes, eml_derivs::PendingReduce{});
+    std::vector<ProductFeed> feeds(n_nodes);  // per group-last node: the product its kernel forms itself (see ProductFeed)
     bool seed_in_kernel = false;
     for (int i = 0; i < n_nodes; i++) {
         const int c = first_consumer[i];
@@ -1224,7 +1287,8 @@ int sweep_from(eml_tape* t, int nv, int64_t seed_elem, eml_derivs** out) {
                 }
             }
             bool small_written = false;
-            EML_TRY(group_backward<T>(t->nodes, grp, d->grads, written, d->have, nv, seed_elem, false, st, lg_small, &small_written));
+            EML_TRY(group_backward<T>(t->nodes, grp, d->grads, written, d->have, nv, seed_elem, false, st, lg_small, &small_written,
+                                      d->fed_by[grp.last] >= 0 ? &feeds[grp.last] : nullptr));
             if (gid) {
                 if (small_written) presmall[par] = gid;
                 else pack_cache_drop(gid);
@@ -1296,7 +1360,26 @@ int sweep_from(eml_tape* t, int nv, int64_t seed_elem, eml_derivs** out) {
             const int which = (a_on_side && nd.p0 < 0) || (b_on_side && nd.p1 < 0) ? 1 : 0;
             if (a_on_side || b_on_side) EML_TRY(fork(which));
             const cudaStream_t sa = a_on_side ? t->side[which] : st, sb = b_on_side ? t->side[which] : st;
-            if (nd.p0 >= 0) {
+            // dA = G * B^T with a short contraction, owed to the last node of a fused group that nothing else contributes
+            // to: the group's backward kernel forms it on the fly (no launch, dA neither written nor read)
+            bool a_fed = false;
+            if (t->feed_products && nd.p0 >= 0 && nd.p0 != nd.p1 && !a_on_side && !written[nd.p0] && nd.p0 != nv &&
+                first_consumer[nd.p0] == i && lowest_consumer[nd.p0] == i && N <= EW_PROD_MAX_K && smallk_shape(M, K, N, sizeof(T))) {
+                const Node& pn = t->nodes[nd.p0];
+                if (pn.group >= 0 && t->groups[pn.group].last == nd.p0 && t->groups[pn.group].n == M * K) {
+                    ProductFeed f;
+                    f.g = g, f.b = B, f.kc = (int)N, f.cols = K;
+                    for (const Value& v : t->values) f.keep |= v.alive && v.node == nd.p0 && v.epoch == t->epoch;
+                    if (group_takes_product<T>(t->nodes, t->groups[pn.group], f, written, nv)) {
+                        feeds[nd.p0] = f;
+                        d->fed_by[nd.p0] = i;
+                        a_fed = true;
+                    }
+                }
+            }
+            if (a_fed) {
+                // (nothing to launch)
+            } else if (nd.p0 >= 0) {
                 GemmOptions ids;
                 ids.b_id = nd.b->identity;
                 ids.zero_plus = !written[nd.p0];  // the first contribution: 0 + product, nobody cleared the buffer
@@ -1314,9 +1397,20 @@ int sweep_from(eml_tape* t, int nv, int64_t seed_elem, eml_derivs** out) {
                 ids.a_id = nd.a->identity;
                 ids.b_id = sb == st ? presmall[i] : 0;  // the small parts of g, written by the group that produced g
                 ids.zero_plus = !written[nd.p1];
+                // a leaf's gradient nothing else contributes to, on this stream: a split-K launch may leave its partial
+                // sums to the weight update (PendingReduce)
+                ids.defer_reduce = t->defer_reduce && leaf1 && ids.zero_plus && sb == st && first_consumer[nd.p1] == i &&
+                                   lowest_consumer[nd.p1] == i && nd.p1 != nv;
                 written[nd.p1] = 1;
                 EML_TRY(contract_dev<T>(t->ctx, A, g, (T*)d->grads[nd.p1]->p, 1, K, N, M, Strides3{0, 1, K},
                                         Strides3{0, N, 1}, Strides3{0, N, 1}, true, false, sb, &ids));
+                if (ids.deferred_ws) {
+                    auto wsb = std::make_shared<DevBuf>();
+                    wsb->p = ids.deferred_ws, wsb->bytes = ids.deferred_bytes, wsb->s = sb;
+                    d->reduce[nd.p1].ws = wsb;
+                    d->reduce[nd.p1].splits = ids.deferred_splits;
+                    d->reduce[nd.p1].stride = ids.deferred_stride;
+                }
                 if (b_on_side) side_busy[nd.p1] = 1;
             } else {
                 // derivatives[0] += sum_kj (A^T G)[k,j] = sum_i rowsum(A)[i] * rowsum(G)[i]
@@ -1358,6 +1452,8 @@ int eml_tape_create(int dtype, eml_tape** out) {
     if (const char* e = getenv("EML_FUSE")) t->fuse = !(e[0] == '0');
     if (const char* e = getenv("EML_EPILOGUE")) t->defer_matmul = e[0] == '1';
     if (const char* e = getenv("EML_ZERO_PLUS")) t->zero_plus = !(e[0] == '0');
+    if (const char* e = getenv("EML_FEED_PRODUCTS")) t->feed_products = e[0] == '1';
+    if (const char* e = getenv("EML_DEFER_REDUCE")) t->defer_reduce = e[0] == '1';
     if (const char* e = getenv("EML_FUSE_PACKS")) t->fuse_packs = !(e[0] == '0');
     const char* se = getenv("EML_SIDE");
     if (!(se && se[0] == '0')) {
@@ -1882,9 +1978,39 @@ int eml_derivs_len(eml_derivs* d, int64_t* len) {
 
 // Derivatives of a node the sweep kept in registers only (interior of a fused elementwise group, no container held):
 // run the group's backward program once more, storing them (nothing else is touched).
+// the deferred split-K reduction of a weight gradient (eml_derivs::PendingReduce), launched for a reader other than the
+// weight update
+static int materialise_reduce(eml_derivs* d, int n) {
+    if (n < 0 || n >= (int)d->reduce.size() || !d->reduce[n].ws) return EML_OK;
+    eml_derivs::PendingReduce& r = d->reduce[n];
+    const int64_t cnt = d->nodes[n].n;
+    if (d->dtype == EML_F32)
+        EML_TRY(launch_splitk_reduce<float>((const float*)r.ws->p, r.splits, (float*)d->grads[n]->p, 1, 1, cnt, Strides3{cnt, cnt, 1},
+                                            ACC_ZERO_PLUS, d->stream));
+    else
+        EML_TRY(launch_splitk_reduce<double>((const double*)r.ws->p, r.splits, (double*)d->grads[n]->p, 1, 1, cnt, Strides3{cnt, cnt, 1},
+                                             ACC_ZERO_PLUS, d->stream));
+    r.ws.reset();
+    return EML_OK;
+}
+
 static int ensure_have(eml_derivs* d, int n) {
+    EML_TRY(materialise_reduce(d, n));
     if (d->have[n]) return EML_OK;
     const Group& g = d->groups[d->nodes[n].group];
+    if (!d->have[g.last] && g.last < (int)d->fed_by.size() && d->fed_by[g.last] >= 0) {
+        // the product the sweep folded into this group's kernel (ProductFeed): launched now, the same fma chains from +0
+        const Node& mm = d->nodes[d->fed_by[g.last]];
+        const void* G = d->grads[d->fed_by[g.last]]->p;
+        if (d->dtype == EML_F32)
+            EML_TRY(contract_dev<float>(d->tape->ctx, (const float*)G, (const float*)mm.b->p, (float*)d->grads[g.last]->p, 1, mm.M, mm.K, mm.N,
+                                        Strides3{0, mm.N, 1}, Strides3{0, 1, mm.N}, Strides3{0, mm.K, 1}, false, false, d->stream));
+        else
+            EML_TRY(contract_dev<double>(d->tape->ctx, (const double*)G, (const double*)mm.b->p, (double*)d->grads[g.last]->p, 1, mm.M, mm.K,
+                                         mm.N, Strides3{0, mm.N, 1}, Strides3{0, 1, mm.N}, Strides3{0, mm.K, 1}, false, false, d->stream));
+        d->have[g.last] = 1;
+        if (d->have[n]) return EML_OK;
+    }
     std::vector<char> written(d->have);
     if (d->dtype == EML_F32) return group_backward<float>(d->nodes, g, d->grads, written, d->have, -1, -1, true, d->stream);
     return group_backward<double>(d->nodes, g, d->grads, written, d->have, -1, -1, true, d->stream);
@@ -1892,6 +2018,7 @@ static int ensure_have(eml_derivs* d, int n) {
 
 static int fold_slot0(eml_derivs* d) {
     if (!d->slot0_pending) return EML_OK;
+    EML_TRY(materialise_reduce(d, 0));  // (the parked sums are added to element 0 of node 0: its numbers come first)
     EML_TRY(flush(d->tape));  // a queued weight update reads derivatives[0] and the parked sum separately
     d->slot0_pending = false;
     if (d->dtype == EML_F32) return launch_fold_slots<float>((float*)d->grads[0]->p, (const float*)d->arena->p, d->slot0_n, false, d->stream);
@@ -2038,7 +2165,8 @@ int eml_tape_sgd_update(eml_tape* t, eml_val hw, eml_derivs* d, double lr) {
         set_error("sgd_update: container is not a tracked variable of the computation these derivatives belong to");
         return EML_ERR_STATE;
     }
-    EML_TRY(ensure_have(d, w->node));
+    const bool deferred = w->node < (int)d->reduce.size() && d->reduce[w->node].ws != nullptr;
+    if (!deferred) EML_TRY(ensure_have(d, w->node));
     const int64_t n = w->n();
     size_t es = esize(t->dtype);
     // x - (derivatives[&x] * lr): Record - T => append_unary(x.index, 1) per element (nd.a stays null = derivative 1)
@@ -2063,6 +2191,7 @@ int eml_tape_sgd_update(eml_tape* t, eml_val hw, eml_derivs* d, double lr) {
                                              &u.small_flag));
     }
     u.arena = d->arena;
+    if (deferred) u.ws = d->reduce[w->node].ws, u.ws_splits = d->reduce[w->node].splits, u.ws_stride = d->reduce[w->node].stride;
     u.d = d->grads[w->node]->p;
     u.slot0 = (d->slot0_pending && w->node == 0) ? d->arena->p : nullptr;  // derivatives[0] + the parked sums, on the fly
     u.slot0_n = d->slot0_n;

@@ -339,3 +339,104 @@ def test_producers_write_the_small_part_planes_of_the_next_product(recorded):
     for a, b in zip(fused[:3], plain[:3]):
         assert same_bits(a, b)
     assert fused[3] == plain[3] - 2, f"{fused[3]} launches per step with producer-written planes, {plain[3]} without"
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("n,i,h,o,hold", [
+    (256, 64, 256, 10, False),   # the NN step's pattern in small: sigmoid(X W1) W2, row length 256
+    (256, 64, 256, 10, True),    # ... with the hidden activations still held (their derivatives are stored as well)
+    (192, 48, 512, 16, False),   # longest contraction the kernels form on the fly
+    (130, 40, 128, 3, False),    # ragged row count
+])
+def test_short_products_of_the_sweep_ride_in_the_group_kernel(dtype, n, i, h, o, hold):
+    """dH = dY W2^T of an output layer (contraction of <= 16 numbers) is owed to the last node of the activation's fused
+    group and to nothing else: the group's backward kernel forms it on the fly instead of reading it from the arena, the
+    product is not launched and dH is not stored (csrc/tape.cu ProductFeed, csrc/ew_fused.cu EW_INIT_PRODUCT).  Every
+    derivative -- including the ones of the hidden activations, materialised on demand by Vec::from(Derivatives) -- must
+    carry the bits of the sweep that launches the product (EML_FEED_PRODUCTS=0); one launch fewer."""
+    r = np.random.default_rng(23)
+    x = r.uniform(0, 1, (n, i)).astype(dtype)
+    w1 = r.uniform(-0.3, 0.3, (i, h)).astype(dtype)
+    w2 = r.uniform(-0.3, 0.3, (h, o)).astype(dtype)
+
+    def program(hist):
+        W1 = eml.RecordTensor.variables(hist, T("ih", w1))
+        W2 = eml.RecordTensor.variables(hist, T("ho", w2))
+        X = eml.RecordTensor.constants(T("ni", x), hist)
+        hidden = sigmoid(X * W1)
+        y = hidden * W2
+        if not hold:
+            del hidden
+        out = y.elementwise_multiply(y) - y
+        before = eml.kernel_launches()
+        d = out.derivatives_for([n - 1, o // 2])
+        launches = eml.kernel_launches() - before
+        res = {"g1": d.at_tensor(W1).data, "g2": d.at_tensor(W2).data}
+        if hold:
+            res["gh"] = d.at_tensor(hidden).data
+        res["all"] = d.to_vec()
+        return res, launches
+
+    (a, la), (b, lb) = program(tape_env(dtype, EML_FEED_PRODUCTS=1)), program(tape_env(dtype, EML_FEED_PRODUCTS=0))  # (opt-in)
+    for k in a:
+        assert same_bits(a[k], b[k]), f"{k}: the product formed inside the group kernel differs from the launched one"
+    # (a block's stride must be a whole number of rows: 256 threads x one 16-byte vector)
+    folded = (256 * (16 // np.dtype(dtype).itemsize)) % h == 0 and np.dtype(dtype).itemsize * h * o <= 32768
+    assert la == lb - (1 if folded else 0), f"{la} launches with the product folded in, {lb} without"
+
+
+@pytest.mark.parametrize("recorded", [False, True])
+def test_split_k_weight_gradient_is_reduced_by_the_weight_update(recorded):
+    """f32: dW1 = X^T dZ of a wide layer runs split-K on the CTA-pair kernel; when nothing else contributes to W1's
+    derivatives the product leaves its partial sums to the reader (GemmOptions::defer_reduce): the weight update adds them
+    in split order itself -- one launch fewer -- and at_tensor launches the reduction on demand.  Same bits as the
+    product reducing them itself (the default, EML_DEFER_REDUCE=0: the deferred form measured slower), eagerly and as a
+    recorded step."""
+    r = np.random.default_rng(29)
+    n, i, h, o = 2048, 300, 512, 10
+    x = r.uniform(0, 1, (n, i)).astype(np.float32)
+    lab = np.eye(o, dtype=np.float32)[r.integers(0, o, n)]
+    w1 = r.uniform(-0.1, 0.1, (i, h)).astype(np.float32)
+    w2 = r.uniform(-0.1, 0.1, (h, o)).astype(np.float32)
+
+    def run(defer):
+        hist = tape_env(np.float32, EML_DEFER_REDUCE=1 if defer else 0)
+        W1 = eml.RecordTensor.variables(hist, T("ih", w1))
+        W2 = eml.RecordTensor.variables(hist, T("ho", w2))
+        X = eml.RecordTensor.constants(T("ni", x), hist)
+        Y = eml.RecordTensor.constants(T("no", lab), hist)
+        seen = {}
+
+        def body(read_gradients=False):
+            out = sigmoid(sigmoid(X * W1) * W2)
+            diff = out - Y
+            loss = diff.elementwise_multiply(diff)
+            d = loss.derivatives_for([n // 2, 3])
+            if read_gradients:  # readers other than the weight update: the reduction is launched on demand
+                seen["g1"] = d.at_tensor(W1).data
+                seen["all"] = d.at_tensor(W2).data
+            eml.sgd_update(W1, d, 0.5)
+            eml.sgd_update(W2, d, 0.5)
+            del out, diff, loss, d
+            hist.clear()
+            W1.reset()
+            W2.reset()
+
+        body(read_gradients=True)
+        before = eml.kernel_launches()
+        if recorded:
+            step = hist.record(lambda: body())
+            per_step = eml.kernel_launches() - before
+            for _ in range(3):
+                step.launch()
+        else:
+            body()
+            per_step = eml.kernel_launches() - before
+            for _ in range(2):
+                body()
+        return seen["g1"], seen["all"], W1.numbers().data, W2.numbers().data, per_step
+
+    a, b = run(True), run(False)
+    for u, v in zip(a[:4], b[:4]):
+        assert same_bits(u, v)
+    assert a[4] == b[4] - 1, f"{a[4]} launches per step with the deferred reduction, {b[4]} without"
