@@ -443,7 +443,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 tf32x3_pair_kernel(const __grid_constant__ Maps maps, float* __restrict__ C, int64_t M, int64_t N, int64_t ldc,
                    int64_t strideC, int kblocks_total, int kblocks_per_split, int splits, int tiles_m, int tiles_n,
                    int work_items, int accumulate, float* __restrict__ ws, int64_t ws_split_stride, const RepairArgs rep,
-                   const EpilogueChain epi) {
+                   const EpilogueChain epi, int tile_w) {
     // programmatic dependent launch: barriers, TMEM and the descriptor prefetch are set up while the predecessor is still
     // running; nothing it wrote is read before pdl_wait() below
     pdl_launch_dependents();
@@ -507,7 +507,9 @@ tf32x3_pair_kernel(const __grid_constant__ Maps maps, float* __restrict__ C, int
                 const Work wk = decode(w, tiles_m, tiles_n, splits);
                 const int kb0 = wk.split * kblocks_per_split;
                 const int kb1 = min(kblocks_total, kb0 + kblocks_per_split);
-                const int row_a = wk.tm * PM + (int)rank * HALF, row_b = wk.tn * PN + (int)rank * HALF;
+                // (a tile of tile_w <= 256 columns: this CTA's half of B starts tile_w / 2 rows into it; the box still brings
+                //  128 rows, of which the MMA reads the first tile_w / 2)
+                const int row_a = wk.tm * PM + (int)rank * HALF, row_b = wk.tn * tile_w + (int)rank * (tile_w >> 1);
                 for (int kb = kb0; kb < kb1; kb++, n++) {
                     const int s = n % STAGES;
                     if (n >= STAGES) mbar_wait(&empty[s], ((n / STAGES) - 1) & 1);
@@ -540,7 +542,7 @@ tf32x3_pair_kernel(const __grid_constant__ Maps maps, float* __restrict__ C, int
     } else if (warp == 1) {
         // ---------------- MMA issuer (leader CTA only) ----------------
         if (rank == 0 && lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_tf32(PM, PN) | (A_KIN ? 0u : UMMA_IDESC_A_MN) | (B_KIN ? 0u : UMMA_IDESC_B_MN);
+            const uint32_t idesc = umma_idesc_tf32(PM, tile_w) | (A_KIN ? 0u : UMMA_IDESC_A_MN) | (B_KIN ? 0u : UMMA_IDESC_B_MN);
             int n = 0, it = 0;  // it counts accumulator uses (one per k chunk)
             for (int w = cluster; w < work_items; w += clusters) {
                 const Work wk = decode(w, tiles_m, tiles_n, splits);
@@ -614,7 +616,9 @@ tf32x3_pair_kernel(const __grid_constant__ Maps maps, float* __restrict__ C, int
             }
             // one store of the tile
             const int64_t row = (int64_t)wk.tm * PM + (int64_t)rank * HALF + q * 32 + lane;
-            const int64_t n0 = (int64_t)wk.tn * PN + half * 128;
+            const int64_t n0 = (int64_t)wk.tn * tile_w + half * 128;
+            // columns of this 128-column half that belong to the tile and to the matrix
+            const int64_t n_end = min((int64_t)(wk.tn + 1) * tile_w, N);
             float* out;
             int64_t ld;
             if (ws) {
@@ -630,9 +634,9 @@ tf32x3_pair_kernel(const __grid_constant__ Maps maps, float* __restrict__ C, int
 #pragma unroll
                 for (int c = 0; c < 4; c++) {
                     const int64_t col0 = n0 + c * 32;
-                    if (col0 >= N) continue;
+                    if (col0 >= n_end) continue;
                     float* p = out + row * ld + col0;
-                    if (vec_ok && col0 + 32 <= N) {
+                    if (vec_ok && col0 + 32 <= n_end) {
 #pragma unroll
                         for (int j = 0; j < 8; j++) {
                             float4 o = make_float4(sum[c * 32 + 4 * j], sum[c * 32 + 4 * j + 1], sum[c * 32 + 4 * j + 2],
@@ -646,7 +650,7 @@ tf32x3_pair_kernel(const __grid_constant__ Maps maps, float* __restrict__ C, int
                     } else {
 #pragma unroll
                         for (int j = 0; j < 32; j++)
-                            if (col0 + j < N) p[j] = add ? p[j] + sum[c * 32 + j] : sum[c * 32 + j];
+                            if (col0 + j < n_end) p[j] = add ? p[j] + sum[c * 32 + j] : sum[c * 32 + j];
                     }
                 }
             }
@@ -654,13 +658,13 @@ tf32x3_pair_kernel(const __grid_constant__ Maps maps, float* __restrict__ C, int
             if (row < M) {
                 if (rep.A && repair_seen) {  // rare: an operand held an Inf / NaN / >= 2^127 value
                     const float* a = rep.A + (int64_t)wk.batch * rep.sAb + row * rep.sAr;
-                    float* crow = out + row * ld;
-                    for (int64_t col = n0; col < n0 + 128 && col < N; col++) {
-                        if (crow[col] == crow[col]) continue;  // only NaNs can be artefacts of the split
+                    for (int64_t col = n0; col < n0 + 128 && col < n_end; col++) {
+                        float* pc = out + row * ld + col;
+                        if (*pc == *pc) continue;  // only NaNs can be artefacts of the split
                         const float* bb = rep.B + (int64_t)wk.batch * rep.sBb + col * rep.sBc;
                         float acc = 0.0f;
                         for (int64_t k = 0; k < rep.K; k++) acc = fmaf(a[k * rep.sAc], bb[k * rep.sBr], acc);
-                        crow[col] = acc;
+                        *pc = acc;
                     }
                 }
                 if constexpr (EPI == 1) {
@@ -719,12 +723,13 @@ tf32x3_pair_kernel(const __grid_constant__ Maps maps, float* __restrict__ C, int
 int launch(const Maps& maps, float* C, int64_t batch, int64_t M, int64_t N, int64_t ldc, int64_t strideC, int kblocks,
            int splits, int sms, int accumulate /* ACC_*; ACC_ZERO_PLUS only with ws */, float* ws, cudaStream_t stream,
            bool upper_only = false, const RepairArgs* repair = nullptr, const EpilogueChain* epi = nullptr, bool a_kin = true,
-           bool b_kin = true, bool skip_reduce = false) {
+           bool b_kin = true, bool skip_reduce = false, int tile_w = PN) {
+    // tile_w: columns of a work item's tile (a multiple of 16, <= 256)
     static thread_local int configured_dev = -1;
     int dev = 0;
     EML_CUDA(cudaGetDevice(&dev));
     using Kernel = void (*)(const Maps, float*, int64_t, int64_t, int64_t, int64_t, int, int, int, int, int, int, int, float*, int64_t,
-                            const RepairArgs, const EpilogueChain);
+                            const RepairArgs, const EpilogueChain, int);
     static const Kernel kernels[2][2][2] = {
         {{tf32x3_pair_kernel<0, false, false>, tf32x3_pair_kernel<0, false, true>},
          {tf32x3_pair_kernel<0, true, false>, tf32x3_pair_kernel<0, true, true>}},
@@ -737,7 +742,8 @@ int launch(const Maps& maps, float* C, int64_t batch, int64_t M, int64_t N, int6
                     EML_CUDA(cudaFuncSetAttribute(kernels[e][a][b], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
         configured_dev = dev;
     }
-    const int tiles_m = (int)((M + PM - 1) / PM), tiles_n = upper_only ? 0 : (int)((N + PN - 1) / PN);
+    if (upper_only || epi) tile_w = PN;  // (the host never combines these with narrow tiles)
+    const int tiles_m = (int)((M + PM - 1) / PM), tiles_n = upper_only ? 0 : (int)((N + tile_w - 1) / tile_w);
     const int per_split = (kblocks + splits - 1) / splits;
     const int used_splits = (kblocks + per_split - 1) / per_split;
     const int64_t tiles = upper_only ? (int64_t)tiles_m * (tiles_m + 1) / 2 : (int64_t)tiles_m * tiles_n;
@@ -747,7 +753,7 @@ int launch(const Maps& maps, float* C, int64_t batch, int64_t M, int64_t N, int6
     if (items < clusters) clusters = (int)items;
     launch_k(kernels[epi ? 1 : 0][a_kin ? 1 : 0][b_kin ? 1 : 0], dim3(2 * clusters), dim3(THREADS), SMEM_BYTES, stream, maps, C, M, N, ldc,
              strideC, kblocks, per_split, used_splits, tiles_m, tiles_n, (int)items, accumulate == ACC_ADD ? 1 : 0, ws, batch * M * N,
-             repair ? *repair : RepairArgs{}, epi ? *epi : EpilogueChain{});
+             repair ? *repair : RepairArgs{}, epi ? *epi : EpilogueChain{}, tile_w);
     count_launch();
     EML_TRY(check_launch("tf32x3_tcgen05 (CTA pair)"));
     if (ws && !skip_reduce)
@@ -1153,6 +1159,44 @@ int launch_gemm_tf32x3_f32(DeviceCtx* ctx, const float* A, const float* B, float
             }
         }
     }
+    // ---- tile width of the CTA-pair kernel (one batch, no epilogue extras) ----
+    // The pair kernel's M tile is fixed (2 x 128 rows); its N tile is whatever the MMA's N field says, a multiple of 16
+    // up to 256.  When the output is a few waves of work, narrower tiles can mean less MMA issue time for the busiest
+    // CTA pair: 300 columns are two tiles of 160 instead of 256 + 44 (zero padding multiplied for nothing), 784 columns
+    // four of 208.  The width with the least  waves x k blocks x width  wins when it beats 256 by 8 % WITHOUT changing
+    // the split-K partition -- every element's accumulation chain is then what it was, so the bits are those of the
+    // plain tiling (and of the in-kernel-split kernel, which always uses it).  Measured: 1000 x 300 x 2048 30.1 -> 26.2 us,
+    // 4096 x 784 x 512 32.6 -> 30.6 us (scripts/probe/balance_ab.py).  EML_SGEMM_BALANCE=0: always 256.
+    // (Also tried: running C^T = B^T A^T when the ragged extent is M -- X^T dZ of the NN step pads 784 rows to 1024 --
+    //  with the tile stored transposed.  4 and 3 us faster for the step's two big products on their own, 5 us SLOWER
+    //  inside the step, and different bits than the in-kernel-split kernel; not kept.)
+    int tile_w = pair::PN;
+    if (use_pair && !upper_only && batch == 1 && !(opt && opt->epilogue)) {
+        const char* be = getenv("EML_SGEMM_BALANCE");
+        if (!(be && be[0] == '0')) {
+            const int clusters = sms / 2;
+            auto plan = [&](int w, int* sp_out) {
+                const int64_t tiles = ((M + pair::PM - 1) / pair::PM) * ((N + w - 1) / w);
+                int sp = 1;
+                if (tiles * 2 <= clusters && kblocks >= 8) {
+                    sp = (int)(clusters / tiles);
+                    if (sp > kblocks / 4) sp = kblocks / 4;
+                    if (sp < 1) sp = 1;
+                }
+                const int per = (kblocks + sp - 1) / sp, used = (kblocks + per - 1) / per;
+                const int64_t waves = (tiles * used + clusters - 1) / clusters;
+                *sp_out = sp;
+                return (double)waves * per * w;
+            };
+            int sp0 = 1;
+            double best = plan(pair::PN, &sp0) * 0.92;
+            for (int w = pair::PN - 16; w >= 128; w -= 16) {
+                int sp = 1;
+                const double c = plan(w, &sp);
+                if (sp == sp0 && c < best) best = c, tile_w = w;
+            }
+        }
+    }
     int acc_mode = accumulate ? ACC_ADD : ACC_WRITE;
     if (zero_plus && !zeroed) {
         if (splits > 1) acc_mode = ACC_ZERO_PLUS;
@@ -1242,7 +1286,7 @@ int launch_gemm_tf32x3_f32(DeviceCtx* ctx, const float* A, const float* B, float
         const bool defer = ws && opt && opt->defer_reduce && acc_mode != ACC_ADD && !upper_only && batch == 1 && sC.r == N &&
                            used_splits > 1 && splitk_reduce_is_sequential(M * N, used_splits);
         EML_TRY(pair::launch(maps, C, batch, M, N, sC.r, sC.b, kblocks, splits, sms, acc_mode, ws, stream, upper_only,
-                             repair_folded ? &rep : nullptr, epi, a_kin, b_kin, defer));
+                             repair_folded ? &rep : nullptr, epi, a_kin, b_kin, defer, tile_w));
         if (defer) {
             opt->deferred_ws = wsbuf.p, opt->deferred_bytes = wsbuf.bytes;
             opt->deferred_splits = used_splits, opt->deferred_stride = M * N;
