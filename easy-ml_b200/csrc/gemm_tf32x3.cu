@@ -1163,7 +1163,7 @@ int launch_gemm_tf32x3_f32(DeviceCtx* ctx, const float* A, const float* B, float
     // The pair kernel's M tile is fixed (2 x 128 rows); its N tile is whatever the MMA's N field says, a multiple of 16
     // up to 256.  When the output is a few waves of work, narrower tiles can mean less MMA issue time for the busiest
     // CTA pair: 300 columns are two tiles of 160 instead of 256 + 44 (zero padding multiplied for nothing), 784 columns
-    // four of 208.  The width with the least  waves x k blocks x width  wins when it beats 256 by 8 % WITHOUT changing
+    // four of 208.  For outputs of ONE wave, the width with the least  k blocks x width  wins when it beats 256 by 8 % WITHOUT changing
     // the split-K partition -- every element's accumulation chain is then what it was, so the bits are those of the
     // plain tiling (and of the in-kernel-split kernel, which always uses it).  Measured: 1000 x 300 x 2048 30.1 -> 26.2 us,
     // 4096 x 784 x 512 32.6 -> 30.6 us (scripts/probe/balance_ab.py).  EML_SGEMM_BALANCE=0: always 256.
@@ -1186,7 +1186,9 @@ int launch_gemm_tf32x3_f32(DeviceCtx* ctx, const float* A, const float* B, float
                 const int per = (kblocks + sp - 1) / sp, used = (kblocks + per - 1) / per;
                 const int64_t waves = (tiles * used + clusters - 1) / clusters;
                 *sp_out = sp;
-                return (double)waves * per * w;
+                // one wave only: with several tiles per CTA pair the narrower ones lose more to operand re-reads than
+                // they save in padding (4096^3 with 240-column tiles: 553 -> 700 us)
+                return waves == 1 ? (double)per * w : 1e30;
             };
             int sp0 = 1;
             double best = plan(pair::PN, &sp0) * 0.92;

@@ -18,7 +18,8 @@ def timeit(f, reps=50):
 os.environ["EML_SGEMM_FUSED"] = "0"
 shapes = [("fwd 8192x512x784", 8192, 512, 784, False), ("dW1 784x512x8192 (A^T)", 784, 512, 8192, True), ("1000x300x2048", 1000, 300, 2048, False),
           ("300x1000x512 (A^T)", 300, 1000, 512, True), ("520x260x300", 520, 260, 300, False), ("2000x2000x256", 2000, 2000, 256, False),
-          ("4096x784x512", 4096, 784, 512, False), ("392x392x4096 (A^T)", 392, 392, 4096, True)]
+          ("4096x784x512", 4096, 784, 512, False), ("392x392x4096 (A^T)", 392, 392, 4096, True),
+          ("4096^3", 4096, 4096, 4096, False), ("2048^3", 2048, 2048, 2048, False), ("3072x3072x1024", 3072, 3072, 1024, False)]
 for name, M, N, K, at in shapes:
     torch.manual_seed(3)
     if at:
