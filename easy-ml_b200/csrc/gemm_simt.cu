@@ -429,7 +429,9 @@ gemm_skinny_rows_kernel(const T* __restrict__ A, const T* __restrict__ B, T* C, 
     }
     const int steps = K / (32 * VEC);
     const int64_t groups = (M + SKR_ROWS - 1) / SKR_ROWS;
-    for (int64_t grp = (int64_t)blockIdx.x * SK_WARPS + warp; grp < groups; grp += (int64_t)gridDim.x * SK_WARPS) {
+    // groups go round the BLOCKS first: when there are fewer groups than warps (8192 rows: 2048 groups, 2368 warps) every
+    // block then has the same number of busy warps, instead of 256 full blocks and 40 idle ones on 148 SMs
+    for (int64_t grp = (int64_t)warp * gridDim.x + blockIdx.x; grp < groups; grp += (int64_t)gridDim.x * SK_WARPS) {
         const int64_t m0 = grp * SKR_ROWS;
         T acc[SKR_ROWS][N];
 #pragma unroll
@@ -481,7 +483,8 @@ gemm_skinny_rows_kernel(const T* __restrict__ A, const T* __restrict__ B, T* C, 
 template <class T, int N>
 int launch_skinny_rows(const T* A, const T* B, T* C, int64_t M, int64_t K, int64_t lda, Strides3 sC, bool accumulate,
                        cudaStream_t stream) {
-    int64_t blocks = ((M + SKR_ROWS - 1) / SKR_ROWS + SK_WARPS - 1) / SK_WARPS;
+    const int64_t groups = (M + SKR_ROWS - 1) / SKR_ROWS;
+    int64_t blocks = (groups + SK_WARPS - 1) / SK_WARPS;
     constexpr int VEC = 16 / sizeof(T);
     const size_t staged_bytes = (size_t)(K / VEC) * (N | 1) * 16;
     static const bool staging = [] {
@@ -489,7 +492,8 @@ int launch_skinny_rows(const T* A, const T* B, T* C, int64_t M, int64_t K, int64
         return !(e && e[0] == '0');
     }();
     if (staging && staged_bytes <= (size_t(48) << 10) && blocks >= 8) {
-        if (blocks > 148 * 2) blocks = 148 * 2;  // persistent: B is staged once per block
+        // persistent: B is staged once per block; two blocks per SM once there is a group for every SM
+        blocks = groups >= 148 * 2 ? 148 * 2 : (groups >= 148 ? 148 : groups);
         launch_k(gemm_skinny_rows_kernel<T, N, true>, dim3((unsigned)blocks), dim3(SK_THREADS), staged_bytes, stream, A, B, C, M, (int)K,
                  lda, sC, accumulate ? 1 : 0);
         count_launch();
