@@ -406,6 +406,44 @@ template int launch_gemm_skinny_tn<double>(DeviceCtx*, const double*, const doub
 namespace {
 constexpr int SKR_ROWS = 4;
 
+// Sums V values per lane over the 32 lanes of a warp in the fixed tree of the xor butterfly (partners 16, 8, 4, 2, 1 apart,
+// in that order), but with a fraction of its shuffles: while the count is even, a lane KEEPS half of its values and
+// sends the other half to its partner (which keeps those), so a level costs V / 2 shuffles instead of V and the count
+// halves; the levels that are left run the plain butterfly on what remains.  Every total is the same sequence of adds
+// over the same partial sums as  v += shfl_xor(v, 16); v += shfl_xor(v, 8); ...  (an add's two operands may be
+// exchanged between the partners: IEEE addition is commutative), so the bits are those of the plain butterfly.
+// The shuffle unit moves one warp instruction per clock and SM; the plain butterfly of the skinny product's 4 x N sums
+// (200 shuffles per warp for N = 10) took 3 of the kernel's 7 us (clock64 timeline), this form needs 45.
+// On return the lane holds `count` totals, of the values base .. base + count - 1, and `writer` says whether this lane is
+// the one (of those that hold the same totals) that stores them.
+template <class T, int V, int OFF>
+struct WarpTree {
+    static __device__ __forceinline__ void run(T (&v)[V], int lane, int& base, bool& writer, T* out, int& count) {
+        if constexpr (OFF == 0) {
+#pragma unroll
+            for (int i = 0; i < V; i++) out[i] = v[i];
+            count = V;
+        } else if constexpr (V % 2 == 0) {
+            const bool up = (lane & OFF) != 0;
+            T w[V / 2];
+#pragma unroll
+            for (int i = 0; i < V / 2; i++) {
+                const T keep = up ? v[i + V / 2] : v[i];
+                const T send = up ? v[i] : v[i + V / 2];
+                w[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
+            }
+            if (up) base += V / 2;
+            WarpTree<T, V / 2, OFF / 2>::run(w, lane, base, writer, out, count);
+        } else {
+#pragma unroll
+            for (int i = 0; i < V; i++) v[i] += __shfl_xor_sync(0xffffffffu, v[i], OFF);
+            writer = writer && (lane & OFF) == 0;
+            WarpTree<T, V, OFF / 2>::run(v, lane, base, writer, out, count);
+        }
+    }
+};
+
+
 // STAGED: B is first copied into shared memory.  A lane's slice of B (VEC rows = N 16-byte units) starts N units after its
 // neighbour's: read from global memory that is 32 different lines per load instruction (N x 32 wavefronts of the L1 per
 // step -- what bounded the first version: 9.7 us for H[8192 x 512] * W2[512 x 10]); in shared memory, with every slice
@@ -465,18 +503,28 @@ gemm_skinny_rows_kernel(const T* __restrict__ A, const T* __restrict__ B, T* C, 
                     for (int n = 0; n < N; n++) acc[r][n] = fma(ae[v], be[v * N + n], acc[r][n]);
             }
         }
+        {
+            constexpr int V = SKR_ROWS * N;
+            T flat[V], tot[V];
 #pragma unroll
-        for (int r = 0; r < SKR_ROWS; r++)
+            for (int r = 0; r < SKR_ROWS; r++)
 #pragma unroll
-            for (int n = 0; n < N; n++) {
-                T v = acc[r][n];
+                for (int n = 0; n < N; n++) flat[r * N + n] = acc[r][n];
+            int base = 0, count = 0;
+            bool writer = true;
+            WarpTree<T, V, 16>::run(flat, lane, base, writer, tot, count);
+            if (writer) {
 #pragma unroll
-                for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-                if (lane == 0 && m0 + r < M) {
-                    T* p = C + (m0 + r) * sC.r + n * sC.c;
-                    *p = accumulate ? *p + v : v;
+                for (int i = 0; i < V; i++) {
+                    if (i >= count) break;
+                    const int e = base + i, r = e / N, n = e % N;
+                    if (m0 + r < M) {
+                        T* p = C + (m0 + r) * sC.r + n * sC.c;
+                        *p = accumulate ? *p + tot[i] : tot[i];
+                    }
                 }
             }
+        }
     }
 }
 
