@@ -10,6 +10,8 @@
 #include <mutex>
 #include <utility>
 
+#include <cstdlib>
+
 #include "common.h"
 #include "ew_rules.cuh"
 #include "tf32_split.cuh"
@@ -486,7 +488,14 @@ int launch_sgd_batch(const SgdBatch& b, cudaStream_t stream) {
     int64_t most = 0;
     for (int y = 0; y < b.count; y++) most = b.n[y] > most ? b.n[y] : most;
     int64_t blocks = (most + EW_THREADS - 1) / EW_THREADS;
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    // few, longer-lived CTAs: every CTA of a job that writes a small-part plane ends with an atomic on the job's ticket
+    // word, and same-address atomics are served one after the other (EML_SGD_BLOCKS overrides: measurement aid)
+    static const int64_t cap = [] {
+        const char* e = getenv("EML_SGD_BLOCKS");
+        const int v = e ? atoi(e) : 0;
+        return (int64_t)(v > 0 ? v : 148 * 2);
+    }();
+    if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     launch_k(sgd_batch_kernel<T>, dim3((unsigned)blocks, (unsigned)(b.count + (b.copy_bytes ? 1 : 0))), dim3(EW_THREADS), 0, stream, b);
     count_launch();
