@@ -487,11 +487,6 @@ tf32x3_pair_kernel(const __grid_constant__ Maps maps, float* __restrict__ C, int
     if (threadIdx.x == 0) TS(0);
     pdl_wait();  // the predecessor has completed and flushed: global memory may be read from here on
     if (threadIdx.x == 0) TS(1);
-    if (threadIdx.x == 32 && rep.A) {
-        repair_seen = ((rep.flag_a && *rep.flag_a) || (rep.flag_b && *rep.flag_b) || *rep.stream_flag) ? 1u : 0u;
-        __threadfence();
-        if (atomicInc(rep.ticket, gridDim.x - 1) == gridDim.x - 1) *rep.stream_flag = 0u;
-    }
     tc_fence_before();
     cluster_sync_all();  // barriers of BOTH CTAs are initialised before any remote arrive / multicast commit
     tc_fence_after();
@@ -584,6 +579,17 @@ tf32x3_pair_kernel(const __grid_constant__ Maps maps, float* __restrict__ C, int
         // ---------------- epilogue (both CTAs) ----------------
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(EPILOGUE_REGS));
         const int q = warp & 3, half = (warp - 4) >> 2;  // TMEM lane quarter, 128-column half
+        if (rep.A) {
+            // the operands' "non-finite input seen" words and this CTA's ticket, read while the first MMAs run (three
+            // dependent global loads and an atomic: ~0.8 us that used to sit in front of the cluster's first barrier);
+            // the epilogue warps meet on a barrier of their own before anybody looks at the result
+            if (threadIdx.x == 128) {
+                repair_seen = ((rep.flag_a && *rep.flag_a) || (rep.flag_b && *rep.flag_b) || *rep.stream_flag) ? 1u : 0u;
+                __threadfence();
+                if (atomicInc(rep.ticket, gridDim.x - 1) == gridDim.x - 1) *rep.stream_flag = 0u;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+        }
         int it = 0;
         for (int w = cluster; w < work_items; w += clusters) {
             const Work wk = decode(w, tiles_m, tiles_n, splits);
