@@ -160,6 +160,45 @@ int launch_gemm_simt(const T* A, const T* B, T* C, int64_t batch, int64_t M, int
 namespace {
 constexpr int SK_NMAX = 16, SK_WARPS = 8, SK_THREADS = SK_WARPS * 32;
 
+// Sums V values per lane over the 32 lanes of a warp in the fixed tree of the xor butterfly (partners 16, 8, 4, 2, 1 apart,
+// in that order), but with a fraction of its shuffles: while the count is even, a lane KEEPS half of its values and
+// sends the other half to its partner (which keeps those), so a level costs V / 2 shuffles instead of V and the count
+// halves; the levels that are left run the plain butterfly on what remains.  Every total is the same sequence of adds
+// over the same partial sums as  v += shfl_xor(v, 16); v += shfl_xor(v, 8); ...  (an add's two operands may be
+// exchanged between the partners: IEEE addition is commutative), so the bits are those of the plain butterfly.
+// The shuffle unit moves one warp instruction per clock and SM; the plain butterfly of the skinny product's 4 x N sums
+// (200 shuffles per warp for N = 10) took 3 of the kernel's 7 us (clock64 timeline), this form needs 45.
+// On return the lane holds `count` totals, of the values base .. base + count - 1, and `writer` says whether this lane is
+// the one (of those that hold the same totals) that stores them.
+template <class T, int V, int OFF>
+struct WarpTree {
+    static __device__ __forceinline__ void run(T (&v)[V], int lane, int& base, bool& writer, T* out, int& count) {
+        if constexpr (OFF == 0) {
+#pragma unroll
+            for (int i = 0; i < V; i++) out[i] = v[i];
+            count = V;
+        } else if constexpr (V % 2 == 0) {
+            const bool up = (lane & OFF) != 0;
+            T w[V / 2];
+#pragma unroll
+            for (int i = 0; i < V / 2; i++) {
+                const T keep = up ? v[i + V / 2] : v[i];
+                const T send = up ? v[i] : v[i + V / 2];
+                w[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
+            }
+            if (up) base += V / 2;
+            WarpTree<T, V / 2, OFF / 2>::run(w, lane, base, writer, out, count);
+        } else {
+#pragma unroll
+            for (int i = 0; i < V; i++) v[i] += __shfl_xor_sync(0xffffffffu, v[i], OFF);
+            writer = writer && (lane & OFF) == 0;
+            WarpTree<T, V, OFF / 2>::run(v, lane, base, writer, out, count);
+        }
+    }
+};
+
+
+
 template <class T>
 __global__ void __launch_bounds__(SK_THREADS)
 gemm_skinny_kernel(const T* __restrict__ A, const T* __restrict__ B, T* C, int64_t batch, int64_t M, int N, int64_t K,
@@ -220,14 +259,22 @@ gemm_skinny_kernel(const T* __restrict__ A, const T* __restrict__ B, T* C, int64
                     }
             }
         }
+        {
+            // (every lane of the warp takes part, also for a row past the end: its sums are zeros and nothing is stored)
+            T tot[SK_NMAX];
+            int base = 0, count = 0;
+            bool writer = true;
+            WarpTree<T, SK_NMAX, 16>::run(acc, lane, base, writer, tot, count);
+            if (writer && m < M) {
 #pragma unroll
-        for (int n = 0; n < SK_NMAX; n++) {
-            T v = acc[n];
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-            if (lane == 0 && n < N && m < M) {
-                T* p = C + b * sC.b + m * sC.r + n * sC.c;
-                *p = accumulate ? *p + v : v;
+                for (int i = 0; i < SK_NMAX; i++) {
+                    if (i >= count) break;
+                    const int n = base + i;
+                    if (n < N) {
+                        T* p = C + b * sC.b + m * sC.r + n * sC.c;
+                        *p = accumulate ? *p + tot[i] : tot[i];
+                    }
+                }
             }
         }
     }
@@ -405,44 +452,6 @@ template int launch_gemm_skinny_tn<double>(DeviceCtx*, const double*, const doub
 // accumulators and B's slice are registers.  One fixed shuffle tree per output; deterministic.
 namespace {
 constexpr int SKR_ROWS = 4;
-
-// Sums V values per lane over the 32 lanes of a warp in the fixed tree of the xor butterfly (partners 16, 8, 4, 2, 1 apart,
-// in that order), but with a fraction of its shuffles: while the count is even, a lane KEEPS half of its values and
-// sends the other half to its partner (which keeps those), so a level costs V / 2 shuffles instead of V and the count
-// halves; the levels that are left run the plain butterfly on what remains.  Every total is the same sequence of adds
-// over the same partial sums as  v += shfl_xor(v, 16); v += shfl_xor(v, 8); ...  (an add's two operands may be
-// exchanged between the partners: IEEE addition is commutative), so the bits are those of the plain butterfly.
-// The shuffle unit moves one warp instruction per clock and SM; the plain butterfly of the skinny product's 4 x N sums
-// (200 shuffles per warp for N = 10) took 3 of the kernel's 7 us (clock64 timeline), this form needs 45.
-// On return the lane holds `count` totals, of the values base .. base + count - 1, and `writer` says whether this lane is
-// the one (of those that hold the same totals) that stores them.
-template <class T, int V, int OFF>
-struct WarpTree {
-    static __device__ __forceinline__ void run(T (&v)[V], int lane, int& base, bool& writer, T* out, int& count) {
-        if constexpr (OFF == 0) {
-#pragma unroll
-            for (int i = 0; i < V; i++) out[i] = v[i];
-            count = V;
-        } else if constexpr (V % 2 == 0) {
-            const bool up = (lane & OFF) != 0;
-            T w[V / 2];
-#pragma unroll
-            for (int i = 0; i < V / 2; i++) {
-                const T keep = up ? v[i + V / 2] : v[i];
-                const T send = up ? v[i] : v[i + V / 2];
-                w[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
-            }
-            if (up) base += V / 2;
-            WarpTree<T, V / 2, OFF / 2>::run(w, lane, base, writer, out, count);
-        } else {
-#pragma unroll
-            for (int i = 0; i < V; i++) v[i] += __shfl_xor_sync(0xffffffffu, v[i], OFF);
-            writer = writer && (lane & OFF) == 0;
-            WarpTree<T, V, OFF / 2>::run(v, lane, base, writer, out, count);
-        }
-    }
-};
-
 
 // STAGED: B is first copied into shared memory.  A lane's slice of B (VEC rows = N 16-byte units) starts N units after its
 // neighbour's: read from global memory that is 32 different lines per load instruction (N x 32 wavefronts of the L1 per
