@@ -366,13 +366,27 @@ gemm_tn_wide_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restr
         }
         __syncthreads();
         const T* a = A + k0 * a_k_stride + threadIdx.x;
-        for (int k = 0; k < kc; k += 8) {  // eight k rows in flight per thread; rows past the chunk read as zero
+        // eight k rows in flight per thread (rows past the chunk read as zero), and the next eight are requested before
+        // the fma of the current ones: the chunk's memory latency overlaps its arithmetic
+        T nx[8][MT];
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+#pragma unroll
+            for (int i = 0; i < MT; i++)
+                nx[j][i] = (j < kc && threadIdx.x + i * TN_THREADS < M) ? a[j * a_k_stride + i * TN_THREADS] : T(0);
+        for (int k = 0; k < kc; k += 8) {
             T av[8][MT];
 #pragma unroll
             for (int j = 0; j < 8; j++)
 #pragma unroll
-                for (int i = 0; i < MT; i++)
-                    av[j][i] = (k + j < kc && threadIdx.x + i * TN_THREADS < M) ? a[(k + j) * a_k_stride + i * TN_THREADS] : T(0);
+                for (int i = 0; i < MT; i++) av[j][i] = nx[j][i];
+            if (k + 8 < kc) {
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+#pragma unroll
+                    for (int i = 0; i < MT; i++)
+                        nx[j][i] = (k + 8 + j < kc && threadIdx.x + i * TN_THREADS < M) ? a[(k + 8 + j) * a_k_stride + i * TN_THREADS] : T(0);
+            }
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 if (k + j >= kc) break;
